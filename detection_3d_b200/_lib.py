@@ -1,0 +1,77 @@
+"""ctypes binding of the C-ABI library (include/scn_b200.h).
+
+The CUDA extension is the product: if libscn_b200.so is missing or no CUDA device is present the
+import of any operator fails loudly -- there is no CPU or PyTorch fallback.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libscn_b200.so")
+
+_lib = None
+L3 = C.c_long * 3
+
+# every symbol include/scn_b200.h declares: (restype, argtypes)
+_vp, _l, _i, _f, _d = C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_double
+_pl, _pi, _pd = C.POINTER(C.c_long), C.POINTER(C.c_int), C.POINTER(C.c_double)
+SYMBOLS = {
+    "scn_last_error": (C.c_char_p, []),
+    "scn_version": (_i, []),
+    "scn_n_rulebook_bits": (_i, []),
+    "scn_metadata_create": (_i, [C.POINTER(_vp), _vp]),
+    "scn_metadata_destroy": (None, [_vp]),
+    "scn_input_layer_build": (_i, [_vp, L3, _vp, _i, _l, _i, _i, _i, _pl, _pi]),
+    "scn_input_layer_forward": (_i, [_vp, _vp, _vp, _i]),
+    "scn_input_layer_backward": (_i, [_vp, _vp, _vp, _i]),
+    "scn_get_nactive": (_i, [_vp, L3, _pl]),
+    "scn_get_spatial_locations": (_i, [_vp, L3, _vp, _i]),
+    "scn_submanifold_prepare": (_i, [_vp, L3, L3, _pl]),
+    "scn_convolution_prepare": (_i, [_vp, L3, L3, L3, L3, _pl, _pl]),
+    "scn_rulebook_info": (_i, [_vp, _i, L3, L3, L3, _pi, _pl]),
+    "scn_rulebook_copy": (_i, [_vp, _i, L3, L3, L3, _i, _vp]),
+    "scn_iteration_order": (_i, [_vp, L3, _vp]),
+    "scn_submanifold_convolution_forward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd]),
+    "scn_convolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd]),
+    "scn_deconvolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd]),
+    "scn_submanifold_convolution_backward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "scn_convolution_backward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "scn_deconvolution_backward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
+    "scn_batchnorm_forward": (_i, [_vp, _vp, _l, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _vp]),
+    "scn_batchnorm_backward": (_i, [_vp, _vp, _vp, _vp, _l, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
+    "scn_add_features": (_i, [_vp, _vp, _vp, _l, _vp]),
+    "scn_set_math_mode": (_i, [_i]),
+    "scn_get_math_mode": (_i, []),
+    "scn_kernel_launch_count": (_l, []),
+}
+
+
+def lib():
+    """Load libscn_b200.so (built by detection_3d_b200/csrc/Makefile or __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
+                "detection_3d_b200 has no CPU fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(handle, name)  # AttributeError = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        raise RuntimeError("scn_b200: " + lib().scn_last_error().decode("utf-8", "replace"))
+
+
+def l3(v):
+    if hasattr(v, "tolist"):
+        v = v.tolist()
+    v = [int(x) for x in v]
+    if len(v) != 3:
+        raise RuntimeError("this build is specialised for dimension 3 (Metadata_3)")
+    return L3(*v)

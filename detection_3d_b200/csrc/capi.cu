@@ -1,0 +1,276 @@
+// extern "C" boundary (include/scn_b200.h).  No torch types: raw device pointers, sizes, a stream.
+#include "../../include/scn_b200.h"
+#include "metadata.cuh"
+#include <algorithm>
+
+namespace scn {
+long g_launches = 0;
+const char *last_error();
+int launch_conv_plan_simt(const float *in, float *out, const float *W, const int *nbr, const int *outRow, int nOut, int K, int Cin, int Cout,
+                          const float *bias, cudaStream_t s);
+int launch_conv_list_simt(const float *in, float *out, const float *W, const int2 *pairs, const int *d_off, const int *offHost, int K, int Cin,
+                          int Cout, int srcIsY, int singlePass, cudaStream_t s);
+int bn_forward(const float *x, float *y, long n, int C, float *saveMean, float *saveInvStd, float *runningMean, float *runningVar,
+               const float *weight, const float *bias, float eps, float momentum, int mode, float leak, void *workspace, cudaStream_t s);
+int bn_backward(const float *x, float *dx, const float *y, float *dy, long n, int C, const float *saveMean, const float *saveInvStd,
+                const float *weight, float *dWeight, float *dBias, float leak, void *workspace, cudaStream_t s);
+int input_forward(const float *in, float *out, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
+int input_backward(float *din, const float *dout, long nIn, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
+int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s);
+int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
+                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s);
+int tc_available();
+int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, int nOut, int K, int Cin, int Cout,
+                        const float *bias, int mathMode, cudaStream_t s);
+static int g_math_mode = 0;
+} // namespace scn
+
+struct scn_metadata {
+  scn::Metadata md;
+};
+
+using scn::Metadata;
+
+#define M_OR_FAIL(m)                               \
+  if (!(m)) {                                      \
+    scn::set_error("null scn_metadata handle");    \
+    return -3;                                     \
+  }
+
+
+extern "C" {
+
+const char *scn_last_error(void) { return scn::last_error(); }
+int scn_version(void) { return 1; }
+int scn_n_rulebook_bits(void) { return 32; }
+long scn_kernel_launch_count(void) { return scn::g_launches; }
+int scn_set_math_mode(int mode) {
+  if (mode < 0 || mode > 2) { scn::set_error("math mode must be 0 (fp32), 1 (tf32) or 2 (bf16)"); return -2; }
+  scn::g_math_mode = mode;
+  return 0;
+}
+int scn_get_math_mode(void) { return scn::g_math_mode; }
+
+int scn_metadata_create(scn_metadata **out, void *stream) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    scn::set_error("no CUDA device: this library has no CPU fallback");
+    return -1;
+  }
+  scn_metadata *m = new scn_metadata();
+  m->md.stream = static_cast<cudaStream_t>(stream);
+  int r = m->md.init();
+  if (r) { delete m; return r; }
+  *out = m;
+  return 0;
+}
+void scn_metadata_destroy(scn_metadata *m) { delete m; }
+
+int scn_input_layer_build(scn_metadata *m, const long sz[3], const long *coords, int on_device, long nrows, int ncols,
+                          int batch_size, int mode, long *n_active, int *max_active) {
+  M_OR_FAIL(m);
+  SCN_TRY(m->md.input_layer(sz, coords, on_device, nrows, ncols, batch_size, mode));
+  if (n_active) *n_active = m->md.input.nOut;
+  if (max_active) *max_active = m->md.input.maxActive;
+  return 0;
+}
+int scn_input_layer_forward(scn_metadata *m, const float *in, float *out, int C) {
+  M_OR_FAIL(m);
+  auto &I = m->md.input;
+  SCN_CHECK(I.valid, "input layer not built");
+  if (I.mode == 0) {
+    SCN_CUDA(cudaMemcpyAsync(out, in, (size_t)I.nOut * C * 4, cudaMemcpyDeviceToDevice, m->md.stream));
+    return 0;
+  }
+  return scn::input_forward(in, out, I.nOut, I.maxActive, C, I.tab, I.mode == 4, m->md.stream);
+}
+int scn_input_layer_backward(scn_metadata *m, float *din, const float *dout, int C) {
+  M_OR_FAIL(m);
+  auto &I = m->md.input;
+  SCN_CHECK(I.valid, "input layer not built");
+  if (I.mode == 0) {
+    SCN_CUDA(cudaMemcpyAsync(din, dout, (size_t)I.nOut * C * 4, cudaMemcpyDeviceToDevice, m->md.stream));
+    return 0;
+  }
+  return scn::input_backward(din, dout, I.nIn, I.nOut, I.maxActive, C, I.tab, I.mode == 4, m->md.stream);
+}
+
+int scn_get_nactive(scn_metadata *m, const long sz[3], long *n) {
+  M_OR_FAIL(m);
+  scn::Grid *g = m->md.find_grid(sz);
+  *n = g ? g->n : 0; // Metadata::getNActive default-constructs 0 for unknown sizes
+  return 0;
+}
+int scn_get_spatial_locations(scn_metadata *m, const long sz[3], long *out, int on_device) {
+  M_OR_FAIL(m);
+  return m->md.spatial_locations(sz, out, on_device);
+}
+int scn_submanifold_prepare(scn_metadata *m, const long sz[3], const long f[3], long *n_rules) {
+  M_OR_FAIL(m);
+  scn::SubmEntry *e;
+  SCN_TRY(m->md.get_submanifold(sz, f, &e));
+  if (n_rules) *n_rules = e->rb.total;
+  return 0;
+}
+int scn_convolution_prepare(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long s[3], long *n_out,
+                            long *n_rules) {
+  M_OR_FAIL(m);
+  scn::ConvEntry *e;
+  SCN_TRY(m->md.get_conv(inS, outS, f, s, &e));
+  SCN_CHECK(e->out == (scn::P3{outS[0], outS[1], outS[2]}), "this (input size, filter, stride) rulebook was built for another output size");
+  if (n_out) *n_out = m->md.find_grid(outS)->n;
+  if (n_rules) *n_rules = e->rb.total;
+  return 0;
+}
+
+static int find_rb(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], scn::RuleBookDev **rb) {
+  if (kind == 1) {
+    auto it = m->md.subm.find(scn::SubmKey{scn::P3{a[0], a[1], a[2]}, scn::P3{b[0], b[1], b[2]}});
+    SCN_CHECK(it != m->md.subm.end(), "submanifold rulebook not built");
+    *rb = &it->second.rb;
+  } else {
+    auto it = m->md.conv.find(scn::ConvKey{scn::P3{a[0], a[1], a[2]}, scn::P3{b[0], b[1], b[2]}, scn::P3{c[0], c[1], c[2]}});
+    SCN_CHECK(it != m->md.conv.end(), "convolution rulebook not built");
+    *rb = &it->second.rb;
+  }
+  return 0;
+}
+int scn_rulebook_info(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], int *n_lists, long *list_len) {
+  M_OR_FAIL(m);
+  if (kind == 0) {
+    auto &I = m->md.input;
+    SCN_CHECK(I.valid, "input layer not built");
+    *n_lists = I.mode == 0 ? 1 : 2;
+    if (list_len) { list_len[0] = 4; if (I.mode) list_len[1] = (long)I.nOut * (1 + I.maxActive); }
+    return 0;
+  }
+  scn::RuleBookDev *rb;
+  SCN_TRY(find_rb(m, kind, a, b, c, &rb));
+  *n_lists = rb->nLists;
+  if (list_len) for (int i = 0; i < rb->nLists; i++) list_len[i] = 2l * (rb->off[i + 1] - rb->off[i]);
+  return 0;
+}
+int scn_rulebook_copy(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], int list, int *dst) {
+  M_OR_FAIL(m);
+  cudaStream_t s = m->md.stream;
+  if (kind == 0) {
+    auto &I = m->md.input;
+    SCN_CHECK(I.valid, "input layer not built");
+    if (list == 0) { dst[0] = I.mode; dst[1] = I.maxActive; dst[2] = I.nIn; dst[3] = I.nOut; return 0; }
+    SCN_CHECK(I.mode != 0 && list == 1, "list index");
+    SCN_CUDA(cudaMemcpyAsync(dst, I.tab, (size_t)I.nOut * (1 + I.maxActive) * 4, cudaMemcpyDeviceToHost, s));
+    SCN_CUDA(cudaStreamSynchronize(s));
+    return 0;
+  }
+  scn::RuleBookDev *rb;
+  SCN_TRY(find_rb(m, kind, a, b, c, &rb));
+  SCN_CHECK(list >= 0 && list < rb->nLists, "list index");
+  long n = rb->off[list + 1] - rb->off[list];
+  if (n) {
+    SCN_CUDA(cudaMemcpyAsync(dst, rb->pairs + rb->off[list], n * 8, cudaMemcpyDeviceToHost, s));
+    SCN_CUDA(cudaStreamSynchronize(s));
+  }
+  return 0;
+}
+int scn_iteration_order(scn_metadata *m, const long sz[3], int *dst) {
+  M_OR_FAIL(m);
+  scn::Grid *g = m->md.find_grid(sz);
+  SCN_CHECK(g, "no active sites recorded for this spatial size");
+  SCN_TRY(m->md.ensure_rank(*g));
+  if (g->n) {
+    SCN_CUDA(cudaMemcpyAsync(dst, g->rank2id, (size_t)g->n * 4, cudaMemcpyDeviceToHost, m->md.stream));
+    SCN_CUDA(cudaStreamSynchronize(m->md.stream));
+  }
+  return 0;
+}
+
+static int run_plan(Metadata &M, const scn::NbrPlan &plan, const float *in, float *out, const float *w, const float *bias, int Cin, int Cout) {
+  if (scn::g_math_mode != 0 && scn::tc_available() && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32 && Cout <= 256)
+    return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.stream);
+  return scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.stream);
+}
+
+int scn_submanifold_convolution_forward(scn_metadata *m, const long sz[3], const long f[3], const float *in, float *out, const float *w,
+                                        const float *bias, int Cin, int Cout, double *macs) {
+  M_OR_FAIL(m);
+  scn::SubmEntry *e;
+  SCN_TRY(m->md.get_submanifold(sz, f, &e));
+  if (macs) *macs = (double)e->rb.total * Cin * Cout;
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout);
+}
+int scn_convolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
+                            float *out, const float *w, const float *bias, int Cin, int Cout, double *macs) {
+  M_OR_FAIL(m);
+  scn::ConvEntry *e;
+  SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
+  if (macs) *macs = (double)e->rb.total * Cin * Cout;
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout);
+}
+__global__ void k_fill_rows_bias(float *out, long n, int C, const float *bias) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n * C; i += (long)gridDim.x * blockDim.x) out[i] = bias ? bias[i % C] : 0.f;
+}
+int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
+                              float *out, const float *w, const float *bias, int Cin, int Cout, double *macs) {
+  M_OR_FAIL(m);
+  // CPU/Deconvolution.cpp:15-16: the rulebook of the convolution outS -> inS
+  scn::ConvEntry *e;
+  SCN_TRY(m->md.get_conv(outS, inS, f, st, &e));
+  if (macs) *macs = (double)e->rb.total * Cin * Cout;
+  scn::Grid *gf = m->md.find_grid(outS);
+  SCN_CHECK(gf, "output grid");
+  cudaStream_t s = m->md.stream;
+  // every fine row with a parent is written exactly once when each input site has one output cell
+  bool single = e->rb.total == gf->n && !bias;
+  if (!single && gf->n) k_fill_rows_bias<<<scn::stream_grid((long)gf->n * Cout, 256), 256, 0, scn::LS(s)>>>(out, gf->n, Cout, bias);
+  return scn::launch_conv_list_simt(in, out, w, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, Cin, Cout, /*srcIsY=*/1, single ? 1 : 0, s);
+}
+
+int scn_submanifold_convolution_backward(scn_metadata *m, const long sz[3], const long f[3], const float *in, float *d_in, const float *d_out,
+                                         const float *w, float *dw, float *d_bias, int Cin, int Cout) {
+  M_OR_FAIL(m);
+  scn::SubmEntry *e;
+  SCN_TRY(m->md.get_submanifold(sz, f, &e));
+  scn::Grid *g = m->md.find_grid(sz);
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.stream);
+}
+int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
+                             float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
+  M_OR_FAIL(m);
+  scn::ConvEntry *e;
+  SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, m->md.find_grid(inS)->n,
+                                 m->md.find_grid(outS)->n, Cin, Cout, 0, m->md.stream);
+}
+int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
+                               float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
+  M_OR_FAIL(m);
+  scn::ConvEntry *e;
+  SCN_TRY(m->md.get_conv(outS, inS, f, st, &e));
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, m->md.find_grid(inS)->n,
+                                 m->md.find_grid(outS)->n, Cin, Cout, 1, m->md.stream);
+}
+
+int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *save_mean, float *save_invstd, float *running_mean,
+                          float *running_var, const float *weight, const float *bias, float eps, float momentum, int mode, float leak,
+                          void *stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SCN_CHECK(mode >= 0 && mode <= 2, "mode");
+  void *ws = nullptr;
+  SCN_CUDA(cudaMallocAsync(&ws, (size_t)C * 24 + 64, s));
+  int r = scn::bn_forward(in, out, n, C, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, mode, leak, ws, s);
+  cudaFreeAsync(ws, s);
+  return r;
+}
+int scn_batchnorm_backward(const float *in, float *d_in, const float *out, float *d_out, long n, int C, const float *save_mean,
+                           const float *save_invstd, const float *weight, float *d_weight, float *d_bias, float leak, void *stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  void *ws = nullptr;
+  SCN_CUDA(cudaMallocAsync(&ws, (size_t)C * 24 + 64, s));
+  int r = scn::bn_backward(in, d_in, out, d_out, n, C, save_mean, save_invstd, weight, d_weight, d_bias, leak, ws, s);
+  cudaFreeAsync(ws, s);
+  return r;
+}
+int scn_add_features(const float *a, const float *b, float *out, long n, void *stream) {
+  return scn::add_rows(a, b, out, n, static_cast<cudaStream_t>(stream));
+}
+}

@@ -1,0 +1,148 @@
+// Shared device/host utilities for the B200 sparse-convolution library.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace scn {
+
+// ---------------------------------------------------------------- errors
+void set_error(const std::string &msg);
+#define SCN_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      char b__[512];                                                                     \
+      snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call,             \
+               cudaGetErrorString(e__));                                                 \
+      scn::set_error(b__);                                                               \
+      return -1;                                                                         \
+    }                                                                                    \
+  } while (0)
+#define SCN_CHECK(cond, msg)                                                             \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      char b__[512];                                                                     \
+      snprintf(b__, sizeof b__, "%s:%d check failed: %s (%s)", __FILE__, __LINE__, #cond, msg); \
+      scn::set_error(b__);                                                               \
+      return -2;                                                                         \
+    }                                                                                    \
+  } while (0)
+#define SCN_TRY(expr)                                                                    \
+  do {                                                                                   \
+    int r__ = (expr);                                                                    \
+    if (r__ != 0) return r__;                                                            \
+  } while (0)
+
+// every kernel launch of this library passes its stream through LS(): launch accounting
+extern long g_launches;
+static inline cudaStream_t LS(cudaStream_t s) { ++g_launches; return s; }
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// B200: 148 SMs.  Element-wise / streaming kernels use grid-stride loops over a grid that is
+// a multiple of the SM count.
+constexpr int kSMs = 148;
+static inline int stream_grid(long n, int threads, int per_sm = 8) {
+  long want = (n + threads - 1) / threads;
+  long cap = (long)kSMs * per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+// ---------------------------------------------------------------- single-pass scan
+// Decoupled look-back exclusive scan (int32) with a fused consumer.  One launch:
+//   value_i  = in(i)
+//   out(i, exclusive_prefix_i, value_i)
+//   *total   = sum (optional)
+// `state` must point at zero-initialised memory: [0] tile ticket, then one uint64 status word
+// per tile ((flag << 32) | value, flag 1 = aggregate, 2 = inclusive prefix).
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+static inline size_t scan_state_words(long n) { return 2 + (size_t)((n + kScanTile - 1) / kScanTile); }
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += t;
+  }
+  return v;
+}
+
+template <class InF, class OutF>
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(long n, InF in, OutF out,
+                                                            unsigned long long *state, int *total) {
+  __shared__ int s_warp[kScanThreads / 32];
+  __shared__ int s_tile, s_prefix;
+  unsigned int *ticket = reinterpret_cast<unsigned int *>(state);
+  volatile unsigned long long *status = state + 1;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const long base = (long)tile * kScanTile + (long)tid * kScanItems;
+  int v[kScanItems];
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; j++) {
+    long i = base + j;
+    v[j] = i < n ? in(i) : 0;
+    sum += v[j];
+  }
+  int incl = warp_incl_scan(sum, lane);
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = lane < kScanThreads / 32 ? s_warp[lane] : 0;
+    int wi = warp_incl_scan(w, lane);
+    if (lane < kScanThreads / 32) s_warp[lane] = wi - w; // exclusive prefix of each warp
+    const int tile_sum = __shfl_sync(0xffffffffu, wi, kScanThreads / 32 - 1);
+    // publish aggregate, then look back
+    int prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) status[0] = (2ull << 32) | (unsigned int)tile_sum;
+    } else {
+      if (lane == 0) status[tile] = (1ull << 32) | (unsigned int)tile_sum;
+      int look = tile - 1;
+      while (true) {
+        int idx = look - lane;
+        unsigned long long s = 0;
+        if (idx >= 0) {
+          do { s = status[idx]; } while ((s >> 32) == 0);
+        } else {
+          s = (2ull << 32); // virtual tile before 0: inclusive prefix 0
+        }
+        const unsigned flag = (unsigned)(s >> 32);
+        const int val = (int)(unsigned)s;
+        const unsigned incl_mask = __ballot_sync(0xffffffffu, flag == 2);
+        // lanes closer than the first inclusive-prefix lane contribute aggregates
+        const int first = incl_mask ? __ffs(incl_mask) - 1 : 32;
+        int contrib = (lane <= first) ? val : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        prefix += contrib;
+        if (incl_mask) break;
+        look -= 32;
+      }
+      if (lane == 0) status[tile] = (2ull << 32) | (unsigned int)(prefix + tile_sum);
+    }
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (total && (long)(tile + 1) * kScanTile >= n) *total = prefix + tile_sum;
+    }
+  }
+  __syncthreads();
+  int run = s_prefix + s_warp[wid] + (incl - sum);
+#pragma unroll
+  for (int j = 0; j < kScanItems; j++) {
+    long i = base + j;
+    if (i < n) out(i, run, v[j]);
+    run += v[j];
+  }
+}
+
+} // namespace scn

@@ -1,0 +1,115 @@
+// Backward of the three convolution kinds (fp32 CUDA cores).
+//   dIn  = sum_k scatter( gather(dOut, rules_k.dst) @ W[k]^T )   -> the forward list kernel run on
+//          (dOut, W^T) with the pair columns swapped, lists back to back (a source row occurs at
+//          most once per list, so the read-modify-write is race free, as in the reference).
+//   dW[k] = gather(in, rules_k.src)^T @ gather(dOut, rules_k.dst) -> split over rule chunks, fp32
+//          atomics into dW (replaces dConvolution_KMxKN_backward_dW_A/B, SCN/CUDA/Convolution.cu:249-410).
+// Reference semantics: SCN/CPU/Convolution.cpp:81-115,152-185, SCN/CPU/Deconvolution.cpp:43-77.
+#include "common.cuh"
+
+namespace scn {
+int launch_conv_list_simt(const float *in, float *out, const float *W, const int2 *pairs, const int *d_off, const int *offHost, int K, int Cin,
+                          int Cout, int srcIsY, int singlePass, cudaStream_t s);
+
+__global__ void k_transpose_w(const float *__restrict__ W, float *__restrict__ Wt, int K, int Cin, int Cout) {
+  long n = (long)K * Cin * Cout;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cout);
+    long t = i / Cout;
+    int ci = (int)(t % Cin), k = (int)(t / Cin);
+    Wt[((long)k * Cout + co) * Cin + ci] = W[i];
+  }
+}
+
+constexpr int BM = 64, BN = 64, BK = 16, BPAD = 4;
+__global__ void __launch_bounds__(256) k_dw(const float *__restrict__ in, const float *__restrict__ dOut, float *__restrict__ dW, const int2 *__restrict__ pairs,
+                                            int start, int len, int chunk, int Cin, int Cout, int srcIsY) {
+  __shared__ __align__(16) float A_s[BK][BM + BPAD];
+  __shared__ __align__(16) float B_s[BK][BN];
+  __shared__ int s_src[BK], s_dst[BK];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int ci0 = blockIdx.y * BM, co0 = blockIdx.z * BN;
+  const int i0 = blockIdx.x * chunk, i1 = min(len, i0 + chunk);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  for (int ib = i0; ib < i1; ib += BK) {
+    __syncthreads();
+    if (tid < BK) {
+      int2 pr = make_int2(-1, -1);
+      if (ib + tid < i1) pr = __ldg(pairs + start + ib + tid);
+      s_src[tid] = srcIsY ? pr.y : pr.x;
+      s_dst[tid] = srcIsY ? pr.x : pr.y;
+    }
+    __syncthreads();
+    // 16 rules x 64 channels each side: 1024 floats, 4 per thread
+    {
+      const int kk = tid >> 4, c4 = (tid & 15) * 4;
+      const int sr = s_src[kk], dr = s_dst[kk];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        int ci = ci0 + c4 + j, co = co0 + c4 + j;
+        A_s[kk][c4 + j] = (sr >= 0 && ci < Cin) ? __ldg(in + (long)sr * Cin + ci) : 0.f;
+        B_s[kk][c4 + j] = (dr >= 0 && co < Cout) ? __ldg(dOut + (long)dr * Cout + co) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) a[i] = A_s[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; j++) b[j] = B_s[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int ci = ci0 + ty * 4 + i, co = co0 + tx * 4 + j;
+      if (ci < Cin && co < Cout) atomicAdd(dW + (long)ci * Cout + co, acc[i][j]);
+    }
+}
+__global__ void k_colsum(const float *__restrict__ x, long n, int C, float *__restrict__ out) {
+  int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (long r = blockIdx.x; r < n; r += gridDim.x) s += x[r * C + c];
+  atomicAdd(out + c, s);
+}
+
+int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
+                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s) {
+  SCN_CUDA(cudaMemsetAsync(d_in, 0, (size_t)nInRows * Cin * 4, s));
+  SCN_CUDA(cudaMemsetAsync(dW, 0, (size_t)K * Cin * Cout * 4, s));
+  if (d_bias) {
+    SCN_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)Cout * 4, s));
+    if (nOutRows) k_colsum<<<dim3(kSMs * 2, cdiv(Cout, 128)), 128, 0, LS(s)>>>(d_out, nOutRows, Cout, d_bias);
+  }
+  if (offHost[K] == 0) return 0;
+  float *Wt = nullptr;
+  SCN_CUDA(cudaMallocAsync((void **)&Wt, (size_t)K * Cin * Cout * 4, s));
+  k_transpose_w<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, Wt, K, Cin, Cout);
+  // dIn: rows of d_out gathered by the forward destination column, scattered to the forward source column
+  int r = launch_conv_list_simt(d_out, d_in, Wt, pairs, d_off, offHost, K, Cout, Cin, !srcIsY, /*singlePass=*/0, s);
+  cudaFreeAsync(Wt, s);
+  if (r) return r;
+  for (int L_ = 0; L_ < K; L_++) {
+    int len = offHost[L_ + 1] - offHost[L_];
+    if (!len) continue;
+    int chunk = std::max(256, cdiv(len, kSMs * 4));
+    chunk = (chunk + BK - 1) / BK * BK;
+    dim3 grid(cdiv(len, chunk), cdiv(Cin, BM), cdiv(Cout, BN));
+    k_dw<<<grid, 256, 0, LS(s)>>>(in, d_out, dW + (long)L_ * Cin * Cout, pairs, offHost[L_], len, chunk, Cin, Cout, srcIsY);
+  }
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+} // namespace scn

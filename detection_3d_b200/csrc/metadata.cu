@@ -1,0 +1,796 @@
+// Metadata: GPU construction of active-site grids, the reference row numbering, the reference
+// hash-iteration order (dense_hash_map emulation), rulebooks in the reference's format and the
+// output-stationary execution plans.  See DESIGN.md "Rulebook build".
+#include "metadata.cuh"
+#include <algorithm>
+#include <limits.h>
+#include <string.h>
+
+namespace scn {
+
+static thread_local std::string g_err;
+void set_error(const std::string &m) { g_err = m; }
+const char *last_error() { return g_err.c_str(); }
+
+// ------------------------------------------------------------------ memory
+Metadata::~Metadata() {
+  for (void *p : allocs) cudaFreeAsync(p, stream);
+  if (h_scalars) cudaFreeHost(h_scalars);
+}
+void *Metadata::alloc(size_t bytes) {
+  void *p = nullptr;
+  if (bytes < 256) bytes = 256;
+  if (cudaMallocAsync(&p, bytes, stream) != cudaSuccess) {
+    set_error("cudaMallocAsync failed");
+    return nullptr;
+  }
+  allocs.push_back(p);
+  return p;
+}
+int Metadata::init() {
+  cudaMemPool_t pool;
+  int dev = 0;
+  SCN_CUDA(cudaGetDevice(&dev));
+  SCN_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+  uint64_t thr = UINT64_MAX; // keep freed blocks cached: steady-state forwards never hit the driver
+  SCN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  zpoolWords = 1 << 19; // 4 MiB of scan state
+  zpool = alloc_n<unsigned long long>(zpoolWords);
+  d_scalars = alloc_n<int>(256);
+  d_err = d_scalars + 200;
+  SCN_CHECK(zpool && d_scalars, "alloc");
+  SCN_CUDA(cudaMemsetAsync(zpool, 0, zpoolWords * 8, stream));
+  SCN_CUDA(cudaMemsetAsync(d_scalars, 0, 256 * 4, stream));
+  SCN_CUDA(cudaMallocHost(&h_scalars, 256 * 4));
+  return 0;
+}
+unsigned long long *Metadata::scan_state(long n) {
+  size_t w = scan_state_words(n);
+  if (zpoolUsed + w > zpoolWords) { // start a fresh zeroed pool
+    size_t words = std::max(zpoolWords, w * 2);
+    zpool = alloc_n<unsigned long long>(words);
+    if (!zpool) return nullptr;
+    cudaMemsetAsync(zpool, 0, words * 8, stream);
+    zpoolWords = words;
+    zpoolUsed = 0;
+  }
+  unsigned long long *p = zpool + zpoolUsed;
+  zpoolUsed += w;
+  return p;
+}
+int Metadata::sync_scalars(int count) {
+  SCN_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, count * 4, cudaMemcpyDeviceToHost, stream));
+  SCN_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+Grid *Metadata::find_grid(const long *sz) {
+  auto it = grids.find(P3{sz[0], sz[1], sz[2]});
+  return it == grids.end() || !it->second.built ? nullptr : &it->second;
+}
+
+template <class InF, class OutF>
+static int run_scan(Metadata &M, long n, InF in, OutF out, int *total) {
+  if (n <= 0) {
+    if (total) SCN_CUDA(cudaMemsetAsync(total, 0, 4, M.stream));
+    return 0;
+  }
+  unsigned long long *st = M.scan_state(n);
+  SCN_CHECK(st, "scan state");
+  scan_kernel<<<cdiv(n, kScanTile), kScanThreads, 0, LS(M.stream)>>>(n, in, out, st, total);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static GridView view(const Grid &g) {
+  return GridView{g.dir, g.bmask, g.wbase, g.dd[0], g.dd[1], g.dd[2], g.dirCells, (int)g.sz[0], (int)g.sz[1], (int)g.sz[2]};
+}
+
+// ------------------------------------------------------------------ block structure
+__global__ void k_coords_to_pts(const long *coords, long n, int ncols, int4 *pts, int *maxBatch) {
+  int mb = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long *c = coords + i * ncols;
+    int b = ncols == 4 ? (int)c[3] : 0;
+    pts[i] = make_int4((int)c[0], (int)c[1], (int)c[2], b);
+    mb = max(mb, b);
+  }
+  if (ncols == 4) {
+    for (int d = 16; d > 0; d >>= 1) mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, d));
+    if ((threadIdx.x & 31) == 0 && mb > 0) atomicMax(maxBatch, mb);
+  }
+}
+__device__ __forceinline__ long dir_cell(const int4 &p, int dd1, int dd2, long dirCells) {
+  return (long)p.w * dirCells + ((long)(p.x >> 3) * dd1 + (p.y >> 3)) * dd2 + (p.z >> 3);
+}
+__global__ void k_mark_dir(const int4 *pts, long n, int *dir, int dd1, int dd2, long dirCells, int sz0, int sz1, int sz2, int *err) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int4 p = pts[i];
+    if (p.x < 0) continue; // invalid event
+    if (p.x >= sz0 || (unsigned)p.y >= (unsigned)sz1 || (unsigned)p.z >= (unsigned)sz2) { *err = 2; continue; }
+    dir[dir_cell(p, dd1, dd2, dirCells)] = 1;
+  }
+}
+struct DirIn { const int *dir; __device__ int operator()(long i) const { return dir[i] != 0; } };
+struct DirOut { int *dir; __device__ void operator()(long i, int pre, int v) const { dir[i] = v ? pre : -1; } };
+__global__ void k_zero_words(unsigned long long *w, const int *nblocks) {
+  long n = (long)(*nblocks) * 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) w[i] = 0ull;
+}
+__global__ void k_set_bits(const int4 *pts, long n, const int *dir, unsigned long long *bmask, int dd1, int dd2, long dirCells, int sz0, int sz1, int sz2) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int4 p = pts[i];
+    if (p.x < 0 || p.x >= sz0 || (unsigned)p.y >= (unsigned)sz1 || (unsigned)p.z >= (unsigned)sz2) continue;
+    int blk = dir[dir_cell(p, dd1, dd2, dirCells)];
+    int bit = ((p.x & 7) << 6) | ((p.y & 7) << 3) | (p.z & 7);
+    atomicOr(bmask + (long)blk * 8 + (bit >> 6), 1ull << (bit & 63));
+  }
+}
+struct WordIn {
+  const unsigned long long *bmask; const int *nblocks;
+  __device__ int operator()(long i) const { return i < (long)(*nblocks) * 8 ? __popcll(bmask[i]) : 0; }
+};
+struct WordOut {
+  int *wbase; const int *nblocks;
+  __device__ void operator()(long i, int pre, int) const { if (i < (long)(*nblocks) * 8) wbase[i] = pre; }
+};
+__global__ void k_lookup_pts(GridView g, const int4 *pts, long n, int *outP) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int4 p = pts[i];
+    outP[i] = p.x < 0 ? -1 : grid_lookup(g, p.x, p.y, p.z, p.w);
+  }
+}
+
+// Builds dir / bmask / wbase of `g` from a point list (duplicates and x<0 "invalid" entries
+// allowed); d_nunique receives the number of distinct points; outP[i] = spatial index of pts[i].
+static int build_blocks(Metadata &M, Grid &g, const int4 *pts, long npts, int *outP, int *d_nunique) {
+  for (int d = 0; d < 3; d++) g.dd[d] = (int)((g.sz[d] + 7) / 8);
+  g.dirCells = (long)g.dd[0] * g.dd[1] * g.dd[2];
+  long cells = g.dirCells * g.batch;
+  SCN_CHECK(cells < (1l << 30), "spatial size too large for the block directory");
+  g.dir = M.alloc_n<int>(cells);
+  g.d_nblocks = M.alloc_n<int>(4);
+  g.maxBlocks = std::max(1l, std::min(npts, cells));
+  g.bmask = M.alloc_n<unsigned long long>(g.maxBlocks * 8);
+  g.wbase = M.alloc_n<int>(g.maxBlocks * 8);
+  SCN_CHECK(g.dir && g.bmask && g.wbase && g.d_nblocks, "alloc");
+  cudaStream_t s = M.stream;
+  SCN_CUDA(cudaMemsetAsync(g.dir, 0, cells * 4, s));
+  if (npts > 0) {
+    k_mark_dir<<<stream_grid(npts, 256), 256, 0, LS(s)>>>(pts, npts, g.dir, g.dd[1], g.dd[2], g.dirCells, (int)g.sz[0], (int)g.sz[1], (int)g.sz[2], M.d_err);
+  }
+  SCN_TRY(run_scan(M, cells, DirIn{g.dir}, DirOut{g.dir}, g.d_nblocks));
+  k_zero_words<<<stream_grid(g.maxBlocks * 8, 256), 256, 0, LS(s)>>>(g.bmask, g.d_nblocks);
+  if (npts > 0) {
+    k_set_bits<<<stream_grid(npts, 256), 256, 0, LS(s)>>>(pts, npts, g.dir, g.bmask, g.dd[1], g.dd[2], g.dirCells, (int)g.sz[0], (int)g.sz[1], (int)g.sz[2]);
+  }
+  SCN_TRY(run_scan(M, g.maxBlocks * 8, WordIn{g.bmask, g.d_nblocks}, WordOut{g.wbase, g.d_nblocks}, d_nunique));
+  if (npts > 0 && outP) k_lookup_pts<<<stream_grid(npts, 256), 256, 0, LS(s)>>>(view(g), pts, npts, outP);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ input layer
+__global__ void k_fill_int(int *p, long n, int v) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_first_rows(const int *rowP, long n, int *firstRow, int *lastRow, int *cnt, int *maxCnt) {
+  int mc = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int p = rowP[i];
+    atomicMin(firstRow + p, (int)i);
+    if (lastRow) atomicMax(lastRow + p, (int)i);
+    int c = atomicAdd(cnt + p, 1) + 1;
+    mc = max(mc, c);
+  }
+  for (int d = 16; d > 0; d >>= 1) mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, d));
+  if ((threadIdx.x & 31) == 0 && mc > 0) atomicMax(maxCnt, mc);
+}
+struct FirstIn {
+  const int *rowP, *firstRow;
+  __device__ int operator()(long i) const { return firstRow[rowP[i]] == (int)i; }
+};
+struct FirstOut {
+  const int *rowP; const int4 *pts; int *p2id, *id2p; int4 *coords;
+  __device__ void operator()(long i, int pre, int v) const {
+    if (v) { int p = rowP[i]; p2id[p] = pre; id2p[pre] = p; coords[pre] = pts[i]; }
+  }
+};
+// rules table rows: [count, rows ascending..., 0 padding]  (IOLayersRules.h:111-124)
+__global__ void k_input_rules_fill(const int *rowP, const int *p2id, long n, int *tab, int w) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int id = p2id[rowP[i]];
+    int slot = atomicAdd(tab + (long)id * w, 1);
+    tab[(long)id * w + 1 + slot] = (int)i;
+  }
+}
+__global__ void k_input_rules_sort(int *tab, int nOut, int w) {
+  for (long id = blockIdx.x * (long)blockDim.x + threadIdx.x; id < nOut; id += (long)gridDim.x * blockDim.x) {
+    int *r = tab + id * w;
+    int c = r[0];
+    for (int a = 2; a <= c; a++) { // insertion sort, lists are tiny
+      int v = r[a], b = a - 1;
+      while (b >= 1 && r[b] > v) { r[b + 1] = r[b]; b--; }
+      r[b + 1] = v;
+    }
+  }
+}
+__global__ void k_input_rules_pick(const int *pick, const int *id2p, int nOut, int *tab) {
+  for (long id = blockIdx.x * (long)blockDim.x + threadIdx.x; id < nOut; id += (long)gridDim.x * blockDim.x) {
+    tab[id * 2] = 1;
+    tab[id * 2 + 1] = pick[id2p[id]];
+  }
+}
+__global__ void k_count_batch(const int4 *coords, int n, int *counts) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) atomicAdd(counts + coords[i].w, 1);
+}
+
+// Metadata::inputLayer -> inputLayerRules (SCN/Metadata/Metadata.cpp:405-417, IOLayersRules.h:18-125).
+int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long nrows, int ncols, int batchHint, int mode) {
+  SCN_CHECK(ncols == 3 || ncols == 4, "coords must be N x 3 or N x 4");
+  SCN_CHECK(mode >= 0 && mode <= 4, "mode");
+  SCN_CHECK(nrows < (1l << 26), "too many input rows");
+  P3 key{sz[0], sz[1], sz[2]};
+  SCN_CHECK(grids.find(key) == grids.end() && !input.valid, "input layer already built for this Metadata");
+  Grid &g = grids[key];
+  g.sz = key;
+  cudaStream_t s = stream;
+  const long *dcoords = coords;
+  if (!onDevice && nrows) {
+    long *tmp = alloc_n<long>(nrows * ncols);
+    SCN_CHECK(tmp, "alloc");
+    SCN_CUDA(cudaMemcpyAsync(tmp, coords, nrows * ncols * 8, cudaMemcpyHostToDevice, s));
+    dcoords = tmp;
+  }
+  int4 *pts = alloc_n<int4>(std::max(1l, nrows));
+  SCN_CHECK(pts, "alloc");
+  int *sc = d_scalars; // [0] maxBatch [1] nUnique [2] maxActive [3] nActive
+  SCN_CUDA(cudaMemsetAsync(sc, 0, 64 * 4, s));
+  if (nrows) k_coords_to_pts<<<stream_grid(nrows, 256), 256, 0, LS(s)>>>(dcoords, nrows, ncols, pts, sc);
+  g.batch = std::max(1, batchHint);
+  if (ncols == 4 && nrows) {
+    SCN_TRY(sync_scalars(1));
+    g.batch = std::max(g.batch, h_scalars[0] + 1);
+  }
+  SCN_CHECK(g.batch <= 48, "batch size > 48 not supported");
+  int *rowP = alloc_n<int>(std::max(1l, nrows));
+  SCN_TRY(build_blocks(*this, g, pts, nrows, rowP, sc + 1));
+  long cap = std::max(1l, nrows);
+  g.coords = alloc_n<int4>(cap);
+  g.p2id = alloc_n<int>(cap);
+  g.id2p = alloc_n<int>(cap);
+  int *firstRow = alloc_n<int>(cap), *cnt = alloc_n<int>(cap), *lastRow = mode == 2 ? alloc_n<int>(cap) : nullptr;
+  SCN_CHECK(g.coords && g.p2id && g.id2p && firstRow && cnt, "alloc");
+  SCN_CUDA(cudaMemsetAsync(firstRow, 0x7f, cap * 4, s));
+  SCN_CUDA(cudaMemsetAsync(cnt, 0, cap * 4, s));
+  if (lastRow) SCN_CUDA(cudaMemsetAsync(lastRow, 0xff, cap * 4, s));
+  if (nrows) k_first_rows<<<stream_grid(nrows, 256), 256, 0, LS(s)>>>(rowP, nrows, firstRow, lastRow, cnt, sc + 2);
+  SCN_TRY(run_scan(*this, nrows, FirstIn{rowP, firstRow}, FirstOut{rowP, pts, g.p2id, g.id2p, g.coords}, sc + 3));
+  // per-batch-item counts (only needed when batch > 1)
+  SCN_TRY(sync_scalars(4));
+  g.n = h_scalars[3];
+  int maxActive = h_scalars[2];
+  SCN_CHECK(h_scalars[1] == g.n, "internal: unique count mismatch");
+  g.itemCount.assign(g.batch, 0);
+  g.itemCtr.assign(g.batch, g.batch == 1 ? 0 : -1);
+  if (g.batch == 1) g.itemCount[0] = g.n;
+  else {
+    SCN_CUDA(cudaMemsetAsync(sc + 8, 0, 48 * 4, s));
+    if (g.n) k_count_batch<<<stream_grid(g.n, 256), 256, 0, LS(s)>>>(g.coords, g.n, sc + 8);
+    SCN_TRY(sync_scalars(8 + 48));
+    for (int b = 0; b < g.batch; b++) g.itemCount[b] = h_scalars[8 + b];
+  }
+  g.built = true;
+  // rules
+  input.mode = mode; input.nIn = (int)nrows; input.nOut = g.n; input.valid = true;
+  input.maxActive = (mode == 3 || mode == 4) ? maxActive : 1;
+  if (mode == 0) { input.tab = nullptr; return 0; }
+  int w = 1 + input.maxActive;
+  input.tab = alloc_n<int>(std::max(1l, (long)g.n * w));
+  SCN_CHECK(input.tab, "alloc");
+  if (g.n == 0) return 0;
+  if (mode == 3 || mode == 4) {
+    SCN_CUDA(cudaMemsetAsync(input.tab, 0, (long)g.n * w * 4, s));
+    k_input_rules_fill<<<stream_grid(nrows, 256), 256, 0, LS(s)>>>(rowP, g.p2id, nrows, input.tab, w);
+    if (maxActive > 1) k_input_rules_sort<<<stream_grid(g.n, 256), 256, 0, LS(s)>>>(input.tab, g.n, w);
+  } else {
+    // IOLayersRules.h:100-110: mode 1 keeps the FIRST row of a voxel, mode 2 the LAST
+    k_input_rules_pick<<<stream_grid(g.n, 256), 256, 0, LS(s)>>>(mode == 1 ? firstRow : lastRow, g.id2p, g.n, input.tab);
+  }
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ dense_hash_map order
+// Table entry: [63:38] rank | [37:12] row id | [11:0] probe count.  Lower rank wins a bucket.
+constexpr unsigned long long kEmpty = ~0ull;
+__device__ __forceinline__ unsigned long long pack_entry(unsigned rank, unsigned id, unsigned probe) {
+  return ((unsigned long long)rank << 38) | ((unsigned long long)id << 12) | probe;
+}
+// Priority insertion: the key of insertion rank i must end at the first bucket of its probe path
+// (b, b+1, b+3, b+6, ...) that no lower-ranked key occupies -- exactly what sequential insertion
+// into google::dense_hash_map produces.  A displaced key is carried on by the displacing thread.
+__device__ __forceinline__ void priority_insert(unsigned long long *tab, unsigned mask, unsigned b, unsigned long long cur, int *err) {
+  while (true) {
+    unsigned long long old = atomicMin(tab + b, cur);
+    if (old == kEmpty) return;
+    if (old > cur) cur = old; // we took the bucket; carry the evicted key onwards
+    unsigned probe = (unsigned)(cur & 0xfffull) + 1u;
+    if (probe >= 4096u) { *err = 3; return; }
+    cur = (cur & ~0xfffull) | probe;
+    b = (b + probe) & mask;
+  }
+}
+struct TabIn { const unsigned long long *tab; __device__ int operator()(long i) const { return tab[i] != kEmpty; } };
+// re-insert the old table's elements in ascending bucket order (copy_from on growth)
+struct RehashOut {
+  const unsigned long long *prev; unsigned long long *cur; unsigned mask; const int4 *coords; int *err;
+  __device__ void operator()(long i, int pre, int v) const {
+    if (!v) return;
+    unsigned id = (unsigned)((prev[i] >> 12) & 0x3ffffffull);
+    int4 c = coords[id];
+    priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, pack_entry((unsigned)pre, id, 0), err);
+  }
+};
+__global__ void k_insert_new(unsigned long long *cur, unsigned mask, const int4 *coords, const int *seq, int idOffset, int from, int to, int *err) {
+  for (int j = from + blockIdx.x * blockDim.x + threadIdx.x; j < to; j += gridDim.x * blockDim.x) {
+    unsigned id = seq ? (unsigned)seq[j] : (unsigned)(j + idOffset);
+    int4 c = coords[id];
+    priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, pack_entry((unsigned)j, id, 0), err);
+  }
+}
+struct OrderOut {
+  const unsigned long long *tab; int *rank2id;
+  __device__ void operator()(long i, int pre, int v) const { if (v) rank2id[pre] = (int)((tab[i] >> 12) & 0x3ffffffull); }
+};
+
+// Single-CTA version of the same phase loop for the first (small) tables, entirely in shared
+// memory: tables up to kSmallNb buckets.  Leaves the last small table in `out` (global).
+constexpr int kSmallNb = 8192;
+__global__ void __launch_bounds__(1024) k_emulate_small(const int4 *coords, const int *seq, int idOffset, int n, unsigned long long *out, int *outNb, int *err) {
+  extern __shared__ unsigned long long sm[];
+  unsigned long long *A = sm, *B = sm + kSmallNb;
+  __shared__ int s_scan[1024 / 32];
+  __shared__ int s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  unsigned long long *prev = A, *cur = B;
+  int nb = 32, nPrev = 0;
+  while (true) {
+    const int nCur = min(n, nb / 2);
+    const unsigned mask = nb - 1;
+    for (int i = tid; i < nb; i += 1024) cur[i] = kEmpty;
+    __syncthreads();
+    // old elements in ascending bucket order of prev (rank = prefix count)
+    if (nPrev > 0) {
+      const int nbPrev = nb / 2;
+      if (tid == 0) s_carry = 0;
+      __syncthreads();
+      for (int base = 0; base < nbPrev; base += 1024) {
+        int i = base + tid;
+        unsigned long long e = i < nbPrev ? prev[i] : kEmpty;
+        int v = e != kEmpty;
+        int incl = warp_incl_scan(v, lane);
+        if (lane == 31) s_scan[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+          int w = s_scan[lane];
+          int wi = warp_incl_scan(w, lane);
+          s_scan[lane] = wi - w;
+        }
+        __syncthreads();
+        int rank = s_carry + s_scan[wid] + incl - v;
+        if (v) {
+          unsigned id = (unsigned)((e >> 12) & 0x3ffffffull);
+          int4 c = coords[id];
+          priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, pack_entry((unsigned)rank, id, 0), err);
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = rank + v;
+        __syncthreads();
+      }
+    }
+    for (int j = nPrev + tid; j < nCur; j += 1024) {
+      unsigned id = seq ? (unsigned)seq[j] : (unsigned)(j + idOffset);
+      int4 c = coords[id];
+      priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, pack_entry((unsigned)j, id, 0), err);
+    }
+    __syncthreads();
+    if (nCur == n || nb == kSmallNb) {
+      for (int i = tid; i < nb; i += 1024) out[i] = cur[i];
+      if (tid == 0) *outNb = nb;
+      return;
+    }
+    unsigned long long *t = prev; prev = cur; cur = t;
+    nPrev = nCur;
+    nb *= 2;
+  }
+}
+
+// Hash-iteration order of one batch item: ids seq[0..n) (or idOffset + 0..n) inserted in that order.
+static int emulate_order(Metadata &M, const int4 *coords, const int *seq, int idOffset, int n, int *rank2idOut) {
+  if (n == 0) return 0;
+  cudaStream_t s = M.stream;
+  long nbFinal = 32;
+  while (n > nbFinal / 2) nbFinal *= 2;
+  unsigned long long *T0 = M.alloc_n<unsigned long long>(nbFinal), *T1 = M.alloc_n<unsigned long long>(nbFinal);
+  SCN_CHECK(T0 && T1, "alloc");
+  static bool attr = false;
+  if (!attr) {
+    SCN_CUDA(cudaFuncSetAttribute(k_emulate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmallNb * 8));
+    attr = true;
+  }
+  // small phases in one CTA
+  k_emulate_small<<<1, 1024, 2 * kSmallNb * 8, LS(s)>>>(coords, seq, idOffset, n, T0, M.d_scalars + 100, M.d_err);
+  SCN_CUDA(cudaGetLastError());
+  long nb = std::min<long>(nbFinal, kSmallNb);
+  unsigned long long *prev = T0, *cur = T1;
+  int nPrev = (int)std::min<long>(n, nb / 2);
+  while (nb < nbFinal) {
+    nb *= 2;
+    int nCur = (int)std::min<long>(n, nb / 2);
+    SCN_CUDA(cudaMemsetAsync(cur, 0xff, nb * 8, s));
+    SCN_TRY(run_scan(M, nb / 2, TabIn{prev}, RehashOut{prev, cur, (unsigned)(nb - 1), coords, M.d_err}, nullptr));
+    if (nCur > nPrev) k_insert_new<<<stream_grid(nCur - nPrev, 256), 256, 0, LS(s)>>>(cur, (unsigned)(nb - 1), coords, seq, idOffset, nPrev, nCur, M.d_err);
+    std::swap(prev, cur);
+    nPrev = nCur;
+  }
+  SCN_TRY(run_scan(M, nbFinal, TabIn{prev}, OrderOut{prev, rank2idOut}, nullptr));
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+struct BatchIn { const int4 *coords; int b; __device__ int operator()(long i) const { return coords[i].w == b; } };
+struct BatchOut { int *seq; __device__ void operator()(long i, int pre, int v) const { if (v) seq[pre] = (int)i; } };
+
+int Metadata::ensure_rank(Grid &g) {
+  if (g.hasRank) return 0;
+  g.rank2id = alloc_n<int>(std::max(1, g.n));
+  SCN_CHECK(g.rank2id, "alloc");
+  int start = 0;
+  for (int b = 0; b < g.batch; b++) {
+    int cnt = g.itemCount[b];
+    if (g.itemCtr[b] >= 0) {
+      SCN_TRY(emulate_order(*this, g.coords, nullptr, g.itemCtr[b], cnt, g.rank2id + start));
+    } else { // ids of item b interleave with other items: compact them in ascending id order
+      int *seq = alloc_n<int>(std::max(1, cnt));
+      SCN_CHECK(seq, "alloc");
+      SCN_TRY(run_scan(*this, g.n, BatchIn{g.coords, b}, BatchOut{seq}, nullptr));
+      SCN_TRY(emulate_order(*this, g.coords, seq, 0, cnt, g.rank2id + start));
+    }
+    start += cnt;
+  }
+  g.hasRank = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------ rule lists (shared machinery)
+// Events are visited in reference order (rank-major).  Each rank r owns at most one event per
+// list, so the position of (r, L) inside list L is the number of earlier ranks with an event in L.
+constexpr int kRuleTile = 256;
+__device__ __forceinline__ void tile_list_counts(unsigned long long mask, int K, int (*s_cnt)[64], int lane, int wid) {
+  for (int L = 0; L < K; L++) {
+    unsigned bal = __ballot_sync(0xffffffffu, (mask >> L) & 1ull);
+    if (lane == 0) s_cnt[wid][L] = __popc(bal);
+  }
+}
+// tileCnt[tile*K + L]
+template <class MaskF>
+__global__ void __launch_bounds__(kRuleTile) k_rule_count(int n, int K, MaskF maskf, int *tileCnt) {
+  __shared__ int s_cnt[kRuleTile / 32][64];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int r = blockIdx.x * kRuleTile + tid;
+  unsigned long long mask = r < n ? maskf(r) : 0ull;
+  tile_list_counts(mask, K, s_cnt, lane, wid);
+  __syncthreads();
+  if (tid < K) {
+    int c = 0;
+    for (int w = 0; w < kRuleTile / 32; w++) c += s_cnt[w][tid];
+    tileCnt[(long)blockIdx.x * K + tid] = c;
+  }
+}
+// one CTA per list: exclusive scan of tileCnt[., L] over tiles (in place), totals[L]
+__global__ void __launch_bounds__(1024) k_rule_scan(int nTiles, int K, int *tileCnt, int *totals) {
+  __shared__ int s_scan[32];
+  __shared__ int s_carry;
+  const int L = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nTiles; base += 1024) {
+    int i = base + tid;
+    int v = i < nTiles ? tileCnt[(long)i * K + L] : 0;
+    int incl = warp_incl_scan(v, lane);
+    if (lane == 31) s_scan[wid] = incl;
+    __syncthreads();
+    if (wid == 0) { int w = s_scan[lane]; int wi = warp_incl_scan(w, lane); s_scan[lane] = wi - w; }
+    __syncthreads();
+    int ex = s_carry + s_scan[wid] + incl - v;
+    if (i < nTiles) tileCnt[(long)i * K + L] = ex;
+    __syncthreads();
+    if (tid == 1023) s_carry = ex + v;
+    __syncthreads();
+  }
+  if (tid == 0) totals[L] = s_carry;
+}
+__global__ void k_list_offsets(int K, const int *totals, int *off) {
+  if (threadIdx.x == 0) { int a = 0; for (int L = 0; L < K; L++) { off[L] = a; a += totals[L]; } off[K] = a; }
+}
+template <class MaskF, class PairF>
+__global__ void __launch_bounds__(kRuleTile) k_rule_write(int n, int K, MaskF maskf, PairF pairf, const int *tileBase, const int *off, int2 *pairs) {
+  __shared__ int s_cnt[kRuleTile / 32][64];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int r = blockIdx.x * kRuleTile + tid;
+  unsigned long long mask = r < n ? maskf(r) : 0ull;
+  tile_list_counts(mask, K, s_cnt, lane, wid);
+  __syncthreads();
+  if (tid < K) { // exclusive prefix over warps
+    int a = 0;
+    for (int w = 0; w < kRuleTile / 32; w++) { int c = s_cnt[w][tid]; s_cnt[w][tid] = a; a += c; }
+  }
+  __syncthreads();
+  for (int L = 0; L < K; L++) {
+    unsigned bal = __ballot_sync(0xffffffffu, (mask >> L) & 1ull);
+    if ((mask >> L) & 1ull) {
+      int pos = off[L] + tileBase[(long)blockIdx.x * K + L] + s_cnt[wid][L] + __popc(bal & ((1u << lane) - 1u));
+      pairs[pos] = pairf(r, L);
+    }
+  }
+}
+template <class MaskF, class PairF>
+static int build_rule_lists(Metadata &M, int n, int K, MaskF maskf, PairF pairf, RuleBookDev &rb, int extraScalars) {
+  SCN_CHECK(K >= 1 && K <= 64, "filter volume must be <= 64");
+  cudaStream_t s = M.stream;
+  rb.nLists = K;
+  rb.off.assign(K + 1, 0);
+  rb.d_off = M.alloc_n<int>(K + 1);
+  int nTiles = cdiv(std::max(n, 1), kRuleTile);
+  int *tileCnt = M.alloc_n<int>((long)nTiles * K);
+  int *totals = M.d_scalars + 128;
+  SCN_CHECK(rb.d_off && tileCnt, "alloc");
+  k_rule_count<<<nTiles, kRuleTile, 0, LS(s)>>>(n, K, maskf, tileCnt);
+  k_rule_scan<<<K, 1024, 0, LS(s)>>>(nTiles, K, tileCnt, totals);
+  k_list_offsets<<<1, 32, 0, LS(s)>>>(K, totals, rb.d_off);
+  SCN_CUDA(cudaMemcpyAsync(M.h_scalars + 128, rb.d_off, (K + 1) * 4, cudaMemcpyDeviceToHost, s));
+  if (extraScalars) SCN_CUDA(cudaMemcpyAsync(M.h_scalars, M.d_scalars, extraScalars * 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));
+  for (int L = 0; L <= K; L++) rb.off[L] = M.h_scalars[128 + L];
+  rb.total = rb.off[K];
+  rb.pairs = M.alloc_n<int2>(std::max(1l, rb.total));
+  SCN_CHECK(rb.pairs, "alloc");
+  if (n > 0) k_rule_write<<<nTiles, kRuleTile, 0, LS(s)>>>(n, K, maskf, pairf, tileCnt, rb.d_off, rb.pairs);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ submanifold
+// nbr[p*K + k] = row id of the neighbour of site p at filter offset k (last dimension fastest,
+// RectangularRegions.h:56-71; window [c - f/2, c + f - 1 - f/2], SubmanifoldConvolutionRules.h:11-22).
+__global__ void k_subm_nbr(GridView g, const int4 *coords, const int *p2id, int n, int f0, int f1, int f2, int *nbr, int *nValid) {
+  const int K = f0 * f1 * f2;
+  int cntv = 0;
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x) {
+    const int id = p2id[p];
+    const int4 c = coords[id];
+    int *row = nbr + p * K;
+    int k = 0;
+    for (int a = 0; a < f0; a++)
+      for (int b = 0; b < f1; b++)
+        for (int d = 0; d < f2; d++, k++) {
+          int x = c.x - f0 / 2 + a, y = c.y - f1 / 2 + b, z = c.z - f2 / 2 + d;
+          int q = (x == c.x && y == c.y && z == c.z) ? (int)p : grid_lookup(g, x, y, z, c.w);
+          int v = q >= 0 ? p2id[q] : -1;
+          row[k] = v;
+          cntv += v >= 0;
+        }
+  }
+  for (int d = 16; d > 0; d >>= 1) cntv += __shfl_xor_sync(0xffffffffu, cntv, d);
+  if ((threadIdx.x & 31) == 0 && cntv) atomicAdd(nValid, cntv);
+}
+struct SubmMask {
+  const int *rank2id, *id2p, *nbr; int K;
+  __device__ unsigned long long operator()(int r) const {
+    const int *row = nbr + (long)id2p[rank2id[r]] * K;
+    unsigned long long m = 0;
+    for (int k = 0; k < K; k++) m |= (unsigned long long)(row[k] >= 0) << k;
+    return m;
+  }
+};
+struct SubmPair {
+  const int *rank2id, *id2p, *nbr; int K;
+  __device__ int2 operator()(int r, int L) const {
+    int id = rank2id[r];
+    return make_int2(nbr[(long)id2p[id] * K + L], id); // (input row, output row)
+  }
+};
+
+// getSubmanifoldRuleBook (Metadata.cpp:429-443) -> SubmanifoldConvolution_SgToRules
+// (SubmanifoldConvolutionRules.h:26-45)
+int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
+  SubmKey key{P3{sz[0], sz[1], sz[2]}, P3{f[0], f[1], f[2]}};
+  auto it = subm.find(key);
+  if (it != subm.end()) { *out = &it->second; return 0; }
+  Grid *g = find_grid(sz);
+  SCN_CHECK(g, "no active sites recorded for this spatial size");
+  long K = f[0] * f[1] * f[2];
+  SCN_CHECK(K >= 1 && K <= 64 && f[0] > 0 && f[1] > 0 && f[2] > 0, "unsupported submanifold filter size");
+  SCN_TRY(ensure_rank(*g));
+  SubmEntry &e = subm[key];
+  e.plan.K = (int)K;
+  e.plan.nOut = g->n;
+  e.plan.outRow = g->p2id;
+  e.plan.nbr = alloc_n<int>(std::max(1l, (long)g->n * K));
+  SCN_CHECK(e.plan.nbr, "alloc");
+  SCN_CUDA(cudaMemsetAsync(d_scalars, 0, 4, stream));
+  if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, d_scalars);
+  SCN_TRY(build_rule_lists(*this, g->n, (int)K, SubmMask{g->rank2id, g->id2p, e.plan.nbr, (int)K},
+                           SubmPair{g->rank2id, g->id2p, e.plan.nbr, (int)K}, e.rb, 1));
+  e.plan.nValid = h_scalars[0];
+  SCN_CHECK(e.plan.nValid == e.rb.total, "internal: rule count mismatch");
+  *out = &e;
+  return 0;
+}
+
+// ------------------------------------------------------------------ strided convolution
+struct ConvGeom {
+  int f[3], s[3], outS[3], cnt[3], M, K;
+};
+// output cells of input point c: [lb, ub] per dim (OutputRegionCalculator, RectangularRegions.h:109-119);
+// event m enumerates them last-dimension-fastest.  Returns false when m is outside the region.
+__device__ __forceinline__ bool conv_event(const ConvGeom &G, const int4 &c, int m, int4 &j, int &off) {
+  int a[3];
+  a[2] = m % G.cnt[2]; m /= G.cnt[2];
+  a[1] = m % G.cnt[1]; m /= G.cnt[1];
+  a[0] = m;
+  const int p[3] = {c.x, c.y, c.z};
+  int jj[3];
+  off = 0;
+  for (int d = 0; d < 3; d++) {
+    int lo = (p[d] - G.f[d] + G.s[d]) / G.s[d]; // C++ truncating division, as the reference
+    if (lo < 0) lo = 0;
+    int hi = min(G.outS[d] - 1, p[d] / G.s[d]);
+    jj[d] = lo + a[d];
+    if (jj[d] > hi) return false;
+    off = off * G.f[d] + (p[d] - jj[d] * G.s[d]); // RectangularRegion::offset, :30-38
+  }
+  j = make_int4(jj[0], jj[1], jj[2], c.w);
+  return true;
+}
+__global__ void k_conv_events(ConvGeom G, const int *rank2id, const int4 *coords, int n, int4 *evPts) {
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < (long)n * G.M; e += (long)gridDim.x * blockDim.x) {
+    int r = (int)(e / G.M), m = (int)(e % G.M);
+    int4 c = coords[rank2id[r]], j;
+    int off;
+    evPts[e] = conv_event(G, c, m, j, off) ? j : make_int4(-1, 0, 0, 0);
+  }
+}
+__global__ void k_first_event(const int *evQ, long E, int *firstEv) {
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < E; e += (long)gridDim.x * blockDim.x) {
+    int q = evQ[e];
+    if (q >= 0) atomicMin(firstEv + q, (int)e);
+  }
+}
+struct EvFirstIn {
+  const int *evQ, *firstEv;
+  __device__ int operator()(long e) const { int q = evQ[e]; return q >= 0 && firstEv[q] == (int)e; }
+};
+struct EvFirstOut {
+  const int *evQ; const int4 *evPts; int *p2id, *id2p; int4 *coords; int *batchCnt;
+  __device__ void operator()(long e, int pre, int v) const {
+    if (v) { int q = evQ[e]; p2id[q] = pre; id2p[pre] = q; coords[pre] = evPts[e]; atomicAdd(batchCnt + evPts[e].w, 1); }
+  }
+};
+struct ConvMask {
+  ConvGeom G; const int *rank2id; const int4 *coords;
+  __device__ unsigned long long operator()(int r) const {
+    int4 c = coords[rank2id[r]], j;
+    unsigned long long m = 0;
+    for (int e = 0; e < G.M; e++) { int off; if (conv_event(G, c, e, j, off)) m |= 1ull << off; }
+    return m;
+  }
+};
+struct ConvPair {
+  ConvGeom G; const int *rank2id; const int4 *coords; const int *evQ; const int *outP2id;
+  __device__ int2 operator()(int r, int L) const {
+    int id = rank2id[r];
+    int4 c = coords[id], j;
+    for (int e = 0; e < G.M; e++) { int off; if (conv_event(G, c, e, j, off) && off == L) return make_int2(id, outP2id[evQ[(long)r * G.M + e]]); }
+    return make_int2(-1, -1);
+  }
+};
+__global__ void k_conv_plan(ConvGeom G, const int *rank2id, const int4 *coords, const int *evQ, int n, int *nbr) {
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < (long)n * G.M; e += (long)gridDim.x * blockDim.x) {
+    int q = evQ[e];
+    if (q < 0) continue;
+    int r = (int)(e / G.M), m = (int)(e % G.M);
+    int id = rank2id[r];
+    int4 j; int off;
+    conv_event(G, coords[id], m, j, off);
+    nbr[(long)q * G.K + off] = id;
+  }
+}
+
+// getRuleBook (Metadata.cpp:484-510) -> Convolution_InputSgToRulesAndOutputSg (ConvolutionRules.h:11-34)
+int Metadata::get_conv(const long *inS, const long *outS, const long *f, const long *st, ConvEntry **out) {
+  ConvKey key{P3{inS[0], inS[1], inS[2]}, P3{f[0], f[1], f[2]}, P3{st[0], st[1], st[2]}};
+  auto it = conv.find(key);
+  if (it != conv.end()) { *out = &it->second; return 0; }
+  Grid *gi = find_grid(inS);
+  SCN_CHECK(gi, "no active sites recorded for the input spatial size");
+  P3 okey{outS[0], outS[1], outS[2]};
+  SCN_CHECK(grids.find(okey) == grids.end(), "output spatial size already has a grid (each spatial size may occur once per Metadata)");
+  ConvGeom G;
+  G.M = 1; G.K = 1;
+  for (int d = 0; d < 3; d++) {
+    SCN_CHECK(f[d] >= 1 && st[d] >= 1 && outS[d] >= 1, "bad filter geometry");
+    G.f[d] = (int)f[d]; G.s[d] = (int)st[d]; G.outS[d] = (int)outS[d];
+    G.cnt[d] = (int)std::min<long>(outS[d], (f[d] + st[d] - 1) / st[d]);
+    if (G.cnt[d] < 1) G.cnt[d] = 1;
+    G.M *= G.cnt[d]; G.K *= (int)f[d];
+  }
+  SCN_CHECK(G.K <= 64 && G.M <= 64, "unsupported convolution filter size");
+  SCN_TRY(ensure_rank(*gi));
+  cudaStream_t s = stream;
+  ConvEntry &e = conv[key];
+  e.out = okey;
+  Grid &go = grids[okey];
+  go.sz = okey;
+  go.batch = gi->batch;
+  const int n = gi->n;
+  const long E = (long)n * G.M;
+  int4 *evPts = alloc_n<int4>(std::max(1l, E));
+  int *evQ = alloc_n<int>(std::max(1l, E));
+  SCN_CHECK(evPts && evQ, "alloc");
+  int *sc = d_scalars; // [1] nunique [3] nOut [8..56) per-item counts
+  SCN_CUDA(cudaMemsetAsync(sc, 0, 64 * 4, s));
+  if (E) k_conv_events<<<stream_grid(E, 256), 256, 0, LS(s)>>>(G, gi->rank2id, gi->coords, n, evPts);
+  SCN_TRY(build_blocks(*this, go, evPts, E, evQ, sc + 1));
+  long cap = std::max(1l, E);
+  go.coords = alloc_n<int4>(cap); go.p2id = alloc_n<int>(cap); go.id2p = alloc_n<int>(cap);
+  int *firstEv = alloc_n<int>(cap);
+  SCN_CHECK(go.coords && go.p2id && go.id2p && firstEv, "alloc");
+  SCN_CUDA(cudaMemsetAsync(firstEv, 0x7f, cap * 4, s));
+  if (E) k_first_event<<<stream_grid(E, 256), 256, 0, LS(s)>>>(evQ, E, firstEv);
+  SCN_TRY(run_scan(*this, E, EvFirstIn{evQ, firstEv}, EvFirstOut{evQ, evPts, go.p2id, go.id2p, go.coords, sc + 8}, sc + 3));
+  // rule lists (one sync: list offsets + nOut + per-item counts)
+  SCN_TRY(build_rule_lists(*this, n, G.K, ConvMask{G, gi->rank2id, gi->coords},
+                           ConvPair{G, gi->rank2id, gi->coords, evQ, go.p2id}, e.rb, 64));
+  go.n = h_scalars[3];
+  SCN_CHECK(h_scalars[1] == go.n, "internal: unique count mismatch (conv)");
+  go.itemCount.assign(go.batch, 0);
+  go.itemCtr.assign(go.batch, 0);
+  int ctr = 0;
+  for (int b = 0; b < go.batch; b++) { go.itemCount[b] = h_scalars[8 + b]; go.itemCtr[b] = ctr; ctr += go.itemCount[b]; }
+  go.built = true;
+  // output-stationary plan
+  e.plan.K = G.K; e.plan.nOut = go.n; e.plan.outRow = go.p2id; e.plan.nValid = e.rb.total;
+  e.plan.nbr = alloc_n<int>(std::max(1l, (long)go.n * G.K));
+  SCN_CHECK(e.plan.nbr, "alloc");
+  SCN_CUDA(cudaMemsetAsync(e.plan.nbr, 0xff, std::max(1l, (long)go.n * G.K) * 4, s));
+  if (E) k_conv_plan<<<stream_grid(E, 256), 256, 0, LS(s)>>>(G, gi->rank2id, gi->coords, evQ, n, e.plan.nbr);
+  SCN_CUDA(cudaGetLastError());
+  *out = &e;
+  return 0;
+}
+
+// ------------------------------------------------------------------ getSpatialLocations
+__global__ void k_locations(const int4 *coords, int n, long *out) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    out[i * 4 + 0] = c.x; out[i * 4 + 1] = c.y; out[i * 4 + 2] = c.z; out[i * 4 + 3] = c.w;
+  }
+}
+// Metadata::getSpatialLocations (Metadata.cpp:147-168): int64 [nActive][4] in row-id order
+int Metadata::spatial_locations(const long *sz, long *out, int outOnDevice) {
+  Grid *g = find_grid(sz);
+  SCN_CHECK(g, "no active sites recorded for this spatial size");
+  if (g->n == 0) return 0;
+  long *dst = out;
+  if (!outOnDevice) { dst = alloc_n<long>((long)g->n * 4); SCN_CHECK(dst, "alloc"); }
+  k_locations<<<stream_grid(g->n, 256), 256, 0, LS(stream)>>>(g->coords, g->n, dst);
+  SCN_CUDA(cudaGetLastError());
+  if (!outOnDevice) {
+    SCN_CUDA(cudaMemcpyAsync(out, dst, (long)g->n * 32, cudaMemcpyDeviceToHost, stream));
+    SCN_CUDA(cudaStreamSynchronize(stream));
+  }
+  return 0;
+}
+
+} // namespace scn

@@ -1,0 +1,130 @@
+// Device-resident Metadata: per spatial size an active-site grid (block directory + occupancy
+// masks for neighbour probes, reference row numbering, reference hash-iteration order) and the
+// rulebooks / execution plans derived from it.  Replaces the host-side Metadata<3> of the
+// reference (SCN/Metadata/Metadata.h:44-163, Metadata.cpp).
+#pragma once
+#include "common.cuh"
+#include <map>
+#include <vector>
+#include <array>
+
+namespace scn {
+
+typedef std::array<long, 3> P3;
+
+struct Grid {
+  P3 sz{};            // spatial size
+  int n = 0;          // active sites over all batch items (host copy)
+  int batch = 1;
+  // block directory: 8x8x8 blocks, one directory plane per batch item
+  int dd[3] = {0, 0, 0};
+  long dirCells = 0;  // per batch item
+  int *dir = nullptr;                  // [batch*dirCells] block index or -1
+  unsigned long long *bmask = nullptr; // [maxBlocks*8] 512-bit occupancy per block
+  int *wbase = nullptr;                // [maxBlocks*8] spatial index of the first bit of each word
+  int *d_nblocks = nullptr;            // device scalar
+  long maxBlocks = 0;
+  int4 *coords = nullptr;              // [n] (x,y,z,batch) by row id  (reference numbering)
+  int *p2id = nullptr, *id2p = nullptr; // spatial index <-> row id
+  int *rank2id = nullptr;              // reference hash-iteration order (batch items concatenated)
+  bool hasRank = false;
+  std::vector<int> itemCount;          // sites per batch item (host)
+  std::vector<int> itemCtr;            // SparseGrid::ctr per item (id offset); -1 when ids interleave (input grid)
+  bool built = false;
+};
+
+// One rulebook in the reference's format: nLists lists of (in,out) int32 pairs, concatenated;
+// list k occupies pairs [off[k], off[k+1]).
+struct RuleBookDev {
+  int nLists = 0;
+  int2 *pairs = nullptr;      // device
+  std::vector<int> off;       // host, nLists+1
+  int *d_off = nullptr;       // device copy
+  long total = 0;
+};
+
+// Output-stationary execution plan: for every output site (in spatial order p) the input row of
+// each filter offset, or -1.
+struct NbrPlan {
+  int K = 0;
+  int nOut = 0;
+  int *nbr = nullptr;         // [nOut*K] input row ids, indexed by OUTPUT spatial index p
+  const int *outRow = nullptr; // p -> output row id (p2id of the output grid)
+  long nValid = 0;            // number of non-negative entries (= rules)
+};
+
+struct SubmKey { P3 sz, f; bool operator<(const SubmKey &o) const { return sz != o.sz ? sz < o.sz : f < o.f; } };
+struct ConvKey { P3 in, f, s; bool operator<(const ConvKey &o) const { return in != o.in ? in < o.in : (f != o.f ? f < o.f : s < o.s); } };
+
+struct SubmEntry { RuleBookDev rb; NbrPlan plan; };
+struct ConvEntry { RuleBookDev rb; NbrPlan plan; P3 out; };
+
+struct InputRules {
+  int mode = 0, maxActive = 0, nIn = 0, nOut = 0;
+  int *tab = nullptr;  // [nOut*(1+maxActive)] device
+  bool valid = false;
+};
+
+struct Metadata {
+  cudaStream_t stream = 0;
+  std::map<P3, Grid> grids;
+  std::map<SubmKey, SubmEntry> subm;   // submanifoldRuleBooks, Metadata.h:58-60
+  std::map<ConvKey, ConvEntry> conv;   // ruleBooks, Metadata.h:65-67
+  InputRules input;
+  std::vector<void *> allocs;
+  // zero-initialised pool for scan states
+  unsigned long long *zpool = nullptr;
+  size_t zpoolWords = 0, zpoolUsed = 0;
+  int *d_scalars = nullptr; // small device scratch (64 ints)
+  int *h_scalars = nullptr; // pinned host mirror
+  int *d_err = nullptr;
+
+  ~Metadata();
+  int init();
+  void *alloc(size_t bytes);
+  template <class T> T *alloc_n(size_t n) { return static_cast<T *>(alloc(n * sizeof(T) + 16)); }
+  unsigned long long *scan_state(long n);
+  int sync_scalars(int count);
+
+  int input_layer(const long *sz, const long *coords, int coordsOnDevice, long nrows, int ncols,
+                  int batchHint, int mode);
+  Grid *find_grid(const long *sz);
+  int ensure_rank(Grid &g);
+  int get_submanifold(const long *sz, const long *f, SubmEntry **out);
+  int get_conv(const long *inS, const long *outS, const long *f, const long *s, ConvEntry **out);
+  int spatial_locations(const long *sz, long *out, int outOnDevice);
+};
+
+// ------------------------------------------------------------------ device helpers
+__host__ __device__ __forceinline__ uint32_t point_hash(int x, int y, int z) {
+  // IntArrayHash<3>, SCN/Metadata/32bits.h:57-66
+  uint32_t h = 16777619u;
+  h *= 2166136261u; h ^= (uint32_t)x;
+  h *= 2166136261u; h ^= (uint32_t)y;
+  h *= 2166136261u; h ^= (uint32_t)z;
+  return h;
+}
+
+struct GridView {
+  const int *dir;
+  const unsigned long long *bmask;
+  const int *wbase;
+  int dd0, dd1, dd2;
+  long dirCells;
+  int sz0, sz1, sz2;
+};
+// spatial index of an active site, or -1
+__device__ __forceinline__ int grid_lookup(const GridView &g, int x, int y, int z, int b) {
+  if ((unsigned)x >= (unsigned)g.sz0 || (unsigned)y >= (unsigned)g.sz1 || (unsigned)z >= (unsigned)g.sz2) return -1;
+  long cell = (long)b * g.dirCells + ((long)(x >> 3) * g.dd1 + (y >> 3)) * g.dd2 + (z >> 3);
+  int blk = __ldg(g.dir + cell);
+  if (blk < 0) return -1;
+  int bit = ((x & 7) << 6) | ((y & 7) << 3) | (z & 7);
+  int w = blk * 8 + (bit >> 6);
+  unsigned long long m = __ldg(g.bmask + w);
+  unsigned long long one = 1ull << (bit & 63);
+  if (!(m & one)) return -1;
+  return __ldg(g.wbase + w) + __popcll(m & (one - 1));
+}
+
+} // namespace scn

@@ -1,0 +1,276 @@
+// Row-wise (HBM-bound) kernels: BatchNorm(+leaky ReLU) forward/backward, InputLayer
+// forward/backward, feature-plane addition.  All stream rows with 16-byte accesses and size
+// their grids as multiples of the 148 SMs.
+//
+// Replaces BatchNormalization_f_train/f_test/b (SCN/CUDA/BatchNormalization.cu:14-198, which run
+// on <= 16 CTAs) and InputLayer_fp_/bp_ (SCN/CUDA/IOLayers.cu:14-58).
+#include "common.cuh"
+
+namespace scn {
+
+// ------------------------------------------------------------------ BN statistics
+// stats[0..C) = sum x, stats[C..2C) = sum x^2 (or sum of (x-shift)^2 terms), in double.
+// Each thread owns one float4 column group and strides over rows; per-CTA partials are reduced
+// in shared memory and added with one double atomic per channel per CTA.
+__global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, long n, int C, int rowsPerCta, double *__restrict__ stats) {
+  extern __shared__ float s_red[]; // [2][256][4]
+  const int cv = C >> 2;           // float4 groups per row
+  const int tid = threadIdx.x;
+  const int lanesPerRow = cv;      // cv <= 256
+  const int rowLanes = 256 / lanesPerRow;
+  const int cg = tid % lanesPerRow, rl = tid / lanesPerRow;
+  float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+  const long r0 = (long)blockIdx.x * rowsPerCta;
+  const long r1 = min(n, r0 + rowsPerCta);
+  if (rl < rowLanes) {
+    for (long r = r0 + rl; r < r1; r += rowLanes) {
+      float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * C) + cg);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+  }
+  float4 *S = reinterpret_cast<float4 *>(s_red), *Q = S + 256;
+  S[tid] = s; Q[tid] = q;
+  __syncthreads();
+  if (tid < lanesPerRow) {
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    for (int l = 0; l < rowLanes; l++) {
+      float4 u = S[l * lanesPerRow + tid], w = Q[l * lanesPerRow + tid];
+      a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+      b[0] += w.x; b[1] += w.y; b[2] += w.z; b[3] += w.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      atomicAdd(stats + tid * 4 + j, a[j]);
+      atomicAdd(stats + C + tid * 4 + j, b[j]);
+    }
+  }
+}
+// scalar fallback for C % 4 != 0 (C <= 256)
+__global__ void __launch_bounds__(256) k_bn_stats_scalar(const float *__restrict__ x, long n, int C, int rowsPerCta, double *__restrict__ stats) {
+  __shared__ float S[256], Q[256];
+  const int tid = threadIdx.x;
+  const int rowLanes = 256 / C;
+  const int c = tid % C, rl = tid / C;
+  float s = 0.f, q = 0.f;
+  const long r0 = (long)blockIdx.x * rowsPerCta, r1 = min(n, r0 + rowsPerCta);
+  if (rl < rowLanes)
+    for (long r = r0 + rl; r < r1; r += rowLanes) { float v = __ldg(x + r * C + c); s += v; q = fmaf(v, v, q); }
+  S[tid] = s; Q[tid] = q;
+  __syncthreads();
+  if (tid < C) {
+    double a = 0, b = 0;
+    for (int l = 0; l < rowLanes; l++) { a += S[l * C + tid]; b += Q[l * C + tid]; }
+    atomicAdd(stats + tid, a);
+    atomicAdd(stats + C + tid, b);
+  }
+}
+
+// mode 0: train   -- BatchNormalization_ForwardPass train branch (SCN/CPU/BatchNormalization.cpp:19-40):
+//                    biased variance for normalisation, running stats updated with unbiased variance.
+// mode 1: eval with given running stats (:41-46).
+// mode 2: eval, track_running_stats=False -- sparseconvnet/batchNormalization.py:51-56: mean(0) and the
+//                    UNBIASED var(0) of this input stand in for the running stats.
+// Emits saveMean/saveInvStd and the fused scale/shift  y = x*scale + shift.
+__global__ void k_bn_finalize(const double *__restrict__ stats, long n, int C, int mode, float eps, float momentum, float *saveMean,
+                              float *saveInvStd, float *runningMean, float *runningVar, const float *__restrict__ weight,
+                              const float *__restrict__ bias, float *scale, float *shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (mode == 1) {
+    mean = runningMean[c];
+    invstd = powf(runningVar[c] + eps, -0.5f);
+  } else {
+    double m = stats[c] / (double)n;
+    double ss = stats[C + c] - m * m * (double)n; // sum of squared deviations
+    if (ss < 0) ss = 0;
+    mean = (float)m;
+    if (mode == 0) {
+      runningMean[c] = momentum * runningMean[c] + (1 - momentum) * mean;
+      runningVar[c] = momentum * runningVar[c] + (1 - momentum) * (float)(ss / (double)(n - 1));
+      invstd = powf((float)(ss / (double)n) + eps, -0.5f);
+    } else {
+      invstd = powf((float)(ss / (double)(n - 1)) + eps, -0.5f);
+    }
+  }
+  saveMean[c] = mean;
+  saveInvStd[c] = invstd;
+  float w = invstd * (weight ? weight[c] : 1.f);
+  scale[c] = w;
+  shift[c] = -mean * w + (bias ? bias[c] : 0.f);
+}
+
+// y = leaky(x*scale + shift)   (:53-61)
+__global__ void __launch_bounds__(256) k_bn_apply(const float *__restrict__ x, float *__restrict__ y, long total4, int cv, const float *__restrict__ scale,
+                                                  const float *__restrict__ shift, float leak) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    int cg = (int)(i % cv);
+    float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+    float4 a = __ldg(reinterpret_cast<const float4 *>(scale) + cg), b = __ldg(reinterpret_cast<const float4 *>(shift) + cg);
+    float4 o;
+    o.x = fmaf(v.x, a.x, b.x); o.y = fmaf(v.y, a.y, b.y); o.z = fmaf(v.z, a.z, b.z); o.w = fmaf(v.w, a.w, b.w);
+    o.x = o.x > 0 ? o.x : o.x * leak; o.y = o.y > 0 ? o.y : o.y * leak; o.z = o.z > 0 ? o.z : o.z * leak; o.w = o.w > 0 ? o.w : o.w * leak;
+    reinterpret_cast<float4 *>(y)[i] = o;
+  }
+}
+__global__ void __launch_bounds__(256) k_bn_apply_scalar(const float *__restrict__ x, float *__restrict__ y, long total, int C, const float *__restrict__ scale,
+                                                         const float *__restrict__ shift, float leak) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    float o = fmaf(__ldg(x + i), scale[c], shift[c]);
+    y[i] = o > 0 ? o : o * leak;
+  }
+}
+
+static int bn_stats_launch(const float *x, long n, int C, double *stats, cudaStream_t s) {
+  SCN_CUDA(cudaMemsetAsync(stats, 0, 2 * C * sizeof(double), s));
+  if (n == 0) return 0;
+  int rowsPerCta = (int)std::max<long>(64, (n + kSMs * 16 - 1) / (kSMs * 16));
+  int grid = cdiv(n, rowsPerCta);
+  if (C % 4 == 0) {
+    SCN_CHECK(C / 4 <= 256, "BatchNorm: more than 1024 channels not supported");
+    k_bn_stats<<<grid, 256, 2 * 256 * 16, LS(s)>>>(x, n, C, rowsPerCta, stats);
+  } else {
+    SCN_CHECK(C <= 256, "BatchNorm: channel count not a multiple of 4 must be <= 256");
+    k_bn_stats_scalar<<<grid, 256, 0, LS(s)>>>(x, n, C, rowsPerCta, stats);
+  }
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// workspace: 2*C doubles + 2*C floats
+int bn_forward(const float *x, float *y, long n, int C, float *saveMean, float *saveInvStd, float *runningMean, float *runningVar,
+               const float *weight, const float *bias, float eps, float momentum, int mode, float leak, void *workspace, cudaStream_t s) {
+  double *stats = static_cast<double *>(workspace);
+  float *scale = reinterpret_cast<float *>(stats + 2 * C), *shift = scale + C;
+  if (mode != 1) SCN_TRY(bn_stats_launch(x, n, C, stats, s));
+  k_bn_finalize<<<cdiv(C, 128), 128, 0, LS(s)>>>(stats, n, C, mode, eps, momentum, saveMean, saveInvStd, runningMean, runningVar, weight, bias, scale, shift);
+  if (n) {
+    long total = n * C;
+    if (C % 4 == 0) k_bn_apply<<<stream_grid(total / 4, 256), 256, 0, LS(s)>>>(x, y, total / 4, C / 4, scale, shift, leak);
+    else k_bn_apply_scalar<<<stream_grid(total, 256), 256, 0, LS(s)>>>(x, y, total, C, scale, shift, leak);
+  }
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ BN backward
+// BatchNormalization_BackwardPass (SCN/CPU/BatchNormalization.cpp:64-107).  Pass 1: d = dy * (y>0?1:leak)
+// written back into dy (the reference rewrites d_output in place, :79-82), per-channel sum d and
+// sum (x-mean)*d.  Pass 2: dx = (d - mean(d) - (x-mean)*k) * invstd * gamma.
+__global__ void __launch_bounds__(256) k_bn_bwd_stats(const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ dy, long n, int C,
+                                                      int rowsPerCta, const float *__restrict__ saveMean, float leak, double *__restrict__ stats) {
+  __shared__ float S[256], Q[256];
+  const int tid = threadIdx.x;
+  const int cols = min(C, 256), rowLanes = 256 / cols;
+  const long r0 = (long)blockIdx.x * rowsPerCta, r1 = min(n, r0 + rowsPerCta);
+  for (int cb = 0; cb < C; cb += cols) {
+    const int c = cb + tid % cols, rl = tid / cols;
+    float s = 0.f, q = 0.f;
+    if (rl < rowLanes && c < C) {
+      const float m = saveMean[c];
+      for (long r = r0 + rl; r < r1; r += rowLanes) {
+        long i = r * C + c;
+        float d = dy[i] * (y[i] > 0 ? 1.f : leak);
+        dy[i] = d;
+        s += d;
+        q = fmaf(x[i] - m, d, q);
+      }
+    }
+    S[tid] = s; Q[tid] = q;
+    __syncthreads();
+    if (tid < cols && cb + tid < C) {
+      double a = 0, b = 0;
+      for (int l = 0; l < rowLanes; l++) { a += S[l * cols + tid]; b += Q[l * cols + tid]; }
+      atomicAdd(stats + cb + tid, a);
+      atomicAdd(stats + C + cb + tid, b);
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_bn_bwd_finalize(const double *__restrict__ stats, long n, int C, const float *__restrict__ saveInvStd, float *dWeight, float *dBias,
+                                  float *gradMean, float *kk) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float gm = (float)stats[c], dotp = (float)stats[C + c];
+  if (dBias) dBias[c] = gm;
+  if (dWeight) dWeight[c] = dotp * saveInvStd[c];
+  gradMean[c] = gm / (float)n;
+  kk[c] = dotp * saveInvStd[c] * saveInvStd[c] / (float)n;
+}
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ x, const float *__restrict__ d, float *__restrict__ dx, long total, int C,
+                                                      const float *__restrict__ saveMean, const float *__restrict__ saveInvStd,
+                                                      const float *__restrict__ weight, const float *__restrict__ gradMean, const float *__restrict__ kk) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % C);
+    dx[i] = (d[i] - gradMean[c] - (x[i] - saveMean[c]) * kk[c]) * saveInvStd[c] * (weight ? weight[c] : 1.f);
+  }
+}
+int bn_backward(const float *x, float *dx, const float *y, float *dy, long n, int C, const float *saveMean, const float *saveInvStd,
+                const float *weight, float *dWeight, float *dBias, float leak, void *workspace, cudaStream_t s) {
+  double *stats = static_cast<double *>(workspace);
+  float *gradMean = reinterpret_cast<float *>(stats + 2 * C), *kk = gradMean + C;
+  SCN_CUDA(cudaMemsetAsync(stats, 0, 2 * C * sizeof(double), s));
+  if (n) {
+    int rowsPerCta = (int)std::max<long>(64, (n + kSMs * 16 - 1) / (kSMs * 16));
+    k_bn_bwd_stats<<<cdiv(n, rowsPerCta), 256, 0, LS(s)>>>(x, y, dy, n, C, rowsPerCta, saveMean, leak, stats);
+  }
+  k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, LS(s)>>>(stats, n, C, saveInvStd, dWeight, dBias, gradMean, kk);
+  if (n) k_bn_bwd_apply<<<stream_grid(n * C, 256), 256, 0, LS(s)>>>(x, dy, dx, n * C, C, saveMean, saveInvStd, weight, gradMean, kk);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ InputLayer
+// InputLayer_ForwardPass (SCN/CPU/IOLayers.cpp:11-29): out[row] = sum_i mult * in[rules[row][i]], rows in list order.
+__global__ void __launch_bounds__(256) k_input_fwd(const float *__restrict__ in, float *__restrict__ out, int nOut, int w, int C, const int *__restrict__ tab, int average) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)nOut * C; i += (long)gridDim.x * blockDim.x) {
+    int row = (int)(i / C), c = (int)(i % C);
+    const int *r = tab + (long)row * w;
+    int na = r[0];
+    float mult = (average && na > 0) ? 1.f / na : 1.f;
+    float acc = 0.f;
+    for (int j = 1; j <= na; j++) acc += mult * __ldg(in + (long)r[j] * C + c);
+    out[i] = acc;
+  }
+}
+// mode 0: rows are unique; out row id <- first-occurrence order == input order
+__global__ void __launch_bounds__(256) k_input_bwd(float *__restrict__ din, const float *__restrict__ dout, int nOut, int w, int C, const int *__restrict__ tab, int average) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)nOut * C; i += (long)gridDim.x * blockDim.x) {
+    int row = (int)(i / C), c = (int)(i % C);
+    const int *r = tab + (long)row * w;
+    int na = r[0];
+    float mult = (average && na > 0) ? 1.f / na : 1.f;
+    float g = mult * dout[i];
+    for (int j = 1; j <= na; j++) din[(long)r[j] * C + c] = g; // an input row feeds exactly one voxel: plain store
+  }
+}
+int input_forward(const float *in, float *out, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s) {
+  if (nOut) k_input_fwd<<<stream_grid((long)nOut * C, 256), 256, 0, LS(s)>>>(in, out, nOut, 1 + maxActive, C, tab, average);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+int input_backward(float *din, const float *dout, long nIn, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s) {
+  SCN_CUDA(cudaMemsetAsync(din, 0, nIn * C * sizeof(float), s)); // rows dropped by modes 1/2 get zero gradient
+  if (nOut) k_input_bwd<<<stream_grid((long)nOut * C, 256), 256, 0, LS(s)>>>(din, dout, nOut, 1 + maxActive, C, tab, average);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ add_feature_planes / AddTable
+__global__ void __launch_bounds__(256) k_add(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ o, long n) {
+  long n4 = n >> 2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 u = __ldg(reinterpret_cast<const float4 *>(a) + i), v = __ldg(reinterpret_cast<const float4 *>(b) + i);
+    reinterpret_cast<float4 *>(o)[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+  for (long i = (n4 << 2) + blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) o[i] = a[i] + b[i];
+}
+int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s) {
+  if (n) k_add<<<stream_grid(n / 4 + 1, 256), 256, 0, LS(s)>>>(a, b, o, n);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
+} // namespace scn

@@ -1,0 +1,145 @@
+"""FPN_Net: the sparse ResNet-FPN backbone of Detection_3D (reference:
+SparseConvNet/sparseconvnet/fpn_net.py:13-265, built by
+maskrcnn_benchmark/modeling/backbone/backbone.py:39-69).
+
+Module tree and parameter names follow the reference so its checkpoints load unchanged:
+layers_in_0, layers_in.{0,1}, layers_out.{0,1}, linear, convs_pro2d.i, m_downs.k..., m_shortcuts.k,
+m_ups.k.{0,1}, m_mergeds.k.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import layers as L
+from .containers import AddTable, ConcatTable, Identity, Sequential, add_feature_planes
+
+
+class OutputLayer(nn.Module):
+    """Parameter-free inverse of InputLayer (reference: sparseconvnet/ioLayers.py:68-90).  FPN_Net holds
+    one in `layers_out` but never calls it; it exists so the module tree matches."""
+
+    def __init__(self, dimension):
+        nn.Module.__init__(self)
+        self.dimension = dimension
+
+    def forward(self, input):
+        raise NotImplementedError("OutputLayer is not on the Detection_3D backbone path")
+
+
+_ELEMENT_CHANNELS = {'xyz': 3, 'color': 3, 'normal': 3}
+
+
+class FPN_Net(nn.Module):
+    def __init__(self, full_scale, dimension, raw_elements, reps, nPlanesF, nPlaneM, residual_blocks,
+                 fpn_scales_from_top, roi_scales_from_top, downsample, rpn_map_sizes,
+                 rpn_3d_2d_selector, leakiness=0, voxel_scale=None, bn_momentum=0.9, track_running_stats=True):
+        """downsample = [kernels, strides], one [kx,ky,kz] per level transition."""
+        nn.Module.__init__(self)
+        self.bn_momentum = bn_momentum
+        self.track_running_stats = track_running_stats
+        self.dimension = dimension
+        self.down_kernels, self.down_strides = downsample[0], downsample[1]
+        self.fpn_scales_from_top = fpn_scales_from_top
+        self.roi_scales_from_top = roi_scales_from_top
+        n_scales = len(nPlanesF)
+        assert len(self.down_kernels) == n_scales - 1 == len(self.down_strides), \
+            f"nPlanesF len = {n_scales}, kernels num = {len(self.down_kernels)}"
+        assert all(len(k) == 3 for k in self.down_kernels) and all(len(s) == 3 for s in self.down_strides)
+        self._merge = 'add'
+        in_channels = sum(_ELEMENT_CHANNELS[e] for e in raw_elements)
+
+        def bn(c):
+            return L.BatchNormLeakyReLU(c, momentum=bn_momentum, leakiness=leakiness, track_running_stats=track_running_stats)
+
+        self.layers_in_0 = Sequential(L.InputLayer(dimension, full_scale, mode=4))
+        self.layers_in = Sequential(L.InputLayer(dimension, full_scale, mode=4),
+                                    L.SubmanifoldConvolution(dimension, in_channels, nPlanesF[0], 3, False))
+        self.layers_out = Sequential(L.BatchNormReLU(nPlanesF[0], momentum=bn_momentum, track_running_stats=track_running_stats),
+                                     OutputLayer(dimension))
+        self.linear = nn.Linear(nPlanesF[0], 20)
+        self.voxel_scale = voxel_scale
+        self.rpn_map_sizes = np.array(rpn_map_sizes)
+        self.rpn_3d_2d_selector = rpn_3d_2d_selector
+
+        # z-collapsing convolutions that turn the 3-D rpn maps into 2-D ones (fpn_net.py:55-57)
+        self.convs_pro2d = nn.ModuleList()
+        for zsize in self.rpn_map_sizes[:, -1]:
+            self.convs_pro2d.append(L.Convolution(dimension, nPlaneM, nPlaneM, [1, 1, int(zsize)], [1, 1, 1], False))
+
+        def residual_or_vgg_block(m, a, b):  # fpn_net.py:60-76
+            if residual_blocks:
+                m.add(ConcatTable()
+                      .add(Identity() if a == b else L.NetworkInNetwork(a, b, False))
+                      .add(Sequential().add(bn(a)).add(L.SubmanifoldConvolution(dimension, a, b, 3, False))
+                           .add(bn(b)).add(L.SubmanifoldConvolution(dimension, b, b, 3, False)))
+                      ).add(AddTable())
+            else:
+                m.add(Sequential().add(bn(a)).add(L.SubmanifoldConvolution(dimension, a, b, 3, False)))
+            return {'kernel': [1, 1, 1], 'stride': [1, 1, 1]}
+
+        self.m_downs, self.m_shortcuts = nn.ModuleList(), nn.ModuleList()
+        self.operations_down = []
+        for k in range(n_scales):
+            m = Sequential()
+            if k > 0:  # fpn_net.py:77-84
+                m.add(Sequential().add(bn(nPlanesF[k - 1])).add(
+                    L.Convolution(dimension, nPlanesF[k - 1], nPlanesF[k], self.down_kernels[k - 1], self.down_strides[k - 1], False)))
+                self.operations_down.append({'kernel': self.down_kernels[k - 1], 'stride': self.down_strides[k - 1]})
+            for _ in range(reps):
+                op = residual_or_vgg_block(m, nPlanesF[k], nPlanesF[k])
+                if k == 0:
+                    self.operations_down.append(op)
+            self.m_downs.append(m)
+            self.m_shortcuts.append(L.SubmanifoldConvolution(dimension, nPlanesF[k], nPlaneM, 1, False))
+
+        self.m_ups, self.m_mergeds = nn.ModuleList(), nn.ModuleList()
+        self.operations_up = []
+        for k in range(n_scales - 1, 0, -1):  # fpn_net.py:86-93,119-126
+            self.m_ups.append(Sequential().add(bn(nPlaneM)).add(
+                L.Deconvolution(dimension, nPlaneM, nPlaneM, self.down_kernels[k - 1], self.down_strides[k - 1], False)))
+            self.operations_up.append({'kernel': self.down_kernels[k - 1], 'stride': self.down_strides[k - 1]})
+            self.m_mergeds.append(L.SubmanifoldConvolution(dimension, nPlaneM, nPlaneM, 3, False))
+
+    def forward(self, net0):
+        """net0 = [coords LongTensor [N,4], features float [N,C]] -> (rpn_maps, roi_maps)."""
+        return self.forward_fpn(self.layers_in(net0))
+
+    def forward_fpn(self, net):
+        n_scales = len(self.m_downs)
+        downs = []
+        for m in self.m_downs:
+            net = m(net)
+            downs.append(net)
+        net = self.m_shortcuts[-1](net)
+        ups = [net]
+        for k in range(n_scales - 1):
+            j = n_scales - 2 - k
+            net = self.m_ups[k](net)
+            net = add_feature_planes([net, self.m_shortcuts[j](downs[j])])
+            ups.append(self.m_mergeds[k](net))
+        rpn_maps_3d = [ups[i] for i in self.fpn_scales_from_top]
+        rpn_maps_2d = [self.convs_pro2d[i](rpn_maps_3d[i]) for i in range(len(rpn_maps_3d))]
+        rpn_maps = rpn_maps_3d + rpn_maps_2d
+        rpn_maps = [rpn_maps[i] for i in self.rpn_3d_2d_selector]
+        roi_maps = [ups[i] for i in self.roi_scales_from_top]
+        for i in range(len(rpn_maps_3d)):
+            assert torch.all(rpn_maps_3d[i].spatial_size == torch.tensor(self.rpn_map_sizes[i]))
+        return rpn_maps, roi_maps
+
+
+def sw4c_fpn432_config():
+    """configs/sw4c/sw4c_fpn432_bs1_lr5.yaml + maskrcnn_benchmark/config/defaults.py:44-53,173-175,225,283-284
+    as resolved by tools/train_net_sparse3d.py:231-318 (BASELINE.json configs 1-4)."""
+    planes = [32, 64, 64, 128, 128, 128, 256, 256, 256]
+    return dict(full_scale=[2048, 2048, 512], dimension=3, raw_elements=['xyz', 'color', 'normal'], reps=1, nPlanesF=planes, nPlaneM=128,
+                residual_blocks=True, fpn_scales_from_top=[4, 3, 2], roi_scales_from_top=[4, 3],
+                downsample=[[[2, 2, 2]] * 8, [[2, 2, 2]] * 8], rpn_map_sizes=[[128, 128, 32], [64, 64, 16], [32, 32, 8]],
+                rpn_3d_2d_selector=[1, 3, 4, 5], bn_momentum=0.9, track_running_stats=False)
+
+
+def c6_fpn4321_config():
+    """configs/6c/6c_Fpn4321_bs1_lr5.yaml (BASELINE.json config 5)."""
+    cfg = sw4c_fpn432_config()
+    cfg.update(full_scale=[4096, 4096, 512], fpn_scales_from_top=[4, 3, 2, 1],
+               rpn_map_sizes=[[256, 256, 32], [128, 128, 16], [64, 64, 8], [32, 32, 4]], rpn_3d_2d_selector=[1, 2, 3, 4, 5, 6])
+    return cfg

@@ -1,0 +1,237 @@
+"""Python face of the native boundary: the functions `sparseconvnet.SCN` exports in the reference
+(SCN/pybind.cpp:200-235), same names, argument order and empty-output-tensor convention, backed
+by the C-ABI in libscn_b200.so.  Dimension 3 / float32 only, CUDA tensors only.
+"""
+import ctypes as C
+
+import torch
+
+from .._lib import check, l3, lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f"{what}: expected a CUDA tensor (this extension has no CPU path)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{what}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{what}: tensor must be contiguous")
+    return C.c_void_p(t.data_ptr())
+
+
+def _opt(t, what):
+    return None if t is None or t.numel() == 0 else _dev_f32(t, what)
+
+
+class Metadata_3(object):
+    """Handle on a device-resident Metadata (reference: Metadata<3>, SCN/Metadata/Metadata.h:44)."""
+
+    def __init__(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("detection_3d_b200: no CUDA device (this extension has no CPU fallback)")
+        self._h = C.c_void_p()
+        check(lib().scn_metadata_create(C.byref(self._h), _stream()))
+        self._keep = []
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().scn_metadata_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    # ---- the methods pybind.cpp:12-32 exposes that the hot path uses
+    def getNActive(self, spatial_size):
+        n = C.c_long()
+        check(lib().scn_get_nactive(self._h, l3(spatial_size), C.byref(n)))
+        return n.value
+
+    def getSpatialLocations(self, spatial_size, device="cpu"):
+        """int64 [nActive, 4] (x, y, z, batch) in row order; the reference returns a CPU tensor."""
+        n = self.getNActive(spatial_size)
+        dev = torch.device(device)
+        out = torch.zeros((n, 4), dtype=torch.int64, device=dev)
+        if n:
+            check(lib().scn_get_spatial_locations(self._h, l3(spatial_size), C.c_void_p(out.data_ptr()), int(dev.type == "cuda")))
+        return out
+
+    # ---- parity / inspection helpers (no reference counterpart in pybind; rulebooks are public C++ members)
+    def iterationOrder(self, spatial_size):
+        n = self.getNActive(spatial_size)
+        out = torch.zeros(n, dtype=torch.int32)
+        check(lib().scn_iteration_order(self._h, l3(spatial_size), C.c_void_p(out.data_ptr())))
+        return out
+
+    def _rulebook(self, kind, a, b, c):
+        nl = C.c_int()
+        lens = (C.c_long * 128)()
+        check(lib().scn_rulebook_info(self._h, kind, a, b, c, C.byref(nl), lens))
+        out = []
+        for i in range(nl.value):
+            t = torch.zeros(lens[i], dtype=torch.int32)
+            if lens[i]:
+                check(lib().scn_rulebook_copy(self._h, kind, a, b, c, i, C.c_void_p(t.data_ptr())))
+            out.append(t)
+        return out
+
+    def inputLayerRuleBook(self):
+        z = l3([0, 0, 0])
+        return self._rulebook(0, z, z, z)
+
+    def submanifoldRuleBook(self, spatial_size, filter_size):
+        n = C.c_long()
+        check(lib().scn_submanifold_prepare(self._h, l3(spatial_size), l3(filter_size), C.byref(n)))
+        return [t.view(-1, 2) for t in self._rulebook(1, l3(spatial_size), l3(filter_size), l3([0, 0, 0]))]
+
+    def ruleBook(self, in_size, out_size, filter_size, filter_stride):
+        n, r = C.c_long(), C.c_long()
+        check(lib().scn_convolution_prepare(self._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), C.byref(n), C.byref(r)))
+        return [t.view(-1, 2) for t in self._rulebook(2, l3(in_size), l3(filter_size), l3(filter_stride))]
+
+
+def n_rulebook_bits():
+    return lib().scn_n_rulebook_bits()
+
+
+# ------------------------------------------------------------------ IO layers
+def InputLayer_updateOutput(m, spatial_size, coords, input_features, output_features, batch_size, mode):
+    """pybind.cpp:154-158.  coords: LongTensor [N, 3|4], CPU (as the reference requires) or CUDA."""
+    if coords.dtype != torch.int64 or coords.dim() != 2:
+        raise RuntimeError("InputLayer: coords must be a 2-d LongTensor")
+    coords = coords.contiguous()
+    m._keep.append(coords)
+    n_active, max_active = C.c_long(), C.c_int()
+    check(lib().scn_input_layer_build(m._h, l3(spatial_size), C.c_void_p(coords.data_ptr()), int(coords.is_cuda), coords.size(0),
+                                      coords.size(1), int(batch_size), int(mode), C.byref(n_active), C.byref(max_active)))
+    planes = input_features.size(1)
+    output_features.resize_(n_active.value, planes)
+    if n_active.value:
+        check(lib().scn_input_layer_forward(m._h, _dev_f32(input_features, "InputLayer features"), _dev_f32(output_features, "out"), planes))
+
+
+def InputLayer_updateGradInput(m, d_input_features, d_output_features):
+    """pybind.cpp:159-162"""
+    rules = m.inputLayerRuleBook()[0]
+    n_in, planes = int(rules[2]), d_output_features.size(1)
+    d_input_features.resize_(n_in, planes)
+    if n_in:
+        check(lib().scn_input_layer_backward(m._h, _dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"), planes))
+
+
+# ------------------------------------------------------------------ convolutions
+def _w3(weight):
+    # (K, groups=1, Cin, Cout)
+    if weight.dim() == 4 and weight.size(1) != 1:
+        raise RuntimeError("groups > 1 is not supported by this build")
+    return weight.size(0), weight.size(-2), weight.size(-1)
+
+
+def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_features, output_features, weight, bias):
+    """pybind.cpp:134-138 -> returns the multiply-add count like the reference."""
+    _, cin, cout = _w3(weight)
+    n = m.getNActive(spatial_size)
+    output_features.resize_(n, cout)
+    macs = C.c_double()
+    check(lib().scn_submanifold_convolution_forward(m._h, l3(spatial_size), l3(filter_size), _dev_f32(input_features, "in"),
+                                                    _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"),
+                                                    cin, cout, C.byref(macs)))
+    return macs.value
+
+
+def SubmanifoldConvolution_backward(spatial_size, filter_size, m, input_features, d_input_features, d_output_features, weight, d_weight, d_bias):
+    """pybind.cpp:139-143"""
+    _, cin, cout = _w3(weight)
+    d_input_features.resize_as_(input_features)
+    check(lib().scn_submanifold_convolution_backward(m._h, l3(spatial_size), l3(filter_size), _dev_f32(input_features, "in"),
+                                                     _dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"),
+                                                     _dev_f32(weight, "weight"), _dev_f32(d_weight, "d_weight"), _opt(d_bias, "d_bias"), cin, cout))
+
+
+def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, input_features, output_features, weight, bias):
+    """pybind.cpp:54-59"""
+    _, cin, cout = _w3(weight)
+    n, r = C.c_long(), C.c_long()
+    check(lib().scn_convolution_prepare(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), C.byref(n), C.byref(r)))
+    output_features.resize_(n.value, cout)
+    macs = C.c_double()
+    check(lib().scn_convolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
+                                        _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs)))
+    return macs.value
+
+
+def Convolution_backward(in_size, out_size, filter_size, filter_stride, m, input_features, d_input_features, d_output_features, weight, d_weight, d_bias):
+    """pybind.cpp:60-65"""
+    _, cin, cout = _w3(weight)
+    d_input_features.resize_as_(input_features)
+    check(lib().scn_convolution_backward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
+                                         _dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"), _dev_f32(weight, "weight"),
+                                         _dev_f32(d_weight, "d_weight"), _opt(d_bias, "d_bias"), cin, cout))
+
+
+def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, input_features, output_features, weight, bias):
+    """pybind.cpp:78-83"""
+    _, cin, cout = _w3(weight)
+    n = m.getNActive(out_size)
+    output_features.resize_(n, cout)
+    macs = C.c_double()
+    check(lib().scn_deconvolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
+                                          _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs)))
+    return macs.value
+
+
+def Deconvolution_backward(in_size, out_size, filter_size, filter_stride, m, input_features, d_input_features, d_output_features, weight, d_weight, d_bias):
+    """pybind.cpp:84-89"""
+    _, cin, cout = _w3(weight)
+    d_input_features.resize_as_(input_features)
+    check(lib().scn_deconvolution_backward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
+                                           _dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"), _dev_f32(weight, "weight"),
+                                           _dev_f32(d_weight, "d_weight"), _opt(d_bias, "d_bias"), cin, cout))
+
+
+# ------------------------------------------------------------------ batch norm
+def BatchNormalization_updateOutput(input_features, output_features, saveMean, saveInvStd, runningMean, runningVar, weight, bias, eps,
+                                    momentum, train, leakiness, instance_stats=False):
+    """pybind.cpp:219-220.  `instance_stats=True` is the eval / track_running_stats=False branch of
+    sparseconvnet/batchNormalization.py:51-56 with the mean / unbiased variance computed by the
+    kernel instead of by torch ops; runningMean / runningVar are then ignored."""
+    n, c = input_features.size(0), input_features.size(1) if input_features.dim() == 2 else 0
+    output_features.resize_as_(input_features)
+    saveMean.resize_(c)
+    saveInvStd.resize_(c)
+    mode = 0 if train else (2 if instance_stats else 1)
+    check(lib().scn_batchnorm_forward(_dev_f32(input_features, "in"), _dev_f32(output_features, "out"), n, c, _dev_f32(saveMean, "saveMean"),
+                                      _dev_f32(saveInvStd, "saveInvStd"), _opt(runningMean, "runningMean"), _opt(runningVar, "runningVar"),
+                                      _opt(weight, "weight"), _opt(bias, "bias"), float(eps), float(momentum), mode, float(leakiness), _stream()))
+
+
+def BatchNormalization_backward(input_features, d_input_features, output_features, d_output_features, saveMean, saveInvStd, runningMean,
+                                runningVar, weight, bias, d_weight, d_bias, leakiness):
+    """pybind.cpp:221"""
+    n, c = input_features.size(0), input_features.size(1)
+    d_input_features.resize_as_(input_features)
+    check(lib().scn_batchnorm_backward(_dev_f32(input_features, "in"), _dev_f32(d_input_features, "d_in"), _dev_f32(output_features, "out"),
+                                       _dev_f32(d_output_features, "d_out"), n, c, _dev_f32(saveMean, "saveMean"), _dev_f32(saveInvStd, "saveInvStd"),
+                                       _opt(weight, "weight"), _opt(d_weight, "d_weight"), _opt(d_bias, "d_bias"), float(leakiness), _stream()))
+
+
+def add_features(a, b):
+    """out = a + b for two feature matrices sharing one Metadata (tables.py:28-41, utils.py:61-66)."""
+    out = torch.empty_like(a)
+    if a.numel():
+        check(lib().scn_add_features(_dev_f32(a, "a"), _dev_f32(b, "b"), _dev_f32(out, "out"), a.numel(), _stream()))
+    return out
+
+
+def set_math_mode(mode):
+    """'fp32' (CUDA cores, exact), 'tf32' or 'bf16' (tcgen05 tensor cores, fp32 accumulate)."""
+    check(lib().scn_set_math_mode({"fp32": 0, "tf32": 1, "bf16": 2}[mode] if isinstance(mode, str) else int(mode)))
+
+
+def kernel_launch_count():
+    return lib().scn_kernel_launch_count()

@@ -48,5 +48,5 @@ def jittered_building(seed, jitter=0.15):
 
 
 def small_building(nx=40, ny=36, nz=12, n_walls=3, seed=0, batch_index=0):
-    """A miniature of the same shape for parity tests the CPU oracle finishes in seconds."""
+    """A miniature of the same shape for parity tests that a CPU checker finishes in seconds."""
     return building_coords(nx, ny, nz, n_walls, seed, batch_index)

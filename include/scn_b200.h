@@ -1,0 +1,132 @@
+/*
+ * scn_b200.h -- C ABI of the B200-native SparseConvNet backbone path.
+ *
+ * This is the drop-in boundary: every entry point replaces one operation of the reference's
+ * native extension `sparseconvnet.SCN` (pybind11; paths below are relative to
+ * /root/reference/SparseConvNet/sparseconvnet/SCN/).  Dimension is fixed to 3 (Metadata_3),
+ * dtype to float32 features / int32 rule indices, as on the reference's hot path
+ * (cuda.cu:52-72 instantiates <float> only; Metadata/32bits.h:11).
+ *
+ * Conventions
+ *  - all feature / weight / gradient pointers are DEVICE pointers (row-major float32);
+ *  - `stream` is a cudaStream_t passed as void*; everything is enqueued on it, nothing runs on the
+ *    legacy default stream and no blocking copy of rule tables ever happens (compare
+ *    CUDA/RuleBookIterator.h:15-32);
+ *  - spatial sizes / filter sizes / strides are `const long[3]` (the reference passes LongTensors);
+ *  - every function returns 0 on success, non-zero on failure with a message in scn_last_error()
+ *    (the reference raises C++ exceptions through pybind -> RuntimeError; the Python wrapper does
+ *    the same from the status code);
+ *  - two-phase sizing: the caller learns the number of output rows from scn_get_nactive /
+ *    scn_convolution_prepare, allocates, and passes the pointer (the reference resizes a caller
+ *    supplied empty tensor, e.g. CPU/Convolution.cpp:55);
+ *  - a scn_metadata is used from one thread / one stream at a time, like the reference's
+ *    Metadata (lazy caches are unguarded, Metadata.cpp:434-441).
+ */
+#ifndef SCN_B200_H
+#define SCN_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scn_metadata scn_metadata;
+
+const char *scn_last_error(void);
+int scn_version(void);
+
+/* n_rulebook_bits()  -- pybind.cpp:234 */
+int scn_n_rulebook_bits(void);
+
+/* Metadata_3() / destructor -- pybind.cpp:12-32, Metadata/Metadata.h:44-163 */
+int scn_metadata_create(scn_metadata **out, void *stream);
+void scn_metadata_destroy(scn_metadata *m);
+
+/* Metadata::inputLayer  (pybind InputLayer_updateOutput, pybind.cpp:154-158; Metadata.cpp:405-417;
+ * Metadata/IOLayersRules.h:18-125).  coords: int64 [nrows][ncols], ncols 3 or 4 (x,y,z[,batch]),
+ * host or device memory.  Builds the level-0 grid and the input rule table; returns the number
+ * of active voxels and the largest number of input rows merged into one voxel. */
+int scn_input_layer_build(scn_metadata *m, const long spatial_size[3], const long *coords, int coords_on_device,
+                          long nrows, int ncols, int batch_size, int mode, long *n_active, int *max_active);
+/* InputLayer_ForwardPass / InputLayer_fp  (CPU/IOLayers.cpp:11-29, CUDA/IOLayers.cu:31-41) */
+int scn_input_layer_forward(scn_metadata *m, const float *in_features, float *out_features, int n_planes);
+/* InputLayer_updateGradInput (pybind.cpp:159-162; CPU/IOLayers.cpp:30-47) */
+int scn_input_layer_backward(scn_metadata *m, float *d_in_features, const float *d_out_features, int n_planes);
+
+/* Metadata::getNActive (Metadata.cpp:67-69) */
+int scn_get_nactive(scn_metadata *m, const long spatial_size[3], long *n_active);
+/* Metadata::getSpatialLocations (pybind.cpp:17; Metadata.cpp:147-168): int64 [nActive][4] */
+int scn_get_spatial_locations(scn_metadata *m, const long spatial_size[3], long *out, int out_on_device);
+
+/* Metadata::getSubmanifoldRuleBook (Metadata.cpp:429-443): builds (once) and reports the total
+ * number of rules over all filter offsets. */
+int scn_submanifold_prepare(scn_metadata *m, const long spatial_size[3], const long filter_size[3], long *n_rules);
+/* Metadata::getRuleBook (Metadata.cpp:484-510): builds (once) the strided rulebook AND the output
+ * grid; reports the output grid's active count and the number of rules. */
+int scn_convolution_prepare(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
+                            const long filter_stride[3], long *n_active_out, long *n_rules);
+
+/* Rulebook access for parity checks (the reference keeps these as public members,
+ * Metadata/Metadata.h:56-67).  kind 0 = input-layer table, 1 = submanifold, 2 = strided.
+ * scn_rulebook_info fills n_lists and list_len[n_lists] (ints per list: 2*pairs; for kind 0:
+ * list 0 = {mode,maxActive,nIn,nOut}, list 1 = nOut*(1+maxActive)).  scn_rulebook_copy copies
+ * one list to HOST memory as the reference lays it out ((in,out) int32 pairs). */
+int scn_rulebook_info(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], int *n_lists, long *list_len);
+int scn_rulebook_copy(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], int list, int *dst);
+/* Reference hash-iteration order of a grid (ids in ascending dense_hash_map bucket order,
+ * batch items concatenated) -- host int32 [nActive]. */
+int scn_iteration_order(scn_metadata *m, const long spatial_size[3], int *dst);
+
+/* SubmanifoldConvolution_updateOutput (pybind.cpp:134-138; CPU/Convolution.cpp:117-150;
+ * CUDA/Convolution.cpp:95-125).  weight [K][Cin][Cout] (= (K,1,Cin,Cout) with groups 1),
+ * bias NULL or [Cout].  *macs = sum_k nRules_k*Cin*Cout, the value the reference returns. */
+int scn_submanifold_convolution_forward(scn_metadata *m, const long spatial_size[3], const long filter_size[3],
+                                        const float *in, float *out, const float *weight, const float *bias,
+                                        int n_in, int n_out, double *macs);
+/* Convolution_updateOutput (pybind.cpp:54-59; CPU/Convolution.cpp:45-79) */
+int scn_convolution_forward(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
+                            const long filter_stride[3], const float *in, float *out, const float *weight,
+                            const float *bias, int n_in, int n_out, double *macs);
+/* Deconvolution_updateOutput (pybind.cpp:78-83; CPU/Deconvolution.cpp:7-41): reuses the rulebook of the
+ * Convolution out_size -> in_size with the pair columns swapped. */
+int scn_deconvolution_forward(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
+                              const long filter_stride[3], const float *in, float *out, const float *weight,
+                              const float *bias, int n_in, int n_out, double *macs);
+
+/* *_backward (pybind.cpp:60-65,84-89,139-143; CPU/Convolution.cpp:81-115,152-185; CPU/Deconvolution.cpp:43-77):
+ * d_in [nIn rows][Cin] is overwritten, d_weight [K][Cin][Cout] is overwritten, d_bias NULL or [Cout]. */
+int scn_submanifold_convolution_backward(scn_metadata *m, const long spatial_size[3], const long filter_size[3],
+                                         const float *in, float *d_in, const float *d_out, const float *weight,
+                                         float *d_weight, float *d_bias, int n_in, int n_out);
+int scn_convolution_backward(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
+                             const long filter_stride[3], const float *in, float *d_in, const float *d_out,
+                             const float *weight, float *d_weight, float *d_bias, int n_in, int n_out);
+int scn_deconvolution_backward(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
+                               const long filter_stride[3], const float *in, float *d_in, const float *d_out,
+                               const float *weight, float *d_weight, float *d_bias, int n_in, int n_out);
+
+/* BatchNormalization_updateOutput (pybind.cpp:219-220; CPU/BatchNormalization.cpp:12-62).
+ * mode 0 = train, 1 = eval with the given running stats, 2 = eval with
+ * track_running_stats=False (batchNormalization.py:51-56: mean(0) / unbiased var(0) of this input).
+ * weight / bias may be NULL.  leakiness 0 = ReLU, 1 = no activation. */
+int scn_batchnorm_forward(const float *in, float *out, long n_rows, int n_planes, float *save_mean, float *save_invstd,
+                          float *running_mean, float *running_var, const float *weight, const float *bias, float eps,
+                          float momentum, int mode, float leakiness, void *stream);
+/* BatchNormalization_backward (pybind.cpp:221; CPU/BatchNormalization.cpp:64-107); d_out is rewritten in place. */
+int scn_batchnorm_backward(const float *in, float *d_in, const float *out, float *d_out, long n_rows, int n_planes,
+                           const float *save_mean, const float *save_invstd, const float *weight, float *d_weight,
+                           float *d_bias, float leakiness, void *stream);
+
+/* AddTable / add_feature_planes (sparseconvnet/tables.py:28-41, utils.py:61-66): out = a + b */
+int scn_add_features(const float *a, const float *b, float *out, long n_elements, void *stream);
+
+/* Selects the arithmetic of the gather-GEMM kernels for this process: 0 = fp32 CUDA cores
+ * (exact-fp32 anchor), 1 = tcgen05 tensor cores, TF32 inputs / fp32 accumulate (default where the
+ * channel counts allow), 2 = tcgen05 BF16 inputs / fp32 accumulate. */
+int scn_set_math_mode(int mode);
+int scn_get_math_mode(void);
+/* number of kernels this library has launched since load (for bench.py's gpu_launches) */
+long scn_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

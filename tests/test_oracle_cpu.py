@@ -1,0 +1,212 @@
+"""CPU suite (no GPU): the oracle against the golden vectors generated from the reference itself,
+the host-side logic, and the C-ABI surface."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fpn_util
+from detection_3d_b200 import synthetic
+from oracle import fpn_oracle, ref_python
+from oracle import scn_oracle as so
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+ROOT = os.path.dirname(HERE)
+
+
+def test_hash_known_answers():
+    g = np.load(os.path.join(GOLD, "rulebook_small.npz"))
+    for (x, y, z), want in zip(g["hash_points"], g["hash_values"]):
+        assert so.point_hash(int(x), int(y), int(z)) & 0xffffffff == int(want)
+    # SURVEY.md A.4 (values recomputed from SCN/Metadata/32bits.h:57-66)
+    assert so.point_hash(0, 0, 0) & 0xffffffff == 0x482c8e87
+    assert so.point_hash(541, 541, 67) & 0xffffffff == 0xc46ab370
+    assert so.point_hash(-1, 0, 0) & 0xffffffff == 0x498037e0
+
+
+def test_small_rulebook_matches_reference_dump():
+    g = np.load(os.path.join(GOLD, "rulebook_small.npz"))
+    md = so.OracleMetadata()
+    assert md.input_layer([8, 8, 8], g["coords"], 0, 4) == 6
+    hdr, tab = md.input_rules()
+    assert hdr.tolist() == g["input0"].tolist() == [4, 2, 7, 6]
+    assert np.array_equal(tab, g["input1"])
+    assert np.array_equal(md.iteration_order([8, 8, 8], 0), g["iter"])
+    for k, r in enumerate(md.submanifold_rules([8, 8, 8], [3, 3, 3])):
+        assert np.array_equal(r, g[f"subm{k}"]), k
+    for k, r in enumerate(md.conv_rules([8, 8, 8], [4, 4, 4], [2, 2, 2], [2, 2, 2])):
+        assert np.array_equal(r, g[f"conv{k}"]), k
+    assert np.array_equal(md.spatial_locations([4, 4, 4]), g["loc4"])
+    for k, r in enumerate(md.conv_rules([4, 4, 4], [4, 4, 1], [1, 1, 4], [1, 1, 1])):
+        assert np.array_equal(r, g[f"pro{k}"]), k
+
+
+@pytest.mark.parametrize("name,bld,full,nl,pro", [
+    ("mini4", dict(nx=60, ny=56, nz=24, n_walls=3, seed=3), [64, 64, 32], 4, (1, 2)),
+    ("sw4c_mid", dict(nx=300, ny=280, nz=40, n_walls=5, seed=5), [2048, 2048, 512], 9, (4, 5, 6)),
+    ("b470", dict(), [2048, 2048, 512], 9, (4, 5, 6)),
+])
+def test_rulebook_digests_match_reference(name, bld, full, nl, pro):
+    gold = json.load(open(os.path.join(GOLD, "rulebooks.json")))[name]
+    coords = synthetic.building_coords(**bld)
+    assert coords.shape[0] == gold["n_input_rows"]
+    md = so.OracleMetadata()
+    md.input_layer(full, coords, 0, 4)
+    got = fpn_util.metadata_digests(md, full, nl, pro)
+    got["input_rules"] = fpn_util.rulebook_digest(md.input_rules())
+    got["n_input_rows"] = int(coords.shape[0])
+    assert got == gold
+
+
+def test_b470_level_counts():
+    # BASELINE.md / SURVEY.md section 8: per-level active sites of the benchmark building
+    gold = json.load(open(os.path.join(GOLD, "rulebooks.json")))["b470"]
+    assert [gold[f"n{l}"] for l in range(9)] == [1155656, 283586, 68672, 16416, 3752, 786, 162, 25, 9]
+    assert gold["n_input_rows"] == 1177224
+
+
+@pytest.mark.parametrize("name,cfgf,bld", [
+    ("mini4", fpn_util.mini4_config, dict(nx=60, ny=56, nz=24, n_walls=3, seed=3)),
+])
+def test_port_fpn_forward_matches_reference_golden(name, cfgf, bld):
+    import detection_3d_b200.sparseconvnet.fpn as fpn
+    cfg = cfgf()
+    g = np.load(os.path.join(GOLD, f"fpn_{name}.npz"))
+    net = fpn.FPN_Net(**cfg)
+    state = fpn_util.deterministic_state(net, seed=1)
+    coords = synthetic.building_coords(**bld)
+    rpn, roi, macs = fpn_oracle.run_fpn_port(cfg, state, coords, fpn_util.features_for(coords))
+    assert macs == float(g["macs"])
+    for tag, maps in (("rpn", rpn), ("roi", roi)):
+        assert len(maps) == int(g[f"n_{tag}"])
+        for i, m in enumerate(maps):
+            assert np.array_equal(m["locations"], g[f"{tag}{i}_locations"])
+            ref = g[f"{tag}{i}_features"]
+            # fp32 tolerance: naive C dot products vs the reference's sgemm
+            np.testing.assert_allclose(m["features"], ref, rtol=2e-4, atol=2e-5 * np.abs(ref).max())
+
+
+def test_state_dict_layout_matches_reference_checkpoint_format():
+    import detection_3d_b200.sparseconvnet as scn
+    net = scn.FPN_Net(**scn.sw4c_fpn432_config())
+    sd = net.state_dict()
+    assert len(sd) == 197 and sum(p.numel() for p in net.parameters()) == 21147124
+    # a few keys / shapes read off the reference module tree (fpn_net.py:40-135)
+    assert tuple(sd["layers_in.1.weight"].shape) == (27, 1, 9, 32)
+    assert tuple(sd["convs_pro2d.0.weight"].shape) == (32, 1, 128, 128)
+    assert tuple(sd["m_downs.1.0.1.weight"].shape) == (8, 1, 32, 64)
+    assert tuple(sd["m_downs.0.0.1.3.weight"].shape) == (27, 1, 32, 32)
+    assert tuple(sd["m_ups.7.1.weight"].shape) == (8, 1, 128, 128)
+    assert tuple(sd["m_shortcuts.8.weight"].shape) == (1, 1, 256, 128)
+    if ref_python.available():
+        ref = ref_python.load_reference_package()
+        args, kw = fpn_util.ref_ctor_args(scn.sw4c_fpn432_config())
+        rsd = ref.FPN_Net(*args, **kw).state_dict()
+        assert list(rsd.keys()) == list(sd.keys())
+        assert all(tuple(rsd[k].shape) == tuple(sd[k].shape) for k in sd)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "scn_b200.h")).read()
+    declared = set(re.findall(r"\b(scn_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    so_path = os.path.join(ROOT, "detection_3d_b200", "libscn_b200.so")
+    assert os.path.exists(so_path), "run __graft_entry__.build() first"
+    handle = ctypes.CDLL(so_path)
+    missing = [s for s in declared if not hasattr(handle, s)]
+    assert not missing, missing
+    from detection_3d_b200 import _lib
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    assert handle.scn_n_rulebook_bits() == 32
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import detection_3d_b200.sparseconvnet as scn
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+        scn.Metadata(3)
+    net = scn.FPN_Net(**fpn_util.mini4_config())
+    c = torch.zeros(4, 4, dtype=torch.int64)
+    with pytest.raises(RuntimeError):
+        net([c, torch.zeros(4, 9)])
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "detection_3d_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert not re.search(r"(import|from)\s+oracle|oracle[./](scn_oracle|_ref|_build)|liboracle", txt), os.path.join(dp, f)
+
+
+@pytest.mark.skipif(not (so.have_ref() and ref_python.available()), reason="reference build only exists in the build container")
+class TestAgainstCompiledReference:
+    """Pins the C restatement (and the restated layer sequence) against the reference's own code."""
+
+    @pytest.mark.parametrize("seed", range(6))
+    def test_random_rulebooks(self, seed):
+        rs = np.random.RandomState(seed)
+        ext = [rs.randint(6, 40) for _ in range(3)]
+        n = rs.randint(1, 4000)
+        c = np.stack([rs.randint(0, e, n) for e in ext], 1).astype(np.int64)
+        bs = rs.randint(1, 4)
+        if seed % 2:
+            c = np.concatenate([c, np.sort(rs.randint(0, bs, (n, 1)), 0)], 1)
+        full = [64, 64, 64]
+        mode = [4, 3, 4, 1, 2, 4][seed]
+        O, R = so.OracleMetadata(), so.RefMetadata()
+        hint = bs if seed % 2 else 0
+        assert O.input_layer(full, c, hint, mode) == R.input_layer(full, c, hint, mode)
+        for a, b in zip(O.input_rules(), R.input_rules()):
+            assert np.array_equal(a, b)
+        d1 = fpn_util.metadata_digests(O, full, 4, (1, 2))
+        d2 = fpn_util.metadata_digests(R, full, 4, (1, 2))
+        assert d1 == d2
+        for f, s in (([3, 3, 3], [2, 2, 2]), ([4, 4, 4], [2, 2, 2]), ([3, 1, 2], [2, 1, 2])):
+            O2, R2 = so.OracleMetadata(), so.RefMetadata()
+            O2.input_layer(full, c, hint, 4), R2.input_layer(full, c, hint, 4)
+            out = [(full[d] - f[d]) // s[d] + 1 for d in range(3)]
+            for a, b in zip(O2.conv_rules(full, out, f, s), R2.conv_rules(full, out, f, s)):
+                assert np.array_equal(a, b)
+            assert np.array_equal(O2.spatial_locations(out), R2.spatial_locations(out))
+
+    def test_ref_driver_reproduces_reference_fpn_bitwise(self):
+        import detection_3d_b200.sparseconvnet.fpn as fpn
+        cfg = fpn_util.mini4_config()
+        g = np.load(os.path.join(GOLD, "fpn_mini4.npz"))
+        state = fpn_util.deterministic_state(fpn.FPN_Net(**cfg), seed=1)
+        coords = synthetic.building_coords(nx=60, ny=56, nz=24, n_walls=3, seed=3)
+        rpn, roi, macs = fpn_oracle.run_fpn_ref(cfg, state, coords, fpn_util.features_for(coords))
+        assert macs == float(g["macs"])
+        for tag, maps in (("rpn", rpn), ("roi", roi)):
+            for i, m in enumerate(maps):
+                assert np.array_equal(m["features"], g[f"{tag}{i}_features"])
+                assert np.array_equal(m["locations"], g[f"{tag}{i}_locations"])
+
+    def test_compute_kernels_of_port_vs_reference_extension(self):
+        import torch
+        SCN = ref_python.load_scn_native()
+        rs = np.random.RandomState(0)
+        x = rs.randn(500, 24).astype(np.float32)
+        gam, bet = (1 + 0.1 * rs.randn(24)).astype(np.float32), (0.1 * rs.randn(24)).astype(np.float32)
+        rm, rv = np.zeros(24, np.float32), np.ones(24, np.float32)
+        out, sm, si = so.o_bn_forward(x, gam, bet, rm, rv, 1e-4, 0.9, True, 0.0)
+        t = torch.from_numpy
+        o2, sm2, si2, rm2, rv2 = torch.empty(0), torch.empty(24), torch.empty(24), torch.zeros(24), torch.ones(24)
+        SCN.BatchNormalization_updateOutput(t(x), o2, sm2, si2, rm2, rv2, t(gam), t(bet), 1e-4, 0.9, True, 0.0)
+        np.testing.assert_allclose(out, o2.numpy(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rv, rv2.numpy(), rtol=1e-5)
+        dy = rs.randn(500, 24).astype(np.float32)
+        din, dw, db = so.o_bn_backward(x, out, dy, sm, si, gam, 0.0)
+        din2, dw2, db2 = torch.empty(0), torch.zeros(24), torch.zeros(24)
+        SCN.BatchNormalization_backward(t(x), din2, o2, t(dy.copy()), sm2, si2, rm2, rv2, t(gam), t(bet), dw2, db2, 0.0)
+        np.testing.assert_allclose(din, din2.numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(dw, dw2.numpy(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(db, db2.numpy(), rtol=1e-4, atol=1e-4)
