@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Benchmark of the Detection_3D sparse backbone path (BASELINE.json north_star).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math tf32|bf16|fp32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one `FPN_Net.forward` of the sw_4c_fpn432 backbone (BASELINE.json configs[1]) on the
+synthetic 470 m^2 building "B470" (1,177,224 input rows / 1,155,656 active voxels), INCLUDING the
+Metadata / rulebook build, which the reference redoes every forward (sparseconvnet/ioLayers.py:52-55).
+Prints ONE JSON line (rank 0).  `value`: inputs resident in HBM.  `e2e`: same metric through the
+public API with HOST (pinned) coords + features, H2D and D2H copies inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+B470_VOXELS = 1155656
+B470_GMAC = 334.126  # reference's own forward_pass_multiplyAdd_count for B470
+# dominant kernel: m_mergeds.7 = SubmanifoldConvolution 128->128, 3^3, on level 0 (10,715,792 rules)
+DOM_RULES, DOM_C = 10715792, 128
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        smax = next((float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()), None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_forward(coords, feats, cfg, state):
+    """One backbone forward on the host cores with the reference's own CPU code (oracle/_ref) when
+    it was built, else with our C port of it.  Returns (seconds, macs, kind, threads)."""
+    import torch
+    from oracle import fpn_oracle, ref_python
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "SCN.so"))
+    fn = fpn_oracle.run_fpn_ref if have_ref else fpn_oracle.run_fpn_port
+    t0 = time.perf_counter()
+    _, _, macs = fn(cfg, state, coords, feats)
+    return time.perf_counter() - t0, macs, ("reference" if have_ref else "port"), threads
+
+
+def make_model(cfg, device):
+    import torch
+    import fpn_util
+    import detection_3d_b200.sparseconvnet as scn
+    torch.manual_seed(0)
+    net = scn.FPN_Net(**cfg)
+    state = fpn_util.deterministic_state(net, seed=1)
+    net.load_state_dict(state)
+    return net.to(device).eval(), state
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import numpy as np
+    import fpn_util
+    import detection_3d_b200.sparseconvnet.fpn as fpn
+    from detection_3d_b200 import synthetic
+    cfg = fpn.sw4c_fpn432_config()
+    import torch
+    net = fpn.FPN_Net(**cfg)
+    state = fpn_util.deterministic_state(net, seed=1)
+    # calibrate on a small crop, then size the per-step sample so the whole run stays within ~4 minutes
+    cal = synthetic.building_coords(nx=136, ny=136, nz=68)
+    tcal, _, kind, threads = cpu_reference_forward(cal, fpn_util.features_for(cal), cfg, state)
+    ncal = np.unique(cal[:, :3], axis=0).shape[0]
+    budget = 200.0 / max(1, args.steps + args.warmup)
+    frac = min(1.0, max(0.02, budget / (tcal * B470_VOXELS / ncal)))
+    nx = max(64, int(542 * frac ** 0.5))
+    coords = synthetic.building_coords(nx=nx, ny=nx, nz=68) if frac < 1.0 else synthetic.building_coords()
+    feats = fpn_util.features_for(coords)
+    nvox = np.unique(coords[:, :3], axis=0).shape[0]
+    times, macs = [], 0.0
+    for i in range(args.warmup + args.steps):
+        t, macs, kind, threads = cpu_reference_forward(coords, feats, cfg, state)
+        if i >= args.warmup:
+            times.append(t)
+    step = sum(times) / len(times)
+    value = (nvox / B470_VOXELS) / step  # B470-equivalent buildings per second
+    sample = f"{nx}x{nx}x68 crop of B470 ({nvox} active voxels = {nvox / B470_VOXELS:.3f} building, {macs / 1e9:.1f} GMAC) per step; value scaled by voxel count"
+    line = {
+        "impl": "reference", "metric": "backbone_buildings_per_s", "value": value, "unit": "buildings/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": "sw_4c_fpn432 backbone forward incl. rulebook build, B470 synthetic building (bounded sample, see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": value, "unit": "buildings/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "buildings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "tflops": 2 * macs / step / 1e12, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--math", default=os.environ.get("SCN_MATH", "auto"), choices=["auto", "fp32", "tf32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import fpn_util
+    import detection_3d_b200.sparseconvnet as scn
+    from detection_3d_b200 import synthetic
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    math = args.math
+    if math == "auto":
+        math = "tf32" if scn.SCN.lib().scn_tensor_core_path_available() else "fp32"
+    scn.set_math_mode(math)
+
+    cfg = scn.sw4c_fpn432_config()
+    net, state = make_model(cfg, dev)
+    coords_np = synthetic.building_coords()  # B470
+    feats_np = fpn_util.features_for(coords_np)
+    coords_dev = torch.from_numpy(coords_np).to(dev)
+    feats_dev = torch.from_numpy(feats_np).to(dev)
+    coords_pin = torch.from_numpy(coords_np).pin_memory()
+    feats_pin = torch.from_numpy(feats_np).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        with torch.no_grad():
+            return net([coords_dev, feats_dev])
+
+    def step_e2e():
+        with torch.no_grad():
+            c = coords_pin.to(dev, non_blocking=True)
+            f = feats_pin.to(dev, non_blocking=True)
+            rpn, roi = net([c, f])
+            host = [m.features.to("cpu", non_blocking=True) for m in rpn + roi]
+        return host
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        l0 = scn.kernel_launch_count()
+        for a, b in ev:
+            flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        launches = scn.kernel_launch_count() - l0
+        if world > 1:
+            dist.barrier()
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), launches
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    scn.forward_pass_multiplyAdd_count = 0
+    total_ms, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop()
+    macs_per_step = scn.forward_pass_multiplyAdd_count / (args.steps + args.warmup)
+    e2e_ms, _ = timed(step_e2e, args.steps, 1)
+    ms_step = total_ms / args.steps
+    value = world * 1e3 / ms_step
+    d2h = 0
+    with torch.no_grad():
+        rpn, roi = net([coords_dev, feats_dev])
+        d2h = sum(m.features.numel() * 4 for m in rpn + roi)
+
+    # roofline of the dominant kernel, timed alone on the launching stream
+    pk = peaks()
+    roof = dominant_kernel_roofline(scn, torch, dev, coords_dev, flush, pk, math)
+
+    line = {
+        "metric": "backbone_buildings_per_s", "value": value, "unit": "buildings/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[math], "data": "synthetic",
+        "config": {"workload": "sw_4c_fpn432 backbone forward incl. Metadata/rulebook build, one B470 synthetic building (1,155,656 active voxels) per GPU per step",
+                   "l2": "256 MiB L2 flush between timed iterations", "parallelism": f"replicas x{world}, no collective"},
+        "tflops": value * 2 * macs_per_step / 1e12, "gmac_per_step": macs_per_step / 1e9,
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": world * 1e3 / (e2e_ms / args.steps), "unit": "buildings/s", "h2d_bytes_per_step": coords_np.nbytes + feats_np.nbytes, "d2h_bytes_per_step": d2h},
+        "roofline": roof,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        nx = 271  # quarter-footprint crop keeps the CPU leg at ~10 s
+        cc = synthetic.building_coords(nx=nx, ny=nx, nz=68)
+        t, macs, kind, threads = cpu_reference_forward(cc, fpn_util.features_for(cc), cfg, state)
+        nv = np.unique(cc[:, :3], axis=0).shape[0]
+        line["cpu_baseline"] = {"value": (nv / B470_VOXELS) / t, "unit": "buildings/s", "cores": threads, "kind": kind,
+                                "sample": f"one forward of a {nx}x{nx}x68 crop of B470 ({nv} voxels = {nv / B470_VOXELS:.3f} building, {macs / 1e9:.1f} GMAC) in {t:.1f} s, scaled by voxel count"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(scn, torch, dev, coords_dev, flush, pk, math):
+    """m_mergeds.7: SubmanifoldConvolution 128->128 3^3 on level 0 -- 175.6 of the 334.1 GMAC."""
+    L = torch.LongTensor
+    md = scn.Metadata(3)
+    x0 = torch.empty(0, device=dev)
+    scn.SCN.InputLayer_updateOutput(md, L([2048, 2048, 512]), coords_dev, torch.zeros(coords_dev.size(0), 1, device=dev), x0, 0, 4)
+    n = md.getNActive(L([2048, 2048, 512]))
+    x = torch.randn(n, DOM_C, device=dev)
+    w = torch.randn(27, 1, DOM_C, DOM_C, device=dev) * 0.02
+    out = torch.empty(0, device=dev)
+    fwd = lambda: scn.SCN.SubmanifoldConvolution_updateOutput(L([2048, 2048, 512]), L([3, 3, 3]), md, x, out, w, torch.Tensor())
+    macs = fwd()
+    for _ in range(2):
+        fwd()
+    ts = []
+    for _ in range(5):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fwd(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sorted(ts)[len(ts) // 2]
+    achieved = 2 * macs / (ms * 1e-3) / 1e12
+    return {"kernel": "conv_plan (SubmanifoldConvolution 128->128 3^3, level 0)", "bound": "tensor", "achieved": achieved, "peak": pk["tc_burst"],
+            "unit": "TFLOP/s", "frac": achieved / pk["tc_burst"], "peak_source": pk["src"] + " bf16 burst", "ms_per_launch": ms,
+            "algorithmic_flops": 2 * macs, "traffic": None}
+
+
+if __name__ == "__main__":
+    main()

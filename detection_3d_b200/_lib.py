@@ -42,6 +42,7 @@ SYMBOLS = {
     "scn_add_features": (_i, [_vp, _vp, _vp, _l, _vp]),
     "scn_set_math_mode": (_i, [_i]),
     "scn_get_math_mode": (_i, []),
+    "scn_tensor_core_path_available": (_i, []),
     "scn_kernel_launch_count": (_l, []),
 }
 

@@ -50,6 +50,7 @@ int scn_set_math_mode(int mode) {
   return 0;
 }
 int scn_get_math_mode(void) { return scn::g_math_mode; }
+int scn_tensor_core_path_available(void) { return scn::tc_available(); }
 
 int scn_metadata_create(scn_metadata **out, void *stream) {
   int ndev = 0;

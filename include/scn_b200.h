@@ -123,6 +123,8 @@ int scn_add_features(const float *a, const float *b, float *out, long n_elements
  * channel counts allow), 2 = tcgen05 BF16 inputs / fp32 accumulate. */
 int scn_set_math_mode(int mode);
 int scn_get_math_mode(void);
+/* 1 when the tcgen05 kernels are compiled in and the device is sm_100 */
+int scn_tensor_core_path_available(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 long scn_kernel_launch_count(void);
 
