@@ -20,8 +20,8 @@ int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s);
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
                        const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s);
 int tc_available();
-int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, int nOut, int K, int Cin, int Cout,
-                        const float *bias, int mathMode, cudaStream_t s);
+int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
+                        int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s);
 static int g_math_mode = 0;
 } // namespace scn
 
@@ -186,8 +186,8 @@ int scn_iteration_order(scn_metadata *m, const long sz[3], int *dst) {
 }
 
 static int run_plan(Metadata &M, const scn::NbrPlan &plan, const float *in, float *out, const float *w, const float *bias, int Cin, int Cout) {
-  if (scn::g_math_mode != 0 && scn::tc_available() && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32 && Cout <= 256)
-    return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.stream);
+  if (scn::g_math_mode != 0 && scn::tc_available() && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32 && Cout <= 256 && plan.K <= 32)
+    return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.tileMask, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.stream);
   return scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.stream);
 }
 

@@ -1,10 +1,346 @@
-// tcgen05 tensor-core gather-GEMM (placeholder until the kernel lands; the dispatcher in capi.cu
-// only routes here when tc_available() says so).
+// tcgen05 tensor-core gather-GEMM for sm_100a: the output-stationary sparse convolution
+//   out[row(p)] = sum_k  in[nbr[p][k]] @ W[k]
+// with fp32 accumulators in TMEM across ALL filter offsets (one store per output element, no
+// read-modify-write, no atomics), A rows gathered with 16-byte cp.async into 128B-swizzled
+// shared memory, W[k] streamed with cp.async.bulk from a pre-swizzled image, MMAs issued by one
+// thread (tcgen05.mma kind::tf32, M=128, N=Cout, K=8).
+//
+// Persistent kernel, one CTA per SM, warp-specialised:
+//   warps 0-3  epilogue   (tcgen05.ld -> registers -> global rows; warp w owns TMEM lanes 32w..)
+//   warps 4-7  A producer (gather rows; 8 threads per 128-byte row chunk, coalesced)
+//   warp  8    MMA issuer (lane 0) + TMEM allocation
+//   warp  9    B loader   (lane 0, bulk copies)
+// A CTA owns a "supertile" of T = min(4, 512/Cout) tiles of 128 output sites whose accumulators
+// live in TMEM simultaneously, so each weight slice W[k][32 channels] is fetched once per
+// supertile instead of once per tile (L2 -> SM traffic of B is 1/T of A's).
+//
+// Replaces dConvolution_KMxKN_forwardA/B (SCN/CUDA/Convolution.cu:57-203: SIMT tiles, fp64
+// accumulators, one launch + one blocking H2D rule copy per filter offset).
 #include "common.cuh"
+
 namespace scn {
-int tc_available() { return 0; }
-int launch_conv_plan_tc(const float *, float *, const float *, const int *, const int *, int, int, int, int, const float *, int, cudaStream_t) {
-  set_error("tcgen05 path not built");
-  return -4;
+
+constexpr int kTileM = 128;
+constexpr int kAStageBytes = kTileM * 128; // 128 rows x 32 tf32
+constexpr int kInflight = 3;               // A stages a producer thread keeps in flight
+constexpr int kThreads = 320;
+
+struct TcParams {
+  const float *in;
+  float *out;
+  const float *wimg;
+  const float *bias;
+  const int *nbr;
+  const int *outRow;
+  const unsigned long long *tileMask;
+  int nOut, K, Cin, Cout, nTiles, T, nSuper, SA, SB;
+};
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t srcBytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(srcBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t dTmem, uint64_t aDesc, uint64_t bDesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(dTmem),
+      "l"(aDesc), "l"(bDesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+        "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nc = P.Cin / 32;                 // K-atoms per filter offset
+  const int bStageBytes = P.Cout * 128;      // Cout rows x 32 tf32
+  unsigned char *sA = smem;
+  unsigned char *sB = sA + (size_t)P.SA * kAStageBytes;
+  int *sIds = reinterpret_cast<int *>(sB + (size_t)P.SB * bStageBytes);
+  unsigned long long *sMask = reinterpret_cast<unsigned long long *>(sIds + (size_t)P.T * kTileM * P.K);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sMask + 8);
+  // barrier indices
+  uint64_t *aFull = bars, *aEmpty = bars + P.SA, *bFull = bars + 2 * P.SA, *bEmpty = bars + 2 * P.SA + P.SB;
+  uint64_t *accFull = bars + 2 * P.SA + 2 * P.SB, *accEmpty = accFull + 1;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 1);
+
+  if (tid == 0) {
+    for (int i = 0; i < P.SA; i++) { mbar_init(smem_u32(aFull + i), 128); mbar_init(smem_u32(aEmpty + i), 1); }
+    for (int i = 0; i < P.SB; i++) { mbar_init(smem_u32(bFull + i), 1); mbar_init(smem_u32(bEmpty + i), 1); }
+    mbar_init(smem_u32(accFull), 1);
+    mbar_init(smem_u32(accEmpty), 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemBase = *tmemSlot;
+
+  if (warp < 4) {
+    // ============================ epilogue ============================
+    uint32_t phase = 0;
+    for (int st = blockIdx.x; st < P.nSuper; st += gridDim.x, phase ^= 1) {
+      mbar_wait(smem_u32(accFull), phase);
+      tc_fence_after();
+      for (int t = 0; t < P.T; t++) {
+        const int tile = st * P.T + t;
+        if (tile >= P.nTiles) break;
+        const int p = tile * kTileM + warp * 32 + lane;
+        const bool valid = p < P.nOut;
+        const bool started = __ldg(P.tileMask + tile) != 0ull;
+        float *dst = valid ? P.out + (size_t)__ldg(P.outRow + p) * P.Cout : nullptr;
+        for (int c0 = 0; c0 < P.Cout; c0 += 32) {
+          uint32_t v[32];
+          if (started) {
+            tmem_ld32(tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * P.Cout + c0), v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = 0u;
+          }
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              if (P.bias) {
+                o.x += __ldg(P.bias + c0 + j); o.y += __ldg(P.bias + c0 + j + 1); o.z += __ldg(P.bias + c0 + j + 2); o.w += __ldg(P.bias + c0 + j + 3);
+              }
+              *reinterpret_cast<float4 *>(dst + c0 + j) = o;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(accEmpty));
+    }
+  } else if (warp < 8) {
+    // ============================ A producer ============================
+    const int ptid = tid - 128;
+    const int rowGroup = ptid >> 3, chunk = ptid & 7;
+    uint32_t stage = 0, phase = 0;
+    for (int st = blockIdx.x; st < P.nSuper; st += gridDim.x) {
+      // neighbour ids of the whole supertile -> shared memory (contiguous in global memory)
+      asm volatile("bar.sync 1, 128;" ::: "memory"); // every producer is done with the previous ids
+      const long base = (long)st * P.T * kTileM * P.K;
+      const long limit = (long)P.nOut * P.K;
+      const int total = P.T * kTileM * P.K;
+      for (int i = ptid; i < total; i += 128) sIds[i] = (base + i < limit) ? __ldg(P.nbr + base + i) : -1;
+      if (ptid < P.T) sMask[ptid] = (st * P.T + ptid < P.nTiles) ? __ldg(P.tileMask + st * P.T + ptid) : 0ull;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      unsigned long long m[4], uni = 0;
+      for (int t = 0; t < 4; t++) { m[t] = t < P.T ? sMask[t] : 0ull; uni |= m[t]; }
+      int pending = 0;           // stages committed but not yet published
+      uint32_t pubStage = stage; // oldest unpublished stage
+      for (int k = 0; k < P.K; k++) {
+        if (!((uni >> k) & 1ull)) continue;
+        for (int c = 0; c < nc; c++) {
+          for (int t = 0; t < P.T; t++) {
+            if (!((m[t] >> k) & 1ull)) continue;
+            mbar_wait(smem_u32(aEmpty + stage), phase ^ 1);
+            const uint32_t sbase = smem_u32(sA + (size_t)stage * kAStageBytes);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int row = i * 16 + rowGroup;
+              const int id = sIds[(t * kTileM + row) * P.K + k];
+              const float *src = P.in + (size_t)(id >= 0 ? id : 0) * P.Cin + c * 32 + chunk * 4;
+              cp_async16(sbase + row * 128 + ((chunk ^ (row & 7)) << 4), src, id >= 0 ? 16u : 0u);
+            }
+            cp_async_commit();
+            if (++stage == (uint32_t)P.SA) { stage = 0; phase ^= 1; }
+            if (++pending == kInflight) {
+              cp_async_wait<kInflight - 1>();
+              fence_proxy_async();
+              mbar_arrive(smem_u32(aFull + pubStage));
+              if (++pubStage == (uint32_t)P.SA) pubStage = 0;
+              pending--;
+            }
+          }
+        }
+      }
+      // drain: publish the last stages of this supertile
+      cp_async_wait<0>();
+      fence_proxy_async();
+      while (pending > 0) {
+        mbar_arrive(smem_u32(aFull + pubStage));
+        if (++pubStage == (uint32_t)P.SA) pubStage = 0;
+        pending--;
+      }
+    }
+  } else if (warp == 8) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=TF32, K-major both, N=Cout, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.Cout >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      uint32_t aStage = 0, aPhase = 0, bStage = 0, bPhase = 0, accPhase = 0;
+      for (int st = blockIdx.x; st < P.nSuper; st += gridDim.x, accPhase ^= 1) {
+        unsigned long long m[4], uni = 0;
+        for (int t = 0; t < 4; t++) { m[t] = (t < P.T && st * P.T + t < P.nTiles) ? __ldg(P.tileMask + st * P.T + t) : 0ull; uni |= m[t]; }
+        mbar_wait(smem_u32(accEmpty), accPhase ^ 1); // epilogue has drained the accumulators
+        tc_fence_after();
+        uint32_t started = 0;
+        for (int k = 0; k < P.K; k++) {
+          if (!((uni >> k) & 1ull)) continue;
+          for (int c = 0; c < nc; c++) {
+            mbar_wait(smem_u32(bFull + bStage), bPhase);
+            tc_fence_after();
+            const uint64_t bDesc = smem_desc_sw128(smem_u32(sB + (size_t)bStage * bStageBytes));
+            for (int t = 0; t < P.T; t++) {
+              if (!((m[t] >> k) & 1ull)) continue;
+              mbar_wait(smem_u32(aFull + aStage), aPhase);
+              tc_fence_after();
+              const uint64_t aDesc = smem_desc_sw128(smem_u32(sA + (size_t)aStage * kAStageBytes));
+              const uint32_t d = tmemBase + (uint32_t)(t * P.Cout);
+#pragma unroll
+              for (int j = 0; j < 4; j++) // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+                tc_mma_tf32(d, aDesc + (uint64_t)(j * 2), bDesc + (uint64_t)(j * 2), idesc, ((started >> t) & 1u) | (j > 0));
+              started |= 1u << t;
+              tc_commit(smem_u32(aEmpty + aStage));
+              if (++aStage == (uint32_t)P.SA) { aStage = 0; aPhase ^= 1; }
+            }
+            tc_commit(smem_u32(bEmpty + bStage));
+            if (++bStage == (uint32_t)P.SB) { bStage = 0; bPhase ^= 1; }
+          }
+        }
+        tc_commit(smem_u32(accFull));
+      }
+    }
+  } else {
+    // ============================ B loader ============================
+    if (lane == 0) {
+      uint32_t bStage = 0, bPhase = 0;
+      for (int st = blockIdx.x; st < P.nSuper; st += gridDim.x) {
+        unsigned long long uni = 0;
+        for (int t = 0; t < P.T; t++) if (st * P.T + t < P.nTiles) uni |= __ldg(P.tileMask + st * P.T + t);
+        for (int k = 0; k < P.K; k++) {
+          if (!((uni >> k) & 1ull)) continue;
+          for (int c = 0; c < nc; c++) {
+            mbar_wait(smem_u32(bEmpty + bStage), bPhase ^ 1);
+            const uint32_t bar = smem_u32(bFull + bStage);
+            mbar_arrive_expect_tx(bar, (uint32_t)bStageBytes);
+            bulk_g2s(smem_u32(sB + (size_t)bStage * bStageBytes), P.wimg + ((size_t)k * nc + c) * P.Cout * 32, (uint32_t)bStageBytes, bar);
+            if (++bStage == (uint32_t)P.SB) { bStage = 0; bPhase ^= 1; }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
+  }
+}
+
+// W [K][Cin][Cout] fp32 -> per (k, 32-channel atom) the exact shared-memory image of the B operand:
+// Cout rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7), values rounded to TF32 (rna).
+__global__ void k_prep_wimg(const float *__restrict__ W, float *__restrict__ img, int K, int Cin, int Cout) {
+  const long n = (long)K * Cin * Cout;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long t = i / Cout;
+    const int ci = (int)(t % Cin), k = (int)(t / Cin);
+    const int c = ci >> 5, j = ci & 31, chunk = j >> 2, within = j & 3;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(W[i]));
+    img[((long)k * (Cin >> 5) + c) * Cout * 32 + (long)co * 32 + ((chunk ^ (co & 7)) << 2) + within] = __uint_as_float(r);
+  }
+}
+
+int tc_available() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) major = 0;
+    cached = major == 10;
+  }
+  return cached;
+}
+
+int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
+                        int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s) {
+  if (nOut == 0) return 0;
+  SCN_CHECK(Cin % 32 == 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && K <= 64, "tcgen05 path: unsupported channel counts");
+  TcParams P;
+  P.in = in; P.out = out; P.bias = bias; P.nbr = nbr; P.outRow = outRow; P.tileMask = tileMask;
+  P.nOut = nOut; P.K = K; P.Cin = Cin; P.Cout = Cout;
+  P.nTiles = cdiv(nOut, kTileM);
+  P.T = std::min(4, 512 / Cout);
+  P.nSuper = cdiv(P.nTiles, P.T);
+  P.SA = 6;
+  P.SB = Cout <= 128 ? 3 : 2;
+  size_t smem = (size_t)P.SA * kAStageBytes + (size_t)P.SB * Cout * 128 + (size_t)P.T * kTileM * K * 4 + 64 + (2 * P.SA + 2 * P.SB + 2) * 8 + 16;
+  SCN_CHECK(smem <= 227 * 1024, "tcgen05 path: shared memory budget exceeded");
+  float *wimg = nullptr;
+  SCN_CUDA(cudaMallocAsync((void **)&wimg, (size_t)K * Cin * Cout * 4, s));
+  P.wimg = wimg;
+  k_prep_wimg<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, wimg, K, Cin, Cout);
+  static bool attr = false;
+  if (!attr) {
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  int grid = std::min(P.nSuper, kSMs);
+  conv_plan_tc<<<grid, kThreads, smem, LS(s)>>>(P);
+  SCN_CUDA(cudaGetLastError());
+  cudaFreeAsync(wimg, s);
+  return 0;
+}
+
 } // namespace scn

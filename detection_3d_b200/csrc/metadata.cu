@@ -560,6 +560,29 @@ static int build_rule_lists(Metadata &M, int n, int K, MaskF maskf, PairF pairf,
   return 0;
 }
 
+// ------------------------------------------------------------------ per-tile offset masks
+__global__ void __launch_bounds__(128) k_tile_masks(const int *__restrict__ nbr, int nOut, int K, unsigned long long *__restrict__ masks) {
+  const int tile = blockIdx.x, p = tile * 128 + threadIdx.x;
+  unsigned long long m = 0;
+  if (p < nOut) {
+    const int *row = nbr + (long)p * K;
+    for (int k = 0; k < K; k++) m |= (unsigned long long)(row[k] >= 0) << k;
+  }
+  for (int d = 16; d > 0; d >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, d);
+  __shared__ unsigned long long s[4];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) masks[tile] = s[0] | s[1] | s[2] | s[3];
+}
+int Metadata::build_tile_masks(NbrPlan &plan) {
+  int nTiles = cdiv(std::max(plan.nOut, 1), 128);
+  plan.tileMask = alloc_n<unsigned long long>(nTiles + 8);
+  SCN_CHECK(plan.tileMask, "alloc");
+  if (plan.nOut > 0) k_tile_masks<<<nTiles, 128, 0, LS(stream)>>>(plan.nbr, plan.nOut, plan.K, plan.tileMask);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ submanifold
 // nbr[p*K + k] = row id of the neighbour of site p at filter offset k (last dimension fastest,
 // RectangularRegions.h:56-71; window [c - f/2, c + f - 1 - f/2], SubmanifoldConvolutionRules.h:11-22).
@@ -624,6 +647,7 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
                            SubmPair{g->rank2id, g->id2p, e.plan.nbr, (int)K}, e.rb, 1));
   e.plan.nValid = h_scalars[0];
   SCN_CHECK(e.plan.nValid == e.rb.total, "internal: rule count mismatch");
+  SCN_TRY(build_tile_masks(e.plan));
   *out = &e;
   return 0;
 }
@@ -766,6 +790,7 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   SCN_CUDA(cudaMemsetAsync(e.plan.nbr, 0xff, std::max(1l, (long)go.n * G.K) * 4, s));
   if (E) k_conv_plan<<<stream_grid(E, 256), 256, 0, LS(s)>>>(G, gi->rank2id, gi->coords, evQ, n, e.plan.nbr);
   SCN_CUDA(cudaGetLastError());
+  SCN_TRY(build_tile_masks(e.plan));
   *out = &e;
   return 0;
 }

@@ -51,6 +51,7 @@ struct NbrPlan {
   int *nbr = nullptr;         // [nOut*K] input row ids, indexed by OUTPUT spatial index p
   const int *outRow = nullptr; // p -> output row id (p2id of the output grid)
   long nValid = 0;            // number of non-negative entries (= rules)
+  unsigned long long *tileMask = nullptr; // per 128-site tile: bit k set when some site of the tile has a neighbour at offset k
 };
 
 struct SubmKey { P3 sz, f; bool operator<(const SubmKey &o) const { return sz != o.sz ? sz < o.sz : f < o.f; } };
@@ -93,6 +94,7 @@ struct Metadata {
   int get_submanifold(const long *sz, const long *f, SubmEntry **out);
   int get_conv(const long *inS, const long *outS, const long *f, const long *s, ConvEntry **out);
   int spatial_locations(const long *sz, long *out, int outOnDevice);
+  int build_tile_masks(NbrPlan &plan);
 };
 
 // ------------------------------------------------------------------ device helpers

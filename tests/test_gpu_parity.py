@@ -345,3 +345,116 @@ def test_fpn_forward_layerwise_vs_oracle():
     for a, b in zip(rpn + roi, orpn + oroi):
         assert np.array_equal(a.get_spatial_locations().numpy(), b["locations"])
         _close(a.features.cpu().numpy(), b["features"], rtol=2e-3, atol=2e-4)
+
+
+# ------------------------------------------------------------------ tcgen05 tensor-core path (TF32 inputs, fp32 accumulate)
+# TF32 keeps 10 mantissa bits of every operand (activations truncated by the tensor core, weights
+# rounded to nearest): per-product relative error <= 2^-10; the tolerance below is that bound
+# against the largest output magnitude of the layer.
+TF32_RTOL, TF32_ATOL = 4e-3, 2e-3
+
+
+def _tc_or_skip(scn):
+    if not scn.SCN.lib().scn_tensor_core_path_available():
+        pytest.skip("tcgen05 path needs an sm_100 device")
+
+
+@pytest.mark.parametrize("cin,cout,f", [(32, 32, 3), (64, 64, 3), (128, 128, 3), (256, 256, 3), (32, 128, 1), (64, 128, 3), (256, 128, 1)])
+def test_tc_submanifold_forward(cin, cout, f):
+    scn, G, O = _setup_levels()
+    _tc_or_skip(scn)
+    sz = [64, 64, 32]
+    n = O.nactive(sz)
+    rs = np.random.RandomState(cin * 3 + cout + f)
+    x = rs.randn(n, cin).astype(np.float32)
+    w = (rs.randn(f ** 3, 1, cin, cout) * (2.0 / (cin * f ** 3)) ** 0.5).astype(np.float32)
+    want, macs = so.o_conv_forward(x, w, O.submanifold_rules(sz, [f] * 3), n)
+    L = torch.LongTensor
+    try:
+        scn.set_math_mode("tf32")
+        out = torch.empty(0, device="cuda")
+        got = scn.SCN.SubmanifoldConvolution_updateOutput(L(sz), L([f] * 3), G.m, torch.from_numpy(x).cuda(), out, torch.from_numpy(w).cuda(), torch.Tensor())
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+    assert got == macs
+    _close(out.cpu().numpy(), want, rtol=TF32_RTOL, atol=TF32_ATOL)
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 64), (128, 128)])
+def test_tc_strided_conv_and_z_collapse(cin, cout):
+    scn, G, O = _setup_levels()
+    _tc_or_skip(scn)
+    L = torch.LongTensor
+    a, b, f, s = [64, 64, 32], [32, 32, 16], [2, 2, 2], [2, 2, 2]
+    rules = O.conv_rules(a, b, f, s)
+    rs = np.random.RandomState(cin + cout + 1)
+    x = rs.randn(O.nactive(a), cin).astype(np.float32)
+    w = (rs.randn(8, 1, cin, cout) * (2.0 / (cin * 8)) ** 0.5).astype(np.float32)
+    want, _ = so.o_conv_forward(x, w, rules, O.nactive(b))
+    o, fz = [32, 32, 1], [1, 1, 16]
+    rz = O.conv_rules(b, o, fz, [1, 1, 1])
+    xz = rs.randn(O.nactive(b), cin).astype(np.float32)
+    wz = (rs.randn(16, 1, cin, cout) * 0.05).astype(np.float32)
+    wantz, _ = so.o_conv_forward(xz, wz, rz, O.nactive(o))
+    try:
+        scn.set_math_mode("tf32")
+        out, outz = torch.empty(0, device="cuda"), torch.empty(0, device="cuda")
+        scn.SCN.Convolution_updateOutput(L(a), L(b), L(f), L(s), G.m, torch.from_numpy(x).cuda(), out, torch.from_numpy(w).cuda(), torch.Tensor())
+        scn.SCN.Convolution_updateOutput(L(b), L(o), L(fz), L([1, 1, 1]), G.m, torch.from_numpy(xz).cuda(), outz, torch.from_numpy(wz).cuda(), torch.Tensor())
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+    _close(out.cpu().numpy(), want, rtol=TF32_RTOL, atol=TF32_ATOL)
+    _close(outz.cpu().numpy(), wantz, rtol=TF32_RTOL, atol=TF32_ATOL)
+
+
+def test_tc_large_level_many_supertiles():
+    """More supertiles than SMs, ragged last tile, on a mid-size building (persistent loop, ring wrap)."""
+    import detection_3d_b200.sparseconvnet as scn
+    _tc_or_skip(scn)
+    c = synthetic.building_coords(nx=300, ny=280, nz=40, n_walls=5, seed=5)
+    G, O = _gpu(), so.OracleMetadata()
+    full = [2048, 2048, 512]
+    n = G.input_layer(full, c, 0, 4)
+    assert n == O.input_layer(full, c, 0, 4)
+    rs = np.random.RandomState(0)
+    x = rs.randn(n, 64).astype(np.float32)
+    w = (rs.randn(27, 1, 64, 64) * (2.0 / (64 * 27)) ** 0.5).astype(np.float32)
+    want, macs = so.o_conv_forward(x, w, O.submanifold_rules(full, [3, 3, 3]), n)
+    L = torch.LongTensor
+    try:
+        scn.set_math_mode("tf32")
+        out = torch.empty(0, device="cuda")
+        got = scn.SCN.SubmanifoldConvolution_updateOutput(L(full), L([3, 3, 3]), G.m, torch.from_numpy(x).cuda(), out, torch.from_numpy(w).cuda(), torch.Tensor())
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+    assert got == macs
+    _close(out.cpu().numpy(), want, rtol=TF32_RTOL, atol=TF32_ATOL)
+
+
+@pytest.mark.parametrize("name,cfgname,bld", [
+    ("mini4", "mini4", dict(nx=60, ny=56, nz=24, n_walls=3, seed=3)),
+    ("sw4c_mid", "sw4c", dict(nx=300, ny=280, nz=40, n_walls=5, seed=5)),
+])
+def test_fpn_forward_tf32_vs_reference_golden(name, cfgname, bld):
+    """End-to-end tensor-core backbone vs the reference's fp32 outputs.  Stated tolerance: 3e-2 of the
+    largest magnitude of each returned map (TF32 operand truncation through ~40 layers; instance norm
+    on as few as 4 rows at the top levels amplifies relative differences)."""
+    import detection_3d_b200.sparseconvnet as scn
+    _tc_or_skip(scn)
+    cfg = fpn_util.mini4_config() if cfgname == "mini4" else scn.sw4c_fpn432_config()
+    g = np.load(os.path.join(GOLD, f"fpn_{name}.npz"))
+    try:
+        rpn, roi, macs, *_ = _run_product_fpn(cfg, bld, "tf32")
+    finally:
+        scn.set_math_mode("fp32")
+    assert macs == float(g["macs"])
+    for tag, maps in (("rpn", rpn), ("roi", roi)):
+        for i, m in enumerate(maps):
+            assert np.array_equal(m.get_spatial_locations().numpy(), g[f"{tag}{i}_locations"]), (tag, i)
+            ref = g[f"{tag}{i}_features"]
+            got = m.features.cpu().numpy()
+            err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
+            assert err < 3e-2, (tag, i, float(err))
