@@ -17,12 +17,13 @@
 // Replaces dConvolution_KMxKN_forwardA/B (SCN/CUDA/Convolution.cu:57-203: SIMT tiles, fp64
 // accumulators, one launch + one blocking H2D rule copy per filter offset).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace scn {
 
 constexpr int kTileM = 128;
 constexpr int kAStageBytes = kTileM * 128; // 128 rows x 32 tf32
-constexpr int kInflight = 3;               // A stages a producer thread keeps in flight
+constexpr int kInflight = 5;               // A stages a producer thread keeps in flight
 constexpr int kThreads = 320;
 
 struct TcParams {
@@ -34,6 +35,8 @@ struct TcParams {
   const int *outRow;
   const unsigned long long *tileMask;
   int nOut, K, Cin, Cout, nTiles, T, nSuper, SA, SB;
+  int dbg;    // developer switches (SCN_TC_DBG): 1 = skip A gathers, 2 = skip B copies, 4 = skip MMAs
+  int kSplit; // > 1: the filter offsets of a supertile are split over kSplit CTAs, epilogue accumulates atomically
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -101,27 +104,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ unsigned long long range_mask(int lo, int hi) { // bits [lo, hi)
+  unsigned long long a = hi >= 64 ? ~0ull : ((1ull << hi) - 1ull);
+  return a & ~((1ull << lo) - 1ull);
+}
+
 // ------------------------------------------------------------------ kernel
+// Work item = (supertile of T <= 2 tiles, range of filter offsets).  Accumulators are double
+// buffered in TMEM (2 x T x Cout <= 512 columns) so the epilogue of item i overlaps the main loop
+// of item i+1.
 __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nc = P.Cin / 32;                 // K-atoms per filter offset
+  const int nWork = P.nSuper * P.kSplit;     // work items
   const int bStageBytes = P.Cout * 128;      // Cout rows x 32 tf32
   unsigned char *sA = smem;
   unsigned char *sB = sA + (size_t)P.SA * kAStageBytes;
-  int *sIds = reinterpret_cast<int *>(sB + (size_t)P.SB * bStageBytes);
-  unsigned long long *sMask = reinterpret_cast<unsigned long long *>(sIds + (size_t)P.T * kTileM * P.K);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sMask + 8);
-  // barrier indices
+  float *sEpi = reinterpret_cast<float *>(sB + (size_t)P.SB * bStageBytes); // 4 warps x 32 rows x 36 floats
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + 4 * 32 * 36);
   uint64_t *aFull = bars, *aEmpty = bars + P.SA, *bFull = bars + 2 * P.SA, *bEmpty = bars + 2 * P.SA + P.SB;
-  uint64_t *accFull = bars + 2 * P.SA + 2 * P.SB, *accEmpty = accFull + 1;
-  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 1);
+  uint64_t *accFull = bars + 2 * P.SA + 2 * P.SB, *accEmpty = accFull + 2;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 2);
 
   if (tid == 0) {
-    for (int i = 0; i < P.SA; i++) { mbar_init(smem_u32(aFull + i), 128); mbar_init(smem_u32(aEmpty + i), 1); }
+    for (int i = 0; i < P.SA; i++) { mbar_init(smem_u32(aFull + i), 4); mbar_init(smem_u32(aEmpty + i), 1); }
     for (int i = 0; i < P.SB; i++) { mbar_init(smem_u32(bFull + i), 1); mbar_init(smem_u32(bEmpty + i), 1); }
-    mbar_init(smem_u32(accFull), 1);
-    mbar_init(smem_u32(accEmpty), 128);
+    for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
@@ -132,92 +141,128 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmemBase = *tmemSlot;
+  const int accCols = P.T * P.Cout; // columns of one accumulator stage
 
   if (warp < 4) {
     // ============================ epilogue ============================
-    uint32_t phase = 0;
-    for (int st = blockIdx.x; st < P.nSuper; st += gridDim.x, phase ^= 1) {
-      mbar_wait(smem_u32(accFull), phase);
+    float *stg = sEpi + warp * (32 * 36);
+    int it = 0;
+    for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
+      const int st = wi / P.kSplit, part = wi % P.kSplit;
+      const unsigned long long kmask = range_mask(P.K * part / P.kSplit, P.K * (part + 1) / P.kSplit);
+      const int a = it & 1;
+      mbar_wait(smem_u32(accFull + a), (it >> 1) & 1);
       tc_fence_after();
       for (int t = 0; t < P.T; t++) {
         const int tile = st * P.T + t;
         if (tile >= P.nTiles) break;
+        const bool started = (__ldg(P.tileMask + tile) & kmask) != 0ull;
+        if (!started && P.kSplit > 1) continue; // nothing to add
         const int p = tile * kTileM + warp * 32 + lane;
-        const bool valid = p < P.nOut;
-        const bool started = __ldg(P.tileMask + tile) != 0ull;
-        float *dst = valid ? P.out + (size_t)__ldg(P.outRow + p) * P.Cout : nullptr;
+        const int myRow = p < P.nOut ? __ldg(P.outRow + p) : -1;
         for (int c0 = 0; c0 < P.Cout; c0 += 32) {
           uint32_t v[32];
           if (started) {
-            tmem_ld32(tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * P.Cout + c0), v);
+            tmem_ld32(tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * accCols + t * P.Cout + c0), v);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = 0u;
           }
-          if (valid) {
+          // stage the 32x32 block so that each store instruction writes whole 128-byte row segments
+          __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              if (P.bias) {
-                o.x += __ldg(P.bias + c0 + j); o.y += __ldg(P.bias + c0 + j + 1); o.z += __ldg(P.bias + c0 + j + 2); o.w += __ldg(P.bias + c0 + j + 3);
-              }
-              *reinterpret_cast<float4 *>(dst + c0 + j) = o;
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4 *>(stg + lane * 36 + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          __syncwarp();
+          const int cc = (lane & 7) * 4;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (P.bias && part == 0) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + c0 + cc));
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int r = i * 4 + (lane >> 3);
+            const int row = __shfl_sync(0xffffffffu, myRow, r);
+            float4 o = *reinterpret_cast<const float4 *>(stg + r * 36 + cc);
+            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            if (row >= 0) {
+              float *dst = P.out + (size_t)row * P.Cout + c0 + cc;
+              if (P.kSplit == 1) *reinterpret_cast<float4 *>(dst) = o;
+              else { atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w); } // pre-zeroed by the launcher
             }
           }
         }
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(accEmpty));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(accEmpty + a));
     }
   } else if (warp < 8) {
     // ============================ A producer ============================
     const int ptid = tid - 128;
-    const int rowGroup = ptid >> 3, chunk = ptid & 7;
+    const int rg = ptid >> 3, chunk = ptid & 7; // 8 threads per row; a thread owns rows rg*8 .. rg*8+7
     uint32_t stage = 0, phase = 0;
-    for (int st = blockIdx.x; st < P.nSuper; st += gridDim.x) {
-      // neighbour ids of the whole supertile -> shared memory (contiguous in global memory)
-      asm volatile("bar.sync 1, 128;" ::: "memory"); // every producer is done with the previous ids
-      const long base = (long)st * P.T * kTileM * P.K;
-      const long limit = (long)P.nOut * P.K;
-      const int total = P.T * kTileM * P.K;
-      for (int i = ptid; i < total; i += 128) sIds[i] = (base + i < limit) ? __ldg(P.nbr + base + i) : -1;
-      if (ptid < P.T) sMask[ptid] = (st * P.T + ptid < P.nTiles) ? __ldg(P.tileMask + st * P.T + ptid) : 0ull;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      unsigned long long m[4], uni = 0;
-      for (int t = 0; t < 4; t++) { m[t] = t < P.T ? sMask[t] : 0ull; uni |= m[t]; }
-      int pending = 0;           // stages committed but not yet published
-      uint32_t pubStage = stage; // oldest unpublished stage
-      for (int k = 0; k < P.K; k++) {
-        if (!((uni >> k) & 1ull)) continue;
+    for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
+      const int st = wi / P.kSplit, part = wi % P.kSplit;
+      const int kLo = P.K * part / P.kSplit, kHi = P.K * (part + 1) / P.kSplit;
+      const unsigned long long kmask = range_mask(kLo, kHi);
+      unsigned long long m[2], uni = 0;
+      for (int t = 0; t < 2; t++) { m[t] = (t < P.T && st * P.T + t < P.nTiles) ? (__ldg(P.tileMask + st * P.T + t) & kmask) : 0ull; uni |= m[t]; }
+      // neighbour ids live in registers, fetched one filter offset ahead
+      int ids[2][8], nxt[2][8];
+      auto load_ids = [&](int k, int (&dst)[2][8]) {
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const long p = (long)(st * P.T + t) * kTileM + rg * 8 + i;
+            dst[t][i] = (t < P.T && p < P.nOut && ((m[t] >> k) & 1ull)) ? __ldg(P.nbr + p * P.K + k) : -1;
+          }
+      };
+      int k = uni ? __ffsll((long long)uni) - 1 : P.K;
+      if (k < P.K) load_ids(k, nxt);
+      int pending = 0;
+      uint32_t pubStage = stage;
+      while (k < P.K) {
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+          for (int i = 0; i < 8; i++) ids[t][i] = nxt[t][i];
+        const unsigned long long rest = (k + 1 < 64) ? (uni >> (k + 1)) : 0ull;
+        const int kNext = rest ? k + 1 + (__ffsll((long long)rest) - 1) : P.K;
+        if (kNext < P.K) load_ids(kNext, nxt);
         for (int c = 0; c < nc; c++) {
-          for (int t = 0; t < P.T; t++) {
+#pragma unroll
+          for (int t = 0; t < 2; t++) {
             if (!((m[t] >> k) & 1ull)) continue;
             mbar_wait(smem_u32(aEmpty + stage), phase ^ 1);
-            const uint32_t sbase = smem_u32(sA + (size_t)stage * kAStageBytes);
+            const uint32_t sbase = smem_u32(sA + (size_t)stage * kAStageBytes) + (uint32_t)(rg * 8) * 128u;
+            if (!(P.dbg & 1)) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-              const int row = i * 16 + rowGroup;
-              const int id = sIds[(t * kTileM + row) * P.K + k];
-              const float *src = P.in + (size_t)(id >= 0 ? id : 0) * P.Cin + c * 32 + chunk * 4;
-              cp_async16(sbase + row * 128 + ((chunk ^ (row & 7)) << 4), src, id >= 0 ? 16u : 0u);
+              for (int i = 0; i < 8; i++) {
+                const int id = ids[t][i];
+                const float *src = P.in + (size_t)(id >= 0 ? id : 0) * P.Cin + c * 32 + chunk * 4;
+                cp_async16(sbase + i * 128 + ((chunk ^ i) << 4), src, id >= 0 ? 16u : 0u);
+              }
             }
             cp_async_commit();
             if (++stage == (uint32_t)P.SA) { stage = 0; phase ^= 1; }
             if (++pending == kInflight) {
               cp_async_wait<kInflight - 1>();
               fence_proxy_async();
-              mbar_arrive(smem_u32(aFull + pubStage));
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(aFull + pubStage));
               if (++pubStage == (uint32_t)P.SA) pubStage = 0;
               pending--;
             }
           }
         }
+        k = kNext;
       }
-      // drain: publish the last stages of this supertile
       cp_async_wait<0>();
       fence_proxy_async();
+      __syncwarp();
       while (pending > 0) {
-        mbar_arrive(smem_u32(aFull + pubStage));
+        if (lane == 0) mbar_arrive(smem_u32(aFull + pubStage));
         if (++pubStage == (uint32_t)P.SA) pubStage = 0;
         pending--;
       }
@@ -227,11 +272,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
     if (lane == 0) {
       // instruction descriptor: D=F32, A=B=TF32, K-major both, N=Cout, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.Cout >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      uint32_t aStage = 0, aPhase = 0, bStage = 0, bPhase = 0, accPhase = 0;
-      for (int st = blockIdx.x; st < P.nSuper; st += gridDim.x, accPhase ^= 1) {
-        unsigned long long m[4], uni = 0;
-        for (int t = 0; t < 4; t++) { m[t] = (t < P.T && st * P.T + t < P.nTiles) ? __ldg(P.tileMask + st * P.T + t) : 0ull; uni |= m[t]; }
-        mbar_wait(smem_u32(accEmpty), accPhase ^ 1); // epilogue has drained the accumulators
+      uint32_t aStage = 0, aPhase = 0, bStage = 0, bPhase = 0;
+      int it = 0;
+      for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
+        const int st = wi / P.kSplit, part = wi % P.kSplit;
+        const unsigned long long kmask = range_mask(P.K * part / P.kSplit, P.K * (part + 1) / P.kSplit);
+        unsigned long long m[2], uni = 0;
+        for (int t = 0; t < 2; t++) { m[t] = (t < P.T && st * P.T + t < P.nTiles) ? (__ldg(P.tileMask + st * P.T + t) & kmask) : 0ull; uni |= m[t]; }
+        const int a = it & 1;
+        mbar_wait(smem_u32(accEmpty + a), ((it >> 1) & 1) ^ 1); // epilogue has drained this accumulator stage
         tc_fence_after();
         uint32_t started = 0;
         for (int k = 0; k < P.K; k++) {
@@ -240,15 +289,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
             mbar_wait(smem_u32(bFull + bStage), bPhase);
             tc_fence_after();
             const uint64_t bDesc = smem_desc_sw128(smem_u32(sB + (size_t)bStage * bStageBytes));
-            for (int t = 0; t < P.T; t++) {
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
               if (!((m[t] >> k) & 1ull)) continue;
               mbar_wait(smem_u32(aFull + aStage), aPhase);
               tc_fence_after();
               const uint64_t aDesc = smem_desc_sw128(smem_u32(sA + (size_t)aStage * kAStageBytes));
-              const uint32_t d = tmemBase + (uint32_t)(t * P.Cout);
+              const uint32_t d = tmemBase + (uint32_t)(a * accCols + t * P.Cout);
+              if (!(P.dbg & 4)) {
 #pragma unroll
-              for (int j = 0; j < 4; j++) // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-                tc_mma_tf32(d, aDesc + (uint64_t)(j * 2), bDesc + (uint64_t)(j * 2), idesc, ((started >> t) & 1u) | (j > 0));
+                for (int j = 0; j < 4; j++) // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
+                  tc_mma_tf32(d, aDesc + (uint64_t)(j * 2), bDesc + (uint64_t)(j * 2), idesc, ((started >> t) & 1u) | (j > 0));
+              }
               started |= 1u << t;
               tc_commit(smem_u32(aEmpty + aStage));
               if (++aStage == (uint32_t)P.SA) { aStage = 0; aPhase ^= 1; }
@@ -257,23 +309,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
             if (++bStage == (uint32_t)P.SB) { bStage = 0; bPhase ^= 1; }
           }
         }
-        tc_commit(smem_u32(accFull));
+        tc_commit(smem_u32(accFull + a));
       }
     }
   } else {
     // ============================ B loader ============================
     if (lane == 0) {
       uint32_t bStage = 0, bPhase = 0;
-      for (int st = blockIdx.x; st < P.nSuper; st += gridDim.x) {
+      for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
+        const int st = wi / P.kSplit, part = wi % P.kSplit;
+        const unsigned long long kmask = range_mask(P.K * part / P.kSplit, P.K * (part + 1) / P.kSplit);
         unsigned long long uni = 0;
-        for (int t = 0; t < P.T; t++) if (st * P.T + t < P.nTiles) uni |= __ldg(P.tileMask + st * P.T + t);
+        for (int t = 0; t < P.T; t++) if (st * P.T + t < P.nTiles) uni |= __ldg(P.tileMask + st * P.T + t) & kmask;
         for (int k = 0; k < P.K; k++) {
           if (!((uni >> k) & 1ull)) continue;
           for (int c = 0; c < nc; c++) {
             mbar_wait(smem_u32(bEmpty + bStage), bPhase ^ 1);
             const uint32_t bar = smem_u32(bFull + bStage);
-            mbar_arrive_expect_tx(bar, (uint32_t)bStageBytes);
-            bulk_g2s(smem_u32(sB + (size_t)bStage * bStageBytes), P.wimg + ((size_t)k * nc + c) * P.Cout * 32, (uint32_t)bStageBytes, bar);
+            if (P.dbg & 2) { mbar_arrive(bar); }
+            else {
+              mbar_arrive_expect_tx(bar, (uint32_t)bStageBytes);
+              bulk_g2s(smem_u32(sB + (size_t)bStage * bStageBytes), P.wimg + ((size_t)k * nc + c) * P.Cout * 32, (uint32_t)bStageBytes, bar);
+            }
             if (++bStage == (uint32_t)P.SB) { bStage = 0; bPhase ^= 1; }
           }
         }
@@ -321,12 +378,29 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   P.in = in; P.out = out; P.bias = bias; P.nbr = nbr; P.outRow = outRow; P.tileMask = tileMask;
   P.nOut = nOut; P.K = K; P.Cin = Cin; P.Cout = Cout;
   P.nTiles = cdiv(nOut, kTileM);
-  P.T = std::min(4, 512 / Cout);
+  // supertile height: 2 tiles share every weight slice when the level is large enough for >= 2
+  // work items per SM (accumulators double-buffered: 2 x T x Cout <= 512 TMEM columns); small levels
+  // use 1-tile items and split the filter offsets over CTAs so the whole chip works on them.
+  const int Tmax = Cout <= 128 ? 2 : 1;
+  P.T = (Tmax == 2 && P.nTiles >= 2 * kSMs * 2) ? 2 : 1;
+  static int envT = -1, envSA = -1, envSB = -1, envDbg = 0;
+  if (envT < 0) {
+    envT = getenv("SCN_TC_T") ? atoi(getenv("SCN_TC_T")) : 0;
+    envSA = getenv("SCN_TC_SA") ? atoi(getenv("SCN_TC_SA")) : 0;
+    envSB = getenv("SCN_TC_SB") ? atoi(getenv("SCN_TC_SB")) : 0;
+    envDbg = getenv("SCN_TC_DBG") ? atoi(getenv("SCN_TC_DBG")) : 0;
+  }
+  P.dbg = envDbg;
+  if (envT > 0 && envT <= Tmax) P.T = envT;
   P.nSuper = cdiv(P.nTiles, P.T);
-  P.SA = 6;
-  P.SB = Cout <= 128 ? 3 : 2;
-  size_t smem = (size_t)P.SA * kAStageBytes + (size_t)P.SB * Cout * 128 + (size_t)P.T * kTileM * K * 4 + 64 + (2 * P.SA + 2 * P.SB + 2) * 8 + 16;
-  SCN_CHECK(smem <= 227 * 1024, "tcgen05 path: shared memory budget exceeded");
+  P.kSplit = 1;
+  if (P.nSuper < kSMs / 2) P.kSplit = std::max(1, std::min(K, kSMs / P.nSuper));
+  P.SB = envSB > 0 ? envSB : (Cout <= 128 ? 3 : 2);
+  size_t fixed = (size_t)P.SB * Cout * 128 + 4 * 32 * 36 * 4 + 64 * 8 + 16;
+  P.SA = (int)std::min<size_t>(envSA > 0 ? envSA : 8, (227 * 1024 - fixed) / kAStageBytes);
+  SCN_CHECK(P.SA > kInflight, "tcgen05 path: shared memory budget exceeded");
+  size_t smem = (size_t)P.SA * kAStageBytes + fixed;
+  if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
   float *wimg = nullptr;
   SCN_CUDA(cudaMallocAsync((void **)&wimg, (size_t)K * Cin * Cout * 4, s));
   P.wimg = wimg;
@@ -336,7 +410,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  int grid = std::min(P.nSuper, kSMs);
+  int grid = std::min(P.nSuper * P.kSplit, kSMs);
   conv_plan_tc<<<grid, kThreads, smem, LS(s)>>>(P);
   SCN_CUDA(cudaGetLastError());
   cudaFreeAsync(wimg, s);

@@ -13,9 +13,18 @@ void set_error(const std::string &m) { g_err = m; }
 const char *last_error() { return g_err.c_str(); }
 
 // ------------------------------------------------------------------ memory
+// pinned scratch blocks are recycled across Metadata objects: cudaMallocHost costs milliseconds and a
+// fresh Metadata is created for every forward (sparseconvnet/ioLayers.py:52-55)
+static std::vector<int *> g_pinned_free;
+static int *pinned_get() {
+  if (!g_pinned_free.empty()) { int *p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
+  int *p = nullptr;
+  if (cudaMallocHost(&p, 256 * 4) != cudaSuccess) return nullptr;
+  return p;
+}
 Metadata::~Metadata() {
   for (void *p : allocs) cudaFreeAsync(p, stream);
-  if (h_scalars) cudaFreeHost(h_scalars);
+  if (h_scalars) g_pinned_free.push_back(h_scalars);
 }
 void *Metadata::alloc(size_t bytes) {
   void *p = nullptr;
@@ -28,12 +37,16 @@ void *Metadata::alloc(size_t bytes) {
   return p;
 }
 int Metadata::init() {
-  cudaMemPool_t pool;
-  int dev = 0;
-  SCN_CUDA(cudaGetDevice(&dev));
-  SCN_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-  uint64_t thr = UINT64_MAX; // keep freed blocks cached: steady-state forwards never hit the driver
-  SCN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  static bool poolConfigured = false;
+  if (!poolConfigured) {
+    cudaMemPool_t pool;
+    int dev = 0;
+    SCN_CUDA(cudaGetDevice(&dev));
+    SCN_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t thr = UINT64_MAX; // keep freed blocks cached: steady-state forwards never hit the driver
+    SCN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    poolConfigured = true;
+  }
   zpoolWords = 1 << 19; // 4 MiB of scan state
   zpool = alloc_n<unsigned long long>(zpoolWords);
   d_scalars = alloc_n<int>(256);
@@ -41,7 +54,8 @@ int Metadata::init() {
   SCN_CHECK(zpool && d_scalars, "alloc");
   SCN_CUDA(cudaMemsetAsync(zpool, 0, zpoolWords * 8, stream));
   SCN_CUDA(cudaMemsetAsync(d_scalars, 0, 256 * 4, stream));
-  SCN_CUDA(cudaMallocHost(&h_scalars, 256 * 4));
+  h_scalars = pinned_get();
+  SCN_CHECK(h_scalars, "pinned host scratch");
   return 0;
 }
 unsigned long long *Metadata::scan_state(long n) {
