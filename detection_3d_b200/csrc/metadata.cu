@@ -315,87 +315,88 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
 }
 
 // ------------------------------------------------------------------ dense_hash_map order
-// Table entry: [63:38] rank | [37:12] row id | [11:0] probe count.  Lower rank wins a bucket.
-constexpr unsigned long long kEmpty = ~0ull;
-__device__ __forceinline__ unsigned long long pack_entry(unsigned rank, unsigned id, unsigned probe) {
-  return ((unsigned long long)rank << 38) | ((unsigned long long)id << 12) | probe;
-}
+// Emulates the bucket layout google::dense_hash_map reaches when the keys are inserted one by one
+// (growth by doubling at load 0.5, re-insertion in ascending bucket order, triangular probing).
+// Table entry (32 bit): [31:7] insertion rank within the current growth phase | [6:0] probe count.
+// Lower rank wins a bucket; the row id of rank r is seq[r].
+constexpr unsigned kEmpty = 0xffffffffu;
+constexpr unsigned kProbeBits = 7, kProbeMask = (1u << kProbeBits) - 1u;
 // Priority insertion: the key of insertion rank i must end at the first bucket of its probe path
 // (b, b+1, b+3, b+6, ...) that no lower-ranked key occupies -- exactly what sequential insertion
-// into google::dense_hash_map produces.  A displaced key is carried on by the displacing thread.
-__device__ __forceinline__ void priority_insert(unsigned long long *tab, unsigned mask, unsigned b, unsigned long long cur, int *err) {
+// produces.  A displaced key is carried onwards by the displacing thread; its next bucket follows
+// from the bucket it sat in and its stored probe count, so its hash is not needed again.
+__device__ __forceinline__ void priority_insert(unsigned *tab, unsigned mask, unsigned b, unsigned cur, int *err) {
   while (true) {
-    unsigned long long old = atomicMin(tab + b, cur);
+    unsigned old = atomicMin(tab + b, cur);
     if (old == kEmpty) return;
-    if (old > cur) cur = old; // we took the bucket; carry the evicted key onwards
-    unsigned probe = (unsigned)(cur & 0xfffull) + 1u;
-    if (probe >= 4096u) { *err = 3; return; }
-    cur = (cur & ~0xfffull) | probe;
+    if (old > cur) cur = old;
+    unsigned probe = (cur & kProbeMask) + 1u;
+    if (probe > kProbeMask) { *err = 3; return; }
+    cur = (cur & ~kProbeMask) | probe;
     b = (b + probe) & mask;
   }
 }
-struct TabIn { const unsigned long long *tab; __device__ int operator()(long i) const { return tab[i] != kEmpty; } };
-// re-insert the old table's elements in ascending bucket order (copy_from on growth)
-struct RehashOut {
-  const unsigned long long *prev; unsigned long long *cur; unsigned mask; const int4 *coords; int *err;
+struct TabIn { const unsigned *tab; __device__ int operator()(long i) const { return tab[i] != kEmpty; } };
+// ids of the old table's elements in ascending bucket order (the re-insertion order on growth)
+struct CompactOut {
+  const unsigned *tab; const int *seqIn; int idOffset; int *seqOut;
   __device__ void operator()(long i, int pre, int v) const {
-    if (!v) return;
-    unsigned id = (unsigned)((prev[i] >> 12) & 0x3ffffffull);
-    int4 c = coords[id];
-    priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, pack_entry((unsigned)pre, id, 0), err);
+    if (v) { unsigned r = tab[i] >> kProbeBits; seqOut[pre] = seqIn ? seqIn[r] : (int)r + idOffset; }
   }
 };
-__global__ void k_insert_new(unsigned long long *cur, unsigned mask, const int4 *coords, const int *seq, int idOffset, int from, int to, int *err) {
-  for (int j = from + blockIdx.x * blockDim.x + threadIdx.x; j < to; j += gridDim.x * blockDim.x) {
-    unsigned id = seq ? (unsigned)seq[j] : (unsigned)(j + idOffset);
+// one thread per key: ranks [0, nPrev) are the re-inserted old keys (ids in oldSeq), ranks
+// [nPrev, nCur) the keys inserted during this phase (ids newSeq[rank] or rank + idOffset)
+__global__ void __launch_bounds__(256) k_phase_insert(unsigned *cur, unsigned mask, const int4 *__restrict__ coords, const int *oldSeq,
+                                                      const int *newSeq, int idOffset, int nPrev, int nCur, int *phaseSeq, int *err) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nCur; j += gridDim.x * blockDim.x) {
+    int id = j < nPrev ? oldSeq[j] : (newSeq ? newSeq[j] : j + idOffset);
+    if (phaseSeq) phaseSeq[j] = id;
     int4 c = coords[id];
-    priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, pack_entry((unsigned)j, id, 0), err);
+    priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, (unsigned)j << kProbeBits, err);
   }
 }
 struct OrderOut {
-  const unsigned long long *tab; int *rank2id;
-  __device__ void operator()(long i, int pre, int v) const { if (v) rank2id[pre] = (int)((tab[i] >> 12) & 0x3ffffffull); }
+  const unsigned *tab; const int *seq; int *rank2id;
+  __device__ void operator()(long i, int pre, int v) const { if (v) rank2id[pre] = seq[tab[i] >> kProbeBits]; }
 };
 
-// Single-CTA version of the same phase loop for the first (small) tables, entirely in shared
-// memory: tables up to kSmallNb buckets.  Leaves the last small table in `out` (global).
-constexpr int kSmallNb = 8192;
-__global__ void __launch_bounds__(1024) k_emulate_small(const int4 *coords, const int *seq, int idOffset, int n, unsigned long long *out, int *outNb, int *err) {
-  extern __shared__ unsigned long long sm[];
-  unsigned long long *A = sm, *B = sm + kSmallNb;
+// The first growth phases (tables up to kSmallNb buckets) in one CTA, entirely in shared memory.
+// Leaves the last small table in `out` and the id of every rank of that phase in `seqOut`.
+constexpr int kSmallNb = 16384;
+__global__ void __launch_bounds__(1024) k_emulate_small(const int4 *coords, const int *seq, int idOffset, int n, unsigned *out, int *seqOut, int *err) {
+  extern __shared__ unsigned sm[];
+  unsigned *A = sm, *B = sm + kSmallNb;
+  int *seqA = reinterpret_cast<int *>(sm + 2 * kSmallNb), *seqB = seqA + kSmallNb / 2; // rank -> id of the two live phases
   __shared__ int s_scan[1024 / 32];
   __shared__ int s_carry;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  unsigned long long *prev = A, *cur = B;
+  unsigned *prev = A, *cur = B;
+  int *seqPrev = seqA, *seqCur = seqB;
   int nb = 32, nPrev = 0;
   while (true) {
     const int nCur = min(n, nb / 2);
     const unsigned mask = nb - 1;
     for (int i = tid; i < nb; i += 1024) cur[i] = kEmpty;
     __syncthreads();
-    // old elements in ascending bucket order of prev (rank = prefix count)
-    if (nPrev > 0) {
+    if (nPrev > 0) { // old elements in ascending bucket order of prev (rank = prefix count)
       const int nbPrev = nb / 2;
       if (tid == 0) s_carry = 0;
       __syncthreads();
       for (int base = 0; base < nbPrev; base += 1024) {
         int i = base + tid;
-        unsigned long long e = i < nbPrev ? prev[i] : kEmpty;
+        unsigned e = i < nbPrev ? prev[i] : kEmpty;
         int v = e != kEmpty;
         int incl = warp_incl_scan(v, lane);
         if (lane == 31) s_scan[wid] = incl;
         __syncthreads();
-        if (wid == 0) {
-          int w = s_scan[lane];
-          int wi = warp_incl_scan(w, lane);
-          s_scan[lane] = wi - w;
-        }
+        if (wid == 0) { int w = s_scan[lane]; int wi = warp_incl_scan(w, lane); s_scan[lane] = wi - w; }
         __syncthreads();
         int rank = s_carry + s_scan[wid] + incl - v;
         if (v) {
-          unsigned id = (unsigned)((e >> 12) & 0x3ffffffull);
+          int id = seqPrev[e >> kProbeBits];
+          seqCur[rank] = id;
           int4 c = coords[id];
-          priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, pack_entry((unsigned)rank, id, 0), err);
+          priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, (unsigned)rank << kProbeBits, err);
         }
         __syncthreads();
         if (tid == 1023) s_carry = rank + v;
@@ -403,17 +404,19 @@ __global__ void __launch_bounds__(1024) k_emulate_small(const int4 *coords, cons
       }
     }
     for (int j = nPrev + tid; j < nCur; j += 1024) {
-      unsigned id = seq ? (unsigned)seq[j] : (unsigned)(j + idOffset);
+      int id = seq ? seq[j] : j + idOffset;
+      seqCur[j] = id;
       int4 c = coords[id];
-      priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, pack_entry((unsigned)j, id, 0), err);
+      priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, (unsigned)j << kProbeBits, err);
     }
     __syncthreads();
     if (nCur == n || nb == kSmallNb) {
       for (int i = tid; i < nb; i += 1024) out[i] = cur[i];
-      if (tid == 0) *outNb = nb;
+      for (int i = tid; i < nCur; i += 1024) seqOut[i] = seqCur[i];
       return;
     }
-    unsigned long long *t = prev; prev = cur; cur = t;
+    unsigned *t = prev; prev = cur; cur = t;
+    int *ts = seqPrev; seqPrev = seqCur; seqCur = ts;
     nPrev = nCur;
     nb *= 2;
   }
@@ -422,32 +425,37 @@ __global__ void __launch_bounds__(1024) k_emulate_small(const int4 *coords, cons
 // Hash-iteration order of one batch item: ids seq[0..n) (or idOffset + 0..n) inserted in that order.
 static int emulate_order(Metadata &M, const int4 *coords, const int *seq, int idOffset, int n, int *rank2idOut) {
   if (n == 0) return 0;
+  SCN_CHECK(n < (1 << 25), "too many active sites in one batch item for the hash-order emulation");
   cudaStream_t s = M.stream;
   long nbFinal = 32;
   while (n > nbFinal / 2) nbFinal *= 2;
-  unsigned long long *T0 = M.alloc_n<unsigned long long>(nbFinal), *T1 = M.alloc_n<unsigned long long>(nbFinal);
-  SCN_CHECK(T0 && T1, "alloc");
+  unsigned *T0 = M.alloc_n<unsigned>(nbFinal), *T1 = M.alloc_n<unsigned>(nbFinal);
+  int *S0 = M.alloc_n<int>(n), *S1 = M.alloc_n<int>(n);
+  SCN_CHECK(T0 && T1 && S0 && S1, "alloc");
+  const int smallSmem = 2 * kSmallNb * 4 + kSmallNb * 4;
   static bool attr = false;
   if (!attr) {
-    SCN_CUDA(cudaFuncSetAttribute(k_emulate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmallNb * 8));
+    SCN_CUDA(cudaFuncSetAttribute(k_emulate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smallSmem));
     attr = true;
   }
-  // small phases in one CTA
-  k_emulate_small<<<1, 1024, 2 * kSmallNb * 8, LS(s)>>>(coords, seq, idOffset, n, T0, M.d_scalars + 100, M.d_err);
+  k_emulate_small<<<1, 1024, smallSmem, LS(s)>>>(coords, seq, idOffset, n, T0, S0, M.d_err);
   SCN_CUDA(cudaGetLastError());
   long nb = std::min<long>(nbFinal, kSmallNb);
-  unsigned long long *prev = T0, *cur = T1;
+  unsigned *prev = T0, *cur = T1;
+  int *seqPrev = S0, *seqCur = S1; // seqPrev: rank -> id of the phase held in `prev`
   int nPrev = (int)std::min<long>(n, nb / 2);
   while (nb < nbFinal) {
     nb *= 2;
     int nCur = (int)std::min<long>(n, nb / 2);
-    SCN_CUDA(cudaMemsetAsync(cur, 0xff, nb * 8, s));
-    SCN_TRY(run_scan(M, nb / 2, TabIn{prev}, RehashOut{prev, cur, (unsigned)(nb - 1), coords, M.d_err}, nullptr));
-    if (nCur > nPrev) k_insert_new<<<stream_grid(nCur - nPrev, 256), 256, 0, LS(s)>>>(cur, (unsigned)(nb - 1), coords, seq, idOffset, nPrev, nCur, M.d_err);
+    SCN_CUDA(cudaMemsetAsync(cur, 0xff, nb * 4, s));
+    // seqCur[0..nPrev) = ids of the old table in bucket order; the insert kernel appends the new ones
+    SCN_TRY(run_scan(M, nb / 2, TabIn{prev}, CompactOut{prev, seqPrev, 0, seqCur}, nullptr));
+    k_phase_insert<<<stream_grid(nCur, 256, 16), 256, 0, LS(s)>>>(cur, (unsigned)(nb - 1), coords, seqCur, seq, idOffset, nPrev, nCur, seqCur, M.d_err);
     std::swap(prev, cur);
+    std::swap(seqPrev, seqCur);
     nPrev = nCur;
   }
-  SCN_TRY(run_scan(M, nbFinal, TabIn{prev}, OrderOut{prev, rank2idOut}, nullptr));
+  SCN_TRY(run_scan(M, nbFinal, TabIn{prev}, OrderOut{prev, seqPrev, rank2idOut}, nullptr));
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
