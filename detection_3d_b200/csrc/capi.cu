@@ -21,7 +21,8 @@ int conv_backward_simt(const float *in, float *d_in, const float *d_out, const f
                        const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s);
 int tc_available();
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
-                        int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s);
+                        int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
+                        long nInRows);
 static int g_math_mode = 0;
 } // namespace scn
 
@@ -185,9 +186,14 @@ int scn_iteration_order(scn_metadata *m, const long sz[3], int *dst) {
   return 0;
 }
 
-static int run_plan(Metadata &M, const scn::NbrPlan &plan, const float *in, float *out, const float *w, const float *bias, int Cin, int Cout) {
-  if (scn::g_math_mode != 0 && scn::tc_available() && Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32 && Cout <= 256 && plan.K <= 32)
-    return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.tileMask, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.stream);
+static bool tc_ok(int Cin, int Cout, int K) {
+  return scn::g_math_mode != 0 && scn::tc_available() && Cout % 32 == 0 && Cout >= 32 && Cout <= 256 && K <= 64 && Cin >= 4 && Cin <= 1024;
+}
+static int run_plan(Metadata &M, const scn::NbrPlan &plan, const float *in, float *out, const float *w, const float *bias, int Cin, int Cout,
+                    long nInRows) {
+  if (tc_ok(Cin, Cout, plan.K))
+    return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.tileMask, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.stream,
+                                    nullptr, plan.K, nInRows);
   return scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.stream);
 }
 
@@ -197,7 +203,7 @@ int scn_submanifold_convolution_forward(scn_metadata *m, const long sz[3], const
   scn::SubmEntry *e;
   SCN_TRY(m->md.get_submanifold(sz, f, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
-  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout);
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(sz)->n);
 }
 int scn_convolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                             float *out, const float *w, const float *bias, int Cin, int Cout, double *macs) {
@@ -205,7 +211,7 @@ int scn_convolution_forward(scn_metadata *m, const long inS[3], const long outS[
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
-  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout);
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(inS)->n);
 }
 __global__ void k_fill_rows_bias(float *out, long n, int C, const float *bias) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n * C; i += (long)gridDim.x * blockDim.x) out[i] = bias ? bias[i % C] : 0.f;
@@ -222,6 +228,12 @@ int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long out
   cudaStream_t s = m->md.stream;
   // every fine row with a parent is written exactly once when each input site has one output cell
   bool single = e->rb.total == gf->n && !bias;
+  if (single && e->geom.M == 1 && tc_ok(Cin, Cout, 1) && gf->n > 0) {
+    SCN_TRY(m->md.get_deconv_plan(*e));
+    const scn::DeconvPlan &d = e->deconv;
+    return scn::launch_conv_plan_tc(in, out, w, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, 1, Cin, Cout, nullptr, scn::g_math_mode, s, d.tileW,
+                                    e->rb.nLists, m->md.find_grid(inS)->n);
+  }
   if (!single && gf->n) k_fill_rows_bias<<<scn::stream_grid((long)gf->n * Cout, 256), 256, 0, scn::LS(s)>>>(out, gf->n, Cout, bias);
   return scn::launch_conv_list_simt(in, out, w, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, Cin, Cout, /*srcIsY=*/1, single ? 1 : 0, s);
 }

@@ -34,6 +34,7 @@ struct TcParams {
   const int *nbr;
   const int *outRow;
   const unsigned long long *tileMask;
+  const int *tileW; // optional: weight slice per tile (deconvolution plans; then K == 1 and T == 1)
   int nOut, K, Cin, Cout, nTiles, T, nSuper, SA, SB;
   int dbg;    // developer switches (SCN_TC_DBG): 1 = skip A gathers, 2 = skip B copies, 4 = skip MMAs
   int kSplit; // > 1: the filter offsets of a supertile are split over kSplit CTAs, epilogue accumulates atomically
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
             if (P.dbg & 2) { mbar_arrive(bar); }
             else {
               mbar_arrive_expect_tx(bar, (uint32_t)bStageBytes);
-              bulk_g2s(smem_u32(sB + (size_t)bStage * bStageBytes), P.wimg + ((size_t)k * nc + c) * P.Cout * 32, (uint32_t)bStageBytes, bar);
+              bulk_g2s(smem_u32(sB + (size_t)bStage * bStageBytes), P.wimg + ((size_t)(P.tileW ? __ldg(P.tileW + st) : k) * nc + c) * P.Cout * 32, (uint32_t)bStageBytes, bar);
             }
             if (++bStage == (uint32_t)P.SB) { bStage = 0; bPhase ^= 1; }
           }
@@ -370,19 +371,39 @@ int tc_available() {
   return cached;
 }
 
+__global__ void k_pad_rows(const float *__restrict__ in, float *__restrict__ out, long n, int C, int Cp) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n * Cp; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    out[i] = c < C ? __ldg(in + (i / Cp) * C + c) : 0.f;
+  }
+}
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
-                        int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s) {
+                        int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
+                        long nInRows) {
   if (nOut == 0) return 0;
-  SCN_CHECK(Cin % 32 == 0 && Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && K <= 64, "tcgen05 path: unsupported channel counts");
+  if (Cin % 32 != 0) { // e.g. the 9-channel input convolution: zero-pad rows and weight slices to 32 channels
+    const int Cp = (Cin + 31) / 32 * 32;
+    float *xp = nullptr, *wp = nullptr;
+    SCN_CUDA(cudaMallocAsync((void **)&xp, (size_t)nInRows * Cp * 4, s));
+    SCN_CUDA(cudaMallocAsync((void **)&wp, (size_t)nWeights * Cp * Cout * 4, s));
+    k_pad_rows<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
+    SCN_CUDA(cudaMemsetAsync(wp, 0, (size_t)nWeights * Cp * Cout * 4, s));
+    SCN_CUDA(cudaMemcpy2DAsync(wp, (size_t)Cp * Cout * 4, W, (size_t)Cin * Cout * 4, (size_t)Cin * Cout * 4, nWeights, cudaMemcpyDeviceToDevice, s));
+    int r = launch_conv_plan_tc(xp, out, wp, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows);
+    cudaFreeAsync(xp, s);
+    cudaFreeAsync(wp, s);
+    return r;
+  }
+  SCN_CHECK(Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && K <= 64, "tcgen05 path: unsupported channel counts");
   TcParams P;
-  P.in = in; P.out = out; P.bias = bias; P.nbr = nbr; P.outRow = outRow; P.tileMask = tileMask;
+  P.in = in; P.out = out; P.bias = bias; P.nbr = nbr; P.outRow = outRow; P.tileMask = tileMask; P.tileW = tileW;
   P.nOut = nOut; P.K = K; P.Cin = Cin; P.Cout = Cout;
   P.nTiles = cdiv(nOut, kTileM);
   // supertile height: 2 tiles share every weight slice when the level is large enough for >= 2
   // work items per SM (accumulators double-buffered: 2 x T x Cout <= 512 TMEM columns); small levels
   // use 1-tile items and split the filter offsets over CTAs so the whole chip works on them.
   const int Tmax = Cout <= 128 ? 2 : 1;
-  P.T = (Tmax == 2 && P.nTiles >= 2 * kSMs * 2) ? 2 : 1;
+  P.T = (Tmax == 2 && P.nTiles >= 2 * kSMs * 2 && !tileW) ? 2 : 1;
   static int envT = -1, envSA = -1, envSB = -1, envDbg = 0;
   if (envT < 0) {
     envT = getenv("SCN_TC_T") ? atoi(getenv("SCN_TC_T")) : 0;
@@ -391,10 +412,10 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     envDbg = getenv("SCN_TC_DBG") ? atoi(getenv("SCN_TC_DBG")) : 0;
   }
   P.dbg = envDbg;
-  if (envT > 0 && envT <= Tmax) P.T = envT;
+  if (envT > 0 && envT <= Tmax && !tileW) P.T = envT;
   P.nSuper = cdiv(P.nTiles, P.T);
   P.kSplit = 1;
-  if (P.nSuper < kSMs / 2) P.kSplit = std::max(1, std::min(K, kSMs / P.nSuper));
+  if (P.nSuper < kSMs / 2 && !tileW) P.kSplit = std::max(1, std::min(K, kSMs / P.nSuper));
   P.SB = envSB > 0 ? envSB : (Cout <= 128 ? 3 : 2);
   size_t fixed = (size_t)P.SB * Cout * 128 + 4 * 32 * 36 * 4 + 64 * 8 + 16;
   P.SA = (int)std::min<size_t>(envSA > 0 ? envSA : 8, (227 * 1024 - fixed) / kAStageBytes);
@@ -402,9 +423,9 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   size_t smem = (size_t)P.SA * kAStageBytes + fixed;
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
   float *wimg = nullptr;
-  SCN_CUDA(cudaMallocAsync((void **)&wimg, (size_t)K * Cin * Cout * 4, s));
+  SCN_CUDA(cudaMallocAsync((void **)&wimg, (size_t)nWeights * Cin * Cout * 4, s));
   P.wimg = wimg;
-  k_prep_wimg<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, wimg, K, Cin, Cout);
+  k_prep_wimg<<<stream_grid((long)nWeights * Cin * Cout, 256), 256, 0, LS(s)>>>(W, wimg, nWeights, Cin, Cout);
   static bool attr = false;
   if (!attr) {
     SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -675,9 +675,7 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
 }
 
 // ------------------------------------------------------------------ strided convolution
-struct ConvGeom {
-  int f[3], s[3], outS[3], cnt[3], M, K;
-};
+typedef ConvGeomHost ConvGeom;
 // output cells of input point c: [lb, ub] per dim (OutputRegionCalculator, RectangularRegions.h:109-119);
 // event m enumerates them last-dimension-fastest.  Returns false when m is outside the region.
 __device__ __forceinline__ bool conv_event(const ConvGeom &G, const int4 &c, int m, int4 &j, int &off) {
@@ -776,6 +774,8 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   cudaStream_t s = stream;
   ConvEntry &e = conv[key];
   e.out = okey;
+  e.in = key.in;
+  e.geom = G;
   Grid &go = grids[okey];
   go.sz = okey;
   go.batch = gi->batch;
@@ -814,6 +814,79 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   SCN_CUDA(cudaGetLastError());
   SCN_TRY(build_tile_masks(e.plan));
   *out = &e;
+  return 0;
+}
+
+// ------------------------------------------------------------------ deconvolution plan
+struct DeconvMask {
+  ConvGeom G; const int *p2id; const int4 *coords;
+  __device__ unsigned long long operator()(int p) const {
+    int4 j; int off;
+    return conv_event(G, coords[p2id[p]], 0, j, off) ? 1ull << off : 0ull;
+  }
+};
+struct DeconvPair {
+  ConvGeom G; const int *p2id; const int4 *coords; GridView coarse; const int *coarseP2id;
+  __device__ int2 operator()(int p, int) const {
+    int id = p2id[p];
+    int4 j; int off;
+    conv_event(G, coords[id], 0, j, off);
+    int q = grid_lookup(coarse, j.x, j.y, j.z, j.w);
+    return make_int2(q >= 0 ? coarseP2id[q] : -1, id); // (coarse source row, fine destination row)
+  }
+};
+__global__ void k_deconv_pad(const int2 *__restrict__ pairs, const int *__restrict__ off, const int *__restrict__ tileW, const int *__restrict__ tileFirst,
+                             int nTiles, int *__restrict__ nbr, int *__restrict__ outRow, unsigned long long *__restrict__ tileMask) {
+  for (long slot = blockIdx.x * (long)blockDim.x + threadIdx.x; slot < (long)nTiles * 128; slot += (long)gridDim.x * blockDim.x) {
+    int tile = (int)(slot >> 7), k = tileW[tile];
+    int idx = (tile - tileFirst[k]) * 128 + (int)(slot & 127);
+    int2 pr = make_int2(-1, -1);
+    if (idx < off[k + 1] - off[k]) pr = pairs[off[k] + idx];
+    nbr[slot] = pr.x;
+    outRow[slot] = pr.y;
+    if ((slot & 127) == 0) tileMask[tile] = 1ull;
+  }
+}
+// Built on first use by a Deconvolution whose rulebook gives every fine site exactly one parent.
+int Metadata::get_deconv_plan(ConvEntry &e) {
+  if (e.deconv.built) return 0;
+  Grid *gf = find_grid(e.in.data()), *gc = find_grid(e.out.data());
+  SCN_CHECK(gf && gc && e.geom.M == 1 && e.rb.total == gf->n, "deconvolution plan needs a single-parent rulebook");
+  const int K = e.geom.K, n = gf->n;
+  cudaStream_t s = stream;
+  // per-offset lists in SPATIAL order of the fine grid (same counts as the reference rulebook)
+  int nT = cdiv(std::max(n, 1), kRuleTile);
+  int *tileCnt = alloc_n<int>((long)nT * K);
+  int2 *dpairs = alloc_n<int2>(std::max(1, n));
+  SCN_CHECK(tileCnt && dpairs, "alloc");
+  DeconvMask mf{e.geom, gf->p2id, gf->coords};
+  DeconvPair pf{e.geom, gf->p2id, gf->coords, view(*gc), gc->p2id};
+  k_rule_count<<<nT, kRuleTile, 0, LS(s)>>>(n, K, mf, tileCnt);
+  k_rule_scan<<<K, 1024, 0, LS(s)>>>(nT, K, tileCnt, d_scalars + 128);
+  if (n > 0) k_rule_write<<<nT, kRuleTile, 0, LS(s)>>>(n, K, mf, pf, tileCnt, e.rb.d_off, dpairs);
+  std::vector<int> tileW, tileFirst(K + 1, 0);
+  for (int k = 0; k < K; k++) {
+    tileFirst[k] = (int)tileW.size();
+    int tiles = cdiv(e.rb.off[k + 1] - e.rb.off[k], 128);
+    for (int t = 0; t < tiles; t++) tileW.push_back(k);
+  }
+  tileFirst[K] = (int)tileW.size();
+  DeconvPlan &d = e.deconv;
+  d.nTiles = (int)tileW.size();
+  d.nbr = alloc_n<int>(std::max(1, d.nTiles) * 128l);
+  d.outRow = alloc_n<int>(std::max(1, d.nTiles) * 128l);
+  d.tileW = alloc_n<int>(std::max(1, d.nTiles));
+  d.tileMask = alloc_n<unsigned long long>(std::max(1, d.nTiles) + 8);
+  int *dFirst = alloc_n<int>(K + 1);
+  SCN_CHECK(d.nbr && d.outRow && d.tileW && d.tileMask && dFirst, "alloc");
+  if (d.nTiles) {
+    SCN_CUDA(cudaMemcpyAsync(d.tileW, tileW.data(), d.nTiles * 4, cudaMemcpyHostToDevice, s));
+    SCN_CUDA(cudaMemcpyAsync(dFirst, tileFirst.data(), (K + 1) * 4, cudaMemcpyHostToDevice, s));
+    SCN_CUDA(cudaStreamSynchronize(s)); // the host vectors die with this scope
+    k_deconv_pad<<<stream_grid(d.nTiles * 128l, 256), 256, 0, LS(s)>>>(dpairs, e.rb.d_off, d.tileW, dFirst, d.nTiles, d.nbr, d.outRow, d.tileMask);
+  }
+  SCN_CUDA(cudaGetLastError());
+  d.built = true;
   return 0;
 }
 

@@ -57,8 +57,19 @@ struct NbrPlan {
 struct SubmKey { P3 sz, f; bool operator<(const SubmKey &o) const { return sz != o.sz ? sz < o.sz : f < o.f; } };
 struct ConvKey { P3 in, f, s; bool operator<(const ConvKey &o) const { return in != o.in ? in < o.in : (f != o.f ? f < o.f : s < o.s); } };
 
+// Deconvolution plan (single-parent strided rulebooks): fine sites grouped by filter offset, each group
+// padded to whole 128-row tiles, so that one tile needs exactly one weight slice.
+struct DeconvPlan {
+  bool built = false;
+  int nTiles = 0;
+  int *nbr = nullptr;      // [nTiles*128] coarse (source) row or -1 (padding)
+  int *outRow = nullptr;   // [nTiles*128] fine (destination) row or -1
+  int *tileW = nullptr;    // [nTiles] weight slice (filter offset) of the tile
+  unsigned long long *tileMask = nullptr; // [nTiles] all ones (kept for the kernel's interface)
+};
+struct ConvGeomHost { int f[3], s[3], outS[3], cnt[3], M, K; };
 struct SubmEntry { RuleBookDev rb; NbrPlan plan; };
-struct ConvEntry { RuleBookDev rb; NbrPlan plan; P3 out; };
+struct ConvEntry { RuleBookDev rb; NbrPlan plan; P3 out; P3 in; ConvGeomHost geom; DeconvPlan deconv; };
 
 struct InputRules {
   int mode = 0, maxActive = 0, nIn = 0, nOut = 0;
@@ -95,6 +106,7 @@ struct Metadata {
   int get_conv(const long *inS, const long *outS, const long *f, const long *s, ConvEntry **out);
   int spatial_locations(const long *sz, long *out, int outOnDevice);
   int build_tile_masks(NbrPlan &plan);
+  int get_deconv_plan(ConvEntry &e);
 };
 
 // ------------------------------------------------------------------ device helpers

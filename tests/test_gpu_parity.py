@@ -359,7 +359,7 @@ def _tc_or_skip(scn):
         pytest.skip("tcgen05 path needs an sm_100 device")
 
 
-@pytest.mark.parametrize("cin,cout,f", [(32, 32, 3), (64, 64, 3), (128, 128, 3), (256, 256, 3), (32, 128, 1), (64, 128, 3), (256, 128, 1)])
+@pytest.mark.parametrize("cin,cout,f", [(9, 32, 3), (32, 32, 3), (64, 64, 3), (128, 128, 3), (256, 256, 3), (32, 128, 1), (64, 128, 3), (256, 128, 1), (20, 64, 3)])
 def test_tc_submanifold_forward(cin, cout, f):
     scn, G, O = _setup_levels()
     _tc_or_skip(scn)
@@ -402,11 +402,18 @@ def test_tc_strided_conv_and_z_collapse(cin, cout):
         out, outz = torch.empty(0, device="cuda"), torch.empty(0, device="cuda")
         scn.SCN.Convolution_updateOutput(L(a), L(b), L(f), L(s), G.m, torch.from_numpy(x).cuda(), out, torch.from_numpy(w).cuda(), torch.Tensor())
         scn.SCN.Convolution_updateOutput(L(b), L(o), L(fz), L([1, 1, 1]), G.m, torch.from_numpy(xz).cuda(), outz, torch.from_numpy(wz).cuda(), torch.Tensor())
+        # deconvolution b -> a on the tensor-core path (per-offset tiles of the reversed rulebook)
+        xd = rs.randn(O.nactive(b), cin).astype(np.float32)
+        wantd, macsd = so.o_conv_forward(xd, w, rules, O.nactive(a), deconv=True)
+        outd = torch.empty(0, device="cuda")
+        gotd = scn.SCN.Deconvolution_updateOutput(L(b), L(a), L(f), L(s), G.m, torch.from_numpy(xd).cuda(), outd, torch.from_numpy(w).cuda(), torch.Tensor())
         torch.cuda.synchronize()
     finally:
         scn.set_math_mode("fp32")
     _close(out.cpu().numpy(), want, rtol=TF32_RTOL, atol=TF32_ATOL)
     _close(outz.cpu().numpy(), wantz, rtol=TF32_RTOL, atol=TF32_ATOL)
+    assert gotd == macsd and outd.shape == (O.nactive(a), cout)
+    _close(outd.cpu().numpy(), wantd, rtol=TF32_RTOL, atol=TF32_ATOL)
 
 
 def test_tc_large_level_many_supertiles():
