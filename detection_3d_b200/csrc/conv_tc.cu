@@ -123,15 +123,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
   unsigned char *sA = smem;
   unsigned char *sB = sA + (size_t)P.SA * kAStageBytes;
   float *sEpi = reinterpret_cast<float *>(sB + (size_t)P.SB * bStageBytes); // 4 warps x 32 rows x 36 floats
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + 4 * 32 * 36);
+  int *sIds = reinterpret_cast<int *>(sEpi + 4 * 32 * 36);                   // T*128*K neighbour ids of the current work item
+  const int idsPerItem = P.T * kTileM * P.K;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sIds + (size_t)idsPerItem);
   uint64_t *aFull = bars, *aEmpty = bars + P.SA, *bFull = bars + 2 * P.SA, *bEmpty = bars + 2 * P.SA + P.SB;
   uint64_t *accFull = bars + 2 * P.SA + 2 * P.SB, *accEmpty = accFull + 2;
-  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 2);
+  uint64_t *idsFull = accEmpty + 2;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(idsFull + 2);
 
   if (tid == 0) {
-    for (int i = 0; i < P.SA; i++) { mbar_init(smem_u32(aFull + i), 4); mbar_init(smem_u32(aEmpty + i), 1); }
+    for (int i = 0; i < P.SA; i++) { mbar_init(smem_u32(aFull + i), 1); mbar_init(smem_u32(aEmpty + i), 1); }
     for (int i = 0; i < P.SB; i++) { mbar_init(smem_u32(bFull + i), 1); mbar_init(smem_u32(bEmpty + i), 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
+    for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); mbar_init(smem_u32(idsFull + i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 8) {
@@ -199,74 +202,76 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
     }
   } else if (warp < 8) {
     // ============================ A producer ============================
+    // Each of the 4 producer warps gathers WHOLE stages (128 rows x 128 B) on its own: warp w owns
+    // the stages n with n % 4 == w, so four gathers proceed independently and every warp keeps two
+    // of its own stages in flight (SA = 8 ring slots; slot = n % SA is owned by warp slot % 4).
+    const int pw = warp - 4;
     const int ptid = tid - 128;
-    const int rg = ptid >> 3, chunk = ptid & 7; // 8 threads per row; a thread owns rows rg*8 .. rg*8+7
-    uint32_t stage = 0, phase = 0;
-    for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
+    const int chunk = lane & 7, rsub = lane >> 3; // lane -> 16-byte chunk of rows rsub, rsub+4, ...
+    const uint32_t idsBytes = (uint32_t)idsPerItem * 4u;
+    auto issue_ids = [&](int wi) {
+      const int st = wi / P.kSplit;
+      const uint32_t bar = smem_u32(idsFull);
+      mbar_arrive_expect_tx(bar, idsBytes);
+      bulk_g2s(smem_u32(sIds), P.nbr + (size_t)st * idsPerItem, idsBytes, bar);
+    };
+    if (ptid == 0 && (int)blockIdx.x < nWork) issue_ids(blockIdx.x);
+    uint32_t n = 0;                 // global stage counter (all warps count every stage)
+    uint32_t pend0 = 0, pend1 = 0;  // ring slots (+1) of this warp's gathers that are not yet published
+    int it = 0;
+    for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
       const int st = wi / P.kSplit, part = wi % P.kSplit;
       const int kLo = P.K * part / P.kSplit, kHi = P.K * (part + 1) / P.kSplit;
       const unsigned long long kmask = range_mask(kLo, kHi);
       unsigned long long m[2], uni = 0;
       for (int t = 0; t < 2; t++) { m[t] = (t < P.T && st * P.T + t < P.nTiles) ? (__ldg(P.tileMask + st * P.T + t) & kmask) : 0ull; uni |= m[t]; }
-      // neighbour ids live in registers, fetched one filter offset ahead
-      int ids[2][8], nxt[2][8];
-      auto load_ids = [&](int k, int (&dst)[2][8]) {
-#pragma unroll
-        for (int t = 0; t < 2; t++)
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const long p = (long)(st * P.T + t) * kTileM + rg * 8 + i;
-            dst[t][i] = (t < P.T && p < P.nOut && ((m[t] >> k) & 1ull)) ? __ldg(P.nbr + p * P.K + k) : -1;
-          }
-      };
-      int k = uni ? __ffsll((long long)uni) - 1 : P.K;
-      if (k < P.K) load_ids(k, nxt);
-      int pending = 0;
-      uint32_t pubStage = stage;
-      while (k < P.K) {
-#pragma unroll
-        for (int t = 0; t < 2; t++)
-#pragma unroll
-          for (int i = 0; i < 8; i++) ids[t][i] = nxt[t][i];
-        const unsigned long long rest = (k + 1 < 64) ? (uni >> (k + 1)) : 0ull;
-        const int kNext = rest ? k + 1 + (__ffsll((long long)rest) - 1) : P.K;
-        if (kNext < P.K) load_ids(kNext, nxt);
+      mbar_wait(smem_u32(idsFull), it & 1);
+      for (int k = kLo; k < kHi; k++) {
+        if (!((uni >> k) & 1ull)) continue;
         for (int c = 0; c < nc; c++) {
 #pragma unroll
           for (int t = 0; t < 2; t++) {
             if (!((m[t] >> k) & 1ull)) continue;
-            mbar_wait(smem_u32(aEmpty + stage), phase ^ 1);
-            const uint32_t sbase = smem_u32(sA + (size_t)stage * kAStageBytes) + (uint32_t)(rg * 8) * 128u;
+            const uint32_t mine = n & 3u, slot = n % (uint32_t)P.SA, round = n / (uint32_t)P.SA;
+            n++;
+            if (mine != (uint32_t)pw) continue;
+            // publish the older of my two gathers before starting a third
+            if (pend0 && pend1) {
+              cp_async_wait<1>();
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(aFull + (pend0 - 1)));
+              pend0 = pend1; pend1 = 0;
+            }
+            mbar_wait(smem_u32(aEmpty + slot), (round & 1u) ^ 1u);
+            const uint32_t sbase = smem_u32(sA + (size_t)slot * kAStageBytes);
+            const int *ids = sIds + (size_t)(t * kTileM) * P.K + k;
             if (!(P.dbg & 1)) {
-#pragma unroll
-              for (int i = 0; i < 8; i++) {
-                const int id = ids[t][i];
+#pragma unroll 8
+              for (int i = 0; i < 32; i++) {
+                const int row = i * 4 + rsub;
+                const int id = ids[row * P.K];
                 const float *src = P.in + (size_t)(id >= 0 ? id : 0) * P.Cin + c * 32 + chunk * 4;
-                cp_async16(sbase + i * 128 + ((chunk ^ i) << 4), src, id >= 0 ? 16u : 0u);
+                cp_async16(sbase + row * 128 + ((chunk ^ (row & 7)) << 4), src, id >= 0 ? 16u : 0u);
               }
             }
             cp_async_commit();
-            if (++stage == (uint32_t)P.SA) { stage = 0; phase ^= 1; }
-            if (++pending == kInflight) {
-              cp_async_wait<kInflight - 1>();
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(aFull + pubStage));
-              if (++pubStage == (uint32_t)P.SA) pubStage = 0;
-              pending--;
-            }
+            if (!pend0) pend0 = slot + 1; else pend1 = slot + 1;
           }
         }
-        k = kNext;
       }
+      // all gathers of this item are issued: once every producer warp got here the id buffer is free
+      // and the next item's ids stream in while the last stages drain
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (ptid == 0 && wi + (int)gridDim.x < nWork) issue_ids(wi + gridDim.x);
       cp_async_wait<0>();
       fence_proxy_async();
       __syncwarp();
-      while (pending > 0) {
-        if (lane == 0) mbar_arrive(smem_u32(aFull + pubStage));
-        if (++pubStage == (uint32_t)P.SA) pubStage = 0;
-        pending--;
+      if (lane == 0) {
+        if (pend0) mbar_arrive(smem_u32(aFull + (pend0 - 1)));
+        if (pend1) mbar_arrive(smem_u32(aFull + (pend1 - 1)));
       }
+      pend0 = pend1 = 0;
     }
   } else if (warp == 8) {
     // ============================ MMA issuer ============================
@@ -294,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
             for (int t = 0; t < 2; t++) {
               if (!((m[t] >> k) & 1ull)) continue;
               mbar_wait(smem_u32(aFull + aStage), aPhase);
-              tc_fence_after();
+              if (!(P.dbg & 8)) tc_fence_after();
               const uint64_t aDesc = smem_desc_sw128(smem_u32(sA + (size_t)aStage * kAStageBytes));
               const uint32_t d = tmemBase + (uint32_t)(a * accCols + t * P.Cout);
               if (!(P.dbg & 4)) {
@@ -303,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
                   tc_mma_tf32(d, aDesc + (uint64_t)(j * 2), bDesc + (uint64_t)(j * 2), idesc, ((started >> t) & 1u) | (j > 0));
               }
               started |= 1u << t;
-              tc_commit(smem_u32(aEmpty + aStage));
+              if (P.dbg & 16) mbar_arrive(smem_u32(aEmpty + aStage)); else tc_commit(smem_u32(aEmpty + aStage));
               if (++aStage == (uint32_t)P.SA) { aStage = 0; aPhase ^= 1; }
             }
             tc_commit(smem_u32(bEmpty + bStage));
@@ -403,7 +408,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   // work items per SM (accumulators double-buffered: 2 x T x Cout <= 512 TMEM columns); small levels
   // use 1-tile items and split the filter offsets over CTAs so the whole chip works on them.
   const int Tmax = Cout <= 128 ? 2 : 1;
-  P.T = (Tmax == 2 && P.nTiles >= 2 * kSMs * 2 && !tileW) ? 2 : 1;
+  P.T = (Tmax == 2 && P.nTiles >= 2 * kSMs * 2 && !tileW && K <= 32) ? 2 : 1;
   static int envT = -1, envSA = -1, envSB = -1, envDbg = 0;
   if (envT < 0) {
     envT = getenv("SCN_TC_T") ? atoi(getenv("SCN_TC_T")) : 0;
@@ -416,10 +421,12 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   P.nSuper = cdiv(P.nTiles, P.T);
   P.kSplit = 1;
   if (P.nSuper < kSMs / 2 && !tileW) P.kSplit = std::max(1, std::min(K, kSMs / P.nSuper));
-  P.SB = envSB > 0 ? envSB : (Cout <= 128 ? 3 : 2);
-  size_t fixed = (size_t)P.SB * Cout * 128 + 4 * 32 * 36 * 4 + 64 * 8 + 16;
+  // weight-slice ring: ~48 KB deep (a slice is only Cout x 128 B, and one is needed per filter offset)
+  P.SB = envSB > 0 ? envSB : std::max(2, std::min(12, (48 * 1024) / (Cout * 128)));
+  size_t fixed = (size_t)P.SB * Cout * 128 + 4 * 32 * 36 * 4 + (size_t)P.T * kTileM * K * 4 + 64 * 8 + 16;
   P.SA = (int)std::min<size_t>(envSA > 0 ? envSA : 8, (227 * 1024 - fixed) / kAStageBytes);
-  SCN_CHECK(P.SA > kInflight, "tcgen05 path: shared memory budget exceeded");
+  P.SA = P.SA >= 8 ? 8 : 4; // ring slots are statically owned by the 4 producer warps
+  SCN_CHECK((size_t)P.SA * kAStageBytes + fixed <= 227 * 1024, "tcgen05 path: shared memory budget exceeded");
   size_t smem = (size_t)P.SA * kAStageBytes + fixed;
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
   float *wimg = nullptr;

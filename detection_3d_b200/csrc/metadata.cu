@@ -661,8 +661,11 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   e.plan.K = (int)K;
   e.plan.nOut = g->n;
   e.plan.outRow = g->p2id;
-  e.plan.nbr = alloc_n<int>(std::max(1l, (long)g->n * K));
+  // rows padded to whole 256-site work items (pad = -1) so the kernel can bulk-copy an item's ids
+  const long nPad = ((long)g->n + 255) / 256 * 256;
+  e.plan.nbr = alloc_n<int>(std::max(1l, nPad * K));
   SCN_CHECK(e.plan.nbr, "alloc");
+  if (nPad > g->n) SCN_CUDA(cudaMemsetAsync(e.plan.nbr + (long)g->n * K, 0xff, (nPad - g->n) * K * 4, stream));
   SCN_CUDA(cudaMemsetAsync(d_scalars, 0, 4, stream));
   if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, d_scalars);
   SCN_TRY(build_rule_lists(*this, g->n, (int)K, SubmMask{g->rank2id, g->id2p, e.plan.nbr, (int)K},
@@ -807,9 +810,10 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   go.built = true;
   // output-stationary plan
   e.plan.K = G.K; e.plan.nOut = go.n; e.plan.outRow = go.p2id; e.plan.nValid = e.rb.total;
-  e.plan.nbr = alloc_n<int>(std::max(1l, (long)go.n * G.K));
+  const long nPadOut = ((long)go.n + 255) / 256 * 256;
+  e.plan.nbr = alloc_n<int>(std::max(1l, nPadOut * G.K));
   SCN_CHECK(e.plan.nbr, "alloc");
-  SCN_CUDA(cudaMemsetAsync(e.plan.nbr, 0xff, std::max(1l, (long)go.n * G.K) * 4, s));
+  SCN_CUDA(cudaMemsetAsync(e.plan.nbr, 0xff, std::max(1l, nPadOut * G.K) * 4, s));
   if (E) k_conv_plan<<<stream_grid(E, 256), 256, 0, LS(s)>>>(G, gi->rank2id, gi->coords, evQ, n, e.plan.nbr);
   SCN_CUDA(cudaGetLastError());
   SCN_TRY(build_tile_masks(e.plan));
@@ -847,6 +851,19 @@ __global__ void k_deconv_pad(const int2 *__restrict__ pairs, const int *__restri
     if ((slot & 127) == 0) tileMask[tile] = 1ull;
   }
 }
+// tile -> filter offset table, from the list offsets already on the device (no host round trip)
+__global__ void k_deconv_tiles(const int *__restrict__ off, int K, int *__restrict__ tileW, int *__restrict__ tileFirst) {
+  __shared__ int first[65];
+  if (threadIdx.x == 0) {
+    int a = 0;
+    for (int k = 0; k < K; k++) { first[k] = a; a += (off[k + 1] - off[k] + 127) / 128; }
+    first[K] = a;
+  }
+  __syncthreads();
+  for (int k = 0; k <= K; k++) if (threadIdx.x == 0) tileFirst[k] = first[k];
+  for (int k = 0; k < K; k++)
+    for (int t = first[k] + threadIdx.x; t < first[k + 1]; t += blockDim.x) tileW[t] = k;
+}
 // Built on first use by a Deconvolution whose rulebook gives every fine site exactly one parent.
 int Metadata::get_deconv_plan(ConvEntry &e) {
   if (e.deconv.built) return 0;
@@ -864,15 +881,9 @@ int Metadata::get_deconv_plan(ConvEntry &e) {
   k_rule_count<<<nT, kRuleTile, 0, LS(s)>>>(n, K, mf, tileCnt);
   k_rule_scan<<<K, 1024, 0, LS(s)>>>(nT, K, tileCnt, d_scalars + 128);
   if (n > 0) k_rule_write<<<nT, kRuleTile, 0, LS(s)>>>(n, K, mf, pf, tileCnt, e.rb.d_off, dpairs);
-  std::vector<int> tileW, tileFirst(K + 1, 0);
-  for (int k = 0; k < K; k++) {
-    tileFirst[k] = (int)tileW.size();
-    int tiles = cdiv(e.rb.off[k + 1] - e.rb.off[k], 128);
-    for (int t = 0; t < tiles; t++) tileW.push_back(k);
-  }
-  tileFirst[K] = (int)tileW.size();
   DeconvPlan &d = e.deconv;
-  d.nTiles = (int)tileW.size();
+  d.nTiles = 0;
+  for (int k = 0; k < K; k++) d.nTiles += cdiv(e.rb.off[k + 1] - e.rb.off[k], 128);
   d.nbr = alloc_n<int>(std::max(1, d.nTiles) * 128l);
   d.outRow = alloc_n<int>(std::max(1, d.nTiles) * 128l);
   d.tileW = alloc_n<int>(std::max(1, d.nTiles));
@@ -880,9 +891,7 @@ int Metadata::get_deconv_plan(ConvEntry &e) {
   int *dFirst = alloc_n<int>(K + 1);
   SCN_CHECK(d.nbr && d.outRow && d.tileW && d.tileMask && dFirst, "alloc");
   if (d.nTiles) {
-    SCN_CUDA(cudaMemcpyAsync(d.tileW, tileW.data(), d.nTiles * 4, cudaMemcpyHostToDevice, s));
-    SCN_CUDA(cudaMemcpyAsync(dFirst, tileFirst.data(), (K + 1) * 4, cudaMemcpyHostToDevice, s));
-    SCN_CUDA(cudaStreamSynchronize(s)); // the host vectors die with this scope
+    k_deconv_tiles<<<1, 256, 0, LS(s)>>>(e.rb.d_off, K, d.tileW, dFirst);
     k_deconv_pad<<<stream_grid(d.nTiles * 128l, 256), 256, 0, LS(s)>>>(dpairs, e.rb.d_off, d.tileW, dFirst, d.nTiles, d.nbr, d.outRow, d.tileMask);
   }
   SCN_CUDA(cudaGetLastError());

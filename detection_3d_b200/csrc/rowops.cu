@@ -23,7 +23,18 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, l
   const long r0 = (long)blockIdx.x * rowsPerCta;
   const long r1 = min(n, r0 + rowsPerCta);
   if (rl < rowLanes) {
-    for (long r = r0 + rl; r < r1; r += rowLanes) {
+    long r = r0 + rl;
+    for (; r + 3l * rowLanes < r1; r += 4l * rowLanes) { // 4 independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) v[u] = __ldg(reinterpret_cast<const float4 *>(x + (r + (long)u * rowLanes) * C) + cg);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+        q.x = fmaf(v[u].x, v[u].x, q.x); q.y = fmaf(v[u].y, v[u].y, q.y); q.z = fmaf(v[u].z, v[u].z, q.z); q.w = fmaf(v[u].w, v[u].w, q.w);
+      }
+    }
+    for (; r < r1; r += rowLanes) {
       float4 v = __ldg(reinterpret_cast<const float4 *>(x + r * C) + cg);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
@@ -126,7 +137,7 @@ __global__ void __launch_bounds__(256) k_bn_apply_scalar(const float *__restrict
 static int bn_stats_launch(const float *x, long n, int C, double *stats, cudaStream_t s) {
   SCN_CUDA(cudaMemsetAsync(stats, 0, 2 * C * sizeof(double), s));
   if (n == 0) return 0;
-  int rowsPerCta = (int)std::max<long>(64, (n + kSMs * 16 - 1) / (kSMs * 16));
+  int rowsPerCta = (int)std::max<long>(64, (n + kSMs * 8 - 1) / (kSMs * 8)); // <= 8 CTAs per SM: few atomics per channel
   int grid = cdiv(n, rowsPerCta);
   if (C % 4 == 0) {
     SCN_CHECK(C / 4 <= 256, "BatchNorm: more than 1024 channels not supported");
