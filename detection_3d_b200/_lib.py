@@ -31,15 +31,15 @@ SYMBOLS = {
     "scn_rulebook_info": (_i, [_vp, _i, L3, L3, L3, _pi, _pl]),
     "scn_rulebook_copy": (_i, [_vp, _i, L3, L3, L3, _i, _vp]),
     "scn_iteration_order": (_i, [_vp, L3, _vp]),
-    "scn_submanifold_convolution_forward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd]),
-    "scn_convolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd]),
-    "scn_deconvolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd]),
+    "scn_submanifold_convolution_forward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp]),
+    "scn_convolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp]),
+    "scn_deconvolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp]),
     "scn_submanifold_convolution_backward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "scn_convolution_backward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "scn_deconvolution_backward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
-    "scn_batchnorm_forward": (_i, [_vp, _vp, _l, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _vp]),
+    "scn_batchnorm_forward": (_i, [_vp, _vp, _l, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _vp, _vp]),
     "scn_batchnorm_backward": (_i, [_vp, _vp, _vp, _vp, _l, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
-    "scn_add_features": (_i, [_vp, _vp, _vp, _l, _vp]),
+    "scn_add_features": (_i, [_vp, _vp, _vp, _l, _vp, _vp]),
     "scn_set_math_mode": (_i, [_i]),
     "scn_get_math_mode": (_i, []),
     "scn_tensor_core_path_available": (_i, []),

@@ -11,18 +11,18 @@ int launch_conv_plan_simt(const float *in, float *out, const float *W, const int
 int launch_conv_list_simt(const float *in, float *out, const float *W, const int2 *pairs, const int *d_off, const int *offHost, int K, int Cin,
                           int Cout, int srcIsY, int singlePass, cudaStream_t s);
 int bn_forward(const float *x, float *y, long n, int C, float *saveMean, float *saveInvStd, float *runningMean, float *runningVar,
-               const float *weight, const float *bias, float eps, float momentum, int mode, float leak, void *workspace, cudaStream_t s);
+               const float *weight, const float *bias, float eps, float momentum, int mode, float leak, void *workspace, cudaStream_t s, void *y16);
 int bn_backward(const float *x, float *dx, const float *y, float *dy, long n, int C, const float *saveMean, const float *saveInvStd,
                 const float *weight, float *dWeight, float *dBias, float leak, void *workspace, cudaStream_t s);
 int input_forward(const float *in, float *out, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
 int input_backward(float *din, const float *dout, long nIn, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
-int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s);
+int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s, void *o16);
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
                        const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s);
 int tc_available();
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
-                        long nInRows);
+                        long nInRows, const void *in16);
 static int g_math_mode = 0;
 } // namespace scn
 
@@ -190,34 +190,34 @@ static bool tc_ok(int Cin, int Cout, int K) {
   return scn::g_math_mode != 0 && scn::tc_available() && Cout % 32 == 0 && Cout >= 32 && Cout <= 256 && K <= 64 && Cin >= 4 && Cin <= 1024;
 }
 static int run_plan(Metadata &M, const scn::NbrPlan &plan, const float *in, float *out, const float *w, const float *bias, int Cin, int Cout,
-                    long nInRows) {
+                    long nInRows, const void *in16) {
   if (tc_ok(Cin, Cout, plan.K))
     return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.tileMask, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.stream,
-                                    nullptr, plan.K, nInRows);
+                                    nullptr, plan.K, nInRows, in16);
   return scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.stream);
 }
 
 int scn_submanifold_convolution_forward(scn_metadata *m, const long sz[3], const long f[3], const float *in, float *out, const float *w,
-                                        const float *bias, int Cin, int Cout, double *macs) {
+                                        const float *bias, int Cin, int Cout, double *macs, const void *in_bf16) {
   M_OR_FAIL(m);
   scn::SubmEntry *e;
   SCN_TRY(m->md.get_submanifold(sz, f, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
-  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(sz)->n);
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(sz)->n, in_bf16);
 }
 int scn_convolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
-                            float *out, const float *w, const float *bias, int Cin, int Cout, double *macs) {
+                            float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16) {
   M_OR_FAIL(m);
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
-  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(inS)->n);
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(inS)->n, in_bf16);
 }
 __global__ void k_fill_rows_bias(float *out, long n, int C, const float *bias) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n * C; i += (long)gridDim.x * blockDim.x) out[i] = bias ? bias[i % C] : 0.f;
 }
 int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
-                              float *out, const float *w, const float *bias, int Cin, int Cout, double *macs) {
+                              float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16) {
   M_OR_FAIL(m);
   // CPU/Deconvolution.cpp:15-16: the rulebook of the convolution outS -> inS
   scn::ConvEntry *e;
@@ -232,7 +232,7 @@ int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long out
     SCN_TRY(m->md.get_deconv_plan(*e));
     const scn::DeconvPlan &d = e->deconv;
     return scn::launch_conv_plan_tc(in, out, w, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, 1, Cin, Cout, nullptr, scn::g_math_mode, s, d.tileW,
-                                    e->rb.nLists, m->md.find_grid(inS)->n);
+                                    e->rb.nLists, m->md.find_grid(inS)->n, in_bf16);
   }
   if (!single && gf->n) k_fill_rows_bias<<<scn::stream_grid((long)gf->n * Cout, 256), 256, 0, scn::LS(s)>>>(out, gf->n, Cout, bias);
   return scn::launch_conv_list_simt(in, out, w, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, Cin, Cout, /*srcIsY=*/1, single ? 1 : 0, s);
@@ -265,12 +265,12 @@ int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long ou
 
 int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *save_mean, float *save_invstd, float *running_mean,
                           float *running_var, const float *weight, const float *bias, float eps, float momentum, int mode, float leak,
-                          void *stream) {
+                          void *stream, void *out_bf16) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SCN_CHECK(mode >= 0 && mode <= 2, "mode");
   void *ws = nullptr;
   SCN_CUDA(cudaMallocAsync(&ws, (size_t)C * 24 + 64, s));
-  int r = scn::bn_forward(in, out, n, C, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, mode, leak, ws, s);
+  int r = scn::bn_forward(in, out, n, C, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, mode, leak, ws, s, out_bf16);
   cudaFreeAsync(ws, s);
   return r;
 }
@@ -283,7 +283,7 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, float
   cudaFreeAsync(ws, s);
   return r;
 }
-int scn_add_features(const float *a, const float *b, float *out, long n, void *stream) {
-  return scn::add_rows(a, b, out, n, static_cast<cudaStream_t>(stream));
+int scn_add_features(const float *a, const float *b, float *out, long n, void *stream, void *out_bf16) {
+  return scn::add_rows(a, b, out, n, static_cast<cudaStream_t>(stream), out_bf16);
 }
 }

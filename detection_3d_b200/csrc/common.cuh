@@ -51,6 +51,12 @@ static inline int stream_grid(long n, int threads, int per_sm = 8) {
   return (int)(want < cap ? want : cap);
 }
 
+// ---------------------------------------------------------------- execution-plan layout
+// (see NbrPlan in metadata.cuh) tiles of 128 output sites, ids of one filter offset contiguous
+constexpr int kPlanPad = 512;
+__host__ __device__ __forceinline__ long nbr_index(long p, int k, int K) { return ((p >> 7) * K + k) * 128 + (p & 127); }
+static inline long plan_padded(long n) { return (n + kPlanPad - 1) / kPlanPad * kPlanPad; }
+
 // ---------------------------------------------------------------- single-pass scan
 // Decoupled look-back exclusive scan (int32) with a fused consumer.  One launch:
 //   value_i  = in(i)

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) conv_plan_simt(const float *__restrict__ 
     for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
   for (int k = 0; k < K; k++) {
     int id = -1;
-    if (tid < TM && p0 + tid < nOut) id = __ldg(nbr + (long)(p0 + tid) * K + k);
+    if (tid < TM && p0 + tid < nOut) id = __ldg(nbr + nbr_index(p0 + tid, k, K));
     __syncthreads(); // previous offset's readers of s_ids / tiles are done
     if (tid < TM) s_ids[tid] = id;
     if (!__syncthreads_or(id >= 0)) continue;

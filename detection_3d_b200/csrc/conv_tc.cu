@@ -1,43 +1,55 @@
 // tcgen05 tensor-core gather-GEMM for sm_100a: the output-stationary sparse convolution
 //   out[row(p)] = sum_k  in[nbr[p][k]] @ W[k]
 // with fp32 accumulators in TMEM across ALL filter offsets (one store per output element, no
-// read-modify-write, no atomics), A rows gathered with 16-byte cp.async into 128B-swizzled
-// shared memory, W[k] streamed with cp.async.bulk from a pre-swizzled image, MMAs issued by one
-// thread (tcgen05.mma kind::tf32, M=128, N=Cout, K=8).
+// read-modify-write, no atomics).
 //
-// Persistent kernel, one CTA per SM, warp-specialised:
-//   warps 0-3  epilogue   (tcgen05.ld -> registers -> global rows; warp w owns TMEM lanes 32w..)
-//   warps 4-7  A producer (gather rows; 8 threads per 128-byte row chunk, coalesced)
-//   warp  8    MMA issuer (lane 0) + TMEM allocation
-//   warp  9    B loader   (lane 0, bulk copies)
-// A CTA owns a "supertile" of T = min(4, 512/Cout) tiles of 128 output sites whose accumulators
-// live in TMEM simultaneously, so each weight slice W[k][32 channels] is fetched once per
-// supertile instead of once per tile (L2 -> SM traffic of B is 1/T of A's).
+// Persistent kernel, one CTA per SM, warp-specialised (14 warps):
+//   warps 0-3   epilogue   (tcgen05.ld -> registers -> shared-memory transpose -> 128-byte row stores)
+//   warps 4-11  A producers (16-byte cp.async row gathers into 128B-swizzled K-major atoms)
+//   warp  12    MMA issuer (one thread: tcgen05.mma M=128, N=Cout, 32 bytes of K per instruction)
+//   warp  13    B loader   (one thread: cp.async.bulk of a pre-swizzled weight atom)
+//
+// Work item  = T <= 4 tiles of 128 output sites (x a range of filter offsets on small levels).
+// Stage      = one 128-byte K atom (32 tf32 / 64 bf16 channels) of ONE filter offset for ALL T tiles
+//              (T x 16 KB of gathered rows) + the matching weight atom (Cout x 128 B).
+// What was measured on B200 and shaped this (profiles/r1_conv_tc_design_notes.md):
+//   * the issuing thread pays ~400 cycles per barrier round trip (try_wait + fence + commit), so a
+//     stage must carry >= ~1000 cycles of MMA: 4 tiles x 4 MMAs x 64 cycles; one full and one
+//     empty barrier per stage shared by the A and B halves;
+//   * the weight atom is read once per stage and feeds T tiles: L2->SM traffic of W is 1/T of a
+//     per-tile scheme (with T = 2 it equalled the gather traffic);
+//   * TMA tile::gather4 delivers correct swizzled rows but only ~7.5 B/clk/SM at 128-byte rows,
+//     against ~32 B/clk/SM for 16-byte cp.async, hence cp.async gathers.
 //
 // Replaces dConvolution_KMxKN_forwardA/B (SCN/CUDA/Convolution.cu:57-203: SIMT tiles, fp64
 // accumulators, one launch + one blocking H2D rule copy per filter offset).
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <stdlib.h>
+#include <algorithm>
 
 namespace scn {
 
 constexpr int kTileM = 128;
-constexpr int kAStageBytes = kTileM * 128; // 128 rows x 32 tf32
-constexpr int kInflight = 5;               // A stages a producer thread keeps in flight
-constexpr int kThreads = 320;
+constexpr int kAtomBytes = kTileM * 128; // 128 rows x 128 B
+constexpr int kProdWarps = 8;
+constexpr int kThreads = 32 * (4 + kProdWarps + 2);
+constexpr int kMaxT = 4;
 
 struct TcParams {
-  const float *in;
+  const unsigned char *in; // activations, row-major, rowBytes per row (fp32 or bf16 elements)
   float *out;
-  const float *wimg;
+  const unsigned char *wimg;
   const float *bias;
   const int *nbr;
   const int *outRow;
   const unsigned long long *tileMask;
   const int *tileW; // optional: weight slice per tile (deconvolution plans; then K == 1 and T == 1)
-  int nOut, K, Cin, Cout, nTiles, T, nSuper, SA, SB;
+  long long *prof;  // developer: per-CTA stall counters (SCN_TC_PROF)
+  int nOut, K, Cout, nTiles, T, nSuper, S, nAcc;
+  int rowBytes, nAtoms, bf16;
   int dbg;    // developer switches (SCN_TC_DBG): 1 = skip A gathers, 2 = skip B copies, 4 = skip MMAs
-  int kSplit; // > 1: the filter offsets of a supertile are split over kSplit CTAs, epilogue accumulates atomically
+  int kSplit; // > 1: the filter offsets of a work item are split over kSplit CTAs, epilogue accumulates atomically
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -64,6 +76,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long &acc, bool on) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t srcBytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(srcBytes) : "memory");
 }
@@ -74,20 +92,42 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ bool elect_one() { // one lane of the (converged) warp
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t dTmem, uint64_t aDesc, uint64_t bDesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(dTmem),
-      "l"(aDesc), "l"(bDesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+template <bool BF16>
+__device__ __forceinline__ void tc_mma(uint32_t dTmem, uint64_t aDesc, uint64_t bDesc, uint32_t idesc, uint32_t accumulate) {
+  if (BF16)
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(dTmem),
+        "l"(aDesc), "l"(bDesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(dTmem),
+        "l"(aDesc), "l"(bDesc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // K-major, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
@@ -110,34 +150,46 @@ __device__ __forceinline__ unsigned long long range_mask(int lo, int hi) { // bi
   return a & ~((1ull << lo) - 1ull);
 }
 
+// the part of a work item every role needs: tiles, offset range, per-tile masks
+struct Item {
+  int st, part;
+  unsigned long long m[kMaxT], uni;
+};
+__device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
+  Item I;
+  I.st = wi / P.kSplit;
+  I.part = wi - I.st * P.kSplit;
+  const unsigned long long kmask = range_mask(P.K * I.part / P.kSplit, P.K * (I.part + 1) / P.kSplit);
+  I.uni = 0;
+#pragma unroll
+  for (int t = 0; t < kMaxT; t++) {
+    const int tile = I.st * P.T + t;
+    I.m[t] = (t < P.T && tile < P.nTiles) ? (__ldg(P.tileMask + tile) & kmask) : 0ull;
+    I.uni |= I.m[t];
+  }
+  return I;
+}
+
 // ------------------------------------------------------------------ kernel
-// Work item = (supertile of T <= 2 tiles, range of filter offsets).  Accumulators are double
-// buffered in TMEM (2 x T x Cout <= 512 columns) so the epilogue of item i overlaps the main loop
-// of item i+1.
-__global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
+template <bool BF16>
+__global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(const TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nc = P.Cin / 32;                 // K-atoms per filter offset
-  const int nWork = P.nSuper * P.kSplit;     // work items
-  const int bStageBytes = P.Cout * 128;      // Cout rows x 32 tf32
-  unsigned char *sA = smem;
-  unsigned char *sB = sA + (size_t)P.SA * kAStageBytes;
-  float *sEpi = reinterpret_cast<float *>(sB + (size_t)P.SB * bStageBytes); // 4 warps x 32 rows x 36 floats
-  int *sIds = reinterpret_cast<int *>(sEpi + 4 * 32 * 36);                   // T*128*K neighbour ids of the current work item
-  const int idsPerItem = P.T * kTileM * P.K;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sIds + (size_t)idsPerItem);
-  uint64_t *aFull = bars, *aEmpty = bars + P.SA, *bFull = bars + 2 * P.SA, *bEmpty = bars + 2 * P.SA + P.SB;
-  uint64_t *accFull = bars + 2 * P.SA + 2 * P.SB, *accEmpty = accFull + 2;
-  uint64_t *idsFull = accEmpty + 2;
-  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(idsFull + 2);
+  const int nWork = P.nSuper * P.kSplit;
+  const uint32_t bBytes = (uint32_t)P.Cout * 128u;
+  const uint32_t stageBytes = (uint32_t)P.T * kAtomBytes + bBytes; // [T A atoms][B atom]
+  unsigned char *sStage = smem;
+  float *sEpi = reinterpret_cast<float *>(sStage + (size_t)P.S * stageBytes); // 4 warps x 32 rows x 36 floats
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + 4 * 32 * 36);
+  uint64_t *full = bars, *empty = bars + P.S, *accFull = bars + 2 * P.S, *accEmpty = accFull + 2;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 2);
 
   if (tid == 0) {
-    for (int i = 0; i < P.SA; i++) { mbar_init(smem_u32(aFull + i), 1); mbar_init(smem_u32(aEmpty + i), 1); }
-    for (int i = 0; i < P.SB; i++) { mbar_init(smem_u32(bFull + i), 1); mbar_init(smem_u32(bEmpty + i), 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); mbar_init(smem_u32(idsFull + i), 1); }
+    for (int i = 0; i < P.S; i++) { mbar_init(smem_u32(full + i), kProdWarps + 1); mbar_init(smem_u32(empty + i), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 12) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -146,24 +198,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
   tc_fence_after();
   const uint32_t tmemBase = *tmemSlot;
   const int accCols = P.T * P.Cout; // columns of one accumulator stage
+  const bool prof = P.prof != nullptr;
+  long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;
+  const long long tStart = prof ? clock64() : 0;
 
   if (warp < 4) {
     // ============================ epilogue ============================
+    // warp w owns TMEM lanes 32w.. = rows 32w.. of every tile.  Per 32-column block: tcgen05.ld ->
+    // padded shared-memory block -> each store instruction writes four whole 128-byte row segments.
     float *stg = sEpi + warp * (32 * 36);
+    const int cc = (lane & 7) * 4, rsub = lane >> 3;
     int it = 0;
     for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
-      const int st = wi / P.kSplit, part = wi % P.kSplit;
-      const unsigned long long kmask = range_mask(P.K * part / P.kSplit, P.K * (part + 1) / P.kSplit);
-      const int a = it & 1;
-      mbar_wait(smem_u32(accFull + a), (it >> 1) & 1);
+      const Item I = load_item(P, wi);
+      const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
+      int myRow[kMaxT]; // output row of (tile t, TMEM lane), fetched before the accumulators are ready
+#pragma unroll
+      for (int t = 0; t < kMaxT; t++) {
+        const long p = (long)(I.st * P.T + t) * kTileM + warp * 32 + lane;
+        myRow[t] = (t < P.T && p < P.nOut) ? __ldg(P.outRow + p) : -1;
+      }
+      mbar_wait_t(smem_u32(accFull + a), use & 1, pw0, prof);
       tc_fence_after();
-      for (int t = 0; t < P.T; t++) {
-        const int tile = st * P.T + t;
-        if (tile >= P.nTiles) break;
-        const bool started = (__ldg(P.tileMask + tile) & kmask) != 0ull;
+#pragma unroll
+      for (int t = 0; t < kMaxT; t++) {
+        if (t >= P.T || I.st * P.T + t >= P.nTiles) continue;
+        const bool started = I.m[t] != 0ull;
         if (!started && P.kSplit > 1) continue; // nothing to add
-        const int p = tile * kTileM + warp * 32 + lane;
-        const int myRow = p < P.nOut ? __ldg(P.outRow + p) : -1;
+        int rows[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) rows[i] = __shfl_sync(0xffffffffu, myRow[t], i * 4 + rsub);
         for (int c0 = 0; c0 < P.Cout; c0 += 32) {
           uint32_t v[32];
           if (started) {
@@ -172,27 +236,31 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
 #pragma unroll
             for (int j = 0; j < 32; j++) v[j] = 0u;
           }
-          // stage the 32x32 block so that each store instruction writes whole 128-byte row segments
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4 *>(stg + lane * 36 + j) =
                 make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
           __syncwarp();
-          const int cc = (lane & 7) * 4;
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (P.bias && part == 0) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + c0 + cc));
+          if (P.bias && I.part == 0) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + c0 + cc));
+          float4 o[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            const int r = i * 4 + (lane >> 3);
-            const int row = __shfl_sync(0xffffffffu, myRow, r);
-            float4 o = *reinterpret_cast<const float4 *>(stg + r * 36 + cc);
-            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-            if (row >= 0) {
-              float *dst = P.out + (size_t)row * P.Cout + c0 + cc;
-              if (P.kSplit == 1) *reinterpret_cast<float4 *>(dst) = o;
-              else { atomicAdd(dst, o.x); atomicAdd(dst + 1, o.y); atomicAdd(dst + 2, o.z); atomicAdd(dst + 3, o.w); } // pre-zeroed by the launcher
-            }
+            o[i] = *reinterpret_cast<const float4 *>(stg + (i * 4 + rsub) * 36 + cc);
+            o[i].x += bv.x; o[i].y += bv.y; o[i].z += bv.z; o[i].w += bv.w;
+          }
+          if (P.kSplit == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              if (rows[i] >= 0) *reinterpret_cast<float4 *>(P.out + (size_t)rows[i] * P.Cout + c0 + cc) = o[i];
+          } else { // offsets split over CTAs: accumulate into the launcher-zeroed output
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              if (rows[i] >= 0) {
+                float *dst = P.out + (size_t)rows[i] * P.Cout + c0 + cc;
+                atomicAdd(dst, o[i].x); atomicAdd(dst + 1, o[i].y); atomicAdd(dst + 2, o[i].z); atomicAdd(dst + 3, o[i].w);
+              }
           }
         }
       }
@@ -200,169 +268,198 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(TcParams P) {
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(accEmpty + a));
     }
-  } else if (warp < 8) {
-    // ============================ A producer ============================
-    // Each of the 4 producer warps gathers WHOLE stages (128 rows x 128 B) on its own: warp w owns
-    // the stages n with n % 4 == w, so four gathers proceed independently and every warp keeps two
-    // of its own stages in flight (SA = 8 ring slots; slot = n % SA is owned by warp slot % 4).
+    if (prof && tid == 0) { P.prof[blockIdx.x * 32 + 0] = clock64() - tStart; P.prof[blockIdx.x * 32 + 1] = pw0; }
+  } else if (warp < 4 + kProdWarps) {
+    // ============================ A producers ============================
+    // Warp pw gathers rows [16 pw, 16 pw + 16) of every tile of the stage: 4 cp.async instructions
+    // per tile (8 lanes x 16 B = one 128-byte row chunk, 4 rows per instruction).  The ids of the
+    // current filter offset sit in registers (lanes 0-15 hold the warp's 16 rows of each tile) and
+    // those of the next active offset are fetched while the current one is gathered.
     const int pw = warp - 4;
-    const int ptid = tid - 128;
-    const int chunk = lane & 7, rsub = lane >> 3; // lane -> 16-byte chunk of rows rsub, rsub+4, ...
-    const uint32_t idsBytes = (uint32_t)idsPerItem * 4u;
-    auto issue_ids = [&](int wi) {
-      const int st = wi / P.kSplit;
-      const uint32_t bar = smem_u32(idsFull);
-      mbar_arrive_expect_tx(bar, idsBytes);
-      bulk_g2s(smem_u32(sIds), P.nbr + (size_t)st * idsPerItem, idsBytes, bar);
-    };
-    if (ptid == 0 && (int)blockIdx.x < nWork) issue_ids(blockIdx.x);
-    uint32_t n = 0;                 // global stage counter (all warps count every stage)
-    uint32_t pend0 = 0, pend1 = 0;  // ring slots (+1) of this warp's gathers that are not yet published
-    int it = 0;
-    for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
-      const int st = wi / P.kSplit, part = wi % P.kSplit;
-      const int kLo = P.K * part / P.kSplit, kHi = P.K * (part + 1) / P.kSplit;
-      const unsigned long long kmask = range_mask(kLo, kHi);
-      unsigned long long m[2], uni = 0;
-      for (int t = 0; t < 2; t++) { m[t] = (t < P.T && st * P.T + t < P.nTiles) ? (__ldg(P.tileMask + st * P.T + t) & kmask) : 0ull; uni |= m[t]; }
-      mbar_wait(smem_u32(idsFull), it & 1);
-      for (int k = kLo; k < kHi; k++) {
-        if (!((uni >> k) & 1ull)) continue;
-        for (int c = 0; c < nc; c++) {
+    const int chunk = lane & 7, rsub = lane >> 3;
+    uint32_t n = 0, slot = 0, round = 0; // stage counter, ring slot, ring round
+    int pendSlot = -1;    // stage issued but not yet published (only when the ring has >= 3 slots)
+    const bool lag = P.S >= 3;
+    for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
+      const Item I = load_item(P, wi);
+      if (!I.uni) continue;
+      const int *idBase = P.nbr + ((size_t)I.st * P.T * P.K) * 128 + pw * 16 + (lane & 15);
+      int idc[kMaxT], idn[kMaxT];
+      auto load_ids = [&](int k, int (&dst)[kMaxT]) {
 #pragma unroll
-          for (int t = 0; t < 2; t++) {
-            if (!((m[t] >> k) & 1ull)) continue;
-            const uint32_t mine = n & 3u, slot = n % (uint32_t)P.SA, round = n / (uint32_t)P.SA;
-            n++;
-            if (mine != (uint32_t)pw) continue;
-            // publish the older of my two gathers before starting a third
-            if (pend0 && pend1) {
-              cp_async_wait<1>();
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(aFull + (pend0 - 1)));
-              pend0 = pend1; pend1 = 0;
-            }
-            mbar_wait(smem_u32(aEmpty + slot), (round & 1u) ^ 1u);
-            const uint32_t sbase = smem_u32(sA + (size_t)slot * kAStageBytes);
-            const int *ids = sIds + (size_t)(t * kTileM) * P.K + k;
-            if (!(P.dbg & 1)) {
-#pragma unroll 8
-              for (int i = 0; i < 32; i++) {
-                const int row = i * 4 + rsub;
-                const int id = ids[row * P.K];
-                const float *src = P.in + (size_t)(id >= 0 ? id : 0) * P.Cin + c * 32 + chunk * 4;
-                cp_async16(sbase + row * 128 + ((chunk ^ (row & 7)) << 4), src, id >= 0 ? 16u : 0u);
+        for (int t = 0; t < kMaxT; t++) dst[t] = ((I.m[t] >> k) & 1ull) ? __ldg(idBase + ((size_t)t * P.K + k) * 128) : -1;
+      };
+      int k = __ffsll((long long)I.uni) - 1;
+      load_ids(k, idn);
+      while (k >= 0) {
+#pragma unroll
+        for (int t = 0; t < kMaxT; t++) idc[t] = idn[t];
+        const unsigned long long rest = (k + 1 < 64) ? (I.uni >> (k + 1)) : 0ull;
+        const int kNext = rest ? k + 1 + (__ffsll((long long)rest) - 1) : -1;
+        if (kNext >= 0) load_ids(kNext, idn);
+        for (int c = 0; c < P.nAtoms; c++) {
+          n++;
+          mbar_wait_t(smem_u32(empty + slot), (round & 1u) ^ 1u, pw0, prof);
+          const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
+          if (!(P.dbg & 1)) {
+#pragma unroll
+            for (int t = 0; t < kMaxT; t++) {
+              if (!((I.m[t] >> k) & 1ull)) continue; // uniform over the CTA
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                const int id = __shfl_sync(0xffffffffu, idc[t], i * 4 + rsub);
+                const int row = pw * 16 + i * 4 + rsub;
+                const unsigned char *src = P.in + (size_t)(id >= 0 ? id : 0) * P.rowBytes + c * 128 + chunk * 16;
+                cp_async16(sbase + t * kAtomBytes + row * 128 + ((chunk ^ (row & 7)) << 4), src, id >= 0 ? 16u : 0u);
               }
             }
-            cp_async_commit();
-            if (!pend0) pend0 = slot + 1; else pend1 = slot + 1;
           }
+          cp_async_commit();
+          if (lag) {
+            if (pendSlot >= 0) {
+              long long t0 = prof ? clock64() : 0;
+              cp_async_wait<1>();
+              if (prof) pw1 += clock64() - t0;
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(smem_u32(full + pendSlot));
+            }
+            pendSlot = (int)slot;
+          } else {
+            long long t0 = prof ? clock64() : 0;
+            cp_async_wait<0>();
+            if (prof) pw1 += clock64() - t0;
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(full + slot));
+          }
+          if (++slot == (uint32_t)P.S) { slot = 0; round++; }
         }
+        k = kNext;
       }
-      // all gathers of this item are issued: once every producer warp got here the id buffer is free
-      // and the next item's ids stream in while the last stages drain
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (ptid == 0 && wi + (int)gridDim.x < nWork) issue_ids(wi + gridDim.x);
+    }
+    if (pendSlot >= 0) {
       cp_async_wait<0>();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        if (pend0) mbar_arrive(smem_u32(aFull + (pend0 - 1)));
-        if (pend1) mbar_arrive(smem_u32(aFull + (pend1 - 1)));
-      }
-      pend0 = pend1 = 0;
+      if (lane == 0) mbar_arrive(smem_u32(full + pendSlot));
     }
-  } else if (warp == 8) {
+    if (prof && lane == 0 && pw == 0) { long long *q = P.prof + blockIdx.x * 32 + 4; q[0] = clock64() - tStart; q[1] = pw0; q[2] = pw1; q[3] = n; }
+  } else if (warp == 12) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=TF32, K-major both, N=Cout, M=128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.Cout >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      uint32_t aStage = 0, aPhase = 0, bStage = 0, bPhase = 0;
+    // The whole warp runs the control flow (converged), one elected lane issues: ptxas then keeps
+    // descriptors in uniform registers and emits straight-line UTCHMMA instead of a per-instruction
+    // election loop (measured: ~120 cycles per MMA issued from a divergent `if (lane == 0)` region).
+    {
+      // instruction descriptor: D=F32, A/B = TF32 (2) or BF16 (1), K-major both, N=Cout, M=128
+      const uint32_t fmt = BF16 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.Cout >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      uint32_t n = 0, slot = 0, round = 0;
       int it = 0;
+      const uint32_t sStage0 = smem_u32(sStage), full0 = smem_u32(full), empty0 = smem_u32(empty);
       for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
-        const int st = wi / P.kSplit, part = wi % P.kSplit;
-        const unsigned long long kmask = range_mask(P.K * part / P.kSplit, P.K * (part + 1) / P.kSplit);
-        unsigned long long m[2], uni = 0;
-        for (int t = 0; t < 2; t++) { m[t] = (t < P.T && st * P.T + t < P.nTiles) ? (__ldg(P.tileMask + st * P.T + t) & kmask) : 0ull; uni |= m[t]; }
-        const int a = it & 1;
-        mbar_wait(smem_u32(accEmpty + a), ((it >> 1) & 1) ^ 1); // epilogue has drained this accumulator stage
+        const Item I = load_item(P, wi);
+        const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
+        mbar_wait_t(smem_u32(accEmpty + a), (use & 1) ^ 1, pw0, prof); // epilogue has drained this accumulator stage
         tc_fence_after();
         uint32_t started = 0;
-        for (int k = 0; k < P.K; k++) {
-          if (!((uni >> k) & 1ull)) continue;
-          for (int c = 0; c < nc; c++) {
-            mbar_wait(smem_u32(bFull + bStage), bPhase);
+        unsigned long long rest = I.uni;
+        while (rest) {
+          const int k = __ffsll((long long)rest) - 1;
+          rest &= rest - 1;
+          for (int c = 0; c < P.nAtoms; c++) {
+            n++;
+            mbar_wait_t(full0 + slot * 8u, round & 1u, pw1, prof);
             tc_fence_after();
-            const uint64_t bDesc = smem_desc_sw128(smem_u32(sB + (size_t)bStage * bStageBytes));
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-              if (!((m[t] >> k) & 1ull)) continue;
-              mbar_wait(smem_u32(aFull + aStage), aPhase);
-              if (!(P.dbg & 8)) tc_fence_after();
-              const uint64_t aDesc = smem_desc_sw128(smem_u32(sA + (size_t)aStage * kAStageBytes));
-              const uint32_t d = tmemBase + (uint32_t)(a * accCols + t * P.Cout);
+            const uint32_t sbase = sStage0 + slot * stageBytes;
+            const uint64_t bDesc = smem_desc_sw128(sbase + (uint32_t)P.T * kAtomBytes);
+            const long long tI0 = prof ? clock64() : 0;
+            if (elect_one()) {
               if (!(P.dbg & 4)) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) // 4 x (K = 8 tf32 = 32 bytes) inside the 128-byte swizzle atom
-                  tc_mma_tf32(d, aDesc + (uint64_t)(j * 2), bDesc + (uint64_t)(j * 2), idesc, ((started >> t) & 1u) | (j > 0));
+                for (int t = 0; t < kMaxT; t++) {
+                  if (!((I.m[t] >> k) & 1ull)) continue;
+                  const uint64_t aDesc = smem_desc_sw128(sbase + t * kAtomBytes);
+                  const uint32_t d = tmemBase + (uint32_t)(a * accCols + t * P.Cout);
+#pragma unroll
+                  for (int j = 0; j < 4; j++) // 4 x 32 bytes of K inside the 128-byte swizzle atom
+                    tc_mma<BF16>(d, aDesc + (uint64_t)(j * 2), bDesc + (uint64_t)(j * 2), idesc, ((started >> t) & 1u) | (j > 0));
+                }
               }
-              started |= 1u << t;
-              if (P.dbg & 16) mbar_arrive(smem_u32(aEmpty + aStage)); else tc_commit(smem_u32(aEmpty + aStage));
-              if (++aStage == (uint32_t)P.SA) { aStage = 0; aPhase ^= 1; }
+              const long long tI1 = prof ? clock64() : 0;
+              tc_commit(empty0 + slot * 8u);
+              if (prof) { pw2 += tI1 - tI0; pw3 += clock64() - tI1; }
             }
-            tc_commit(smem_u32(bEmpty + bStage));
-            if (++bStage == (uint32_t)P.SB) { bStage = 0; bPhase ^= 1; }
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < kMaxT; t++) started |= (uint32_t)((I.m[t] >> k) & 1ull) << t;
+            if (++slot == (uint32_t)P.S) { slot = 0; round++; }
           }
         }
-        tc_commit(smem_u32(accFull + a));
+        if (elect_one()) tc_commit(smem_u32(accFull + a));
+        __syncwarp();
+      }
+      if (prof) { // pw2/pw3 live in whichever lane was elected
+        long long *q = P.prof + blockIdx.x * 32 + 10;
+        if (lane == 0) { q[0] = clock64() - tStart; q[1] = pw0; q[2] = pw1; q[3] = n; }
+        if (pw2 | pw3) { q[4] = pw2; q[5] = pw3; }
       }
     }
   } else {
     // ============================ B loader ============================
     if (lane == 0) {
-      uint32_t bStage = 0, bPhase = 0;
+      uint32_t n = 0, slot = 0, round = 0;
       for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
-        const int st = wi / P.kSplit, part = wi % P.kSplit;
-        const unsigned long long kmask = range_mask(P.K * part / P.kSplit, P.K * (part + 1) / P.kSplit);
-        unsigned long long uni = 0;
-        for (int t = 0; t < P.T; t++) if (st * P.T + t < P.nTiles) uni |= __ldg(P.tileMask + st * P.T + t) & kmask;
-        for (int k = 0; k < P.K; k++) {
-          if (!((uni >> k) & 1ull)) continue;
-          for (int c = 0; c < nc; c++) {
-            mbar_wait(smem_u32(bEmpty + bStage), bPhase ^ 1);
-            const uint32_t bar = smem_u32(bFull + bStage);
+        const Item I = load_item(P, wi);
+        unsigned long long rest = I.uni;
+        while (rest) {
+          const int k = __ffsll((long long)rest) - 1;
+          rest &= rest - 1;
+          const int w = P.tileW ? __ldg(P.tileW + I.st) : k;
+          for (int c = 0; c < P.nAtoms; c++) {
+            n++;
+            mbar_wait_t(smem_u32(empty + slot), (round & 1u) ^ 1u, pw0, prof);
+            const uint32_t bar = smem_u32(full + slot);
             if (P.dbg & 2) { mbar_arrive(bar); }
             else {
-              mbar_arrive_expect_tx(bar, (uint32_t)bStageBytes);
-              bulk_g2s(smem_u32(sB + (size_t)bStage * bStageBytes), P.wimg + ((size_t)(P.tileW ? __ldg(P.tileW + st) : k) * nc + c) * P.Cout * 32, (uint32_t)bStageBytes, bar);
+              mbar_arrive_expect_tx(bar, bBytes);
+              bulk_g2s(smem_u32(sStage) + slot * stageBytes + (uint32_t)P.T * kAtomBytes, P.wimg + ((size_t)w * P.nAtoms + c) * bBytes, bBytes, bar);
             }
-            if (++bStage == (uint32_t)P.SB) { bStage = 0; bPhase ^= 1; }
+            if (++slot == (uint32_t)P.S) { slot = 0; round++; }
           }
         }
       }
+      if (prof) { long long *q = P.prof + blockIdx.x * 32 + 16; q[0] = clock64() - tStart; q[1] = pw0; q[2] = n; }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
   }
 }
 
-// W [K][Cin][Cout] fp32 -> per (k, 32-channel atom) the exact shared-memory image of the B operand:
-// Cout rows x 128 bytes, 16-byte chunks XOR-swizzled by (row & 7), values rounded to TF32 (rna).
-__global__ void k_prep_wimg(const float *__restrict__ W, float *__restrict__ img, int K, int Cin, int Cout) {
+// W [K][Cin][Cout] fp32 -> per (k, 128-byte K atom) the exact shared-memory image of the B operand:
+// Cout rows x 128 bytes (32 tf32 / 64 bf16 input channels of one output channel), 16-byte chunks
+// XOR-swizzled by (row & 7); values rounded to nearest (TF32: cvt.rna, BF16: rn).
+__global__ void k_prep_wimg(const float *__restrict__ W, unsigned char *__restrict__ img, int K, int Cin, int Cout, int bf16) {
   const long n = (long)K * Cin * Cout;
+  const int per = bf16 ? 64 : 32, nAtoms = Cin / per;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const int co = (int)(i % Cout);
     const long t = i / Cout;
     const int ci = (int)(t % Cin), k = (int)(t / Cin);
-    const int c = ci >> 5, j = ci & 31, chunk = j >> 2, within = j & 3;
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(W[i]));
-    img[((long)k * (Cin >> 5) + c) * Cout * 32 + (long)co * 32 + ((chunk ^ (co & 7)) << 2) + within] = __uint_as_float(r);
+    const int c = ci / per, j = ci % per;
+    const int byte = j * (bf16 ? 2 : 4), chunk = byte >> 4, within = byte & 15;
+    unsigned char *dst = img + ((long)k * nAtoms + c) * Cout * 128 + (long)co * 128 + ((chunk ^ (co & 7)) << 4) + within;
+    if (bf16) {
+      *reinterpret_cast<unsigned short *>(dst) = __bfloat16_as_ushort(__float2bfloat16_rn(W[i]));
+    } else {
+      uint32_t r;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(W[i]));
+      *reinterpret_cast<uint32_t *>(dst) = r;
+    }
   }
 }
 
@@ -382,9 +479,21 @@ __global__ void k_pad_rows(const float *__restrict__ in, float *__restrict__ out
     out[i] = c < C ? __ldg(in + (i / Cp) * C + c) : 0.f;
   }
 }
+// fp32 -> bf16 (rn) copy of a feature matrix, for inputs that arrive without a bf16 shadow
+__global__ void __launch_bounds__(256) k_to_bf16(const float *__restrict__ x, uint2 *__restrict__ y, long n4) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<unsigned int *>(&lo);
+    pk.y = *reinterpret_cast<unsigned int *>(&hi);
+    y[i] = pk;
+  }
+}
+// in16: optional bf16 copy of `in` (same layout); used in math mode 2 when Cin is a multiple of 64
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
-                        long nInRows) {
+                        long nInRows, const void *in16) {
   if (nOut == 0) return 0;
   if (Cin % 32 != 0) { // e.g. the 9-channel input convolution: zero-pad rows and weight slices to 32 channels
     const int Cp = (Cin + 31) / 32 * 32;
@@ -394,54 +503,88 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     k_pad_rows<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
     SCN_CUDA(cudaMemsetAsync(wp, 0, (size_t)nWeights * Cp * Cout * 4, s));
     SCN_CUDA(cudaMemcpy2DAsync(wp, (size_t)Cp * Cout * 4, W, (size_t)Cin * Cout * 4, (size_t)Cin * Cout * 4, nWeights, cudaMemcpyDeviceToDevice, s));
-    int r = launch_conv_plan_tc(xp, out, wp, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows);
+    int r = launch_conv_plan_tc(xp, out, wp, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr);
     cudaFreeAsync(xp, s);
     cudaFreeAsync(wp, s);
     return r;
   }
   SCN_CHECK(Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && K <= 64, "tcgen05 path: unsupported channel counts");
-  TcParams P;
-  P.in = in; P.out = out; P.bias = bias; P.nbr = nbr; P.outRow = outRow; P.tileMask = tileMask; P.tileW = tileW;
-  P.nOut = nOut; P.K = K; P.Cin = Cin; P.Cout = Cout;
-  P.nTiles = cdiv(nOut, kTileM);
-  // supertile height: 2 tiles share every weight slice when the level is large enough for >= 2
-  // work items per SM (accumulators double-buffered: 2 x T x Cout <= 512 TMEM columns); small levels
-  // use 1-tile items and split the filter offsets over CTAs so the whole chip works on them.
-  const int Tmax = Cout <= 128 ? 2 : 1;
-  P.T = (Tmax == 2 && P.nTiles >= 2 * kSMs * 2 && !tileW && K <= 32) ? 2 : 1;
-  static int envT = -1, envSA = -1, envSB = -1, envDbg = 0;
+  static int envT = -1, envS = -1, envDbg = 0, envProf = 0;
   if (envT < 0) {
     envT = getenv("SCN_TC_T") ? atoi(getenv("SCN_TC_T")) : 0;
-    envSA = getenv("SCN_TC_SA") ? atoi(getenv("SCN_TC_SA")) : 0;
-    envSB = getenv("SCN_TC_SB") ? atoi(getenv("SCN_TC_SB")) : 0;
+    envS = getenv("SCN_TC_S") ? atoi(getenv("SCN_TC_S")) : 0;
     envDbg = getenv("SCN_TC_DBG") ? atoi(getenv("SCN_TC_DBG")) : 0;
+    envProf = getenv("SCN_TC_PROF") ? atoi(getenv("SCN_TC_PROF")) : 0;
   }
+  TcParams P;
+  P.in = reinterpret_cast<const unsigned char *>(in); P.out = out; P.bias = bias; P.nbr = nbr; P.outRow = outRow; P.tileMask = tileMask; P.tileW = tileW;
+  P.nOut = nOut; P.K = K; P.Cout = Cout;
+  P.bf16 = (mathMode == 2 && Cin % 64 == 0) ? 1 : 0; // narrower layers keep TF32 operands (128-byte rows either way)
+  void *tmp16 = nullptr;
+  if (P.bf16) {
+    if (!in16) {
+      SCN_CUDA(cudaMallocAsync(&tmp16, (size_t)nInRows * Cin * 2 + 16, s));
+      if (nInRows) k_to_bf16<<<stream_grid(nInRows * Cin / 4, 256), 256, 0, LS(s)>>>(in, static_cast<uint2 *>(tmp16), nInRows * Cin / 4);
+      in16 = tmp16;
+    }
+    P.in = static_cast<const unsigned char *>(in16);
+  }
+  P.rowBytes = Cin * (P.bf16 ? 2 : 4);
+  P.nAtoms = P.rowBytes / 128;
+  P.nTiles = cdiv(nOut, kTileM);
   P.dbg = envDbg;
-  if (envT > 0 && envT <= Tmax && !tileW) P.T = envT;
+  // Tiles per work item: as many as TMEM holds (T x Cout <= 512 columns) so that a weight atom is
+  // fetched once per T tiles, but never so many that fewer than ~2 items per SM remain; small levels
+  // use 1-tile items and split the filter offsets over CTAs so the whole chip works on them.
+  const int Tcap = std::min(kMaxT, 512 / Cout);
+  const size_t fixed = 4 * 32 * 36 * 4 + 64 * 8 + 64;
+  auto ring = [&](int t) { return (int)((227 * 1024 - fixed) / ((size_t)t * kAtomBytes + (size_t)Cout * 128)); };
+  int T = Tcap;
+  while (T > 2 && ring(T) < 3) T--; // a 2-slot ring exposes the gather latency (measured: T=3/S=3 beats T=4/S=2 by 12 %)
+  while (T > 1 && cdiv(P.nTiles, T) < 2 * kSMs) T--;
+  if (tileW) T = 1;
+  if (envT > 0 && envT <= Tcap && !tileW) T = envT;
+  P.T = T;
+  P.nAcc = 2 * T * Cout <= 512 ? 2 : 1;
   P.nSuper = cdiv(P.nTiles, P.T);
   P.kSplit = 1;
   if (P.nSuper < kSMs / 2 && !tileW) P.kSplit = std::max(1, std::min(K, kSMs / P.nSuper));
-  // weight-slice ring: ~48 KB deep (a slice is only Cout x 128 B, and one is needed per filter offset)
-  P.SB = envSB > 0 ? envSB : std::max(2, std::min(12, (48 * 1024) / (Cout * 128)));
-  size_t fixed = (size_t)P.SB * Cout * 128 + 4 * 32 * 36 * 4 + (size_t)P.T * kTileM * K * 4 + 64 * 8 + 16;
-  P.SA = (int)std::min<size_t>(envSA > 0 ? envSA : 8, (227 * 1024 - fixed) / kAStageBytes);
-  P.SA = P.SA >= 8 ? 8 : 4; // ring slots are statically owned by the 4 producer warps
-  SCN_CHECK((size_t)P.SA * kAStageBytes + fixed <= 227 * 1024, "tcgen05 path: shared memory budget exceeded");
-  size_t smem = (size_t)P.SA * kAStageBytes + fixed;
+  const size_t stageBytes = (size_t)P.T * kAtomBytes + (size_t)Cout * 128;
+  P.S = (int)std::min<size_t>(envS > 0 ? envS : 6, (227 * 1024 - fixed) / stageBytes);
+  SCN_CHECK(P.S >= 2, "tcgen05 path: shared memory budget exceeded");
+  const size_t smem = (size_t)P.S * stageBytes + fixed;
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
-  float *wimg = nullptr;
+  unsigned char *wimg = nullptr;
   SCN_CUDA(cudaMallocAsync((void **)&wimg, (size_t)nWeights * Cin * Cout * 4, s));
   P.wimg = wimg;
-  k_prep_wimg<<<stream_grid((long)nWeights * Cin * Cout, 256), 256, 0, LS(s)>>>(W, wimg, nWeights, Cin, Cout);
+  k_prep_wimg<<<stream_grid((long)nWeights * Cin * Cout, 256), 256, 0, LS(s)>>>(W, wimg, nWeights, Cin, Cout, P.bf16);
   static bool attr = false;
   if (!attr) {
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  int grid = std::min(P.nSuper * P.kSplit, kSMs);
-  conv_plan_tc<<<grid, kThreads, smem, LS(s)>>>(P);
+  const int grid = std::min(P.nSuper * P.kSplit, kSMs);
+  P.prof = nullptr;
+  if (envProf) {
+    SCN_CUDA(cudaMallocAsync((void **)&P.prof, kSMs * 32 * 8, s));
+    SCN_CUDA(cudaMemsetAsync(P.prof, 0, kSMs * 32 * 8, s));
+  }
+  if (P.bf16) conv_plan_tc<true><<<grid, kThreads, smem, LS(s)>>>(P);
+  else conv_plan_tc<false><<<grid, kThreads, smem, LS(s)>>>(P);
   SCN_CUDA(cudaGetLastError());
+  if (envProf) { // developer aid: mean stall cycles per role over the CTAs of this launch
+    static long long h[kSMs * 32];
+    SCN_CUDA(cudaMemcpyAsync(h, P.prof, sizeof h, cudaMemcpyDeviceToHost, s));
+    SCN_CUDA(cudaStreamSynchronize(s));
+    double m[32] = {0};
+    for (int b = 0; b < grid; b++) for (int i = 0; i < 32; i++) m[i] += (double)h[b * 32 + i] / grid;
+    fprintf(stderr, "[tcprof] grid=%d T=%d K=%d Cin=%d Cout=%d S=%d nAcc=%d kSplit=%d | epi total %.0f waitAcc %.0f | prod total %.0f empty %.0f cpwait %.0f stages %.0f | mma total %.0f accEmpty %.0f full %.0f stages %.0f issue %.0f commit %.0f | bld total %.0f empty %.0f\n",
+            grid, P.T, K, Cin, Cout, P.S, P.nAcc, P.kSplit, m[0], m[1], m[4], m[5], m[6], m[7], m[10], m[11], m[12], m[13], m[14], m[15], m[16], m[17]);
+    cudaFreeAsync(P.prof, s);
+  }
   cudaFreeAsync(wimg, s);
+  if (tmp16) cudaFreeAsync(tmp16, s);
   return 0;
 }
 

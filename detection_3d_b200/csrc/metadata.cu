@@ -587,8 +587,7 @@ __global__ void __launch_bounds__(128) k_tile_masks(const int *__restrict__ nbr,
   const int tile = blockIdx.x, p = tile * 128 + threadIdx.x;
   unsigned long long m = 0;
   if (p < nOut) {
-    const int *row = nbr + (long)p * K;
-    for (int k = 0; k < K; k++) m |= (unsigned long long)(row[k] >= 0) << k;
+    for (int k = 0; k < K; k++) m |= (unsigned long long)(nbr[nbr_index(p, k, K)] >= 0) << k;
   }
   for (int d = 16; d > 0; d >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, d);
   __shared__ unsigned long long s[4];
@@ -606,7 +605,7 @@ int Metadata::build_tile_masks(NbrPlan &plan) {
 }
 
 // ------------------------------------------------------------------ submanifold
-// nbr[p*K + k] = row id of the neighbour of site p at filter offset k (last dimension fastest,
+// nbr[nbr_index(p, k, K)] = row id of the neighbour of site p at filter offset k (last dimension fastest,
 // RectangularRegions.h:56-71; window [c - f/2, c + f - 1 - f/2], SubmanifoldConvolutionRules.h:11-22).
 __global__ void k_subm_nbr(GridView g, const int4 *coords, const int *p2id, int n, int f0, int f1, int f2, int *nbr, int *nValid) {
   const int K = f0 * f1 * f2;
@@ -614,7 +613,6 @@ __global__ void k_subm_nbr(GridView g, const int4 *coords, const int *p2id, int 
   for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x) {
     const int id = p2id[p];
     const int4 c = coords[id];
-    int *row = nbr + p * K;
     int k = 0;
     for (int a = 0; a < f0; a++)
       for (int b = 0; b < f1; b++)
@@ -622,7 +620,7 @@ __global__ void k_subm_nbr(GridView g, const int4 *coords, const int *p2id, int 
           int x = c.x - f0 / 2 + a, y = c.y - f1 / 2 + b, z = c.z - f2 / 2 + d;
           int q = (x == c.x && y == c.y && z == c.z) ? (int)p : grid_lookup(g, x, y, z, c.w);
           int v = q >= 0 ? p2id[q] : -1;
-          row[k] = v;
+          nbr[nbr_index(p, k, K)] = v;
           cntv += v >= 0;
         }
   }
@@ -632,9 +630,9 @@ __global__ void k_subm_nbr(GridView g, const int4 *coords, const int *p2id, int 
 struct SubmMask {
   const int *rank2id, *id2p, *nbr; int K;
   __device__ unsigned long long operator()(int r) const {
-    const int *row = nbr + (long)id2p[rank2id[r]] * K;
+    const long p = id2p[rank2id[r]];
     unsigned long long m = 0;
-    for (int k = 0; k < K; k++) m |= (unsigned long long)(row[k] >= 0) << k;
+    for (int k = 0; k < K; k++) m |= (unsigned long long)(nbr[nbr_index(p, k, K)] >= 0) << k;
     return m;
   }
 };
@@ -642,7 +640,7 @@ struct SubmPair {
   const int *rank2id, *id2p, *nbr; int K;
   __device__ int2 operator()(int r, int L) const {
     int id = rank2id[r];
-    return make_int2(nbr[(long)id2p[id] * K + L], id); // (input row, output row)
+    return make_int2(nbr[nbr_index(id2p[id], L, K)], id); // (input row, output row)
   }
 };
 
@@ -661,11 +659,13 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   e.plan.K = (int)K;
   e.plan.nOut = g->n;
   e.plan.outRow = g->p2id;
-  // rows padded to whole 256-site work items (pad = -1) so the kernel can bulk-copy an item's ids
-  const long nPad = ((long)g->n + 255) / 256 * 256;
+  const long nPad = plan_padded(g->n);
   e.plan.nbr = alloc_n<int>(std::max(1l, nPad * K));
   SCN_CHECK(e.plan.nbr, "alloc");
-  if (nPad > g->n) SCN_CUDA(cudaMemsetAsync(e.plan.nbr + (long)g->n * K, 0xff, (nPad - g->n) * K * 4, stream));
+  { // -1 in every slot of the last (partial) work item: whole tiles from the first incomplete one
+    const long t0 = (long)g->n / 128;
+    SCN_CUDA(cudaMemsetAsync(e.plan.nbr + t0 * K * 128, 0xff, (nPad / 128 - t0) * K * 128 * 4, stream));
+  }
   SCN_CUDA(cudaMemsetAsync(d_scalars, 0, 4, stream));
   if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, d_scalars);
   SCN_TRY(build_rule_lists(*this, g->n, (int)K, SubmMask{g->rank2id, g->id2p, e.plan.nbr, (int)K},
@@ -750,7 +750,7 @@ __global__ void k_conv_plan(ConvGeom G, const int *rank2id, const int4 *coords, 
     int id = rank2id[r];
     int4 j; int off;
     conv_event(G, coords[id], m, j, off);
-    nbr[(long)q * G.K + off] = id;
+    nbr[nbr_index(q, off, G.K)] = id;
   }
 }
 
@@ -810,7 +810,7 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   go.built = true;
   // output-stationary plan
   e.plan.K = G.K; e.plan.nOut = go.n; e.plan.outRow = go.p2id; e.plan.nValid = e.rb.total;
-  const long nPadOut = ((long)go.n + 255) / 256 * 256;
+  const long nPadOut = plan_padded(go.n);
   e.plan.nbr = alloc_n<int>(std::max(1l, nPadOut * G.K));
   SCN_CHECK(e.plan.nbr, "alloc");
   SCN_CUDA(cudaMemsetAsync(e.plan.nbr, 0xff, std::max(1l, nPadOut * G.K) * 4, s));

@@ -44,11 +44,13 @@ struct RuleBookDev {
 };
 
 // Output-stationary execution plan: for every output site (in spatial order p) the input row of
-// each filter offset, or -1.
+// each filter offset, or -1.  Layout: tiles of 128 consecutive sites; inside a tile the 128 ids of
+// one filter offset are contiguous (one coalesced 512-byte read per (tile, offset) in the gather
+// kernels).  The buffer is padded with -1 to whole work items of kPlanPad sites.
 struct NbrPlan {
   int K = 0;
   int nOut = 0;
-  int *nbr = nullptr;         // [nOut*K] input row ids, indexed by OUTPUT spatial index p
+  int *nbr = nullptr;         // [plan_padded(nOut)*K] input row ids at nbr_index(p, k, K), p = OUTPUT spatial index
   const int *outRow = nullptr; // p -> output row id (p2id of the output grid)
   long nValid = 0;            // number of non-negative entries (= rules)
   unsigned long long *tileMask = nullptr; // per 128-site tile: bit k set when some site of the tile has a neighbour at offset k

@@ -5,6 +5,7 @@
 // Replaces BatchNormalization_f_train/f_test/b (SCN/CUDA/BatchNormalization.cu:14-198, which run
 // on <= 16 CTAs) and InputLayer_fp_/bp_ (SCN/CUDA/IOLayers.cu:14-58).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace scn {
 
@@ -113,8 +114,16 @@ __global__ void k_bn_finalize(const double *__restrict__ stats, long n, int C, i
 }
 
 // y = leaky(x*scale + shift)   (:53-61)
+// y16 (optional): the same values rounded to bf16, the gather operand of a following bf16 convolution
+__device__ __forceinline__ void store_bf16x4(void *base, long i, float4 o) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<unsigned int *>(&lo);
+  pk.y = *reinterpret_cast<unsigned int *>(&hi);
+  reinterpret_cast<uint2 *>(base)[i] = pk;
+}
 __global__ void __launch_bounds__(256) k_bn_apply(const float *__restrict__ x, float *__restrict__ y, long total4, int cv, const float *__restrict__ scale,
-                                                  const float *__restrict__ shift, float leak) {
+                                                  const float *__restrict__ shift, float leak, void *__restrict__ y16) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
     int cg = (int)(i % cv);
     float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
@@ -123,6 +132,7 @@ __global__ void __launch_bounds__(256) k_bn_apply(const float *__restrict__ x, f
     o.x = fmaf(v.x, a.x, b.x); o.y = fmaf(v.y, a.y, b.y); o.z = fmaf(v.z, a.z, b.z); o.w = fmaf(v.w, a.w, b.w);
     o.x = o.x > 0 ? o.x : o.x * leak; o.y = o.y > 0 ? o.y : o.y * leak; o.z = o.z > 0 ? o.z : o.z * leak; o.w = o.w > 0 ? o.w : o.w * leak;
     reinterpret_cast<float4 *>(y)[i] = o;
+    if (y16) store_bf16x4(y16, i, o);
   }
 }
 __global__ void __launch_bounds__(256) k_bn_apply_scalar(const float *__restrict__ x, float *__restrict__ y, long total, int C, const float *__restrict__ scale,
@@ -152,14 +162,15 @@ static int bn_stats_launch(const float *x, long n, int C, double *stats, cudaStr
 
 // workspace: 2*C doubles + 2*C floats
 int bn_forward(const float *x, float *y, long n, int C, float *saveMean, float *saveInvStd, float *runningMean, float *runningVar,
-               const float *weight, const float *bias, float eps, float momentum, int mode, float leak, void *workspace, cudaStream_t s) {
+               const float *weight, const float *bias, float eps, float momentum, int mode, float leak, void *workspace, cudaStream_t s, void *y16) {
   double *stats = static_cast<double *>(workspace);
   float *scale = reinterpret_cast<float *>(stats + 2 * C), *shift = scale + C;
   if (mode != 1) SCN_TRY(bn_stats_launch(x, n, C, stats, s));
   k_bn_finalize<<<cdiv(C, 128), 128, 0, LS(s)>>>(stats, n, C, mode, eps, momentum, saveMean, saveInvStd, runningMean, runningVar, weight, bias, scale, shift);
   if (n) {
     long total = n * C;
-    if (C % 4 == 0) k_bn_apply<<<stream_grid(total / 4, 256), 256, 0, LS(s)>>>(x, y, total / 4, C / 4, scale, shift, leak);
+    SCN_CHECK(!y16 || C % 4 == 0, "bf16 shadow needs a channel count that is a multiple of 4");
+    if (C % 4 == 0) k_bn_apply<<<stream_grid(total / 4, 256), 256, 0, LS(s)>>>(x, y, total / 4, C / 4, scale, shift, leak, y16);
     else k_bn_apply_scalar<<<stream_grid(total, 256), 256, 0, LS(s)>>>(x, y, total, C, scale, shift, leak);
   }
   SCN_CUDA(cudaGetLastError());
@@ -270,16 +281,19 @@ int input_backward(float *din, const float *dout, long nIn, int nOut, int maxAct
 }
 
 // ------------------------------------------------------------------ add_feature_planes / AddTable
-__global__ void __launch_bounds__(256) k_add(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ o, long n) {
+__global__ void __launch_bounds__(256) k_add(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ o, long n, void *__restrict__ o16) {
   long n4 = n >> 2;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     float4 u = __ldg(reinterpret_cast<const float4 *>(a) + i), v = __ldg(reinterpret_cast<const float4 *>(b) + i);
-    reinterpret_cast<float4 *>(o)[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    float4 r = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    reinterpret_cast<float4 *>(o)[i] = r;
+    if (o16) store_bf16x4(o16, i, r);
   }
   for (long i = (n4 << 2) + blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) o[i] = a[i] + b[i];
 }
-int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s) {
-  if (n) k_add<<<stream_grid(n / 4 + 1, 256), 256, 0, LS(s)>>>(a, b, o, n);
+int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s, void *o16) {
+  SCN_CHECK(!o16 || n % 4 == 0, "bf16 shadow needs an element count that is a multiple of 4");
+  if (n) k_add<<<stream_grid(n / 4 + 1, 256), 256, 0, LS(s)>>>(a, b, o, n, o16);
   SCN_CUDA(cudaGetLastError());
   return 0;
 }

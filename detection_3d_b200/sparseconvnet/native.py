@@ -27,6 +27,32 @@ def _opt(t, what):
     return None if t is None or t.numel() == 0 else _dev_f32(t, what)
 
 
+# ---- bf16 shadows (math mode 'bf16' only).  A BatchNorm / add output carries a bfloat16 copy of
+# itself as a Python attribute of the tensor object, written by the same kernel that wrote the
+# fp32 values; the next convolution gathers from that copy (half the bytes).  The attribute dies
+# with the tensor object and is ignored once the tensor has been modified in place (_version).
+_MATH = {"mode": 0}
+
+
+def _new_shadow(t):
+    """bf16 buffer for the fp32 feature matrix `t` (or None when the mode / shape does not use one)."""
+    if _MATH["mode"] != 2 or t.dim() != 2 or t.size(1) % 64 != 0 or t.size(0) == 0:
+        return None
+    return torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
+
+
+def _attach_shadow(t, sh):
+    if sh is not None:
+        t._scn_bf16 = (sh, t._version)
+
+
+def _shadow_ptr(t):
+    sh = getattr(t, "_scn_bf16", None)
+    if sh is None or _MATH["mode"] != 2 or sh[1] != t._version or sh[0].shape != t.shape:
+        return None
+    return C.c_void_p(sh[0].data_ptr())
+
+
 class Metadata_3(object):
     """Handle on a device-resident Metadata (reference: Metadata<3>, SCN/Metadata/Metadata.h:44)."""
 
@@ -140,7 +166,7 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
     macs = C.c_double()
     check(lib().scn_submanifold_convolution_forward(m._h, l3(spatial_size), l3(filter_size), _dev_f32(input_features, "in"),
                                                     _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"),
-                                                    cin, cout, C.byref(macs)))
+                                                    cin, cout, C.byref(macs), _shadow_ptr(input_features)))
     return macs.value
 
 
@@ -161,7 +187,8 @@ def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, i
     output_features.resize_(n.value, cout)
     macs = C.c_double()
     check(lib().scn_convolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
-                                        _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs)))
+                                        _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs),
+                                        _shadow_ptr(input_features)))
     return macs.value
 
 
@@ -181,7 +208,8 @@ def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m,
     output_features.resize_(n, cout)
     macs = C.c_double()
     check(lib().scn_deconvolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
-                                          _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs)))
+                                          _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs),
+                                          _shadow_ptr(input_features)))
     return macs.value
 
 
@@ -205,9 +233,12 @@ def BatchNormalization_updateOutput(input_features, output_features, saveMean, s
     saveMean.resize_(c)
     saveInvStd.resize_(c)
     mode = 0 if train else (2 if instance_stats else 1)
+    sh = _new_shadow(output_features)
     check(lib().scn_batchnorm_forward(_dev_f32(input_features, "in"), _dev_f32(output_features, "out"), n, c, _dev_f32(saveMean, "saveMean"),
                                       _dev_f32(saveInvStd, "saveInvStd"), _opt(runningMean, "runningMean"), _opt(runningVar, "runningVar"),
-                                      _opt(weight, "weight"), _opt(bias, "bias"), float(eps), float(momentum), mode, float(leakiness), _stream()))
+                                      _opt(weight, "weight"), _opt(bias, "bias"), float(eps), float(momentum), mode, float(leakiness), _stream(),
+                                      None if sh is None else C.c_void_p(sh.data_ptr())))
+    _attach_shadow(output_features, sh)
 
 
 def BatchNormalization_backward(input_features, d_input_features, output_features, d_output_features, saveMean, saveInvStd, runningMean,
@@ -224,13 +255,18 @@ def add_features(a, b):
     """out = a + b for two feature matrices sharing one Metadata (tables.py:28-41, utils.py:61-66)."""
     out = torch.empty_like(a)
     if a.numel():
-        check(lib().scn_add_features(_dev_f32(a, "a"), _dev_f32(b, "b"), _dev_f32(out, "out"), a.numel(), _stream()))
+        sh = _new_shadow(out)
+        check(lib().scn_add_features(_dev_f32(a, "a"), _dev_f32(b, "b"), _dev_f32(out, "out"), a.numel(), _stream(),
+                                     None if sh is None else C.c_void_p(sh.data_ptr())))
+        _attach_shadow(out, sh)
     return out
 
 
 def set_math_mode(mode):
     """'fp32' (CUDA cores, exact), 'tf32' or 'bf16' (tcgen05 tensor cores, fp32 accumulate)."""
-    check(lib().scn_set_math_mode({"fp32": 0, "tf32": 1, "bf16": 2}[mode] if isinstance(mode, str) else int(mode)))
+    code = {"fp32": 0, "tf32": 1, "bf16": 2}[mode] if isinstance(mode, str) else int(mode)
+    check(lib().scn_set_math_mode(code))
+    _MATH["mode"] = lib().scn_get_math_mode()
 
 
 def kernel_launch_count():

@@ -77,19 +77,22 @@ int scn_iteration_order(scn_metadata *m, const long spatial_size[3], int *dst);
 
 /* SubmanifoldConvolution_updateOutput (pybind.cpp:134-138; CPU/Convolution.cpp:117-150;
  * CUDA/Convolution.cpp:95-125).  weight [K][Cin][Cout] (= (K,1,Cin,Cout) with groups 1),
- * bias NULL or [Cout].  *macs = sum_k nRules_k*Cin*Cout, the value the reference returns. */
+ * bias NULL or [Cout].  *macs = sum_k nRules_k*Cin*Cout, the value the reference returns.
+ * in_bf16 (all three forward calls): NULL, or a device copy of `in` rounded to bfloat16 (same
+ * [rows][n_in] layout) that a preceding scn_batchnorm_forward / scn_add_features produced; it is
+ * only read in math mode 2, where a NULL makes the call convert `in` itself. */
 int scn_submanifold_convolution_forward(scn_metadata *m, const long spatial_size[3], const long filter_size[3],
                                         const float *in, float *out, const float *weight, const float *bias,
-                                        int n_in, int n_out, double *macs);
+                                        int n_in, int n_out, double *macs, const void *in_bf16);
 /* Convolution_updateOutput (pybind.cpp:54-59; CPU/Convolution.cpp:45-79) */
 int scn_convolution_forward(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
                             const long filter_stride[3], const float *in, float *out, const float *weight,
-                            const float *bias, int n_in, int n_out, double *macs);
+                            const float *bias, int n_in, int n_out, double *macs, const void *in_bf16);
 /* Deconvolution_updateOutput (pybind.cpp:78-83; CPU/Deconvolution.cpp:7-41): reuses the rulebook of the
  * Convolution out_size -> in_size with the pair columns swapped. */
 int scn_deconvolution_forward(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
                               const long filter_stride[3], const float *in, float *out, const float *weight,
-                              const float *bias, int n_in, int n_out, double *macs);
+                              const float *bias, int n_in, int n_out, double *macs, const void *in_bf16);
 
 /* *_backward (pybind.cpp:60-65,84-89,139-143; CPU/Convolution.cpp:81-115,152-185; CPU/Deconvolution.cpp:43-77):
  * d_in [nIn rows][Cin] is overwritten, d_weight [K][Cin][Cout] is overwritten, d_bias NULL or [Cout]. */
@@ -106,17 +109,19 @@ int scn_deconvolution_backward(scn_metadata *m, const long in_size[3], const lon
 /* BatchNormalization_updateOutput (pybind.cpp:219-220; CPU/BatchNormalization.cpp:12-62).
  * mode 0 = train, 1 = eval with the given running stats, 2 = eval with
  * track_running_stats=False (batchNormalization.py:51-56: mean(0) / unbiased var(0) of this input).
- * weight / bias may be NULL.  leakiness 0 = ReLU, 1 = no activation. */
+ * weight / bias may be NULL.  leakiness 0 = ReLU, 1 = no activation.
+ * out_bf16: NULL, or [n_rows][n_planes] bfloat16 that receives `out` rounded to nearest (the gather
+ * operand of a following convolution in math mode 2; n_planes % 4 == 0). */
 int scn_batchnorm_forward(const float *in, float *out, long n_rows, int n_planes, float *save_mean, float *save_invstd,
                           float *running_mean, float *running_var, const float *weight, const float *bias, float eps,
-                          float momentum, int mode, float leakiness, void *stream);
+                          float momentum, int mode, float leakiness, void *stream, void *out_bf16);
 /* BatchNormalization_backward (pybind.cpp:221; CPU/BatchNormalization.cpp:64-107); d_out is rewritten in place. */
 int scn_batchnorm_backward(const float *in, float *d_in, const float *out, float *d_out, long n_rows, int n_planes,
                            const float *save_mean, const float *save_invstd, const float *weight, float *d_weight,
                            float *d_bias, float leakiness, void *stream);
 
 /* AddTable / add_feature_planes (sparseconvnet/tables.py:28-41, utils.py:61-66): out = a + b */
-int scn_add_features(const float *a, const float *b, float *out, long n_elements, void *stream);
+int scn_add_features(const float *a, const float *b, float *out, long n_elements, void *stream, void *out_bf16);
 
 /* Selects the arithmetic of the gather-GEMM kernels for this process: 0 = fp32 CUDA cores
  * (exact-fp32 anchor), 1 = tcgen05 tensor cores, TF32 inputs / fp32 accumulate (default where the
