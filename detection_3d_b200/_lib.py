@@ -21,6 +21,7 @@ SYMBOLS = {
     "scn_n_rulebook_bits": (_i, []),
     "scn_metadata_create": (_i, [C.POINTER(_vp), _vp]),
     "scn_metadata_destroy": (None, [_vp]),
+    "scn_metadata_prefetch": (_i, [_vp, _i, _vp]),
     "scn_input_layer_build": (_i, [_vp, L3, _vp, _i, _l, _i, _i, _i, _pl, _pi]),
     "scn_input_layer_forward": (_i, [_vp, _vp, _vp, _i]),
     "scn_input_layer_backward": (_i, [_vp, _vp, _vp, _i]),

@@ -2,10 +2,15 @@
 #include "../../include/scn_b200.h"
 #include "metadata.cuh"
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 namespace scn {
-long g_launches = 0;
+std::atomic<long> g_launches{0};
 const char *last_error();
+void set_prefetch_worker_thread(bool on);
 int launch_conv_plan_simt(const float *in, float *out, const float *W, const int *nbr, const int *outRow, int nOut, int K, int Cin, int Cout,
                           const float *bias, cudaStream_t s);
 int launch_conv_list_simt(const float *in, float *out, const float *W, const int2 *pairs, const int *d_off, const int *offHost, int K, int Cin,
@@ -26,8 +31,15 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
 static int g_math_mode = 0;
 } // namespace scn
 
+// The caller's thread and the prefetch worker (scn_metadata_prefetch) build into the same lazily
+// filled caches; Metadata::buildMu / mapMu (metadata.cuh) keep them apart.
+struct PrefetchOp { long v[13]; }; // kind, a[3], b[3], f[3], s[3]
 struct scn_metadata {
   scn::Metadata md;
+  std::thread worker;
+  std::atomic<bool> stop{false};
+  std::vector<PrefetchOp> ops;
+  int device = 0;
 };
 
 using scn::Metadata;
@@ -60,13 +72,56 @@ int scn_metadata_create(scn_metadata **out, void *stream) {
     return -1;
   }
   scn_metadata *m = new scn_metadata();
+  cudaGetDevice(&m->device);
   m->md.stream = static_cast<cudaStream_t>(stream);
   int r = m->md.init();
   if (r) { delete m; return r; }
   *out = m;
   return 0;
 }
-void scn_metadata_destroy(scn_metadata *m) { delete m; }
+void scn_metadata_destroy(scn_metadata *m) {
+  if (!m) return;
+  m->stop = true;
+  if (m->worker.joinable()) m->worker.join();
+  delete m;
+}
+
+// Builds ahead, on a worker thread and the Metadata's build stream, the rulebooks / plans the caller
+// is about to request (ops: n_ops x 13 longs = kind, a[3], b[3], filter[3], stride[3]; kind 1 =
+// submanifold(a = size), 2 = convolution(a = in, b = out), 3 = deconvolution(a = in (coarse),
+// b = out (fine))).  Purely a hint: results are identical with or without it, entries are built
+// in the same lazily-filled caches (Metadata.cpp:429-510) under the same keys; a failing hint is
+// ignored and the error resurfaces when the caller requests that entry itself.
+static void prefetch_worker(scn_metadata *m) {
+  cudaSetDevice(m->device);
+  scn::set_prefetch_worker_thread(true);
+  for (const PrefetchOp &op : m->ops) {
+    if (m->stop) break;
+    const long *a = op.v + 1, *b = op.v + 4, *f = op.v + 7, *s = op.v + 10;
+    if (op.v[0] == 1) {
+      scn::SubmEntry *e;
+      if (m->md.get_submanifold(a, f, &e)) break;
+    } else if (op.v[0] == 2) {
+      scn::ConvEntry *e;
+      if (m->md.get_conv(a, b, f, s, &e)) break;
+    } else if (op.v[0] == 3) {
+      scn::ConvEntry *e;
+      if (m->md.get_conv(b, a, f, s, &e)) break;
+      scn::Grid *gf = m->md.find_grid(b);
+      if (scn::g_math_mode != 0 && scn::tc_available() && gf && gf->n > 0 && e->geom.M == 1 && e->rb.total == gf->n)
+        if (m->md.get_deconv_plan(*e)) break;
+    }
+  }
+}
+int scn_metadata_prefetch(scn_metadata *m, int n_ops, const long *ops) {
+  if (!m) { scn::set_error("null scn_metadata handle"); return -3; }
+  if (m->worker.joinable()) m->worker.join();
+  m->ops.resize(n_ops);
+  for (int i = 0; i < n_ops; i++) for (int j = 0; j < 13; j++) m->ops[i].v[j] = ops[i * 13 + j];
+  m->stop = false;
+  m->worker = std::thread(prefetch_worker, m);
+  return 0;
+}
 
 int scn_input_layer_build(scn_metadata *m, const long sz[3], const long *coords, int on_device, long nrows, int ncols,
                           int batch_size, int mode, long *n_active, int *max_active) {
@@ -80,21 +135,23 @@ int scn_input_layer_forward(scn_metadata *m, const float *in, float *out, int C)
   M_OR_FAIL(m);
   auto &I = m->md.input;
   SCN_CHECK(I.valid, "input layer not built");
+  SCN_TRY(m->md.wait_ready(I.rdy));
   if (I.mode == 0) {
-    SCN_CUDA(cudaMemcpyAsync(out, in, (size_t)I.nOut * C * 4, cudaMemcpyDeviceToDevice, m->md.stream));
+    SCN_CUDA(cudaMemcpyAsync(out, in, (size_t)I.nOut * C * 4, cudaMemcpyDeviceToDevice, m->md.cstream));
     return 0;
   }
-  return scn::input_forward(in, out, I.nOut, I.maxActive, C, I.tab, I.mode == 4, m->md.stream);
+  return scn::input_forward(in, out, I.nOut, I.maxActive, C, I.tab, I.mode == 4, m->md.cstream);
 }
 int scn_input_layer_backward(scn_metadata *m, float *din, const float *dout, int C) {
   M_OR_FAIL(m);
   auto &I = m->md.input;
   SCN_CHECK(I.valid, "input layer not built");
+  SCN_TRY(m->md.wait_ready(I.rdy));
   if (I.mode == 0) {
-    SCN_CUDA(cudaMemcpyAsync(din, dout, (size_t)I.nOut * C * 4, cudaMemcpyDeviceToDevice, m->md.stream));
+    SCN_CUDA(cudaMemcpyAsync(din, dout, (size_t)I.nOut * C * 4, cudaMemcpyDeviceToDevice, m->md.cstream));
     return 0;
   }
-  return scn::input_backward(din, dout, I.nIn, I.nOut, I.maxActive, C, I.tab, I.mode == 4, m->md.stream);
+  return scn::input_backward(din, dout, I.nIn, I.nOut, I.maxActive, C, I.tab, I.mode == 4, m->md.cstream);
 }
 
 int scn_get_nactive(scn_metadata *m, const long sz[3], long *n) {
@@ -126,13 +183,14 @@ int scn_convolution_prepare(scn_metadata *m, const long inS[3], const long outS[
 }
 
 static int find_rb(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], scn::RuleBookDev **rb) {
+  std::lock_guard<std::mutex> lk(m->md.mapMu);
   if (kind == 1) {
     auto it = m->md.subm.find(scn::SubmKey{scn::P3{a[0], a[1], a[2]}, scn::P3{b[0], b[1], b[2]}});
-    SCN_CHECK(it != m->md.subm.end(), "submanifold rulebook not built");
+    SCN_CHECK(it != m->md.subm.end() && it->second.rdy.ready, "submanifold rulebook not built");
     *rb = &it->second.rb;
   } else {
     auto it = m->md.conv.find(scn::ConvKey{scn::P3{a[0], a[1], a[2]}, scn::P3{b[0], b[1], b[2]}, scn::P3{c[0], c[1], c[2]}});
-    SCN_CHECK(it != m->md.conv.end(), "convolution rulebook not built");
+    SCN_CHECK(it != m->md.conv.end() && it->second.rdy.ready, "convolution rulebook not built");
     *rb = &it->second.rb;
   }
   return 0;
@@ -178,6 +236,7 @@ int scn_iteration_order(scn_metadata *m, const long sz[3], int *dst) {
   M_OR_FAIL(m);
   scn::Grid *g = m->md.find_grid(sz);
   SCN_CHECK(g, "no active sites recorded for this spatial size");
+  scn::Metadata::BuildLock bl(m->md);
   SCN_TRY(m->md.ensure_rank(*g));
   if (g->n) {
     SCN_CUDA(cudaMemcpyAsync(dst, g->rank2id, (size_t)g->n * 4, cudaMemcpyDeviceToHost, m->md.stream));
@@ -192,9 +251,9 @@ static bool tc_ok(int Cin, int Cout, int K) {
 static int run_plan(Metadata &M, const scn::NbrPlan &plan, const float *in, float *out, const float *w, const float *bias, int Cin, int Cout,
                     long nInRows, const void *in16) {
   if (tc_ok(Cin, Cout, plan.K))
-    return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.tileMask, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.stream,
+    return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.tileMask, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.cstream,
                                     nullptr, plan.K, nInRows, in16);
-  return scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.stream);
+  return scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.cstream);
 }
 
 int scn_submanifold_convolution_forward(scn_metadata *m, const long sz[3], const long f[3], const float *in, float *out, const float *w,
@@ -203,6 +262,7 @@ int scn_submanifold_convolution_forward(scn_metadata *m, const long sz[3], const
   scn::SubmEntry *e;
   SCN_TRY(m->md.get_submanifold(sz, f, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
+  SCN_TRY(m->md.wait_ready(e->rdy));
   return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(sz)->n, in_bf16);
 }
 int scn_convolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
@@ -211,6 +271,7 @@ int scn_convolution_forward(scn_metadata *m, const long inS[3], const long outS[
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
+  SCN_TRY(m->md.wait_ready(e->rdy));
   return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(inS)->n, in_bf16);
 }
 __global__ void k_fill_rows_bias(float *out, long n, int C, const float *bias) {
@@ -225,15 +286,17 @@ int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long out
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
   scn::Grid *gf = m->md.find_grid(outS);
   SCN_CHECK(gf, "output grid");
-  cudaStream_t s = m->md.stream;
+  cudaStream_t s = m->md.cstream;
   // every fine row with a parent is written exactly once when each input site has one output cell
   bool single = e->rb.total == gf->n && !bias;
   if (single && e->geom.M == 1 && tc_ok(Cin, Cout, 1) && gf->n > 0) {
     SCN_TRY(m->md.get_deconv_plan(*e));
+    SCN_TRY(m->md.wait_ready(e->deconvRdy));
     const scn::DeconvPlan &d = e->deconv;
     return scn::launch_conv_plan_tc(in, out, w, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, 1, Cin, Cout, nullptr, scn::g_math_mode, s, d.tileW,
                                     e->rb.nLists, m->md.find_grid(inS)->n, in_bf16);
   }
+  SCN_TRY(m->md.wait_ready(e->rdy));
   if (!single && gf->n) k_fill_rows_bias<<<scn::stream_grid((long)gf->n * Cout, 256), 256, 0, scn::LS(s)>>>(out, gf->n, Cout, bias);
   return scn::launch_conv_list_simt(in, out, w, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, Cin, Cout, /*srcIsY=*/1, single ? 1 : 0, s);
 }
@@ -244,23 +307,26 @@ int scn_submanifold_convolution_backward(scn_metadata *m, const long sz[3], cons
   scn::SubmEntry *e;
   SCN_TRY(m->md.get_submanifold(sz, f, &e));
   scn::Grid *g = m->md.find_grid(sz);
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.stream);
+  SCN_TRY(m->md.wait_ready(e->rdy));
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.cstream);
 }
 int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                              float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
   M_OR_FAIL(m);
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
+  SCN_TRY(m->md.wait_ready(e->rdy));
   return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, m->md.find_grid(inS)->n,
-                                 m->md.find_grid(outS)->n, Cin, Cout, 0, m->md.stream);
+                                 m->md.find_grid(outS)->n, Cin, Cout, 0, m->md.cstream);
 }
 int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                                float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
   M_OR_FAIL(m);
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(outS, inS, f, st, &e));
+  SCN_TRY(m->md.wait_ready(e->rdy));
   return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, m->md.find_grid(inS)->n,
-                                 m->md.find_grid(outS)->n, Cin, Cout, 1, m->md.stream);
+                                 m->md.find_grid(outS)->n, Cin, Cout, 1, m->md.cstream);
 }
 
 int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *save_mean, float *save_invstd, float *running_mean,

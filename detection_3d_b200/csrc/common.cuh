@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <atomic>
 
 namespace scn {
 
@@ -36,7 +37,7 @@ void set_error(const std::string &msg);
   } while (0)
 
 // every kernel launch of this library passes its stream through LS(): launch accounting
-extern long g_launches;
+extern std::atomic<long> g_launches;
 static inline cudaStream_t LS(cudaStream_t s) { ++g_launches; return s; }
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

@@ -2,6 +2,7 @@
 // hash-iteration order (dense_hash_map emulation), rulebooks in the reference's format and the
 // output-stationary execution plans.  See DESIGN.md "Rulebook build".
 #include "metadata.cuh"
+#include <stdlib.h>
 #include <algorithm>
 #include <limits.h>
 #include <string.h>
@@ -22,12 +23,69 @@ static int *pinned_get() {
   if (cudaMallocHost(&p, 256 * 4) != cudaSuccess) return nullptr;
   return p;
 }
+// build streams are recycled like the pinned blocks (stream creation is not free either)
+static std::vector<cudaStream_t> g_stream_free;
+static std::vector<cudaEvent_t> g_event_free;
+static std::mutex g_pool_mu; // the recycling lists above are shared by all Metadata objects
+thread_local bool tl_prefetch_worker = false;
+void set_prefetch_worker_thread(bool on) { tl_prefetch_worker = on; }
+Metadata::BuildLock::BuildLock(Metadata &md) : m(md) {
+  if (tl_prefetch_worker) {
+    while (m.callerWaiting.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    m.buildMu.lock();
+  } else {
+    m.callerWaiting.fetch_add(1, std::memory_order_acq_rel);
+    m.buildMu.lock();
+    m.callerWaiting.fetch_sub(1, std::memory_order_acq_rel);
+  }
+}
+int Metadata::mark_ready(Ready &r) {
+  if (stream != cstream) {
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      if (!g_event_free.empty()) { r.ev = g_event_free.back(); g_event_free.pop_back(); }
+    }
+    if (!r.ev) SCN_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+    events.push_back(r.ev);
+    SCN_CUDA(cudaEventRecord(r.ev, stream));
+  }
+  std::lock_guard<std::mutex> lk(mapMu);
+  r.ready = true;
+  return 0;
+}
+int Metadata::wait_ready(Ready &r) {
+  if (r.ev && !r.waited) SCN_CUDA(cudaStreamWaitEvent(cstream, r.ev, 0));
+  r.waited = true;
+  return 0;
+}
 Metadata::~Metadata() {
+  from_compute(); // the frees below are ordered after every feature kernel that still reads these buffers
   for (void *p : allocs) cudaFreeAsync(p, stream);
   if (h_scalars) g_pinned_free.push_back(h_scalars);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (ownStream) g_stream_free.push_back(stream);
+    for (cudaEvent_t e : events) g_event_free.push_back(e);
+  }
+  if (evBuild) cudaEventDestroy(evBuild);
+  if (evCompute) cudaEventDestroy(evCompute);
+}
+int Metadata::to_compute() {
+  if (!buildDirty || stream == cstream) { buildDirty = false; return 0; }
+  SCN_CUDA(cudaEventRecord(evBuild, stream));
+  SCN_CUDA(cudaStreamWaitEvent(cstream, evBuild, 0));
+  buildDirty = false;
+  return 0;
+}
+int Metadata::from_compute() {
+  if (stream == cstream || !evCompute) return 0;
+  SCN_CUDA(cudaEventRecord(evCompute, cstream));
+  SCN_CUDA(cudaStreamWaitEvent(stream, evCompute, 0));
+  return 0;
 }
 void *Metadata::alloc(size_t bytes) {
   void *p = nullptr;
+  buildDirty = true;
   if (bytes < 256) bytes = 256;
   if (cudaMallocAsync(&p, bytes, stream) != cudaSuccess) {
     set_error("cudaMallocAsync failed");
@@ -46,6 +104,23 @@ int Metadata::init() {
     uint64_t thr = UINT64_MAX; // keep freed blocks cached: steady-state forwards never hit the driver
     SCN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     poolConfigured = true;
+  }
+  cstream = stream;
+  static int async = -1;
+  if (async < 0) async = getenv("SCN_ASYNC_BUILD") ? atoi(getenv("SCN_ASYNC_BUILD")) : 1;
+  if (async) {
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      if (!g_stream_free.empty()) { stream = g_stream_free.back(); g_stream_free.pop_back(); ownStream = true; }
+    }
+    if (!ownStream) {
+      int lo = 0, hi = 0;
+      SCN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      SCN_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, hi));
+    }
+    ownStream = true;
+    SCN_CUDA(cudaEventCreateWithFlags(&evBuild, cudaEventDisableTiming));
+    SCN_CUDA(cudaEventCreateWithFlags(&evCompute, cudaEventDisableTiming));
   }
   zpoolWords = 1 << 19; // 4 MiB of scan state
   zpool = alloc_n<unsigned long long>(zpoolWords);
@@ -78,6 +153,7 @@ int Metadata::sync_scalars(int count) {
   return 0;
 }
 Grid *Metadata::find_grid(const long *sz) {
+  std::lock_guard<std::mutex> lk(mapMu);
   auto it = grids.find(P3{sz[0], sz[1], sz[2]});
   return it == grids.end() || !it->second.built ? nullptr : &it->second;
 }
@@ -244,10 +320,18 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
   SCN_CHECK(mode >= 0 && mode <= 4, "mode");
   SCN_CHECK(nrows < (1l << 26), "too many input rows");
   P3 key{sz[0], sz[1], sz[2]};
-  SCN_CHECK(grids.find(key) == grids.end() && !input.valid, "input layer already built for this Metadata");
-  Grid &g = grids[key];
+  BuildLock bl(*this);
+  Grid *gp;
+  {
+    std::lock_guard<std::mutex> lk(mapMu);
+    SCN_CHECK(grids.find(key) == grids.end() && !input.valid, "input layer already built for this Metadata");
+    gp = &grids[key];
+  }
+  Grid &g = *gp;
   g.sz = key;
   cudaStream_t s = stream;
+  if (onDevice) SCN_TRY(from_compute()); // the coordinates were produced on the caller's stream
+  buildDirty = true;
   const long *dcoords = coords;
   if (!onDevice && nrows) {
     long *tmp = alloc_n<long>(nrows * ncols);
@@ -293,15 +377,15 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
     SCN_TRY(sync_scalars(8 + 48));
     for (int b = 0; b < g.batch; b++) g.itemCount[b] = h_scalars[8 + b];
   }
-  g.built = true;
+  { std::lock_guard<std::mutex> lk(mapMu); g.built = true; }
   // rules
   input.mode = mode; input.nIn = (int)nrows; input.nOut = g.n; input.valid = true;
   input.maxActive = (mode == 3 || mode == 4) ? maxActive : 1;
-  if (mode == 0) { input.tab = nullptr; return 0; }
+  if (mode == 0) { input.tab = nullptr; return mark_ready(input.rdy); }
   int w = 1 + input.maxActive;
   input.tab = alloc_n<int>(std::max(1l, (long)g.n * w));
   SCN_CHECK(input.tab, "alloc");
-  if (g.n == 0) return 0;
+  if (g.n == 0) return mark_ready(input.rdy);
   if (mode == 3 || mode == 4) {
     SCN_CUDA(cudaMemsetAsync(input.tab, 0, (long)g.n * w * 4, s));
     k_input_rules_fill<<<stream_grid(nrows, 256), 256, 0, LS(s)>>>(rowP, g.p2id, nrows, input.tab, w);
@@ -311,7 +395,7 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
     k_input_rules_pick<<<stream_grid(g.n, 256), 256, 0, LS(s)>>>(mode == 1 ? firstRow : lastRow, g.id2p, g.n, input.tab);
   }
   SCN_CUDA(cudaGetLastError());
-  return 0;
+  return mark_ready(input.rdy);
 }
 
 // ------------------------------------------------------------------ dense_hash_map order
@@ -648,14 +732,22 @@ struct SubmPair {
 // (SubmanifoldConvolutionRules.h:26-45)
 int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   SubmKey key{P3{sz[0], sz[1], sz[2]}, P3{f[0], f[1], f[2]}};
-  auto it = subm.find(key);
-  if (it != subm.end()) { *out = &it->second; return 0; }
+  auto lookup = [&]() -> SubmEntry * {
+    std::lock_guard<std::mutex> lk(mapMu);
+    auto it = subm.find(key);
+    return it != subm.end() && it->second.rdy.ready ? &it->second : nullptr;
+  };
+  if ((*out = lookup())) return 0;
+  BuildLock bl(*this);
+  if ((*out = lookup())) return 0; // built by the other thread in the meantime
   Grid *g = find_grid(sz);
   SCN_CHECK(g, "no active sites recorded for this spatial size");
   long K = f[0] * f[1] * f[2];
   SCN_CHECK(K >= 1 && K <= 64 && f[0] > 0 && f[1] > 0 && f[2] > 0, "unsupported submanifold filter size");
   SCN_TRY(ensure_rank(*g));
-  SubmEntry &e = subm[key];
+  SubmEntry *ep;
+  { std::lock_guard<std::mutex> lk(mapMu); ep = &subm[key]; }
+  SubmEntry &e = *ep;
   e.plan.K = (int)K;
   e.plan.nOut = g->n;
   e.plan.outRow = g->p2id;
@@ -673,6 +765,7 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   e.plan.nValid = h_scalars[0];
   SCN_CHECK(e.plan.nValid == e.rb.total, "internal: rule count mismatch");
   SCN_TRY(build_tile_masks(e.plan));
+  SCN_TRY(mark_ready(e.rdy));
   *out = &e;
   return 0;
 }
@@ -757,12 +850,21 @@ __global__ void k_conv_plan(ConvGeom G, const int *rank2id, const int4 *coords, 
 // getRuleBook (Metadata.cpp:484-510) -> Convolution_InputSgToRulesAndOutputSg (ConvolutionRules.h:11-34)
 int Metadata::get_conv(const long *inS, const long *outS, const long *f, const long *st, ConvEntry **out) {
   ConvKey key{P3{inS[0], inS[1], inS[2]}, P3{f[0], f[1], f[2]}, P3{st[0], st[1], st[2]}};
-  auto it = conv.find(key);
-  if (it != conv.end()) { *out = &it->second; return 0; }
+  auto lookup = [&]() -> ConvEntry * {
+    std::lock_guard<std::mutex> lk(mapMu);
+    auto it = conv.find(key);
+    return it != conv.end() && it->second.rdy.ready ? &it->second : nullptr;
+  };
+  if ((*out = lookup())) return 0;
+  BuildLock bl(*this);
+  if ((*out = lookup())) return 0; // built by the other thread in the meantime
   Grid *gi = find_grid(inS);
   SCN_CHECK(gi, "no active sites recorded for the input spatial size");
   P3 okey{outS[0], outS[1], outS[2]};
-  SCN_CHECK(grids.find(okey) == grids.end(), "output spatial size already has a grid (each spatial size may occur once per Metadata)");
+  {
+    std::lock_guard<std::mutex> lk(mapMu);
+    SCN_CHECK(grids.find(okey) == grids.end(), "output spatial size already has a grid (each spatial size may occur once per Metadata)");
+  }
   ConvGeom G;
   G.M = 1; G.K = 1;
   for (int d = 0; d < 3; d++) {
@@ -775,11 +877,14 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   SCN_CHECK(G.K <= 64 && G.M <= 64, "unsupported convolution filter size");
   SCN_TRY(ensure_rank(*gi));
   cudaStream_t s = stream;
-  ConvEntry &e = conv[key];
+  ConvEntry *ep;
+  Grid *gop;
+  { std::lock_guard<std::mutex> lk(mapMu); ep = &conv[key]; gop = &grids[okey]; }
+  ConvEntry &e = *ep;
   e.out = okey;
   e.in = key.in;
   e.geom = G;
-  Grid &go = grids[okey];
+  Grid &go = *gop;
   go.sz = okey;
   go.batch = gi->batch;
   const int n = gi->n;
@@ -807,7 +912,7 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   go.itemCtr.assign(go.batch, 0);
   int ctr = 0;
   for (int b = 0; b < go.batch; b++) { go.itemCount[b] = h_scalars[8 + b]; go.itemCtr[b] = ctr; ctr += go.itemCount[b]; }
-  go.built = true;
+  { std::lock_guard<std::mutex> lk(mapMu); go.built = true; }
   // output-stationary plan
   e.plan.K = G.K; e.plan.nOut = go.n; e.plan.outRow = go.p2id; e.plan.nValid = e.rb.total;
   const long nPadOut = plan_padded(go.n);
@@ -817,6 +922,7 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   if (E) k_conv_plan<<<stream_grid(E, 256), 256, 0, LS(s)>>>(G, gi->rank2id, gi->coords, evQ, n, e.plan.nbr);
   SCN_CUDA(cudaGetLastError());
   SCN_TRY(build_tile_masks(e.plan));
+  SCN_TRY(mark_ready(e.rdy));
   *out = &e;
   return 0;
 }
@@ -866,7 +972,9 @@ __global__ void k_deconv_tiles(const int *__restrict__ off, int K, int *__restri
 }
 // Built on first use by a Deconvolution whose rulebook gives every fine site exactly one parent.
 int Metadata::get_deconv_plan(ConvEntry &e) {
-  if (e.deconv.built) return 0;
+  if (is_ready(e.deconvRdy)) return 0;
+  BuildLock bl(*this);
+  if (is_ready(e.deconvRdy)) return 0;
   Grid *gf = find_grid(e.in.data()), *gc = find_grid(e.out.data());
   SCN_CHECK(gf && gc && e.geom.M == 1 && e.rb.total == gf->n, "deconvolution plan needs a single-parent rulebook");
   const int K = e.geom.K, n = gf->n;
@@ -896,6 +1004,7 @@ int Metadata::get_deconv_plan(ConvEntry &e) {
   }
   SCN_CUDA(cudaGetLastError());
   d.built = true;
+  SCN_TRY(mark_ready(e.deconvRdy));
   return 0;
 }
 
@@ -908,13 +1017,17 @@ __global__ void k_locations(const int4 *coords, int n, long *out) {
 }
 // Metadata::getSpatialLocations (Metadata.cpp:147-168): int64 [nActive][4] in row-id order
 int Metadata::spatial_locations(const long *sz, long *out, int outOnDevice) {
+  BuildLock bl(*this);
   Grid *g = find_grid(sz);
   SCN_CHECK(g, "no active sites recorded for this spatial size");
   if (g->n == 0) return 0;
   long *dst = out;
   if (!outOnDevice) { dst = alloc_n<long>((long)g->n * 4); SCN_CHECK(dst, "alloc"); }
+  if (outOnDevice) SCN_TRY(from_compute()); // `out` was allocated by the caller on its stream
   k_locations<<<stream_grid(g->n, 256), 256, 0, LS(stream)>>>(g->coords, g->n, dst);
   SCN_CUDA(cudaGetLastError());
+  buildDirty = true;
+  if (outOnDevice) SCN_TRY(to_compute());
   if (!outOnDevice) {
     SCN_CUDA(cudaMemcpyAsync(out, dst, (long)g->n * 32, cudaMemcpyDeviceToHost, stream));
     SCN_CUDA(cudaStreamSynchronize(stream));

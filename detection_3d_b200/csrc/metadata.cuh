@@ -7,6 +7,9 @@
 #include <map>
 #include <vector>
 #include <array>
+#include <mutex>
+#include <atomic>
+#include <thread>
 
 namespace scn {
 
@@ -70,17 +73,52 @@ struct DeconvPlan {
   unsigned long long *tileMask = nullptr; // [nTiles] all ones (kept for the kernel's interface)
 };
 struct ConvGeomHost { int f[3], s[3], outS[3], cnt[3], M, K; };
-struct SubmEntry { RuleBookDev rb; NbrPlan plan; };
-struct ConvEntry { RuleBookDev rb; NbrPlan plan; P3 out; P3 in; ConvGeomHost geom; DeconvPlan deconv; };
+// `ready` (guarded by Metadata::mapMu) flips once the entry is completely described on the host and
+// all its kernels are queued on the build stream; `ev` marks that point on the build stream and the
+// first feature kernel that uses the entry makes the compute stream wait for it (`waited`).
+struct Ready { bool ready = false; cudaEvent_t ev = nullptr; bool waited = false; };
+struct SubmEntry { RuleBookDev rb; NbrPlan plan; Ready rdy; };
+struct ConvEntry { RuleBookDev rb; NbrPlan plan; P3 out; P3 in; ConvGeomHost geom; DeconvPlan deconv; Ready rdy, deconvRdy; };
 
 struct InputRules {
   int mode = 0, maxActive = 0, nIn = 0, nOut = 0;
   int *tab = nullptr;  // [nOut*(1+maxActive)] device
   bool valid = false;
+  Ready rdy;
 };
 
 struct Metadata {
-  cudaStream_t stream = 0;
+  // Two streams: everything that BUILDS (grids, hash order, rulebooks, plans -- many short kernels
+  // and a few host readbacks of counts) runs on `stream`, a private high-priority stream; feature
+  // kernels run on the caller's `cstream`.  A host wait for a count then only drains the short
+  // build queue while the convolutions already submitted keep the GPU busy (the reference is
+  // synchronous throughout, SURVEY.md section 8b "Threading / streams").
+  cudaStream_t stream = 0;   // build stream
+  cudaStream_t cstream = 0;  // caller's compute stream
+  bool ownStream = false;
+  bool buildDirty = false;   // build work was queued since the last hand-off to the compute stream
+  cudaEvent_t evBuild = nullptr, evCompute = nullptr;
+  int to_compute();          // compute stream waits for everything built so far
+  int from_compute();        // build stream waits for everything the caller has queued so far
+  // Two threads may use one Metadata: the caller's and the prefetch worker (capi.cu).  `buildMu`
+  // serialises builds (they share the build stream and the scalar scratch); `mapMu` guards the
+  // structure of the caches and the ready flags, so that feature kernels of finished entries are
+  // submitted while the worker is still building later ones.
+  std::recursive_mutex buildMu;
+  std::mutex mapMu;
+  // glibc mutexes are not fair: a worker that re-locks buildMu for its next entry right after
+  // unlocking starves the caller (measured: the caller's first convolution waited 5.8 ms, until the
+  // worker had built the whole pyramid).  The caller announces itself here and the worker yields.
+  std::atomic<int> callerWaiting{0};
+  struct BuildLock {
+    Metadata &m;
+    explicit BuildLock(Metadata &md);
+    ~BuildLock() { m.buildMu.unlock(); }
+  };
+  std::vector<cudaEvent_t> events;
+  int mark_ready(Ready &r);   // record r.ev on the build stream, publish r.ready
+  int wait_ready(Ready &r);   // first use on the compute stream: wait for r.ev
+  bool is_ready(const Ready &r) { std::lock_guard<std::mutex> lk(mapMu); return r.ready; }
   std::map<P3, Grid> grids;
   std::map<SubmKey, SubmEntry> subm;   // submanifoldRuleBooks, Metadata.h:58-60
   std::map<ConvKey, ConvEntry> conv;   // ruleBooks, Metadata.h:65-67

@@ -124,6 +124,11 @@ class FPN_Net(nn.Module):
         roi_maps = [ups[i] for i in self.roi_scales_from_top]
         for i in range(len(rpn_maps_3d)):
             assert torch.all(rpn_maps_3d[i].spatial_size == torch.tensor(self.rpn_map_sizes[i]))
+        # The sequence of rulebooks a forward requests depends on the network only: remember it so that
+        # the next forward's Metadata can build them ahead of the layers (native.Metadata_3.prefetch).
+        inp = self.layers_in[0]
+        if getattr(inp, "prefetch_ops", None) is None and hasattr(net.metadata, "_oplog"):
+            inp.prefetch_ops = list(net.metadata._oplog)
         return rpn_maps, roi_maps
 
 

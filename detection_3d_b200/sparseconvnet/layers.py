@@ -58,6 +58,7 @@ class InputLayer(Module):
         self.spatial_size = toLongTensor(dimension, spatial_size)
         self.mode = mode
         self.device = None
+        self.prefetch_ops = None  # rulebook requests of an earlier forward of the owning network (a hint)
 
     def to(self, device):
         self.device = device
@@ -71,6 +72,8 @@ class InputLayer(Module):
         feats = input[1].to(self.device) if self.device else input[1]
         out.features = InputLayerFunction.apply(self.dimension, out.metadata, self.spatial_size, coords.long(), feats,
                                                 0 if len(input) == 2 else input[2], self.mode)
+        if self.prefetch_ops:
+            out.metadata.prefetch(self.prefetch_ops)
         return out
 
 

@@ -62,6 +62,21 @@ class Metadata_3(object):
         self._h = C.c_void_p()
         check(lib().scn_metadata_create(C.byref(self._h), _stream()))
         self._keep = []
+        self._oplog, self._opseen = [], set()  # rulebook requests of this forward, in order (see prefetch)
+
+    def _log(self, kind, a, b, f, s):
+        key = (kind,) + tuple(int(v) for t in (a, b, f, s) for v in t)
+        if key not in self._opseen:
+            self._opseen.add(key)
+            self._oplog.append(key)
+
+    def prefetch(self, ops):
+        """Hint: build these rulebooks ahead on a worker thread (scn_metadata_prefetch).  `ops` is the
+        `_oplog` of an earlier forward of the same network; results do not depend on it."""
+        if not ops:
+            return
+        flat = (C.c_long * (13 * len(ops)))(*[v for op in ops for v in op])
+        check(lib().scn_metadata_prefetch(self._h, len(ops), flat))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -162,6 +177,7 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
     """pybind.cpp:134-138 -> returns the multiply-add count like the reference."""
     _, cin, cout = _w3(weight)
     n = m.getNActive(spatial_size)
+    m._log(1, spatial_size, (0, 0, 0), filter_size, (0, 0, 0))
     output_features.resize_(n, cout)
     macs = C.c_double()
     check(lib().scn_submanifold_convolution_forward(m._h, l3(spatial_size), l3(filter_size), _dev_f32(input_features, "in"),
@@ -183,6 +199,7 @@ def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, i
     """pybind.cpp:54-59"""
     _, cin, cout = _w3(weight)
     n, r = C.c_long(), C.c_long()
+    m._log(2, in_size, out_size, filter_size, filter_stride)
     check(lib().scn_convolution_prepare(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), C.byref(n), C.byref(r)))
     output_features.resize_(n.value, cout)
     macs = C.c_double()
@@ -205,6 +222,7 @@ def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m,
     """pybind.cpp:78-83"""
     _, cin, cout = _w3(weight)
     n = m.getNActive(out_size)
+    m._log(3, in_size, out_size, filter_size, filter_stride)
     output_features.resize_(n, cout)
     macs = C.c_double()
     check(lib().scn_deconvolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),

@@ -59,6 +59,12 @@ int scn_get_spatial_locations(scn_metadata *m, const long spatial_size[3], long 
 /* Metadata::getSubmanifoldRuleBook (Metadata.cpp:429-443): builds (once) and reports the total
  * number of rules over all filter offsets. */
 int scn_submanifold_prepare(scn_metadata *m, const long spatial_size[3], const long filter_size[3], long *n_rules);
+/* Hint (no reference counterpart; the reference builds every rulebook lazily and synchronously on the
+ * calling thread, Metadata.cpp:429-510): build these rulebooks ahead on a worker thread + the build
+ * stream while the caller keeps submitting feature kernels.  ops = n_ops x 13 longs: kind (1 submanifold,
+ * 2 convolution, 3 deconvolution), a[3], b[3], filter[3], stride[3] with (a, b) = (size, -) / (in, out) /
+ * (in, out) exactly as the corresponding *_forward call receives them.  Results are unaffected. */
+int scn_metadata_prefetch(scn_metadata *m, int n_ops, const long *ops);
 /* Metadata::getRuleBook (Metadata.cpp:484-510): builds (once) the strided rulebook AND the output
  * grid; reports the output grid's active count and the number of rules. */
 int scn_convolution_prepare(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
