@@ -32,9 +32,9 @@ SYMBOLS = {
     "scn_rulebook_info": (_i, [_vp, _i, L3, L3, L3, _pi, _pl]),
     "scn_rulebook_copy": (_i, [_vp, _i, L3, L3, L3, _i, _vp]),
     "scn_iteration_order": (_i, [_vp, L3, _vp]),
-    "scn_submanifold_convolution_forward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp]),
-    "scn_convolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp]),
-    "scn_deconvolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp]),
+    "scn_submanifold_convolution_forward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp, C.c_longlong]),
+    "scn_convolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp, C.c_longlong]),
+    "scn_deconvolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp, C.c_longlong]),
     "scn_submanifold_convolution_backward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "scn_convolution_backward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "scn_deconvolution_backward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
@@ -70,10 +70,25 @@ def check(status):
         raise RuntimeError("scn_b200: " + lib().scn_last_error().decode("utf-8", "replace"))
 
 
+_L3_CACHE = {}
+
+
 def l3(v):
+    """long[3] argument.  Spatial / filter sizes arrive as small CPU LongTensors that live as long as
+    the module tree; the converted ctypes array is cached on (object id, version) for those."""
     if hasattr(v, "tolist"):
-        v = v.tolist()
-    v = [int(x) for x in v]
-    if len(v) != 3:
+        key = (id(v), v._version) if hasattr(v, "_version") else None
+        hit = _L3_CACHE.get(key) if key else None
+        if hit is not None and hit[0] is v:
+            return hit[1]
+        lst = [int(x) for x in v.tolist()]
+    else:
+        key, lst = None, [int(x) for x in v]
+    if len(lst) != 3:
         raise RuntimeError("this build is specialised for dimension 3 (Metadata_3)")
-    return L3(*v)
+    arr = L3(*lst)
+    if key is not None:
+        if len(_L3_CACHE) > 4096:
+            _L3_CACHE.clear()
+        _L3_CACHE[key] = (v, arr)  # keeps `v` alive, so its id cannot be reused while cached
+    return arr

@@ -27,7 +27,7 @@ int conv_backward_simt(const float *in, float *d_in, const float *d_out, const f
 int tc_available();
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
-                        long nInRows, const void *in16);
+                        long nInRows, const void *in16, long long wTag, int CinW = 0);
 static int g_math_mode = 0;
 } // namespace scn
 
@@ -249,36 +249,36 @@ static bool tc_ok(int Cin, int Cout, int K) {
   return scn::g_math_mode != 0 && scn::tc_available() && Cout % 32 == 0 && Cout >= 32 && Cout <= 256 && K <= 64 && Cin >= 4 && Cin <= 1024;
 }
 static int run_plan(Metadata &M, const scn::NbrPlan &plan, const float *in, float *out, const float *w, const float *bias, int Cin, int Cout,
-                    long nInRows, const void *in16) {
+                    long nInRows, const void *in16, long long wTag) {
   if (tc_ok(Cin, Cout, plan.K))
     return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.tileMask, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.cstream,
-                                    nullptr, plan.K, nInRows, in16);
+                                    nullptr, plan.K, nInRows, in16, wTag);
   return scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.cstream);
 }
 
 int scn_submanifold_convolution_forward(scn_metadata *m, const long sz[3], const long f[3], const float *in, float *out, const float *w,
-                                        const float *bias, int Cin, int Cout, double *macs, const void *in_bf16) {
+                                        const float *bias, int Cin, int Cout, double *macs, const void *in_bf16, long long weight_tag) {
   M_OR_FAIL(m);
   scn::SubmEntry *e;
   SCN_TRY(m->md.get_submanifold(sz, f, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
   SCN_TRY(m->md.wait_ready(e->rdy));
-  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(sz)->n, in_bf16);
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(sz)->n, in_bf16, weight_tag);
 }
 int scn_convolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
-                            float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16) {
+                            float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16, long long weight_tag) {
   M_OR_FAIL(m);
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
   SCN_TRY(m->md.wait_ready(e->rdy));
-  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(inS)->n, in_bf16);
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(inS)->n, in_bf16, weight_tag);
 }
 __global__ void k_fill_rows_bias(float *out, long n, int C, const float *bias) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n * C; i += (long)gridDim.x * blockDim.x) out[i] = bias ? bias[i % C] : 0.f;
 }
 int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
-                              float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16) {
+                              float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16, long long weight_tag) {
   M_OR_FAIL(m);
   // CPU/Deconvolution.cpp:15-16: the rulebook of the convolution outS -> inS
   scn::ConvEntry *e;
@@ -294,7 +294,7 @@ int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long out
     SCN_TRY(m->md.wait_ready(e->deconvRdy));
     const scn::DeconvPlan &d = e->deconv;
     return scn::launch_conv_plan_tc(in, out, w, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, 1, Cin, Cout, nullptr, scn::g_math_mode, s, d.tileW,
-                                    e->rb.nLists, m->md.find_grid(inS)->n, in_bf16);
+                                    e->rb.nLists, m->md.find_grid(inS)->n, in_bf16, weight_tag);
   }
   SCN_TRY(m->md.wait_ready(e->rdy));
   if (!single && gf->n) k_fill_rows_bias<<<scn::stream_grid((long)gf->n * Cout, 256), 256, 0, scn::LS(s)>>>(out, gf->n, Cout, bias);
@@ -334,11 +334,23 @@ int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *sav
                           void *stream, void *out_bf16) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   SCN_CHECK(mode >= 0 && mode <= 2, "mode");
+  // persistent, zero-initialised workspace per stream (calls on one stream are ordered; the
+  // finalize kernel re-zeroes the statistics): no allocation, no memset per call
+  static std::mutex mu;
+  static std::vector<std::pair<cudaStream_t, void *>> cache;
+  constexpr int kMaxC = scn::kBnMaxC;
+  SCN_CHECK(C <= kMaxC, "BatchNorm: too many channels");
   void *ws = nullptr;
-  SCN_CUDA(cudaMallocAsync(&ws, (size_t)C * 24 + 64, s));
-  int r = scn::bn_forward(in, out, n, C, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, mode, leak, ws, s, out_bf16);
-  cudaFreeAsync(ws, s);
-  return r;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto &e : cache) if (e.first == s) ws = e.second;
+    if (!ws) {
+      SCN_CUDA(cudaMalloc(&ws, (size_t)kMaxC * 24 + 64));
+      SCN_CUDA(cudaMemset(ws, 0, (size_t)kMaxC * 24 + 64));
+      cache.emplace_back(s, ws);
+    }
+  }
+  return scn::bn_forward(in, out, n, C, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, mode, leak, ws, s, out_bf16);
 }
 int scn_batchnorm_backward(const float *in, float *d_in, const float *out, float *d_out, long n, int C, const float *save_mean,
                            const float *save_invstd, const float *weight, float *d_weight, float *d_bias, float leak, void *stream) {

@@ -27,6 +27,9 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 namespace scn {
 
@@ -443,7 +446,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(const TcParams P) {
 // W [K][Cin][Cout] fp32 -> per (k, 128-byte K atom) the exact shared-memory image of the B operand:
 // Cout rows x 128 bytes (32 tf32 / 64 bf16 input channels of one output channel), 16-byte chunks
 // XOR-swizzled by (row & 7); values rounded to nearest (TF32: cvt.rna, BF16: rn).
-__global__ void k_prep_wimg(const float *__restrict__ W, unsigned char *__restrict__ img, int K, int Cin, int Cout, int bf16) {
+// Cin = padded channel count of the image (multiple of the atom width), CinW = channels W really has.
+__global__ void k_prep_wimg(const float *__restrict__ W, unsigned char *__restrict__ img, int K, int Cin, int CinW, int Cout, int bf16) {
   const long n = (long)K * Cin * Cout;
   const int per = bf16 ? 64 : 32, nAtoms = Cin / per;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -453,14 +457,71 @@ __global__ void k_prep_wimg(const float *__restrict__ W, unsigned char *__restri
     const int c = ci / per, j = ci % per;
     const int byte = j * (bf16 ? 2 : 4), chunk = byte >> 4, within = byte & 15;
     unsigned char *dst = img + ((long)k * nAtoms + c) * Cout * 128 + (long)co * 128 + ((chunk ^ (co & 7)) << 4) + within;
+    const float w = ci < CinW ? W[((long)k * CinW + ci) * Cout + co] : 0.f;
     if (bf16) {
-      *reinterpret_cast<unsigned short *>(dst) = __bfloat16_as_ushort(__float2bfloat16_rn(W[i]));
+      *reinterpret_cast<unsigned short *>(dst) = __bfloat16_as_ushort(__float2bfloat16_rn(w));
     } else {
       uint32_t r;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(W[i]));
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w));
       *reinterpret_cast<uint32_t *>(dst) = r;
     }
   }
+}
+
+// Weight images are cached across calls: (device pointer, caller's version tag, shape, operand
+// type) -> image.  The tag is how the caller says "same contents as last time" (the Python layer
+// passes a per-Parameter token combined with the tensor's in-place version counter); tag 0 = no caching.
+struct WimgKey {
+  const void *w; long long tag; int K, Cin, CinW, Cout, bf16;
+  bool operator<(const WimgKey &o) const {
+    return std::tie(w, tag, K, Cin, CinW, Cout, bf16) < std::tie(o.w, o.tag, o.K, o.Cin, o.CinW, o.Cout, o.bf16);
+  }
+};
+struct WimgVal { unsigned char *img; size_t bytes; cudaEvent_t ready; cudaStream_t stream; unsigned long long lastUse; };
+static std::map<WimgKey, WimgVal> g_wimg;
+static std::mutex g_wimg_mu;
+static size_t g_wimg_bytes = 0;
+static unsigned long long g_wimg_clock = 0;
+constexpr size_t kWimgBudget = 768u << 20;
+// Returns the image; *owned = true when the caller must cudaFreeAsync it (uncached).
+static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int Cout, int bf16, cudaStream_t s, unsigned char **img, bool *owned) {
+  const size_t bytes = (size_t)K * Cin * Cout * (bf16 ? 2 : 4);
+  *owned = false;
+  if (tag != 0) {
+    std::lock_guard<std::mutex> lk(g_wimg_mu);
+    WimgKey key{W, tag, K, Cin, CinW, Cout, bf16};
+    auto it = g_wimg.find(key);
+    if (it != g_wimg.end()) {
+      it->second.lastUse = ++g_wimg_clock;
+      if (it->second.stream != s) SCN_CUDA(cudaStreamWaitEvent(s, it->second.ready, 0));
+      *img = it->second.img;
+      return 0;
+    }
+    // stale versions of the same weight tensor, then least-recently-used entries beyond the budget
+    for (auto j = g_wimg.begin(); j != g_wimg.end();) {
+      if (j->first.w == W && j->first.tag != tag) { cudaFree(j->second.img); cudaEventDestroy(j->second.ready); g_wimg_bytes -= j->second.bytes; j = g_wimg.erase(j); }
+      else ++j;
+    }
+    while (g_wimg_bytes + bytes > kWimgBudget && !g_wimg.empty()) {
+      auto lru = g_wimg.begin();
+      for (auto j = g_wimg.begin(); j != g_wimg.end(); ++j) if (j->second.lastUse < lru->second.lastUse) lru = j;
+      cudaFree(lru->second.img); cudaEventDestroy(lru->second.ready); g_wimg_bytes -= lru->second.bytes; g_wimg.erase(lru);
+    }
+    WimgVal v;
+    SCN_CUDA(cudaMalloc((void **)&v.img, bytes));
+    SCN_CUDA(cudaEventCreateWithFlags(&v.ready, cudaEventDisableTiming));
+    k_prep_wimg<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, v.img, K, Cin, CinW, Cout, bf16);
+    SCN_CUDA(cudaEventRecord(v.ready, s));
+    v.bytes = bytes; v.stream = s; v.lastUse = ++g_wimg_clock;
+    g_wimg[key] = v;
+    g_wimg_bytes += bytes;
+    *img = v.img;
+    return 0;
+  }
+  SCN_CUDA(cudaMallocAsync((void **)img, bytes, s));
+  k_prep_wimg<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, *img, K, Cin, CinW, Cout, bf16);
+  *owned = true;
+  return 0;
 }
 
 int tc_available() {
@@ -493,19 +554,16 @@ __global__ void __launch_bounds__(256) k_to_bf16(const float *__restrict__ x, ui
 // in16: optional bf16 copy of `in` (same layout); used in math mode 2 when Cin is a multiple of 64
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
-                        long nInRows, const void *in16) {
+                        long nInRows, const void *in16, long long wTag, int CinW = 0) {
   if (nOut == 0) return 0;
-  if (Cin % 32 != 0) { // e.g. the 9-channel input convolution: zero-pad rows and weight slices to 32 channels
+  if (CinW == 0) CinW = Cin;
+  if (Cin % 32 != 0) { // e.g. the 9-channel input convolution: rows zero-padded to 32 channels (the weight image pads itself)
     const int Cp = (Cin + 31) / 32 * 32;
-    float *xp = nullptr, *wp = nullptr;
+    float *xp = nullptr;
     SCN_CUDA(cudaMallocAsync((void **)&xp, (size_t)nInRows * Cp * 4, s));
-    SCN_CUDA(cudaMallocAsync((void **)&wp, (size_t)nWeights * Cp * Cout * 4, s));
     k_pad_rows<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
-    SCN_CUDA(cudaMemsetAsync(wp, 0, (size_t)nWeights * Cp * Cout * 4, s));
-    SCN_CUDA(cudaMemcpy2DAsync(wp, (size_t)Cp * Cout * 4, W, (size_t)Cin * Cout * 4, (size_t)Cin * Cout * 4, nWeights, cudaMemcpyDeviceToDevice, s));
-    int r = launch_conv_plan_tc(xp, out, wp, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr);
+    int r = launch_conv_plan_tc(xp, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr, wTag, Cin);
     cudaFreeAsync(xp, s);
-    cudaFreeAsync(wp, s);
     return r;
   }
   SCN_CHECK(Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && K <= 64, "tcgen05 path: unsupported channel counts");
@@ -555,9 +613,9 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   const size_t smem = (size_t)P.S * stageBytes + fixed;
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
   unsigned char *wimg = nullptr;
-  SCN_CUDA(cudaMallocAsync((void **)&wimg, (size_t)nWeights * Cin * Cout * 4, s));
+  bool wimgOwned = false;
+  SCN_TRY(get_wimg(W, wTag, nWeights, Cin, CinW, Cout, P.bf16, s, &wimg, &wimgOwned));
   P.wimg = wimg;
-  k_prep_wimg<<<stream_grid((long)nWeights * Cin * Cout, 256), 256, 0, LS(s)>>>(W, wimg, nWeights, Cin, Cout, P.bf16);
   static bool attr = false;
   if (!attr) {
     SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -583,7 +641,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
             grid, P.T, K, Cin, Cout, P.S, P.nAcc, P.kSplit, m[0], m[1], m[4], m[5], m[6], m[7], m[10], m[11], m[12], m[13], m[14], m[15], m[16], m[17]);
     cudaFreeAsync(P.prof, s);
   }
-  cudaFreeAsync(wimg, s);
+  if (wimgOwned) cudaFreeAsync(wimg, s);
   if (tmp16) cudaFreeAsync(tmp16, s);
   return 0;
 }

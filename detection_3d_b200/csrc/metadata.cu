@@ -86,12 +86,25 @@ int Metadata::from_compute() {
 void *Metadata::alloc(size_t bytes) {
   void *p = nullptr;
   buildDirty = true;
-  if (bytes < 256) bytes = 256;
-  if (cudaMallocAsync(&p, bytes, stream) != cudaSuccess) {
+  bytes = (std::max<size_t>(bytes, 256) + 255) & ~(size_t)255;
+  if (arena && arenaUsed + bytes <= arenaCap) {
+    p = arena + arenaUsed;
+    arenaUsed += bytes;
+    return p;
+  }
+  const bool dedicated = bytes > arenaNext / 2; // large buffers get their own block, the current chunk stays in use
+  const size_t cap = dedicated ? bytes : arenaNext;
+  if (cudaMallocAsync(&p, cap, stream) != cudaSuccess) {
     set_error("cudaMallocAsync failed");
     return nullptr;
   }
   allocs.push_back(p);
+  if (!dedicated) {
+    arena = static_cast<char *>(p);
+    arenaCap = cap;
+    arenaUsed = bytes;
+    arenaNext = std::min<size_t>(arenaNext * 2, 256u << 20);
+  }
   return p;
 }
 int Metadata::init() {

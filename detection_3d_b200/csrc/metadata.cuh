@@ -124,6 +124,10 @@ struct Metadata {
   std::map<ConvKey, ConvEntry> conv;   // ruleBooks, Metadata.h:65-67
   InputRules input;
   std::vector<void *> allocs;
+  // bump allocator over a few stream-ordered chunks: a Metadata makes ~350 small allocations per
+  // forward and frees them all together, and each cudaMallocAsync / cudaFreeAsync costs 3-5 us of host time
+  char *arena = nullptr;
+  size_t arenaCap = 0, arenaUsed = 0, arenaNext = 16u << 20;
   // zero-initialised pool for scan states
   unsigned long long *zpool = nullptr;
   size_t zpoolWords = 0, zpoolUsed = 0;

@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(256) k_bn_stats_scalar(const float *__restrict
 // mode 2: eval, track_running_stats=False -- sparseconvnet/batchNormalization.py:51-56: mean(0) and the
 //                    UNBIASED var(0) of this input stand in for the running stats.
 // Emits saveMean/saveInvStd and the fused scale/shift  y = x*scale + shift.
-__global__ void k_bn_finalize(const double *__restrict__ stats, long n, int C, int mode, float eps, float momentum, float *saveMean,
+// Leaves `stats` zeroed for the next call (the forward workspace is persistent per stream and starts zeroed).
+__global__ void k_bn_finalize(double *__restrict__ stats, long n, int C, int mode, float eps, float momentum, float *saveMean,
                               float *saveInvStd, float *runningMean, float *runningVar, const float *__restrict__ weight,
                               const float *__restrict__ bias, float *scale, float *shift) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,6 +97,8 @@ __global__ void k_bn_finalize(const double *__restrict__ stats, long n, int C, i
   } else {
     double m = stats[c] / (double)n;
     double ss = stats[C + c] - m * m * (double)n; // sum of squared deviations
+    stats[c] = 0.0;
+    stats[C + c] = 0.0;
     if (ss < 0) ss = 0;
     mean = (float)m;
     if (mode == 0) {
@@ -145,7 +148,6 @@ __global__ void __launch_bounds__(256) k_bn_apply_scalar(const float *__restrict
 }
 
 static int bn_stats_launch(const float *x, long n, int C, double *stats, cudaStream_t s) {
-  SCN_CUDA(cudaMemsetAsync(stats, 0, 2 * C * sizeof(double), s));
   if (n == 0) return 0;
   int rowsPerCta = (int)std::max<long>(64, (n + kSMs * 8 - 1) / (kSMs * 8)); // <= 8 CTAs per SM: few atomics per channel
   int grid = cdiv(n, rowsPerCta);
@@ -160,11 +162,11 @@ static int bn_stats_launch(const float *x, long n, int C, double *stats, cudaStr
   return 0;
 }
 
-// workspace: 2*C doubles + 2*C floats
+// workspace: 2*kBnMaxC doubles (zero on entry, zero again on exit) + 2*kBnMaxC floats
 int bn_forward(const float *x, float *y, long n, int C, float *saveMean, float *saveInvStd, float *runningMean, float *runningVar,
                const float *weight, const float *bias, float eps, float momentum, int mode, float leak, void *workspace, cudaStream_t s, void *y16) {
   double *stats = static_cast<double *>(workspace);
-  float *scale = reinterpret_cast<float *>(stats + 2 * C), *shift = scale + C;
+  float *scale = reinterpret_cast<float *>(stats + 2 * kBnMaxC), *shift = scale + kBnMaxC; // fixed layout: the statistics area stays zero between calls
   if (mode != 1) SCN_TRY(bn_stats_launch(x, n, C, stats, s));
   k_bn_finalize<<<cdiv(C, 128), 128, 0, LS(s)>>>(stats, n, C, mode, eps, momentum, saveMean, saveInvStd, runningMean, runningVar, weight, bias, scale, shift);
   if (n) {

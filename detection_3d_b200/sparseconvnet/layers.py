@@ -36,6 +36,21 @@ def Metadata(dim):
     return native.Metadata_3()
 
 
+class _NoCtx(object):
+    """Stand-in for the autograd context when no graph is being recorded."""
+
+    def save_for_backward(self, *tensors):
+        pass
+
+
+def _run(fn, *args):
+    """fn.apply(*args) when autograd is recording, else the forward alone (Function.apply costs
+    ~15 us per call and the backbone has ~100 calls per forward)."""
+    if torch.is_grad_enabled():
+        return fn.apply(*args)
+    return fn.forward(_NoCtx(), *args)
+
+
 def _counters():
     import detection_3d_b200.sparseconvnet as pkg
     return pkg
@@ -70,7 +85,7 @@ class InputLayer(Module):
         if not coords.is_cuda:  # the reference keeps coordinates on the host; a CUDA tensor is accepted as is
             coords = coords.long()
         feats = input[1].to(self.device) if self.device else input[1]
-        out.features = InputLayerFunction.apply(self.dimension, out.metadata, self.spatial_size, coords.long(), feats,
+        out.features = _run(InputLayerFunction, self.dimension, out.metadata, self.spatial_size, coords.long(), feats,
                                                 0 if len(input) == 2 else input[2], self.mode)
         if self.prefetch_ops:
             out.metadata.prefetch(self.prefetch_ops)
@@ -108,7 +123,7 @@ class SubmanifoldConvolution(Module):
     def forward(self, input):
         assert input.features.nelement() == 0 or input.features.size(1) == self.nIn, (self.nIn, self.nOut, input)
         out = SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size)
-        out.features = SubmanifoldConvolutionFunction.apply(input.features, self.weight, optionalTensor(self, 'bias'), input.metadata,
+        out.features = _run(SubmanifoldConvolutionFunction, input.features, self.weight, optionalTensor(self, 'bias'), input.metadata,
                                                             input.spatial_size, self.dimension, self.filter_size)
         return out
 
@@ -177,7 +192,7 @@ class Convolution(Module):
         out.spatial_size = (input.spatial_size - self.filter_size) // self.filter_stride + 1
         assert ((out.spatial_size - 1) * self.filter_stride + self.filter_size == input.spatial_size).all(), \
             (input.spatial_size, out.spatial_size, self.filter_size, self.filter_stride)
-        out.features = ConvolutionFunction.apply(input.features, self.weight, optionalTensor(self, 'bias'), input.metadata, input.spatial_size,
+        out.features = _run(ConvolutionFunction, input.features, self.weight, optionalTensor(self, 'bias'), input.metadata, input.spatial_size,
                                                  out.spatial_size, self.dimension, self.filter_size, self.filter_stride)
         return out
 
@@ -228,7 +243,7 @@ class Deconvolution(Module):
         assert input.features.nelement() == 0 or input.features.size(1) == self.nIn
         out = SparseConvNetTensor(metadata=input.metadata)
         out.spatial_size = (input.spatial_size - 1) * self.filter_stride + self.filter_size
-        out.features = DeconvolutionFunction.apply(input.features, self.weight, optionalTensor(self, 'bias'), input.metadata, input.spatial_size,
+        out.features = _run(DeconvolutionFunction, input.features, self.weight, optionalTensor(self, 'bias'), input.metadata, input.spatial_size,
                                                    out.spatial_size, self.dimension, self.filter_size, self.filter_stride)
         return out
 
@@ -285,7 +300,7 @@ class BatchNormalization(Module):
         assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes, (self.nPlanes, input.features.shape)
         out = SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size)
         instance = not (self.training or self.track_running_stats)
-        out.features = BatchNormalizationFunction.apply(input.features, optionalTensor(self, 'weight'), optionalTensor(self, 'bias'),
+        out.features = _run(BatchNormalizationFunction, input.features, optionalTensor(self, 'weight'), optionalTensor(self, 'bias'),
                                                         self.running_mean, self.running_var, self.eps, self.momentum, self.training,
                                                         self.leakiness, instance)
         return out

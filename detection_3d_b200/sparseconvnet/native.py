@@ -46,6 +46,22 @@ def _attach_shadow(t, sh):
         t._scn_bf16 = (sh, t._version)
 
 
+_TOKENS = iter(range(1, 1 << 40))
+
+
+def _weight_tag(w):
+    """Identifies the contents of a weight tensor for the native operand-image cache: a token that
+    is unique per tensor OBJECT (ids and addresses get reused) combined with the in-place version."""
+    tok = getattr(w, "_scn_token", None)
+    if tok is None:
+        tok = next(_TOKENS)
+        try:
+            w._scn_token = tok
+        except Exception:
+            return 0
+    return (tok << 24) + (w._version & 0xFFFFFF) + 1
+
+
 def _shadow_ptr(t):
     sh = getattr(t, "_scn_bf16", None)
     if sh is None or _MATH["mode"] != 2 or sh[1] != t._version or sh[0].shape != t.shape:
@@ -182,7 +198,7 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
     macs = C.c_double()
     check(lib().scn_submanifold_convolution_forward(m._h, l3(spatial_size), l3(filter_size), _dev_f32(input_features, "in"),
                                                     _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"),
-                                                    cin, cout, C.byref(macs), _shadow_ptr(input_features)))
+                                                    cin, cout, C.byref(macs), _shadow_ptr(input_features), _weight_tag(weight)))
     return macs.value
 
 
@@ -205,7 +221,7 @@ def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, i
     macs = C.c_double()
     check(lib().scn_convolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
                                         _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs),
-                                        _shadow_ptr(input_features)))
+                                        _shadow_ptr(input_features), _weight_tag(weight)))
     return macs.value
 
 
@@ -227,7 +243,7 @@ def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m,
     macs = C.c_double()
     check(lib().scn_deconvolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
                                           _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs),
-                                          _shadow_ptr(input_features)))
+                                          _shadow_ptr(input_features), _weight_tag(weight)))
     return macs.value
 
 
