@@ -183,12 +183,20 @@ int scn_convolution_prepare(scn_metadata *m, const long inS[3], const long outS[
 }
 
 static int find_rb(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], scn::RuleBookDev **rb) {
-  std::lock_guard<std::mutex> lk(m->md.mapMu);
   if (kind == 1) {
-    auto it = m->md.subm.find(scn::SubmKey{scn::P3{a[0], a[1], a[2]}, scn::P3{b[0], b[1], b[2]}});
-    SCN_CHECK(it != m->md.subm.end() && it->second.rdy.ready, "submanifold rulebook not built");
-    *rb = &it->second.rb;
-  } else {
+    scn::SubmEntry *e = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(m->md.mapMu);
+      auto it = m->md.subm.find(scn::SubmKey{scn::P3{a[0], a[1], a[2]}, scn::P3{b[0], b[1], b[2]}});
+      SCN_CHECK(it != m->md.subm.end() && it->second.rdy.ready, "submanifold rulebook not built");
+      e = &it->second;
+    }
+    SCN_TRY(m->md.ensure_subm_rules(*e));
+    *rb = &e->rb;
+    return 0;
+  }
+  std::lock_guard<std::mutex> lk(m->md.mapMu);
+  {
     auto it = m->md.conv.find(scn::ConvKey{scn::P3{a[0], a[1], a[2]}, scn::P3{b[0], b[1], b[2]}, scn::P3{c[0], c[1], c[2]}});
     SCN_CHECK(it != m->md.conv.end() && it->second.rdy.ready, "convolution rulebook not built");
     *rb = &it->second.rb;
@@ -306,8 +314,10 @@ int scn_submanifold_convolution_backward(scn_metadata *m, const long sz[3], cons
   M_OR_FAIL(m);
   scn::SubmEntry *e;
   SCN_TRY(m->md.get_submanifold(sz, f, &e));
+  SCN_TRY(m->md.ensure_subm_rules(*e));
   scn::Grid *g = m->md.find_grid(sz);
   SCN_TRY(m->md.wait_ready(e->rdy));
+  SCN_TRY(m->md.wait_ready(e->rulesRdy));
   return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.cstream);
 }
 int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,

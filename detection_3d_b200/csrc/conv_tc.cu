@@ -174,8 +174,11 @@ __device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
 }
 
 // ------------------------------------------------------------------ kernel
+// Launch bound 576 (> the 448 threads used) caps the kernel at 112 registers per thread: a resident
+// CTA then leaves ~15K registers and ~17 KB of shared memory per SM, enough for the short
+// rulebook-build kernels of the other stream to run beside it instead of queueing behind it.
 template <bool BF16>
-__global__ void __launch_bounds__(kThreads, 1) conv_plan_tc(const TcParams P) {
+__global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWork = P.nSuper * P.kSplit;

@@ -757,7 +757,6 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   SCN_CHECK(g, "no active sites recorded for this spatial size");
   long K = f[0] * f[1] * f[2];
   SCN_CHECK(K >= 1 && K <= 64 && f[0] > 0 && f[1] > 0 && f[2] > 0, "unsupported submanifold filter size");
-  SCN_TRY(ensure_rank(*g));
   SubmEntry *ep;
   { std::lock_guard<std::mutex> lk(mapMu); ep = &subm[key]; }
   SubmEntry &e = *ep;
@@ -773,14 +772,31 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   }
   SCN_CUDA(cudaMemsetAsync(d_scalars, 0, 4, stream));
   if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, d_scalars);
-  SCN_TRY(build_rule_lists(*this, g->n, (int)K, SubmMask{g->rank2id, g->id2p, e.plan.nbr, (int)K},
-                           SubmPair{g->rank2id, g->id2p, e.plan.nbr, (int)K}, e.rb, 1));
-  e.plan.nValid = h_scalars[0];
-  SCN_CHECK(e.plan.nValid == e.rb.total, "internal: rule count mismatch");
+  // The forward pass only needs the plan and the rule COUNT (the reference's multiply-add counter);
+  // the per-offset (in,out) lists in the reference's hash-iteration order are materialised on demand
+  // (ensure_subm_rules: backward pass, rulebook inspection).
   SCN_TRY(build_tile_masks(e.plan));
+  SCN_TRY(sync_scalars(1));
+  e.plan.nValid = h_scalars[0];
+  e.rb.nLists = (int)K;
+  e.rb.total = e.plan.nValid;
+  e.sz = key.sz;
   SCN_TRY(mark_ready(e.rdy));
   *out = &e;
   return 0;
+}
+// SubmanifoldConvolution_SgToRules order (SubmanifoldConvolutionRules.h:26-45): sites in hash-iteration order
+int Metadata::ensure_subm_rules(SubmEntry &e) {
+  if (is_ready(e.rulesRdy)) return 0;
+  BuildLock bl(*this);
+  if (is_ready(e.rulesRdy)) return 0;
+  Grid *g = find_grid(e.sz.data());
+  SCN_CHECK(g, "grid");
+  SCN_TRY(ensure_rank(*g));
+  const int K = e.plan.K;
+  SCN_TRY(build_rule_lists(*this, g->n, K, SubmMask{g->rank2id, g->id2p, e.plan.nbr, K}, SubmPair{g->rank2id, g->id2p, e.plan.nbr, K}, e.rb, 0));
+  SCN_CHECK(e.plan.nValid == e.rb.total, "internal: rule count mismatch");
+  return mark_ready(e.rulesRdy);
 }
 
 // ------------------------------------------------------------------ strided convolution

@@ -77,7 +77,7 @@ struct ConvGeomHost { int f[3], s[3], outS[3], cnt[3], M, K; };
 // all its kernels are queued on the build stream; `ev` marks that point on the build stream and the
 // first feature kernel that uses the entry makes the compute stream wait for it (`waited`).
 struct Ready { bool ready = false; cudaEvent_t ev = nullptr; bool waited = false; };
-struct SubmEntry { RuleBookDev rb; NbrPlan plan; Ready rdy; };
+struct SubmEntry { RuleBookDev rb; NbrPlan plan; Ready rdy, rulesRdy; P3 sz; }; // rb.pairs / offsets only after ensure_subm_rules
 struct ConvEntry { RuleBookDev rb; NbrPlan plan; P3 out; P3 in; ConvGeomHost geom; DeconvPlan deconv; Ready rdy, deconvRdy; };
 
 struct InputRules {
@@ -147,6 +147,7 @@ struct Metadata {
   Grid *find_grid(const long *sz);
   int ensure_rank(Grid &g);
   int get_submanifold(const long *sz, const long *f, SubmEntry **out);
+  int ensure_subm_rules(SubmEntry &e);
   int get_conv(const long *inS, const long *outS, const long *f, const long *s, ConvEntry **out);
   int spatial_locations(const long *sz, long *out, int outOnDevice);
   int build_tile_masks(NbrPlan &plan);
