@@ -17,16 +17,27 @@ const char *last_error() { return g_err.c_str(); }
 // pinned scratch blocks are recycled across Metadata objects: cudaMallocHost costs milliseconds and a
 // fresh Metadata is created for every forward (sparseconvnet/ioLayers.py:52-55)
 static std::vector<int *> g_pinned_free;
+static std::mutex g_pool_mu; // the recycling lists (pinned blocks, streams, events, chunks) are shared by all Metadata objects
 static int *pinned_get() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
   if (!g_pinned_free.empty()) { int *p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
   int *p = nullptr;
   if (cudaMallocHost(&p, 256 * 4) != cudaSuccess) return nullptr;
   return p;
 }
+// Device memory of a Metadata comes from a process-wide list of chunks that are never handed back to
+// the driver.  The CUDA stream-ordered pool was measured to stall for 2-9 ms per call here: every
+// Metadata allocates on its own build stream and is freed while the next one is already building on
+// another stream, so the pool cannot reuse the blocks and maps fresh memory each forward.  A chunk
+// carries the event that marks the end of its previous owner's work; the next owner's build stream
+// waits for that event before the first use.
+static std::vector<Chunk> g_chunks;
+static size_t g_chunk_bytes = 0;
+constexpr size_t kChunkKeep = 12ull << 30; // beyond this much idle memory, chunks go back to the driver
+static size_t chunk_round(size_t b) { const size_t q = 32u << 20; return (b + q - 1) / q * q; }
 // build streams are recycled like the pinned blocks (stream creation is not free either)
 static std::vector<cudaStream_t> g_stream_free;
 static std::vector<cudaEvent_t> g_event_free;
-static std::mutex g_pool_mu; // the recycling lists above are shared by all Metadata objects
 thread_local bool tl_prefetch_worker = false;
 void set_prefetch_worker_thread(bool on) { tl_prefetch_worker = on; }
 Metadata::BuildLock::BuildLock(Metadata &md) : m(md) {
@@ -59,9 +70,18 @@ int Metadata::wait_ready(Ready &r) {
   return 0;
 }
 Metadata::~Metadata() {
-  from_compute(); // the frees below are ordered after every feature kernel that still reads these buffers
-  for (void *p : allocs) cudaFreeAsync(p, stream);
-  if (h_scalars) g_pinned_free.push_back(h_scalars);
+  from_compute(); // what follows on the build stream is ordered after every feature kernel that still reads these buffers
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    for (Chunk &c : chunks) {
+      if (!c.freed) cudaEventCreateWithFlags(&c.freed, cudaEventDisableTiming);
+      cudaEventRecord(c.freed, stream);
+      if (g_chunk_bytes + c.cap > kChunkKeep) { cudaEventSynchronize(c.freed); cudaFree(c.p); cudaEventDestroy(c.freed); continue; }
+      g_chunks.push_back(c);
+      g_chunk_bytes += c.cap;
+    }
+    if (h_scalars) g_pinned_free.push_back(h_scalars);
+  }
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     if (ownStream) g_stream_free.push_back(stream);
@@ -93,15 +113,26 @@ void *Metadata::alloc(size_t bytes) {
     return p;
   }
   const bool dedicated = bytes > arenaNext / 2; // large buffers get their own block, the current chunk stays in use
-  const size_t cap = dedicated ? bytes : arenaNext;
-  if (cudaMallocAsync(&p, cap, stream) != cudaSuccess) {
-    set_error("cudaMallocAsync failed");
-    return nullptr;
+  const size_t cap = chunk_round(dedicated ? bytes : arenaNext);
+  Chunk c{nullptr, 0, nullptr};
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    int best = -1;
+    for (int i = 0; i < (int)g_chunks.size(); i++)
+      if (g_chunks[i].cap >= cap && g_chunks[i].cap <= 2 * cap && (best < 0 || g_chunks[i].cap < g_chunks[best].cap)) best = i;
+    if (best >= 0) { c = g_chunks[best]; g_chunks.erase(g_chunks.begin() + best); g_chunk_bytes -= c.cap; }
   }
-  allocs.push_back(p);
+  if (c.p) {
+    if (cudaStreamWaitEvent(stream, c.freed, 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); return nullptr; }
+  } else {
+    if (cudaMalloc(&c.p, cap) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
+    c.cap = cap;
+  }
+  chunks.push_back(c);
+  p = c.p;
   if (!dedicated) {
     arena = static_cast<char *>(p);
-    arenaCap = cap;
+    arenaCap = c.cap;
     arenaUsed = bytes;
     arenaNext = std::min<size_t>(arenaNext * 2, 256u << 20);
   }

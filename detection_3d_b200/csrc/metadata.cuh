@@ -87,6 +87,7 @@ struct InputRules {
   Ready rdy;
 };
 
+struct Chunk { void *p; size_t cap; cudaEvent_t freed; };
 struct Metadata {
   // Two streams: everything that BUILDS (grids, hash order, rulebooks, plans -- many short kernels
   // and a few host readbacks of counts) runs on `stream`, a private high-priority stream; feature
@@ -123,7 +124,7 @@ struct Metadata {
   std::map<SubmKey, SubmEntry> subm;   // submanifoldRuleBooks, Metadata.h:58-60
   std::map<ConvKey, ConvEntry> conv;   // ruleBooks, Metadata.h:65-67
   InputRules input;
-  std::vector<void *> allocs;
+  std::vector<Chunk> chunks; // device memory of this Metadata (returned to the process-wide list on destruction)
   // bump allocator over a few stream-ordered chunks: a Metadata makes ~350 small allocations per
   // forward and frees them all together, and each cudaMallocAsync / cudaFreeAsync costs 3-5 us of host time
   char *arena = nullptr;

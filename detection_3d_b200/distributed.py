@@ -1,0 +1,110 @@
+"""Multi-GPU host logic of the backbone path: one process per GPU.
+
+* Inference shards by BUILDING: every forward builds its own Metadata (sparseconvnet/ioLayers.py:52-55),
+  buildings share nothing, so ranks never exchange data on the data path; the per-building results
+  are collected on the host at the end (`gather_results`).
+* Training is data parallel: the only collective is one all-reduce of the gradients
+  (tools/train_net_sparse3d.py:52-58 wraps the model in DistributedDataParallel with
+  broadcast_buffers=False; BatchNorm statistics stay per GPU).  Parameters of the dead top-down
+  levels never receive a gradient; they are reduced as zeros so that every rank
+  reduces the same flat layout.
+
+Backend-agnostic: NCCL over NVLink on the GPU box, gloo in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_buildings(sizes, world_size, rank, policy="lpt"):
+    """Indices of the buildings rank `rank` processes.
+
+    sizes: per-building cost proxy (active voxels / input rows).  policy 'lpt' = longest processing
+    time first onto the least loaded rank (ties -> lowest rank), 'round_robin' = i % world_size.
+    Deterministic and identical on every rank; the shards are disjoint and cover every building."""
+    n = len(sizes)
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world_size")
+    if policy == "round_robin":
+        return [i for i in range(n) if i % world_size == rank]
+    if policy != "lpt":
+        raise ValueError("policy must be 'lpt' or 'round_robin'")
+    order = sorted(range(n), key=lambda i: (-int(sizes[i]), i))
+    load = [0] * world_size
+    mine = []
+    for i in order:
+        r = min(range(world_size), key=lambda q: (load[q], q))
+        load[r] += int(sizes[i])
+        if r == rank:
+            mine.append(i)
+    return sorted(mine)
+
+
+def gather_results(local, dst=0, group=None):
+    """local: {building index: picklable result} of this rank.  Returns the merged dict on `dst`
+    (None elsewhere).  Host-side only: nothing on the GPU data path."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dict(local)
+    world = dist.get_world_size(group)
+    bucket = [None] * world if dist.get_rank(group) == dst else None
+    dist.gather_object(dict(local), bucket, dst=dst, group=group)
+    if bucket is None:
+        return None
+    merged = {}
+    for part in bucket:
+        dup = set(merged) & set(part)
+        if dup:
+            raise RuntimeError(f"buildings processed twice: {sorted(dup)}")
+        merged.update(part)
+    return merged
+
+
+def allreduce_gradients(params, group=None, bucket_bytes=64 << 20, average=True):
+    """Sum (or average) the gradients of `params` over all ranks with as few collectives as possible:
+    gradients are packed into flat fp32 buckets of <= bucket_bytes, all-reduced, and copied back.
+    A parameter whose .grad is None on this rank contributes zeros and receives the reduced value,
+    so ranks whose buildings leave different levels untouched still agree on the layout.
+    Returns the number of collectives issued."""
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return 0
+    dev = params[0].device
+    buckets, cur, cur_bytes = [], [], 0
+    for p in params:
+        nb = p.numel() * 4
+        if cur and cur_bytes + nb > bucket_bytes:
+            buckets.append(cur)
+            cur, cur_bytes = [], 0
+        cur.append(p)
+        cur_bytes += nb
+    if cur:
+        buckets.append(cur)
+    for bucket in buckets:
+        flat = torch.zeros(sum(p.numel() for p in bucket), dtype=torch.float32, device=dev)
+        off = 0
+        for p in bucket:
+            if p.grad is not None:
+                flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+            off += p.numel()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(world)
+        off = 0
+        for p in bucket:
+            g = flat[off:off + p.numel()].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += p.numel()
+    return len(buckets)
+
+
+def max_over_ranks_ms(ms, device, group=None):
+    """Device-timed milliseconds -> max over ranks (how every multi-GPU number of bench.py is taken)."""
+    t = torch.tensor([float(ms)], dtype=torch.float64, device=device)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

@@ -36,6 +36,10 @@ def Metadata(dim):
     return native.Metadata_3()
 
 
+import os as _os
+_PREFETCH = _os.environ.get("SCN_PREFETCH", "1") != "0"  # developer switch: build rulebooks lazily on the calling thread only
+
+
 class _NoCtx(object):
     """Stand-in for the autograd context when no graph is being recorded."""
 
@@ -87,7 +91,7 @@ class InputLayer(Module):
         feats = input[1].to(self.device) if self.device else input[1]
         out.features = _run(InputLayerFunction, self.dimension, out.metadata, self.spatial_size, coords.long(), feats,
                                                 0 if len(input) == 2 else input[2], self.mode)
-        if self.prefetch_ops:
+        if self.prefetch_ops and _PREFETCH:
             out.metadata.prefetch(self.prefetch_ops)
         return out
 

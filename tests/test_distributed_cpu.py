@@ -1,0 +1,97 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: building sharding without a collective,
+host-side result gathering, the data-parallel gradient all-reduce."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from detection_3d_b200 import distributed as D  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_shards_are_disjoint_cover_everything_and_balance():
+    sizes = [1155656, 900000, 1300000, 40000, 700000, 1100000, 950000, 20000, 1250000, 600000, 1000000]
+    for world in (1, 2, 4, 8):
+        for policy in ("lpt", "round_robin"):
+            shards = [D.shard_buildings(sizes, world, r, policy) for r in range(world)]
+            flat = sorted(i for s in shards for i in s)
+            assert flat == list(range(len(sizes))), (world, policy)
+        loads = [sum(sizes[i] for i in D.shard_buildings(sizes, world, r)) for r in range(world)]
+        if world > 1:  # LPT bound: max load <= mean + largest item
+            assert max(loads) <= sum(sizes) / world + max(sizes)
+            rr = [sum(sizes[i] for i in D.shard_buildings(sizes, world, r, "round_robin")) for r in range(world)]
+            assert max(loads) <= max(rr)
+    assert D.shard_buildings([], 2, 1) == []
+    with pytest.raises(ValueError):
+        D.shard_buildings(sizes, 2, 2)
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # ---- inference: each rank "processes" its shard; only the host-side gather communicates
+        sizes = [50, 10, 40, 30, 20, 60, 5]
+        mine = D.shard_buildings(sizes, world, rank)
+        local = {i: {"rows": sizes[i] * 2, "rank": rank} for i in mine}
+        merged = D.gather_results(local, dst=0)
+        if rank == 0:
+            assert sorted(merged) == list(range(len(sizes)))
+            assert all(merged[i]["rows"] == sizes[i] * 2 for i in merged)
+        else:
+            assert merged is None
+        # ---- training: gradient all-reduce; parameter 1 has no gradient on rank 1, parameter 2 on no rank
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.zeros(7, 3)), torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(2, 2)),
+              torch.nn.Parameter(torch.zeros(1000))]
+        ps[0].grad = torch.full((7, 3), float(rank + 1))
+        if rank == 0:
+            ps[1].grad = torch.arange(5, dtype=torch.float32)
+        ps[3].grad = torch.full((1000,), 2.0 * rank)
+        n = D.allreduce_gradients(ps, bucket_bytes=2048)  # forces several buckets
+        assert n >= 2
+        assert torch.allclose(ps[0].grad, torch.full((7, 3), (1 + 2) / 2.0))
+        assert torch.allclose(ps[1].grad, torch.arange(5, dtype=torch.float32) / 2.0)  # zeros from rank 1
+        assert ps[2].grad is not None and torch.count_nonzero(ps[2].grad) == 0
+        assert torch.allclose(ps[3].grad, torch.full((1000,), 1.0))
+        # ---- timing helper: max over ranks
+        assert D.max_over_ranks_ms(10.0 + rank, torch.device("cpu")) == 10.0 + world - 1
+        ret[rank] = "ok"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding_gather_and_gradient_allreduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        ret = mgr.dict()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, ret)) for r in range(world)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(120)
+        assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+        assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_single_process_paths_need_no_process_group():
+    assert D.gather_results({3: "x"}) == {3: "x"}
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.ones(3)
+    assert D.allreduce_gradients([p]) == 0 and torch.equal(p.grad, torch.ones(3))

@@ -24,6 +24,8 @@ x0 = torch.empty(0, device="cuda")
 scn.SCN.InputLayer_updateOutput(md, L([2048, 2048, 512]), coords, torch.zeros(coords.size(0), 1, device="cuda"), x0, 0, 4)
 n = md.getNActive(L([2048, 2048, 512]))
 x = torch.randn(n, a.c, device="cuda")
+if a.math == "bf16":  # as inside the network: the producer (BatchNorm / add kernel) has already written the bf16 copy
+    x._scn_bf16 = (x.to(torch.bfloat16), x._version)
 w = torch.randn(27, 1, a.c, a.c, device="cuda") * 0.02
 out = torch.empty(0, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
