@@ -35,9 +35,8 @@ namespace scn {
 
 constexpr int kTileM = 128;
 constexpr int kAtomBytes = kTileM * 128; // 128 rows x 128 B
-constexpr int kProdWarps = 8;
-constexpr int kThreads = 32 * (4 + kProdWarps + 2);
 constexpr int kMaxT = 4;
+constexpr int kEpiBytes = 4 * 32 * 32 * 4; // 4 epilogue warps x (32 rows x 32 floats), XOR-swizzled
 
 struct TcParams {
   const unsigned char *in; // activations, row-major, rowBytes per row (fp32 or bf16 elements)
@@ -50,7 +49,7 @@ struct TcParams {
   const int *tileW; // optional: weight slice per tile (deconvolution plans; then K == 1 and T == 1)
   long long *prof;  // developer: per-CTA stall counters (SCN_TC_PROF)
   int nOut, K, Cout, nTiles, T, nSuper, S, nAcc;
-  int rowBytes, nAtoms, bf16;
+  int rowBytes, nAtoms, bf16, tmemCols;
   int dbg;    // developer switches (SCN_TC_DBG): 1 = skip A gathers, 2 = skip B copies, 4 = skip MMAs
   int kSplit; // > 1: the filter offsets of a work item are split over kSplit CTAs, epilogue accumulates atomically
 };
@@ -177,16 +176,21 @@ __device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
 // Launch bound 576 (> the 448 threads used) caps the kernel at 112 registers per thread: a resident
 // CTA then leaves ~15K registers and ~17 KB of shared memory per SM, enough for the short
 // rulebook-build kernels of the other stream to run beside it instead of queueing behind it.
-template <bool BF16>
-__global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
+// PW = producer warps: 8 with one CTA per SM (all 512 TMEM columns), 4 with two CTAs per SM (256
+// columns and half the shared memory each): two independent pipelines per SM hide each other's
+// barrier hand-offs.
+template <bool BF16, int PW>
+__global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_plan_tc(const TcParams P) {
+  constexpr int kProdWarps = PW;
+  constexpr int kRowsPerWarp = kTileM / PW; // rows of a tile one producer warp gathers
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nWork = P.nSuper * P.kSplit;
   const uint32_t bBytes = (uint32_t)P.Cout * 128u;
   const uint32_t stageBytes = (uint32_t)P.T * kAtomBytes + bBytes; // [T A atoms][B atom]
   unsigned char *sStage = smem;
-  float *sEpi = reinterpret_cast<float *>(sStage + (size_t)P.S * stageBytes); // 4 warps x 32 rows x 36 floats
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + 4 * 32 * 36);
+  float *sEpi = reinterpret_cast<float *>(sStage + (size_t)P.S * stageBytes);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + kEpiBytes / 4);
   uint64_t *full = bars, *empty = bars + P.S, *accFull = bars + 2 * P.S, *accEmpty = accFull + 2;
   uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 2);
 
@@ -195,8 +199,9 @@ __global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
     for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"(512u) : "memory");
+  constexpr int kMmaWarp = 4 + PW, kLoadWarp = 5 + PW;
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"((uint32_t)P.tmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
     // ============================ epilogue ============================
     // warp w owns TMEM lanes 32w.. = rows 32w.. of every tile.  Per 32-column block: tcgen05.ld ->
     // padded shared-memory block -> each store instruction writes four whole 128-byte row segments.
-    float *stg = sEpi + warp * (32 * 36);
+    float *stg = sEpi + warp * (32 * 32);
     const int cc = (lane & 7) * 4, rsub = lane >> 3;
     int it = 0;
     for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
@@ -244,8 +249,8 @@ __global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
           }
           __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4 *>(stg + lane * 36 + j) =
+          for (int j = 0; j < 32; j += 4) // 16-byte chunk j/4 of row `lane` goes to chunk (j/4) ^ (lane & 7): conflict-free both ways
+            *reinterpret_cast<float4 *>(stg + lane * 32 + ((((j >> 2) ^ (lane & 7))) << 2)) =
                 make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
           __syncwarp();
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
           float4 o[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            o[i] = *reinterpret_cast<const float4 *>(stg + (i * 4 + rsub) * 36 + cc);
+            o[i] = *reinterpret_cast<const float4 *>(stg + (i * 4 + rsub) * 32 + (((lane & 7) ^ ((i * 4 + rsub) & 7)) << 2));
             o[i].x += bv.x; o[i].y += bv.y; o[i].z += bv.z; o[i].w += bv.w;
           }
           if (P.kSplit == 1) {
@@ -277,10 +282,10 @@ __global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
     if (prof && tid == 0) { P.prof[blockIdx.x * 32 + 0] = clock64() - tStart; P.prof[blockIdx.x * 32 + 1] = pw0; }
   } else if (warp < 4 + kProdWarps) {
     // ============================ A producers ============================
-    // Warp pw gathers rows [16 pw, 16 pw + 16) of every tile of the stage: 4 cp.async instructions
-    // per tile (8 lanes x 16 B = one 128-byte row chunk, 4 rows per instruction).  The ids of the
-    // current filter offset sit in registers (lanes 0-15 hold the warp's 16 rows of each tile) and
-    // those of the next active offset are fetched while the current one is gathered.
+    // Warp pw gathers rows [R pw, R pw + R) of every tile of the stage (R = 128 / PW): R / 4 cp.async
+    // instructions per tile (8 lanes x 16 B = one 128-byte row chunk, 4 rows per instruction).  The
+    // ids of the current filter offset sit in registers (lane l holds row R pw + l % R of each tile)
+    // and those of the next active offset are fetched while the current one is gathered.
     const int pw = warp - 4;
     const int chunk = lane & 7, rsub = lane >> 3;
     uint32_t n = 0, slot = 0, round = 0; // stage counter, ring slot, ring round
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
     for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
       const Item I = load_item(P, wi);
       if (!I.uni) continue;
-      const int *idBase = P.nbr + ((size_t)I.st * P.T * P.K) * 128 + pw * 16 + (lane & 15);
+      const int *idBase = P.nbr + ((size_t)I.st * P.T * P.K) * 128 + pw * kRowsPerWarp + (lane & (kRowsPerWarp - 1));
       int idc[kMaxT], idn[kMaxT];
       auto load_ids = [&](int k, int (&dst)[kMaxT]) {
 #pragma unroll
@@ -312,9 +317,9 @@ __global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
             for (int t = 0; t < kMaxT; t++) {
               if (!((I.m[t] >> k) & 1ull)) continue; // uniform over the CTA
 #pragma unroll
-              for (int i = 0; i < 4; i++) {
+              for (int i = 0; i < kRowsPerWarp / 4; i++) {
                 const int id = __shfl_sync(0xffffffffu, idc[t], i * 4 + rsub);
-                const int row = pw * 16 + i * 4 + rsub;
+                const int row = pw * kRowsPerWarp + i * 4 + rsub;
                 const unsigned char *src = P.in + (size_t)(id >= 0 ? id : 0) * P.rowBytes + c * 128 + chunk * 16;
                 cp_async16(sbase + t * kAtomBytes + row * 128 + ((chunk ^ (row & 7)) << 4), src, id >= 0 ? 16u : 0u);
               }
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
       if (lane == 0) mbar_arrive(smem_u32(full + pendSlot));
     }
     if (prof && lane == 0 && pw == 0) { long long *q = P.prof + blockIdx.x * 32 + 4; q[0] = clock64() - tStart; q[1] = pw0; q[2] = pw1; q[3] = n; }
-  } else if (warp == 12) {
+  } else if (warp == kMmaWarp) {
     // ============================ MMA issuer ============================
     // The whole warp runs the control flow (converged), one elected lane issues: ptxas then keeps
     // descriptors in uniform registers and emits straight-line UTCHMMA instead of a per-instruction
@@ -440,9 +445,9 @@ __global__ void __launch_bounds__(576, 1) conv_plan_tc(const TcParams P) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"((uint32_t)P.tmemCols) : "memory");
   }
 }
 
@@ -570,8 +575,9 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     return r;
   }
   SCN_CHECK(Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && K <= 64, "tcgen05 path: unsupported channel counts");
-  static int envT = -1, envS = -1, envDbg = 0, envProf = 0;
+  static int envT = -1, envS = -1, envDbg = 0, envProf = 0, envCtas = 0;
   if (envT < 0) {
+    envCtas = getenv("SCN_TC_CTAS") ? atoi(getenv("SCN_TC_CTAS")) : 0;
     envT = getenv("SCN_TC_T") ? atoi(getenv("SCN_TC_T")) : 0;
     envS = getenv("SCN_TC_S") ? atoi(getenv("SCN_TC_S")) : 0;
     envDbg = getenv("SCN_TC_DBG") ? atoi(getenv("SCN_TC_DBG")) : 0;
@@ -597,21 +603,27 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   // Tiles per work item: as many as TMEM holds (T x Cout <= 512 columns) so that a weight atom is
   // fetched once per T tiles, but never so many that fewer than ~2 items per SM remain; small levels
   // use 1-tile items and split the filter offsets over CTAs so the whole chip works on them.
-  const int Tcap = std::min(kMaxT, 512 / Cout);
-  const size_t fixed = 4 * 32 * 36 * 4 + 64 * 8 + 64;
-  auto ring = [&](int t) { return (int)((227 * 1024 - fixed) / ((size_t)t * kAtomBytes + (size_t)Cout * 128)); };
+  // two CTAs per SM (each with 256 TMEM columns and half the shared memory) unless the layer is too wide for that
+  int ctas = envCtas ? envCtas : 2;
+  if (Cout > 128) ctas = 1;
+  P.tmemCols = ctas == 2 ? 256 : 512;
+  const size_t smemBudget = ctas == 2 ? (233472 / 2 - 1024) : 227 * 1024;
+  const int Tcap = std::min(kMaxT, P.tmemCols / Cout);
+  const size_t fixed = kEpiBytes + 64 * 8 + 64;
+  auto ring = [&](int t) { return (int)((smemBudget - fixed) / ((size_t)t * kAtomBytes + (size_t)Cout * 128)); };
   int T = Tcap;
-  while (T > 2 && ring(T) < 3) T--; // a 2-slot ring exposes the gather latency (measured: T=3/S=3 beats T=4/S=2 by 12 %)
-  while (T > 1 && cdiv(P.nTiles, T) < 2 * kSMs) T--;
+  if (ctas == 1) while (T > 2 && ring(T) < 3) T--; // a 2-slot ring exposes the gather latency (measured: T=3/S=3 beats T=4/S=2 by 12 %)
+  while (T > 1 && ring(T) < 2) T--;
+  while (T > 1 && cdiv(P.nTiles, T) < 2 * kSMs * ctas) T--;
   if (tileW) T = 1;
   if (envT > 0 && envT <= Tcap && !tileW) T = envT;
   P.T = T;
-  P.nAcc = 2 * T * Cout <= 512 ? 2 : 1;
+  P.nAcc = 2 * T * Cout <= P.tmemCols ? 2 : 1;
   P.nSuper = cdiv(P.nTiles, P.T);
   P.kSplit = 1;
-  if (P.nSuper < kSMs / 2 && !tileW) P.kSplit = std::max(1, std::min(K, kSMs / P.nSuper));
+  if (P.nSuper < kSMs * ctas / 2 && !tileW) P.kSplit = std::max(1, std::min(K, kSMs * ctas / P.nSuper));
   const size_t stageBytes = (size_t)P.T * kAtomBytes + (size_t)Cout * 128;
-  P.S = (int)std::min<size_t>(envS > 0 ? envS : 6, (227 * 1024 - fixed) / stageBytes);
+  P.S = (int)std::min<size_t>(envS > 0 ? envS : 6, (smemBudget - fixed) / stageBytes);
   SCN_CHECK(P.S >= 2, "tcgen05 path: shared memory budget exceeded");
   const size_t smem = (size_t)P.S * stageBytes + fixed;
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
@@ -621,27 +633,34 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   P.wimg = wimg;
   static bool attr = false;
   if (!attr) {
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
     attr = true;
   }
-  const int grid = std::min(P.nSuper * P.kSplit, kSMs);
+  const int grid = std::min(P.nSuper * P.kSplit, kSMs * ctas);
   P.prof = nullptr;
   if (envProf) {
-    SCN_CUDA(cudaMallocAsync((void **)&P.prof, kSMs * 32 * 8, s));
-    SCN_CUDA(cudaMemsetAsync(P.prof, 0, kSMs * 32 * 8, s));
+    SCN_CUDA(cudaMallocAsync((void **)&P.prof, 2 * kSMs * 32 * 8, s));
+    SCN_CUDA(cudaMemsetAsync(P.prof, 0, 2 * kSMs * 32 * 8, s));
   }
-  if (P.bf16) conv_plan_tc<true><<<grid, kThreads, smem, LS(s)>>>(P);
-  else conv_plan_tc<false><<<grid, kThreads, smem, LS(s)>>>(P);
+  if (ctas == 2) {
+    if (P.bf16) conv_plan_tc<true, 4><<<grid, 32 * 10, smem, LS(s)>>>(P);
+    else conv_plan_tc<false, 4><<<grid, 32 * 10, smem, LS(s)>>>(P);
+  } else {
+    if (P.bf16) conv_plan_tc<true, 8><<<grid, 32 * 14, smem, LS(s)>>>(P);
+    else conv_plan_tc<false, 8><<<grid, 32 * 14, smem, LS(s)>>>(P);
+  }
   SCN_CUDA(cudaGetLastError());
   if (envProf) { // developer aid: mean stall cycles per role over the CTAs of this launch
-    static long long h[kSMs * 32];
+    static long long h[2 * kSMs * 32];
     SCN_CUDA(cudaMemcpyAsync(h, P.prof, sizeof h, cudaMemcpyDeviceToHost, s));
     SCN_CUDA(cudaStreamSynchronize(s));
     double m[32] = {0};
     for (int b = 0; b < grid; b++) for (int i = 0; i < 32; i++) m[i] += (double)h[b * 32 + i] / grid;
-    fprintf(stderr, "[tcprof] grid=%d T=%d K=%d Cin=%d Cout=%d S=%d nAcc=%d kSplit=%d | epi total %.0f waitAcc %.0f | prod total %.0f empty %.0f cpwait %.0f stages %.0f | mma total %.0f accEmpty %.0f full %.0f stages %.0f issue %.0f commit %.0f | bld total %.0f empty %.0f\n",
-            grid, P.T, K, Cin, Cout, P.S, P.nAcc, P.kSplit, m[0], m[1], m[4], m[5], m[6], m[7], m[10], m[11], m[12], m[13], m[14], m[15], m[16], m[17]);
+    fprintf(stderr, "[tcprof] ctas=%d grid=%d T=%d K=%d Cin=%d Cout=%d S=%d nAcc=%d kSplit=%d | epi total %.0f waitAcc %.0f | prod total %.0f empty %.0f cpwait %.0f stages %.0f | mma total %.0f accEmpty %.0f full %.0f stages %.0f issue %.0f commit %.0f | bld total %.0f empty %.0f\n",
+            ctas, grid, P.T, K, Cin, Cout, P.S, P.nAcc, P.kSplit, m[0], m[1], m[4], m[5], m[6], m[7], m[10], m[11], m[12], m[13], m[14], m[15], m[16], m[17]);
     cudaFreeAsync(P.prof, s);
   }
   if (wimgOwned) cudaFreeAsync(wimg, s);
