@@ -22,6 +22,13 @@ SYMBOLS = {
     "scn_metadata_create": (_i, [C.POINTER(_vp), _vp]),
     "scn_metadata_destroy": (None, [_vp]),
     "scn_metadata_prefetch": (_i, [_vp, _i, _vp]),
+    "scn_program_create": (_i, [C.POINTER(_vp)]),
+    "scn_program_destroy": (None, [_vp]),
+    "scn_program_add": (_i, [_vp, _i, _vp, _i, _vp, _i]),
+    "scn_program_finish": (_i, [_vp, _i, _vp, _i]),
+    "scn_program_run": (_i, [_vp, _vp, _vp, _i, _l, _i, _vp, _vp, _vp, _i, _vp, _pd]),
+    "scn_program_output": (_i, [_vp, _i, C.POINTER(_l), C.POINTER(_i), C.POINTER(_vp)]),
+    "scn_copy_device": (_i, [_vp, _vp, _l, _vp]),
     "scn_input_layer_build": (_i, [_vp, L3, _vp, _i, _l, _i, _i, _i, _pl, _pi]),
     "scn_input_layer_forward": (_i, [_vp, _vp, _vp, _i]),
     "scn_input_layer_backward": (_i, [_vp, _vp, _vp, _i]),

@@ -1,0 +1,211 @@
+// Recorded layer programs: the sequence of native calls one forward of a network makes, replayed by
+// ONE C-ABI call.  The reference drives every layer from Python (sparseconvnet/*.py -> one pybind
+// call per layer); on B200 the ~100 layer calls of the Detection_3D backbone cost more host time
+// (Python + ctypes, ~60 us each) than the GPU needs for the small pyramid levels.  A program is
+// nothing but the same calls of include/scn_b200.h issued from C++: same kernels, same order,
+// same results; feature tensors live in registers whose buffers the executor allocates on the
+// caller's stream and frees after their last use.
+#include "../../include/scn_b200.h"
+#include "common.cuh"
+#include <vector>
+
+namespace {
+
+enum Kind { K_INPUT = 0, K_SUBM = 1, K_CONV = 2, K_DECONV = 3, K_BN = 4, K_ADD = 5 };
+struct Op {
+  int kind;
+  long a[24];
+  double f[4];
+};
+struct Reg {
+  float *p = nullptr;
+  void *p16 = nullptr; // bfloat16 copy (math mode 2, written by BatchNorm / add)
+  long rows = 0;
+  int cols = 0;
+};
+
+} // namespace
+
+struct scn_program {
+  std::vector<Op> ops;
+  int nRegs = 0;
+  std::vector<int> lastUse;     // op index after which a register's buffers can be freed
+  std::vector<char> isOutput;
+  std::vector<Reg> regs;
+  float *bnScratch = nullptr;   // saveMean / saveInvStd of inference-mode BatchNorm (unused downstream)
+  cudaStream_t stream = nullptr;
+};
+
+static void release_regs(scn_program *p, bool outputsToo) {
+  for (size_t i = 0; i < p->regs.size(); i++) {
+    Reg &r = p->regs[i];
+    if (!outputsToo && p->isOutput[i]) continue;
+    if (r.p) cudaFreeAsync(r.p, p->stream);
+    if (r.p16) cudaFreeAsync(r.p16, p->stream);
+    r.p = nullptr;
+    r.p16 = nullptr;
+  }
+}
+
+extern "C" {
+
+int scn_program_create(scn_program **out) {
+  *out = new scn_program();
+  return 0;
+}
+void scn_program_destroy(scn_program *p) {
+  if (!p) return;
+  release_regs(p, true);
+  if (p->bnScratch) cudaFree(p->bnScratch);
+  delete p;
+}
+int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, const double *fargs, int n_fargs) {
+  SCN_CHECK(p && kind >= K_INPUT && kind <= K_ADD && n_iargs <= 24 && n_fargs <= 4, "bad program op");
+  Op op;
+  op.kind = kind;
+  for (int i = 0; i < 24; i++) op.a[i] = i < n_iargs ? iargs[i] : 0;
+  for (int i = 0; i < 4; i++) op.f[i] = i < n_fargs ? fargs[i] : 0.0;
+  p->ops.push_back(op);
+  return 0;
+}
+int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_outputs) {
+  SCN_CHECK(p && n_regs > 0, "bad program");
+  p->nRegs = n_regs;
+  p->lastUse.assign(n_regs, -1);
+  p->isOutput.assign(n_regs, 0);
+  p->regs.assign(n_regs, Reg());
+  auto use = [&](long r, int i) -> int {
+    SCN_CHECK(r >= 0 && r < n_regs, "register index");
+    p->lastUse[r] = i;
+    return 0;
+  };
+  for (int i = 0; i < (int)p->ops.size(); i++) {
+    const Op &op = p->ops[i];
+    switch (op.kind) {
+      case K_INPUT: SCN_TRY(use(op.a[0], i)); break;
+      case K_ADD: SCN_TRY(use(op.a[0], i)); SCN_TRY(use(op.a[1], i)); SCN_TRY(use(op.a[2], i)); break;
+      default: SCN_TRY(use(op.a[0], i)); SCN_TRY(use(op.a[1], i)); break;
+    }
+  }
+  for (int i = 0; i < n_outputs; i++) {
+    SCN_CHECK(outputs[i] >= 0 && outputs[i] < n_regs, "output register");
+    p->isOutput[outputs[i]] = 1;
+  }
+  return 0;
+}
+
+// params[i] / tags[i]: device pointers of the recorded parameter tensors (and their content tags, see
+// weight_tag in scn_*_convolution_forward), in the order the recorder numbered them.
+int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coords_on_device, long nrows, int ncols, const float *feats,
+                    const void *const *params, const long long *tags, int n_params, void *stream, double *macs_out) {
+  SCN_CHECK(p && m && p->nRegs > 0, "program not finished");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  release_regs(p, true); // outputs of the previous run
+  p->stream = s;
+  const int mode = scn_get_math_mode();
+  if (!p->bnScratch) SCN_CUDA(cudaMalloc((void **)&p->bnScratch, 2 * scn::kBnMaxC * sizeof(float)));
+  auto P = [&](long i) -> const float * { return (i < 0 || i >= n_params) ? nullptr : static_cast<const float *>(params[i]); };
+  auto T = [&](long i) -> long long { return (i < 0 || i >= n_params || !tags) ? 0 : tags[i]; };
+  auto alloc_reg = [&](long r, long rows, int cols, bool shadow) -> int {
+    Reg &R = p->regs[r];
+    R.rows = rows;
+    R.cols = cols;
+    SCN_CUDA(cudaMallocAsync((void **)&R.p, (size_t)std::max(1l, rows * cols) * 4, s));
+    if (shadow && mode == 2 && cols % 64 == 0 && rows > 0) SCN_CUDA(cudaMallocAsync(&R.p16, (size_t)rows * cols * 2, s));
+    return 0;
+  };
+  double macs = 0, mk = 0;
+  int rc = 0;
+  for (int i = 0; i < (int)p->ops.size() && rc == 0; i++) {
+    const Op &op = p->ops[i];
+    const long *a = op.a;
+    switch (op.kind) {
+      case K_INPUT: { // out, size[3], mode, batch hint, planes
+        long nActive = 0;
+        int maxActive = 0;
+        rc = scn_input_layer_build(m, a + 1, coords, coords_on_device, nrows, ncols, (int)a[5], (int)a[4], &nActive, &maxActive);
+        if (rc) break;
+        { // the rulebooks this program is about to request, built ahead on the worker thread
+          std::vector<long> hints;
+          for (const Op &o : p->ops) {
+            long h[13] = {0};
+            if (o.kind == K_SUBM) { h[0] = 1; for (int d = 0; d < 3; d++) { h[1 + d] = o.a[2 + d]; h[7 + d] = o.a[5 + d]; } }
+            else if (o.kind == K_CONV || o.kind == K_DECONV) { h[0] = o.kind == K_CONV ? 2 : 3; for (int d = 0; d < 12; d++) h[1 + d] = o.a[2 + d]; }
+            else continue;
+            hints.insert(hints.end(), h, h + 13);
+          }
+          if (!hints.empty()) rc = scn_metadata_prefetch(m, (int)(hints.size() / 13), hints.data());
+          if (rc) break;
+        }
+        rc = alloc_reg(a[0], nActive, (int)a[6], false);
+        if (rc == 0 && nActive) rc = scn_input_layer_forward(m, feats, p->regs[a[0]].p, (int)a[6]);
+        break;
+      }
+      case K_SUBM: { // in, out, size[3], filter[3], w, bias, Cin, Cout
+        long n = 0;
+        rc = scn_get_nactive(m, a + 2, &n);
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], false);
+        const Reg &I = p->regs[a[0]];
+        if (rc == 0) rc = scn_submanifold_convolution_forward(m, a + 2, a + 5, I.p, p->regs[a[1]].p, P(a[8]), P(a[9]), (int)a[10], (int)a[11], &mk, I.p16, T(a[8]));
+        macs += mk;
+        break;
+      }
+      case K_CONV: { // in, out, inS[3], outS[3], f[3], s[3], w, bias, Cin, Cout
+        long n = 0, nr = 0;
+        rc = scn_convolution_prepare(m, a + 2, a + 5, a + 8, a + 11, &n, &nr);
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], false);
+        const Reg &I = p->regs[a[0]];
+        if (rc == 0) rc = scn_convolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]));
+        macs += mk;
+        break;
+      }
+      case K_DECONV: {
+        long n = 0;
+        rc = scn_get_nactive(m, a + 5, &n);
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], false);
+        const Reg &I = p->regs[a[0]];
+        if (rc == 0) rc = scn_deconvolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]));
+        macs += mk;
+        break;
+      }
+      case K_BN: { // in, out, C, weight, bias, running mean, running var, mode; f: eps, momentum, leakiness
+        const Reg &I = p->regs[a[0]];
+        rc = alloc_reg(a[1], I.rows, (int)a[2], true);
+        if (rc == 0)
+          rc = scn_batchnorm_forward(I.p, p->regs[a[1]].p, I.rows, (int)a[2], p->bnScratch, p->bnScratch + scn::kBnMaxC, const_cast<float *>(P(a[5])),
+                                     const_cast<float *>(P(a[6])), P(a[3]), P(a[4]), (float)op.f[0], (float)op.f[1], (int)a[7], (float)op.f[2], s, p->regs[a[1]].p16);
+        break;
+      }
+      case K_ADD: { // a, b, out
+        const Reg &A = p->regs[a[0]], &B = p->regs[a[1]];
+        if (A.rows != B.rows || A.cols != B.cols) { scn::set_error("program: add of differently shaped feature matrices"); rc = -2; break; }
+        rc = alloc_reg(a[2], A.rows, A.cols, true);
+        if (rc == 0 && A.rows) rc = scn_add_features(A.p, B.p, p->regs[a[2]].p, A.rows * A.cols, s, p->regs[a[2]].p16);
+        break;
+      }
+    }
+    if (rc) break;
+    for (int r = 0; r < p->nRegs; r++) // free what this op used last (stream-ordered: safe right after the launch)
+      if (p->lastUse[r] == i && !p->isOutput[r]) {
+        Reg &R = p->regs[r];
+        if (R.p) { cudaFreeAsync(R.p, s); R.p = nullptr; }
+        if (R.p16) { cudaFreeAsync(R.p16, s); R.p16 = nullptr; }
+      }
+  }
+  if (rc) { release_regs(p, true); return rc; }
+  if (macs_out) *macs_out = macs;
+  return 0;
+}
+
+int scn_copy_device(void *dst, const void *src, long bytes, void *stream) {
+  if (bytes > 0) SCN_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const float **ptr) {
+  SCN_CHECK(p && reg >= 0 && reg < p->nRegs && p->isOutput[reg], "not an output register");
+  *rows = p->regs[reg].rows;
+  *cols = p->regs[reg].cols;
+  *ptr = p->regs[reg].p;
+  return 0;
+}
+}

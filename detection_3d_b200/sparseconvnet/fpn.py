@@ -10,8 +10,14 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+import os
+
 from . import layers as L
+from . import native, program
 from .containers import AddTable, ConcatTable, Identity, Sequential, add_feature_planes
+from .tensor import SparseConvNetTensor
+
+_PROGRAMS = os.environ.get("SCN_PROGRAM", "1") != "0"  # developer switch: always run layer by layer
 
 
 class OutputLayer(nn.Module):
@@ -101,8 +107,45 @@ class FPN_Net(nn.Module):
             self.m_mergeds.append(L.SubmanifoldConvolution(dimension, nPlaneM, nPlaneM, 3, False))
 
     def forward(self, net0):
-        """net0 = [coords LongTensor [N,4], features float [N,C]] -> (rpn_maps, roi_maps)."""
+        """net0 = [coords LongTensor [N,4], features float [N,C]] -> (rpn_maps, roi_maps).
+
+        Inference (eval mode, no autograd graph) runs as a recorded program after the first call: the
+        first forward is executed layer by layer while `program.Trace` records the native calls, later
+        forwards replay them with one native call (same kernels, same order).  Training, a changed math
+        mode, unusual inputs or SCN_PROGRAM=0 use the layer-by-layer path."""
+        if _PROGRAMS and not self.training and not torch.is_grad_enabled() and len(net0) == 2:
+            coords, feats = net0[0], net0[1]
+            dev = self.layers_in[0].device
+            if dev is not None and isinstance(feats, torch.Tensor):
+                feats = feats.to(dev)
+            mode = native.math_mode()
+            prog = self.__dict__.get("_program")
+            if prog is not None and isinstance(coords, torch.Tensor) and prog.usable(coords, feats, mode):
+                return self._run_program(prog, coords, feats)
+            if prog is None and self.__dict__.get("_program_error") is None and isinstance(feats, torch.Tensor) and feats.is_cuda:
+                with program.Trace() as tr:
+                    rpn_maps, roi_maps = self.forward_fpn(self.layers_in(net0))
+                try:
+                    self.__dict__["_program"] = program.Program(tr, [(m.features, m.spatial_size) for m in rpn_maps + roi_maps], mode)
+                    self.__dict__["_program_n_rpn"] = len(rpn_maps)
+                except Exception as e:  # the layer-by-layer path stays in charge
+                    self.__dict__["_program_error"] = str(e)
+                return rpn_maps, roi_maps
         return self.forward_fpn(self.layers_in(net0))
+
+    def reset_program(self):
+        """Forget the recorded program (call after changing the module tree)."""
+        self.__dict__.pop("_program", None)
+        self.__dict__.pop("_program_error", None)
+
+    def _run_program(self, prog, coords, feats):
+        import detection_3d_b200.sparseconvnet as pkg
+        md = L.Metadata(self.dimension)
+        outs, macs = prog.run(md, coords, feats)
+        pkg.forward_pass_multiplyAdd_count += macs
+        maps = [SparseConvNetTensor(features=f, metadata=md, spatial_size=s.clone()) for f, s in zip(outs, prog.out_sizes)]
+        n = self.__dict__["_program_n_rpn"]
+        return maps[:n], maps[n:]
 
     def forward_fpn(self, net):
         n_scales = len(self.m_downs)

@@ -7,6 +7,21 @@ import ctypes as C
 import torch
 
 from .._lib import check, l3, lib
+from . import program as _program
+
+
+def _tr():
+    """the recording in progress, if any (sparseconvnet/program.py)"""
+    t = _program.active()
+    return t if t is not None and t.failed is None else None
+
+
+def _ints(t):
+    return [int(v) for v in (t.tolist() if hasattr(t, "tolist") else t)]
+
+
+def copy_device_to_tensor(t, src_ptr):
+    check(lib().scn_copy_device(C.c_void_p(t.data_ptr()), C.c_void_p(src_ptr), t.numel() * t.element_size(), _stream()))
 
 
 def _stream():
@@ -170,6 +185,11 @@ def InputLayer_updateOutput(m, spatial_size, coords, input_features, output_feat
     output_features.resize_(n_active.value, planes)
     if n_active.value:
         check(lib().scn_input_layer_forward(m._h, _dev_f32(input_features, "InputLayer features"), _dev_f32(output_features, "out"), planes))
+    tr = _tr()
+    if tr is not None:
+        if tr.ops:
+            tr.fail("more than one InputLayer in a recording")
+        tr.add(0, [tr.new_reg(output_features)] + _ints(spatial_size) + [int(mode), int(batch_size), planes])
 
 
 def InputLayer_updateGradInput(m, d_input_features, d_output_features):
@@ -199,6 +219,10 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
     check(lib().scn_submanifold_convolution_forward(m._h, l3(spatial_size), l3(filter_size), _dev_f32(input_features, "in"),
                                                     _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"),
                                                     cin, cout, C.byref(macs), _shadow_ptr(input_features), _weight_tag(weight)))
+    tr = _tr()
+    if tr is not None:
+        tr.add(1, [tr.reg(input_features), tr.new_reg(output_features)] + _ints(spatial_size) + _ints(filter_size)
+               + [tr.param(weight), tr.param(bias), cin, cout])
     return macs.value
 
 
@@ -222,6 +246,10 @@ def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, i
     check(lib().scn_convolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
                                         _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs),
                                         _shadow_ptr(input_features), _weight_tag(weight)))
+    tr = _tr()
+    if tr is not None:
+        tr.add(2, [tr.reg(input_features), tr.new_reg(output_features)] + _ints(in_size) + _ints(out_size) + _ints(filter_size)
+               + _ints(filter_stride) + [tr.param(weight), tr.param(bias), cin, cout])
     return macs.value
 
 
@@ -244,6 +272,10 @@ def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m,
     check(lib().scn_deconvolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
                                           _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs),
                                           _shadow_ptr(input_features), _weight_tag(weight)))
+    tr = _tr()
+    if tr is not None:
+        tr.add(3, [tr.reg(input_features), tr.new_reg(output_features)] + _ints(in_size) + _ints(out_size) + _ints(filter_size)
+               + _ints(filter_stride) + [tr.param(weight), tr.param(bias), cin, cout])
     return macs.value
 
 
@@ -273,6 +305,12 @@ def BatchNormalization_updateOutput(input_features, output_features, saveMean, s
                                       _opt(weight, "weight"), _opt(bias, "bias"), float(eps), float(momentum), mode, float(leakiness), _stream(),
                                       None if sh is None else C.c_void_p(sh.data_ptr())))
     _attach_shadow(output_features, sh)
+    tr = _tr()
+    if tr is not None:
+        if train:
+            tr.fail("training-mode BatchNorm is not recorded")
+        tr.add(4, [tr.reg(input_features), tr.new_reg(output_features), c, tr.param(weight), tr.param(bias), tr.param(runningMean),
+                   tr.param(runningVar), mode], [eps, momentum, leakiness])
 
 
 def BatchNormalization_backward(input_features, d_input_features, output_features, d_output_features, saveMean, saveInvStd, runningMean,
@@ -293,6 +331,11 @@ def add_features(a, b):
         check(lib().scn_add_features(_dev_f32(a, "a"), _dev_f32(b, "b"), _dev_f32(out, "out"), a.numel(), _stream(),
                                      None if sh is None else C.c_void_p(sh.data_ptr())))
         _attach_shadow(out, sh)
+    tr = _tr()
+    if tr is not None:
+        if a.numel() == 0:
+            tr.fail("empty add")
+        tr.add(5, [tr.reg(a), tr.reg(b), tr.new_reg(out)])
     return out
 
 
@@ -301,6 +344,10 @@ def set_math_mode(mode):
     code = {"fp32": 0, "tf32": 1, "bf16": 2}[mode] if isinstance(mode, str) else int(mode)
     check(lib().scn_set_math_mode(code))
     _MATH["mode"] = lib().scn_get_math_mode()
+
+
+def math_mode():
+    return _MATH["mode"]
 
 
 def kernel_launch_count():

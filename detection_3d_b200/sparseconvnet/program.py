@@ -1,0 +1,139 @@
+"""Recorded layer programs (include/scn_b200.h, "recorded layer programs").
+
+A forward of the backbone makes ~100 calls into the native library, one per layer, exactly as the
+reference makes one pybind call per layer.  `Trace` records those calls while an ordinary forward
+runs (every feature tensor becomes a register, every parameter an index); `Program` replays them
+with ONE native call.  Same kernels, same order, same results -- only the Python round trips are
+gone.  Anything the recorder does not understand (a feature tensor produced by a torch op, an
+unknown layer) aborts the recording and the network keeps running layer by layer.
+"""
+import ctypes as C
+
+import torch
+
+from .._lib import check, l3, lib
+
+_ACTIVE = None  # the Trace that is currently recording (set by Trace.__enter__)
+
+
+def active():
+    return _ACTIVE
+
+
+class Trace(object):
+    def __init__(self):
+        self.ops = []          # (kind, [ints], [floats])
+        self.regs = {}         # id(tensor) -> register
+        self.params = []       # parameter / buffer tensors, index = position
+        self.pindex = {}
+        self.keep = []         # keeps every recorded tensor alive so ids stay unique while recording
+        self.failed = None
+        self.input_features = None
+
+    def __enter__(self):
+        global _ACTIVE
+        self._prev, _ACTIVE = _ACTIVE, self
+        return self
+
+    def __exit__(self, *exc):
+        global _ACTIVE
+        _ACTIVE = self._prev
+        return False
+
+    # ---- helpers used by native.py
+    def fail(self, why):
+        if self.failed is None:
+            self.failed = why
+
+    def new_reg(self, t):
+        self.keep.append(t)
+        r = self.regs[id(t)] = len(self.regs)
+        return r
+
+    def reg(self, t):
+        r = self.regs.get(id(t))
+        if r is None:
+            self.fail("a feature tensor was not produced by a recorded layer")
+            return -1
+        return r
+
+    def param(self, t):
+        if t is None or t.numel() == 0:
+            return -1
+        i = self.pindex.get(id(t))
+        if i is None:
+            i = self.pindex[id(t)] = len(self.params)
+            self.params.append(t)
+        return i
+
+    def add(self, kind, ints, floats=()):
+        self.ops.append((kind, [int(v) for v in ints], [float(v) for v in floats]))
+
+
+def _l(t):
+    return [int(v) for v in (t.tolist() if hasattr(t, "tolist") else t)]
+
+
+class Program(object):
+    """A finished recording bound to the native executor."""
+
+    def __init__(self, trace, outputs, math_mode):
+        """outputs: list of (feature tensor, spatial_size LongTensor) in the order the network returns them."""
+        if trace.failed:
+            raise RuntimeError(trace.failed)
+        self.math_mode = math_mode
+        self.params = trace.params
+        self.out_regs, self.out_sizes = [], []
+        for feats, size in outputs:
+            r = trace.regs.get(id(feats))
+            if r is None:
+                raise RuntimeError("an output was not produced by a recorded layer")
+            self.out_regs.append(r)
+            self.out_sizes.append(size.clone())
+        self._h = C.c_void_p()
+        check(lib().scn_program_create(C.byref(self._h)))
+        for kind, ints, floats in trace.ops:
+            ia = (C.c_long * len(ints))(*ints)
+            fa = (C.c_double * max(1, len(floats)))(*floats) if floats else None
+            check(lib().scn_program_add(self._h, kind, ia, len(ints), fa, len(floats)))
+        uniq = sorted(set(self.out_regs))
+        check(lib().scn_program_finish(self._h, len(trace.regs), (C.c_int * len(uniq))(*uniq), len(uniq)))
+        self.n_ops = len(trace.ops)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                lib().scn_program_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def usable(self, coords, feats, math_mode):
+        return (math_mode == self.math_mode and isinstance(feats, torch.Tensor) and feats.is_cuda and feats.dtype == torch.float32
+                and feats.dim() == 2 and coords.dtype == torch.int64 and coords.dim() == 2)
+
+    def run(self, metadata, coords, feats):
+        """-> (list of output feature tensors, multiply-add count)."""
+        from . import native
+        coords = coords.contiguous()
+        feats = feats.contiguous()
+        metadata._keep.append(coords)
+        n = len(self.params)
+        ptrs = (C.c_void_p * n)(*[p.data_ptr() for p in self.params])
+        tags = (C.c_longlong * n)(*[native._weight_tag(p) if p.dim() >= 3 else 0 for p in self.params])
+        macs = C.c_double()
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(lib().scn_program_run(self._h, metadata._h, C.c_void_p(coords.data_ptr()), int(coords.is_cuda), coords.size(0), coords.size(1),
+                                    C.c_void_p(feats.data_ptr()), ptrs, tags, n, stream, C.byref(macs)))
+        outs, cache = [], {}
+        for r in self.out_regs:
+            if r not in cache:
+                rows, cols, ptr = C.c_long(), C.c_int(), C.c_void_p()
+                check(lib().scn_program_output(self._h, r, C.byref(rows), C.byref(cols), C.byref(ptr)))
+                t = torch.empty((rows.value, cols.value), dtype=torch.float32, device=feats.device)
+                if t.numel():
+                    native.copy_device_to_tensor(t, ptr.value)
+                cache[r] = t
+            outs.append(cache[r])
+        return outs, macs.value

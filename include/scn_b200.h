@@ -132,6 +132,31 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, float
 /* AddTable / add_feature_planes (sparseconvnet/tables.py:28-41, utils.py:61-66): out = a + b */
 int scn_add_features(const float *a, const float *b, float *out, long n_elements, void *stream, void *out_bf16);
 
+/* ---- recorded layer programs (no reference counterpart: the reference drives every layer from Python,
+ * one pybind call per layer).  A program is the list of the calls above that one forward of a network
+ * makes, recorded once by the host layer and replayed by ONE call: same kernels, same order, same
+ * results, without ~100 Python round trips per forward.  Feature tensors are registers (0..n_regs-1);
+ * their buffers are allocated on `stream` and freed after their last use, output registers stay valid
+ * until the next run / destroy.  Op kinds and integer arguments:
+ *   0 INPUT  : out, size[3], mode, batch_size, n_planes                      (scn_input_layer_build + _forward)
+ *   1 SUBM   : in, out, size[3], filter[3], w, bias, n_in, n_out             (scn_submanifold_convolution_forward)
+ *   2 CONV   : in, out, in_size[3], out_size[3], filter[3], stride[3], w, bias, n_in, n_out
+ *   3 DECONV : same argument layout as CONV                                   (scn_deconvolution_forward)
+ *   4 BN     : in, out, n_planes, weight, bias, running_mean, running_var, mode;  fargs eps, momentum, leakiness
+ *   5 ADD    : a, b, out                                                      (scn_add_features)
+ * w / bias / ... are indices into the params[] array given to scn_program_run (-1 = none). */
+typedef struct scn_program scn_program;
+int scn_program_create(scn_program **out);
+void scn_program_destroy(scn_program *p);
+int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, const double *fargs, int n_fargs);
+int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_outputs);
+int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coords_on_device, long nrows, int ncols,
+                    const float *features, const void *const *params, const long long *weight_tags, int n_params,
+                    void *stream, double *macs);
+int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const float **ptr);
+/* device-to-device copy on `stream` (hands an output register to a caller-owned tensor) */
+int scn_copy_device(void *dst, const void *src, long bytes, void *stream);
+
 /* Selects the arithmetic of the gather-GEMM kernels for this process: 0 = fp32 CUDA cores
  * (exact-fp32 anchor), 1 = tcgen05 tensor cores, TF32 inputs / fp32 accumulate (default where the
  * channel counts allow), 2 = tcgen05 BF16 inputs / fp32 accumulate. */

@@ -516,3 +516,52 @@ def test_fpn_forward_tensor_core_vs_reference_golden(name, cfgname, bld, math):
             got = m.features.cpu().numpy()
             err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
             assert err < TC_E2E[math], (tag, i, float(err))
+
+
+# ------------------------------------------------------------------ recorded program (one native call per forward)
+@pytest.mark.parametrize("math", ["fp32", "bf16"])
+def test_recorded_program_matches_layer_by_layer(math):
+    """The second and later inference forwards replay the native calls the first one made
+    (sparseconvnet/program.py).  Same kernels in the same order: results must agree with the
+    layer-by-layer forward to rounding of the atomically accumulated small levels, the row numbering
+    exactly, and the multiply-add counter exactly -- also for a DIFFERENT building than the recorded one."""
+    import detection_3d_b200.sparseconvnet as scn
+    if math != "fp32":
+        _tc_or_skip(scn)
+    cfg = fpn_util.mini4_config()
+    try:
+        scn.set_math_mode(math)
+        net = scn.FPN_Net(**cfg)
+        net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+        net = net.cuda().eval()
+        blds = [dict(nx=60, ny=56, nz=24, n_walls=3, seed=3), dict(nx=44, ny=40, nz=20, n_walls=3, seed=9)]
+        inputs = []
+        for b in blds:
+            c = synthetic.building_coords(**b)
+            inputs.append((torch.from_numpy(c), torch.from_numpy(fpn_util.features_for(c)).cuda()))
+        with torch.no_grad():
+            ref = []
+            for c, f in inputs:  # layer by layer (a fresh, unrecorded network object shares the weights)
+                net.reset_program()
+                net.__dict__["_program_error"] = "disabled for the reference run"
+                scn.forward_pass_multiplyAdd_count = 0
+                rpn, roi = net([c, f])
+                ref.append(([m.features.clone() for m in rpn + roi], [m.get_spatial_locations() for m in rpn + roi], scn.forward_pass_multiplyAdd_count))
+            net.reset_program()
+            net([inputs[0][0], inputs[0][1]])          # records
+            assert net.__dict__.get("_program") is not None, net.__dict__.get("_program_error")
+            for (c, f), (feats, locs, macs) in zip(inputs, ref):
+                scn.forward_pass_multiplyAdd_count = 0
+                rpn, roi = net([c, f])                  # replays
+                assert scn.forward_pass_multiplyAdd_count == macs
+                for m, fr, lr in zip(rpn + roi, feats, locs):
+                    assert torch.equal(m.get_spatial_locations(), lr)
+                    assert m.features.shape == fr.shape
+                    scale = max(1.0, float(fr.abs().max()))
+                    # fp32: only the summation order of the atomically accumulated small levels differs.  bf16: those
+                    # last-bit differences flip the bf16 rounding of individual activations of the next layer (one
+                    # bf16 ulp = 4e-3 relative), so two runs of the SAME path already differ by ~1e-2 of max|x|.
+                    assert float((m.features - fr).abs().max()) <= (1e-4 if math == "fp32" else 4e-2) * scale
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
