@@ -6,11 +6,34 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <chrono>
+#include <stdlib.h>
 
 namespace scn {
 std::atomic<long> g_launches{0};
+namespace {
+struct TlEv { const char *who; int kind; long a, b; double t; };
+std::vector<TlEv> g_tl;
+std::mutex g_tl_mu;
+int g_tl_on = -1;
+double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+} // namespace
+void timeline_mark(const char *who, int kind, long a, long b) {
+  if (g_tl_on < 0) g_tl_on = getenv("SCN_TIMELINE") ? atoi(getenv("SCN_TIMELINE")) : 0;
+  if (!g_tl_on) return;
+  std::lock_guard<std::mutex> lk(g_tl_mu);
+  g_tl.push_back(TlEv{who, kind, a, b, now_us()});
+}
+void timeline_dump() {
+  if (g_tl_on <= 0) return;
+  std::lock_guard<std::mutex> lk(g_tl_mu);
+  if (g_tl.empty()) return;
+  const double t0 = g_tl[0].t;
+  for (const TlEv &e : g_tl) fprintf(stderr, "[tl] %8.1f us %-8s kind %d  %ld %ld\n", e.t - t0, e.who, e.kind, e.a, e.b);
+  g_tl.clear();
+}
 const char *last_error();
-void set_prefetch_worker_thread(bool on);
+void set_prefetch_worker_thread(bool on, int ctx);
 int launch_conv_plan_simt(const float *in, float *out, const float *W, const int *nbr, const int *outRow, int nOut, int K, int Cin, int Cout,
                           const float *bias, cudaStream_t s);
 int launch_conv_list_simt(const float *in, float *out, const float *W, const int2 *pairs, const int *d_off, const int *offHost, int K, int Cin,
@@ -36,9 +59,9 @@ static int g_math_mode = 0;
 struct PrefetchOp { long v[13]; }; // kind, a[3], b[3], f[3], s[3]
 struct scn_metadata {
   scn::Metadata md;
-  std::thread worker;
+  std::thread worker, worker2;
   std::atomic<bool> stop{false};
-  std::vector<PrefetchOp> ops;
+  std::vector<PrefetchOp> ops, ops2; // chain worker (strided convolutions = the grid pyramid) / everything else
   int device = 0;
 };
 
@@ -73,7 +96,7 @@ int scn_metadata_create(scn_metadata **out, void *stream) {
   }
   scn_metadata *m = new scn_metadata();
   cudaGetDevice(&m->device);
-  m->md.stream = static_cast<cudaStream_t>(stream);
+  m->md.cstream = static_cast<cudaStream_t>(stream);
   int r = m->md.init();
   if (r) { delete m; return r; }
   *out = m;
@@ -82,8 +105,11 @@ int scn_metadata_create(scn_metadata **out, void *stream) {
 void scn_metadata_destroy(scn_metadata *m) {
   if (!m) return;
   m->stop = true;
+  m->md.set_chain_done(true);
   if (m->worker.joinable()) m->worker.join();
+  if (m->worker2.joinable()) m->worker2.join();
   delete m;
+  scn::timeline_dump();
 }
 
 // Builds ahead, on a worker thread and the Metadata's build stream, the rulebooks / plans the caller
@@ -92,12 +118,14 @@ void scn_metadata_destroy(scn_metadata *m) {
 // b = out (fine))).  Purely a hint: results are identical with or without it, entries are built
 // in the same lazily-filled caches (Metadata.cpp:429-510) under the same keys; a failing hint is
 // ignored and the error resurfaces when the caller requests that entry itself.
-static void prefetch_worker(scn_metadata *m) {
+static void prefetch_worker(scn_metadata *m, int which) {
   cudaSetDevice(m->device);
-  scn::set_prefetch_worker_thread(true);
-  for (const PrefetchOp &op : m->ops) {
+  scn::set_prefetch_worker_thread(true, which);
+  struct Done { scn_metadata *m; int which; ~Done() { if (which == 0) m->md.set_chain_done(true); } } done{m, which};
+  for (const PrefetchOp &op : (which == 0 ? m->ops : m->ops2)) {
     if (m->stop) break;
     const long *a = op.v + 1, *b = op.v + 4, *f = op.v + 7, *s = op.v + 10;
+    struct Mark { const PrefetchOp &o; ~Mark() { scn::timeline_mark("worker", (int)o.v[0], o.v[1], o.v[7]); } } mark{op};
     if (op.v[0] == 1) {
       scn::SubmEntry *e;
       if (m->md.get_submanifold(a, f, &e)) break;
@@ -105,8 +133,9 @@ static void prefetch_worker(scn_metadata *m) {
       scn::ConvEntry *e;
       if (m->md.get_conv(a, b, f, s, &e)) break;
     } else if (op.v[0] == 3) {
-      scn::ConvEntry *e;
-      if (m->md.get_conv(b, a, f, s, &e)) break;
+      scn::ConvEntry *e = which == 1 ? m->md.wait_conv(b, f, s) : nullptr; // built by the chain worker
+      if (m->stop) break;
+      if (!e && m->md.get_conv(b, a, f, s, &e)) break;
       scn::Grid *gf = m->md.find_grid(b);
       if (scn::g_math_mode != 0 && scn::tc_available() && gf && gf->n > 0 && e->geom.M == 1 && e->rb.total == gf->n)
         if (m->md.get_deconv_plan(*e)) break;
@@ -115,18 +144,32 @@ static void prefetch_worker(scn_metadata *m) {
 }
 int scn_metadata_prefetch(scn_metadata *m, int n_ops, const long *ops) {
   if (!m) { scn::set_error("null scn_metadata handle"); return -3; }
+  m->md.set_chain_done(true);
   if (m->worker.joinable()) m->worker.join();
-  m->ops.resize(n_ops);
-  for (int i = 0; i < n_ops; i++) for (int j = 0; j < 13; j++) m->ops[i].v[j] = ops[i * 13 + j];
+  if (m->worker2.joinable()) m->worker2.join();
+  m->ops.clear();
+  m->ops2.clear();
+  // The strided convolutions create the grids level by level: that chain is the critical path, so it
+  // gets a worker (and a build stream) of its own; submanifold plans and deconvolution plans only
+  // hang off it and are built by a second worker on the second build context.
+  for (int i = 0; i < n_ops; i++) {
+    PrefetchOp op;
+    for (int j = 0; j < 13; j++) op.v[j] = ops[i * 13 + j];
+    (m->md.nCtx >= 2 && op.v[0] != 2 ? m->ops2 : m->ops).push_back(op);
+  }
   m->stop = false;
-  m->worker = std::thread(prefetch_worker, m);
+  m->md.set_chain_done(false);
+  m->worker = std::thread(prefetch_worker, m, 0);
+  if (!m->ops2.empty()) m->worker2 = std::thread(prefetch_worker, m, 1);
   return 0;
 }
 
 int scn_input_layer_build(scn_metadata *m, const long sz[3], const long *coords, int on_device, long nrows, int ncols,
                           int batch_size, int mode, long *n_active, int *max_active) {
   M_OR_FAIL(m);
+  scn::timeline_mark("input", 0, nrows, 0);
   SCN_TRY(m->md.input_layer(sz, coords, on_device, nrows, ncols, batch_size, mode));
+  scn::timeline_mark("input", 1, nrows, 0);
   if (n_active) *n_active = m->md.input.nOut;
   if (max_active) *max_active = m->md.input.maxActive;
   return 0;
@@ -220,7 +263,7 @@ int scn_rulebook_info(scn_metadata *m, int kind, const long a[3], const long b[3
 }
 int scn_rulebook_copy(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], int list, int *dst) {
   M_OR_FAIL(m);
-  cudaStream_t s = m->md.stream;
+  cudaStream_t s = m->md.cur().stream;
   if (kind == 0) {
     auto &I = m->md.input;
     SCN_CHECK(I.valid, "input layer not built");
@@ -247,8 +290,8 @@ int scn_iteration_order(scn_metadata *m, const long sz[3], int *dst) {
   scn::Metadata::BuildLock bl(m->md);
   SCN_TRY(m->md.ensure_rank(*g));
   if (g->n) {
-    SCN_CUDA(cudaMemcpyAsync(dst, g->rank2id, (size_t)g->n * 4, cudaMemcpyDeviceToHost, m->md.stream));
-    SCN_CUDA(cudaStreamSynchronize(m->md.stream));
+    SCN_CUDA(cudaMemcpyAsync(dst, g->rank2id, (size_t)g->n * 4, cudaMemcpyDeviceToHost, m->md.cur().stream));
+    SCN_CUDA(cudaStreamSynchronize(m->md.cur().stream));
   }
   return 0;
 }

@@ -36,6 +36,9 @@ void set_error(const std::string &msg);
     if (r__ != 0) return r__;                                                            \
   } while (0)
 
+// developer timeline (SCN_TIMELINE=1): host timestamps of build / submit milestones, printed to stderr
+void timeline_mark(const char *who, int kind, long a, long b);
+void timeline_dump();
 // every kernel launch of this library passes its stream through LS(): launch accounting
 extern std::atomic<long> g_launches;
 static inline cudaStream_t LS(cudaStream_t s) { ++g_launches; return s; }

@@ -559,6 +559,22 @@ __global__ void __launch_bounds__(256) k_to_bf16(const float *__restrict__ x, ui
     y[i] = pk;
   }
 }
+// Grow-only scratch per stream for the operand copies a call may need (zero-padded rows of a narrow
+// input, bf16 copy of an input that arrived without one).  Uses on one stream are ordered, so one
+// buffer per stream suffices; cudaMallocAsync took milliseconds for these 150-300 MB blocks.
+static int stream_scratch(cudaStream_t s, size_t bytes, void **out) {
+  static std::mutex mu;
+  static std::map<cudaStream_t, std::pair<void *, size_t>> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto &e = cache[s];
+  if (e.second < bytes) {
+    if (e.first) { SCN_CUDA(cudaStreamSynchronize(s)); SCN_CUDA(cudaFree(e.first)); }
+    e.second = bytes + bytes / 8 + (1u << 20);
+    SCN_CUDA(cudaMalloc(&e.first, e.second));
+  }
+  *out = e.first;
+  return 0;
+}
 // in16: optional bf16 copy of `in` (same layout); used in math mode 2 when Cin is a multiple of 64
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
@@ -568,11 +584,9 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (Cin % 32 != 0) { // e.g. the 9-channel input convolution: rows zero-padded to 32 channels (the weight image pads itself)
     const int Cp = (Cin + 31) / 32 * 32;
     float *xp = nullptr;
-    SCN_CUDA(cudaMallocAsync((void **)&xp, (size_t)nInRows * Cp * 4, s));
+    SCN_TRY(stream_scratch(s, (size_t)nInRows * Cp * 4 + 16, (void **)&xp));
     k_pad_rows<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
-    int r = launch_conv_plan_tc(xp, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr, wTag, Cin);
-    cudaFreeAsync(xp, s);
-    return r;
+    return launch_conv_plan_tc(xp, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr, wTag, Cin);
   }
   SCN_CHECK(Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && K <= 64, "tcgen05 path: unsupported channel counts");
   static int envT = -1, envS = -1, envDbg = 0, envProf = 0, envCtas = 0;
@@ -590,7 +604,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   void *tmp16 = nullptr;
   if (P.bf16) {
     if (!in16) {
-      SCN_CUDA(cudaMallocAsync(&tmp16, (size_t)nInRows * Cin * 2 + 16, s));
+      SCN_TRY(stream_scratch(s, (size_t)nInRows * Cin * 2 + 16, &tmp16));
       if (nInRows) k_to_bf16<<<stream_grid(nInRows * Cin / 4, 256), 256, 0, LS(s)>>>(in, static_cast<uint2 *>(tmp16), nInRows * Cin / 4);
       in16 = tmp16;
     }
@@ -664,7 +678,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     cudaFreeAsync(P.prof, s);
   }
   if (wimgOwned) cudaFreeAsync(wimg, s);
-  if (tmp16) cudaFreeAsync(tmp16, s);
+
   return 0;
 }
 

@@ -39,29 +39,53 @@ static size_t chunk_round(size_t b) { const size_t q = 32u << 20; return (b + q 
 static std::vector<cudaStream_t> g_stream_free;
 static std::vector<cudaEvent_t> g_event_free;
 thread_local bool tl_prefetch_worker = false;
-void set_prefetch_worker_thread(bool on) { tl_prefetch_worker = on; }
-Metadata::BuildLock::BuildLock(Metadata &md) : m(md) {
+thread_local int tl_ctx = 0; // build context of this thread: 0 = caller and chain worker, 1 = second prefetch worker
+void set_prefetch_worker_thread(bool on, int ctx) { tl_prefetch_worker = on; tl_ctx = ctx; }
+BuildCtx &Metadata::cur() { return cx[tl_ctx < nCtx ? tl_ctx : 0]; }
+Metadata::BuildLock::BuildLock(Metadata &md) : c(md.cur()) {
   if (tl_prefetch_worker) {
-    while (m.callerWaiting.load(std::memory_order_acquire) > 0) std::this_thread::yield();
-    m.buildMu.lock();
+    while (c.callerWaiting.load(std::memory_order_acquire) > 0) std::this_thread::yield();
+    c.mu.lock();
   } else {
-    m.callerWaiting.fetch_add(1, std::memory_order_acq_rel);
-    m.buildMu.lock();
-    m.callerWaiting.fetch_sub(1, std::memory_order_acq_rel);
+    c.callerWaiting.fetch_add(1, std::memory_order_acq_rel);
+    c.mu.lock();
+    c.callerWaiting.fetch_sub(1, std::memory_order_acq_rel);
   }
 }
 int Metadata::mark_ready(Ready &r) {
-  if (stream != cstream) {
+  BuildCtx &c = cur();
+  if (c.stream != cstream) {
     {
       std::lock_guard<std::mutex> lk(g_pool_mu);
       if (!g_event_free.empty()) { r.ev = g_event_free.back(); g_event_free.pop_back(); }
     }
     if (!r.ev) SCN_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
-    events.push_back(r.ev);
-    SCN_CUDA(cudaEventRecord(r.ev, stream));
+    SCN_CUDA(cudaEventRecord(r.ev, c.stream));
   }
-  std::lock_guard<std::mutex> lk(mapMu);
-  r.ready = true;
+  {
+    std::lock_guard<std::mutex> lk(mapMu);
+    if (r.ev) events.push_back(r.ev);
+    r.by = c.stream;
+    r.ready = true;
+    r.building = false;
+  }
+  cv.notify_all();
+  return 0;
+}
+void Metadata::unclaim(Ready &r) {
+  { std::lock_guard<std::mutex> lk(mapMu); r.building = false; }
+  cv.notify_all();
+}
+bool Metadata::claim(Ready &r) {
+  std::unique_lock<std::mutex> lk(mapMu);
+  for (;;) {
+    if (r.ready) return false;
+    if (!r.building) { r.building = true; return true; }
+    cv.wait(lk);
+  }
+}
+int Metadata::need(Ready &r) {
+  if (r.ev && r.by != cur().stream) SCN_CUDA(cudaStreamWaitEvent(cur().stream, r.ev, 0));
   return 0;
 }
 int Metadata::wait_ready(Ready &r) {
@@ -70,74 +94,66 @@ int Metadata::wait_ready(Ready &r) {
   return 0;
 }
 Metadata::~Metadata() {
-  from_compute(); // what follows on the build stream is ordered after every feature kernel that still reads these buffers
-  {
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    for (Chunk &c : chunks) {
-      if (!c.freed) cudaEventCreateWithFlags(&c.freed, cudaEventDisableTiming);
-      cudaEventRecord(c.freed, stream);
-      if (g_chunk_bytes + c.cap > kChunkKeep) { cudaEventSynchronize(c.freed); cudaFree(c.p); cudaEventDestroy(c.freed); continue; }
-      g_chunks.push_back(c);
-      g_chunk_bytes += c.cap;
+  // what follows on the build streams is ordered after every feature kernel that still reads these buffers
+  if (evCompute) cudaEventRecord(evCompute, cstream);
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (int i = 0; i < nCtx; i++) {
+    BuildCtx &c = cx[i];
+    if (evCompute && c.stream != cstream) cudaStreamWaitEvent(c.stream, evCompute, 0);
+    for (Chunk &k : c.chunks) {
+      if (!k.freed) cudaEventCreateWithFlags(&k.freed, cudaEventDisableTiming);
+      cudaEventRecord(k.freed, c.stream);
+      if (g_chunk_bytes + k.cap > kChunkKeep) { cudaEventSynchronize(k.freed); cudaFree(k.p); cudaEventDestroy(k.freed); continue; }
+      g_chunks.push_back(k);
+      g_chunk_bytes += k.cap;
     }
-    if (h_scalars) g_pinned_free.push_back(h_scalars);
+    if (c.h_scalars) g_pinned_free.push_back(c.h_scalars);
+    if (c.ownStream) g_stream_free.push_back(c.stream);
   }
-  {
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    if (ownStream) g_stream_free.push_back(stream);
-    for (cudaEvent_t e : events) g_event_free.push_back(e);
-  }
-  if (evBuild) cudaEventDestroy(evBuild);
+  for (cudaEvent_t e : events) g_event_free.push_back(e);
   if (evCompute) cudaEventDestroy(evCompute);
 }
-int Metadata::to_compute() {
-  if (!buildDirty || stream == cstream) { buildDirty = false; return 0; }
-  SCN_CUDA(cudaEventRecord(evBuild, stream));
-  SCN_CUDA(cudaStreamWaitEvent(cstream, evBuild, 0));
-  buildDirty = false;
-  return 0;
-}
 int Metadata::from_compute() {
-  if (stream == cstream || !evCompute) return 0;
+  if (cur().stream == cstream || !evCompute) return 0;
   SCN_CUDA(cudaEventRecord(evCompute, cstream));
-  SCN_CUDA(cudaStreamWaitEvent(stream, evCompute, 0));
+  SCN_CUDA(cudaStreamWaitEvent(cur().stream, evCompute, 0));
   return 0;
 }
-void *Metadata::alloc(size_t bytes) {
+void *Metadata::alloc_in(BuildCtx &c, size_t bytes) {
   void *p = nullptr;
-  buildDirty = true;
   bytes = (std::max<size_t>(bytes, 256) + 255) & ~(size_t)255;
-  if (arena && arenaUsed + bytes <= arenaCap) {
-    p = arena + arenaUsed;
-    arenaUsed += bytes;
+  if (c.arena && c.arenaUsed + bytes <= c.arenaCap) {
+    p = c.arena + c.arenaUsed;
+    c.arenaUsed += bytes;
     return p;
   }
-  const bool dedicated = bytes > arenaNext / 2; // large buffers get their own block, the current chunk stays in use
-  const size_t cap = chunk_round(dedicated ? bytes : arenaNext);
-  Chunk c{nullptr, 0, nullptr};
+  const bool dedicated = bytes > c.arenaNext / 2; // large buffers get their own block, the current chunk stays in use
+  const size_t cap = chunk_round(dedicated ? bytes : c.arenaNext);
+  Chunk k{nullptr, 0, nullptr};
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
     int best = -1;
     for (int i = 0; i < (int)g_chunks.size(); i++)
       if (g_chunks[i].cap >= cap && g_chunks[i].cap <= 2 * cap && (best < 0 || g_chunks[i].cap < g_chunks[best].cap)) best = i;
-    if (best >= 0) { c = g_chunks[best]; g_chunks.erase(g_chunks.begin() + best); g_chunk_bytes -= c.cap; }
+    if (best >= 0) { k = g_chunks[best]; g_chunks.erase(g_chunks.begin() + best); g_chunk_bytes -= k.cap; }
   }
-  if (c.p) {
-    if (cudaStreamWaitEvent(stream, c.freed, 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); return nullptr; }
+  if (k.p) {
+    if (cudaStreamWaitEvent(c.stream, k.freed, 0) != cudaSuccess) { set_error("cudaStreamWaitEvent failed"); return nullptr; }
   } else {
-    if (cudaMalloc(&c.p, cap) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
-    c.cap = cap;
+    if (cudaMalloc(&k.p, cap) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
+    k.cap = cap;
   }
-  chunks.push_back(c);
-  p = c.p;
+  c.chunks.push_back(k);
+  p = k.p;
   if (!dedicated) {
-    arena = static_cast<char *>(p);
-    arenaCap = c.cap;
-    arenaUsed = bytes;
-    arenaNext = std::min<size_t>(arenaNext * 2, 256u << 20);
+    c.arena = static_cast<char *>(p);
+    c.arenaCap = k.cap;
+    c.arenaUsed = bytes;
+    c.arenaNext = std::min<size_t>(c.arenaNext * 2, 256u << 20);
   }
   return p;
 }
+void *Metadata::alloc(size_t bytes) { return alloc_in(cur(), bytes); }
 int Metadata::init() {
   static bool poolConfigured = false;
   if (!poolConfigured) {
@@ -149,52 +165,84 @@ int Metadata::init() {
     SCN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     poolConfigured = true;
   }
-  cstream = stream;
-  static int async = -1;
-  if (async < 0) async = getenv("SCN_ASYNC_BUILD") ? atoi(getenv("SCN_ASYNC_BUILD")) : 1;
-  if (async) {
-    {
-      std::lock_guard<std::mutex> lk(g_pool_mu);
-      if (!g_stream_free.empty()) { stream = g_stream_free.back(); g_stream_free.pop_back(); ownStream = true; }
-    }
-    if (!ownStream) {
-      int lo = 0, hi = 0;
-      SCN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-      SCN_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, hi));
-    }
-    ownStream = true;
-    SCN_CUDA(cudaEventCreateWithFlags(&evBuild, cudaEventDisableTiming));
-    SCN_CUDA(cudaEventCreateWithFlags(&evCompute, cudaEventDisableTiming));
+  static int async = -1, workers = -1;
+  if (async < 0) {
+    async = getenv("SCN_ASYNC_BUILD") ? atoi(getenv("SCN_ASYNC_BUILD")) : 1;
+    workers = getenv("SCN_BUILD_WORKERS") ? atoi(getenv("SCN_BUILD_WORKERS")) : 2;
   }
-  zpoolWords = 1 << 19; // 4 MiB of scan state
-  zpool = alloc_n<unsigned long long>(zpoolWords);
-  d_scalars = alloc_n<int>(256);
-  d_err = d_scalars + 200;
-  SCN_CHECK(zpool && d_scalars, "alloc");
-  SCN_CUDA(cudaMemsetAsync(zpool, 0, zpoolWords * 8, stream));
-  SCN_CUDA(cudaMemsetAsync(d_scalars, 0, 256 * 4, stream));
-  h_scalars = pinned_get();
-  SCN_CHECK(h_scalars, "pinned host scratch");
+  nCtx = (async && workers >= 2) ? 2 : 1;
+  if (async) SCN_CUDA(cudaEventCreateWithFlags(&evCompute, cudaEventDisableTiming));
+  for (int i = 0; i < nCtx; i++) {
+    BuildCtx &c = cx[i];
+    c.stream = cstream;
+    if (async) {
+      {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_stream_free.empty()) { c.stream = g_stream_free.back(); g_stream_free.pop_back(); c.ownStream = true; }
+      }
+      if (!c.ownStream) {
+        int lo = 0, hi = 0;
+        SCN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SCN_CUDA(cudaStreamCreateWithPriority(&c.stream, cudaStreamNonBlocking, hi));
+        c.ownStream = true;
+      }
+    }
+    c.zpoolWords = 1 << 19; // 4 MiB of scan state
+    c.zpool = static_cast<unsigned long long *>(alloc_in(c, c.zpoolWords * 8));
+    c.d_scalars = static_cast<int *>(alloc_in(c, 256 * 4));
+    SCN_CHECK(c.zpool && c.d_scalars, "alloc");
+    c.d_err = c.d_scalars + 200;
+    SCN_CUDA(cudaMemsetAsync(c.zpool, 0, c.zpoolWords * 8, c.stream));
+    SCN_CUDA(cudaMemsetAsync(c.d_scalars, 0, 256 * 4, c.stream));
+    c.h_scalars = pinned_get();
+    SCN_CHECK(c.h_scalars, "pinned host scratch");
+  }
   return 0;
 }
 unsigned long long *Metadata::scan_state(long n) {
+  BuildCtx &c = cur();
   size_t w = scan_state_words(n);
-  if (zpoolUsed + w > zpoolWords) { // start a fresh zeroed pool
-    size_t words = std::max(zpoolWords, w * 2);
-    zpool = alloc_n<unsigned long long>(words);
-    if (!zpool) return nullptr;
-    cudaMemsetAsync(zpool, 0, words * 8, stream);
-    zpoolWords = words;
-    zpoolUsed = 0;
+  if (c.zpoolUsed + w > c.zpoolWords) { // start a fresh zeroed pool
+    size_t words = std::max(c.zpoolWords, w * 2);
+    c.zpool = alloc_n<unsigned long long>(words);
+    if (!c.zpool) return nullptr;
+    cudaMemsetAsync(c.zpool, 0, words * 8, c.stream);
+    c.zpoolWords = words;
+    c.zpoolUsed = 0;
   }
-  unsigned long long *p = zpool + zpoolUsed;
-  zpoolUsed += w;
+  unsigned long long *p = c.zpool + c.zpoolUsed;
+  c.zpoolUsed += w;
   return p;
 }
 int Metadata::sync_scalars(int count) {
-  SCN_CUDA(cudaMemcpyAsync(h_scalars, d_scalars, count * 4, cudaMemcpyDeviceToHost, stream));
-  SCN_CUDA(cudaStreamSynchronize(stream));
+  BuildCtx &c = cur();
+  SCN_CUDA(cudaMemcpyAsync(c.h_scalars, c.d_scalars, count * 4, cudaMemcpyDeviceToHost, c.stream));
+  SCN_CUDA(cudaStreamSynchronize(c.stream));
   return 0;
+}
+// Worker threads may run ahead of the chain worker that creates the grids: wait for it.
+Grid *Metadata::find_grid_wait(const long *sz) {
+  std::unique_lock<std::mutex> lk(mapMu);
+  for (;;) {
+    auto it = grids.find(P3{sz[0], sz[1], sz[2]});
+    if (it != grids.end() && it->second.built) return &it->second;
+    if (!tl_prefetch_worker || chainDone.load()) return nullptr;
+    cv.wait_for(lk, std::chrono::milliseconds(2));
+  }
+}
+ConvEntry *Metadata::wait_conv(const long *inS, const long *f, const long *st) {
+  ConvKey key{P3{inS[0], inS[1], inS[2]}, P3{f[0], f[1], f[2]}, P3{st[0], st[1], st[2]}};
+  std::unique_lock<std::mutex> lk(mapMu);
+  for (;;) {
+    auto it = conv.find(key);
+    if (it != conv.end() && it->second.rdy.ready) return &it->second;
+    if (chainDone.load()) return nullptr;
+    cv.wait_for(lk, std::chrono::milliseconds(2));
+  }
+}
+void Metadata::set_chain_done(bool v) {
+  chainDone.store(v);
+  cv.notify_all();
 }
 Grid *Metadata::find_grid(const long *sz) {
   std::lock_guard<std::mutex> lk(mapMu);
@@ -205,12 +253,12 @@ Grid *Metadata::find_grid(const long *sz) {
 template <class InF, class OutF>
 static int run_scan(Metadata &M, long n, InF in, OutF out, int *total) {
   if (n <= 0) {
-    if (total) SCN_CUDA(cudaMemsetAsync(total, 0, 4, M.stream));
+    if (total) SCN_CUDA(cudaMemsetAsync(total, 0, 4, M.cur().stream));
     return 0;
   }
   unsigned long long *st = M.scan_state(n);
   SCN_CHECK(st, "scan state");
-  scan_kernel<<<cdiv(n, kScanTile), kScanThreads, 0, LS(M.stream)>>>(n, in, out, st, total);
+  scan_kernel<<<cdiv(n, kScanTile), kScanThreads, 0, LS(M.cur().stream)>>>(n, in, out, st, total);
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -287,10 +335,10 @@ static int build_blocks(Metadata &M, Grid &g, const int4 *pts, long npts, int *o
   g.bmask = M.alloc_n<unsigned long long>(g.maxBlocks * 8);
   g.wbase = M.alloc_n<int>(g.maxBlocks * 8);
   SCN_CHECK(g.dir && g.bmask && g.wbase && g.d_nblocks, "alloc");
-  cudaStream_t s = M.stream;
+  cudaStream_t s = M.cur().stream;
   SCN_CUDA(cudaMemsetAsync(g.dir, 0, cells * 4, s));
   if (npts > 0) {
-    k_mark_dir<<<stream_grid(npts, 256), 256, 0, LS(s)>>>(pts, npts, g.dir, g.dd[1], g.dd[2], g.dirCells, (int)g.sz[0], (int)g.sz[1], (int)g.sz[2], M.d_err);
+    k_mark_dir<<<stream_grid(npts, 256), 256, 0, LS(s)>>>(pts, npts, g.dir, g.dd[1], g.dd[2], g.dirCells, (int)g.sz[0], (int)g.sz[1], (int)g.sz[2], M.cur().d_err);
   }
   SCN_TRY(run_scan(M, cells, DirIn{g.dir}, DirOut{g.dir}, g.d_nblocks));
   k_zero_words<<<stream_grid(g.maxBlocks * 8, 256), 256, 0, LS(s)>>>(g.bmask, g.d_nblocks);
@@ -373,9 +421,8 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
   }
   Grid &g = *gp;
   g.sz = key;
-  cudaStream_t s = stream;
-  if (onDevice) SCN_TRY(from_compute()); // the coordinates were produced on the caller's stream
-  buildDirty = true;
+  cudaStream_t s = cur().stream;
+  if (onDevice) SCN_TRY(from_compute()); // the coordinates were produced on the caller's cur().stream
   const long *dcoords = coords;
   if (!onDevice && nrows) {
     long *tmp = alloc_n<long>(nrows * ncols);
@@ -385,13 +432,13 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
   }
   int4 *pts = alloc_n<int4>(std::max(1l, nrows));
   SCN_CHECK(pts, "alloc");
-  int *sc = d_scalars; // [0] maxBatch [1] nUnique [2] maxActive [3] nActive
+  int *sc = cur().d_scalars; // [0] maxBatch [1] nUnique [2] maxActive [3] nActive
   SCN_CUDA(cudaMemsetAsync(sc, 0, 64 * 4, s));
   if (nrows) k_coords_to_pts<<<stream_grid(nrows, 256), 256, 0, LS(s)>>>(dcoords, nrows, ncols, pts, sc);
   g.batch = std::max(1, batchHint);
   if (ncols == 4 && nrows) {
     SCN_TRY(sync_scalars(1));
-    g.batch = std::max(g.batch, h_scalars[0] + 1);
+    g.batch = std::max(g.batch, cur().h_scalars[0] + 1);
   }
   SCN_CHECK(g.batch <= 48, "batch size > 48 not supported");
   int *rowP = alloc_n<int>(std::max(1l, nrows));
@@ -409,9 +456,9 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
   SCN_TRY(run_scan(*this, nrows, FirstIn{rowP, firstRow}, FirstOut{rowP, pts, g.p2id, g.id2p, g.coords}, sc + 3));
   // per-batch-item counts (only needed when batch > 1)
   SCN_TRY(sync_scalars(4));
-  g.n = h_scalars[3];
-  int maxActive = h_scalars[2];
-  SCN_CHECK(h_scalars[1] == g.n, "internal: unique count mismatch");
+  g.n = cur().h_scalars[3];
+  int maxActive = cur().h_scalars[2];
+  SCN_CHECK(cur().h_scalars[1] == g.n, "internal: unique count mismatch");
   g.itemCount.assign(g.batch, 0);
   g.itemCtr.assign(g.batch, g.batch == 1 ? 0 : -1);
   if (g.batch == 1) g.itemCount[0] = g.n;
@@ -419,9 +466,10 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
     SCN_CUDA(cudaMemsetAsync(sc + 8, 0, 48 * 4, s));
     if (g.n) k_count_batch<<<stream_grid(g.n, 256), 256, 0, LS(s)>>>(g.coords, g.n, sc + 8);
     SCN_TRY(sync_scalars(8 + 48));
-    for (int b = 0; b < g.batch; b++) g.itemCount[b] = h_scalars[8 + b];
+    for (int b = 0; b < g.batch; b++) g.itemCount[b] = cur().h_scalars[8 + b];
   }
   { std::lock_guard<std::mutex> lk(mapMu); g.built = true; }
+  SCN_TRY(mark_ready(g.rdy));
   // rules
   input.mode = mode; input.nIn = (int)nrows; input.nOut = g.n; input.valid = true;
   input.maxActive = (mode == 3 || mode == 4) ? maxActive : 1;
@@ -554,7 +602,7 @@ __global__ void __launch_bounds__(1024) k_emulate_small(const int4 *coords, cons
 static int emulate_order(Metadata &M, const int4 *coords, const int *seq, int idOffset, int n, int *rank2idOut) {
   if (n == 0) return 0;
   SCN_CHECK(n < (1 << 25), "too many active sites in one batch item for the hash-order emulation");
-  cudaStream_t s = M.stream;
+  cudaStream_t s = M.cur().stream;
   long nbFinal = 32;
   while (n > nbFinal / 2) nbFinal *= 2;
   unsigned *T0 = M.alloc_n<unsigned>(nbFinal), *T1 = M.alloc_n<unsigned>(nbFinal);
@@ -566,7 +614,7 @@ static int emulate_order(Metadata &M, const int4 *coords, const int *seq, int id
     SCN_CUDA(cudaFuncSetAttribute(k_emulate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smallSmem));
     attr = true;
   }
-  k_emulate_small<<<1, 1024, smallSmem, LS(s)>>>(coords, seq, idOffset, n, T0, S0, M.d_err);
+  k_emulate_small<<<1, 1024, smallSmem, LS(s)>>>(coords, seq, idOffset, n, T0, S0, M.cur().d_err);
   SCN_CUDA(cudaGetLastError());
   long nb = std::min<long>(nbFinal, kSmallNb);
   unsigned *prev = T0, *cur = T1;
@@ -578,7 +626,7 @@ static int emulate_order(Metadata &M, const int4 *coords, const int *seq, int id
     SCN_CUDA(cudaMemsetAsync(cur, 0xff, nb * 4, s));
     // seqCur[0..nPrev) = ids of the old table in bucket order; the insert kernel appends the new ones
     SCN_TRY(run_scan(M, nb / 2, TabIn{prev}, CompactOut{prev, seqPrev, 0, seqCur}, nullptr));
-    k_phase_insert<<<stream_grid(nCur, 256, 16), 256, 0, LS(s)>>>(cur, (unsigned)(nb - 1), coords, seqCur, seq, idOffset, nPrev, nCur, seqCur, M.d_err);
+    k_phase_insert<<<stream_grid(nCur, 256, 16), 256, 0, LS(s)>>>(cur, (unsigned)(nb - 1), coords, seqCur, seq, idOffset, nPrev, nCur, seqCur, M.cur().d_err);
     std::swap(prev, cur);
     std::swap(seqPrev, seqCur);
     nPrev = nCur;
@@ -687,21 +735,21 @@ __global__ void __launch_bounds__(kRuleTile) k_rule_write(int n, int K, MaskF ma
 template <class MaskF, class PairF>
 static int build_rule_lists(Metadata &M, int n, int K, MaskF maskf, PairF pairf, RuleBookDev &rb, int extraScalars) {
   SCN_CHECK(K >= 1 && K <= 64, "filter volume must be <= 64");
-  cudaStream_t s = M.stream;
+  cudaStream_t s = M.cur().stream;
   rb.nLists = K;
   rb.off.assign(K + 1, 0);
   rb.d_off = M.alloc_n<int>(K + 1);
   int nTiles = cdiv(std::max(n, 1), kRuleTile);
   int *tileCnt = M.alloc_n<int>((long)nTiles * K);
-  int *totals = M.d_scalars + 128;
+  int *totals = M.cur().d_scalars + 128;
   SCN_CHECK(rb.d_off && tileCnt, "alloc");
   k_rule_count<<<nTiles, kRuleTile, 0, LS(s)>>>(n, K, maskf, tileCnt);
   k_rule_scan<<<K, 1024, 0, LS(s)>>>(nTiles, K, tileCnt, totals);
   k_list_offsets<<<1, 32, 0, LS(s)>>>(K, totals, rb.d_off);
-  SCN_CUDA(cudaMemcpyAsync(M.h_scalars + 128, rb.d_off, (K + 1) * 4, cudaMemcpyDeviceToHost, s));
-  if (extraScalars) SCN_CUDA(cudaMemcpyAsync(M.h_scalars, M.d_scalars, extraScalars * 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaMemcpyAsync(M.cur().h_scalars + 128, rb.d_off, (K + 1) * 4, cudaMemcpyDeviceToHost, s));
+  if (extraScalars) SCN_CUDA(cudaMemcpyAsync(M.cur().h_scalars, M.cur().d_scalars, extraScalars * 4, cudaMemcpyDeviceToHost, s));
   SCN_CUDA(cudaStreamSynchronize(s));
-  for (int L = 0; L <= K; L++) rb.off[L] = M.h_scalars[128 + L];
+  for (int L = 0; L <= K; L++) rb.off[L] = M.cur().h_scalars[128 + L];
   rb.total = rb.off[K];
   rb.pairs = M.alloc_n<int2>(std::max(1l, rb.total));
   SCN_CHECK(rb.pairs, "alloc");
@@ -727,7 +775,7 @@ int Metadata::build_tile_masks(NbrPlan &plan) {
   int nTiles = cdiv(std::max(plan.nOut, 1), 128);
   plan.tileMask = alloc_n<unsigned long long>(nTiles + 8);
   SCN_CHECK(plan.tileMask, "alloc");
-  if (plan.nOut > 0) k_tile_masks<<<nTiles, 128, 0, LS(stream)>>>(plan.nbr, plan.nOut, plan.K, plan.tileMask);
+  if (plan.nOut > 0) k_tile_masks<<<nTiles, 128, 0, LS(cur().stream)>>>(plan.nbr, plan.nOut, plan.K, plan.tileMask);
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -776,21 +824,18 @@ struct SubmPair {
 // (SubmanifoldConvolutionRules.h:26-45)
 int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   SubmKey key{P3{sz[0], sz[1], sz[2]}, P3{f[0], f[1], f[2]}};
-  auto lookup = [&]() -> SubmEntry * {
-    std::lock_guard<std::mutex> lk(mapMu);
-    auto it = subm.find(key);
-    return it != subm.end() && it->second.rdy.ready ? &it->second : nullptr;
-  };
-  if ((*out = lookup())) return 0;
-  BuildLock bl(*this);
-  if ((*out = lookup())) return 0; // built by the other thread in the meantime
-  Grid *g = find_grid(sz);
-  SCN_CHECK(g, "no active sites recorded for this spatial size");
   long K = f[0] * f[1] * f[2];
   SCN_CHECK(K >= 1 && K <= 64 && f[0] > 0 && f[1] > 0 && f[2] > 0, "unsupported submanifold filter size");
+  Grid *g = tl_prefetch_worker ? find_grid_wait(sz) : find_grid(sz);
+  SCN_CHECK(g, "no active sites recorded for this spatial size");
   SubmEntry *ep;
   { std::lock_guard<std::mutex> lk(mapMu); ep = &subm[key]; }
   SubmEntry &e = *ep;
+  *out = ep;
+  if (!claim(e.rdy)) return 0; // built (or just finished) by another thread
+  struct Guard { Metadata &m; Ready &r; ~Guard() { if (!r.ready) m.unclaim(r); } } guard{*this, e.rdy};
+  BuildLock bl(*this);
+  SCN_TRY(need(g->rdy));
   e.plan.K = (int)K;
   e.plan.nOut = g->n;
   e.plan.outRow = g->p2id;
@@ -799,16 +844,16 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   SCN_CHECK(e.plan.nbr, "alloc");
   { // -1 in every slot of the last (partial) work item: whole tiles from the first incomplete one
     const long t0 = (long)g->n / 128;
-    SCN_CUDA(cudaMemsetAsync(e.plan.nbr + t0 * K * 128, 0xff, (nPad / 128 - t0) * K * 128 * 4, stream));
+    SCN_CUDA(cudaMemsetAsync(e.plan.nbr + t0 * K * 128, 0xff, (nPad / 128 - t0) * K * 128 * 4, cur().stream));
   }
-  SCN_CUDA(cudaMemsetAsync(d_scalars, 0, 4, stream));
-  if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, d_scalars);
+  SCN_CUDA(cudaMemsetAsync(cur().d_scalars, 0, 4, cur().stream));
+  if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, cur().d_scalars);
   // The forward pass only needs the plan and the rule COUNT (the reference's multiply-add counter);
   // the per-offset (in,out) lists in the reference's hash-iteration order are materialised on demand
   // (ensure_subm_rules: backward pass, rulebook inspection).
   SCN_TRY(build_tile_masks(e.plan));
   SCN_TRY(sync_scalars(1));
-  e.plan.nValid = h_scalars[0];
+  e.plan.nValid = cur().h_scalars[0];
   e.rb.nLists = (int)K;
   e.rb.total = e.plan.nValid;
   e.sz = key.sz;
@@ -818,11 +863,13 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
 }
 // SubmanifoldConvolution_SgToRules order (SubmanifoldConvolutionRules.h:26-45): sites in hash-iteration order
 int Metadata::ensure_subm_rules(SubmEntry &e) {
-  if (is_ready(e.rulesRdy)) return 0;
+  if (!claim(e.rulesRdy)) return 0;
+  struct Guard { Metadata &m; Ready &r; ~Guard() { if (!r.ready) m.unclaim(r); } } guard{*this, e.rulesRdy};
   BuildLock bl(*this);
-  if (is_ready(e.rulesRdy)) return 0;
   Grid *g = find_grid(e.sz.data());
   SCN_CHECK(g, "grid");
+  SCN_TRY(need(g->rdy));
+  SCN_TRY(need(e.rdy));
   SCN_TRY(ensure_rank(*g));
   const int K = e.plan.K;
   SCN_TRY(build_rule_lists(*this, g->n, K, SubmMask{g->rank2id, g->id2p, e.plan.nbr, K}, SubmPair{g->rank2id, g->id2p, e.plan.nbr, K}, e.rb, 0));
@@ -910,17 +957,16 @@ __global__ void k_conv_plan(ConvGeom G, const int *rank2id, const int4 *coords, 
 // getRuleBook (Metadata.cpp:484-510) -> Convolution_InputSgToRulesAndOutputSg (ConvolutionRules.h:11-34)
 int Metadata::get_conv(const long *inS, const long *outS, const long *f, const long *st, ConvEntry **out) {
   ConvKey key{P3{inS[0], inS[1], inS[2]}, P3{f[0], f[1], f[2]}, P3{st[0], st[1], st[2]}};
-  auto lookup = [&]() -> ConvEntry * {
-    std::lock_guard<std::mutex> lk(mapMu);
-    auto it = conv.find(key);
-    return it != conv.end() && it->second.rdy.ready ? &it->second : nullptr;
-  };
-  if ((*out = lookup())) return 0;
-  BuildLock bl(*this);
-  if ((*out = lookup())) return 0; // built by the other thread in the meantime
-  Grid *gi = find_grid(inS);
+  Grid *gi = tl_prefetch_worker ? find_grid_wait(inS) : find_grid(inS);
   SCN_CHECK(gi, "no active sites recorded for the input spatial size");
   P3 okey{outS[0], outS[1], outS[2]};
+  ConvEntry *ep;
+  { std::lock_guard<std::mutex> lk(mapMu); ep = &conv[key]; }
+  *out = ep;
+  if (!claim(ep->rdy)) return 0; // built (or just finished) by another thread
+  struct Guard { Metadata &m; Ready &r; ~Guard() { if (!r.ready) m.unclaim(r); } } guard{*this, ep->rdy};
+  BuildLock bl(*this);
+  SCN_TRY(need(gi->rdy));
   {
     std::lock_guard<std::mutex> lk(mapMu);
     SCN_CHECK(grids.find(okey) == grids.end(), "output spatial size already has a grid (each spatial size may occur once per Metadata)");
@@ -936,10 +982,9 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   }
   SCN_CHECK(G.K <= 64 && G.M <= 64, "unsupported convolution filter size");
   SCN_TRY(ensure_rank(*gi));
-  cudaStream_t s = stream;
-  ConvEntry *ep;
+  cudaStream_t s = cur().stream;
   Grid *gop;
-  { std::lock_guard<std::mutex> lk(mapMu); ep = &conv[key]; gop = &grids[okey]; }
+  { std::lock_guard<std::mutex> lk(mapMu); gop = &grids[okey]; }
   ConvEntry &e = *ep;
   e.out = okey;
   e.in = key.in;
@@ -952,7 +997,7 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   int4 *evPts = alloc_n<int4>(std::max(1l, E));
   int *evQ = alloc_n<int>(std::max(1l, E));
   SCN_CHECK(evPts && evQ, "alloc");
-  int *sc = d_scalars; // [1] nunique [3] nOut [8..56) per-item counts
+  int *sc = cur().d_scalars; // [1] nunique [3] nOut [8..56) per-item counts
   SCN_CUDA(cudaMemsetAsync(sc, 0, 64 * 4, s));
   if (E) k_conv_events<<<stream_grid(E, 256), 256, 0, LS(s)>>>(G, gi->rank2id, gi->coords, n, evPts);
   SCN_TRY(build_blocks(*this, go, evPts, E, evQ, sc + 1));
@@ -966,13 +1011,12 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   // rule lists (one sync: list offsets + nOut + per-item counts)
   SCN_TRY(build_rule_lists(*this, n, G.K, ConvMask{G, gi->rank2id, gi->coords},
                            ConvPair{G, gi->rank2id, gi->coords, evQ, go.p2id}, e.rb, 64));
-  go.n = h_scalars[3];
-  SCN_CHECK(h_scalars[1] == go.n, "internal: unique count mismatch (conv)");
+  go.n = cur().h_scalars[3];
+  SCN_CHECK(cur().h_scalars[1] == go.n, "internal: unique count mismatch (conv)");
   go.itemCount.assign(go.batch, 0);
   go.itemCtr.assign(go.batch, 0);
   int ctr = 0;
-  for (int b = 0; b < go.batch; b++) { go.itemCount[b] = h_scalars[8 + b]; go.itemCtr[b] = ctr; ctr += go.itemCount[b]; }
-  { std::lock_guard<std::mutex> lk(mapMu); go.built = true; }
+  for (int b = 0; b < go.batch; b++) { go.itemCount[b] = cur().h_scalars[8 + b]; go.itemCtr[b] = ctr; ctr += go.itemCount[b]; }
   // output-stationary plan
   e.plan.K = G.K; e.plan.nOut = go.n; e.plan.outRow = go.p2id; e.plan.nValid = e.rb.total;
   const long nPadOut = plan_padded(go.n);
@@ -982,8 +1026,10 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   if (E) k_conv_plan<<<stream_grid(E, 256), 256, 0, LS(s)>>>(G, gi->rank2id, gi->coords, evQ, n, e.plan.nbr);
   SCN_CUDA(cudaGetLastError());
   SCN_TRY(build_tile_masks(e.plan));
+  SCN_TRY(mark_ready(go.rdy)); // the event first: a thread that sees `built` must also see the event to wait for
+  { std::lock_guard<std::mutex> lk(mapMu); go.built = true; }
+  cv.notify_all();
   SCN_TRY(mark_ready(e.rdy));
-  *out = &e;
   return 0;
 }
 
@@ -1032,13 +1078,16 @@ __global__ void k_deconv_tiles(const int *__restrict__ off, int K, int *__restri
 }
 // Built on first use by a Deconvolution whose rulebook gives every fine site exactly one parent.
 int Metadata::get_deconv_plan(ConvEntry &e) {
-  if (is_ready(e.deconvRdy)) return 0;
+  if (!claim(e.deconvRdy)) return 0;
+  struct Guard { Metadata &m; Ready &r; ~Guard() { if (!r.ready) m.unclaim(r); } } guard{*this, e.deconvRdy};
   BuildLock bl(*this);
-  if (is_ready(e.deconvRdy)) return 0;
   Grid *gf = find_grid(e.in.data()), *gc = find_grid(e.out.data());
+  if (gf) SCN_TRY(need(gf->rdy));
+  if (gc) SCN_TRY(need(gc->rdy));
+  SCN_TRY(need(e.rdy));
   SCN_CHECK(gf && gc && e.geom.M == 1 && e.rb.total == gf->n, "deconvolution plan needs a single-parent rulebook");
   const int K = e.geom.K, n = gf->n;
-  cudaStream_t s = stream;
+  cudaStream_t s = cur().stream;
   // per-offset lists in SPATIAL order of the fine grid (same counts as the reference rulebook)
   int nT = cdiv(std::max(n, 1), kRuleTile);
   int *tileCnt = alloc_n<int>((long)nT * K);
@@ -1047,7 +1096,7 @@ int Metadata::get_deconv_plan(ConvEntry &e) {
   DeconvMask mf{e.geom, gf->p2id, gf->coords};
   DeconvPair pf{e.geom, gf->p2id, gf->coords, view(*gc), gc->p2id};
   k_rule_count<<<nT, kRuleTile, 0, LS(s)>>>(n, K, mf, tileCnt);
-  k_rule_scan<<<K, 1024, 0, LS(s)>>>(nT, K, tileCnt, d_scalars + 128);
+  k_rule_scan<<<K, 1024, 0, LS(s)>>>(nT, K, tileCnt, cur().d_scalars + 128);
   if (n > 0) k_rule_write<<<nT, kRuleTile, 0, LS(s)>>>(n, K, mf, pf, tileCnt, e.rb.d_off, dpairs);
   DeconvPlan &d = e.deconv;
   d.nTiles = 0;
@@ -1081,16 +1130,16 @@ int Metadata::spatial_locations(const long *sz, long *out, int outOnDevice) {
   Grid *g = find_grid(sz);
   SCN_CHECK(g, "no active sites recorded for this spatial size");
   if (g->n == 0) return 0;
+  SCN_TRY(need(g->rdy));
   long *dst = out;
   if (!outOnDevice) { dst = alloc_n<long>((long)g->n * 4); SCN_CHECK(dst, "alloc"); }
-  if (outOnDevice) SCN_TRY(from_compute()); // `out` was allocated by the caller on its stream
-  k_locations<<<stream_grid(g->n, 256), 256, 0, LS(stream)>>>(g->coords, g->n, dst);
+  if (outOnDevice) SCN_TRY(from_compute()); // `out` was allocated by the caller on its cur().stream
+  k_locations<<<stream_grid(g->n, 256), 256, 0, LS(cur().stream)>>>(g->coords, g->n, dst);
   SCN_CUDA(cudaGetLastError());
-  buildDirty = true;
-  if (outOnDevice) SCN_TRY(to_compute());
+  if (outOnDevice) { Ready r; SCN_TRY(mark_ready(r)); SCN_TRY(wait_ready(r)); }
   if (!outOnDevice) {
-    SCN_CUDA(cudaMemcpyAsync(out, dst, (long)g->n * 32, cudaMemcpyDeviceToHost, stream));
-    SCN_CUDA(cudaStreamSynchronize(stream));
+    SCN_CUDA(cudaMemcpyAsync(out, dst, (long)g->n * 32, cudaMemcpyDeviceToHost, cur().stream));
+    SCN_CUDA(cudaStreamSynchronize(cur().stream));
   }
   return 0;
 }

@@ -8,6 +8,8 @@
 #include <vector>
 #include <array>
 #include <mutex>
+#include <condition_variable>
+#include <chrono>
 #include <atomic>
 #include <thread>
 
@@ -15,7 +17,13 @@ namespace scn {
 
 typedef std::array<long, 3> P3;
 
+// `ready` (guarded by Metadata::mapMu) flips once the object is completely described on the host and
+// all its kernels are queued on a build stream (`by`); `building` = some thread has claimed the build;
+// `ev` marks the end of the build on that stream: other build streams (Metadata::need) and the
+// first feature kernel that uses the object (`waited`, Metadata::wait_ready) wait for it.
+struct Ready { bool ready = false, building = false; cudaEvent_t ev = nullptr; cudaStream_t by = nullptr; bool waited = false; };
 struct Grid {
+  Ready rdy;          // active-site structures (directory, masks, numbering)
   P3 sz{};            // spatial size
   int n = 0;          // active sites over all batch items (host copy)
   int batch = 1;
@@ -73,10 +81,6 @@ struct DeconvPlan {
   unsigned long long *tileMask = nullptr; // [nTiles] all ones (kept for the kernel's interface)
 };
 struct ConvGeomHost { int f[3], s[3], outS[3], cnt[3], M, K; };
-// `ready` (guarded by Metadata::mapMu) flips once the entry is completely described on the host and
-// all its kernels are queued on the build stream; `ev` marks that point on the build stream and the
-// first feature kernel that uses the entry makes the compute stream wait for it (`waited`).
-struct Ready { bool ready = false; cudaEvent_t ev = nullptr; bool waited = false; };
 struct SubmEntry { RuleBookDev rb; NbrPlan plan; Ready rdy, rulesRdy; P3 sz; }; // rb.pairs / offsets only after ensure_subm_rules
 struct ConvEntry { RuleBookDev rb; NbrPlan plan; P3 out; P3 in; ConvGeomHost geom; DeconvPlan deconv; Ready rdy, deconvRdy; };
 
@@ -88,57 +92,67 @@ struct InputRules {
 };
 
 struct Chunk { void *p; size_t cap; cudaEvent_t freed; };
-struct Metadata {
-  // Two streams: everything that BUILDS (grids, hash order, rulebooks, plans -- many short kernels
-  // and a few host readbacks of counts) runs on `stream`, a private high-priority stream; feature
-  // kernels run on the caller's `cstream`.  A host wait for a count then only drains the short
-  // build queue while the convolutions already submitted keep the GPU busy (the reference is
-  // synchronous throughout, SURVEY.md section 8b "Threading / streams").
-  cudaStream_t stream = 0;   // build stream
-  cudaStream_t cstream = 0;  // caller's compute stream
+// Everything a thread needs to BUILD (grids, hash order, rulebooks, plans): a private high-priority
+// stream, scalar scratch with its pinned host mirror, zeroed scan state and a bump allocator.  The
+// caller's thread and the chain worker share context 0, the second prefetch worker owns context 1.
+struct BuildCtx {
+  cudaStream_t stream = 0;
   bool ownStream = false;
-  bool buildDirty = false;   // build work was queued since the last hand-off to the compute stream
-  cudaEvent_t evBuild = nullptr, evCompute = nullptr;
-  int to_compute();          // compute stream waits for everything built so far
-  int from_compute();        // build stream waits for everything the caller has queued so far
-  // Two threads may use one Metadata: the caller's and the prefetch worker (capi.cu).  `buildMu`
-  // serialises builds (they share the build stream and the scalar scratch); `mapMu` guards the
-  // structure of the caches and the ready flags, so that feature kernels of finished entries are
-  // submitted while the worker is still building later ones.
-  std::recursive_mutex buildMu;
-  std::mutex mapMu;
-  // glibc mutexes are not fair: a worker that re-locks buildMu for its next entry right after
-  // unlocking starves the caller (measured: the caller's first convolution waited 5.8 ms, until the
-  // worker had built the whole pyramid).  The caller announces itself here and the worker yields.
+  int *d_scalars = nullptr; // small device scratch (256 ints)
+  int *h_scalars = nullptr; // pinned host mirror
+  int *d_err = nullptr;
+  unsigned long long *zpool = nullptr; // zero-initialised pool for scan states
+  size_t zpoolWords = 0, zpoolUsed = 0;
+  // bump allocator over a few chunks: a Metadata makes ~350 small allocations per forward and frees them all together
+  char *arena = nullptr;
+  size_t arenaCap = 0, arenaUsed = 0, arenaNext = 16u << 20;
+  std::vector<Chunk> chunks; // device memory taken from the process-wide list, returned on destruction
+  std::recursive_mutex mu;   // serialises the builds that use this context
+  // glibc mutexes are not fair: a worker that re-locks `mu` for its next entry right after unlocking
+  // starves the caller (measured: the caller's first convolution waited 5.8 ms, until the worker had
+  // built the whole pyramid).  The caller announces itself here and the worker yields.
   std::atomic<int> callerWaiting{0};
-  struct BuildLock {
-    Metadata &m;
-    explicit BuildLock(Metadata &md);
-    ~BuildLock() { m.buildMu.unlock(); }
-  };
+};
+struct Metadata {
+  // Feature kernels run on the caller's `cstream`; builds (many short kernels and a few host
+  // readbacks of counts) run on the private streams of the build contexts, so a host wait for a count
+  // only drains a short build queue while the convolutions already submitted keep the GPU busy (the
+  // reference is synchronous throughout, SURVEY.md section 8b "Threading / streams").
+  cudaStream_t cstream = 0;  // caller's compute stream
+  BuildCtx cx[2];
+  int nCtx = 1;
+  BuildCtx &cur();           // build context of the calling thread
+  cudaEvent_t evCompute = nullptr;
+  int from_compute();        // the current build stream waits for everything the caller has queued so far
+  // `mapMu` guards the structure of the caches and the ready / building flags; `cv` wakes threads
+  // that wait for an entry another thread is building.
+  std::mutex mapMu;
+  std::condition_variable cv;
+  std::atomic<bool> chainDone{true}; // no chain worker is producing grids (set_chain_done)
   std::vector<cudaEvent_t> events;
-  int mark_ready(Ready &r);   // record r.ev on the build stream, publish r.ready
+  struct BuildLock {
+    BuildCtx &c;
+    explicit BuildLock(Metadata &md);
+    ~BuildLock() { c.mu.unlock(); }
+  };
+  bool claim(Ready &r);       // false: already built; true: the caller builds it (others wait in claim)
+  void unclaim(Ready &r);     // a build failed: let a waiter retry
+  int mark_ready(Ready &r);   // record r.ev on the current build stream, publish r.ready
+  int need(Ready &r);         // the current build stream waits for something built on another build stream
   int wait_ready(Ready &r);   // first use on the compute stream: wait for r.ev
   bool is_ready(const Ready &r) { std::lock_guard<std::mutex> lk(mapMu); return r.ready; }
+  Grid *find_grid_wait(const long *sz);
+  ConvEntry *wait_conv(const long *inS, const long *f, const long *st);
+  void set_chain_done(bool v);
   std::map<P3, Grid> grids;
   std::map<SubmKey, SubmEntry> subm;   // submanifoldRuleBooks, Metadata.h:58-60
   std::map<ConvKey, ConvEntry> conv;   // ruleBooks, Metadata.h:65-67
   InputRules input;
-  std::vector<Chunk> chunks; // device memory of this Metadata (returned to the process-wide list on destruction)
-  // bump allocator over a few stream-ordered chunks: a Metadata makes ~350 small allocations per
-  // forward and frees them all together, and each cudaMallocAsync / cudaFreeAsync costs 3-5 us of host time
-  char *arena = nullptr;
-  size_t arenaCap = 0, arenaUsed = 0, arenaNext = 16u << 20;
-  // zero-initialised pool for scan states
-  unsigned long long *zpool = nullptr;
-  size_t zpoolWords = 0, zpoolUsed = 0;
-  int *d_scalars = nullptr; // small device scratch (64 ints)
-  int *h_scalars = nullptr; // pinned host mirror
-  int *d_err = nullptr;
 
   ~Metadata();
   int init();
   void *alloc(size_t bytes);
+  void *alloc_in(BuildCtx &c, size_t bytes);
   template <class T> T *alloc_n(size_t n) { return static_cast<T *>(alloc(n * sizeof(T) + 16)); }
   unsigned long long *scan_state(long n);
   int sync_scalars(int count);

@@ -63,3 +63,8 @@ for e in k[1:]:
 print("idle total %.2f ms in %d gaps; largest:" % (sum(g[0] for g in gaps) / 1e3, len(gaps)))
 for g in sorted(gaps, reverse=True)[:10]:
     print("   %.1f us before %s" % g)
+rt_sorted = sorted(rt, key=lambda e: -e["dur"])[:14]
+tmin = min(e["ts"] for e in rt)
+print("longest CUDA runtime calls:")
+for e in rt_sorted:
+    print("   tid %12d at %9.2f ms  %8.3f ms  %s" % (e["tid"], (e["ts"] - tmin) / 1e3, e["dur"] / 1e3, e["name"]))
