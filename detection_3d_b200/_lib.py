@@ -39,9 +39,9 @@ SYMBOLS = {
     "scn_rulebook_info": (_i, [_vp, _i, L3, L3, L3, _pi, _pl]),
     "scn_rulebook_copy": (_i, [_vp, _i, L3, L3, L3, _i, _vp]),
     "scn_iteration_order": (_i, [_vp, L3, _vp]),
-    "scn_submanifold_convolution_forward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp, C.c_longlong]),
-    "scn_convolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp, C.c_longlong]),
-    "scn_deconvolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp, C.c_longlong]),
+    "scn_submanifold_convolution_forward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp, C.c_longlong, _vp, _vp]),
+    "scn_convolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp, C.c_longlong, _vp, _vp]),
+    "scn_deconvolution_forward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _i, _i, _pd, _vp, C.c_longlong, _vp, _vp]),
     "scn_submanifold_convolution_backward": (_i, [_vp, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "scn_convolution_backward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "scn_deconvolution_backward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),

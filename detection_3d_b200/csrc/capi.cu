@@ -50,7 +50,8 @@ int conv_backward_simt(const float *in, float *d_in, const float *d_out, const f
 int tc_available();
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
-                        long nInRows, const void *in16, long long wTag, int CinW = 0);
+                        long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0);
+int to_bf16(const float *x, void *y, long n, cudaStream_t s);
 static int g_math_mode = 0;
 } // namespace scn
 
@@ -152,11 +153,25 @@ int scn_metadata_prefetch(scn_metadata *m, int n_ops, const long *ops) {
   // The strided convolutions create the grids level by level: that chain is the critical path, so it
   // gets a worker (and a build stream) of its own; submanifold plans and deconvolution plans only
   // hang off it and are built by a second worker on the second build context.
+  // A strided convolution is on the chain when something hangs off its OUTPUT grid; the z-collapsing
+  // convolutions at the end of the FPN are leaves and go to the second worker as well.
+  auto key3 = [](const long *v) { return (v[0] << 42) ^ (v[1] << 21) ^ v[2]; };
+  std::vector<long> usedAsInput;
+  for (int i = 0; i < n_ops; i++) usedAsInput.push_back(key3(ops + i * 13 + (ops[i * 13] == 3 ? 4 : 1)));
   for (int i = 0; i < n_ops; i++) {
     PrefetchOp op;
     for (int j = 0; j < 13; j++) op.v[j] = ops[i * 13 + j];
-    (m->md.nCtx >= 2 && op.v[0] != 2 ? m->ops2 : m->ops).push_back(op);
+    bool chain = op.v[0] == 2 && std::find(usedAsInput.begin(), usedAsInput.end(), key3(op.v + 4)) != usedAsInput.end();
+    (m->md.nCtx >= 2 && !chain ? m->ops2 : m->ops).push_back(op);
   }
+  // Second worker: shallow levels first.  Its entries become buildable as the chain worker descends
+  // (a submanifold plan needs its grid, a deconvolution plan the convolution that created the coarse
+  // grid); taken in request order it would sit on the deepest level's deconvolution plans while the
+  // shallow ones -- buildable long before -- queue behind them.
+  std::stable_sort(m->ops2.begin(), m->ops2.end(), [](const PrefetchOp &x, const PrefetchOp &y) {
+    auto fine = [](const PrefetchOp &o) { return o.v[0] == 3 ? o.v[4] : o.v[1]; }; // spatial size[0] of the (fine) grid the entry hangs off
+    return fine(x) > fine(y);
+  });
   m->stop = false;
   m->md.set_chain_done(false);
   m->worker = std::thread(prefetch_worker, m, 0);
@@ -299,37 +314,48 @@ int scn_iteration_order(scn_metadata *m, const long sz[3], int *dst) {
 static bool tc_ok(int Cin, int Cout, int K) {
   return scn::g_math_mode != 0 && scn::tc_available() && Cout % 32 == 0 && Cout >= 32 && Cout <= 256 && K <= 64 && Cin >= 4 && Cin <= 1024;
 }
+// out += addend (optional) and the bf16 copy of out (optional), for the paths whose kernels do not fuse them
+static int plain_epilogue(float *out, const float *addend, void *out16, long rows, int C, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  if (addend) return scn::add_rows(out, addend, out, rows * C, s, out16);
+  if (out16) return scn::to_bf16(out, out16, rows * C, s);
+  return 0;
+}
 static int run_plan(Metadata &M, const scn::NbrPlan &plan, const float *in, float *out, const float *w, const float *bias, int Cin, int Cout,
-                    long nInRows, const void *in16, long long wTag) {
+                    long nInRows, const void *in16, long long wTag, const float *addend, void *out16) {
   if (tc_ok(Cin, Cout, plan.K))
     return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.tileMask, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.cstream,
-                                    nullptr, plan.K, nInRows, in16, wTag);
-  return scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.cstream);
+                                    nullptr, plan.K, nInRows, in16, wTag, addend, out16, plan.nOut);
+  SCN_TRY(scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.cstream));
+  return plain_epilogue(out, addend, out16, plan.nOut, Cout, M.cstream);
 }
 
 int scn_submanifold_convolution_forward(scn_metadata *m, const long sz[3], const long f[3], const float *in, float *out, const float *w,
-                                        const float *bias, int Cin, int Cout, double *macs, const void *in_bf16, long long weight_tag) {
+                                        const float *bias, int Cin, int Cout, double *macs, const void *in_bf16, long long weight_tag,
+                                        const float *add_in, void *out_bf16) {
   M_OR_FAIL(m);
   scn::SubmEntry *e;
   SCN_TRY(m->md.get_submanifold(sz, f, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
   SCN_TRY(m->md.wait_ready(e->rdy));
-  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(sz)->n, in_bf16, weight_tag);
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(sz)->n, in_bf16, weight_tag, add_in, out_bf16);
 }
 int scn_convolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
-                            float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16, long long weight_tag) {
+                            float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16, long long weight_tag,
+                              const float *add_in, void *out_bf16) {
   M_OR_FAIL(m);
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
   if (macs) *macs = (double)e->rb.total * Cin * Cout;
   SCN_TRY(m->md.wait_ready(e->rdy));
-  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(inS)->n, in_bf16, weight_tag);
+  return run_plan(m->md, e->plan, in, out, w, bias, Cin, Cout, m->md.find_grid(inS)->n, in_bf16, weight_tag, add_in, out_bf16);
 }
 __global__ void k_fill_rows_bias(float *out, long n, int C, const float *bias) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n * C; i += (long)gridDim.x * blockDim.x) out[i] = bias ? bias[i % C] : 0.f;
 }
 int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
-                              float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16, long long weight_tag) {
+                              float *out, const float *w, const float *bias, int Cin, int Cout, double *macs, const void *in_bf16, long long weight_tag,
+                              const float *add_in, void *out_bf16) {
   M_OR_FAIL(m);
   // CPU/Deconvolution.cpp:15-16: the rulebook of the convolution outS -> inS
   scn::ConvEntry *e;
@@ -345,11 +371,12 @@ int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long out
     SCN_TRY(m->md.wait_ready(e->deconvRdy));
     const scn::DeconvPlan &d = e->deconv;
     return scn::launch_conv_plan_tc(in, out, w, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, 1, Cin, Cout, nullptr, scn::g_math_mode, s, d.tileW,
-                                    e->rb.nLists, m->md.find_grid(inS)->n, in_bf16, weight_tag);
+                                    e->rb.nLists, m->md.find_grid(inS)->n, in_bf16, weight_tag, add_in, out_bf16, gf->n);
   }
   SCN_TRY(m->md.wait_ready(e->rdy));
   if (!single && gf->n) k_fill_rows_bias<<<scn::stream_grid((long)gf->n * Cout, 256), 256, 0, scn::LS(s)>>>(out, gf->n, Cout, bias);
-  return scn::launch_conv_list_simt(in, out, w, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, Cin, Cout, /*srcIsY=*/1, single ? 1 : 0, s);
+  SCN_TRY(scn::launch_conv_list_simt(in, out, w, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, Cin, Cout, /*srcIsY=*/1, single ? 1 : 0, s));
+  return plain_epilogue(out, add_in, out_bf16, gf->n, Cout, s);
 }
 
 int scn_submanifold_convolution_backward(scn_metadata *m, const long sz[3], const long f[3], const float *in, float *d_in, const float *d_out,

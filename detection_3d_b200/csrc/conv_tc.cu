@@ -43,6 +43,8 @@ struct TcParams {
   float *out;
   const unsigned char *wimg;
   const float *bias;
+  const float *addend; // optional [output rows][Cout]: out = conv + addend (the residual / lateral add fused into the epilogue)
+  void *out16;         // optional bf16 copy of the result (gather operand of the next convolution in bf16 mode)
   const int *nbr;
   const int *outRow;
   const unsigned long long *tileMask;
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
       for (int t = 0; t < kMaxT; t++) {
         if (t >= P.T || I.st * P.T + t >= P.nTiles) continue;
         const bool started = I.m[t] != 0ull;
-        if (!started && P.kSplit > 1) continue; // nothing to add
+        if (!started && P.kSplit > 1 && !((P.addend || P.bias) && I.part == 0)) continue; // nothing to add
         int rows[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) rows[i] = __shfl_sync(0xffffffffu, myRow[t], i * 4 + rsub);
@@ -261,10 +263,30 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
             o[i] = *reinterpret_cast<const float4 *>(stg + (i * 4 + rsub) * 32 + (((lane & 7) ^ ((i * 4 + rsub) & 7)) << 2));
             o[i].x += bv.x; o[i].y += bv.y; o[i].z += bv.z; o[i].w += bv.w;
           }
+          if (P.addend && I.part == 0) {
+#pragma unroll
+            for (int h = 0; h < 8; h += 4) { // four 16-byte loads in flight per thread
+              float4 ad[4];
+#pragma unroll
+              for (int i = 0; i < 4; i++)
+                ad[i] = rows[h + i] >= 0 ? __ldg(reinterpret_cast<const float4 *>(P.addend + (size_t)rows[h + i] * P.Cout + c0 + cc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int i = 0; i < 4; i++) { o[h + i].x += ad[i].x; o[h + i].y += ad[i].y; o[h + i].z += ad[i].z; o[h + i].w += ad[i].w; }
+            }
+          }
           if (P.kSplit == 1) {
 #pragma unroll
             for (int i = 0; i < 8; i++)
-              if (rows[i] >= 0) *reinterpret_cast<float4 *>(P.out + (size_t)rows[i] * P.Cout + c0 + cc) = o[i];
+              if (rows[i] >= 0) {
+                *reinterpret_cast<float4 *>(P.out + (size_t)rows[i] * P.Cout + c0 + cc) = o[i];
+                if (P.out16) {
+                  __nv_bfloat162 lo = __floats2bfloat162_rn(o[i].x, o[i].y), hi = __floats2bfloat162_rn(o[i].z, o[i].w);
+                  uint2 pk;
+                  pk.x = *reinterpret_cast<unsigned int *>(&lo);
+                  pk.y = *reinterpret_cast<unsigned int *>(&hi);
+                  *reinterpret_cast<uint2 *>(static_cast<unsigned char *>(P.out16) + ((size_t)rows[i] * P.Cout + c0 + cc) * 2) = pk;
+                }
+              }
           } else { // offsets split over CTAs: accumulate into the launcher-zeroed output
 #pragma unroll
             for (int i = 0; i < 8; i++)
@@ -559,6 +581,12 @@ __global__ void __launch_bounds__(256) k_to_bf16(const float *__restrict__ x, ui
     y[i] = pk;
   }
 }
+int to_bf16(const float *x, void *y, long n, cudaStream_t s) {
+  SCN_CHECK(n % 4 == 0, "bf16 copy needs an element count that is a multiple of 4");
+  if (n) k_to_bf16<<<stream_grid(n / 4, 256), 256, 0, LS(s)>>>(x, static_cast<uint2 *>(y), n / 4);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
 // Grow-only scratch per stream for the operand copies a call may need (zero-padded rows of a narrow
 // input, bf16 copy of an input that arrived without one).  Uses on one stream are ordered, so one
 // buffer per stream suffices; cudaMallocAsync took milliseconds for these 150-300 MB blocks.
@@ -578,7 +606,7 @@ static int stream_scratch(cudaStream_t s, size_t bytes, void **out) {
 // in16: optional bf16 copy of `in` (same layout); used in math mode 2 when Cin is a multiple of 64
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
-                        long nInRows, const void *in16, long long wTag, int CinW = 0) {
+                        long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0) {
   if (nOut == 0) return 0;
   if (CinW == 0) CinW = Cin;
   if (Cin % 32 != 0) { // e.g. the 9-channel input convolution: rows zero-padded to 32 channels (the weight image pads itself)
@@ -586,7 +614,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     float *xp = nullptr;
     SCN_TRY(stream_scratch(s, (size_t)nInRows * Cp * 4 + 16, (void **)&xp));
     k_pad_rows<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
-    return launch_conv_plan_tc(xp, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr, wTag, Cin);
+    return launch_conv_plan_tc(xp, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr, wTag, addend, out16, nOutRows, Cin);
   }
   SCN_CHECK(Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && K <= 64, "tcgen05 path: unsupported channel counts");
   static int envT = -1, envS = -1, envDbg = 0, envProf = 0, envCtas = 0;
@@ -598,7 +626,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     envProf = getenv("SCN_TC_PROF") ? atoi(getenv("SCN_TC_PROF")) : 0;
   }
   TcParams P;
-  P.in = reinterpret_cast<const unsigned char *>(in); P.out = out; P.bias = bias; P.nbr = nbr; P.outRow = outRow; P.tileMask = tileMask; P.tileW = tileW;
+  P.in = reinterpret_cast<const unsigned char *>(in); P.out = out; P.bias = bias; P.addend = addend; P.out16 = out16; P.nbr = nbr; P.outRow = outRow; P.tileMask = tileMask; P.tileW = tileW;
   P.nOut = nOut; P.K = K; P.Cout = Cout;
   P.bf16 = (mathMode == 2 && Cin % 64 == 0) ? 1 : 0; // narrower layers keep TF32 operands (128-byte rows either way)
   void *tmp16 = nullptr;
@@ -677,6 +705,8 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
             ctas, grid, P.T, K, Cin, Cout, P.S, P.nAcc, P.kSplit, m[0], m[1], m[4], m[5], m[6], m[7], m[10], m[11], m[12], m[13], m[14], m[15], m[16], m[17]);
     cudaFreeAsync(P.prof, s);
   }
+  if (out16 && P.kSplit > 1 && nOutRows > 0) // partial sums were accumulated atomically: the bf16 copy needs the finished rows
+    k_to_bf16<<<stream_grid(nOutRows * Cout / 4, 256), 256, 0, LS(s)>>>(out, static_cast<uint2 *>(out16), nOutRows * Cout / 4);
   if (wimgOwned) cudaFreeAsync(wimg, s);
 
   return 0;

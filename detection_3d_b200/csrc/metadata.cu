@@ -640,7 +640,9 @@ struct BatchIn { const int4 *coords; int b; __device__ int operator()(long i) co
 struct BatchOut { int *seq; __device__ void operator()(long i, int pre, int v) const { if (v) seq[pre] = (int)i; } };
 
 int Metadata::ensure_rank(Grid &g) {
-  if (g.hasRank) return 0;
+  if (!claim(g.rankRdy)) return need(g.rankRdy); // built by another thread, possibly on the other build stream
+  struct Guard { Metadata &m; Ready &r; ~Guard() { if (!r.ready) m.unclaim(r); } } guard{*this, g.rankRdy};
+  SCN_TRY(need(g.rdy)); // (every caller already holds the lock of its build context)
   g.rank2id = alloc_n<int>(std::max(1, g.n));
   SCN_CHECK(g.rank2id, "alloc");
   int start = 0;
@@ -657,7 +659,7 @@ int Metadata::ensure_rank(Grid &g) {
     start += cnt;
   }
   g.hasRank = true;
-  return 0;
+  return mark_ready(g.rankRdy);
 }
 
 // ------------------------------------------------------------------ rule lists (shared machinery)

@@ -24,6 +24,7 @@ typedef std::array<long, 3> P3;
 struct Ready { bool ready = false, building = false; cudaEvent_t ev = nullptr; cudaStream_t by = nullptr; bool waited = false; };
 struct Grid {
   Ready rdy;          // active-site structures (directory, masks, numbering)
+  Ready rankRdy;      // rank2id (reference hash-iteration order)
   P3 sz{};            // spatial size
   int n = 0;          // active sites over all batch items (host copy)
   int batch = 1;

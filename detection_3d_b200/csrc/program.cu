@@ -92,11 +92,47 @@ int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, co
   op.kind = kind;
   for (int i = 0; i < 24; i++) op.a[i] = i < n_iargs ? iargs[i] : 0;
   for (int i = 0; i < 4; i++) op.f[i] = i < n_fargs ? fargs[i] : 0.0;
+  op.a[22] = -1; // register added in the epilogue of a convolution (set by the fusion pass of scn_program_finish)
   p->ops.push_back(op);
   return 0;
 }
 int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_outputs) {
   SCN_CHECK(p && n_regs > 0, "bad program");
+  { // Fuse `ADD(conv_out, other)` into the convolution's epilogue (out = conv + other, one kernel and one pass
+    // over the rows less): AddTable after a residual block, add_feature_planes after a Deconvolution.
+    auto out_of = [](const Op &o) -> long { return o.kind == K_INPUT ? o.a[0] : (o.kind == K_ADD ? o.a[2] : o.a[1]); };
+    std::vector<int> producer(n_regs, -1), consumers(n_regs, 0);
+    std::vector<char> isOut(n_regs, 0);
+    for (int i = 0; i < n_outputs; i++) if (outputs[i] >= 0 && outputs[i] < n_regs) isOut[outputs[i]] = 1;
+    for (int i = 0; i < (int)p->ops.size(); i++) {
+      const Op &o = p->ops[i];
+      long r = out_of(o);
+      SCN_CHECK(r >= 0 && r < n_regs, "register index");
+      producer[r] = i;
+      if (o.kind == K_ADD) { consumers[o.a[0]]++; consumers[o.a[1]]++; }
+      else if (o.kind != K_INPUT) consumers[o.a[0]]++;
+    }
+    std::vector<char> dead(p->ops.size(), 0);
+    for (int i = 0; i < (int)p->ops.size(); i++) {
+      Op &add = p->ops[i];
+      if (add.kind != K_ADD) continue;
+      const long ra = add.a[0], rb = add.a[1];
+      const int pa = producer[ra], pb = producer[rb];
+      if (pa < 0 || pb < 0 || pa == pb) continue;
+      const int host = std::max(pa, pb);               // the operand produced last; the other one exists by then
+      const long hostReg = host == pa ? ra : rb, other = host == pa ? rb : ra;
+      Op &h = p->ops[host];
+      if (h.kind != K_SUBM && h.kind != K_CONV && h.kind != K_DECONV) continue;
+      if (consumers[hostReg] != 1 || isOut[hostReg] || h.a[22] >= 0) continue;
+      h.a[22] = other;
+      h.a[1] = add.a[2]; // the convolution now writes the sum
+      producer[add.a[2]] = host;
+      dead[i] = 1;
+    }
+    std::vector<Op> kept;
+    for (int i = 0; i < (int)p->ops.size(); i++) if (!dead[i]) kept.push_back(p->ops[i]);
+    p->ops.swap(kept);
+  }
   p->nRegs = n_regs;
   p->lastUse.assign(n_regs, -1);
   p->isOutput.assign(n_regs, 0);
@@ -111,7 +147,11 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
     switch (op.kind) {
       case K_INPUT: SCN_TRY(use(op.a[0], i)); break;
       case K_ADD: SCN_TRY(use(op.a[0], i)); SCN_TRY(use(op.a[1], i)); SCN_TRY(use(op.a[2], i)); break;
-      default: SCN_TRY(use(op.a[0], i)); SCN_TRY(use(op.a[1], i)); break;
+      default:
+        SCN_TRY(use(op.a[0], i));
+        SCN_TRY(use(op.a[1], i));
+        if (op.kind != K_BN && op.a[22] >= 0) SCN_TRY(use(op.a[22], i));
+        break;
     }
   }
   for (int i = 0; i < n_outputs; i++) {
@@ -176,27 +216,33 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_SUBM: { // in, out, size[3], filter[3], w, bias, Cin, Cout
         long n = 0;
         rc = scn_get_nactive(m, a + 2, &n);
-        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], false);
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], a[22] >= 0);
         const Reg &I = p->regs[a[0]];
-        if (rc == 0) rc = scn_submanifold_convolution_forward(m, a + 2, a + 5, I.p, p->regs[a[1]].p, P(a[8]), P(a[9]), (int)a[10], (int)a[11], &mk, I.p16, T(a[8]));
+        if (rc == 0)
+          rc = scn_submanifold_convolution_forward(m, a + 2, a + 5, I.p, p->regs[a[1]].p, P(a[8]), P(a[9]), (int)a[10], (int)a[11], &mk, I.p16, T(a[8]),
+                                                   a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         macs += mk;
         break;
       }
       case K_CONV: { // in, out, inS[3], outS[3], f[3], s[3], w, bias, Cin, Cout
         long n = 0, nr = 0;
         rc = scn_convolution_prepare(m, a + 2, a + 5, a + 8, a + 11, &n, &nr);
-        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], false);
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0);
         const Reg &I = p->regs[a[0]];
-        if (rc == 0) rc = scn_convolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]));
+        if (rc == 0)
+          rc = scn_convolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]),
+                                       a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         macs += mk;
         break;
       }
       case K_DECONV: {
         long n = 0;
         rc = scn_get_nactive(m, a + 5, &n);
-        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], false);
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0);
         const Reg &I = p->regs[a[0]];
-        if (rc == 0) rc = scn_deconvolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]));
+        if (rc == 0)
+          rc = scn_deconvolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]),
+                                         a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         macs += mk;
         break;
       }

@@ -218,7 +218,7 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
     macs = C.c_double()
     check(lib().scn_submanifold_convolution_forward(m._h, l3(spatial_size), l3(filter_size), _dev_f32(input_features, "in"),
                                                     _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"),
-                                                    cin, cout, C.byref(macs), _shadow_ptr(input_features), _weight_tag(weight)))
+                                                    cin, cout, C.byref(macs), _shadow_ptr(input_features), _weight_tag(weight), None, None))
     tr = _tr()
     if tr is not None:
         tr.add(1, [tr.reg(input_features), tr.new_reg(output_features)] + _ints(spatial_size) + _ints(filter_size)
@@ -245,7 +245,7 @@ def Convolution_updateOutput(in_size, out_size, filter_size, filter_stride, m, i
     macs = C.c_double()
     check(lib().scn_convolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
                                         _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs),
-                                        _shadow_ptr(input_features), _weight_tag(weight)))
+                                        _shadow_ptr(input_features), _weight_tag(weight), None, None))
     tr = _tr()
     if tr is not None:
         tr.add(2, [tr.reg(input_features), tr.new_reg(output_features)] + _ints(in_size) + _ints(out_size) + _ints(filter_size)
@@ -271,7 +271,7 @@ def Deconvolution_updateOutput(in_size, out_size, filter_size, filter_stride, m,
     macs = C.c_double()
     check(lib().scn_deconvolution_forward(m._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), _dev_f32(input_features, "in"),
                                           _dev_f32(output_features, "out"), _dev_f32(weight, "weight"), _opt(bias, "bias"), cin, cout, C.byref(macs),
-                                          _shadow_ptr(input_features), _weight_tag(weight)))
+                                          _shadow_ptr(input_features), _weight_tag(weight), None, None))
     tr = _tr()
     if tr is not None:
         tr.add(3, [tr.reg(input_features), tr.new_reg(output_features)] + _ints(in_size) + _ints(out_size) + _ints(filter_size)

@@ -74,6 +74,31 @@ def _l(t):
     return [int(v) for v in (t.tolist() if hasattr(t, "tolist") else t)]
 
 
+def _hoist_pointwise(ops):
+    """Move every 1x1x1 SubmanifoldConvolution right behind the op that produces its input.  In the FPN
+    these are the lateral 'shortcut' convolutions: the network calls them in the top-down pass, but
+    they only depend on the bottom-up features, so they can run while the GPU waits for the deeper
+    levels' rulebooks instead of lengthening the tail of the forward.  Same op, same input: same result."""
+    ops = list(ops)
+    out = []
+    for op in ops:
+        kind, ints, _ = op
+        if kind == 1 and ints[5:8] == [1, 1, 1]:
+            src = ints[0]
+            pos = None
+            for j in range(len(out) - 1, -1, -1):
+                k2, i2, _f = out[j]
+                produced = i2[0] if k2 == 0 else (i2[2] if k2 == 5 else i2[1])
+                if produced == src:
+                    pos = j + 1
+                    break
+            if pos is not None:
+                out.insert(pos, op)
+                continue
+        out.append(op)
+    return out
+
+
 class Program(object):
     """A finished recording bound to the native executor."""
 
@@ -90,9 +115,10 @@ class Program(object):
                 raise RuntimeError("an output was not produced by a recorded layer")
             self.out_regs.append(r)
             self.out_sizes.append(size.clone())
+        ops = _hoist_pointwise(trace.ops)
         self._h = C.c_void_p()
         check(lib().scn_program_create(C.byref(self._h)))
-        for kind, ints, floats in trace.ops:
+        for kind, ints, floats in ops:
             ia = (C.c_long * len(ints))(*ints)
             fa = (C.c_double * max(1, len(floats)))(*floats) if floats else None
             check(lib().scn_program_add(self._h, kind, ia, len(ints), fa, len(floats)))

@@ -89,19 +89,25 @@ int scn_iteration_order(scn_metadata *m, const long spatial_size[3], int *dst);
  * only read in math mode 2, where a NULL makes the call convert `in` itself.
  * weight_tag: 0, or a value that identifies the CONTENTS of `weight` (same pointer + same tag =
  * same values as in an earlier call): the tensor-core paths then reuse the operand image they
- * derived from it (rounded, swizzled copy) instead of rebuilding it on every call. */
+ * derived from it (rounded, swizzled copy) instead of rebuilding it on every call.
+ * add_in: NULL, or [output rows][n_out] float32 added to the result (out = conv(in) + add_in): the
+ * residual / lateral AddTable that follows the convolution in the network, fused into its epilogue.
+ * out_bf16: NULL, or [output rows][n_out] bfloat16 that receives the (summed) result rounded to nearest. */
 int scn_submanifold_convolution_forward(scn_metadata *m, const long spatial_size[3], const long filter_size[3],
                                         const float *in, float *out, const float *weight, const float *bias,
-                                        int n_in, int n_out, double *macs, const void *in_bf16, long long weight_tag);
+                                        int n_in, int n_out, double *macs, const void *in_bf16, long long weight_tag,
+                                        const float *add_in, void *out_bf16);
 /* Convolution_updateOutput (pybind.cpp:54-59; CPU/Convolution.cpp:45-79) */
 int scn_convolution_forward(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
                             const long filter_stride[3], const float *in, float *out, const float *weight,
-                            const float *bias, int n_in, int n_out, double *macs, const void *in_bf16, long long weight_tag);
+                            const float *bias, int n_in, int n_out, double *macs, const void *in_bf16, long long weight_tag,
+                            const float *add_in, void *out_bf16);
 /* Deconvolution_updateOutput (pybind.cpp:78-83; CPU/Deconvolution.cpp:7-41): reuses the rulebook of the
  * Convolution out_size -> in_size with the pair columns swapped. */
 int scn_deconvolution_forward(scn_metadata *m, const long in_size[3], const long out_size[3], const long filter_size[3],
                               const long filter_stride[3], const float *in, float *out, const float *weight,
-                              const float *bias, int n_in, int n_out, double *macs, const void *in_bf16, long long weight_tag);
+                              const float *bias, int n_in, int n_out, double *macs, const void *in_bf16, long long weight_tag,
+                            const float *add_in, void *out_bf16);
 
 /* *_backward (pybind.cpp:60-65,84-89,139-143; CPU/Convolution.cpp:81-115,152-185; CPU/Deconvolution.cpp:43-77):
  * d_in [nIn rows][Cin] is overwritten, d_weight [K][Cin][Cout] is overwritten, d_bias NULL or [Cout]. */

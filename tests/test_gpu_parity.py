@@ -565,3 +565,46 @@ def test_recorded_program_matches_layer_by_layer(math):
         torch.cuda.synchronize()
     finally:
         scn.set_math_mode("fp32")
+
+
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+@pytest.mark.parametrize("big", [False, True])
+def test_fused_epilogue_add_and_bf16_copy(math, big):
+    """scn_submanifold_convolution_forward(..., add_in, out_bf16): out = conv(in) + add_in and the bf16
+    copy of the sum, fused into the epilogue.  Checked against the unfused calls (conv, then
+    scn_add_features) on a small level (filter offsets split over CTAs, atomic accumulation) and on a
+    level with more work items than SMs."""
+    import ctypes as C
+    import detection_3d_b200.sparseconvnet as scn
+    from detection_3d_b200._lib import l3, lib, check
+    _tc_or_skip(scn)
+    if big:
+        c = synthetic.building_coords(nx=300, ny=280, nz=40, n_walls=5, seed=5)
+        sz = [2048, 2048, 512]
+    else:
+        c = synthetic.small_building(40, 36, 12, 3, seed=4)
+        sz = [64, 64, 32]
+    G = _gpu()
+    n = G.input_layer(sz, c, 0, 4)
+    rs = np.random.RandomState(7)
+    x = torch.from_numpy(rs.randn(n, 64).astype(np.float32)).cuda()
+    w = torch.from_numpy((rs.randn(27, 1, 64, 128) * 0.03).astype(np.float32)).cuda()
+    r = torch.from_numpy(rs.randn(n, 128).astype(np.float32)).cuda()
+    L = torch.LongTensor
+    try:
+        scn.set_math_mode(math)
+        plain = torch.empty(0, device="cuda")
+        scn.SCN.SubmanifoldConvolution_updateOutput(L(sz), L([3] * 3), G.m, x, plain, w, torch.Tensor())
+        want = scn.SCN.add_features(plain, r)
+        fused = torch.empty(n, 128, device="cuda")
+        fused16 = torch.empty(n, 128, dtype=torch.bfloat16, device="cuda")
+        macs = C.c_double()
+        p = lambda t: C.c_void_p(t.data_ptr())
+        check(lib().scn_submanifold_convolution_forward(G.m._h, l3(sz), l3([3, 3, 3]), p(x), p(fused), p(w), None, 64, 128, C.byref(macs), None,
+                                                        C.c_longlong(0), p(r), p(fused16)))
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+    scale = max(1.0, float(want.abs().max()))
+    assert float((fused - want).abs().max()) <= 1e-5 * scale      # same products; only the order of the atomic sums may differ
+    assert torch.equal(fused16, fused.to(torch.bfloat16))
