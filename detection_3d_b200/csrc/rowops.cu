@@ -9,11 +9,50 @@
 
 namespace scn {
 
+// mode 0: train   -- BatchNormalization_ForwardPass train branch (SCN/CPU/BatchNormalization.cpp:19-40):
+//                    biased variance for normalisation, running stats updated with unbiased variance.
+// mode 1: eval with given running stats (:41-46).
+// mode 2: eval, track_running_stats=False -- sparseconvnet/batchNormalization.py:51-56: mean(0) and the
+//                    UNBIASED var(0) of this input stand in for the running stats.
+// (sum, sumsq) -> saveMean / saveInvStd and the fused scale / shift of  y = x*scale + shift.
+struct BnFin {
+  long n; int C, mode; float eps, momentum;
+  float *saveMean, *saveInvStd, *runningMean, *runningVar;
+  const float *weight, *bias;
+  float *scale, *shift;
+};
+__device__ __forceinline__ void bn_finalize_channel(const BnFin &F, int c, double sum, double sumsq) {
+  float mean, invstd;
+  if (F.mode == 1) {
+    mean = F.runningMean[c];
+    invstd = powf(F.runningVar[c] + F.eps, -0.5f);
+  } else {
+    double m = sum / (double)F.n;
+    double ss = sumsq - m * m * (double)F.n; // sum of squared deviations
+    if (ss < 0) ss = 0;
+    mean = (float)m;
+    if (F.mode == 0) {
+      F.runningMean[c] = F.momentum * F.runningMean[c] + (1 - F.momentum) * mean;
+      F.runningVar[c] = F.momentum * F.runningVar[c] + (1 - F.momentum) * (float)(ss / (double)(F.n - 1));
+      invstd = powf((float)(ss / (double)F.n) + F.eps, -0.5f);
+    } else {
+      invstd = powf((float)(ss / (double)(F.n - 1)) + F.eps, -0.5f);
+    }
+  }
+  F.saveMean[c] = mean;
+  F.saveInvStd[c] = invstd;
+  float w = invstd * (F.weight ? F.weight[c] : 1.f);
+  F.scale[c] = w;
+  F.shift[c] = -mean * w + (F.bias ? F.bias[c] : 0.f);
+}
 // ------------------------------------------------------------------ BN statistics
 // stats[0..C) = sum x, stats[C..2C) = sum x^2 (or sum of (x-shift)^2 terms), in double.
 // Each thread owns one float4 column group and strides over rows; per-CTA partials are reduced
 // in shared memory and added with one double atomic per channel per CTA.
-__global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, long n, int C, int rowsPerCta, double *__restrict__ stats) {
+// The CTA that finishes last (ticket) turns the sums into scale / shift and re-zeroes sums and ticket:
+// statistics + finalize are one launch.
+__global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, long n, int C, int rowsPerCta, double *__restrict__ stats,
+                                                  unsigned *ticket, BnFin F) {
   extern __shared__ float s_red[]; // [2][256][4]
   const int cv = C >> 2;           // float4 groups per row
   const int tid = threadIdx.x;
@@ -57,6 +96,73 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, l
       atomicAdd(stats + C + tid * 4 + j, b[j]);
     }
   }
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    volatile double *vs = stats;
+    for (int c = tid; c < C; c += 256) {
+      const double a = vs[c], b = vs[C + c];
+      bn_finalize_channel(F, c, a, b);
+      vs[c] = 0.0;
+      vs[C + c] = 0.0;
+    }
+    if (tid == 0) *ticket = 0u;
+  }
+}
+// One launch for small inputs: CTA b owns channels [32 b, 32 b + 32); statistics, scale / shift and the
+// normalised output (the rows come back out of L1/L2 for the second pass).
+__global__ void __launch_bounds__(256) k_bn_small(const float *__restrict__ x, float *__restrict__ y, int n, int C, BnFin F, float leak, void *__restrict__ y16) {
+  __shared__ float4 S[256], Q[256];
+  __shared__ float sScale[32], sShift[32];
+  const int tid = threadIdx.x, cgl = tid & 7, rl = tid >> 3; // 8 float4 column groups x 32 row lanes
+  const int cg = blockIdx.x * 8 + cgl, cv = C >> 2;
+  const bool live = cg < cv;
+  float4 s = make_float4(0, 0, 0, 0), q = make_float4(0, 0, 0, 0);
+  if (live && F.mode != 1)
+    for (int r = rl; r < n; r += 32) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(x + (long)r * C) + cg);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+    }
+  S[tid] = s; Q[tid] = q;
+  __syncthreads();
+  if (tid < 32) { // one thread per channel of this CTA
+    const int c = blockIdx.x * 32 + tid, g = tid >> 2, j = tid & 3;
+    if (c < C) {
+      double a = 0, b = 0;
+      for (int l = 0; l < 32; l++) {
+        const float4 u = S[l * 8 + g], w = Q[l * 8 + g];
+        a += j == 0 ? u.x : j == 1 ? u.y : j == 2 ? u.z : u.w;
+        b += j == 0 ? w.x : j == 1 ? w.y : j == 2 ? w.z : w.w;
+      }
+      bn_finalize_channel(F, c, a, b);
+      sScale[tid] = F.scale[c];
+      sShift[tid] = F.shift[c];
+    }
+  }
+  __syncthreads();
+  if (!live) return;
+  const float4 a = make_float4(sScale[cgl * 4], sScale[cgl * 4 + 1], sScale[cgl * 4 + 2], sScale[cgl * 4 + 3]);
+  const float4 b = make_float4(sShift[cgl * 4], sShift[cgl * 4 + 1], sShift[cgl * 4 + 2], sShift[cgl * 4 + 3]);
+  for (int r = rl; r < n; r += 32) {
+    const long i = (long)r * cv + cg;
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+    float4 o;
+    o.x = fmaf(v.x, a.x, b.x); o.y = fmaf(v.y, a.y, b.y); o.z = fmaf(v.z, a.z, b.z); o.w = fmaf(v.w, a.w, b.w);
+    o.x = o.x > 0 ? o.x : o.x * leak; o.y = o.y > 0 ? o.y : o.y * leak; o.z = o.z > 0 ? o.z : o.z * leak; o.w = o.w > 0 ? o.w : o.w * leak;
+    reinterpret_cast<float4 *>(y)[i] = o;
+    if (y16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<unsigned int *>(&lo);
+      pk.y = *reinterpret_cast<unsigned int *>(&hi);
+      reinterpret_cast<uint2 *>(y16)[i] = pk;
+    }
+  }
 }
 // scalar fallback for C % 4 != 0 (C <= 256)
 __global__ void __launch_bounds__(256) k_bn_stats_scalar(const float *__restrict__ x, long n, int C, int rowsPerCta, double *__restrict__ stats) {
@@ -78,42 +184,13 @@ __global__ void __launch_bounds__(256) k_bn_stats_scalar(const float *__restrict
   }
 }
 
-// mode 0: train   -- BatchNormalization_ForwardPass train branch (SCN/CPU/BatchNormalization.cpp:19-40):
-//                    biased variance for normalisation, running stats updated with unbiased variance.
-// mode 1: eval with given running stats (:41-46).
-// mode 2: eval, track_running_stats=False -- sparseconvnet/batchNormalization.py:51-56: mean(0) and the
-//                    UNBIASED var(0) of this input stand in for the running stats.
-// Emits saveMean/saveInvStd and the fused scale/shift  y = x*scale + shift.
-// Leaves `stats` zeroed for the next call (the forward workspace is persistent per stream and starts zeroed).
-__global__ void k_bn_finalize(double *__restrict__ stats, long n, int C, int mode, float eps, float momentum, float *saveMean,
-                              float *saveInvStd, float *runningMean, float *runningVar, const float *__restrict__ weight,
-                              const float *__restrict__ bias, float *scale, float *shift) {
+// standalone finalize: eval with running statistics (no sums needed) and the scalar-statistics path
+__global__ void k_bn_finalize(double *__restrict__ stats, BnFin F) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float mean, invstd;
-  if (mode == 1) {
-    mean = runningMean[c];
-    invstd = powf(runningVar[c] + eps, -0.5f);
-  } else {
-    double m = stats[c] / (double)n;
-    double ss = stats[C + c] - m * m * (double)n; // sum of squared deviations
-    stats[c] = 0.0;
-    stats[C + c] = 0.0;
-    if (ss < 0) ss = 0;
-    mean = (float)m;
-    if (mode == 0) {
-      runningMean[c] = momentum * runningMean[c] + (1 - momentum) * mean;
-      runningVar[c] = momentum * runningVar[c] + (1 - momentum) * (float)(ss / (double)(n - 1));
-      invstd = powf((float)(ss / (double)n) + eps, -0.5f);
-    } else {
-      invstd = powf((float)(ss / (double)(n - 1)) + eps, -0.5f);
-    }
-  }
-  saveMean[c] = mean;
-  saveInvStd[c] = invstd;
-  float w = invstd * (weight ? weight[c] : 1.f);
-  scale[c] = w;
-  shift[c] = -mean * w + (bias ? bias[c] : 0.f);
+  if (c >= F.C) return;
+  double a = 0, b = 0;
+  if (F.mode != 1) { a = stats[c]; b = stats[F.C + c]; stats[c] = 0.0; stats[F.C + c] = 0.0; }
+  bn_finalize_channel(F, c, a, b);
 }
 
 // y = leaky(x*scale + shift)   (:53-61)
@@ -147,31 +224,35 @@ __global__ void __launch_bounds__(256) k_bn_apply_scalar(const float *__restrict
   }
 }
 
-static int bn_stats_launch(const float *x, long n, int C, double *stats, cudaStream_t s) {
-  if (n == 0) return 0;
-  int rowsPerCta = (int)std::max<long>(64, (n + kSMs * 8 - 1) / (kSMs * 8)); // <= 8 CTAs per SM: few atomics per channel
-  int grid = cdiv(n, rowsPerCta);
-  if (C % 4 == 0) {
-    SCN_CHECK(C / 4 <= 256, "BatchNorm: more than 1024 channels not supported");
-    k_bn_stats<<<grid, 256, 2 * 256 * 16, LS(s)>>>(x, n, C, rowsPerCta, stats);
-  } else {
-    SCN_CHECK(C <= 256, "BatchNorm: channel count not a multiple of 4 must be <= 256");
-    k_bn_stats_scalar<<<grid, 256, 0, LS(s)>>>(x, n, C, rowsPerCta, stats);
-  }
-  SCN_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// workspace: 2*kBnMaxC doubles (zero on entry, zero again on exit) + 2*kBnMaxC floats
+// workspace: 2*kBnMaxC doubles (zero on entry, zero again on exit) + 2*kBnMaxC floats (scale, shift) + a ticket (zero)
 int bn_forward(const float *x, float *y, long n, int C, float *saveMean, float *saveInvStd, float *runningMean, float *runningVar,
                const float *weight, const float *bias, float eps, float momentum, int mode, float leak, void *workspace, cudaStream_t s, void *y16) {
   double *stats = static_cast<double *>(workspace);
   float *scale = reinterpret_cast<float *>(stats + 2 * kBnMaxC), *shift = scale + kBnMaxC; // fixed layout: the statistics area stays zero between calls
-  if (mode != 1) SCN_TRY(bn_stats_launch(x, n, C, stats, s));
-  k_bn_finalize<<<cdiv(C, 128), 128, 0, LS(s)>>>(stats, n, C, mode, eps, momentum, saveMean, saveInvStd, runningMean, runningVar, weight, bias, scale, shift);
+  unsigned *ticket = reinterpret_cast<unsigned *>(shift + kBnMaxC);
+  BnFin F{n, C, mode, eps, momentum, saveMean, saveInvStd, runningMean, runningVar, weight, bias, scale, shift};
+  SCN_CHECK(!y16 || C % 4 == 0, "bf16 shadow needs a channel count that is a multiple of 4");
+  if (C % 4 == 0 && n > 0 && n <= 2048) { // small levels: statistics, finalize and apply in ONE launch
+    k_bn_small<<<cdiv(C, 32), 256, 0, LS(s)>>>(x, y, (int)n, C, F, leak, y16);
+    SCN_CUDA(cudaGetLastError());
+    return 0;
+  }
+  bool finalized = false;
+  if (mode != 1 && n > 0) {
+    int rowsPerCta = (int)std::max<long>(64, (n + kSMs * 8 - 1) / (kSMs * 8)); // <= 8 CTAs per SM: few atomics per channel
+    int grid = cdiv(n, rowsPerCta);
+    if (C % 4 == 0) {
+      SCN_CHECK(C / 4 <= 256, "BatchNorm: more than 1024 channels not supported");
+      k_bn_stats<<<grid, 256, 2 * 256 * 16, LS(s)>>>(x, n, C, rowsPerCta, stats, ticket, F); // last CTA finalizes
+      finalized = true;
+    } else {
+      SCN_CHECK(C <= 256, "BatchNorm: channel count not a multiple of 4 must be <= 256");
+      k_bn_stats_scalar<<<grid, 256, 0, LS(s)>>>(x, n, C, rowsPerCta, stats);
+    }
+  }
+  if (!finalized) k_bn_finalize<<<cdiv(C, 128), 128, 0, LS(s)>>>(stats, F);
   if (n) {
     long total = n * C;
-    SCN_CHECK(!y16 || C % 4 == 0, "bf16 shadow needs a channel count that is a multiple of 4");
     if (C % 4 == 0) k_bn_apply<<<stream_grid(total / 4, 256), 256, 0, LS(s)>>>(x, y, total / 4, C / 4, scale, shift, leak, y16);
     else k_bn_apply_scalar<<<stream_grid(total, 256), 256, 0, LS(s)>>>(x, y, total, C, scale, shift, leak);
   }
