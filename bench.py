@@ -194,9 +194,11 @@ def main():
 
     def step_e2e():
         with torch.no_grad():
-            c = coords_pin.to(dev, non_blocking=True)
+            # the reference's calling convention: coordinates stay a host LongTensor (ioLayers.py:60), features go
+            # to the device; the library copies the pinned coordinates on its build stream while the feature copy
+            # runs on the caller's stream
             f = feats_pin.to(dev, non_blocking=True)
-            rpn, roi = net([c, f])
+            rpn, roi = net([coords_pin, f])
             host = [m.features.to("cpu", non_blocking=True) for m in rpn + roi]
         return host
 

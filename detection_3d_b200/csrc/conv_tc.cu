@@ -50,7 +50,7 @@ struct TcParams {
   const unsigned long long *tileMask;
   const int *tileW; // optional: weight slice per tile (deconvolution plans; then K == 1 and T == 1)
   long long *prof;  // developer: per-CTA stall counters (SCN_TC_PROF)
-  int nOut, K, Cout, nTiles, T, nSuper, S, nAcc;
+  int nOut, K, Cout, nTiles, T, nSuper, S, nAcc, lag;
   int rowBytes, nAtoms, bf16, tmemCols;
   int dbg;    // developer switches (SCN_TC_DBG): 1 = skip A gathers, 2 = skip B copies, 4 = skip MMAs
   int kSplit; // > 1: the filter offsets of a work item are split over kSplit CTAs, epilogue accumulates atomically
@@ -88,6 +88,9 @@ __device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long 
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t srcBytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(srcBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
   uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 2);
 
   if (tid == 0) {
-    for (int i = 0; i < P.S; i++) { mbar_init(smem_u32(full + i), kProdWarps + 1); mbar_init(smem_u32(empty + i), 1); }
+    for (int i = 0; i < P.S; i++) { mbar_init(smem_u32(full + i), kProdWarps * 32 + 1); mbar_init(smem_u32(empty + i), 1); }
     for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -311,8 +314,6 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
     const int pw = warp - 4;
     const int chunk = lane & 7, rsub = lane >> 3;
     uint32_t n = 0, slot = 0, round = 0; // stage counter, ring slot, ring round
-    int pendSlot = -1;    // stage issued but not yet published (only when the ring has >= 3 slots)
-    const bool lag = P.S >= 3;
     for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
       const Item I = load_item(P, wi);
       if (!I.uni) continue;
@@ -347,35 +348,17 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
               }
             }
           }
-          cp_async_commit();
-          if (lag) {
-            if (pendSlot >= 0) {
-              long long t0 = prof ? clock64() : 0;
-              cp_async_wait<1>();
-              if (prof) pw1 += clock64() - t0;
-              fence_proxy_async();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(full + pendSlot));
-            }
-            pendSlot = (int)slot;
-          } else {
-            long long t0 = prof ? clock64() : 0;
-            cp_async_wait<0>();
-            if (prof) pw1 += clock64() - t0;
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(full + slot));
-          }
+          // The stage's full barrier receives this thread's arrival when its copies above have landed
+          // (cp.async.mbarrier.arrive.noinc): no wait_group, no fence, the warp moves on to the next free
+          // slot at once.  Same hand-off as CUTLASS's sm100 cp.async -> UMMA mainloop
+          // (sm100_mma_cpasync_warpspecialized.hpp), which issues tcgen05.mma right after the barrier wait.
+          // Measured before: a warp that waited (cp.async.wait_group + fence.proxy.async, i.e. MEMBAR.ALL.CTA)
+          // drained ALL its copies at every stage, so deeper rings bought nothing.
+          cp_async_mbar_arrive_noinc(smem_u32(full + slot));
           if (++slot == (uint32_t)P.S) { slot = 0; round++; }
         }
         k = kNext;
       }
-    }
-    if (pendSlot >= 0) {
-      cp_async_wait<0>();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(full + pendSlot));
     }
     if (prof && lane == 0 && pw == 0) { long long *q = P.prof + blockIdx.x * 32 + 4; q[0] = clock64() - tStart; q[1] = pw0; q[2] = pw1; q[3] = n; }
   } else if (warp == kMmaWarp) {
@@ -667,6 +650,10 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   const size_t stageBytes = (size_t)P.T * kAtomBytes + (size_t)Cout * 128;
   P.S = (int)std::min<size_t>(envS > 0 ? envS : 6, (smemBudget - fixed) / stageBytes);
   SCN_CHECK(P.S >= 2, "tcgen05 path: shared memory budget exceeded");
+  static int envLag = -2;
+  if (envLag == -2) envLag = getenv("SCN_TC_LAG") ? atoi(getenv("SCN_TC_LAG")) : -1;
+  P.lag = std::max(0, std::min(3, envLag >= 0 ? envLag : P.S - 2));
+  if (P.lag > P.S - 2) P.lag = std::max(0, P.S - 2);
   const size_t smem = (size_t)P.S * stageBytes + fixed;
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
   unsigned char *wimg = nullptr;
@@ -681,7 +668,9 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
     attr = true;
   }
-  const int grid = std::min(P.nSuper * P.kSplit, kSMs * ctas);
+  static int envSms = -1;
+  if (envSms < 0) envSms = getenv("SCN_TC_SMS") ? atoi(getenv("SCN_TC_SMS")) : kSMs;
+  const int grid = std::min(P.nSuper * P.kSplit, std::min(kSMs, envSms) * ctas);
   P.prof = nullptr;
   if (envProf) {
     SCN_CUDA(cudaMallocAsync((void **)&P.prof, 2 * kSMs * 32 * 8, s));

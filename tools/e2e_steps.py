@@ -28,10 +28,9 @@ with torch.no_grad():
         t0 = time.perf_counter()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        cc = coords_pin.to(dev, non_blocking=True)
         ff = feats_pin.to(dev, non_blocking=True)
         t1 = time.perf_counter()
-        rpn, roi = net([cc, ff])
+        rpn, roi = net([coords_pin if len(sys.argv) < 3 else coords_pin.to(dev, non_blocking=True), ff])
         t2 = time.perf_counter()
         host = [m.features.to("cpu", non_blocking=True) for m in rpn + roi]
         b.record()
