@@ -425,8 +425,8 @@ int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *sav
     std::lock_guard<std::mutex> lk(mu);
     for (auto &e : cache) if (e.first == s) ws = e.second;
     if (!ws) {
-      SCN_CUDA(cudaMalloc(&ws, (size_t)kMaxC * 24 + 64));
-      SCN_CUDA(cudaMemset(ws, 0, (size_t)kMaxC * 24 + 64));
+      SCN_CUDA(cudaMalloc(&ws, scn::kBnWorkspaceBytes));
+      SCN_CUDA(cudaMemset(ws, 0, scn::kBnWorkspaceBytes));
       cache.emplace_back(s, ws);
     }
   }

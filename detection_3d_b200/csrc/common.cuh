@@ -48,7 +48,10 @@ static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 // B200: 148 SMs.  Element-wise / streaming kernels use grid-stride loops over a grid that is
 // a multiple of the SM count.
 constexpr int kSMs = 148;
-constexpr int kBnMaxC = 4096; // BatchNorm forward workspace: 2*kBnMaxC doubles (statistics) + 2*kBnMaxC floats (scale, shift)
+constexpr int kBnMaxC = 4096; // BatchNorm forward workspace: kBnReplicas x 2*kBnMaxC doubles (statistics) + 2*kBnMaxC floats (scale, shift)
+constexpr int kBnReplicas = 8;
+constexpr int kFusedStatsC = 128; // channel stride of the statistics a convolution epilogue accumulates: [kBnReplicas][2][kFusedStatsC] doubles
+constexpr size_t kBnWorkspaceBytes = (size_t)kBnReplicas * 2 * kBnMaxC * 8 + 2 * kBnMaxC * 4 + 64;
 static inline int stream_grid(long n, int threads, int per_sm = 8) {
   long want = (n + threads - 1) / threads;
   long cap = (long)kSMs * per_sm;

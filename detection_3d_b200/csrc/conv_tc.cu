@@ -49,6 +49,7 @@ struct TcParams {
   const int *outRow;
   const unsigned long long *tileMask;
   const int *tileW; // optional: weight slice per tile (deconvolution plans; then K == 1 and T == 1)
+  double *stats;    // optional [kBnReplicas][2][kFusedStatsC]: per-channel sum / sum of squares of `out` (statistics of a following BatchNorm)
   long long *prof;  // developer: per-CTA stall counters (SCN_TC_PROF)
   int nOut, K, Cout, nTiles, T, nSuper, S, nAcc, lag;
   int rowBytes, nAtoms, bf16, tmemCols;
@@ -224,6 +225,7 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
     // padded shared-memory block -> each store instruction writes four whole 128-byte row segments.
     float *stg = sEpi + warp * (32 * 32);
     const int cc = (lane & 7) * 4, rsub = lane >> 3;
+    float4 sAcc = make_float4(0.f, 0.f, 0.f, 0.f), qAcc = sAcc; // column sums of the 32-column block this lane group owns (block == rsub)
     int it = 0;
     for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
       const Item I = load_item(P, wi);
@@ -277,6 +279,26 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
               for (int i = 0; i < 4; i++) { o[h + i].x += ad[i].x; o[h + i].y += ad[i].y; o[h + i].z += ad[i].z; o[h + i].w += ad[i].w; }
             }
           }
+          if (P.stats) { // launcher guarantees kSplit == 1 and Cout <= 128: o[] holds final output values
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              if (rows[i] >= 0) {
+                s4.x += o[i].x; s4.y += o[i].y; s4.z += o[i].z; s4.w += o[i].w;
+                q4.x = fmaf(o[i].x, o[i].x, q4.x); q4.y = fmaf(o[i].y, o[i].y, q4.y); q4.z = fmaf(o[i].z, o[i].z, q4.z); q4.w = fmaf(o[i].w, o[i].w, q4.w);
+              }
+#pragma unroll
+            for (int d = 8; d <= 16; d <<= 1) { // the 4 lanes that hold the same columns (rsub = 0..3)
+              s4.x += __shfl_xor_sync(0xffffffffu, s4.x, d); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, d);
+              s4.z += __shfl_xor_sync(0xffffffffu, s4.z, d); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, d);
+              q4.x += __shfl_xor_sync(0xffffffffu, q4.x, d); q4.y += __shfl_xor_sync(0xffffffffu, q4.y, d);
+              q4.z += __shfl_xor_sync(0xffffffffu, q4.z, d); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, d);
+            }
+            if (rsub == (c0 >> 5)) {
+              sAcc.x += s4.x; sAcc.y += s4.y; sAcc.z += s4.z; sAcc.w += s4.w;
+              qAcc.x += q4.x; qAcc.y += q4.y; qAcc.z += q4.z; qAcc.w += q4.w;
+            }
+          }
           if (P.kSplit == 1) {
 #pragma unroll
             for (int i = 0; i < 8; i++)
@@ -303,6 +325,15 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(accEmpty + a));
+    }
+    if (P.stats) { // one double atomic per (warp, channel) into one of kBnReplicas accumulators
+      const int c = rsub * 32 + cc;
+      if (c < P.Cout) {
+        double *rep = P.stats + (size_t)(blockIdx.x % kBnReplicas) * 2 * kFusedStatsC;
+        atomicAdd(rep + c, (double)sAcc.x); atomicAdd(rep + c + 1, (double)sAcc.y); atomicAdd(rep + c + 2, (double)sAcc.z); atomicAdd(rep + c + 3, (double)sAcc.w);
+        rep += kFusedStatsC;
+        atomicAdd(rep + c, (double)qAcc.x); atomicAdd(rep + c + 1, (double)qAcc.y); atomicAdd(rep + c + 2, (double)qAcc.z); atomicAdd(rep + c + 3, (double)qAcc.w);
+      }
     }
     if (prof && tid == 0) { P.prof[blockIdx.x * 32 + 0] = clock64() - tStart; P.prof[blockIdx.x * 32 + 1] = pw0; }
   } else if (warp < 4 + kProdWarps) {
@@ -586,6 +617,13 @@ static int stream_scratch(cudaStream_t s, size_t bytes, void **out) {
   *out = e.first;
   return 0;
 }
+// Side channel used by the program executor (program.cu): the next tensor-core convolution launched by THIS thread
+// also accumulates the per-channel sum / sum of squares of its output into `sums` (zeroed by the caller) when its
+// configuration allows it; epilogue_stats_take() says whether it did and disarms the request.
+static thread_local double *tl_stats = nullptr;
+static thread_local bool tl_stats_done = false;
+void epilogue_stats_arm(double *sums) { tl_stats = sums; tl_stats_done = false; }
+bool epilogue_stats_take() { bool d = tl_stats_done; tl_stats = nullptr; tl_stats_done = false; return d; }
 // in16: optional bf16 copy of `in` (same layout); used in math mode 2 when Cin is a multiple of 64
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
@@ -647,6 +685,9 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   P.nSuper = cdiv(P.nTiles, P.T);
   P.kSplit = 1;
   if (P.nSuper < kSMs * ctas / 2 && !tileW) P.kSplit = std::max(1, std::min(K, kSMs * ctas / P.nSuper));
+  P.stats = nullptr;
+  if (tl_stats && P.kSplit == 1 && Cout <= kFusedStatsC && Cout % 32 == 0) { P.stats = tl_stats; tl_stats_done = true; }
+  tl_stats = nullptr;
   const size_t stageBytes = (size_t)P.T * kAtomBytes + (size_t)Cout * 128;
   P.S = (int)std::min<size_t>(envS > 0 ? envS : 6, (smemBudget - fixed) / stageBytes);
   SCN_CHECK(P.S >= 2, "tcgen05 path: shared memory budget exceeded");

@@ -9,6 +9,13 @@
 #include "common.cuh"
 #include <vector>
 
+namespace scn {
+void epilogue_stats_arm(double *sums);
+bool epilogue_stats_take();
+int bn_forward_from_sums(const float *x, float *y, long n, int C, const double *sums, float *saveMean, float *saveInvStd, float *runningMean,
+                         float *runningVar, const float *weight, const float *bias, float eps, float momentum, int mode, float leak, cudaStream_t s, void *y16);
+} // namespace scn
+
 namespace {
 
 enum Kind { K_INPUT = 0, K_SUBM = 1, K_CONV = 2, K_DECONV = 3, K_BN = 4, K_ADD = 5 };
@@ -39,6 +46,9 @@ struct scn_program {
   std::vector<char> isOutput;
   std::vector<Reg> regs;
   float *bnScratch = nullptr;   // saveMean / saveInvStd of inference-mode BatchNorm (unused downstream)
+  int nStats = 0;               // convolutions whose epilogue accumulates the statistics of the BatchNorm that follows
+  double *stats = nullptr;      // nStats x [kBnReplicas][2][kFusedStatsC], zeroed at the start of every run
+  std::vector<char> statsDone;
   cudaStream_t stream = nullptr;
 };
 
@@ -84,6 +94,7 @@ void scn_program_destroy(scn_program *p) {
   cudaDeviceSynchronize();
   for (Slot &s : p->slots) cudaFree(s.p);
   if (p->bnScratch) cudaFree(p->bnScratch);
+  if (p->stats) cudaFree(p->stats);
   delete p;
 }
 int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, const double *fargs, int n_fargs) {
@@ -92,6 +103,7 @@ int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, co
   op.kind = kind;
   for (int i = 0; i < 24; i++) op.a[i] = i < n_iargs ? iargs[i] : 0;
   for (int i = 0; i < 4; i++) op.f[i] = i < n_fargs ? fargs[i] : 0.0;
+  op.a[21] = -1; // statistics slot shared by a convolution and the BatchNorm ops that read its output (scn_program_finish)
   op.a[22] = -1; // register added in the epilogue of a convolution (set by the fusion pass of scn_program_finish)
   p->ops.push_back(op);
   return 0;
@@ -132,6 +144,24 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
     std::vector<Op> kept;
     for (int i = 0; i < (int)p->ops.size(); i++) if (!dead[i]) kept.push_back(p->ops[i]);
     p->ops.swap(kept);
+  }
+  { // BatchNorm statistics in the producing convolution's epilogue: BN(conv_out) with batch statistics (modes 0 / 2)
+    // reads per-channel sums the convolution kernel accumulated while it still held the output values, and runs
+    // only its apply pass.  Whether a given convolution launch can do it (tensor-core path, no offset splitting,
+    // <= 128 channels) is decided at run time; otherwise the BatchNorm computes its own statistics as before.
+    auto out_of = [](const Op &o) -> long { return o.kind == K_INPUT ? o.a[0] : (o.kind == K_ADD ? o.a[2] : o.a[1]); };
+    std::vector<int> producer(n_regs, -1);
+    for (int i = 0; i < (int)p->ops.size(); i++) producer[out_of(p->ops[i])] = i;
+    p->nStats = 0;
+    for (Op &bn : p->ops) {
+      if (bn.kind != K_BN || bn.a[7] == 1 || bn.a[2] > scn::kFusedStatsC || bn.a[2] % 32 != 0) continue;
+      const int j = producer[bn.a[0]];
+      if (j < 0) continue;
+      Op &c = p->ops[j];
+      if (c.kind != K_SUBM && c.kind != K_CONV && c.kind != K_DECONV) continue;
+      if (c.a[21] < 0) c.a[21] = p->nStats++;
+      bn.a[21] = c.a[21];
+    }
   }
   p->nRegs = n_regs;
   p->lastUse.assign(n_regs, -1);
@@ -186,6 +216,14 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     }
     return 0;
   };
+  const size_t statsStride = (size_t)scn::kBnReplicas * 2 * scn::kFusedStatsC;
+  if (p->nStats) {
+    if (!p->stats) SCN_CUDA(cudaMalloc((void **)&p->stats, p->nStats * statsStride * sizeof(double)));
+    SCN_CUDA(cudaMemsetAsync(p->stats, 0, p->nStats * statsStride * sizeof(double), s));
+    p->statsDone.assign(p->nStats, 0);
+  }
+  auto arm = [&](const Op &op) { if (op.a[21] >= 0) scn::epilogue_stats_arm(p->stats + op.a[21] * statsStride); };
+  auto took = [&](const Op &op) { const bool d = scn::epilogue_stats_take(); if (op.a[21] >= 0) p->statsDone[op.a[21]] = d; };
   double macs = 0, mk = 0;
   int rc = 0;
   for (int i = 0; i < (int)p->ops.size() && rc == 0; i++) {
@@ -218,9 +256,11 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
         rc = scn_get_nactive(m, a + 2, &n);
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], a[22] >= 0);
         const Reg &I = p->regs[a[0]];
+        if (rc == 0) arm(op);
         if (rc == 0)
           rc = scn_submanifold_convolution_forward(m, a + 2, a + 5, I.p, p->regs[a[1]].p, P(a[8]), P(a[9]), (int)a[10], (int)a[11], &mk, I.p16, T(a[8]),
                                                    a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
+        took(op);
         macs += mk;
         break;
       }
@@ -229,9 +269,11 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
         rc = scn_convolution_prepare(m, a + 2, a + 5, a + 8, a + 11, &n, &nr);
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0);
         const Reg &I = p->regs[a[0]];
+        if (rc == 0) arm(op);
         if (rc == 0)
           rc = scn_convolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]),
                                        a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
+        took(op);
         macs += mk;
         break;
       }
@@ -240,15 +282,23 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
         rc = scn_get_nactive(m, a + 5, &n);
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0);
         const Reg &I = p->regs[a[0]];
+        if (rc == 0) arm(op);
         if (rc == 0)
           rc = scn_deconvolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]),
                                          a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
+        took(op);
         macs += mk;
         break;
       }
       case K_BN: { // in, out, C, weight, bias, running mean, running var, mode; f: eps, momentum, leakiness
         const Reg &I = p->regs[a[0]];
         rc = alloc_reg(a[1], I.rows, (int)a[2], true);
+        if (rc == 0 && a[21] >= 0 && p->statsDone[a[21]] && I.rows > 0) {
+          rc = scn::bn_forward_from_sums(I.p, p->regs[a[1]].p, I.rows, (int)a[2], p->stats + a[21] * statsStride, p->bnScratch, p->bnScratch + scn::kBnMaxC,
+                                         const_cast<float *>(P(a[5])), const_cast<float *>(P(a[6])), P(a[3]), P(a[4]), (float)op.f[0], (float)op.f[1], (int)a[7],
+                                         (float)op.f[2], s, p->regs[a[1]].p16);
+          break;
+        }
         if (rc == 0)
           rc = scn_batchnorm_forward(I.p, p->regs[a[1]].p, I.rows, (int)a[2], p->bnScratch, p->bnScratch + scn::kBnMaxC, const_cast<float *>(P(a[5])),
                                      const_cast<float *>(P(a[6])), P(a[3]), P(a[4]), (float)op.f[0], (float)op.f[1], (int)a[7], (float)op.f[2], s, p->regs[a[1]].p16);
