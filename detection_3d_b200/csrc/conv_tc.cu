@@ -53,6 +53,7 @@ struct TcParams {
   long long *prof;  // developer: per-CTA stall counters (SCN_TC_PROF)
   int nOut, K, Cout, nTiles, T, nSuper, S, nAcc, lag;
   int rowBytes, nAtoms, bf16, tmemCols;
+  int KG;     // packed layers (template G > 1): number of offset groups = ceil(K / G)
   int dbg;    // developer switches (SCN_TC_DBG): 1 = skip A gathers, 2 = skip B copies, 4 = skip MMAs
   int kSplit; // > 1: the filter offsets of a work item are split over kSplit CTAs, epilogue accumulates atomically
 };
@@ -163,16 +164,27 @@ struct Item {
   int st, part;
   unsigned long long m[kMaxT], uni;
 };
+// G > 1 (packed layers, rows of 128 / G bytes): G consecutive filter offsets share one 128-byte K atom.  The
+// masks then carry one bit per GROUP, kept at bit position G * group (so that `k` in the role loops is the first
+// offset of the group); a group is live when any of its offsets is.
+template <int G>
+__device__ __forceinline__ unsigned long long group_mask(unsigned long long m) {
+  if (G == 2) return (m | (m >> 1)) & 0x5555555555555555ull;
+  if (G == 4) return (m | (m >> 1) | (m >> 2) | (m >> 3)) & 0x1111111111111111ull;
+  return m;
+}
+template <int G>
 __device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
   Item I;
   I.st = wi / P.kSplit;
   I.part = wi - I.st * P.kSplit;
-  const unsigned long long kmask = range_mask(P.K * I.part / P.kSplit, P.K * (I.part + 1) / P.kSplit);
+  const int nG = G > 1 ? P.KG : P.K; // split whole groups over the CTAs of an item
+  const unsigned long long kmask = range_mask(G * (nG * I.part / P.kSplit), G * (nG * (I.part + 1) / P.kSplit));
   I.uni = 0;
 #pragma unroll
   for (int t = 0; t < kMaxT; t++) {
     const int tile = I.st * P.T + t;
-    I.m[t] = (t < P.T && tile < P.nTiles) ? (__ldg(P.tileMask + tile) & kmask) : 0ull;
+    I.m[t] = (t < P.T && tile < P.nTiles) ? (group_mask<G>(__ldg(P.tileMask + tile)) & kmask) : 0ull;
     I.uni |= I.m[t];
   }
   return I;
@@ -185,8 +197,9 @@ __device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
 // PW = producer warps: 8 with one CTA per SM (all 512 TMEM columns), 4 with two CTAs per SM (256
 // columns and half the shared memory each): two independent pipelines per SM hide each other's
 // barrier hand-offs.
-template <bool BF16, int PW>
+template <bool BF16, int PW, int G>
 __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_plan_tc(const TcParams P) {
+  constexpr int TM = G == 4 ? 2 : kMaxT; // tiles per item the producers keep neighbour ids for (G ids per row and tile)
   constexpr int kProdWarps = PW;
   constexpr int kRowsPerWarp = kTileM / PW; // rows of a tile one producer warp gathers
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -228,7 +241,7 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
     float4 sAcc = make_float4(0.f, 0.f, 0.f, 0.f), qAcc = sAcc; // column sums of the 32-column block this lane group owns (block == rsub)
     int it = 0;
     for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
-      const Item I = load_item(P, wi);
+      const Item I = load_item<G>(P, wi);
       const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
       int myRow[kMaxT]; // output row of (tile t, TMEM lane), fetched before the accumulators are ready
 #pragma unroll
@@ -346,19 +359,27 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
     const int chunk = lane & 7, rsub = lane >> 3;
     uint32_t n = 0, slot = 0, round = 0; // stage counter, ring slot, ring round
     for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
-      const Item I = load_item(P, wi);
+      const Item I = load_item<G>(P, wi);
       if (!I.uni) continue;
       const int *idBase = P.nbr + ((size_t)I.st * P.T * P.K) * 128 + pw * kRowsPerWarp + (lane & (kRowsPerWarp - 1));
-      int idc[kMaxT], idn[kMaxT];
-      auto load_ids = [&](int k, int (&dst)[kMaxT]) {
+      int idc[G][TM], idn[G][TM];
+      auto load_ids = [&](int k, int (&dst)[G][TM]) {
 #pragma unroll
-        for (int t = 0; t < kMaxT; t++) dst[t] = ((I.m[t] >> k) & 1ull) ? __ldg(idBase + ((size_t)t * P.K + k) * 128) : -1;
+        for (int g = 0; g < G; g++)
+#pragma unroll
+          for (int t = 0; t < TM; t++)
+            dst[g][t] = (((I.m[t] >> k) & 1ull) && k + g < P.K) ? __ldg(idBase + ((size_t)t * P.K + k + g) * 128) : -1;
       };
+      // packed rows: 16-byte chunk `chunk` of the 128-byte atom row belongs to offset k + myG, bytes [16 sub, 16 sub + 16) of that neighbour's row
+      constexpr int kChunksPerRow = 8 / G;
+      const int myG = chunk / kChunksPerRow, sub = chunk % kChunksPerRow;
       int k = __ffsll((long long)I.uni) - 1;
       load_ids(k, idn);
       while (k >= 0) {
 #pragma unroll
-        for (int t = 0; t < kMaxT; t++) idc[t] = idn[t];
+        for (int g = 0; g < G; g++)
+#pragma unroll
+          for (int t = 0; t < TM; t++) idc[g][t] = idn[g][t];
         const unsigned long long rest = (k + 1 < 64) ? (I.uni >> (k + 1)) : 0ull;
         const int kNext = rest ? k + 1 + (__ffsll((long long)rest) - 1) : -1;
         if (kNext >= 0) load_ids(kNext, idn);
@@ -368,13 +389,19 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
           const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
           if (!(P.dbg & 1)) {
 #pragma unroll
-            for (int t = 0; t < kMaxT; t++) {
+            for (int t = 0; t < TM; t++) {
               if (!((I.m[t] >> k) & 1ull)) continue; // uniform over the CTA
 #pragma unroll
               for (int i = 0; i < kRowsPerWarp / 4; i++) {
-                const int id = __shfl_sync(0xffffffffu, idc[t], i * 4 + rsub);
+                int id = __shfl_sync(0xffffffffu, idc[0][t], i * 4 + rsub);
+#pragma unroll
+                for (int g = 1; g < G; g++) {
+                  const int v = __shfl_sync(0xffffffffu, idc[g][t], i * 4 + rsub);
+                  if (g == myG) id = v;
+                }
                 const int row = pw * kRowsPerWarp + i * 4 + rsub;
-                const unsigned char *src = P.in + (size_t)(id >= 0 ? id : 0) * P.rowBytes + c * 128 + chunk * 16;
+                const unsigned char *src = G == 1 ? P.in + (size_t)(id >= 0 ? id : 0) * P.rowBytes + c * 128 + chunk * 16
+                                                  : P.in + (size_t)(id >= 0 ? id : 0) * (128 / G) + sub * 16;
                 cp_async16(sbase + t * kAtomBytes + row * 128 + ((chunk ^ (row & 7)) << 4), src, id >= 0 ? 16u : 0u);
               }
             }
@@ -405,7 +432,7 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
       int it = 0;
       const uint32_t sStage0 = smem_u32(sStage), full0 = smem_u32(full), empty0 = smem_u32(empty);
       for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
-        const Item I = load_item(P, wi);
+        const Item I = load_item<G>(P, wi);
         const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
         mbar_wait_t(smem_u32(accEmpty + a), (use & 1) ^ 1, pw0, prof); // epilogue has drained this accumulator stage
         tc_fence_after();
@@ -457,12 +484,12 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
     if (lane == 0) {
       uint32_t n = 0, slot = 0, round = 0;
       for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
-        const Item I = load_item(P, wi);
+        const Item I = load_item<G>(P, wi);
         unsigned long long rest = I.uni;
         while (rest) {
           const int k = __ffsll((long long)rest) - 1;
           rest &= rest - 1;
-          const int w = P.tileW ? __ldg(P.tileW + I.st) : k;
+          const int w = P.tileW ? __ldg(P.tileW + I.st) : k / G; // packed: one weight atom per offset group
           for (int c = 0; c < P.nAtoms; c++) {
             n++;
             mbar_wait_t(smem_u32(empty + slot), (round & 1u) ^ 1u, pw0, prof);
@@ -512,6 +539,24 @@ __global__ void k_prep_wimg(const float *__restrict__ W, unsigned char *__restri
   }
 }
 
+// Packed layers (bf16 rows of 128 / G bytes, G = 2 or 4): the K atom of offset group kg holds, for output channel co,
+// [offset kg G | offset kg G + 1 | ...] x Cin input channels -- the same order in which the producers lay the G
+// gathered neighbour rows side by side.  Offsets beyond K and channels beyond CinW are zero.
+__global__ void k_prep_wimg_packed(const float *__restrict__ W, unsigned char *__restrict__ img, int K, int G, int Cin, int CinW, int Cout) {
+  const int KG = (K + G - 1) / G;
+  const long n = (long)KG * G * Cin * Cout;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long t = i / Cout;
+    const int ci = (int)(t % Cin), k = (int)(t / Cin);
+    const int kg = k / G, g = k % G;
+    const int byte = (g * Cin + ci) * 2, chunk = byte >> 4, within = byte & 15;
+    unsigned char *dst = img + (long)kg * Cout * 128 + (long)co * 128 + ((chunk ^ (co & 7)) << 4) + within;
+    const float w = (k < K && ci < CinW) ? W[((long)k * CinW + ci) * Cout + co] : 0.f;
+    *reinterpret_cast<unsigned short *>(dst) = __bfloat16_as_ushort(__float2bfloat16_rn(w));
+  }
+}
+
 // Weight images are cached across calls: (device pointer, caller's version tag, shape, operand
 // type) -> image.  The tag is how the caller says "same contents as last time" (the Python layer
 // passes a per-Parameter token combined with the tensor's in-place version counter); tag 0 = no caching.
@@ -528,8 +573,15 @@ static size_t g_wimg_bytes = 0;
 static unsigned long long g_wimg_clock = 0;
 constexpr size_t kWimgBudget = 768u << 20;
 // Returns the image; *owned = true when the caller must cudaFreeAsync it (uncached).
+// fmt: 0 = tf32, 1 = bf16, 1 + 16 G = packed bf16 (G offsets per atom)
+static void launch_prep_wimg(const float *W, unsigned char *img, int K, int Cin, int CinW, int Cout, int fmt, cudaStream_t s) {
+  const int G = fmt >> 4;
+  if (G > 1) k_prep_wimg_packed<<<stream_grid((long)((K + G - 1) / G) * G * Cin * Cout, 256), 256, 0, LS(s)>>>(W, img, K, G, Cin, CinW, Cout);
+  else k_prep_wimg<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, img, K, Cin, CinW, Cout, fmt & 1);
+}
 static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int Cout, int bf16, cudaStream_t s, unsigned char **img, bool *owned) {
-  const size_t bytes = (size_t)K * Cin * Cout * (bf16 ? 2 : 4);
+  const int packG = bf16 >> 4;
+  const size_t bytes = packG > 1 ? (size_t)((K + packG - 1) / packG) * Cout * 128 : (size_t)K * Cin * Cout * (bf16 ? 2 : 4);
   *owned = false;
   if (tag != 0) {
     std::lock_guard<std::mutex> lk(g_wimg_mu);
@@ -554,7 +606,7 @@ static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int
     WimgVal v;
     SCN_CUDA(cudaMalloc((void **)&v.img, bytes));
     SCN_CUDA(cudaEventCreateWithFlags(&v.ready, cudaEventDisableTiming));
-    k_prep_wimg<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, v.img, K, Cin, CinW, Cout, bf16);
+    launch_prep_wimg(W, v.img, K, Cin, CinW, Cout, bf16, s);
     SCN_CUDA(cudaEventRecord(v.ready, s));
     v.bytes = bytes; v.stream = s; v.lastUse = ++g_wimg_clock;
     g_wimg[key] = v;
@@ -563,7 +615,7 @@ static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int
     return 0;
   }
   SCN_CUDA(cudaMallocAsync((void **)img, bytes, s));
-  k_prep_wimg<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, *img, K, Cin, CinW, Cout, bf16);
+  launch_prep_wimg(W, *img, K, Cin, CinW, Cout, bf16, s);
   *owned = true;
   return 0;
 }
@@ -582,6 +634,13 @@ __global__ void k_pad_rows(const float *__restrict__ in, float *__restrict__ out
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n * Cp; i += (long)gridDim.x * blockDim.x) {
     int c = (int)(i % Cp);
     out[i] = c < C ? __ldg(in + (i / Cp) * C + c) : 0.f;
+  }
+}
+// rows of C <= Cp channels -> bf16 rows zero-padded to Cp channels (the 9-channel network input -> 16 channels = 32-byte rows)
+__global__ void k_pad_rows_bf16(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, long n, int C, int Cp) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n * Cp; i += (long)gridDim.x * blockDim.x) {
+    int c = (int)(i % Cp);
+    out[i] = __float2bfloat16_rn(c < C ? __ldg(in + (i / Cp) * C + c) : 0.f);
   }
 }
 // fp32 -> bf16 (rn) copy of a feature matrix, for inputs that arrive without a bf16 shadow
@@ -630,7 +689,17 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
                         long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0) {
   if (nOut == 0) return 0;
   if (CinW == 0) CinW = Cin;
-  if (Cin % 32 != 0) { // e.g. the 9-channel input convolution: rows zero-padded to 32 channels (the weight image pads itself)
+  const bool canPack = mathMode == 2 && !tileW && Cout <= 128; // packed narrow rows: two-CTA configuration only
+  if (canPack && CinW == Cin && Cin != 16 && Cin % 32 != 0) {
+    // bf16 mode, odd channel counts (e.g. the 9-channel network input): bf16 rows zero-padded to 16 channels (packed, G = 4),
+    // 32 channels (G = 2) or a multiple of 64 (whole atoms), written by one pass; the weight image pads itself
+    const int Cp = Cin < 16 ? 16 : (Cin < 32 ? 32 : (Cin + 63) / 64 * 64);
+    __nv_bfloat16 *xp = nullptr;
+    SCN_TRY(stream_scratch(s, (size_t)nInRows * Cp * 2 + 16, (void **)&xp));
+    k_pad_rows_bf16<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
+    return launch_conv_plan_tc(in, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, xp, wTag, addend, out16, nOutRows, Cin);
+  }
+  if (Cin % 32 != 0 && !(canPack && Cin == 16)) { // rows zero-padded to a multiple of 32 channels (the weight image pads itself)
     const int Cp = (Cin + 31) / 32 * 32;
     float *xp = nullptr;
     SCN_TRY(stream_scratch(s, (size_t)nInRows * Cp * 4 + 16, (void **)&xp));
@@ -649,7 +718,10 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   TcParams P;
   P.in = reinterpret_cast<const unsigned char *>(in); P.out = out; P.bias = bias; P.addend = addend; P.out16 = out16; P.nbr = nbr; P.outRow = outRow; P.tileMask = tileMask; P.tileW = tileW;
   P.nOut = nOut; P.K = K; P.Cout = Cout;
-  P.bf16 = (mathMode == 2 && Cin % 64 == 0) ? 1 : 0; // narrower layers keep TF32 operands (128-byte rows either way)
+  // bf16 mode: rows of >= 64 channels are whole 128-byte atoms; 32- and 16-channel rows (64 / 32 bytes) are PACKED, G = 2 / 4
+  // filter offsets side by side in one atom: half / a quarter of the stages, gather bytes and MMAs of the 128-byte-row layout
+  const int packG = (canPack && (Cin == 32 || Cin == 16)) ? 64 / Cin : 1;
+  P.bf16 = (mathMode == 2 && (Cin % 64 == 0 || packG > 1)) ? 1 : 0; // other narrow layers keep TF32 operands
   void *tmp16 = nullptr;
   if (P.bf16) {
     if (!in16) {
@@ -660,7 +732,8 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     P.in = static_cast<const unsigned char *>(in16);
   }
   P.rowBytes = Cin * (P.bf16 ? 2 : 4);
-  P.nAtoms = P.rowBytes / 128;
+  P.nAtoms = packG > 1 ? 1 : P.rowBytes / 128;
+  P.KG = (K + packG - 1) / packG;
   P.nTiles = cdiv(nOut, kTileM);
   P.dbg = envDbg;
   // Tiles per work item: as many as TMEM holds (T x Cout <= 512 columns) so that a weight atom is
@@ -669,9 +742,10 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   // two CTAs per SM (each with 256 TMEM columns and half the shared memory) unless the layer is too wide for that
   int ctas = envCtas ? envCtas : 2;
   if (Cout > 128) ctas = 1;
+  if (packG > 1) ctas = 2;
   P.tmemCols = ctas == 2 ? 256 : 512;
   const size_t smemBudget = ctas == 2 ? (233472 / 2 - 1024) : 227 * 1024;
-  const int Tcap = std::min(kMaxT, P.tmemCols / Cout);
+  const int Tcap = std::min(packG == 4 ? 2 : kMaxT, P.tmemCols / Cout);
   const size_t fixed = kEpiBytes + 64 * 8 + 64;
   auto ring = [&](int t) { return (int)((smemBudget - fixed) / ((size_t)t * kAtomBytes + (size_t)Cout * 128)); };
   int T = Tcap;
@@ -684,7 +758,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   P.nAcc = 2 * T * Cout <= P.tmemCols ? 2 : 1;
   P.nSuper = cdiv(P.nTiles, P.T);
   P.kSplit = 1;
-  if (P.nSuper < kSMs * ctas / 2 && !tileW) P.kSplit = std::max(1, std::min(K, kSMs * ctas / P.nSuper));
+  if (P.nSuper < kSMs * ctas / 2 && !tileW) P.kSplit = std::max(1, std::min(packG > 1 ? P.KG : K, kSMs * ctas / P.nSuper));
   P.stats = nullptr;
   if (tl_stats && P.kSplit == 1 && Cout <= kFusedStatsC && Cout % 32 == 0) { P.stats = tl_stats; tl_stats_done = true; }
   tl_stats = nullptr;
@@ -699,14 +773,16 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
   unsigned char *wimg = nullptr;
   bool wimgOwned = false;
-  SCN_TRY(get_wimg(W, wTag, nWeights, Cin, CinW, Cout, P.bf16, s, &wimg, &wimgOwned));
+  SCN_TRY(get_wimg(W, wTag, nWeights, Cin, CinW, Cout, packG > 1 ? 1 + 16 * packG : P.bf16, s, &wimg, &wimgOwned));
   P.wimg = wimg;
   static bool attr = false;
   if (!attr) {
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
     attr = true;
   }
   static int envSms = -1;
@@ -717,12 +793,14 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     SCN_CUDA(cudaMallocAsync((void **)&P.prof, 2 * kSMs * 32 * 8, s));
     SCN_CUDA(cudaMemsetAsync(P.prof, 0, 2 * kSMs * 32 * 8, s));
   }
-  if (ctas == 2) {
-    if (P.bf16) conv_plan_tc<true, 4><<<grid, 32 * 10, smem, LS(s)>>>(P);
-    else conv_plan_tc<false, 4><<<grid, 32 * 10, smem, LS(s)>>>(P);
+  if (packG == 2) conv_plan_tc<true, 4, 2><<<grid, 32 * 10, smem, LS(s)>>>(P);
+  else if (packG == 4) conv_plan_tc<true, 4, 4><<<grid, 32 * 10, smem, LS(s)>>>(P);
+  else if (ctas == 2) {
+    if (P.bf16) conv_plan_tc<true, 4, 1><<<grid, 32 * 10, smem, LS(s)>>>(P);
+    else conv_plan_tc<false, 4, 1><<<grid, 32 * 10, smem, LS(s)>>>(P);
   } else {
-    if (P.bf16) conv_plan_tc<true, 8><<<grid, 32 * 14, smem, LS(s)>>>(P);
-    else conv_plan_tc<false, 8><<<grid, 32 * 14, smem, LS(s)>>>(P);
+    if (P.bf16) conv_plan_tc<true, 8, 1><<<grid, 32 * 14, smem, LS(s)>>>(P);
+    else conv_plan_tc<false, 8, 1><<<grid, 32 * 14, smem, LS(s)>>>(P);
   }
   SCN_CUDA(cudaGetLastError());
   if (envProf) { // developer aid: mean stall cycles per role over the CTAs of this launch

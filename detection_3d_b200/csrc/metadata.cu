@@ -539,10 +539,11 @@ struct OrderOut {
 // The first growth phases (tables up to kSmallNb buckets) in one CTA, entirely in shared memory.
 // Leaves the last small table in `out` and the id of every rank of that phase in `seqOut`.
 constexpr int kSmallNb = 16384;
-__global__ void __launch_bounds__(1024) k_emulate_small(const int4 *coords, const int *seq, int idOffset, int n, unsigned *out, int *seqOut, int *err) {
-  extern __shared__ unsigned sm[];
-  unsigned *A = sm, *B = sm + kSmallNb;
-  int *seqA = reinterpret_cast<int *>(sm + 2 * kSmallNb), *seqB = seqA + kSmallNb / 2; // rank -> id of the two live phases
+struct SmallEmu { unsigned *tab; int *seq; int nb, nCur; }; // last table the CTA built (shared memory), rank -> id of that phase
+// cap = buckets of the largest table this call can reach (a power of two <= kSmallNb): shared memory = 3 * cap words
+__device__ __forceinline__ SmallEmu emulate_small_body(const int4 *coords, const int *seq, int idOffset, int n, unsigned *sm, int cap, int *err) {
+  unsigned *A = sm, *B = sm + cap;
+  int *seqA = reinterpret_cast<int *>(sm + 2 * cap), *seqB = seqA + cap / 2; // rank -> id of the two live phases
   __shared__ int s_scan[1024 / 32];
   __shared__ int s_carry;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -586,16 +587,18 @@ __global__ void __launch_bounds__(1024) k_emulate_small(const int4 *coords, cons
       priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, (unsigned)j << kProbeBits, err);
     }
     __syncthreads();
-    if (nCur == n || nb == kSmallNb) {
-      for (int i = tid; i < nb; i += 1024) out[i] = cur[i];
-      for (int i = tid; i < nCur; i += 1024) seqOut[i] = seqCur[i];
-      return;
-    }
+    if (nCur == n || nb == cap) return SmallEmu{cur, seqCur, nb, nCur};
     unsigned *t = prev; prev = cur; cur = t;
     int *ts = seqPrev; seqPrev = seqCur; seqCur = ts;
     nPrev = nCur;
     nb *= 2;
   }
+}
+__global__ void __launch_bounds__(1024) k_emulate_small(const int4 *coords, const int *seq, int idOffset, int n, int cap, unsigned *out, int *seqOut, int *err) {
+  extern __shared__ unsigned sm[];
+  const SmallEmu e = emulate_small_body(coords, seq, idOffset, n, sm, cap, err);
+  for (int i = threadIdx.x; i < e.nb; i += 1024) out[i] = e.tab[i];
+  for (int i = threadIdx.x; i < e.nCur; i += 1024) seqOut[i] = e.seq[i];
 }
 
 // Hash-iteration order of one batch item: ids seq[0..n) (or idOffset + 0..n) inserted in that order.
@@ -608,13 +611,14 @@ static int emulate_order(Metadata &M, const int4 *coords, const int *seq, int id
   unsigned *T0 = M.alloc_n<unsigned>(nbFinal), *T1 = M.alloc_n<unsigned>(nbFinal);
   int *S0 = M.alloc_n<int>(n), *S1 = M.alloc_n<int>(n);
   SCN_CHECK(T0 && T1 && S0 && S1, "alloc");
-  const int smallSmem = 2 * kSmallNb * 4 + kSmallNb * 4;
+  const int cap = (int)std::min<long>(nbFinal, kSmallNb);
+  const int smallSmem = 3 * cap * 4; // small grids leave shared memory to whatever else runs on that SM
   static bool attr = false;
   if (!attr) {
-    SCN_CUDA(cudaFuncSetAttribute(k_emulate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, smallSmem));
+    SCN_CUDA(cudaFuncSetAttribute(k_emulate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kSmallNb * 4));
     attr = true;
   }
-  k_emulate_small<<<1, 1024, smallSmem, LS(s)>>>(coords, seq, idOffset, n, T0, S0, M.cur().d_err);
+  k_emulate_small<<<1, 1024, smallSmem, LS(s)>>>(coords, seq, idOffset, n, cap, T0, S0, M.cur().d_err);
   SCN_CUDA(cudaGetLastError());
   long nb = std::min<long>(nbFinal, kSmallNb);
   unsigned *prev = T0, *cur = T1;
@@ -958,6 +962,208 @@ __global__ void k_conv_plan(ConvGeom G, const int *rank2id, const int4 *coords, 
   }
 }
 
+// ------------------------------------------------------------------ small levels: one launch per strided convolution
+// The deep pyramid levels hold a few thousand sites, yet the general path above spends ~25 launches and 3 host
+// round trips on each (measured: ~0.3 ms per level, all of it launch latency, and the grid pyramid is the critical
+// path of the forward).  For an input grid of <= kSmallSites sites (one batch item, one output cell per site) ONE CTA
+// does the whole build -- hash-iteration order, output grid, first-touch numbering, rule lists in reference order,
+// execution plan, tile masks -- with __syncthreads between the steps, and the host reads the counts back once.
+// Same algorithm, same results as the multi-launch path (tests compare both against the reference rulebooks).
+constexpr int kSmallSites = kSmallNb / 2;
+struct ConvSmallArgs {
+  const int4 *inCoords; int n, idOffset, doRank; int *rank2id;
+  ConvGeom G;
+  int *dir; unsigned long long *bmask; int *wbase; int *d_nblocks; int cells, dd1, dd2; int sz0, sz1, sz2; int cap;
+  int4 *evPts; int *evQ, *evOff, *firstEv;
+  int4 *oCoords; int *p2id, *id2p;
+  int2 *pairs; int *d_off;
+  int *nbr; unsigned long long *tileMask; int nTilesCap;
+  int *sc, *err;
+};
+// exclusive scan over n items by the whole CTA (1024 threads, item i handled by thread i % 1024); returns the total
+template <class InF, class OutF>
+__device__ __forceinline__ int cta_scan(int n, InF in, OutF out, int *s_scan /* [33] */) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int carry = 0;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const int v = i < n ? in(i) : 0;
+    const int incl = warp_incl_scan(v, lane);
+    if (lane == 31) s_scan[wid] = incl;
+    __syncthreads();
+    if (wid == 0) { int w = s_scan[lane]; int wi = warp_incl_scan(w, lane); s_scan[lane] = wi - w; if (lane == 31) s_scan[32] = wi; }
+    __syncthreads();
+    if (i < n) out(i, carry + s_scan[wid] + incl - v, v);
+    carry += s_scan[32];
+    __syncthreads();
+  }
+  return carry;
+}
+__global__ void __launch_bounds__(1024) k_conv_small(const ConvSmallArgs A) {
+  extern __shared__ unsigned sm[];
+  __shared__ int s_scan[33];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = A.n, K = A.G.K;
+  // ---- reference hash-iteration order of the input grid
+  if (A.doRank) {
+    const SmallEmu e = emulate_small_body(A.inCoords, nullptr, A.idOffset, n, sm, A.cap, A.err);
+    cta_scan(e.nb, [&](int i) { return e.tab[i] != kEmpty; },
+             [&](int i, int pre, int v) { if (v) A.rank2id[pre] = e.seq[e.tab[i] >> kProbeBits]; }, s_scan);
+  }
+  __syncthreads();
+  // ---- events (one per input site, rank order) and the block directory of the output grid
+  for (int r = tid; r < n; r += 1024) {
+    const int4 c = A.inCoords[__ldcg(A.rank2id + r)];
+    int4 j; int off;
+    bool ok = conv_event(A.G, c, 0, j, off);
+    if (ok && (j.x >= A.sz0 || (unsigned)j.y >= (unsigned)A.sz1 || (unsigned)j.z >= (unsigned)A.sz2)) { *A.err = 2; ok = false; }
+    A.evPts[r] = ok ? j : make_int4(-1, 0, 0, 0);
+    A.evOff[r] = ok ? off : -1;
+    if (ok) A.dir[((j.x >> 3) * A.dd1 + (j.y >> 3)) * A.dd2 + (j.z >> 3)] = 1;
+  }
+  __syncthreads();
+  const int nblocks = cta_scan(A.cells, [&](int i) { return __ldcg(A.dir + i) != 0; }, [&](int i, int pre, int v) { A.dir[i] = v ? pre : -1; }, s_scan);
+  if (tid == 0) *A.d_nblocks = nblocks;
+  for (int i = tid; i < nblocks * 8; i += 1024) A.bmask[i] = 0ull;
+  __syncthreads();
+  for (int r = tid; r < n; r += 1024) {
+    if (A.evOff[r] < 0) continue;
+    const int4 j = A.evPts[r];
+    const int blk = __ldcg(A.dir + ((j.x >> 3) * A.dd1 + (j.y >> 3)) * A.dd2 + (j.z >> 3));
+    const int bit = ((j.x & 7) << 6) | ((j.y & 7) << 3) | (j.z & 7);
+    atomicOr(A.bmask + (long)blk * 8 + (bit >> 6), 1ull << (bit & 63));
+  }
+  __syncthreads();
+  const int nunique = cta_scan(nblocks * 8, [&](int i) { return __popcll(__ldcg(A.bmask + i)); }, [&](int i, int pre, int) { A.wbase[i] = pre; }, s_scan);
+  // ---- spatial index of every event, first event per output site
+  for (int r = tid; r < n; r += 1024) {
+    int q = -1;
+    if (A.evOff[r] >= 0) {
+      const int4 j = A.evPts[r];
+      const int blk = __ldcg(A.dir + ((j.x >> 3) * A.dd1 + (j.y >> 3)) * A.dd2 + (j.z >> 3));
+      const int bit = ((j.x & 7) << 6) | ((j.y & 7) << 3) | (j.z & 7);
+      const int w = blk * 8 + (bit >> 6);
+      const unsigned long long m = __ldcg(A.bmask + w), one = 1ull << (bit & 63);
+      q = __ldcg(A.wbase + w) + __popcll(m & (one - 1));
+      atomicMin(A.firstEv + q, r);
+    }
+    A.evQ[r] = q;
+  }
+  __syncthreads();
+  // ---- first-touch numbering of the output sites (ConvolutionRules.h:19-31)
+  const int nOut = cta_scan(n, [&](int r) { const int q = A.evQ[r]; return (int)(q >= 0 && __ldcg(A.firstEv + q) == r); },
+                            [&](int r, int pre, int v) { if (v) { const int q = A.evQ[r]; A.p2id[q] = pre; A.id2p[pre] = q; A.oCoords[pre] = A.evPts[r]; } }, s_scan);
+  // ---- rule lists: list L holds the (input row, output row) pairs of the events with offset L, in rank order
+  int *s_tot = reinterpret_cast<int *>(sm), *s_off = s_tot + 64;
+  int(*s_w)[64] = reinterpret_cast<int(*)[64]>(sm + 192);
+  if (tid < 64) s_tot[tid] = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int r = base + tid, L = r < n ? A.evOff[r] : -1;
+    for (int l = 0; l < K; l++) {
+      const unsigned bal = __ballot_sync(0xffffffffu, L == l);
+      if (lane == 0 && bal) atomicAdd(s_tot + l, __popc(bal));
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0;
+    for (int l = 0; l < K; l++) { s_off[l] = a; A.d_off[l] = a; A.sc[128 + l] = a; a += s_tot[l]; }
+    s_off[K] = a; A.d_off[K] = a; A.sc[128 + K] = a;
+    A.sc[1] = nunique; A.sc[3] = nOut;
+  }
+  __syncthreads();
+  if (tid < 64) s_tot[tid] = 0; // from here: pairs already written per list
+  for (int t = tid; t < A.nTilesCap; t += 1024) A.tileMask[t] = 0ull;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int r = base + tid, L = r < n ? A.evOff[r] : -1;
+    unsigned mine = 0;
+    for (int l = 0; l < K; l++) {
+      const unsigned bal = __ballot_sync(0xffffffffu, L == l);
+      if (lane == 0) s_w[wid][l] = __popc(bal);
+      if (L == l) mine = bal;
+    }
+    __syncthreads();
+    if (tid < K) {
+      int a = s_tot[tid];
+      for (int w = 0; w < 32; w++) { const int c = s_w[w][tid]; s_w[w][tid] = a; a += c; }
+      s_tot[tid] = a;
+    }
+    __syncthreads();
+    if (L >= 0) {
+      const int id = __ldcg(A.rank2id + r), q = A.evQ[r];
+      A.pairs[s_off[L] + s_w[wid][L] + __popc(mine & ((1u << lane) - 1u))] = make_int2(id, __ldcg(A.p2id + q));
+      // output-stationary plan + per-tile offset masks
+      A.nbr[nbr_index(q, L, K)] = id;
+      atomicOr(A.tileMask + (q >> 7), 1ull << L);
+    }
+    __syncthreads();
+  }
+}
+int Metadata::get_conv_small(Grid &gi, Grid &go, ConvEntry &e, const ConvGeomHost &G) {
+  cudaStream_t s = cur().stream;
+  const int n = gi.n;
+  const bool doRank = claim(gi.rankRdy);
+  struct Guard { Metadata &m; Ready &r; bool on; ~Guard() { if (on && !r.ready) m.unclaim(r); } } guard{*this, gi.rankRdy, doRank};
+  if (doRank) { gi.rank2id = alloc_n<int>(n); SCN_CHECK(gi.rank2id, "alloc"); }
+  else SCN_TRY(need(gi.rankRdy));
+  for (int d = 0; d < 3; d++) go.dd[d] = (int)((go.sz[d] + 7) / 8);
+  go.dirCells = (long)go.dd[0] * go.dd[1] * go.dd[2];
+  const long cells = go.dirCells;
+  go.dir = alloc_n<int>(cells);
+  go.d_nblocks = alloc_n<int>(4);
+  go.maxBlocks = std::max(1l, std::min<long>(n, cells));
+  go.bmask = alloc_n<unsigned long long>(go.maxBlocks * 8);
+  go.wbase = alloc_n<int>(go.maxBlocks * 8);
+  go.coords = alloc_n<int4>(n); go.p2id = alloc_n<int>(n); go.id2p = alloc_n<int>(n);
+  int4 *evPts = alloc_n<int4>(n);
+  int *evQ = alloc_n<int>(n), *evOff = alloc_n<int>(n), *firstEv = alloc_n<int>(n);
+  const long nPad = plan_padded(n);
+  const int nTilesCap = (int)(nPad / 128);
+  e.rb.nLists = G.K;
+  e.rb.d_off = alloc_n<int>(G.K + 1);
+  e.rb.pairs = alloc_n<int2>(n);
+  e.plan.nbr = alloc_n<int>(nPad * G.K);
+  e.plan.tileMask = alloc_n<unsigned long long>(nTilesCap + 8);
+  SCN_CHECK(go.dir && go.d_nblocks && go.bmask && go.wbase && go.coords && go.p2id && go.id2p && evPts && evQ && evOff && firstEv && e.rb.d_off &&
+                e.rb.pairs && e.plan.nbr && e.plan.tileMask, "alloc");
+  int *sc = cur().d_scalars;
+  SCN_CUDA(cudaMemsetAsync(go.dir, 0, cells * 4, s));
+  SCN_CUDA(cudaMemsetAsync(firstEv, 0x7f, (size_t)n * 4, s));
+  SCN_CUDA(cudaMemsetAsync(e.plan.nbr, 0xff, (size_t)nPad * G.K * 4, s));
+  ConvSmallArgs A;
+  A.inCoords = gi.coords; A.n = n; A.idOffset = gi.itemCtr[0]; A.doRank = doRank ? 1 : 0; A.rank2id = gi.rank2id;
+  A.G = G;
+  A.dir = go.dir; A.bmask = go.bmask; A.wbase = go.wbase; A.d_nblocks = go.d_nblocks; A.cells = (int)cells; A.dd1 = go.dd[1]; A.dd2 = go.dd[2];
+  A.sz0 = (int)go.sz[0]; A.sz1 = (int)go.sz[1]; A.sz2 = (int)go.sz[2];
+  A.evPts = evPts; A.evQ = evQ; A.evOff = evOff; A.firstEv = firstEv;
+  A.oCoords = go.coords; A.p2id = go.p2id; A.id2p = go.id2p;
+  A.pairs = e.rb.pairs; A.d_off = e.rb.d_off;
+  A.nbr = e.plan.nbr; A.tileMask = e.plan.tileMask; A.nTilesCap = nTilesCap;
+  A.sc = sc; A.err = cur().d_err;
+  int capB = 32;
+  while (n > capB / 2) capB *= 2; // final table of the hash-order emulation (n <= kSmallSites => capB <= kSmallNb)
+  A.cap = capB;
+  const int smem = std::max(3 * capB * 4, 10 * 1024); // the rule-list pass reuses the buffer (9 KB)
+  static bool attr = false;
+  if (!attr) { SCN_CUDA(cudaFuncSetAttribute(k_conv_small, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * kSmallNb * 4)); attr = true; }
+  k_conv_small<<<1, 1024, smem, LS(s)>>>(A);
+  SCN_CUDA(cudaGetLastError());
+  SCN_CUDA(cudaMemcpyAsync(cur().h_scalars, sc, (128 + G.K + 1) * 4, cudaMemcpyDeviceToHost, s));
+  SCN_CUDA(cudaStreamSynchronize(s));
+  if (doRank) { gi.hasRank = true; SCN_TRY(mark_ready(gi.rankRdy)); }
+  e.rb.off.assign(G.K + 1, 0);
+  for (int L = 0; L <= G.K; L++) e.rb.off[L] = cur().h_scalars[128 + L];
+  e.rb.total = e.rb.off[G.K];
+  go.n = cur().h_scalars[3];
+  SCN_CHECK(cur().h_scalars[1] == go.n, "internal: unique count mismatch (small conv)");
+  go.itemCount.assign(1, go.n);
+  go.itemCtr.assign(1, 0);
+  e.plan.K = G.K; e.plan.nOut = go.n; e.plan.outRow = go.p2id; e.plan.nValid = e.rb.total;
+  return 0;
+}
+
 // getRuleBook (Metadata.cpp:484-510) -> Convolution_InputSgToRulesAndOutputSg (ConvolutionRules.h:11-34)
 int Metadata::get_conv(const long *inS, const long *outS, const long *f, const long *st, ConvEntry **out) {
   ConvKey key{P3{inS[0], inS[1], inS[2]}, P3{f[0], f[1], f[2]}, P3{st[0], st[1], st[2]}};
@@ -985,8 +1191,6 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
     G.M *= G.cnt[d]; G.K *= (int)f[d];
   }
   SCN_CHECK(G.K <= 64 && G.M <= 64, "unsupported convolution filter size");
-  SCN_TRY(ensure_rank(*gi));
-  cudaStream_t s = cur().stream;
   Grid *gop;
   { std::lock_guard<std::mutex> lk(mapMu); gop = &grids[okey]; }
   ConvEntry &e = *ep;
@@ -996,6 +1200,19 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   Grid &go = *gop;
   go.sz = okey;
   go.batch = gi->batch;
+  static int smallOn = -1;
+  if (smallOn < 0) smallOn = getenv("SCN_SMALL_FUSED") ? atoi(getenv("SCN_SMALL_FUSED")) : 1;
+  if (smallOn && G.M == 1 && gi->batch == 1 && gi->n > 0 && gi->n <= kSmallSites && gi->itemCtr.size() == 1 && gi->itemCtr[0] >= 0 &&
+      ((outS[0] + 7) / 8) * ((outS[1] + 7) / 8) * ((outS[2] + 7) / 8) <= (1 << 16)) {
+    SCN_TRY(get_conv_small(*gi, go, e, G));
+    SCN_TRY(mark_ready(go.rdy));
+    { std::lock_guard<std::mutex> lk(mapMu); go.built = true; }
+    cv.notify_all();
+    SCN_TRY(mark_ready(e.rdy));
+    return 0;
+  }
+  SCN_TRY(ensure_rank(*gi));
+  cudaStream_t s = cur().stream;
   const int n = gi->n;
   const long E = (long)n * G.M;
   int4 *evPts = alloc_n<int4>(std::max(1l, E));

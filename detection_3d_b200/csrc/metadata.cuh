@@ -165,6 +165,7 @@ struct Metadata {
   int get_submanifold(const long *sz, const long *f, SubmEntry **out);
   int ensure_subm_rules(SubmEntry &e);
   int get_conv(const long *inS, const long *outS, const long *f, const long *s, ConvEntry **out);
+  int get_conv_small(Grid &gi, Grid &go, ConvEntry &e, const ConvGeomHost &G); // one-launch build for small input grids
   int spatial_locations(const long *sz, long *out, int outOnDevice);
   int build_tile_masks(NbrPlan &plan);
   int get_deconv_plan(ConvEntry &e);

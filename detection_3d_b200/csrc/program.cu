@@ -210,7 +210,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     R.cols = cols;
     R.p = static_cast<float *>(slot_get(p, (size_t)std::max(1l, rows * cols) * 4));
     if (!R.p) return -1;
-    if (shadow && mode == 2 && cols % 64 == 0 && rows > 0) {
+    if (shadow && mode == 2 && cols % 32 == 0 && rows > 0) {
       R.p16 = slot_get(p, (size_t)rows * cols * 2);
       if (!R.p16) return -1;
     }

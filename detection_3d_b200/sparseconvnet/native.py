@@ -51,7 +51,7 @@ _MATH = {"mode": 0}
 
 def _new_shadow(t):
     """bf16 buffer for the fp32 feature matrix `t` (or None when the mode / shape does not use one)."""
-    if _MATH["mode"] != 2 or t.dim() != 2 or t.size(1) % 64 != 0 or t.size(0) == 0:
+    if _MATH["mode"] != 2 or t.dim() != 2 or t.size(1) % 32 != 0 or t.size(0) == 0:
         return None
     return torch.empty(t.shape, dtype=torch.bfloat16, device=t.device)
 
