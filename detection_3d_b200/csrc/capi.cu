@@ -122,7 +122,7 @@ void scn_metadata_destroy(scn_metadata *m) {
 static void prefetch_worker(scn_metadata *m, int which) {
   cudaSetDevice(m->device);
   scn::set_prefetch_worker_thread(true, which);
-  struct Done { scn_metadata *m; int which; ~Done() { if (which == 0) m->md.set_chain_done(true); } } done{m, which};
+  struct Done { scn_metadata *m; int which; ~Done() { if (which == 0) m->md.set_chain_done(true); else { m->md.worker2Done.store(true); m->md.cv.notify_all(); } } } done{m, which};
   for (const PrefetchOp &op : (which == 0 ? m->ops : m->ops2)) {
     if (m->stop) break;
     const long *a = op.v + 1, *b = op.v + 4, *f = op.v + 7, *s = op.v + 10;
@@ -168,14 +168,23 @@ int scn_metadata_prefetch(scn_metadata *m, int n_ops, const long *ops) {
   // (a submanifold plan needs its grid, a deconvolution plan the convolution that created the coarse
   // grid); taken in request order it would sit on the deepest level's deconvolution plans while the
   // shallow ones -- buildable long before -- queue behind them.
+  // Submanifold plans first (the bottom-up pass needs them level by level, as the chain worker descends), then what the
+  // top-down pass and the z-collapsing convolutions need, deepest level first -- the order in which the network uses them.
   std::stable_sort(m->ops2.begin(), m->ops2.end(), [](const PrefetchOp &x, const PrefetchOp &y) {
     auto fine = [](const PrefetchOp &o) { return o.v[0] == 3 ? o.v[4] : o.v[1]; }; // spatial size[0] of the (fine) grid the entry hangs off
-    return fine(x) > fine(y);
+    const bool sx = x.v[0] == 1, sy = y.v[0] == 1;
+    if (sx != sy) return sx;
+    return sx ? fine(x) > fine(y) : fine(x) < fine(y);
   });
+  {
+    std::lock_guard<std::mutex> lk(m->md.mapMu);
+    for (const PrefetchOp &o : m->ops2)
+      if (o.v[0] == 1) m->md.subm[scn::SubmKey{scn::P3{o.v[1], o.v[2], o.v[3]}, scn::P3{o.v[7], o.v[8], o.v[9]}}].assigned = true;
+  }
   m->stop = false;
   m->md.set_chain_done(false);
   m->worker = std::thread(prefetch_worker, m, 0);
-  if (!m->ops2.empty()) m->worker2 = std::thread(prefetch_worker, m, 1);
+  if (!m->ops2.empty()) { m->md.worker2Done.store(false); m->worker2 = std::thread(prefetch_worker, m, 1); }
   return 0;
 }
 

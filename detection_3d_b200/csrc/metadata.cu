@@ -531,6 +531,27 @@ __global__ void __launch_bounds__(256) k_phase_insert(unsigned *cur, unsigned ma
     priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, (unsigned)j << kProbeBits, err);
   }
 }
+struct PhaseIn {
+  const unsigned *tab; long nbPrev;
+  __device__ int operator()(long i) const { return i < nbPrev && tab[i] != kEmpty; }
+};
+struct PhaseOut {
+  const unsigned *tab; long nbPrev; const int *seqIn, *newSeq; int idOffset, nPrev; int *seqOut; unsigned *cur; unsigned mask; const int4 *coords; int *err;
+  __device__ void operator()(long i, int pre, int v) const {
+    int j, id;
+    if (i < nbPrev) {
+      if (!v) return;
+      id = seqIn[tab[i] >> kProbeBits];
+      j = pre;
+    } else {
+      j = nPrev + (int)(i - nbPrev);
+      id = newSeq ? newSeq[j] : j + idOffset;
+    }
+    seqOut[j] = id;
+    const int4 c = coords[id];
+    priority_insert(cur, mask, point_hash(c.x, c.y, c.z) & mask, (unsigned)j << kProbeBits, err);
+  }
+};
 struct OrderOut {
   const unsigned *tab; const int *seq; int *rank2id;
   __device__ void operator()(long i, int pre, int v) const { if (v) rank2id[pre] = seq[tab[i] >> kProbeBits]; }
@@ -608,10 +629,13 @@ static int emulate_order(Metadata &M, const int4 *coords, const int *seq, int id
   cudaStream_t s = M.cur().stream;
   long nbFinal = 32;
   while (n > nbFinal / 2) nbFinal *= 2;
-  unsigned *T0 = M.alloc_n<unsigned>(nbFinal), *T1 = M.alloc_n<unsigned>(nbFinal);
   int *S0 = M.alloc_n<int>(n), *S1 = M.alloc_n<int>(n);
-  SCN_CHECK(T0 && T1 && S0 && S1, "alloc");
   const int cap = (int)std::min<long>(nbFinal, kSmallNb);
+  // one table per growth phase beyond the small ones (cap*2, cap*4, ..., nbFinal buckets: < 2 nbFinal words in all),
+  // cleared by ONE memset up front, so that a phase is a single launch
+  unsigned *T0 = M.alloc_n<unsigned>(cap), *big = nbFinal > cap ? M.alloc_n<unsigned>(2 * nbFinal) : nullptr;
+  SCN_CHECK(T0 && S0 && S1 && (big || nbFinal <= cap), "alloc");
+  if (big) SCN_CUDA(cudaMemsetAsync(big, 0xff, (size_t)(2 * nbFinal - 2 * cap) * 4, s));
   const int smallSmem = 3 * cap * 4; // small grids leave shared memory to whatever else runs on that SM
   static bool attr = false;
   if (!attr) {
@@ -620,18 +644,29 @@ static int emulate_order(Metadata &M, const int4 *coords, const int *seq, int id
   }
   k_emulate_small<<<1, 1024, smallSmem, LS(s)>>>(coords, seq, idOffset, n, cap, T0, S0, M.cur().d_err);
   SCN_CUDA(cudaGetLastError());
-  long nb = std::min<long>(nbFinal, kSmallNb);
-  unsigned *prev = T0, *cur = T1;
+  long nb = cap;
+  unsigned *prev = T0, *cur = big;
   int *seqPrev = S0, *seqCur = S1; // seqPrev: rank -> id of the phase held in `prev`
   int nPrev = (int)std::min<long>(n, nb / 2);
+  static int fusedPhases = -1;
+  if (fusedPhases < 0) fusedPhases = getenv("SCN_PHASE_FUSED") ? atoi(getenv("SCN_PHASE_FUSED")) : 0; // measured: the fused launch is 2x slower (8 sequential insertions per scan thread)
   while (nb < nbFinal) {
+    const long nbPrev = nb;
     nb *= 2;
     int nCur = (int)std::min<long>(n, nb / 2);
-    SCN_CUDA(cudaMemsetAsync(cur, 0xff, nb * 4, s));
-    // seqCur[0..nPrev) = ids of the old table in bucket order; the insert kernel appends the new ones
-    SCN_TRY(run_scan(M, nb / 2, TabIn{prev}, CompactOut{prev, seqPrev, 0, seqCur}, nullptr));
-    k_phase_insert<<<stream_grid(nCur, 256, 16), 256, 0, LS(s)>>>(cur, (unsigned)(nb - 1), coords, seqCur, seq, idOffset, nPrev, nCur, seqCur, M.cur().d_err);
-    std::swap(prev, cur);
+    if (!fusedPhases) { // two launches: compaction scan, then one thread per key
+      SCN_TRY(run_scan(M, nbPrev, TabIn{prev}, CompactOut{prev, seqPrev, 0, seqCur}, nullptr));
+      k_phase_insert<<<stream_grid(nCur, 256, 16), 256, 0, LS(s)>>>(cur, (unsigned)(nb - 1), coords, seqCur, seq, idOffset, nPrev, nCur, seqCur, M.cur().d_err);
+      prev = cur; cur += nb; std::swap(seqPrev, seqCur); nPrev = nCur;
+      continue;
+    }
+    // One launch per phase: a scan over the old table ranks its keys in ascending bucket order and its consumer
+    // inserts them straight away; the keys that arrive during this phase (ranks nPrev..nCur) ride along as extra
+    // scan items with value 0 -- priority insertion reaches the same fixed point in any order.
+    SCN_TRY(run_scan(M, nbPrev + (nCur - nPrev), PhaseIn{prev, nbPrev},
+                     PhaseOut{prev, nbPrev, seqPrev, seq, idOffset, nPrev, seqCur, cur, (unsigned)(nb - 1), coords, M.cur().d_err}, nullptr));
+    prev = cur;
+    cur += nb;
     std::swap(seqPrev, seqCur);
     nPrev = nCur;
   }
@@ -838,6 +873,12 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   { std::lock_guard<std::mutex> lk(mapMu); ep = &subm[key]; }
   SubmEntry &e = *ep;
   *out = ep;
+  if (!tl_prefetch_worker) {
+    // The caller shares build context 0 (stream and lock) with the chain worker: a plan the second worker is about
+    // to build anyway is waited for instead of being built here, in front of the grid pyramid on the critical path.
+    std::unique_lock<std::mutex> lk(mapMu);
+    while (e.assigned && !e.rdy.ready && !worker2Done.load()) cv.wait_for(lk, std::chrono::milliseconds(1));
+  }
   if (!claim(e.rdy)) return 0; // built (or just finished) by another thread
   struct Guard { Metadata &m; Ready &r; ~Guard() { if (!r.ready) m.unclaim(r); } } guard{*this, e.rdy};
   BuildLock bl(*this);

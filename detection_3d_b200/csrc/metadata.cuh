@@ -82,7 +82,7 @@ struct DeconvPlan {
   unsigned long long *tileMask = nullptr; // [nTiles] all ones (kept for the kernel's interface)
 };
 struct ConvGeomHost { int f[3], s[3], outS[3], cnt[3], M, K; };
-struct SubmEntry { RuleBookDev rb; NbrPlan plan; Ready rdy, rulesRdy; P3 sz; }; // rb.pairs / offsets only after ensure_subm_rules
+struct SubmEntry { RuleBookDev rb; NbrPlan plan; Ready rdy, rulesRdy; P3 sz; bool assigned = false; /* the second prefetch worker will build it */ }; // rb.pairs / offsets only after ensure_subm_rules
 struct ConvEntry { RuleBookDev rb; NbrPlan plan; P3 out; P3 in; ConvGeomHost geom; DeconvPlan deconv; Ready rdy, deconvRdy; };
 
 struct InputRules {
@@ -130,6 +130,7 @@ struct Metadata {
   std::mutex mapMu;
   std::condition_variable cv;
   std::atomic<bool> chainDone{true}; // no chain worker is producing grids (set_chain_done)
+  std::atomic<bool> worker2Done{true}; // the second prefetch worker is not running (entries marked `assigned` will not be built by it)
   std::vector<cudaEvent_t> events;
   struct BuildLock {
     BuildCtx &c;
