@@ -36,6 +36,7 @@ namespace scn {
 constexpr int kTileM = 128;
 constexpr int kAtomBytes = kTileM * 128; // 128 rows x 128 B
 constexpr int kMaxT = 4;
+constexpr int kLateralBit = 63; // mask bit of the lateral stage (real filter offsets use bits 0..K-1, K <= 63 then)
 constexpr int kEpiBytes = 4 * 32 * 32 * 4; // 4 epilogue warps x (32 rows x 32 floats), XOR-swizzled
 
 struct TcParams {
@@ -49,6 +50,9 @@ struct TcParams {
   const int *outRow;
   const unsigned long long *tileMask;
   const int *tileW; // optional: weight slice per tile (deconvolution plans; then K == 1 and T == 1)
+  // optional second source ("lateral"): out += in2[outRow] @ W2, one more accumulation stage per tile, carried as pseudo filter offset kLateralBit
+  const unsigned char *in2, *wimg2;
+  int rowBytes2, nAtoms2;
   double *stats;    // optional [kBnReplicas][2][kFusedStatsC]: per-channel sum / sum of squares of `out` (statistics of a following BatchNorm)
   long long *prof;  // developer: per-CTA stall counters (SCN_TC_PROF)
   int nOut, K, Cout, nTiles, T, nSuper, S, nAcc, lag;
@@ -185,6 +189,7 @@ __device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
   for (int t = 0; t < kMaxT; t++) {
     const int tile = I.st * P.T + t;
     I.m[t] = (t < P.T && tile < P.nTiles) ? (group_mask<G>(__ldg(P.tileMask + tile)) & kmask) : 0ull;
+    if (G == 1 && P.in2 && I.part == 0 && t < P.T && tile < P.nTiles) I.m[t] |= 1ull << kLateralBit;
     I.uni |= I.m[t];
   }
   return I;
@@ -367,8 +372,14 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
 #pragma unroll
         for (int g = 0; g < G; g++)
 #pragma unroll
-          for (int t = 0; t < TM; t++)
-            dst[g][t] = (((I.m[t] >> k) & 1ull) && k + g < P.K) ? __ldg(idBase + ((size_t)t * P.K + k + g) * 128) : -1;
+          for (int t = 0; t < TM; t++) {
+            if (G == 1 && k == kLateralBit) { // lateral stage: the input row of an output site is its own output row
+              const long p = (long)(I.st * P.T + t) * kTileM + pw * kRowsPerWarp + (lane & (kRowsPerWarp - 1));
+              dst[g][t] = (((I.m[t] >> k) & 1ull) && p < P.nOut) ? __ldg(P.outRow + p) : -1;
+            } else {
+              dst[g][t] = (((I.m[t] >> k) & 1ull) && k + g < P.K) ? __ldg(idBase + ((size_t)t * P.K + k + g) * 128) : -1;
+            }
+          }
       };
       // packed rows: 16-byte chunk `chunk` of the 128-byte atom row belongs to offset k + myG, bytes [16 sub, 16 sub + 16) of that neighbour's row
       constexpr int kChunksPerRow = 8 / G;
@@ -383,7 +394,10 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
         const unsigned long long rest = (k + 1 < 64) ? (I.uni >> (k + 1)) : 0ull;
         const int kNext = rest ? k + 1 + (__ffsll((long long)rest) - 1) : -1;
         if (kNext >= 0) load_ids(kNext, idn);
-        for (int c = 0; c < P.nAtoms; c++) {
+        const bool lat = G == 1 && k == kLateralBit;
+        const unsigned char *srcBase = lat ? P.in2 : P.in;
+        const int srcRowBytes = lat ? P.rowBytes2 : P.rowBytes, nA = lat ? P.nAtoms2 : P.nAtoms;
+        for (int c = 0; c < nA; c++) {
           n++;
           mbar_wait_t(smem_u32(empty + slot), (round & 1u) ^ 1u, pw0, prof);
           const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
@@ -400,9 +414,11 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
                   if (g == myG) id = v;
                 }
                 const int row = pw * kRowsPerWarp + i * 4 + rsub;
-                const unsigned char *src = G == 1 ? P.in + (size_t)(id >= 0 ? id : 0) * P.rowBytes + c * 128 + chunk * 16
+                const unsigned char *src = G == 1 ? srcBase + (size_t)(id >= 0 ? id : 0) * srcRowBytes + c * 128 + chunk * 16
                                                   : P.in + (size_t)(id >= 0 ? id : 0) * (128 / G) + sub * 16;
-                cp_async16(sbase + t * kAtomBytes + row * 128 + ((chunk ^ (row & 7)) << 4), src, id >= 0 ? 16u : 0u);
+                // rows narrower than the atom (a 32-channel bf16 lateral): the missing chunks are zero-filled
+                const bool have = id >= 0 && (G > 1 || c * 128 + chunk * 16 < srcRowBytes);
+                cp_async16(sbase + t * kAtomBytes + row * 128 + ((chunk ^ (row & 7)) << 4), have ? src : srcBase, have ? 16u : 0u);
               }
             }
           }
@@ -441,7 +457,8 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
         while (rest) {
           const int k = __ffsll((long long)rest) - 1;
           rest &= rest - 1;
-          for (int c = 0; c < P.nAtoms; c++) {
+          const int nA = (G == 1 && k == kLateralBit) ? P.nAtoms2 : P.nAtoms;
+          for (int c = 0; c < nA; c++) {
             n++;
             mbar_wait_t(full0 + slot * 8u, round & 1u, pw1, prof);
             tc_fence_after();
@@ -489,15 +506,18 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
         while (rest) {
           const int k = __ffsll((long long)rest) - 1;
           rest &= rest - 1;
-          const int w = P.tileW ? __ldg(P.tileW + I.st) : k / G; // packed: one weight atom per offset group
-          for (int c = 0; c < P.nAtoms; c++) {
+          const bool lat = G == 1 && k == kLateralBit;
+          const int w = lat ? 0 : (P.tileW ? __ldg(P.tileW + I.st) : k / G); // packed: one weight atom per offset group
+          const unsigned char *wsrc = lat ? P.wimg2 : P.wimg;
+          const int nA = lat ? P.nAtoms2 : P.nAtoms;
+          for (int c = 0; c < nA; c++) {
             n++;
             mbar_wait_t(smem_u32(empty + slot), (round & 1u) ^ 1u, pw0, prof);
             const uint32_t bar = smem_u32(full + slot);
             if (P.dbg & 2) { mbar_arrive(bar); }
             else {
               mbar_arrive_expect_tx(bar, bBytes);
-              bulk_g2s(smem_u32(sStage) + slot * stageBytes + (uint32_t)P.T * kAtomBytes, P.wimg + ((size_t)w * P.nAtoms + c) * bBytes, bBytes, bar);
+              bulk_g2s(smem_u32(sStage) + slot * stageBytes + (uint32_t)P.T * kAtomBytes, wsrc + ((size_t)w * nA + c) * bBytes, bBytes, bar);
             }
             if (++slot == (uint32_t)P.S) { slot = 0; round++; }
           }
@@ -682,6 +702,13 @@ static int stream_scratch(cudaStream_t s, size_t bytes, void **out) {
 static thread_local double *tl_stats = nullptr;
 static thread_local bool tl_stats_done = false;
 void epilogue_stats_arm(double *sums) { tl_stats = sums; tl_stats_done = false; }
+// Same for a lateral 1x1x1 convolution folded into the next convolution: out = conv(in) [+ addend] + lat_in[row] @ lat_w.
+// lat_in: fp32 rows; lat_in16: their bf16 copy (may be null); taken when the launch is a whole-atom (unpacked) tensor-core launch.
+struct Lateral { const float *in; const void *in16; const float *w; long long tag; int Cin; long rows; };
+static thread_local Lateral tl_lat = {nullptr, nullptr, nullptr, 0, 0, 0};
+static thread_local bool tl_lat_done = false;
+void lateral_arm(const float *in, const void *in16, const float *w, long long tag, int Cin, long rows) { tl_lat = Lateral{in, in16, w, tag, Cin, rows}; tl_lat_done = false; }
+bool lateral_take() { bool d = tl_lat_done; tl_lat.in = nullptr; tl_lat_done = false; return d; }
 bool epilogue_stats_take() { bool d = tl_stats_done; tl_stats = nullptr; tl_stats_done = false; return d; }
 // in16: optional bf16 copy of `in` (same layout); used in math mode 2 when Cin is a multiple of 64
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
@@ -775,6 +802,22 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   bool wimgOwned = false;
   SCN_TRY(get_wimg(W, wTag, nWeights, Cin, CinW, Cout, packG > 1 ? 1 + 16 * packG : P.bf16, s, &wimg, &wimgOwned));
   P.wimg = wimg;
+  P.in2 = nullptr; P.wimg2 = nullptr; P.rowBytes2 = 0; P.nAtoms2 = 0;
+  unsigned char *wimg2 = nullptr;
+  bool wimg2Owned = false;
+  if (tl_lat.in && packG == 1 && K < kLateralBit && tl_lat.rows > 0 && (!P.bf16 || tl_lat.in16)) {
+    const int esz = P.bf16 ? 2 : 4, per = 128 / esz, C2 = tl_lat.Cin; // per = channels of one K atom
+    if ((C2 * esz) % 16 == 0) {
+      const int C2p = (C2 + per - 1) / per * per;
+      SCN_TRY(get_wimg(tl_lat.w, tl_lat.tag, 1, C2p, C2, Cout, P.bf16, s, &wimg2, &wimg2Owned));
+      P.in2 = static_cast<const unsigned char *>(P.bf16 ? tl_lat.in16 : static_cast<const void *>(tl_lat.in));
+      P.rowBytes2 = C2 * esz;
+      P.nAtoms2 = C2p / per;
+      P.wimg2 = wimg2;
+      tl_lat_done = true;
+    }
+  }
+  tl_lat.in = nullptr;
   static bool attr = false;
   if (!attr) {
     SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -816,6 +859,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (out16 && P.kSplit > 1 && nOutRows > 0) // partial sums were accumulated atomically: the bf16 copy needs the finished rows
     k_to_bf16<<<stream_grid(nOutRows * Cout / 4, 256), 256, 0, LS(s)>>>(out, static_cast<uint2 *>(out16), nOutRows * Cout / 4);
   if (wimgOwned) cudaFreeAsync(wimg, s);
+  if (wimg2Owned) cudaFreeAsync(wimg2, s);
 
   return 0;
 }

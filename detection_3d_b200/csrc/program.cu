@@ -12,6 +12,8 @@
 namespace scn {
 void epilogue_stats_arm(double *sums);
 bool epilogue_stats_take();
+void lateral_arm(const float *in, const void *in16, const float *w, long long tag, int Cin, long rows);
+bool lateral_take();
 int bn_forward_from_sums(const float *x, float *y, long n, int C, const double *sums, float *saveMean, float *saveInvStd, float *runningMean,
                          float *runningVar, const float *weight, const float *bias, float eps, float momentum, int mode, float leak, cudaStream_t s, void *y16);
 } // namespace scn
@@ -103,6 +105,7 @@ int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, co
   op.kind = kind;
   for (int i = 0; i < 24; i++) op.a[i] = i < n_iargs ? iargs[i] : 0;
   for (int i = 0; i < 4; i++) op.f[i] = i < n_fargs ? fargs[i] : 0.0;
+  op.a[18] = -1; // lateral 1x1x1 convolution folded into this convolution: its input register, weight parameter (a[19]), channels (a[20])
   op.a[21] = -1; // statistics slot shared by a convolution and the BatchNorm ops that read its output (scn_program_finish)
   op.a[22] = -1; // register added in the epilogue of a convolution (set by the fusion pass of scn_program_finish)
   p->ops.push_back(op);
@@ -145,6 +148,40 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
     for (int i = 0; i < (int)p->ops.size(); i++) if (!dead[i]) kept.push_back(p->ops[i]);
     p->ops.swap(kept);
   }
+  { // Lateral 1x1x1 convolutions: `conv(x) + NiN(y)` (the FPN's top-down step: Deconvolution + shortcut) becomes ONE kernel
+    // that accumulates y[row] @ W_nin into the same TMEM accumulators as an extra stage, so the lateral tensor is never
+    // written or read.  Pattern: a convolution with a fused addend whose producer is a bias-free 1x1x1 SubmanifoldConvolution
+    // consumed by nothing else.
+    auto out_of = [](const Op &o) -> long { return o.kind == K_INPUT ? o.a[0] : (o.kind == K_ADD ? o.a[2] : o.a[1]); };
+    std::vector<int> producer(n_regs, -1), consumers(n_regs, 0);
+    std::vector<char> isOut(n_regs, 0);
+    for (int i = 0; i < n_outputs; i++) if (outputs[i] >= 0 && outputs[i] < n_regs) isOut[outputs[i]] = 1;
+    for (int i = 0; i < (int)p->ops.size(); i++) {
+      const Op &o = p->ops[i];
+      producer[out_of(o)] = i;
+      if (o.kind == K_ADD) { consumers[o.a[0]]++; consumers[o.a[1]]++; }
+      else if (o.kind != K_INPUT) { consumers[o.a[0]]++; if (o.kind != K_BN && o.a[22] >= 0) consumers[o.a[22]]++; }
+    }
+    std::vector<char> dead(p->ops.size(), 0);
+    static const bool on = !(getenv("SCN_LATERAL_FUSED") && atoi(getenv("SCN_LATERAL_FUSED")) == 0);
+    for (int i = 0; on && i < (int)p->ops.size(); i++) {
+      Op &h = p->ops[i];
+      if ((h.kind != K_SUBM && h.kind != K_CONV && h.kind != K_DECONV) || h.a[22] < 0) continue;
+      const long r = h.a[22];
+      const int j = producer[r];
+      if (j < 0 || j >= i || consumers[r] != 1 || isOut[r]) continue;
+      const Op &nin = p->ops[j];
+      if (nin.kind != K_SUBM || nin.a[5] != 1 || nin.a[6] != 1 || nin.a[7] != 1 || nin.a[9] >= 0) continue; // 1x1x1, no bias
+      const long ninOutC = nin.a[11], hostOutC = h.kind == K_SUBM ? h.a[11] : h.a[17];
+      if (ninOutC != hostOutC) continue;
+      h.a[18] = nin.a[0]; h.a[19] = nin.a[8]; h.a[20] = nin.a[10];
+      h.a[22] = -1;
+      dead[j] = 1;
+    }
+    std::vector<Op> kept;
+    for (int i = 0; i < (int)p->ops.size(); i++) if (!dead[i]) kept.push_back(p->ops[i]);
+    p->ops.swap(kept);
+  }
   { // BatchNorm statistics in the producing convolution's epilogue: BN(conv_out) with batch statistics (modes 0 / 2)
     // reads per-channel sums the convolution kernel accumulated while it still held the output values, and runs
     // only its apply pass.  Whether a given convolution launch can do it (tensor-core path, no offset splitting,
@@ -181,6 +218,7 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
         SCN_TRY(use(op.a[0], i));
         SCN_TRY(use(op.a[1], i));
         if (op.kind != K_BN && op.a[22] >= 0) SCN_TRY(use(op.a[22], i));
+        if (op.kind != K_BN && op.a[18] >= 0) SCN_TRY(use(op.a[18], i));
         break;
     }
   }
@@ -216,6 +254,8 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     }
     return 0;
   };
+  double macs = 0, mk = 0;
+  int rc = 0;
   const size_t statsStride = (size_t)scn::kBnReplicas * 2 * scn::kFusedStatsC;
   if (p->nStats) {
     if (!p->stats) SCN_CUDA(cudaMalloc((void **)&p->stats, p->nStats * statsStride * sizeof(double)));
@@ -224,8 +264,27 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   }
   auto arm = [&](const Op &op) { if (op.a[21] >= 0) scn::epilogue_stats_arm(p->stats + op.a[21] * statsStride); };
   auto took = [&](const Op &op) { const bool d = scn::epilogue_stats_take(); if (op.a[21] >= 0) p->statsDone[op.a[21]] = d; };
-  double macs = 0, mk = 0;
-  int rc = 0;
+  auto arm_lateral = [&](const Op &op) {
+    if (op.a[18] < 0) return;
+    const Reg &Y = p->regs[op.a[18]];
+    scn::lateral_arm(Y.p, Y.p16, P(op.a[19]), T(op.a[19]), (int)op.a[20], Y.rows);
+  };
+  // the convolution did not take the lateral (e.g. it ran on the CUDA-core path): run the 1x1x1 convolution on its own and add it
+  auto lateral_fallback = [&](const Op &op, scn_metadata *md, const long *sz, Reg &out, int Cout) -> int {
+    const bool done = scn::lateral_take();
+    if (op.a[18] < 0) return 0;
+    const Reg &Y = p->regs[op.a[18]];
+    macs += (double)Y.rows * (double)op.a[20] * Cout;
+    if (done || out.rows == 0) return 0;
+    float *tmp = static_cast<float *>(slot_get(p, (size_t)out.rows * Cout * 4));
+    if (!tmp) return -1;
+    const long one[3] = {1, 1, 1};
+    double mk2 = 0;
+    int r = scn_submanifold_convolution_forward(md, sz, one, Y.p, tmp, P(op.a[19]), nullptr, (int)op.a[20], Cout, &mk2, Y.p16, T(op.a[19]), nullptr, nullptr);
+    if (r == 0) r = scn_add_features(out.p, tmp, out.p, out.rows * Cout, s, out.p16);
+    slot_put(p, tmp);
+    return r;
+  };
   for (int i = 0; i < (int)p->ops.size() && rc == 0; i++) {
     const Op &op = p->ops[i];
     const long *a = op.a;
@@ -254,39 +313,42 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_SUBM: { // in, out, size[3], filter[3], w, bias, Cin, Cout
         long n = 0;
         rc = scn_get_nactive(m, a + 2, &n);
-        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], a[22] >= 0);
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], a[22] >= 0 || a[18] >= 0);
         const Reg &I = p->regs[a[0]];
-        if (rc == 0) arm(op);
+        if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0)
           rc = scn_submanifold_convolution_forward(m, a + 2, a + 5, I.p, p->regs[a[1]].p, P(a[8]), P(a[9]), (int)a[10], (int)a[11], &mk, I.p16, T(a[8]),
                                                    a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         took(op);
+        if (rc == 0) rc = lateral_fallback(op, m, a + 2, p->regs[a[1]], (int)a[11]);
         macs += mk;
         break;
       }
       case K_CONV: { // in, out, inS[3], outS[3], f[3], s[3], w, bias, Cin, Cout
         long n = 0, nr = 0;
         rc = scn_convolution_prepare(m, a + 2, a + 5, a + 8, a + 11, &n, &nr);
-        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0);
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0 || a[18] >= 0);
         const Reg &I = p->regs[a[0]];
-        if (rc == 0) arm(op);
+        if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0)
           rc = scn_convolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]),
                                        a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         took(op);
+        if (rc == 0) rc = lateral_fallback(op, m, a + 5, p->regs[a[1]], (int)a[17]);
         macs += mk;
         break;
       }
       case K_DECONV: {
         long n = 0;
         rc = scn_get_nactive(m, a + 5, &n);
-        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0);
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0 || a[18] >= 0);
         const Reg &I = p->regs[a[0]];
-        if (rc == 0) arm(op);
+        if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0)
           rc = scn_deconvolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]),
                                          a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         took(op);
+        if (rc == 0) rc = lateral_fallback(op, m, a + 5, p->regs[a[1]], (int)a[17]);
         macs += mk;
         break;
       }
