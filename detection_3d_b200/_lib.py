@@ -28,6 +28,9 @@ SYMBOLS = {
     "scn_program_finish": (_i, [_vp, _i, _vp, _i]),
     "scn_program_run": (_i, [_vp, _vp, _vp, _i, _l, _i, _vp, _vp, _vp, _i, _vp, _pd]),
     "scn_program_output": (_i, [_vp, _i, C.POINTER(_l), C.POINTER(_i), C.POINTER(_vp)]),
+    "scn_program_prepare": (_i, [_vp, _vp, _vp, _i, _l, _i]),
+    "scn_program_throttle": (_i, [_vp]),
+    "scn_input_layer_built": (_i, [_vp, _pl, _pi]),
     "scn_copy_device": (_i, [_vp, _vp, _l, _vp]),
     "scn_input_layer_build": (_i, [_vp, L3, _vp, _i, _l, _i, _i, _i, _pl, _pi]),
     "scn_input_layer_forward": (_i, [_vp, _vp, _vp, _i]),
@@ -52,6 +55,7 @@ SYMBOLS = {
     "scn_get_math_mode": (_i, []),
     "scn_tensor_core_path_available": (_i, []),
     "scn_kernel_launch_count": (_l, []),
+    "scn_debug_counter": (_l, [_i]),
 }
 
 

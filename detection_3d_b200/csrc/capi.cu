@@ -48,6 +48,9 @@ int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s, v
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
                        const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s);
 int tc_available();
+long debug_chunk_mallocs();
+long debug_chunk_waits();
+long debug_chunk_total_mb();
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
                         long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0);
@@ -81,6 +84,7 @@ const char *scn_last_error(void) { return scn::last_error(); }
 int scn_version(void) { return 1; }
 int scn_n_rulebook_bits(void) { return 32; }
 long scn_kernel_launch_count(void) { return scn::g_launches; }
+long scn_debug_counter(int which) { return which == 0 ? scn::debug_chunk_mallocs() : which == 1 ? scn::debug_chunk_waits() : scn::debug_chunk_total_mb(); }
 int scn_set_math_mode(int mode) {
   if (mode < 0 || mode > 2) { scn::set_error("math mode must be 0 (fp32), 1 (tf32) or 2 (bf16)"); return -2; }
   scn::g_math_mode = mode;
@@ -197,6 +201,12 @@ int scn_input_layer_build(scn_metadata *m, const long sz[3], const long *coords,
   if (n_active) *n_active = m->md.input.nOut;
   if (max_active) *max_active = m->md.input.maxActive;
   return 0;
+}
+int scn_input_layer_built(scn_metadata *m, long *n_active, int *max_active) {
+  if (!m || !m->md.input.valid) return 0;
+  if (n_active) *n_active = m->md.input.nOut;
+  if (max_active) *max_active = m->md.input.maxActive;
+  return 1;
 }
 int scn_input_layer_forward(scn_metadata *m, const float *in, float *out, int C) {
   M_OR_FAIL(m);

@@ -37,7 +37,12 @@ constexpr int kTileM = 128;
 constexpr int kAtomBytes = kTileM * 128; // 128 rows x 128 B
 constexpr int kMaxT = 4;
 constexpr int kLateralBit = 63; // mask bit of the lateral stage (real filter offsets use bits 0..K-1, K <= 63 then)
-constexpr int kEpiBytes = 4 * 32 * 32 * 4; // 4 epilogue warps x (32 rows x 32 floats), XOR-swizzled
+#ifndef SCN_EPI_COLS
+#define SCN_EPI_COLS 32
+#endif
+constexpr int kEpiCols = SCN_EPI_COLS;           // output columns per epilogue round: 32 (16 KB of staging per CTA) or 16 (8 KB)
+constexpr int kEpiBytes = 4 * 32 * kEpiCols * 4; // 4 epilogue warps x (32 rows x kEpiCols floats), XOR-swizzled
+constexpr int kBuildRoom = SCN_EPI_COLS == 16 ? 12 * 1024 : 0; // shared memory per SM left to the build kernels that run beside this one
 
 struct TcParams {
   const unsigned char *in; // activations, row-major, rowBytes per row (fp32 or bf16 elements)
@@ -146,7 +151,7 @@ __device__ __forceinline__ void tc_mma(uint32_t dTmem, uint64_t aDesc, uint64_t 
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3fffu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
       "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -158,6 +163,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+        "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ unsigned long long range_mask(int lo, int hi) { // bits [lo, hi)
   unsigned long long a = hi >= 64 ? ~0ull : ((1ull << hi) - 1ull);
   return a & ~((1ull << lo) - 1ull);
@@ -203,7 +216,7 @@ __device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
 // columns and half the shared memory each): two independent pipelines per SM hide each other's
 // barrier hand-offs.
 template <bool BF16, int PW, int G>
-__global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_plan_tc(const TcParams P) {
+__global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 320), PW == 8 ? 1 : 2) conv_plan_tc(const TcParams P) {
   constexpr int TM = G == 4 ? 2 : kMaxT; // tiles per item the producers keep neighbour ids for (G ids per row and tile)
   constexpr int kProdWarps = PW;
   constexpr int kRowsPerWarp = kTileM / PW; // rows of a tile one producer warp gathers
@@ -241,9 +254,11 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
     // ============================ epilogue ============================
     // warp w owns TMEM lanes 32w.. = rows 32w.. of every tile.  Per 32-column block: tcgen05.ld ->
     // padded shared-memory block -> each store instruction writes four whole 128-byte row segments.
-    float *stg = sEpi + warp * (32 * 32);
-    const int cc = (lane & 7) * 4, rsub = lane >> 3;
-    float4 sAcc = make_float4(0.f, 0.f, 0.f, 0.f), qAcc = sAcc; // column sums of the 32-column block this lane group owns (block == rsub)
+    // EC = columns per round (kEpiCols): EC / 4 lanes cover one EC*4-byte row segment, 128 / EC rows per instruction.
+    constexpr int EC = kEpiCols, LPR = EC / 4, RPI = 32 / LPR, NI = 32 / RPI; // lanes per row, rows per instruction, instructions per 32 rows
+    float *stg = sEpi + warp * (32 * EC);
+    const int cl = lane % LPR, cc = cl * 4, rsub = lane / LPR;
+    float4 sAcc = make_float4(0.f, 0.f, 0.f, 0.f), qAcc = sAcc; // column sums of the EC-column block this lane group owns (block == rsub)
     int it = 0;
     for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
       const Item I = load_item<G>(P, wi);
@@ -261,34 +276,38 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
         if (t >= P.T || I.st * P.T + t >= P.nTiles) continue;
         const bool started = I.m[t] != 0ull;
         if (!started && P.kSplit > 1 && !((P.addend || P.bias) && I.part == 0)) continue; // nothing to add
-        int rows[8];
+        int rows[NI];
 #pragma unroll
-        for (int i = 0; i < 8; i++) rows[i] = __shfl_sync(0xffffffffu, myRow[t], i * 4 + rsub);
-        for (int c0 = 0; c0 < P.Cout; c0 += 32) {
-          uint32_t v[32];
+        for (int i = 0; i < NI; i++) rows[i] = __shfl_sync(0xffffffffu, myRow[t], i * RPI + rsub);
+        for (int c0 = 0; c0 < P.Cout; c0 += EC) {
+          uint32_t v[EC];
           if (started) {
-            tmem_ld32(tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * accCols + t * P.Cout + c0), v);
+            const uint32_t taddr = tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * accCols + t * P.Cout + c0);
+            tmem_ld(taddr, v); // .x32 or .x16 by the array size
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = 0u;
+            for (int j = 0; j < EC; j++) v[j] = 0u;
           }
           __syncwarp();
+          // 16-byte chunk q of row r is stored at chunk position q ^ sw(r); sw keeps both the row-wise writes and the
+          // column-wise reads free of bank conflicts (EC = 32: r & 7; EC = 16: (r >> 1) & 3, two rows per 128 bytes)
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) // 16-byte chunk j/4 of row `lane` goes to chunk (j/4) ^ (lane & 7): conflict-free both ways
-            *reinterpret_cast<float4 *>(stg + lane * 32 + ((((j >> 2) ^ (lane & 7))) << 2)) =
+          for (int j = 0; j < EC; j += 4)
+            *reinterpret_cast<float4 *>(stg + lane * EC + ((((j >> 2) ^ (EC == 32 ? (lane & 7) : ((lane >> 1) & 3)))) << 2)) =
                 make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
           __syncwarp();
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           if (P.bias && I.part == 0) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + c0 + cc));
-          float4 o[8];
+          float4 o[NI];
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            o[i] = *reinterpret_cast<const float4 *>(stg + (i * 4 + rsub) * 32 + (((lane & 7) ^ ((i * 4 + rsub) & 7)) << 2));
+          for (int i = 0; i < NI; i++) {
+            const int r = i * RPI + rsub;
+            o[i] = *reinterpret_cast<const float4 *>(stg + r * EC + ((cl ^ (EC == 32 ? (r & 7) : ((r >> 1) & 3))) << 2));
             o[i].x += bv.x; o[i].y += bv.y; o[i].z += bv.z; o[i].w += bv.w;
           }
           if (P.addend && I.part == 0) {
 #pragma unroll
-            for (int h = 0; h < 8; h += 4) { // four 16-byte loads in flight per thread
+            for (int h = 0; h < NI; h += 4) { // four 16-byte loads in flight per thread
               float4 ad[4];
 #pragma unroll
               for (int i = 0; i < 4; i++)
@@ -300,26 +319,26 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
           if (P.stats) { // launcher guarantees kSplit == 1 and Cout <= 128: o[] holds final output values
             float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), q4 = s4;
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < NI; i++)
               if (rows[i] >= 0) {
                 s4.x += o[i].x; s4.y += o[i].y; s4.z += o[i].z; s4.w += o[i].w;
                 q4.x = fmaf(o[i].x, o[i].x, q4.x); q4.y = fmaf(o[i].y, o[i].y, q4.y); q4.z = fmaf(o[i].z, o[i].z, q4.z); q4.w = fmaf(o[i].w, o[i].w, q4.w);
               }
 #pragma unroll
-            for (int d = 8; d <= 16; d <<= 1) { // the 4 lanes that hold the same columns (rsub = 0..3)
+            for (int d = LPR; d <= 16; d <<= 1) { // the RPI lanes that hold the same columns
               s4.x += __shfl_xor_sync(0xffffffffu, s4.x, d); s4.y += __shfl_xor_sync(0xffffffffu, s4.y, d);
               s4.z += __shfl_xor_sync(0xffffffffu, s4.z, d); s4.w += __shfl_xor_sync(0xffffffffu, s4.w, d);
               q4.x += __shfl_xor_sync(0xffffffffu, q4.x, d); q4.y += __shfl_xor_sync(0xffffffffu, q4.y, d);
               q4.z += __shfl_xor_sync(0xffffffffu, q4.z, d); q4.w += __shfl_xor_sync(0xffffffffu, q4.w, d);
             }
-            if (rsub == (c0 >> 5)) {
+            if (rsub == c0 / EC) { // Cout / EC <= RPI blocks, one per lane group
               sAcc.x += s4.x; sAcc.y += s4.y; sAcc.z += s4.z; sAcc.w += s4.w;
               qAcc.x += q4.x; qAcc.y += q4.y; qAcc.z += q4.z; qAcc.w += q4.w;
             }
           }
           if (P.kSplit == 1) {
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < NI; i++)
               if (rows[i] >= 0) {
                 *reinterpret_cast<float4 *>(P.out + (size_t)rows[i] * P.Cout + c0 + cc) = o[i];
                 if (P.out16) {
@@ -332,7 +351,7 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
               }
           } else { // offsets split over CTAs: accumulate into the launcher-zeroed output
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < NI; i++)
               if (rows[i] >= 0) {
                 float *dst = P.out + (size_t)rows[i] * P.Cout + c0 + cc;
                 atomicAdd(dst, o[i].x); atomicAdd(dst + 1, o[i].y); atomicAdd(dst + 2, o[i].z); atomicAdd(dst + 3, o[i].w);
@@ -345,7 +364,7 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : 320, PW == 8 ? 1 : 2) conv_pla
       if (lane == 0) mbar_arrive(smem_u32(accEmpty + a));
     }
     if (P.stats) { // one double atomic per (warp, channel) into one of kBnReplicas accumulators
-      const int c = rsub * 32 + cc;
+      const int c = rsub * EC + cc;
       if (c < P.Cout) {
         double *rep = P.stats + (size_t)(blockIdx.x % kBnReplicas) * 2 * kFusedStatsC;
         atomicAdd(rep + c, (double)sAcc.x); atomicAdd(rep + c + 1, (double)sAcc.y); atomicAdd(rep + c + 2, (double)sAcc.z); atomicAdd(rep + c + 3, (double)sAcc.w);
@@ -771,7 +790,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (Cout > 128) ctas = 1;
   if (packG > 1) ctas = 2;
   P.tmemCols = ctas == 2 ? 256 : 512;
-  const size_t smemBudget = ctas == 2 ? (233472 / 2 - 1024) : 227 * 1024;
+  const size_t smemBudget = ctas == 2 ? ((233472 - kBuildRoom) / 2 - 1024) : (227 * 1024 - kBuildRoom);
   const int Tcap = std::min(packG == 4 ? 2 : kMaxT, P.tmemCols / Cout);
   const size_t fixed = kEpiBytes + 64 * 8 + 64;
   auto ring = [&](int t) { return (int)((smemBudget - fixed) / ((size_t)t * kAtomBytes + (size_t)Cout * 128)); };
@@ -822,10 +841,10 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (!attr) {
     SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 233472 / 2 - 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (233472 - kBuildRoom) / 2 - 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (233472 - kBuildRoom) / 2 - 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (233472 - kBuildRoom) / 2 - 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (233472 - kBuildRoom) / 2 - 1024));
     attr = true;
   }
   static int envSms = -1;

@@ -32,9 +32,21 @@ static int *pinned_get() {
 // carries the event that marks the end of its previous owner's work; the next owner's build stream
 // waits for that event before the first use.
 static std::vector<Chunk> g_chunks;
-static size_t g_chunk_bytes = 0;
-constexpr size_t kChunkKeep = 12ull << 30; // beyond this much idle memory, chunks go back to the driver
-static size_t chunk_round(size_t b) { const size_t q = 32u << 20; return (b + q - 1) / q * q; }
+static size_t g_chunk_bytes = 0;       // idle chunks
+static long g_chunk_mallocs = 0, g_chunk_waits = 0;
+long debug_chunk_mallocs() { return g_chunk_mallocs; }
+long debug_chunk_waits() { return g_chunk_waits; }
+long debug_chunk_total_mb() ;
+static size_t g_chunk_bytes_total = 0; // every chunk ever taken from the driver and not returned
+constexpr size_t kChunkKeep = 32ull << 30; // beyond this much idle memory, chunks go back to the driver
+long debug_chunk_total_mb() { return (long)(g_chunk_bytes_total >> 20); }
+constexpr size_t kChunkGrow = 16ull << 30; // below this total, a new chunk is allocated rather than waiting for one that is still in use
+// Size classes are powers of two (>= 32 MiB) and a request is only served by a chunk of exactly its class: every
+// Metadata of a given network then draws the same multiset of classes, and the pool stops growing after the first few
+// forwards.  (With best-fit over a size range, requests of concurrently building Metadata objects occasionally took each
+// other's chunks and forced a cudaMalloc in steady state -- measured at 12 ms beside a busy GPU, with the driver lock
+// blocking every other thread's launches.)
+static size_t chunk_round(size_t b) { size_t c = 32u << 20; while (c < b) c <<= 1; return c; }
 // build streams are recycled like the pinned blocks (stream creation is not free either)
 static std::vector<cudaStream_t> g_stream_free;
 static std::vector<cudaEvent_t> g_event_free;
@@ -94,16 +106,25 @@ int Metadata::wait_ready(Ready &r) {
   return 0;
 }
 Metadata::~Metadata() {
-  // what follows on the build streams is ordered after every feature kernel that still reads these buffers
-  if (evCompute) cudaEventRecord(evCompute, cstream);
+  // The buffers may still be read by feature kernels queued on the caller's stream and (rarely) written by a build
+  // stream: a chunk is reusable once BOTH are done.  The caller's stream is made to wait for the build streams' tails
+  // and the chunks' `freed` events are recorded on the caller's stream -- the build streams themselves are never
+  // blocked, so that the next Metadata (which recycles them, possibly while this forward still computes: streaming
+  // inference with FPN_Net.prefetch) can start building at once.
   std::lock_guard<std::mutex> lk(g_pool_mu);
   for (int i = 0; i < nCtx; i++) {
     BuildCtx &c = cx[i];
-    if (evCompute && c.stream != cstream) cudaStreamWaitEvent(c.stream, evCompute, 0);
+    if (evCompute && c.stream != cstream) {
+      cudaEventRecord(evCompute, c.stream);
+      cudaStreamWaitEvent(cstream, evCompute, 0);
+    }
+  }
+  for (int i = 0; i < nCtx; i++) {
+    BuildCtx &c = cx[i];
     for (Chunk &k : c.chunks) {
       if (!k.freed) cudaEventCreateWithFlags(&k.freed, cudaEventDisableTiming);
-      cudaEventRecord(k.freed, c.stream);
-      if (g_chunk_bytes + k.cap > kChunkKeep) { cudaEventSynchronize(k.freed); cudaFree(k.p); cudaEventDestroy(k.freed); continue; }
+      cudaEventRecord(k.freed, cstream);
+      if (g_chunk_bytes + k.cap > kChunkKeep) { cudaEventSynchronize(k.freed); cudaFree(k.p); cudaEventDestroy(k.freed); g_chunk_bytes_total -= k.cap; continue; }
       g_chunks.push_back(k);
       g_chunk_bytes += k.cap;
     }
@@ -132,9 +153,18 @@ void *Metadata::alloc_in(BuildCtx &c, size_t bytes) {
   Chunk k{nullptr, 0, nullptr};
   {
     std::lock_guard<std::mutex> lk(g_pool_mu);
-    int best = -1;
-    for (int i = 0; i < (int)g_chunks.size(); i++)
-      if (g_chunks[i].cap >= cap && g_chunks[i].cap <= 2 * cap && (best < 0 || g_chunks[i].cap < g_chunks[best].cap)) best = i;
+    // best fit among the chunks whose previous owner's work has already finished; a chunk that is still in use (its
+    // forward is still computing) is taken only when the pool is full -- waiting for it would serialise this build
+    // behind that forward
+    int best = -1, bestBusy = -1;
+    for (int i = 0; i < (int)g_chunks.size(); i++) {
+      if (g_chunks[i].cap != cap) continue;
+      const bool done = !g_chunks[i].freed || cudaEventQuery(g_chunks[i].freed) == cudaSuccess;
+      int &b = done ? best : bestBusy;
+      if (b < 0 || g_chunks[i].cap < g_chunks[b].cap) b = i;
+    }
+    cudaGetLastError(); // cudaEventQuery leaves cudaErrorNotReady behind
+    if (best < 0 && bestBusy >= 0 && g_chunk_bytes_total + cap > kChunkGrow) { best = bestBusy; g_chunk_waits++; } // (cudaMalloc beside a busy GPU was measured at ~100 ms)
     if (best >= 0) { k = g_chunks[best]; g_chunks.erase(g_chunks.begin() + best); g_chunk_bytes -= k.cap; }
   }
   if (k.p) {
@@ -142,6 +172,7 @@ void *Metadata::alloc_in(BuildCtx &c, size_t bytes) {
   } else {
     if (cudaMalloc(&k.p, cap) != cudaSuccess) { set_error("cudaMalloc failed"); return nullptr; }
     k.cap = cap;
+    { std::lock_guard<std::mutex> lk(g_pool_mu); g_chunk_bytes_total += cap; g_chunk_mallocs++; }
   }
   c.chunks.push_back(k);
   p = k.p;
@@ -422,7 +453,7 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
   Grid &g = *gp;
   g.sz = key;
   cudaStream_t s = cur().stream;
-  if (onDevice) SCN_TRY(from_compute()); // the coordinates were produced on the caller's cur().stream
+  if (onDevice == 1) SCN_TRY(from_compute()); // the coordinates were produced on the caller's stream (2: already complete, no dependency)
   const long *dcoords = coords;
   if (!onDevice && nrows) {
     long *tmp = alloc_n<long>(nrows * ncols);

@@ -51,6 +51,8 @@ struct scn_program {
   int nStats = 0;               // convolutions whose epilogue accumulates the statistics of the BatchNorm that follows
   double *stats = nullptr;      // nStats x [kBnReplicas][2][kFusedStatsC], zeroed at the start of every run
   std::vector<char> statsDone;
+  cudaEvent_t evEnd[2] = {nullptr, nullptr}; // end of the last two runs on `stream` (throttle of scn_program_prepare)
+  long nRuns = 0;
   cudaStream_t stream = nullptr;
 };
 
@@ -97,6 +99,7 @@ void scn_program_destroy(scn_program *p) {
   for (Slot &s : p->slots) cudaFree(s.p);
   if (p->bnScratch) cudaFree(p->bnScratch);
   if (p->stats) cudaFree(p->stats);
+  for (cudaEvent_t e : p->evEnd) if (e) cudaEventDestroy(e);
   delete p;
 }
 int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, const double *fargs, int n_fargs) {
@@ -229,6 +232,44 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
   return 0;
 }
 
+// The build half of a run: input layer (active sites of the finest grid) and, on the worker threads, every rulebook /
+// plan the program will request.  scn_program_run calls it when the Metadata comes unprepared; a caller that streams
+// buildings through the network calls it for building i+1 right after it has queued building i
+// (coords_on_device = 2: device coordinates that are already complete), so that this build runs while the GPU
+// computes building i.
+// Streaming throttle: building i+2's Metadata is not started before forward i has finished on the GPU.  Two forwards in
+// flight are what the overlap needs (one computing, one queued with its Metadata being built); a host that ran further
+// ahead would only pile up Metadata memory.  Call it BEFORE creating the Metadata that scn_program_prepare will fill,
+// so that the new Metadata finds the finished forward's memory free.
+int scn_program_throttle(scn_program *p) {
+  SCN_CHECK(p, "null program");
+  if (p->nRuns >= 2 && p->evEnd[p->nRuns & 1]) SCN_CUDA(cudaEventSynchronize(p->evEnd[p->nRuns & 1]));
+  return 0;
+}
+int scn_program_prepare(scn_program *p, scn_metadata *m, const long *coords, int coords_on_device, long nrows, int ncols) {
+  SCN_CHECK(p && m && p->nRegs > 0, "program not finished");
+  SCN_TRY(scn_program_throttle(p));
+  for (const Op &op : p->ops) {
+    if (op.kind != K_INPUT) continue;
+    const long *a = op.a;
+    long nActive = 0;
+    int maxActive = 0;
+    SCN_TRY(scn_input_layer_build(m, a + 1, coords, coords_on_device, nrows, ncols, (int)a[5], (int)a[4], &nActive, &maxActive));
+    std::vector<long> hints; // the rulebooks this program is about to request, built ahead on the worker threads
+    for (const Op &o : p->ops) {
+      long h[13] = {0};
+      if (o.kind == K_SUBM) { h[0] = 1; for (int d = 0; d < 3; d++) { h[1 + d] = o.a[2 + d]; h[7 + d] = o.a[5 + d]; } }
+      else if (o.kind == K_CONV || o.kind == K_DECONV) { h[0] = o.kind == K_CONV ? 2 : 3; for (int d = 0; d < 12; d++) h[1 + d] = o.a[2 + d]; }
+      else continue;
+      hints.insert(hints.end(), h, h + 13);
+    }
+    if (!hints.empty()) SCN_TRY(scn_metadata_prefetch(m, (int)(hints.size() / 13), hints.data()));
+    return 0;
+  }
+  scn::set_error("program has no input layer");
+  return -2;
+}
+
 // params[i] / tags[i]: device pointers of the recorded parameter tensors (and their content tags, see
 // weight_tag in scn_*_convolution_forward), in the order the recorder numbered them.
 int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coords_on_device, long nrows, int ncols, const float *feats,
@@ -292,18 +333,9 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_INPUT: { // out, size[3], mode, batch hint, planes
         long nActive = 0;
         int maxActive = 0;
-        rc = scn_input_layer_build(m, a + 1, coords, coords_on_device, nrows, ncols, (int)a[5], (int)a[4], &nActive, &maxActive);
-        if (rc) break;
-        { // the rulebooks this program is about to request, built ahead on the worker thread
-          std::vector<long> hints;
-          for (const Op &o : p->ops) {
-            long h[13] = {0};
-            if (o.kind == K_SUBM) { h[0] = 1; for (int d = 0; d < 3; d++) { h[1 + d] = o.a[2 + d]; h[7 + d] = o.a[5 + d]; } }
-            else if (o.kind == K_CONV || o.kind == K_DECONV) { h[0] = o.kind == K_CONV ? 2 : 3; for (int d = 0; d < 12; d++) h[1 + d] = o.a[2 + d]; }
-            else continue;
-            hints.insert(hints.end(), h, h + 13);
-          }
-          if (!hints.empty()) rc = scn_metadata_prefetch(m, (int)(hints.size() / 13), hints.data());
+        if (!scn_input_layer_built(m, &nActive, &maxActive)) { // not prepared ahead (scn_program_prepare)
+          rc = scn_program_prepare(p, m, coords, coords_on_device, nrows, ncols);
+          if (rc == 0 && !scn_input_layer_built(m, &nActive, &maxActive)) { scn::set_error("program: no input layer"); rc = -2; }
           if (rc) break;
         }
         rc = alloc_reg(a[0], nActive, (int)a[6], false);
@@ -385,6 +417,10 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   }
   if (rc) { release_regs(p, true); return rc; }
   if (macs_out) *macs_out = macs;
+  cudaEvent_t &ev = p->evEnd[p->nRuns & 1];
+  if (!ev) SCN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  SCN_CUDA(cudaEventRecord(ev, s));
+  p->nRuns++;
   return 0;
 }
 

@@ -133,6 +133,26 @@ class FPN_Net(nn.Module):
                 return rpn_maps, roi_maps
         return self.forward_fpn(self.layers_in(net0))
 
+    def prefetch(self, coords):
+        """Streaming inference: start building the Metadata (active-site grids, rulebooks) of the NEXT input now, on the
+        library's build streams, while the GPU still computes the forwards queued before.  May be called for several inputs
+        (first in, first out); a `forward` whose coordinate tensor is one of these objects uses its Metadata, any other
+        input simply ignores them.  Calling it TWO buildings ahead hides the whole build behind the computation.  Results are identical with or
+        without the call.  Device coordinates must be complete (not still being written by another stream).
+        No-op until a program has been recorded (i.e. before the second inference forward)."""
+        prog = self.__dict__.get("_program")
+        if prog is None or self.training or not isinstance(coords, torch.Tensor) or coords.dtype != torch.int64 or coords.dim() != 2:
+            return False
+        if native.math_mode() != prog.math_mode:
+            return False
+        prog.throttle()  # before the Metadata is created: it then recycles the memory of the forward that just finished
+        md = L.Metadata(self.dimension)
+        prog.prepare(md, coords)
+        q = self.__dict__.setdefault("_prefetched", [])
+        q.append((coords, coords._version, md))
+        del q[:-4]  # at most a few buildings ahead
+        return True
+
     def reset_program(self):
         """Forget the recorded program (call after changing the module tree)."""
         self.__dict__.pop("_program", None)
@@ -140,7 +160,16 @@ class FPN_Net(nn.Module):
 
     def _run_program(self, prog, coords, feats):
         import detection_3d_b200.sparseconvnet as pkg
-        md = L.Metadata(self.dimension)
+        md = None
+        q = self.__dict__.get("_prefetched")
+        if q:  # built ahead by prefetch(): the oldest entry made for this very tensor
+            for i, pre in enumerate(q):
+                if pre[0] is coords and pre[1] == coords._version:
+                    md = pre[2]
+                    del q[i]
+                    break
+        if md is None:
+            md = L.Metadata(self.dimension)
         outs, macs = prog.run(md, coords, feats)
         pkg.forward_pass_multiplyAdd_count += macs
         maps = [SparseConvNetTensor(features=f, metadata=md, spatial_size=s.clone()) for f, s in zip(outs, prog.out_sizes)]

@@ -139,6 +139,17 @@ class Program(object):
         return (math_mode == self.math_mode and isinstance(feats, torch.Tensor) and feats.is_cuda and feats.dtype == torch.float32
                 and feats.dim() == 2 and coords.dtype == torch.int64 and coords.dim() == 2)
 
+    def throttle(self):
+        """Wait until at most one forward of this program is still running (scn_program_throttle)."""
+        check(lib().scn_program_throttle(self._h))
+
+    def prepare(self, metadata, coords):
+        """Build half of a run for `coords` (see scn_program_prepare): input layer + rulebook workers, on the library's
+        build streams.  Device coordinates must be complete (no pending writes on any stream)."""
+        coords = coords.contiguous()
+        metadata._keep.append(coords)
+        check(lib().scn_program_prepare(self._h, metadata._h, C.c_void_p(coords.data_ptr()), 2 if coords.is_cuda else 0, coords.size(0), coords.size(1)))
+
     def run(self, metadata, coords, feats):
         """-> (list of output feature tensors, multiply-add count)."""
         from . import native

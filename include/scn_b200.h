@@ -46,6 +46,8 @@ void scn_metadata_destroy(scn_metadata *m);
  * of active voxels and the largest number of input rows merged into one voxel. */
 int scn_input_layer_build(scn_metadata *m, const long spatial_size[3], const long *coords, int coords_on_device,
                           long nrows, int ncols, int batch_size, int mode, long *n_active, int *max_active);
+/* 1 (and the counts) when scn_input_layer_build has run on this Metadata, else 0 */
+int scn_input_layer_built(scn_metadata *m, long *n_active, int *max_active);
 /* InputLayer_ForwardPass / InputLayer_fp  (CPU/IOLayers.cpp:11-29, CUDA/IOLayers.cu:31-41) */
 int scn_input_layer_forward(scn_metadata *m, const float *in_features, float *out_features, int n_planes);
 /* InputLayer_updateGradInput (pybind.cpp:159-162; CPU/IOLayers.cpp:30-47) */
@@ -159,6 +161,14 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
 int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coords_on_device, long nrows, int ncols,
                     const float *features, const void *const *params, const long long *weight_tags, int n_params,
                     void *stream, double *macs);
+/* Build half of a run, callable ahead of scn_program_run for the NEXT input while the GPU still computes the current
+ * one (streaming many buildings through one network): input layer + the worker threads that build every rulebook the
+ * program requests.  coords_on_device: 0 host, 1 device (ordered after the caller's stream), 2 device and complete.
+ * scn_program_run on a Metadata prepared this way skips its own build. */
+int scn_program_prepare(scn_program *p, scn_metadata *m, const long *coords, int coords_on_device, long nrows, int ncols);
+/* Blocks until at most one forward of this program is still running on the GPU (call before scn_metadata_create of the
+ * Metadata to prepare: it then reuses the memory of the forward that just finished). */
+int scn_program_throttle(scn_program *p);
 int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const float **ptr);
 /* device-to-device copy on `stream` (hands an output register to a caller-owned tensor) */
 int scn_copy_device(void *dst, const void *src, long bytes, void *stream);
@@ -172,6 +182,8 @@ int scn_get_math_mode(void);
 int scn_tensor_core_path_available(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 long scn_kernel_launch_count(void);
+/* developer counters of the Metadata memory pool: 0 = chunks taken from the driver, 1 = waits for a chunk still in use, 2 = pool size in MiB */
+long scn_debug_counter(int which);
 
 #ifdef __cplusplus
 }

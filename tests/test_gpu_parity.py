@@ -608,3 +608,53 @@ def test_fused_epilogue_add_and_bf16_copy(math, big):
     scale = max(1.0, float(want.abs().max()))
     assert float((fused - want).abs().max()) <= 1e-5 * scale      # same products; only the order of the atomic sums may differ
     assert torch.equal(fused16, fused.to(torch.bfloat16))
+
+
+@pytest.mark.gpu
+def test_prefetched_metadata_gives_identical_results():
+    """FPN_Net.prefetch(coords) builds the next input's Metadata ahead (scn_program_prepare); the forward that follows must
+    return exactly what an unprepared forward returns (same kernels, same rulebooks), also when several buildings are
+    streamed and a prefetched Metadata goes unused."""
+    import torch
+    import fpn_util
+    import detection_3d_b200.sparseconvnet as scn
+    from detection_3d_b200 import synthetic
+    scn.set_math_mode("tf32")
+    try:
+        cfg = fpn_util.mini4_config()
+        net = scn.FPN_Net(**cfg)
+        net.load_state_dict(fpn_util.deterministic_state(net, seed=3))
+        net = net.cuda().eval()
+        builds = []
+        for seed, (nx, ny) in enumerate([(44, 40), (36, 48), (52, 33)]):
+            c = synthetic.building_coords(nx=nx, ny=ny, nz=20, n_walls=3, seed=seed)
+            builds.append((torch.from_numpy(c).cuda(), torch.from_numpy(fpn_util.features_for(c)).cuda()))
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            net(list(builds[0]))  # records the program
+            plain = []
+            for c, f in builds:
+                rpn, roi = net([c, f])
+                plain.append([(m.features.clone(), m.get_spatial_locations().clone()) for m in rpn + roi])
+            assert net.prefetch(builds[0][0])
+            streamed = []
+            for i, (c, f) in enumerate(builds):
+                rpn, roi = net([c, f])
+                if i + 1 < len(builds):
+                    net.prefetch(builds[i + 1][0])
+                streamed.append([(m.features.clone(), m.get_spatial_locations().clone()) for m in rpn + roi])
+            net.prefetch(builds[1][0])       # prefetched but not used by the next forward
+            rpn, roi = net(list(builds[2]))
+            unused = [(m.features.clone(), m.get_spatial_locations().clone()) for m in rpn + roi]
+        torch.cuda.synchronize()
+        def same(x, y):  # small levels accumulate split filter offsets atomically: run-to-run differences in the last bits
+            (fa, la), (fb, lb) = x, y
+            assert torch.equal(la, lb)
+            assert float((fa - fb).abs().max()) <= 1e-3 * max(1.0, float(fa.abs().max()))
+        for a, b in zip(plain, streamed):
+            for x, y in zip(a, b):
+                same(x, y)
+        for x, y in zip(plain[2], unused):
+            same(x, y)
+    finally:
+        scn.set_math_mode("fp32")

@@ -21,12 +21,18 @@ net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
 net = net.cuda().eval()
 coords = torch.from_numpy(synthetic.building_coords()).cuda()
 feats = torch.from_numpy(fpn_util.features_for(coords.cpu().numpy())).cuda()
+stream_mode = os.environ.get("TRACE_STREAM") == "1"  # streaming: forward + prefetch of the next building, two steps traced
 with torch.no_grad():
-    for _ in range(3):
+    for _ in range(12 if stream_mode else 3):
         net([coords, feats])
+        if stream_mode:
+            net.prefetch(coords)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-        net([coords, feats])
+        for _ in range(2 if stream_mode else 1):
+            net([coords, feats])
+            if stream_mode:
+                net.prefetch(coords)
         torch.cuda.synchronize()
 out = os.path.join(ROOT, "gpurun_out", f"trace_{mode}.json")
 os.makedirs(os.path.dirname(out), exist_ok=True)
