@@ -6,6 +6,8 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <deque>
+#include <condition_variable>
 #include <chrono>
 #include <stdlib.h>
 
@@ -48,6 +50,7 @@ int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s, v
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
                        const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s);
 int tc_available();
+void set_pool_growth(int on);
 long debug_chunk_mallocs();
 long debug_chunk_waits();
 long debug_chunk_total_mb();
@@ -63,7 +66,10 @@ static int g_math_mode = 0;
 struct PrefetchOp { long v[13]; }; // kind, a[3], b[3], f[3], s[3]
 struct scn_metadata {
   scn::Metadata md;
-  std::thread worker, worker2;
+  // prefetch jobs of this Metadata that the process-wide worker threads have not finished yet
+  std::mutex jobMu;
+  std::condition_variable jobCv;
+  int pending = 0;
   std::atomic<bool> stop{false};
   std::vector<PrefetchOp> ops, ops2; // chain worker (strided convolutions = the grid pyramid) / everything else
   int device = 0;
@@ -84,6 +90,7 @@ const char *scn_last_error(void) { return scn::last_error(); }
 int scn_version(void) { return 1; }
 int scn_n_rulebook_bits(void) { return 32; }
 long scn_kernel_launch_count(void) { return scn::g_launches; }
+int scn_set_pool_growth(int on) { scn::set_pool_growth(on); return 0; }
 long scn_debug_counter(int which) { return which == 0 ? scn::debug_chunk_mallocs() : which == 1 ? scn::debug_chunk_waits() : scn::debug_chunk_total_mb(); }
 int scn_set_math_mode(int mode) {
   if (mode < 0 || mode > 2) { scn::set_error("math mode must be 0 (fp32), 1 (tf32) or 2 (bf16)"); return -2; }
@@ -107,12 +114,15 @@ int scn_metadata_create(scn_metadata **out, void *stream) {
   *out = m;
   return 0;
 }
+static void wait_jobs(scn_metadata *m) {
+  std::unique_lock<std::mutex> lk(m->jobMu);
+  m->jobCv.wait(lk, [&] { return m->pending == 0; });
+}
 void scn_metadata_destroy(scn_metadata *m) {
   if (!m) return;
   m->stop = true;
   m->md.set_chain_done(true);
-  if (m->worker.joinable()) m->worker.join();
-  if (m->worker2.joinable()) m->worker2.join();
+  wait_jobs(m);
   delete m;
   scn::timeline_dump();
 }
@@ -124,8 +134,6 @@ void scn_metadata_destroy(scn_metadata *m) {
 // in the same lazily-filled caches (Metadata.cpp:429-510) under the same keys; a failing hint is
 // ignored and the error resurfaces when the caller requests that entry itself.
 static void prefetch_worker(scn_metadata *m, int which) {
-  cudaSetDevice(m->device);
-  scn::set_prefetch_worker_thread(true, which);
   struct Done { scn_metadata *m; int which; ~Done() { if (which == 0) m->md.set_chain_done(true); else { m->md.worker2Done.store(true); m->md.cv.notify_all(); } } } done{m, which};
   for (const PrefetchOp &op : (which == 0 ? m->ops : m->ops2)) {
     if (m->stop) break;
@@ -147,11 +155,47 @@ static void prefetch_worker(scn_metadata *m, int which) {
     }
   }
 }
+// Two process-wide worker threads (chain / everything else) serve the prefetch jobs of all Metadata objects: a thread per
+// forward cost ~0.2 ms before its first kernel (creation + binding the CUDA context), on the critical path of the forward.
+namespace {
+struct WorkerPool {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<scn_metadata *> q[2];
+};
+WorkerPool *g_pool = nullptr; // never destroyed: the threads sleep on it until the process ends
+std::once_flag g_pool_once;
+void pool_main(int which) {
+  scn::set_prefetch_worker_thread(true, which);
+  int dev = -1;
+  for (;;) {
+    scn_metadata *m;
+    {
+      std::unique_lock<std::mutex> lk(g_pool->mu);
+      g_pool->cv.wait(lk, [&] { return !g_pool->q[which].empty(); });
+      m = g_pool->q[which].front();
+      g_pool->q[which].pop_front();
+    }
+    if (dev != m->device) { cudaSetDevice(m->device); dev = m->device; }
+    prefetch_worker(m, which);
+    { std::lock_guard<std::mutex> lk(m->jobMu); m->pending--; }
+    m->jobCv.notify_all();
+  }
+}
+void pool_submit(scn_metadata *m, int which) {
+  std::call_once(g_pool_once, [] {
+    g_pool = new WorkerPool();
+    for (int w = 0; w < 2; w++) std::thread(pool_main, w).detach();
+  });
+  { std::lock_guard<std::mutex> lk(m->jobMu); m->pending++; }
+  { std::lock_guard<std::mutex> lk(g_pool->mu); g_pool->q[which].push_back(m); }
+  g_pool->cv.notify_all();
+}
+} // namespace
 int scn_metadata_prefetch(scn_metadata *m, int n_ops, const long *ops) {
   if (!m) { scn::set_error("null scn_metadata handle"); return -3; }
   m->md.set_chain_done(true);
-  if (m->worker.joinable()) m->worker.join();
-  if (m->worker2.joinable()) m->worker2.join();
+  wait_jobs(m);
   m->ops.clear();
   m->ops2.clear();
   // The strided convolutions create the grids level by level: that chain is the critical path, so it
@@ -187,8 +231,8 @@ int scn_metadata_prefetch(scn_metadata *m, int n_ops, const long *ops) {
   }
   m->stop = false;
   m->md.set_chain_done(false);
-  m->worker = std::thread(prefetch_worker, m, 0);
-  if (!m->ops2.empty()) { m->md.worker2Done.store(false); m->worker2 = std::thread(prefetch_worker, m, 1); }
+  pool_submit(m, 0);
+  if (!m->ops2.empty()) { m->md.worker2Done.store(false); pool_submit(m, 1); }
   return 0;
 }
 
@@ -272,12 +316,15 @@ static int find_rb(scn_metadata *m, int kind, const long a[3], const long b[3], 
     *rb = &e->rb;
     return 0;
   }
-  std::lock_guard<std::mutex> lk(m->md.mapMu);
+  scn::ConvEntry *ce = nullptr;
   {
+    std::lock_guard<std::mutex> lk(m->md.mapMu);
     auto it = m->md.conv.find(scn::ConvKey{scn::P3{a[0], a[1], a[2]}, scn::P3{b[0], b[1], b[2]}, scn::P3{c[0], c[1], c[2]}});
     SCN_CHECK(it != m->md.conv.end() && it->second.rdy.ready, "convolution rulebook not built");
-    *rb = &it->second.rb;
+    ce = &it->second;
   }
+  SCN_TRY(m->md.ensure_conv_rules(*ce));
+  *rb = &ce->rb;
   return 0;
 }
 int scn_rulebook_info(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], int *n_lists, long *list_len) {
@@ -392,7 +439,9 @@ int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long out
     return scn::launch_conv_plan_tc(in, out, w, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, 1, Cin, Cout, nullptr, scn::g_math_mode, s, d.tileW,
                                     e->rb.nLists, m->md.find_grid(inS)->n, in_bf16, weight_tag, add_in, out_bf16, gf->n);
   }
+  SCN_TRY(m->md.ensure_conv_rules(*e));
   SCN_TRY(m->md.wait_ready(e->rdy));
+  SCN_TRY(m->md.wait_ready(e->rulesRdy));
   if (!single && gf->n) k_fill_rows_bias<<<scn::stream_grid((long)gf->n * Cout, 256), 256, 0, scn::LS(s)>>>(out, gf->n, Cout, bias);
   SCN_TRY(scn::launch_conv_list_simt(in, out, w, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, Cin, Cout, /*srcIsY=*/1, single ? 1 : 0, s));
   return plain_epilogue(out, add_in, out_bf16, gf->n, Cout, s);
@@ -414,7 +463,9 @@ int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS
   M_OR_FAIL(m);
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
+  SCN_TRY(m->md.ensure_conv_rules(*e));
   SCN_TRY(m->md.wait_ready(e->rdy));
+  SCN_TRY(m->md.wait_ready(e->rulesRdy));
   return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, m->md.find_grid(inS)->n,
                                  m->md.find_grid(outS)->n, Cin, Cout, 0, m->md.cstream);
 }
@@ -423,7 +474,9 @@ int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long ou
   M_OR_FAIL(m);
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(outS, inS, f, st, &e));
+  SCN_TRY(m->md.ensure_conv_rules(*e));
   SCN_TRY(m->md.wait_ready(e->rdy));
+  SCN_TRY(m->md.wait_ready(e->rulesRdy));
   return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, m->md.find_grid(inS)->n,
                                  m->md.find_grid(outS)->n, Cin, Cout, 1, m->md.cstream);
 }

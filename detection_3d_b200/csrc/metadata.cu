@@ -34,6 +34,8 @@ static int *pinned_get() {
 static std::vector<Chunk> g_chunks;
 static size_t g_chunk_bytes = 0;       // idle chunks
 static long g_chunk_mallocs = 0, g_chunk_waits = 0;
+std::atomic<int> g_pool_growth{0};
+void set_pool_growth(int on) { g_pool_growth.store(on); }
 long debug_chunk_mallocs() { return g_chunk_mallocs; }
 long debug_chunk_waits() { return g_chunk_waits; }
 long debug_chunk_total_mb() ;
@@ -164,7 +166,10 @@ void *Metadata::alloc_in(BuildCtx &c, size_t bytes) {
       if (b < 0 || g_chunks[i].cap < g_chunks[b].cap) b = i;
     }
     cudaGetLastError(); // cudaEventQuery leaves cudaErrorNotReady behind
-    if (best < 0 && bestBusy >= 0 && g_chunk_bytes_total + cap > kChunkGrow) { best = bestBusy; g_chunk_waits++; } // (cudaMalloc beside a busy GPU was measured at ~100 ms)
+    // Nothing finished: a Metadata built AHEAD of its forward (streaming, g_pool_growth) takes fresh memory so that it does
+    // not queue behind the forward that still owns the busy chunk; otherwise wait for that chunk -- a cudaMalloc beside a
+    // busy GPU was measured at 0.4-100 ms and would make one-building-at-a-time latency erratic.
+    if (best < 0 && bestBusy >= 0 && (!poolGrowth || g_chunk_bytes_total + cap > kChunkGrow)) { best = bestBusy; g_chunk_waits++; }
     if (best >= 0) { k = g_chunks[best]; g_chunks.erase(g_chunks.begin() + best); g_chunk_bytes -= k.cap; }
   }
   if (k.p) {
@@ -186,6 +191,7 @@ void *Metadata::alloc_in(BuildCtx &c, size_t bytes) {
 }
 void *Metadata::alloc(size_t bytes) { return alloc_in(cur(), bytes); }
 int Metadata::init() {
+  poolGrowth = g_pool_growth.load() != 0; // created ahead of its forward (FPN_Net.prefetch): see alloc_in
   static bool poolConfigured = false;
   if (!poolConfigured) {
     cudaMemPool_t pool;
@@ -804,8 +810,9 @@ __global__ void __launch_bounds__(kRuleTile) k_rule_write(int n, int K, MaskF ma
     }
   }
 }
+// write = false: counts and list offsets only (tileCntOut receives the per-tile prefix table for a later k_rule_write)
 template <class MaskF, class PairF>
-static int build_rule_lists(Metadata &M, int n, int K, MaskF maskf, PairF pairf, RuleBookDev &rb, int extraScalars) {
+static int build_rule_lists(Metadata &M, int n, int K, MaskF maskf, PairF pairf, RuleBookDev &rb, int extraScalars, bool write = true, int **tileCntOut = nullptr) {
   SCN_CHECK(K >= 1 && K <= 64, "filter volume must be <= 64");
   cudaStream_t s = M.cur().stream;
   rb.nLists = K;
@@ -823,6 +830,8 @@ static int build_rule_lists(Metadata &M, int n, int K, MaskF maskf, PairF pairf,
   SCN_CUDA(cudaStreamSynchronize(s));
   for (int L = 0; L <= K; L++) rb.off[L] = M.cur().h_scalars[128 + L];
   rb.total = rb.off[K];
+  if (tileCntOut) *tileCntOut = tileCnt;
+  if (!write) return 0;
   rb.pairs = M.alloc_n<int2>(std::max(1l, rb.total));
   SCN_CHECK(rb.pairs, "alloc");
   if (n > 0) k_rule_write<<<nTiles, kRuleTile, 0, LS(s)>>>(n, K, maskf, pairf, tileCnt, rb.d_off, rb.pairs);
@@ -1277,6 +1286,7 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   if (smallOn && G.M == 1 && gi->batch == 1 && gi->n > 0 && gi->n <= kSmallSites && gi->itemCtr.size() == 1 && gi->itemCtr[0] >= 0 &&
       ((outS[0] + 7) / 8) * ((outS[1] + 7) / 8) * ((outS[2] + 7) / 8) <= (1 << 16)) {
     SCN_TRY(get_conv_small(*gi, go, e, G));
+    SCN_TRY(mark_ready(e.rulesRdy)); // the one-launch build writes the lists as well
     SCN_TRY(mark_ready(go.rdy));
     { std::lock_guard<std::mutex> lk(mapMu); go.built = true; }
     cv.notify_all();
@@ -1303,7 +1313,8 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   SCN_TRY(run_scan(*this, E, EvFirstIn{evQ, firstEv}, EvFirstOut{evQ, evPts, go.p2id, go.id2p, go.coords, go.batch > 1 ? sc + 8 : nullptr}, sc + 3));
   // rule lists (one sync: list offsets + nOut + per-item counts)
   SCN_TRY(build_rule_lists(*this, n, G.K, ConvMask{G, gi->rank2id, gi->coords},
-                           ConvPair{G, gi->rank2id, gi->coords, evQ, go.p2id}, e.rb, 64));
+                           ConvPair{G, gi->rank2id, gi->coords, evQ, go.p2id}, e.rb, 64, /*write=*/false, &e.tileCnt));
+  e.evQ = evQ;
   go.n = cur().h_scalars[3];
   SCN_CHECK(cur().h_scalars[1] == go.n, "internal: unique count mismatch (conv)");
   go.itemCount.assign(go.batch, 0);
@@ -1324,6 +1335,25 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   cv.notify_all();
   SCN_TRY(mark_ready(e.rdy));
   return 0;
+}
+
+// The (in,out) lists of a strided convolution in the reference's order (ConvolutionRules.h:11-34), written on demand.
+int Metadata::ensure_conv_rules(ConvEntry &e) {
+  if (!claim(e.rulesRdy)) return 0;
+  struct Guard { Metadata &m; Ready &r; ~Guard() { if (!r.ready) m.unclaim(r); } } guard{*this, e.rulesRdy};
+  BuildLock bl(*this);
+  Grid *gi = find_grid(e.in.data()), *go = find_grid(e.out.data());
+  SCN_CHECK(gi && go && e.evQ && e.tileCnt, "convolution rulebook not built");
+  SCN_TRY(need(e.rdy));
+  SCN_TRY(need(gi->rankRdy));
+  const int n = gi->n, K = e.geom.K;
+  e.rb.pairs = alloc_n<int2>(std::max(1l, e.rb.total));
+  SCN_CHECK(e.rb.pairs, "alloc");
+  if (n > 0)
+    k_rule_write<<<cdiv(n, kRuleTile), kRuleTile, 0, LS(cur().stream)>>>(n, K, ConvMask{e.geom, gi->rank2id, gi->coords},
+                                                                         ConvPair{e.geom, gi->rank2id, gi->coords, e.evQ, go->p2id}, e.tileCnt, e.rb.d_off, e.rb.pairs);
+  SCN_CUDA(cudaGetLastError());
+  return mark_ready(e.rulesRdy);
 }
 
 // ------------------------------------------------------------------ deconvolution plan

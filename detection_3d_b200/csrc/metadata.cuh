@@ -83,7 +83,12 @@ struct DeconvPlan {
 };
 struct ConvGeomHost { int f[3], s[3], outS[3], cnt[3], M, K; };
 struct SubmEntry { RuleBookDev rb; NbrPlan plan; Ready rdy, rulesRdy; P3 sz; bool assigned = false; /* the second prefetch worker will build it */ }; // rb.pairs / offsets only after ensure_subm_rules
-struct ConvEntry { RuleBookDev rb; NbrPlan plan; P3 out; P3 in; ConvGeomHost geom; DeconvPlan deconv; Ready rdy, deconvRdy; };
+// rb.pairs (the (in,out) lists in the reference's order) are written on demand (ensure_conv_rules: backward pass, rulebook
+// inspection, CUDA-core deconvolution); the forward needs only the plan, the list offsets and the rule count.
+struct ConvEntry {
+  RuleBookDev rb; NbrPlan plan; P3 out; P3 in; ConvGeomHost geom; DeconvPlan deconv; Ready rdy, deconvRdy, rulesRdy;
+  const int *evQ = nullptr; int *tileCnt = nullptr; // kept for the deferred list write
+};
 
 struct InputRules {
   int mode = 0, maxActive = 0, nIn = 0, nOut = 0;
@@ -120,6 +125,7 @@ struct Metadata {
   // only drains a short build queue while the convolutions already submitted keep the GPU busy (the
   // reference is synchronous throughout, SURVEY.md section 8b "Threading / streams").
   cudaStream_t cstream = 0;  // caller's compute stream
+  bool poolGrowth = false;   // may take fresh memory instead of waiting for chunks a running forward still owns
   BuildCtx cx[2];
   int nCtx = 1;
   BuildCtx &cur();           // build context of the calling thread
@@ -167,6 +173,7 @@ struct Metadata {
   int ensure_subm_rules(SubmEntry &e);
   int get_conv(const long *inS, const long *outS, const long *f, const long *s, ConvEntry **out);
   int get_conv_small(Grid &gi, Grid &go, ConvEntry &e, const ConvGeomHost &G); // one-launch build for small input grids
+  int ensure_conv_rules(ConvEntry &e);
   int spatial_locations(const long *sz, long *out, int outOnDevice);
   int build_tile_masks(NbrPlan &plan);
   int get_deconv_plan(ConvEntry &e);

@@ -203,6 +203,25 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
       bn.a[21] = c.a[21];
     }
   }
+  { // bf16 mode: a BatchNorm output that only feeds tensor-core convolutions gathering its bf16 copy is never read in fp32;
+    // such BatchNorm ops (a[19] = 1) write the bf16 copy only.  Deconvolutions are excluded (their CUDA-core fallback is a
+    // run-time decision), as are outputs, addends and anything whose channel counts take the TF32 / CUDA-core route.
+    std::vector<int> good(n_regs, 0), bad(n_regs, 0);
+    for (int i = 0; i < n_outputs; i++) bad[outputs[i]] = 1;
+    for (const Op &o : p->ops) {
+      if (o.kind == K_INPUT) continue;
+      if (o.kind == K_ADD) { bad[o.a[0]] = 1; bad[o.a[1]] = 1; continue; }
+      if (o.kind == K_BN) { bad[o.a[0]] = 1; continue; }
+      const long Cin = o.kind == K_SUBM ? o.a[10] : o.a[16], Cout = o.kind == K_SUBM ? o.a[11] : o.a[17];
+      long K = 1;
+      for (int d = 0; d < 3; d++) K *= o.kind == K_SUBM ? o.a[5 + d] : o.a[8 + d];
+      const bool tc = Cout % 32 == 0 && Cout >= 32 && Cout <= 256 && K <= 63 && (Cin % 64 == 0 || (Cin == 32 && Cout <= 128));
+      if (o.kind != K_DECONV && tc) good[o.a[0]] = 1; else bad[o.a[0]] = 1;
+      if (o.a[22] >= 0) bad[o.a[22]] = 1;
+      if (o.a[18] >= 0) bad[o.a[18]] = 1; // whether a lateral is folded in (bf16 copy) or run on its own is decided at run time: keep the fp32 rows
+    }
+    for (Op &bn : p->ops) if (bn.kind == K_BN) bn.a[19] = (good[bn.a[1]] && !bad[bn.a[1]] && bn.a[2] % 32 == 0) ? 1 : 0;
+  }
   p->nRegs = n_regs;
   p->lastUse.assign(n_regs, -1);
   p->isOutput.assign(n_regs, 0);
@@ -283,12 +302,12 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   if (!p->bnScratch) SCN_CUDA(cudaMalloc((void **)&p->bnScratch, 2 * scn::kBnMaxC * sizeof(float)));
   auto P = [&](long i) -> const float * { return (i < 0 || i >= n_params) ? nullptr : static_cast<const float *>(params[i]); };
   auto T = [&](long i) -> long long { return (i < 0 || i >= n_params || !tags) ? 0 : tags[i]; };
-  auto alloc_reg = [&](long r, long rows, int cols, bool shadow) -> int {
+  auto alloc_reg = [&](long r, long rows, int cols, bool shadow, bool halfOnly = false) -> int {
     Reg &R = p->regs[r];
     R.rows = rows;
     R.cols = cols;
-    R.p = static_cast<float *>(slot_get(p, (size_t)std::max(1l, rows * cols) * 4));
-    if (!R.p) return -1;
+    R.p = halfOnly ? nullptr : static_cast<float *>(slot_get(p, (size_t)std::max(1l, rows * cols) * 4));
+    if (!R.p && !halfOnly) return -1;
     if (shadow && mode == 2 && cols % 32 == 0 && rows > 0) {
       R.p16 = slot_get(p, (size_t)rows * cols * 2);
       if (!R.p16) return -1;
@@ -386,8 +405,10 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       }
       case K_BN: { // in, out, C, weight, bias, running mean, running var, mode; f: eps, momentum, leakiness
         const Reg &I = p->regs[a[0]];
-        rc = alloc_reg(a[1], I.rows, (int)a[2], true);
-        if (rc == 0 && a[21] >= 0 && p->statsDone[a[21]] && I.rows > 0) {
+        const bool fromSums = a[21] >= 0 && p->statsDone[a[21]] && I.rows > 0;
+        const bool halfOnly = fromSums && a[19] == 1 && mode == 2 && scn_tensor_core_path_available();
+        rc = alloc_reg(a[1], I.rows, (int)a[2], true, halfOnly);
+        if (rc == 0 && fromSums) {
           rc = scn::bn_forward_from_sums(I.p, p->regs[a[1]].p, I.rows, (int)a[2], p->stats + a[21] * statsStride, p->bnScratch, p->bnScratch + scn::kBnMaxC,
                                          const_cast<float *>(P(a[5])), const_cast<float *>(P(a[6])), P(a[3]), P(a[4]), (float)op.f[0], (float)op.f[1], (int)a[7],
                                          (float)op.f[2], s, p->regs[a[1]].p16);

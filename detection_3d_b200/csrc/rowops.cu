@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256) k_bn_apply_sums(const float *__restrict__
     float4 o;
     o.x = fmaf(v.x, a.x, b.x); o.y = fmaf(v.y, a.y, b.y); o.z = fmaf(v.z, a.z, b.z); o.w = fmaf(v.w, a.w, b.w);
     o.x = o.x > 0 ? o.x : o.x * leak; o.y = o.y > 0 ? o.y : o.y * leak; o.z = o.z > 0 ? o.z : o.z * leak; o.w = o.w > 0 ? o.w : o.w * leak;
-    reinterpret_cast<float4 *>(y)[i] = o;
+    if (y) reinterpret_cast<float4 *>(y)[i] = o; // y == nullptr: only the bf16 copy is consumed downstream
     if (y16) store_bf16x4(y16, i, o);
   }
 }

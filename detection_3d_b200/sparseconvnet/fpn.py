@@ -146,8 +146,12 @@ class FPN_Net(nn.Module):
         if native.math_mode() != prog.math_mode:
             return False
         prog.throttle()  # before the Metadata is created: it then recycles the memory of the forward that just finished
-        md = L.Metadata(self.dimension)
-        prog.prepare(md, coords)
+        native.lib().scn_set_pool_growth(1)  # built ahead: do not queue behind a running forward for memory
+        try:
+            md = L.Metadata(self.dimension)
+            prog.prepare(md, coords)
+        finally:
+            native.lib().scn_set_pool_growth(0)
         q = self.__dict__.setdefault("_prefetched", [])
         q.append((coords, coords._version, md))
         del q[:-4]  # at most a few buildings ahead

@@ -169,6 +169,9 @@ int scn_program_prepare(scn_program *p, scn_metadata *m, const long *coords, int
 /* Blocks until at most one forward of this program is still running on the GPU (call before scn_metadata_create of the
  * Metadata to prepare: it then reuses the memory of the forward that just finished). */
 int scn_program_throttle(scn_program *p);
+/* 1 while a Metadata is created / prepared AHEAD of its forward: its memory may then come from fresh chunks instead of
+ * waiting for chunks a still-running forward owns (bounded pool growth); 0 (default) otherwise. */
+int scn_set_pool_growth(int on);
 int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const float **ptr);
 /* device-to-device copy on `stream` (hands an output register to a caller-owned tensor) */
 int scn_copy_device(void *dst, const void *src, long bytes, void *stream);
