@@ -168,6 +168,15 @@ def main():
     import detection_3d_b200.sparseconvnet as scn
     from detection_3d_b200 import synthetic
 
+    if world > 1 and os.environ.get("BENCH_AFFINITY", "1") == "1" and hasattr(os, "sched_setaffinity"):
+        # one process per GPU: give every rank its own slice of the host cores (main thread + the two build workers wake up on
+        # GPU events dozens of times per forward; ranks migrating over each other's cores cost ~2 ms per step at N = 2)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per] or cores)
+        except OSError:
+            pass
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
