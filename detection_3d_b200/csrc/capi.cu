@@ -48,7 +48,8 @@ int input_forward(const float *in, float *out, int nOut, int maxActive, int C, c
 int input_backward(float *din, const float *dout, long nIn, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
 int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s, void *o16);
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
-                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s);
+                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn = 0);
+int transpose_weights(const float *W, float *Wt, int K, int Cin, int Cout, int reverse, cudaStream_t s);
 int tc_available();
 void set_pool_growth(int on);
 long debug_chunk_mallocs();
@@ -447,6 +448,20 @@ int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long out
   return plain_epilogue(out, add_in, out_bf16, gf->n, Cout, s);
 }
 
+// d_in = forward tensor-core convolution of d_out with transposed weights (conv_bwd.cu header).  W: [K][Cin][Cout] of the
+// FORWARD layer; d_out rows have Cout channels (nSrcRows of them), d_in rows Cin channels (nDstRows, all written by the plan).
+static int dIn_tensor_core(Metadata &M, const float *d_out, float *d_in, const float *W, int K, int Cin, int Cout, int reverse, const int *nbr,
+                           const int *outRow, const unsigned long long *tileMask, int nOutPlan, const int *tileW, long nSrcRows, long nDstRows) {
+  cudaStream_t s = M.cstream;
+  float *Wt = nullptr;
+  SCN_CUDA(cudaMallocAsync((void **)&Wt, (size_t)K * Cin * Cout * 4, s));
+  int r = scn::transpose_weights(W, Wt, K, Cin, Cout, reverse, s);
+  if (r == 0)
+    r = scn::launch_conv_plan_tc(d_out, d_in, Wt, nbr, outRow, tileMask, nOutPlan, tileW ? 1 : K, /*Cin=*/Cout, /*Cout=*/Cin, nullptr, scn::g_math_mode, s, tileW, K,
+                                 nSrcRows, nullptr, 0, nullptr, nullptr, nDstRows);
+  cudaFreeAsync(Wt, s);
+  return r;
+}
 int scn_submanifold_convolution_backward(scn_metadata *m, const long sz[3], const long f[3], const float *in, float *d_in, const float *d_out,
                                          const float *w, float *dw, float *d_bias, int Cin, int Cout) {
   M_OR_FAIL(m);
@@ -456,7 +471,10 @@ int scn_submanifold_convolution_backward(scn_metadata *m, const long sz[3], cons
   scn::Grid *g = m->md.find_grid(sz);
   SCN_TRY(m->md.wait_ready(e->rdy));
   SCN_TRY(m->md.wait_ready(e->rulesRdy));
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.cstream);
+  // d_in on the tensor cores: the plan of an odd filter is symmetric, d_in[q] = sum_j d_out[nbr[q][j]] @ W[K-1-j]^T
+  const bool tcIn = tc_ok(Cout, Cin, e->plan.K) && f[0] % 2 == 1 && f[1] % 2 == 1 && f[2] % 2 == 1 && g->n > 0;
+  if (tcIn) SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->plan.K, Cin, Cout, /*reverse=*/1, e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut, nullptr, g->n, g->n));
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.cstream, tcIn);
 }
 int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                              float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
@@ -466,8 +484,16 @@ int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS
   SCN_TRY(m->md.ensure_conv_rules(*e));
   SCN_TRY(m->md.wait_ready(e->rdy));
   SCN_TRY(m->md.wait_ready(e->rulesRdy));
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, m->md.find_grid(inS)->n,
-                                 m->md.find_grid(outS)->n, Cin, Cout, 0, m->md.cstream);
+  // d_in (fine rows) on the tensor cores: a deconvolution of d_out with W^T over the single-parent plan
+  scn::Grid *gf = m->md.find_grid(inS), *gc = m->md.find_grid(outS);
+  const bool tcIn = tc_ok(Cout, Cin, 1) && e->geom.M == 1 && e->rb.total == gf->n && gf->n > 0;
+  if (tcIn) {
+    SCN_TRY(m->md.get_deconv_plan(*e));
+    SCN_TRY(m->md.wait_ready(e->deconvRdy));
+    const scn::DeconvPlan &d = e->deconv;
+    SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->rb.nLists, Cin, Cout, /*reverse=*/0, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, d.tileW, gc->n, gf->n));
+  }
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, gf->n, gc->n, Cin, Cout, 0, m->md.cstream, tcIn);
 }
 int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                                float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
@@ -477,8 +503,11 @@ int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long ou
   SCN_TRY(m->md.ensure_conv_rules(*e));
   SCN_TRY(m->md.wait_ready(e->rdy));
   SCN_TRY(m->md.wait_ready(e->rulesRdy));
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, m->md.find_grid(inS)->n,
-                                 m->md.find_grid(outS)->n, Cin, Cout, 1, m->md.cstream);
+  // d_in (coarse rows) on the tensor cores: the strided convolution fine -> coarse of d_out with W^T
+  scn::Grid *gc = m->md.find_grid(inS), *gf = m->md.find_grid(outS);
+  const bool tcIn = tc_ok(Cout, Cin, e->plan.K) && gc->n > 0;
+  if (tcIn) SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->plan.K, Cin, Cout, /*reverse=*/0, e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut, nullptr, gf->n, gc->n));
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, gc->n, gf->n, Cin, Cout, 1, m->md.cstream, tcIn);
 }
 
 int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *save_mean, float *save_invstd, float *running_mean,

@@ -1,5 +1,7 @@
 // Backward of the three convolution kinds (fp32 CUDA cores).
-//   dIn  = sum_k scatter( gather(dOut, rules_k.dst) @ W[k]^T )   -> the forward list kernel run on
+//   dIn  = sum_k scatter( gather(dOut, rules_k.dst) @ W[k]^T )   -> in tf32 / bf16 mode the tcgen05 FORWARD kernel on
+//          (dOut, W^T): the submanifold plan is symmetric (dIn[q] = sum_j dOut[nbr[q][j]] @ W[K-1-j]^T), the input
+//          gradient of a strided convolution is a deconvolution and vice versa (capi.cu); in fp32 mode the forward list kernel run on
 //          (dOut, W^T) with the pair columns swapped, lists back to back (a source row occurs at
 //          most once per list, so the read-modify-write is race free, as in the reference).
 //   dW[k] = gather(in, rules_k.src)^T @ gather(dOut, rules_k.dst) -> split over rule chunks, fp32
@@ -11,14 +13,20 @@ namespace scn {
 int launch_conv_list_simt(const float *in, float *out, const float *W, const int2 *pairs, const int *d_off, const int *offHost, int K, int Cin,
                           int Cout, int srcIsY, int singlePass, cudaStream_t s);
 
-__global__ void k_transpose_w(const float *__restrict__ W, float *__restrict__ Wt, int K, int Cin, int Cout) {
+// Wt[k'][co][ci] = W[k][ci][co], k' = k or (reverse) K - 1 - k
+__global__ void k_transpose_w(const float *__restrict__ W, float *__restrict__ Wt, int K, int Cin, int Cout, int reverse) {
   long n = (long)K * Cin * Cout;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     int co = (int)(i % Cout);
     long t = i / Cout;
     int ci = (int)(t % Cin), k = (int)(t / Cin);
-    Wt[((long)k * Cout + co) * Cin + ci] = W[i];
+    Wt[((long)(reverse ? K - 1 - k : k) * Cout + co) * Cin + ci] = W[i];
   }
+}
+int transpose_weights(const float *W, float *Wt, int K, int Cin, int Cout, int reverse, cudaStream_t s) {
+  k_transpose_w<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, Wt, K, Cin, Cout, reverse);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
 }
 
 constexpr int BM = 64, BN = 64, BK = 16, BPAD = 4;
@@ -85,22 +93,25 @@ __global__ void k_colsum(const float *__restrict__ x, long n, int C, float *__re
   atomicAdd(out + c, s);
 }
 
+// skipDIn: the caller computes d_in itself (tensor-core forward kernel on (d_out, W^T)); only dW / d_bias here
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
-                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s) {
-  SCN_CUDA(cudaMemsetAsync(d_in, 0, (size_t)nInRows * Cin * 4, s));
+                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn) {
+  if (!skipDIn) SCN_CUDA(cudaMemsetAsync(d_in, 0, (size_t)nInRows * Cin * 4, s));
   SCN_CUDA(cudaMemsetAsync(dW, 0, (size_t)K * Cin * Cout * 4, s));
   if (d_bias) {
     SCN_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)Cout * 4, s));
     if (nOutRows) k_colsum<<<dim3(kSMs * 2, cdiv(Cout, 128)), 128, 0, LS(s)>>>(d_out, nOutRows, Cout, d_bias);
   }
   if (offHost[K] == 0) return 0;
-  float *Wt = nullptr;
-  SCN_CUDA(cudaMallocAsync((void **)&Wt, (size_t)K * Cin * Cout * 4, s));
-  k_transpose_w<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, Wt, K, Cin, Cout);
-  // dIn: rows of d_out gathered by the forward destination column, scattered to the forward source column
-  int r = launch_conv_list_simt(d_out, d_in, Wt, pairs, d_off, offHost, K, Cout, Cin, !srcIsY, /*singlePass=*/0, s);
-  cudaFreeAsync(Wt, s);
-  if (r) return r;
+  if (!skipDIn) {
+    float *Wt = nullptr;
+    SCN_CUDA(cudaMallocAsync((void **)&Wt, (size_t)K * Cin * Cout * 4, s));
+    k_transpose_w<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, Wt, K, Cin, Cout, 0);
+    // dIn: rows of d_out gathered by the forward destination column, scattered to the forward source column
+    int r = launch_conv_list_simt(d_out, d_in, Wt, pairs, d_off, offHost, K, Cout, Cin, !srcIsY, /*singlePass=*/0, s);
+    cudaFreeAsync(Wt, s);
+    if (r) return r;
+  }
   for (int L_ = 0; L_ < K; L_++) {
     int len = offHost[L_ + 1] - offHost[L_];
     if (!len) continue;

@@ -388,6 +388,59 @@ def test_tc_submanifold_forward(cin, cout, f, math):
     _close(out.cpu().numpy(), want, rtol=TC_TOL[math][0], atol=TC_TOL[math][1])
 
 
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+def test_tc_input_gradients(math):
+    """tf32 / bf16 mode: the input gradient of all three convolution kinds runs on the tcgen05 forward kernel with transposed
+    weights (submanifold: symmetric plan with reversed offsets; strided convolution: a deconvolution; deconvolution: the
+    strided convolution); d_weight stays on the fp32 CUDA cores.  Checked against the oracle's backward."""
+    scn, G, O = _setup_levels()
+    _tc_or_skip(scn)
+    L = torch.LongTensor
+    T = lambda a: torch.from_numpy(a).cuda()
+    rtol, atol = TC_TOL[math]
+    try:
+        scn.set_math_mode(math)
+        sz = [64, 64, 32]
+        n = O.nactive(sz)
+        for cin, cout, f in [(64, 128, 3), (128, 128, 3), (32, 32, 3), (32, 128, 1), (256, 64, 3)]:
+            rs = np.random.RandomState(cin + 3 * cout + f)
+            x, dy = rs.randn(n, cin).astype(np.float32), rs.randn(n, cout).astype(np.float32)
+            w = (rs.randn(f ** 3, 1, cin, cout) * (2.0 / (cin * f ** 3)) ** 0.5).astype(np.float32)
+            rules = O.submanifold_rules(sz, [f] * 3)
+            out = torch.empty(0, device="cuda")
+            scn.SCN.SubmanifoldConvolution_updateOutput(L(sz), L([f] * 3), G.m, T(x), out, T(w), torch.Tensor())
+            din_w, dw_w = so.o_conv_backward(x, dy, w, rules)
+            din, dw = torch.empty(0, device="cuda"), torch.zeros(w.shape, device="cuda")
+            scn.SCN.SubmanifoldConvolution_backward(L(sz), L([f] * 3), G.m, T(x), din, T(dy), T(w), dw, torch.Tensor())
+            _close(din.cpu().numpy(), din_w, rtol=rtol, atol=atol)
+            _close(dw.cpu().numpy(), dw_w, rtol=1e-3, atol=1e-4)
+        a, b, f, s = [64, 64, 32], [32, 32, 16], [2, 2, 2], [2, 2, 2]
+        rules = O.conv_rules(a, b, f, s)
+        na, nb = O.nactive(a), O.nactive(b)
+        for cin, cout in [(32, 64), (128, 128)]:
+            rs = np.random.RandomState(cin + cout)
+            x, dy = rs.randn(na, cin).astype(np.float32), rs.randn(nb, cout).astype(np.float32)
+            w = (rs.randn(8, 1, cin, cout) * (2.0 / (cin * 8)) ** 0.5).astype(np.float32)
+            out = torch.empty(0, device="cuda")
+            scn.SCN.Convolution_updateOutput(L(a), L(b), L(f), L(s), G.m, T(x), out, T(w), torch.Tensor())
+            din_w, dw_w = so.o_conv_backward(x, dy, w, rules)
+            din, dw = torch.empty(0, device="cuda"), torch.zeros(w.shape, device="cuda")
+            scn.SCN.Convolution_backward(L(a), L(b), L(f), L(s), G.m, T(x), din, T(dy), T(w), dw, torch.Tensor())
+            _close(din.cpu().numpy(), din_w, rtol=rtol, atol=atol)
+            _close(dw.cpu().numpy(), dw_w, rtol=1e-3, atol=1e-4)
+            xc, dyf = rs.randn(nb, cin).astype(np.float32), rs.randn(na, cout).astype(np.float32)
+            out = torch.empty(0, device="cuda")
+            scn.SCN.Deconvolution_updateOutput(L(b), L(a), L(f), L(s), G.m, T(xc), out, T(w), torch.Tensor())
+            din_w, dw_w = so.o_conv_backward(xc, dyf, w, rules, deconv=True)
+            din, dw = torch.empty(0, device="cuda"), torch.zeros(w.shape, device="cuda")
+            scn.SCN.Deconvolution_backward(L(b), L(a), L(f), L(s), G.m, T(xc), din, T(dyf), T(w), dw, torch.Tensor())
+            _close(din.cpu().numpy(), din_w, rtol=rtol, atol=atol)
+            _close(dw.cpu().numpy(), dw_w, rtol=1e-3, atol=1e-4)
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+
+
 def test_bf16_shadow_from_batchnorm_and_add():
     """In 'bf16' mode BatchNorm / add outputs carry a bfloat16 copy written by the same kernel; the
     convolution that follows gathers from it.  The copy must equal the fp32 output rounded to nearest,
