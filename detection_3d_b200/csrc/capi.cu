@@ -48,7 +48,7 @@ int input_forward(const float *in, float *out, int nOut, int maxActive, int C, c
 int input_backward(float *din, const float *dout, long nIn, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
 int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s, void *o16);
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
-                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn = 0);
+                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn = 0, int mathMode = 0);
 int transpose_weights(const float *W, float *Wt, int K, int Cin, int Cout, int reverse, cudaStream_t s);
 int tc_available();
 void set_pool_growth(int on);
@@ -474,7 +474,7 @@ int scn_submanifold_convolution_backward(scn_metadata *m, const long sz[3], cons
   // d_in on the tensor cores: the plan of an odd filter is symmetric, d_in[q] = sum_j d_out[nbr[q][j]] @ W[K-1-j]^T
   const bool tcIn = tc_ok(Cout, Cin, e->plan.K) && f[0] % 2 == 1 && f[1] % 2 == 1 && f[2] % 2 == 1 && g->n > 0;
   if (tcIn) SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->plan.K, Cin, Cout, /*reverse=*/1, e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut, nullptr, g->n, g->n));
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.cstream, tcIn);
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.cstream, tcIn, scn::g_math_mode);
 }
 int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                              float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
@@ -493,7 +493,7 @@ int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS
     const scn::DeconvPlan &d = e->deconv;
     SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->rb.nLists, Cin, Cout, /*reverse=*/0, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, d.tileW, gc->n, gf->n));
   }
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, gf->n, gc->n, Cin, Cout, 0, m->md.cstream, tcIn);
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, gf->n, gc->n, Cin, Cout, 0, m->md.cstream, tcIn, scn::g_math_mode);
 }
 int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                                float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
@@ -507,7 +507,7 @@ int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long ou
   scn::Grid *gc = m->md.find_grid(inS), *gf = m->md.find_grid(outS);
   const bool tcIn = tc_ok(Cout, Cin, e->plan.K) && gc->n > 0;
   if (tcIn) SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->plan.K, Cin, Cout, /*reverse=*/0, e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut, nullptr, gf->n, gc->n));
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, gc->n, gf->n, Cin, Cout, 1, m->md.cstream, tcIn);
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, gc->n, gf->n, Cin, Cout, 1, m->md.cstream, tcIn, scn::g_math_mode);
 }
 
 int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *save_mean, float *save_invstd, float *running_mean,

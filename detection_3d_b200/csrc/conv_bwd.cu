@@ -12,6 +12,8 @@
 namespace scn {
 int launch_conv_list_simt(const float *in, float *out, const float *W, const int2 *pairs, const int *d_off, const int *offHost, int K, int Cin,
                           int Cout, int srcIsY, int singlePass, cudaStream_t s);
+int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2 *pairs, const int *d_off, const int *offHost, int K, long nInRows,
+                      long nOutRows, int Cin, int Cout, int srcIsY, int mathMode, cudaStream_t s);
 
 // Wt[k'][co][ci] = W[k][ci][co], k' = k or (reverse) K - 1 - k
 __global__ void k_transpose_w(const float *__restrict__ W, float *__restrict__ Wt, int K, int Cin, int Cout, int reverse) {
@@ -95,7 +97,7 @@ __global__ void k_colsum(const float *__restrict__ x, long n, int C, float *__re
 
 // skipDIn: the caller computes d_in itself (tensor-core forward kernel on (d_out, W^T)); only dW / d_bias here
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
-                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn) {
+                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn, int mathMode) {
   if (!skipDIn) SCN_CUDA(cudaMemsetAsync(d_in, 0, (size_t)nInRows * Cin * 4, s));
   SCN_CUDA(cudaMemsetAsync(dW, 0, (size_t)K * Cin * Cout * 4, s));
   if (d_bias) {
@@ -111,6 +113,10 @@ int conv_backward_simt(const float *in, float *d_in, const float *d_out, const f
     int r = launch_conv_list_simt(d_out, d_in, Wt, pairs, d_off, offHost, K, Cout, Cin, !srcIsY, /*singlePass=*/0, s);
     cudaFreeAsync(Wt, s);
     if (r) return r;
+  }
+  if (mathMode != 0) { // weight gradient on the tensor cores where the channel counts allow (conv_tc.cu, conv_dw_tc)
+    int r = launch_conv_dw_tc(in, d_out, dW, pairs, d_off, offHost, K, nInRows, nOutRows, Cin, Cout, srcIsY, mathMode, s);
+    if (r <= 0) return r;
   }
   for (int L_ = 0; L_ < K; L_++) {
     int len = offHost[L_ + 1] - offHost[L_];

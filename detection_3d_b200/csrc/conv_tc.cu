@@ -883,4 +883,204 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   return 0;
 }
 
+// ====================================================================== weight gradient on the tensor cores
+//   dW[k] = sum over the rules (i, o) of filter offset k of   in[i]^T (Cin x 1)  *  dOut[o] (1 x Cout)
+// = a GEMM with M = Cin, N = Cout and the RULES as the reduction dimension.  The gathered rows land in shared memory
+// exactly as in the forward kernel (one 128-byte swizzled row per rule and 64-channel block); read as an MN-MAJOR
+// operand (instruction descriptor bits 15 / 16, shared-memory descriptor LBO = distance between channel blocks, SBO =
+// 1024 B between groups of 8 rules) the very same bytes are the transposed matrices the product needs -- no transpose
+// pass, both operands are plain row gathers.  Replaces dConvolution_KMxKN_backward_dW_A/B (SCN/CUDA/Convolution.cu:249-410).
+// One CTA per SM: 4 epilogue warps (TMEM -> red.global.add), 8 producer warps, 1 MMA warp; a work item is a chunk of
+// one offset's rule list, its partial dW[k] is accumulated in TMEM and added to global memory once.
+struct DwParams {
+  const unsigned char *a, *b; // operand-typed rows: `in` (rowBytesA per row) and `d_out` (rowBytesB)
+  const int2 *pairs;
+  const int *d_off;           // K + 1 list offsets
+  float *dW;
+  int K, Cin, Cout, chunk, srcIsY, rowBytesA, rowBytesB, R, S, nAcc;
+};
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lboBytes) {
+  return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lboBytes >> 4) & 0x3fffu) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+template <bool BF16>
+__global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ int s_first[66]; // first work item of every list (prefix of ceil(len / chunk))
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = P.R, nBa = P.rowBytesA / 128, nBb = P.rowBytesB / 128;
+  const uint32_t blockBytes = (uint32_t)R * 128u, stageBytes = (uint32_t)(nBa + nBb) * blockBytes;
+  unsigned char *sStage = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStage + (size_t)P.S * stageBytes);
+  uint64_t *full = bars, *empty = bars + P.S, *accFull = bars + 2 * P.S, *accEmpty = accFull + 2;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 2);
+  if (tid == 0) {
+    for (int i = 0; i < P.S; i++) { mbar_init(smem_u32(full + i), 8 * 32); mbar_init(smem_u32(empty + i), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int a = 0;
+    for (int k = 0; k < P.K; k++) { s_first[k] = a; a += (P.d_off[k + 1] - P.d_off[k] + P.chunk - 1) / P.chunk; }
+    s_first[P.K] = a;
+  }
+  constexpr int kMmaWarp = 12;
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemBase = *tmemSlot;
+  const int nItems = s_first[P.K];
+  const int nMh = P.Cin / 128, accCols = nMh * P.Cout;
+  // item -> (list k, first rule, number of rules)
+  auto item = [&](int w, int &k, int &r0, int &cnt) {
+    k = 0;
+    while (s_first[k + 1] <= w) k++;
+    const int lo = __ldg(P.d_off + k), hi = __ldg(P.d_off + k + 1);
+    r0 = lo + (w - s_first[k]) * P.chunk;
+    cnt = min(P.chunk, hi - r0);
+  };
+  if (warp < 4) {
+    // ---------------- epilogue: partial dW[k] of the item -> global memory (fp32 reductions)
+    int it = 0;
+    for (int w = blockIdx.x; w < nItems; w += gridDim.x, it++) {
+      int k, r0, cnt;
+      item(w, k, r0, cnt);
+      const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
+      mbar_wait(smem_u32(accFull + a), use & 1);
+      tc_fence_after();
+      for (int mh = 0; mh < nMh; mh++) {
+        const int ci = mh * 128 + warp * 32 + lane;
+        float *dst = P.dW + ((size_t)k * P.Cin + ci) * P.Cout;
+        for (int c0 = 0; c0 < P.Cout; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld(tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * accCols + mh * P.Cout + c0), v);
+#pragma unroll
+          for (int j = 0; j < 32; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(accEmpty + a));
+    }
+  } else if (warp < 12) {
+    // ---------------- producers: rows of `in` by the rules' source ids, rows of `d_out` by their destination ids
+    const int pw = warp - 4, RW = R / 8; // rules per warp and stage (16 or 8)
+    const int chunk = lane & 7, rsub = lane >> 3;
+    uint32_t slot = 0, round = 0;
+    for (int w = blockIdx.x; w < nItems; w += gridDim.x) {
+      int k, r0, cnt;
+      item(w, k, r0, cnt);
+      for (int base = 0; base < cnt; base += R) {
+        const int rr = base + pw * RW + (lane & (RW - 1));
+        int2 pr = make_int2(-1, -1);
+        if (rr < cnt) pr = __ldg(P.pairs + r0 + rr);
+        const int srcId = P.srcIsY ? pr.y : pr.x, dstId = P.srcIsY ? pr.x : pr.y;
+        mbar_wait(smem_u32(empty + slot), (round & 1u) ^ 1u);
+        const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
+        for (int i = 0; i < RW / 4; i++) {
+          const int row = pw * RW + i * 4 + rsub;
+          const int ia = __shfl_sync(0xffffffffu, srcId, i * 4 + rsub), ib = __shfl_sync(0xffffffffu, dstId, i * 4 + rsub);
+          const uint32_t off = (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4);
+          for (int b = 0; b < nBa; b++)
+            cp_async16(sbase + b * blockBytes + off, P.a + (size_t)(ia >= 0 ? ia : 0) * P.rowBytesA + b * 128 + chunk * 16, ia >= 0 ? 16u : 0u);
+          for (int b = 0; b < nBb; b++)
+            cp_async16(sbase + (nBa + b) * blockBytes + off, P.b + (size_t)(ib >= 0 ? ib : 0) * P.rowBytesB + b * 128 + chunk * 16, ib >= 0 ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(smem_u32(full + slot));
+        if (++slot == (uint32_t)P.S) { slot = 0; round++; }
+      }
+    }
+  } else {
+    // ---------------- MMA issuer: both operands MN-major (bits 15, 16), M = 128, N = Cout, 32 bytes of K (= 16 bf16 / 8 tf32 rules) per instruction
+    const uint32_t fmt = BF16 ? 1u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr int kRulesPerMma = BF16 ? 16 : 8;
+    uint32_t slot = 0, round = 0;
+    int it = 0;
+    for (int w = blockIdx.x; w < nItems; w += gridDim.x, it++) {
+      int k, r0, cnt;
+      item(w, k, r0, cnt);
+      const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
+      mbar_wait(smem_u32(accEmpty + a), (use & 1) ^ 1);
+      tc_fence_after();
+      for (int base = 0; base < cnt; base += R) {
+        mbar_wait(smem_u32(full + slot), round & 1u);
+        tc_fence_after();
+        const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
+        if (elect_one()) {
+          for (int j = 0; j < R / kRulesPerMma; j++) {
+            const uint64_t bDesc = smem_desc_mn_sw128(sbase + nBa * blockBytes + (uint32_t)j * kRulesPerMma * 128u, blockBytes);
+            for (int mh = 0; mh < nMh; mh++) {
+              const uint64_t aDesc = smem_desc_mn_sw128(sbase + (uint32_t)mh * (nBa / nMh) * blockBytes + (uint32_t)j * kRulesPerMma * 128u, blockBytes);
+              tc_mma<BF16>(tmemBase + (uint32_t)(a * accCols + mh * P.Cout), aDesc, bDesc, idesc, (base > 0 || j > 0) ? 1u : 0u);
+            }
+          }
+          tc_commit(smem_u32(empty + slot));
+        }
+        __syncwarp();
+        if (++slot == (uint32_t)P.S) { slot = 0; round++; }
+      }
+      if (elect_one()) tc_commit(smem_u32(accFull + a));
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
+  }
+}
+// dW must be zero on entry.  Returns 1 when the configuration is not supported (the caller then uses the CUDA-core kernel).
+int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2 *pairs, const int *d_off, const int *offHost, int K, long nInRows,
+                      long nOutRows, int Cin, int Cout, int srcIsY, int mathMode, cudaStream_t s) {
+  // bf16 mode only: with TF32 operands the MN-major product came out as zeros on B200 (unresolved; tf32 mode keeps the CUDA-core kernel)
+  if (mathMode != 2 || !tc_available()) return 1;
+  const bool bf16 = true;
+  const int per = bf16 ? 64 : 32; // channels per 128-byte block
+  if (Cin % 128 != 0 || Cin > 256 || Cout % per != 0 || Cout % 16 != 0 || Cout < 16 || Cout > 256 || (Cin / 128) * Cout > 512 || K > 64) return 1;
+  const long total = offHost[K];
+  if (total == 0) return 0;
+  DwParams P;
+  P.pairs = pairs; P.d_off = d_off; P.dW = dW; P.K = K; P.Cin = Cin; P.Cout = Cout; P.srcIsY = srcIsY;
+  P.rowBytesA = Cin * (bf16 ? 2 : 4);
+  P.rowBytesB = Cout * (bf16 ? 2 : 4);
+  if (bf16) { // operand copies of both row matrices, side by side in the stream's scratch buffer
+    unsigned char *scr = nullptr;
+    const size_t na = ((size_t)nInRows * Cin * 2 + 255) & ~(size_t)255;
+    SCN_TRY(stream_scratch(s, na + (size_t)nOutRows * Cout * 2 + 16, (void **)&scr));
+    SCN_TRY(to_bf16(in, scr, nInRows * Cin, s));
+    SCN_TRY(to_bf16(d_out, scr + na, nOutRows * Cout, s));
+    P.a = scr; P.b = scr + na;
+  } else {
+    P.a = reinterpret_cast<const unsigned char *>(in); P.b = reinterpret_cast<const unsigned char *>(d_out);
+  }
+  const int nBlocks = P.rowBytesA / 128 + P.rowBytesB / 128;
+  const size_t budget = 225 * 1024 - 1024; // (the kernel also has ~1 KB of static shared memory)
+  P.R = (size_t)nBlocks * 128 * 128 * 3 <= budget ? 128 : 64;
+  const size_t stageBytes = (size_t)nBlocks * P.R * 128;
+  P.S = (int)std::min<size_t>(4, budget / stageBytes);
+  if (P.S < 2) return 1;
+  const int accCols = (Cin / 128) * Cout;
+  P.nAcc = 2 * accCols <= 512 ? 2 : 1;
+  long chunk = (total + kSMs * 3 - 1) / (kSMs * 3);
+  chunk = std::max<long>(4 * P.R, (chunk + P.R - 1) / P.R * P.R);
+  P.chunk = (int)chunk;
+  long nItems = 0;
+  for (int k = 0; k < K; k++) nItems += (offHost[k + 1] - offHost[k] + chunk - 1) / chunk;
+  const size_t smemBytes = (size_t)P.S * stageBytes + 64 * 8 + 64;
+  static bool attr = false;
+  if (!attr) {
+    SCN_CUDA(cudaFuncSetAttribute(conv_dw_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_dw_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    attr = true;
+  }
+  const int grid = (int)std::min<long>(nItems, kSMs);
+  if (bf16) conv_dw_tc<true><<<grid, 416, smemBytes, LS(s)>>>(P);
+  else conv_dw_tc<false><<<grid, 416, smemBytes, LS(s)>>>(P);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
+
 } // namespace scn
