@@ -907,7 +907,8 @@ __global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ int s_first[66]; // first work item of every list (prefix of ceil(len / chunk))
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int R = P.R, nBa = P.rowBytesA / 128, nBb = P.rowBytesB / 128;
+  // `in` rows narrower than 128 channels are zero-padded to M = 128 in shared memory (zero-filled chunks, no traffic)
+  const int R = P.R, nBa = max(P.rowBytesA, 256) / 128, nBb = (P.rowBytesB + 127) / 128;
   const uint32_t blockBytes = (uint32_t)R * 128u, stageBytes = (uint32_t)(nBa + nBb) * blockBytes;
   unsigned char *sStage = smem;
   uint64_t *bars = reinterpret_cast<uint64_t *>(sStage + (size_t)P.S * stageBytes);
@@ -931,7 +932,7 @@ __global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
   tc_fence_after();
   const uint32_t tmemBase = *tmemSlot;
   const int nItems = s_first[P.K];
-  const int nMh = P.Cin / 128, accCols = nMh * P.Cout;
+  const int nMh = (P.Cin + 127) / 128, accCols = nMh * P.Cout;
   // item -> (list k, first rule, number of rules)
   auto item = [&](int w, int &k, int &r0, int &cnt) {
     k = 0;
@@ -952,11 +953,14 @@ __global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
       for (int mh = 0; mh < nMh; mh++) {
         const int ci = mh * 128 + warp * 32 + lane;
         float *dst = P.dW + ((size_t)k * P.Cin + ci) * P.Cout;
+        if (mh * 128 + warp * 32 >= P.Cin) continue; // rows of the channel padding (warp-uniform)
         for (int c0 = 0; c0 < P.Cout; c0 += 32) {
           uint32_t v[32];
           tmem_ld(tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * accCols + mh * P.Cout + c0), v);
+          if (ci < P.Cin) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+          }
         }
       }
       tc_fence_before();
@@ -982,10 +986,14 @@ __global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
           const int row = pw * RW + i * 4 + rsub;
           const int ia = __shfl_sync(0xffffffffu, srcId, i * 4 + rsub), ib = __shfl_sync(0xffffffffu, dstId, i * 4 + rsub);
           const uint32_t off = (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4);
-          for (int b = 0; b < nBa; b++)
-            cp_async16(sbase + b * blockBytes + off, P.a + (size_t)(ia >= 0 ? ia : 0) * P.rowBytesA + b * 128 + chunk * 16, ia >= 0 ? 16u : 0u);
-          for (int b = 0; b < nBb; b++)
-            cp_async16(sbase + (nBa + b) * blockBytes + off, P.b + (size_t)(ib >= 0 ? ib : 0) * P.rowBytesB + b * 128 + chunk * 16, ib >= 0 ? 16u : 0u);
+          for (int b = 0; b < nBa; b++) {
+            const bool have = ia >= 0 && b * 128 + chunk * 16 < P.rowBytesA;
+            cp_async16(sbase + b * blockBytes + off, have ? P.a + (size_t)ia * P.rowBytesA + b * 128 + chunk * 16 : P.a, have ? 16u : 0u);
+          }
+          for (int b = 0; b < nBb; b++) {
+            const bool have = ib >= 0 && b * 128 + chunk * 16 < P.rowBytesB;
+            cp_async16(sbase + (nBa + b) * blockBytes + off, have ? P.b + (size_t)ib * P.rowBytesB + b * 128 + chunk * 16 : P.b, have ? 16u : 0u);
+          }
         }
         cp_async_mbar_arrive_noinc(smem_u32(full + slot));
         if (++slot == (uint32_t)P.S) { slot = 0; round++; }
@@ -1038,8 +1046,7 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
   // bf16 mode only: with TF32 operands the MN-major product came out as zeros on B200 (unresolved; tf32 mode keeps the CUDA-core kernel)
   if (mathMode != 2 || !tc_available()) return 1;
   const bool bf16 = true;
-  const int per = bf16 ? 64 : 32; // channels per 128-byte block
-  if (Cin % 128 != 0 || Cin > 256 || Cout % per != 0 || Cout % 16 != 0 || Cout < 16 || Cout > 256 || (Cin / 128) * Cout > 512 || K > 64) return 1;
+  if (Cin % 32 != 0 || Cin > 256 || (Cin > 128 && Cin % 128 != 0) || Cout % 32 != 0 || Cout > 256 || ((Cin + 127) / 128) * Cout > 512 || K > 64) return 1;
   const long total = offHost[K];
   if (total == 0) return 0;
   DwParams P;
@@ -1056,13 +1063,13 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
   } else {
     P.a = reinterpret_cast<const unsigned char *>(in); P.b = reinterpret_cast<const unsigned char *>(d_out);
   }
-  const int nBlocks = P.rowBytesA / 128 + P.rowBytesB / 128;
+  const int nBlocks = std::max(P.rowBytesA, 256) / 128 + (P.rowBytesB + 127) / 128;
   const size_t budget = 225 * 1024 - 1024; // (the kernel also has ~1 KB of static shared memory)
   P.R = (size_t)nBlocks * 128 * 128 * 3 <= budget ? 128 : 64;
   const size_t stageBytes = (size_t)nBlocks * P.R * 128;
   P.S = (int)std::min<size_t>(4, budget / stageBytes);
   if (P.S < 2) return 1;
-  const int accCols = (Cin / 128) * Cout;
+  const int accCols = ((Cin + 127) / 128) * Cout;
   P.nAcc = 2 * accCols <= 512 ? 2 : 1;
   long chunk = (total + kSMs * 3 - 1) / (kSMs * 3);
   chunk = std::max<long>(4 * P.R, (chunk + P.R - 1) / P.R * P.R);
