@@ -472,9 +472,9 @@ int scn_submanifold_convolution_backward(scn_metadata *m, const long sz[3], cons
   SCN_TRY(m->md.wait_ready(e->rdy));
   SCN_TRY(m->md.wait_ready(e->rulesRdy));
   // d_in on the tensor cores: the plan of an odd filter is symmetric, d_in[q] = sum_j d_out[nbr[q][j]] @ W[K-1-j]^T
-  const bool tcIn = tc_ok(Cout, Cin, e->plan.K) && f[0] % 2 == 1 && f[1] % 2 == 1 && f[2] % 2 == 1 && g->n > 0;
+  const bool tcIn = d_in && tc_ok(Cout, Cin, e->plan.K) && f[0] % 2 == 1 && f[1] % 2 == 1 && f[2] % 2 == 1 && g->n > 0;
   if (tcIn) SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->plan.K, Cin, Cout, /*reverse=*/1, e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut, nullptr, g->n, g->n));
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.cstream, tcIn, scn::g_math_mode);
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.cstream, tcIn || !d_in, scn::g_math_mode); // d_in == NULL: input gradient not wanted
 }
 int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                              float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {

@@ -1046,18 +1046,20 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
   // bf16 mode only: with TF32 operands the MN-major product came out as zeros on B200 (unresolved; tf32 mode keeps the CUDA-core kernel)
   if (mathMode != 2 || !tc_available()) return 1;
   const bool bf16 = true;
-  if (Cin % 32 != 0 || Cin > 256 || (Cin > 128 && Cin % 128 != 0) || Cout % 32 != 0 || Cout > 256 || ((Cin + 127) / 128) * Cout > 512 || K > 64) return 1;
+  if ((Cin % 32 != 0 && Cin > 32) || Cin > 256 || (Cin > 128 && Cin % 128 != 0) || Cout % 32 != 0 || Cout > 256 || ((Cin + 127) / 128) * Cout > 512 || K > 64) return 1;
+  const int CinP = Cin % 32 == 0 ? Cin : (Cin <= 16 ? 16 : 32); // odd narrow inputs (the 9-channel network input): bf16 rows zero-padded to 16 / 32 channels
   const long total = offHost[K];
   if (total == 0) return 0;
   DwParams P;
   P.pairs = pairs; P.d_off = d_off; P.dW = dW; P.K = K; P.Cin = Cin; P.Cout = Cout; P.srcIsY = srcIsY;
-  P.rowBytesA = Cin * (bf16 ? 2 : 4);
+  P.rowBytesA = CinP * (bf16 ? 2 : 4);
   P.rowBytesB = Cout * (bf16 ? 2 : 4);
   if (bf16) { // operand copies of both row matrices, side by side in the stream's scratch buffer
     unsigned char *scr = nullptr;
-    const size_t na = ((size_t)nInRows * Cin * 2 + 255) & ~(size_t)255;
+    const size_t na = ((size_t)nInRows * CinP * 2 + 255) & ~(size_t)255;
     SCN_TRY(stream_scratch(s, na + (size_t)nOutRows * Cout * 2 + 16, (void **)&scr));
-    SCN_TRY(to_bf16(in, scr, nInRows * Cin, s));
+    if (CinP == Cin) SCN_TRY(to_bf16(in, scr, nInRows * Cin, s));
+    else if (nInRows) k_pad_rows_bf16<<<stream_grid(nInRows * CinP, 256), 256, 0, LS(s)>>>(in, reinterpret_cast<__nv_bfloat16 *>(scr), nInRows, Cin, CinP);
     SCN_TRY(to_bf16(d_out, scr + na, nOutRows * Cout, s));
     P.a = scr; P.b = scr + na;
   } else {

@@ -159,7 +159,8 @@ class SubmanifoldConvolutionFunction(Function):
     @staticmethod
     def backward(ctx, grad_output):
         input_features, spatial_size, weight, bias, filter_size = ctx.saved_tensors
-        grad_input = grad_output.new()
+        # the network's first convolution: its input (the InputLayer output of leaf features) needs no gradient
+        grad_input = grad_output.new() if ctx.needs_input_grad[0] else None
         grad_weight = torch.zeros_like(weight)
         grad_bias = torch.zeros_like(bias)
         native.SubmanifoldConvolution_backward(spatial_size, filter_size, ctx.input_metadata, input_features.contiguous(), grad_input,

@@ -229,9 +229,10 @@ def SubmanifoldConvolution_updateOutput(spatial_size, filter_size, m, input_feat
 def SubmanifoldConvolution_backward(spatial_size, filter_size, m, input_features, d_input_features, d_output_features, weight, d_weight, d_bias):
     """pybind.cpp:139-143"""
     _, cin, cout = _w3(weight)
-    d_input_features.resize_as_(input_features)
+    if d_input_features is not None:  # None: the caller does not need the input gradient (native side skips it)
+        d_input_features.resize_as_(input_features)
     check(lib().scn_submanifold_convolution_backward(m._h, l3(spatial_size), l3(filter_size), _dev_f32(input_features, "in"),
-                                                     _dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"),
+                                                     None if d_input_features is None else _dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"),
                                                      _dev_f32(weight, "weight"), _dev_f32(d_weight, "d_weight"), _opt(d_bias, "d_bias"), cin, cout))
 
 

@@ -112,7 +112,8 @@ int scn_deconvolution_forward(scn_metadata *m, const long in_size[3], const long
                             const float *add_in, void *out_bf16);
 
 /* *_backward (pybind.cpp:60-65,84-89,139-143; CPU/Convolution.cpp:81-115,152-185; CPU/Deconvolution.cpp:43-77):
- * d_in [nIn rows][Cin] is overwritten, d_weight [K][Cin][Cout] is overwritten, d_bias NULL or [Cout]. */
+ * d_in [nIn rows][Cin] is overwritten (scn_submanifold_convolution_backward: NULL = not wanted, skipped), d_weight [K][Cin][Cout]
+ * is overwritten, d_bias NULL or [Cout]. */
 int scn_submanifold_convolution_backward(scn_metadata *m, const long spatial_size[3], const long filter_size[3],
                                          const float *in, float *d_in, const float *d_out, const float *weight,
                                          float *d_weight, float *d_bias, int n_in, int n_out);

@@ -403,7 +403,7 @@ def test_tc_input_gradients(math):
         scn.set_math_mode(math)
         sz = [64, 64, 32]
         n = O.nactive(sz)
-        for cin, cout, f in [(64, 128, 3), (128, 128, 3), (32, 32, 3), (32, 128, 1), (256, 64, 3)]:
+        for cin, cout, f in [(64, 128, 3), (128, 128, 3), (32, 32, 3), (32, 128, 1), (256, 64, 3), (9, 32, 3)]:
             rs = np.random.RandomState(cin + 3 * cout + f)
             x, dy = rs.randn(n, cin).astype(np.float32), rs.randn(n, cout).astype(np.float32)
             w = (rs.randn(f ** 3, 1, cin, cout) * (2.0 / (cin * f ** 3)) ** 0.5).astype(np.float32)
