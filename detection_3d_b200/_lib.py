@@ -35,6 +35,7 @@ SYMBOLS = {
     "scn_copy_device": (_i, [_vp, _vp, _l, _vp]),
     "scn_input_layer_build": (_i, [_vp, L3, _vp, _i, _l, _i, _i, _i, _pl, _pi]),
     "scn_input_layer_forward": (_i, [_vp, _vp, _vp, _i]),
+    "scn_input_layer_forward_padded_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "scn_input_layer_backward": (_i, [_vp, _vp, _vp, _i]),
     "scn_get_nactive": (_i, [_vp, L3, _pl]),
     "scn_get_spatial_locations": (_i, [_vp, L3, _vp, _i]),

@@ -45,6 +45,7 @@ int bn_forward(const float *x, float *y, long n, int C, float *saveMean, float *
 int bn_backward(const float *x, float *dx, const float *y, float *dy, long n, int C, const float *saveMean, const float *saveInvStd,
                 const float *weight, float *dWeight, float *dBias, float leak, void *workspace, cudaStream_t s);
 int input_forward(const float *in, float *out, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
+int input_forward_pad16(const float *in, float *out, void *out16, int nOut, int maxActive, int C, int Cp, const int *tab, int average, cudaStream_t s);
 int input_backward(float *din, const float *dout, long nIn, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
 int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s, void *o16);
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
@@ -263,6 +264,15 @@ int scn_input_layer_forward(scn_metadata *m, const float *in, float *out, int C)
     return 0;
   }
   return scn::input_forward(in, out, I.nOut, I.maxActive, C, I.tab, I.mode == 4, m->md.cstream);
+}
+// InputLayer forward that also writes the rows as bfloat16 zero-padded to `padded` (16 or 32) channels: what the first
+// convolution of a bf16-mode program gathers (modes 1-4; used by the program executor).
+int scn_input_layer_forward_padded_bf16(scn_metadata *m, const float *in, float *out, void *out_bf16, int C, int padded) {
+  M_OR_FAIL(m);
+  auto &I = m->md.input;
+  SCN_CHECK(I.valid && I.mode != 0 && padded >= C, "input layer not built / unsupported mode");
+  SCN_TRY(m->md.wait_ready(I.rdy));
+  return scn::input_forward_pad16(in, out, out_bf16, I.nOut, I.maxActive, C, padded, I.tab, I.mode == 4, m->md.cstream);
 }
 int scn_input_layer_backward(scn_metadata *m, float *din, const float *dout, int C) {
   M_OR_FAIL(m);

@@ -721,6 +721,11 @@ static int stream_scratch(cudaStream_t s, size_t bytes, void **out) {
 static thread_local double *tl_stats = nullptr;
 static thread_local bool tl_stats_done = false;
 void epilogue_stats_arm(double *sums) { tl_stats = sums; tl_stats_done = false; }
+// A bf16 copy of the next convolution's input rows that is already zero-padded to `Cp` channels (written by the input layer).
+static thread_local const void *tl_prepad = nullptr;
+static thread_local int tl_prepad_c = 0;
+void prepadded_arm(const void *rows16, int Cp) { tl_prepad = rows16; tl_prepad_c = Cp; }
+void prepadded_disarm() { tl_prepad = nullptr; tl_prepad_c = 0; }
 // Same for a lateral 1x1x1 convolution folded into the next convolution: out = conv(in) [+ addend] + lat_in[row] @ lat_w.
 // lat_in: fp32 rows; lat_in16: their bf16 copy (may be null); taken when the launch is a whole-atom (unpacked) tensor-core launch.
 struct Lateral { const float *in; const void *in16; const float *w; long long tag; int Cin; long rows; };
@@ -741,8 +746,13 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     // 32 channels (G = 2) or a multiple of 64 (whole atoms), written by one pass; the weight image pads itself
     const int Cp = Cin < 16 ? 16 : (Cin < 32 ? 32 : (Cin + 63) / 64 * 64);
     __nv_bfloat16 *xp = nullptr;
-    SCN_TRY(stream_scratch(s, (size_t)nInRows * Cp * 2 + 16, (void **)&xp));
-    k_pad_rows_bf16<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
+    if (tl_prepad && tl_prepad_c == Cp) {
+      xp = const_cast<__nv_bfloat16 *>(static_cast<const __nv_bfloat16 *>(tl_prepad)); // the producer already wrote the padded copy
+    } else {
+      SCN_TRY(stream_scratch(s, (size_t)nInRows * Cp * 2 + 16, (void **)&xp));
+      k_pad_rows_bf16<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
+    }
+    tl_prepad = nullptr;
     return launch_conv_plan_tc(in, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, xp, wTag, addend, out16, nOutRows, Cin);
   }
   if (Cin % 32 != 0 && !(canPack && Cin == 16)) { // rows zero-padded to a multiple of 32 channels (the weight image pads itself)

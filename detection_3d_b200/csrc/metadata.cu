@@ -864,22 +864,36 @@ int Metadata::build_tile_masks(NbrPlan &plan) {
 // ------------------------------------------------------------------ submanifold
 // nbr[nbr_index(p, k, K)] = row id of the neighbour of site p at filter offset k (last dimension fastest,
 // RectangularRegions.h:56-71; window [c - f/2, c + f - 1 - f/2], SubmanifoldConvolutionRules.h:11-22).
-__global__ void k_subm_nbr(GridView g, const int4 *coords, const int *p2id, int n, int f0, int f1, int f2, int *nbr, int *nValid) {
+// 128 threads per block = one plan tile per loop iteration: the tile's offset mask (bit k: some site of the tile has a
+// neighbour at offset k) is reduced on the spot instead of by a second pass over the plan.
+__global__ void __launch_bounds__(128) k_subm_nbr(GridView g, const int4 *coords, const int *p2id, int n, int f0, int f1, int f2, int *nbr, int *nValid,
+                                                  unsigned long long *tileMask) {
   const int K = f0 * f1 * f2;
+  __shared__ unsigned long long s_m[4];
   int cntv = 0;
-  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x) {
-    const int id = p2id[p];
-    const int4 c = coords[id];
-    int k = 0;
-    for (int a = 0; a < f0; a++)
-      for (int b = 0; b < f1; b++)
-        for (int d = 0; d < f2; d++, k++) {
-          int x = c.x - f0 / 2 + a, y = c.y - f1 / 2 + b, z = c.z - f2 / 2 + d;
-          int q = (x == c.x && y == c.y && z == c.z) ? (int)p : grid_lookup(g, x, y, z, c.w);
-          int v = q >= 0 ? p2id[q] : -1;
-          nbr[nbr_index(p, k, K)] = v;
-          cntv += v >= 0;
-        }
+  const long nPad = ((long)n + 127) / 128 * 128;
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < nPad; p += (long)gridDim.x * blockDim.x) {
+    unsigned long long m = 0;
+    if (p < n) {
+      const int id = p2id[p];
+      const int4 c = coords[id];
+      int k = 0;
+      for (int a = 0; a < f0; a++)
+        for (int b = 0; b < f1; b++)
+          for (int d = 0; d < f2; d++, k++) {
+            int x = c.x - f0 / 2 + a, y = c.y - f1 / 2 + b, z = c.z - f2 / 2 + d;
+            int q = (x == c.x && y == c.y && z == c.z) ? (int)p : grid_lookup(g, x, y, z, c.w);
+            int v = q >= 0 ? p2id[q] : -1;
+            nbr[nbr_index(p, k, K)] = v;
+            cntv += v >= 0;
+            m |= (unsigned long long)(v >= 0) << k;
+          }
+    }
+    for (int d = 16; d > 0; d >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, d);
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) tileMask[p >> 7] = s_m[0] | s_m[1] | s_m[2] | s_m[3];
+    __syncthreads();
   }
   for (int d = 16; d > 0; d >>= 1) cntv += __shfl_xor_sync(0xffffffffu, cntv, d);
   if ((threadIdx.x & 31) == 0 && cntv) atomicAdd(nValid, cntv);
@@ -934,11 +948,12 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
     SCN_CUDA(cudaMemsetAsync(e.plan.nbr + t0 * K * 128, 0xff, (nPad / 128 - t0) * K * 128 * 4, cur().stream));
   }
   SCN_CUDA(cudaMemsetAsync(cur().d_scalars, 0, 4, cur().stream));
-  if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, cur().d_scalars);
+  e.plan.tileMask = alloc_n<unsigned long long>(cdiv(std::max(g->n, 1), 128) + 8);
+  SCN_CHECK(e.plan.tileMask, "alloc");
+  if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, cur().d_scalars, e.plan.tileMask);
   // The forward pass only needs the plan and the rule COUNT (the reference's multiply-add counter);
   // the per-offset (in,out) lists in the reference's hash-iteration order are materialised on demand
   // (ensure_subm_rules: backward pass, rulebook inspection).
-  SCN_TRY(build_tile_masks(e.plan));
   SCN_TRY(sync_scalars(1));
   e.plan.nValid = cur().h_scalars[0];
   e.rb.nLists = (int)K;

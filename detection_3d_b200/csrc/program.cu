@@ -14,6 +14,8 @@ void epilogue_stats_arm(double *sums);
 bool epilogue_stats_take();
 void lateral_arm(const float *in, const void *in16, const float *w, long long tag, int Cin, long rows);
 bool lateral_take();
+void prepadded_arm(const void *rows16, int Cp);
+void prepadded_disarm();
 int bn_forward_from_sums(const float *x, float *y, long n, int C, const double *sums, float *saveMean, float *saveInvStd, float *runningMean,
                          float *runningVar, const float *weight, const float *bias, float eps, float momentum, int mode, float leak, cudaStream_t s, void *y16);
 } // namespace scn
@@ -31,6 +33,7 @@ struct Reg {
   void *p16 = nullptr; // bfloat16 copy (math mode 2, written by BatchNorm / add)
   long rows = 0;
   int cols = 0;
+  int pad16 = 0; // > 0: p16 holds the rows zero-padded to this many channels (network input in bf16 mode)
 };
 
 } // namespace
@@ -306,6 +309,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     Reg &R = p->regs[r];
     R.rows = rows;
     R.cols = cols;
+    R.pad16 = 0;
     R.p = halfOnly ? nullptr : static_cast<float *>(slot_get(p, (size_t)std::max(1l, rows * cols) * 4));
     if (!R.p && !halfOnly) return -1;
     if (shadow && mode == 2 && cols % 32 == 0 && rows > 0) {
@@ -327,7 +331,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   auto arm_lateral = [&](const Op &op) {
     if (op.a[18] < 0) return;
     const Reg &Y = p->regs[op.a[18]];
-    scn::lateral_arm(Y.p, Y.p16, P(op.a[19]), T(op.a[19]), (int)op.a[20], Y.rows);
+    scn::lateral_arm(Y.p, Y.pad16 ? nullptr : Y.p16, P(op.a[19]), T(op.a[19]), (int)op.a[20], Y.rows);
   };
   // the convolution did not take the lateral (e.g. it ran on the CUDA-core path): run the 1x1x1 convolution on its own and add it
   auto lateral_fallback = [&](const Op &op, scn_metadata *md, const long *sz, Reg &out, int Cout) -> int {
@@ -340,7 +344,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     if (!tmp) return -1;
     const long one[3] = {1, 1, 1};
     double mk2 = 0;
-    int r = scn_submanifold_convolution_forward(md, sz, one, Y.p, tmp, P(op.a[19]), nullptr, (int)op.a[20], Cout, &mk2, Y.p16, T(op.a[19]), nullptr, nullptr);
+    int r = scn_submanifold_convolution_forward(md, sz, one, Y.p, tmp, P(op.a[19]), nullptr, (int)op.a[20], Cout, &mk2, Y.pad16 ? nullptr : Y.p16, T(op.a[19]), nullptr, nullptr);
     if (r == 0) r = scn_add_features(out.p, tmp, out.p, out.rows * Cout, s, out.p16);
     slot_put(p, tmp);
     return r;
@@ -358,7 +362,16 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
           if (rc) break;
         }
         rc = alloc_reg(a[0], nActive, (int)a[6], false);
-        if (rc == 0 && nActive) rc = scn_input_layer_forward(m, feats, p->regs[a[0]].p, (int)a[6]);
+        p->regs[a[0]].pad16 = 0;
+        const int C0 = (int)a[6], Cp = C0 < 16 ? 16 : 32;
+        if (rc == 0 && nActive && mode == 2 && a[4] != 0 && C0 % 32 != 0 && C0 < 32 && scn_tensor_core_path_available()) {
+          // bf16 mode: the first convolution gathers bf16 rows zero-padded to 16 / 32 channels; written here, by the same pass
+          Reg &R0 = p->regs[a[0]];
+          R0.p16 = slot_get(p, (size_t)nActive * Cp * 2);
+          if (!R0.p16) { rc = -1; break; }
+          R0.pad16 = Cp;
+          rc = scn_input_layer_forward_padded_bf16(m, feats, R0.p, R0.p16, C0, Cp);
+        } else if (rc == 0 && nActive) rc = scn_input_layer_forward(m, feats, p->regs[a[0]].p, (int)a[6]);
         break;
       }
       case K_SUBM: { // in, out, size[3], filter[3], w, bias, Cin, Cout
@@ -367,10 +380,12 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], a[22] >= 0 || a[18] >= 0);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
+        if (rc == 0 && I.pad16) scn::prepadded_arm(I.p16, I.pad16);
         if (rc == 0)
-          rc = scn_submanifold_convolution_forward(m, a + 2, a + 5, I.p, p->regs[a[1]].p, P(a[8]), P(a[9]), (int)a[10], (int)a[11], &mk, I.p16, T(a[8]),
+          rc = scn_submanifold_convolution_forward(m, a + 2, a + 5, I.p, p->regs[a[1]].p, P(a[8]), P(a[9]), (int)a[10], (int)a[11], &mk, I.pad16 ? nullptr : I.p16, T(a[8]),
                                                    a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         took(op);
+        scn::prepadded_disarm();
         if (rc == 0) rc = lateral_fallback(op, m, a + 2, p->regs[a[1]], (int)a[11]);
         macs += mk;
         break;
@@ -382,7 +397,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0)
-          rc = scn_convolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]),
+          rc = scn_convolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.pad16 ? nullptr : I.p16, T(a[14]),
                                        a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         took(op);
         if (rc == 0) rc = lateral_fallback(op, m, a + 5, p->regs[a[1]], (int)a[17]);
@@ -396,7 +411,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0)
-          rc = scn_deconvolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.p16, T(a[14]),
+          rc = scn_deconvolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.pad16 ? nullptr : I.p16, T(a[14]),
                                          a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         took(op);
         if (rc == 0) rc = lateral_fallback(op, m, a + 5, p->regs[a[1]], (int)a[17]);

@@ -406,6 +406,28 @@ __global__ void __launch_bounds__(256) k_input_bwd(float *__restrict__ din, cons
     for (int j = 1; j <= na; j++) din[(long)r[j] * C + c] = g; // an input row feeds exactly one voxel: plain store
   }
 }
+// Same, plus a bf16 copy of the output rows zero-padded to Cp channels (the packed operand of the first convolution in
+// bf16 mode, which otherwise needs a separate padding pass over the rows).
+__global__ void __launch_bounds__(256) k_input_fwd_pad16(const float *__restrict__ in, float *__restrict__ out, __nv_bfloat16 *__restrict__ out16, int nOut, int w,
+                                                         int C, int Cp, const int *__restrict__ tab, int average) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)nOut * Cp; i += (long)gridDim.x * blockDim.x) {
+    int row = (int)(i / Cp), c = (int)(i % Cp);
+    float acc = 0.f;
+    if (c < C) {
+      const int *r = tab + (long)row * w;
+      int na = r[0];
+      float mult = (average && na > 0) ? 1.f / na : 1.f;
+      for (int j = 1; j <= na; j++) acc += mult * __ldg(in + (long)r[j] * C + c);
+      out[(long)row * C + c] = acc;
+    }
+    out16[i] = __float2bfloat16_rn(acc);
+  }
+}
+int input_forward_pad16(const float *in, float *out, void *out16, int nOut, int maxActive, int C, int Cp, const int *tab, int average, cudaStream_t s) {
+  if (nOut) k_input_fwd_pad16<<<stream_grid((long)nOut * Cp, 256), 256, 0, LS(s)>>>(in, out, static_cast<__nv_bfloat16 *>(out16), nOut, 1 + maxActive, C, Cp, tab, average);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
 int input_forward(const float *in, float *out, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s) {
   if (nOut) k_input_fwd<<<stream_grid((long)nOut * C, 256), 256, 0, LS(s)>>>(in, out, nOut, 1 + maxActive, C, tab, average);
   SCN_CUDA(cudaGetLastError());

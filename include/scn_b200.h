@@ -50,6 +50,8 @@ int scn_input_layer_build(scn_metadata *m, const long spatial_size[3], const lon
 int scn_input_layer_built(scn_metadata *m, long *n_active, int *max_active);
 /* InputLayer_ForwardPass / InputLayer_fp  (CPU/IOLayers.cpp:11-29, CUDA/IOLayers.cu:31-41) */
 int scn_input_layer_forward(scn_metadata *m, const float *in_features, float *out_features, int n_planes);
+/* scn_input_layer_forward that also writes the rows as bfloat16 zero-padded to `padded` channels (first convolution of a bf16 program) */
+int scn_input_layer_forward_padded_bf16(scn_metadata *m, const float *in_features, float *out_features, void *out_bf16, int n_planes, int padded);
 /* InputLayer_updateGradInput (pybind.cpp:159-162; CPU/IOLayers.cpp:30-47) */
 int scn_input_layer_backward(scn_metadata *m, float *d_in_features, const float *d_out_features, int n_planes);
 
