@@ -203,11 +203,10 @@ def main():
 
     def step_e2e():
         with torch.no_grad():
-            # the reference's calling convention: coordinates stay a host LongTensor (ioLayers.py:60), features go
-            # to the device; the library copies the pinned coordinates on its build stream while the feature copy
-            # runs on the caller's stream
-            f = feats_pin.to(dev, non_blocking=True)
-            rpn, roi = net([coords_pin, f])
+            # the reference's calling convention: coordinates stay a host LongTensor (ioLayers.py:60); the features are
+            # handed over as a pinned host tensor too: the library copies the coordinates on its build stream and the
+            # module queues the feature copy on the caller's stream right after
+            rpn, roi = net([coords_pin, feats_pin])  # the module uploads both (coordinates first: the grid build needs them first)
             host = [m.features.to("cpu", non_blocking=True) for m in rpn + roi]
         return host
 

@@ -814,7 +814,12 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   P.nAcc = 2 * T * Cout <= P.tmemCols ? 2 : 1;
   P.nSuper = cdiv(P.nTiles, P.T);
   P.kSplit = 1;
-  if (P.nSuper < kSMs * ctas / 2 && !tileW) P.kSplit = std::max(1, std::min(packG > 1 ? P.KG : K, kSMs * ctas / P.nSuper));
+  // Only really small levels (<= kSplitMaxItems items) spread the filter offsets of an item over CTAs: the split costs a memset,
+  // atomic accumulation and a separate bf16 pass, and rules out the BatchNorm statistics in the epilogue; from a few dozen
+  // items on, one CTA per item doing all offsets is as fast and needs one launch instead of three.
+  static int kSplitMaxItems = -1;
+  if (kSplitMaxItems < 0) kSplitMaxItems = getenv("SCN_TC_SPLIT_MAX") ? atoi(getenv("SCN_TC_SPLIT_MAX")) : 24;
+  if (P.nSuper <= kSplitMaxItems && !tileW) P.kSplit = std::max(1, std::min(packG > 1 ? P.KG : K, kSMs * ctas / P.nSuper));
   P.stats = nullptr;
   if (tl_stats && P.kSplit == 1 && Cout <= kFusedStatsC && Cout % 32 == 0) { P.stats = tl_stats; tl_stats_done = true; }
   tl_stats = nullptr;

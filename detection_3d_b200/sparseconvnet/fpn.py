@@ -116,10 +116,21 @@ class FPN_Net(nn.Module):
         if _PROGRAMS and not self.training and not torch.is_grad_enabled() and len(net0) == 2:
             coords, feats = net0[0], net0[1]
             dev = self.layers_in[0].device
-            if dev is not None and isinstance(feats, torch.Tensor):
-                feats = feats.to(dev)
+            if dev is None and isinstance(feats, torch.Tensor) and not feats.is_cuda:
+                # (extension of the reference's calling convention: host features are accepted when the network lives on a GPU)
+                pdev = next(self.parameters()).device
+                dev = pdev if pdev.type == "cuda" else None
             mode = native.math_mode()
             prog = self.__dict__.get("_program")
+            if (prog is not None and dev is not None and isinstance(feats, torch.Tensor) and not feats.is_cuda and isinstance(coords, torch.Tensor)
+                    and coords.dtype == torch.int64 and coords.dim() == 2 and mode == prog.math_mode and not self._has_prefetched(coords)):
+                # host features: start the Metadata build first -- it uploads the coordinates, which the forward needs before
+                # anything else -- and only then queue the feature copy, which then overlaps the grid build
+                md = L.Metadata(self.dimension)
+                prog.prepare(md, coords)
+                self.__dict__.setdefault("_prefetched", []).append((coords, coords._version, md))
+            if dev is not None and isinstance(feats, torch.Tensor):
+                feats = feats.to(dev, non_blocking=True)
             if prog is not None and isinstance(coords, torch.Tensor) and prog.usable(coords, feats, mode):
                 return self._run_program(prog, coords, feats)
             if prog is None and self.__dict__.get("_program_error") is None and isinstance(feats, torch.Tensor) and feats.is_cuda:
@@ -132,6 +143,9 @@ class FPN_Net(nn.Module):
                     self.__dict__["_program_error"] = str(e)
                 return rpn_maps, roi_maps
         return self.forward_fpn(self.layers_in(net0))
+
+    def _has_prefetched(self, coords):
+        return any(pre[0] is coords and pre[1] == coords._version for pre in self.__dict__.get("_prefetched", ()))
 
     def prefetch(self, coords):
         """Streaming inference: start building the Metadata (active-site grids, rulebooks) of the NEXT input now, on the
