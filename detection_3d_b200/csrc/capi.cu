@@ -74,6 +74,8 @@ struct scn_metadata {
   int pending = 0;
   std::atomic<bool> stop{false};
   std::vector<PrefetchOp> ops, ops2; // chain worker (strided convolutions = the grid pyramid) / everything else
+  // input-layer arguments of a job that starts with the input layer itself (kind 0, scn_metadata_build_reference_grids)
+  long inSz[3] = {0, 0, 0}; const long *inCoords = nullptr; int inOnDevice = 0; long inRows = 0; int inCols = 0, inBatch = 0, inMode = 0;
   int device = 0;
 };
 
@@ -141,7 +143,9 @@ static void prefetch_worker(scn_metadata *m, int which) {
     if (m->stop) break;
     const long *a = op.v + 1, *b = op.v + 4, *f = op.v + 7, *s = op.v + 10;
     struct Mark { const PrefetchOp &o; ~Mark() { scn::timeline_mark("worker", (int)o.v[0], o.v[1], o.v[7]); } } mark{op};
-    if (op.v[0] == 1) {
+    if (op.v[0] == 0) {
+      if (m->md.input_layer(m->inSz, m->inCoords, m->inOnDevice, m->inRows, m->inCols, m->inBatch, m->inMode)) break;
+    } else if (op.v[0] == 1) {
       scn::SubmEntry *e;
       if (m->md.get_submanifold(a, f, &e)) break;
     } else if (op.v[0] == 2) {
@@ -163,12 +167,12 @@ namespace {
 struct WorkerPool {
   std::mutex mu;
   std::condition_variable cv;
-  std::deque<scn_metadata *> q[2];
+  std::deque<scn_metadata *> q[3];
 };
 WorkerPool *g_pool = nullptr; // never destroyed: the threads sleep on it until the process ends
 std::once_flag g_pool_once;
 void pool_main(int which) {
-  scn::set_prefetch_worker_thread(true, which);
+  scn::set_prefetch_worker_thread(true, which == 2 ? 0 : which); // thread 2 serves whole-Metadata jobs (reference grids) on their context 0
   int dev = -1;
   for (;;) {
     scn_metadata *m;
@@ -179,7 +183,7 @@ void pool_main(int which) {
       g_pool->q[which].pop_front();
     }
     if (dev != m->device) { cudaSetDevice(m->device); dev = m->device; }
-    prefetch_worker(m, which);
+    prefetch_worker(m, which == 2 ? 0 : which);
     { std::lock_guard<std::mutex> lk(m->jobMu); m->pending--; }
     m->jobCv.notify_all();
   }
@@ -187,7 +191,7 @@ void pool_main(int which) {
 void pool_submit(scn_metadata *m, int which) {
   std::call_once(g_pool_once, [] {
     g_pool = new WorkerPool();
-    for (int w = 0; w < 2; w++) std::thread(pool_main, w).detach();
+    for (int w = 0; w < 3; w++) std::thread(pool_main, w).detach();
   });
   { std::lock_guard<std::mutex> lk(m->jobMu); m->pending++; }
   { std::lock_guard<std::mutex> lk(g_pool->mu); g_pool->q[which].push_back(m); }
@@ -238,6 +242,36 @@ int scn_metadata_prefetch(scn_metadata *m, int n_ops, const long *ops) {
   return 0;
 }
 
+// Reference-numbered grids beside an internally numbered forward (program.cu): input layer + the given strided convolutions
+// (ops: n_ops x 13 longs, kind 2), all on a worker thread; scn_metadata_wait_jobs blocks until they are built.
+int scn_metadata_build_reference_grids(scn_metadata *m, const long sz[3], const long *coords, int on_device, long nrows, int ncols, int batch_size,
+                                       int mode, int n_ops, const long *ops, void *coords_ready_event) {
+  M_OR_FAIL(m);
+  m->md.set_chain_done(true);
+  wait_jobs(m);
+  for (int d = 0; d < 3; d++) m->inSz[d] = sz[d];
+  m->inCoords = coords; m->inOnDevice = on_device; m->inRows = nrows; m->inCols = ncols; m->inBatch = batch_size; m->inMode = mode;
+  m->md.coordsReady = static_cast<cudaEvent_t>(coords_ready_event);
+  m->ops.clear();
+  m->ops2.clear();
+  PrefetchOp in;
+  for (int j = 0; j < 13; j++) in.v[j] = 0;
+  m->ops.push_back(in);
+  for (int i = 0; i < n_ops; i++) {
+    PrefetchOp op;
+    for (int j = 0; j < 13; j++) op.v[j] = ops[i * 13 + j];
+    if (op.v[0] == 2) m->ops.push_back(op);
+  }
+  m->stop = false;
+  m->md.set_chain_done(false);
+  pool_submit(m, 2);
+  return 0;
+}
+int scn_metadata_wait_jobs(scn_metadata *m) {
+  M_OR_FAIL(m);
+  wait_jobs(m);
+  return 0;
+}
 int scn_input_layer_build(scn_metadata *m, const long sz[3], const long *coords, int on_device, long nrows, int ncols,
                           int batch_size, int mode, long *n_active, int *max_active) {
   M_OR_FAIL(m);
@@ -286,6 +320,57 @@ int scn_input_layer_backward(scn_metadata *m, float *din, const float *dout, int
   return scn::input_backward(din, dout, I.nIn, I.nOut, I.maxActive, C, I.tab, I.mode == 4, m->md.cstream);
 }
 
+// ---- internal row numbering (program replay): see Metadata::spatialIds
+int scn_metadata_set_internal_numbering(scn_metadata *m, int on) {
+  M_OR_FAIL(m);
+  SCN_CHECK(!m->md.input.valid, "set the numbering before the input layer is built");
+  m->md.spatialIds = on != 0;
+  return 0;
+}
+namespace {
+__global__ void k_row_permutation(const int4 *refCoords, int n, scn::GridView g, const int *p2id, int *perm) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int4 c = refCoords[i];
+    const int p = scn::grid_lookup(g, c.x, c.y, c.z, c.w);
+    perm[i] = p >= 0 ? p2id[p] : -1;
+  }
+}
+__global__ void k_gather_rows(const float4 *__restrict__ src, float4 *__restrict__ dst, const int *__restrict__ perm, long rows, int c4) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < rows * c4; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c4;
+    const int s = perm[r];
+    dst[i] = s >= 0 ? src[(long)s * c4 + (i - r * c4)] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+} // namespace
+// dst[id] = src[row of the same site in `internal`] for the grid of spatial size sz: rows of a feature matrix computed in the
+// internal numbering of `internal` are handed out in the reference numbering of `ref` (both built from the same input).
+// Runs on ref's compute stream; cols % 4 == 0.
+int scn_rows_to_reference_order(scn_metadata *ref, scn_metadata *internal, const long sz[3], const float *src, float *dst, int cols) {
+  M_OR_FAIL(ref);
+  M_OR_FAIL(internal);
+  scn::Grid *gr = ref->md.find_grid(sz), *gi = internal->md.find_grid(sz);
+  SCN_CHECK(gr && gi && gr->n == gi->n && cols % 4 == 0, "rows_to_reference_order: grids differ");
+  if (gr->n == 0) return 0;
+  cudaStream_t s = ref->md.cstream;
+  SCN_TRY(ref->md.wait_ready(gr->rdy));
+  if (gi->rdy.ev) SCN_CUDA(cudaStreamWaitEvent(s, gi->rdy.ev, 0));
+  int *perm = nullptr;
+  SCN_CUDA(cudaMallocAsync((void **)&perm, (size_t)gr->n * 4, s));
+  const scn::GridView v{gi->dir, gi->bmask, gi->wbase, gi->dd[0], gi->dd[1], gi->dd[2], gi->dirCells, (int)gi->sz[0], (int)gi->sz[1], (int)gi->sz[2]};
+  k_row_permutation<<<scn::stream_grid(gr->n, 256), 256, 0, scn::LS(s)>>>(gr->coords, gr->n, v, gi->p2id, perm);
+  k_gather_rows<<<scn::stream_grid((long)gr->n * cols / 4, 256), 256, 0, scn::LS(s)>>>(reinterpret_cast<const float4 *>(src), reinterpret_cast<float4 *>(dst), perm,
+                                                                                       gr->n, cols / 4);
+  SCN_CUDA(cudaGetLastError());
+  cudaFreeAsync(perm, s);
+  return 0;
+}
+int scn_get_batch_size(scn_metadata *m, const long sz[3], int *batch) {
+  M_OR_FAIL(m);
+  scn::Grid *g = m->md.find_grid(sz);
+  *batch = g ? g->batch : 0;
+  return 0;
+}
 int scn_get_nactive(scn_metadata *m, const long sz[3], long *n) {
   M_OR_FAIL(m);
   scn::Grid *g = m->md.find_grid(sz);

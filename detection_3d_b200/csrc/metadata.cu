@@ -443,6 +443,24 @@ __global__ void k_count_batch(const int4 *coords, int n, int *counts) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) atomicAdd(counts + coords[i].w, 1);
 }
 
+__global__ void k_iota(int *p, int n) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = (int)i;
+}
+// spatialIds: row id = spatial index.  One writer per site (the first input row / any event of the site: same values).
+__global__ void k_spatial_input_ids(const int *rowP, const int4 *pts, long n, const int *firstRow, int4 *coords, int *p2id, int *id2p) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int p = rowP[i];
+    if (firstRow[p] == (int)i) { coords[p] = pts[i]; p2id[p] = p; id2p[p] = p; }
+  }
+}
+__global__ void k_spatial_conv_ids(const int *evQ, const int4 *evPts, long E, int4 *coords, int *p2id, int *id2p) {
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < E; e += (long)gridDim.x * blockDim.x) {
+    const int q = evQ[e];
+    if (q >= 0) { coords[q] = evPts[e]; p2id[q] = q; id2p[q] = q; }
+  }
+}
+__global__ void k_copy_scalar(const int *src, int *dst) { *dst = *src; }
+
 // Metadata::inputLayer -> inputLayerRules (SCN/Metadata/Metadata.cpp:405-417, IOLayersRules.h:18-125).
 int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long nrows, int ncols, int batchHint, int mode) {
   SCN_CHECK(ncols == 3 || ncols == 4, "coords must be N x 3 or N x 4");
@@ -459,7 +477,10 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
   Grid &g = *gp;
   g.sz = key;
   cudaStream_t s = cur().stream;
-  if (onDevice == 1) SCN_TRY(from_compute()); // the coordinates were produced on the caller's stream (2: already complete, no dependency)
+  if (onDevice == 1) { // the coordinates were produced on the caller's stream (2: already complete, no dependency)
+    if (coordsReady) SCN_CUDA(cudaStreamWaitEvent(s, coordsReady, 0));
+    else SCN_TRY(from_compute());
+  }
   const long *dcoords = coords;
   if (!onDevice && nrows) {
     long *tmp = alloc_n<long>(nrows * ncols);
@@ -490,7 +511,12 @@ int Metadata::input_layer(const long *sz, const long *coords, int onDevice, long
   SCN_CUDA(cudaMemsetAsync(cnt, 0, cap * 4, s));
   if (lastRow) SCN_CUDA(cudaMemsetAsync(lastRow, 0xff, cap * 4, s));
   if (nrows) k_first_rows<<<stream_grid(nrows, 256), 256, 0, LS(s)>>>(rowP, nrows, firstRow, lastRow, cnt, sc + 2);
-  SCN_TRY(run_scan(*this, nrows, FirstIn{rowP, firstRow}, FirstOut{rowP, pts, g.p2id, g.id2p, g.coords}, sc + 3));
+  if (spatialIds) {
+    if (nrows) k_spatial_input_ids<<<stream_grid(nrows, 256), 256, 0, LS(s)>>>(rowP, pts, nrows, firstRow, g.coords, g.p2id, g.id2p);
+    k_copy_scalar<<<1, 1, 0, LS(s)>>>(sc + 1, sc + 3); // nActive = number of distinct sites
+  } else {
+    SCN_TRY(run_scan(*this, nrows, FirstIn{rowP, firstRow}, FirstOut{rowP, pts, g.p2id, g.id2p, g.coords}, sc + 3));
+  }
   // per-batch-item counts (only needed when batch > 1)
   SCN_TRY(sync_scalars(4));
   g.n = cur().h_scalars[3];
@@ -721,6 +747,11 @@ int Metadata::ensure_rank(Grid &g) {
   SCN_TRY(need(g.rdy)); // (every caller already holds the lock of its build context)
   g.rank2id = alloc_n<int>(std::max(1, g.n));
   SCN_CHECK(g.rank2id, "alloc");
+  if (spatialIds) { // sites are visited in row order: no hash-order emulation
+    if (g.n) k_iota<<<stream_grid(g.n, 256), 256, 0, LS(cur().stream)>>>(g.rank2id, g.n);
+    g.hasRank = true;
+    return mark_ready(g.rankRdy);
+  }
   int start = 0;
   for (int b = 0; b < g.batch; b++) {
     int cnt = g.itemCount[b];
@@ -1067,7 +1098,7 @@ __global__ void k_conv_plan(ConvGeom G, const int *rank2id, const int4 *coords, 
 // Same algorithm, same results as the multi-launch path (tests compare both against the reference rulebooks).
 constexpr int kSmallSites = kSmallNb / 2;
 struct ConvSmallArgs {
-  const int4 *inCoords; int n, idOffset, doRank; int *rank2id;
+  const int4 *inCoords; int n, idOffset, doRank, spatial; int *rank2id;
   ConvGeom G;
   int *dir; unsigned long long *bmask; int *wbase; int *d_nblocks; int cells, dd1, dd2; int sz0, sz1, sz2; int cap;
   int4 *evPts; int *evQ, *evOff, *firstEv;
@@ -1101,7 +1132,9 @@ __global__ void __launch_bounds__(1024) k_conv_small(const ConvSmallArgs A) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = A.n, K = A.G.K;
   // ---- reference hash-iteration order of the input grid
-  if (A.doRank) {
+  if (A.doRank && A.spatial) {
+    for (int r = tid; r < n; r += 1024) A.rank2id[r] = r + A.idOffset;
+  } else if (A.doRank) {
     const SmallEmu e = emulate_small_body(A.inCoords, nullptr, A.idOffset, n, sm, A.cap, A.err);
     cta_scan(e.nb, [&](int i) { return e.tab[i] != kEmpty; },
              [&](int i, int pre, int v) { if (v) A.rank2id[pre] = e.seq[e.tab[i] >> kProbeBits]; }, s_scan);
@@ -1147,8 +1180,18 @@ __global__ void __launch_bounds__(1024) k_conv_small(const ConvSmallArgs A) {
   }
   __syncthreads();
   // ---- first-touch numbering of the output sites (ConvolutionRules.h:19-31)
-  const int nOut = cta_scan(n, [&](int r) { const int q = A.evQ[r]; return (int)(q >= 0 && __ldcg(A.firstEv + q) == r); },
-                            [&](int r, int pre, int v) { if (v) { const int q = A.evQ[r]; A.p2id[q] = pre; A.id2p[pre] = q; A.oCoords[pre] = A.evPts[r]; } }, s_scan);
+  int nOut;
+  if (A.spatial) { // row id = spatial index
+    for (int r = tid; r < n; r += 1024) {
+      const int q = A.evQ[r];
+      if (q >= 0 && __ldcg(A.firstEv + q) == r) { A.p2id[q] = q; A.id2p[q] = q; A.oCoords[q] = A.evPts[r]; }
+    }
+    nOut = nunique;
+    __syncthreads();
+  } else {
+    nOut = cta_scan(n, [&](int r) { const int q = A.evQ[r]; return (int)(q >= 0 && __ldcg(A.firstEv + q) == r); },
+                    [&](int r, int pre, int v) { if (v) { const int q = A.evQ[r]; A.p2id[q] = pre; A.id2p[pre] = q; A.oCoords[pre] = A.evPts[r]; } }, s_scan);
+  }
   // ---- rule lists: list L holds the (input row, output row) pairs of the events with offset L, in rank order
   int *s_tot = reinterpret_cast<int *>(sm), *s_off = s_tot + 64;
   int(*s_w)[64] = reinterpret_cast<int(*)[64]>(sm + 192);
@@ -1229,7 +1272,7 @@ int Metadata::get_conv_small(Grid &gi, Grid &go, ConvEntry &e, const ConvGeomHos
   SCN_CUDA(cudaMemsetAsync(firstEv, 0x7f, (size_t)n * 4, s));
   SCN_CUDA(cudaMemsetAsync(e.plan.nbr, 0xff, (size_t)nPad * G.K * 4, s));
   ConvSmallArgs A;
-  A.inCoords = gi.coords; A.n = n; A.idOffset = gi.itemCtr[0]; A.doRank = doRank ? 1 : 0; A.rank2id = gi.rank2id;
+  A.inCoords = gi.coords; A.n = n; A.idOffset = gi.itemCtr[0]; A.doRank = doRank ? 1 : 0; A.spatial = spatialIds ? 1 : 0; A.rank2id = gi.rank2id;
   A.G = G;
   A.dir = go.dir; A.bmask = go.bmask; A.wbase = go.wbase; A.d_nblocks = go.d_nblocks; A.cells = (int)cells; A.dd1 = go.dd[1]; A.dd2 = go.dd[2];
   A.sz0 = (int)go.sz[0]; A.sz1 = (int)go.sz[1]; A.sz2 = (int)go.sz[2];
@@ -1323,9 +1366,14 @@ int Metadata::get_conv(const long *inS, const long *outS, const long *f, const l
   go.coords = alloc_n<int4>(cap); go.p2id = alloc_n<int>(cap); go.id2p = alloc_n<int>(cap);
   int *firstEv = alloc_n<int>(cap);
   SCN_CHECK(go.coords && go.p2id && go.id2p && firstEv, "alloc");
-  SCN_CUDA(cudaMemsetAsync(firstEv, 0x7f, cap * 4, s));
-  if (E) k_first_event<<<stream_grid(E, 256), 256, 0, LS(s)>>>(evQ, E, firstEv);
-  SCN_TRY(run_scan(*this, E, EvFirstIn{evQ, firstEv}, EvFirstOut{evQ, evPts, go.p2id, go.id2p, go.coords, go.batch > 1 ? sc + 8 : nullptr}, sc + 3));
+  if (spatialIds) {
+    if (E) k_spatial_conv_ids<<<stream_grid(E, 256), 256, 0, LS(s)>>>(evQ, evPts, E, go.coords, go.p2id, go.id2p);
+    k_copy_scalar<<<1, 1, 0, LS(s)>>>(sc + 1, sc + 3);
+  } else {
+    SCN_CUDA(cudaMemsetAsync(firstEv, 0x7f, cap * 4, s));
+    if (E) k_first_event<<<stream_grid(E, 256), 256, 0, LS(s)>>>(evQ, E, firstEv);
+    SCN_TRY(run_scan(*this, E, EvFirstIn{evQ, firstEv}, EvFirstOut{evQ, evPts, go.p2id, go.id2p, go.coords, go.batch > 1 ? sc + 8 : nullptr}, sc + 3));
+  }
   // rule lists (one sync: list offsets + nOut + per-item counts)
   SCN_TRY(build_rule_lists(*this, n, G.K, ConvMask{G, gi->rank2id, gi->coords},
                            ConvPair{G, gi->rank2id, gi->coords, evQ, go.p2id}, e.rb, 64, /*write=*/false, &e.tileCnt));

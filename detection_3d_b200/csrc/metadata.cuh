@@ -125,11 +125,16 @@ struct Metadata {
   // only drains a short build queue while the convolutions already submitted keep the GPU busy (the
   // reference is synchronous throughout, SURVEY.md section 8b "Threading / streams").
   cudaStream_t cstream = 0;  // caller's compute stream
+  // Internal numbering (program replay only, never exposed): row id = spatial index.  Skips the emulation of the reference's
+  // hash-iteration order and the first-touch numbering -- the two steps that serialise the grid pyramid; the reference
+  // numbering of the few OUTPUT levels comes from a second, ordinary Metadata built beside it (program.cu).
+  bool spatialIds = false;
   bool poolGrowth = false;   // may take fresh memory instead of waiting for chunks a running forward still owns
   BuildCtx cx[2];
   int nCtx = 1;
   BuildCtx &cur();           // build context of the calling thread
   cudaEvent_t evCompute = nullptr;
+  cudaEvent_t coordsReady = nullptr; // optional (not owned): device coordinates are complete once this event has fired (input_layer, on_device == 1)
   int from_compute();        // the current build stream waits for everything the caller has queued so far
   // `mapMu` guards the structure of the caches and the ready / building flags; `cv` wakes threads
   // that wait for an entry another thread is building.

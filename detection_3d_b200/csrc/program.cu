@@ -7,6 +7,8 @@
 // caller's stream and frees after their last use.
 #include "../../include/scn_b200.h"
 #include "common.cuh"
+#include <algorithm>
+#include <array>
 #include <vector>
 
 namespace scn {
@@ -49,11 +51,15 @@ struct scn_program {
   int nRegs = 0;
   std::vector<int> lastUse;     // op index after which a register's buffers can be freed
   std::vector<char> isOutput;
+  std::vector<std::array<long, 3>> outSize; // spatial size of the grid every register lives on
   std::vector<Reg> regs;
   float *bnScratch = nullptr;   // saveMean / saveInvStd of inference-mode BatchNorm (unused downstream)
   int nStats = 0;               // convolutions whose epilogue accumulates the statistics of the BatchNorm that follows
   double *stats = nullptr;      // nStats x [kBnReplicas][2][kFusedStatsC], zeroed at the start of every run
   std::vector<char> statsDone;
+  scn_metadata *ms = nullptr;   // internally numbered Metadata of the current / last run (see scn_program_run)
+  bool internal = false;        // the registers of the last run are in internal row order
+  cudaEvent_t evCoords = nullptr;
   cudaEvent_t evEnd[2] = {nullptr, nullptr}; // end of the last two runs on `stream` (throttle of scn_program_prepare)
   long nRuns = 0;
   cudaStream_t stream = nullptr;
@@ -103,6 +109,8 @@ void scn_program_destroy(scn_program *p) {
   if (p->bnScratch) cudaFree(p->bnScratch);
   if (p->stats) cudaFree(p->stats);
   for (cudaEvent_t e : p->evEnd) if (e) cudaEventDestroy(e);
+  if (p->ms) scn_metadata_destroy(p->ms);
+  if (p->evCoords) cudaEventDestroy(p->evCoords);
   delete p;
 }
 int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, const double *fargs, int n_fargs) {
@@ -251,6 +259,17 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
     SCN_CHECK(outputs[i] >= 0 && outputs[i] < n_regs, "output register");
     p->isOutput[outputs[i]] = 1;
   }
+  p->outSize.assign(n_regs, std::array<long, 3>{0, 0, 0});
+  for (const Op &o : p->ops) { // grid of every register, propagated from its producer
+    auto sz3 = [](const long *v) { return std::array<long, 3>{v[0], v[1], v[2]}; };
+    switch (o.kind) {
+      case K_INPUT: p->outSize[o.a[0]] = sz3(o.a + 1); break;
+      case K_SUBM: p->outSize[o.a[1]] = sz3(o.a + 2); break;
+      case K_CONV: case K_DECONV: p->outSize[o.a[1]] = sz3(o.a + 5); break;
+      case K_BN: p->outSize[o.a[1]] = p->outSize[o.a[0]]; break;
+      case K_ADD: p->outSize[o.a[2]] = p->outSize[o.a[0]]; break;
+    }
+  }
   return 0;
 }
 
@@ -302,6 +321,62 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   if (p->stream && p->stream != s) SCN_CUDA(cudaStreamSynchronize(p->stream)); // slots are recycled in stream order
   p->stream = s;
   const int mode = scn_get_math_mode();
+  // ---- Which Metadata do the layers run on?
+  // A forward whose Metadata arrives unprepared runs on an INTERNALLY NUMBERED Metadata of its own (rows = spatial order):
+  // the reference's hash-iteration order and first-touch numbering -- ~40 % of the grid-pyramid latency, all of it on the
+  // critical path -- are not needed to compute anything, only to NAME the rows.  The caller's Metadata `m` is built beside
+  // it on a worker thread (input layer + the strided convolutions that lead to the output grids, in the reference's
+  // numbering) and the output rows are handed out in that numbering (scn_program_output_copy).  A Metadata prepared ahead
+  // (scn_program_prepare) or an input mode / batch the internal numbering does not cover uses `m` for everything, as before.
+  static int internalOn = -1;
+  if (internalOn < 0) internalOn = getenv("SCN_INTERNAL_IDS") ? atoi(getenv("SCN_INTERNAL_IDS")) : 1;
+  if (p->ms) { scn_metadata_destroy(p->ms); p->ms = nullptr; }
+  p->internal = false;
+  scn_metadata *M = m;
+  const Op *inOp = nullptr;
+  for (const Op &o : p->ops) if (o.kind == K_INPUT) { inOp = &o; break; }
+  if (internalOn && inOp && inOp->a[4] != 0 && !scn_input_layer_built(m, nullptr, nullptr)) {
+    if (coords_on_device == 1) {
+      if (!p->evCoords) SCN_CUDA(cudaEventCreateWithFlags(&p->evCoords, cudaEventDisableTiming));
+      SCN_CUDA(cudaEventRecord(p->evCoords, s));
+    }
+    SCN_TRY(scn_metadata_create(&p->ms, stream));
+    SCN_TRY(scn_metadata_set_internal_numbering(p->ms, 1));
+    SCN_TRY(scn_program_prepare(p, p->ms, coords, coords_on_device, nrows, ncols));
+    int batch = 0;
+    SCN_TRY(scn_get_batch_size(p->ms, inOp->a + 1, &batch));
+    // the strided convolutions whose output grid an output register lives on, or that lead there
+    std::vector<std::array<long, 3>> need;
+    for (int r = 0; r < p->nRegs; r++) if (p->isOutput[r]) need.push_back(p->outSize[r]);
+    std::vector<long> hints;
+    for (bool grew = true; grew;) {
+      grew = false;
+      for (const Op &o : p->ops) {
+        if (o.kind != K_CONV) continue;
+        const std::array<long, 3> in{o.a[2], o.a[3], o.a[4]}, out{o.a[5], o.a[6], o.a[7]};
+        if (std::find(need.begin(), need.end(), out) != need.end() && std::find(need.begin(), need.end(), in) == need.end()) { need.push_back(in); grew = true; }
+      }
+    }
+    for (const Op &o : p->ops) {
+      if (o.kind != K_CONV) continue;
+      const std::array<long, 3> out{o.a[5], o.a[6], o.a[7]};
+      if (std::find(need.begin(), need.end(), out) == need.end()) continue;
+      long h[13] = {0};
+      h[0] = 2;
+      for (int d = 0; d < 12; d++) h[1 + d] = o.a[2 + d];
+      hints.insert(hints.end(), h, h + 13);
+    }
+    if (batch == 1)
+    SCN_TRY(scn_metadata_build_reference_grids(m, inOp->a + 1, coords, coords_on_device, nrows, ncols, (int)inOp->a[5], (int)inOp->a[4],
+                                               (int)(hints.size() / 13), hints.data(), coords_on_device == 1 ? p->evCoords : nullptr));
+    if (batch == 1) {
+      M = p->ms;
+      p->internal = true;
+    } else { // several batch items: the caller's Metadata does everything (reference numbering throughout)
+      scn_metadata_destroy(p->ms);
+      p->ms = nullptr;
+    }
+  }
   if (!p->bnScratch) SCN_CUDA(cudaMalloc((void **)&p->bnScratch, 2 * scn::kBnMaxC * sizeof(float)));
   auto P = [&](long i) -> const float * { return (i < 0 || i >= n_params) ? nullptr : static_cast<const float *>(params[i]); };
   auto T = [&](long i) -> long long { return (i < 0 || i >= n_params || !tags) ? 0 : tags[i]; };
@@ -356,9 +431,9 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_INPUT: { // out, size[3], mode, batch hint, planes
         long nActive = 0;
         int maxActive = 0;
-        if (!scn_input_layer_built(m, &nActive, &maxActive)) { // not prepared ahead (scn_program_prepare)
-          rc = scn_program_prepare(p, m, coords, coords_on_device, nrows, ncols);
-          if (rc == 0 && !scn_input_layer_built(m, &nActive, &maxActive)) { scn::set_error("program: no input layer"); rc = -2; }
+        if (!scn_input_layer_built(M, &nActive, &maxActive)) { // not prepared ahead (scn_program_prepare)
+          rc = scn_program_prepare(p, M, coords, coords_on_device, nrows, ncols);
+          if (rc == 0 && !scn_input_layer_built(M, &nActive, &maxActive)) { scn::set_error("program: no input layer"); rc = -2; }
           if (rc) break;
         }
         rc = alloc_reg(a[0], nActive, (int)a[6], false);
@@ -370,51 +445,51 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
           R0.p16 = slot_get(p, (size_t)nActive * Cp * 2);
           if (!R0.p16) { rc = -1; break; }
           R0.pad16 = Cp;
-          rc = scn_input_layer_forward_padded_bf16(m, feats, R0.p, R0.p16, C0, Cp);
-        } else if (rc == 0 && nActive) rc = scn_input_layer_forward(m, feats, p->regs[a[0]].p, (int)a[6]);
+          rc = scn_input_layer_forward_padded_bf16(M, feats, R0.p, R0.p16, C0, Cp);
+        } else if (rc == 0 && nActive) rc = scn_input_layer_forward(M, feats, p->regs[a[0]].p, (int)a[6]);
         break;
       }
       case K_SUBM: { // in, out, size[3], filter[3], w, bias, Cin, Cout
         long n = 0;
-        rc = scn_get_nactive(m, a + 2, &n);
+        rc = scn_get_nactive(M, a + 2, &n);
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], a[22] >= 0 || a[18] >= 0);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0 && I.pad16) scn::prepadded_arm(I.p16, I.pad16);
         if (rc == 0)
-          rc = scn_submanifold_convolution_forward(m, a + 2, a + 5, I.p, p->regs[a[1]].p, P(a[8]), P(a[9]), (int)a[10], (int)a[11], &mk, I.pad16 ? nullptr : I.p16, T(a[8]),
+          rc = scn_submanifold_convolution_forward(M, a + 2, a + 5, I.p, p->regs[a[1]].p, P(a[8]), P(a[9]), (int)a[10], (int)a[11], &mk, I.pad16 ? nullptr : I.p16, T(a[8]),
                                                    a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         took(op);
         scn::prepadded_disarm();
-        if (rc == 0) rc = lateral_fallback(op, m, a + 2, p->regs[a[1]], (int)a[11]);
+        if (rc == 0) rc = lateral_fallback(op, M, a + 2, p->regs[a[1]], (int)a[11]);
         macs += mk;
         break;
       }
       case K_CONV: { // in, out, inS[3], outS[3], f[3], s[3], w, bias, Cin, Cout
         long n = 0, nr = 0;
-        rc = scn_convolution_prepare(m, a + 2, a + 5, a + 8, a + 11, &n, &nr);
+        rc = scn_convolution_prepare(M, a + 2, a + 5, a + 8, a + 11, &n, &nr);
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0 || a[18] >= 0);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0)
-          rc = scn_convolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.pad16 ? nullptr : I.p16, T(a[14]),
+          rc = scn_convolution_forward(M, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.pad16 ? nullptr : I.p16, T(a[14]),
                                        a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         took(op);
-        if (rc == 0) rc = lateral_fallback(op, m, a + 5, p->regs[a[1]], (int)a[17]);
+        if (rc == 0) rc = lateral_fallback(op, M, a + 5, p->regs[a[1]], (int)a[17]);
         macs += mk;
         break;
       }
       case K_DECONV: {
         long n = 0;
-        rc = scn_get_nactive(m, a + 5, &n);
+        rc = scn_get_nactive(M, a + 5, &n);
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0 || a[18] >= 0);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0)
-          rc = scn_deconvolution_forward(m, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.pad16 ? nullptr : I.p16, T(a[14]),
+          rc = scn_deconvolution_forward(M, a + 2, a + 5, a + 8, a + 11, I.p, p->regs[a[1]].p, P(a[14]), P(a[15]), (int)a[16], (int)a[17], &mk, I.pad16 ? nullptr : I.p16, T(a[14]),
                                          a[22] >= 0 ? p->regs[a[22]].p : nullptr, p->regs[a[1]].p16);
         took(op);
-        if (rc == 0) rc = lateral_fallback(op, m, a + 5, p->regs[a[1]], (int)a[17]);
+        if (rc == 0) rc = lateral_fallback(op, M, a + 5, p->regs[a[1]], (int)a[17]);
         macs += mk;
         break;
       }
@@ -453,6 +528,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   }
   if (rc) { release_regs(p, true); return rc; }
   if (macs_out) *macs_out = macs;
+  if (p->internal) SCN_TRY(scn_metadata_wait_jobs(m)); // the reference-numbered grids of the outputs
   cudaEvent_t &ev = p->evEnd[p->nRuns & 1];
   if (!ev) SCN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   SCN_CUDA(cudaEventRecord(ev, s));
@@ -463,6 +539,15 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
 int scn_copy_device(void *dst, const void *src, long bytes, void *stream) {
   if (bytes > 0) SCN_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return 0;
+}
+// Copies an output register into caller memory (device, on the run's stream) in the row order of `m`: a plain copy, or --
+// when the run used the internal numbering -- the rows gathered into the reference numbering.
+int scn_program_output_copy(scn_program *p, scn_metadata *m, int reg, const long spatial_size[3], float *dst) {
+  SCN_CHECK(p && reg >= 0 && reg < p->nRegs && p->isOutput[reg], "not an output register");
+  const Reg &R = p->regs[reg];
+  if (R.rows == 0) return 0;
+  if (p->internal) return scn_rows_to_reference_order(m, p->ms, spatial_size, R.p, dst, R.cols);
+  return scn_copy_device(dst, R.p, R.rows * R.cols * 4, p->stream);
 }
 int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const float **ptr) {
   SCN_CHECK(p && reg >= 0 && reg < p->nRegs && p->isOutput[reg], "not an output register");

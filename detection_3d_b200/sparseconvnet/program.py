@@ -164,13 +164,13 @@ class Program(object):
         check(lib().scn_program_run(self._h, metadata._h, C.c_void_p(coords.data_ptr()), int(coords.is_cuda), coords.size(0), coords.size(1),
                                     C.c_void_p(feats.data_ptr()), ptrs, tags, n, stream, C.byref(macs)))
         outs, cache = [], {}
-        for r in self.out_regs:
+        for r, size in zip(self.out_regs, self.out_sizes):
             if r not in cache:
                 rows, cols, ptr = C.c_long(), C.c_int(), C.c_void_p()
                 check(lib().scn_program_output(self._h, r, C.byref(rows), C.byref(cols), C.byref(ptr)))
                 t = torch.empty((rows.value, cols.value), dtype=torch.float32, device=feats.device)
-                if t.numel():
-                    native.copy_device_to_tensor(t, ptr.value)
+                if t.numel():  # rows in the numbering of `metadata` (the executor may have computed them in its internal order)
+                    check(lib().scn_program_output_copy(self._h, metadata._h, r, l3(size), C.c_void_p(t.data_ptr())))
                 cache[r] = t
             outs.append(cache[r])
         return outs, macs.value

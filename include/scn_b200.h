@@ -164,6 +164,17 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
 int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coords_on_device, long nrows, int ncols,
                     const float *features, const void *const *params, const long long *weight_tags, int n_params,
                     void *stream, double *macs);
+/* Internal row numbering (used by scn_program_run, never handed to callers): rows of every grid are numbered by spatial
+ * index instead of the reference's first-touch order in dense_hash_map iteration order, which removes the hash-order
+ * emulation from the critical path.  scn_rows_to_reference_order hands a feature matrix computed under such a Metadata
+ * out in the reference numbering of an ordinary Metadata built from the same input. */
+int scn_metadata_set_internal_numbering(scn_metadata *m, int on);
+int scn_metadata_build_reference_grids(scn_metadata *m, const long spatial_size[3], const long *coords, int coords_on_device, long nrows, int ncols,
+                                       int batch_size, int mode, int n_ops, const long *ops, void *coords_ready_event);
+int scn_metadata_wait_jobs(scn_metadata *m);
+/* batch items of the grid of this spatial size (0 when there is none) */
+int scn_get_batch_size(scn_metadata *m, const long spatial_size[3], int *batch);
+int scn_rows_to_reference_order(scn_metadata *ref, scn_metadata *internal, const long spatial_size[3], const float *src, float *dst, int cols);
 /* Build half of a run, callable ahead of scn_program_run for the NEXT input while the GPU still computes the current
  * one (streaming many buildings through one network): input layer + the worker threads that build every rulebook the
  * program requests.  coords_on_device: 0 host, 1 device (ordered after the caller's stream), 2 device and complete.
@@ -176,6 +187,8 @@ int scn_program_throttle(scn_program *p);
  * waiting for chunks a still-running forward owns (bounded pool growth); 0 (default) otherwise. */
 int scn_set_pool_growth(int on);
 int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const float **ptr);
+/* output register -> caller's device buffer [rows][cols], in the row numbering of the caller's Metadata `m` */
+int scn_program_output_copy(scn_program *p, scn_metadata *m, int reg, const long spatial_size[3], float *dst);
 /* device-to-device copy on `stream` (hands an output register to a caller-owned tensor) */
 int scn_copy_device(void *dst, const void *src, long bytes, void *stream);
 
