@@ -252,6 +252,7 @@ int scn_metadata_build_reference_grids(scn_metadata *m, const long sz[3], const 
   for (int d = 0; d < 3; d++) m->inSz[d] = sz[d];
   m->inCoords = coords; m->inOnDevice = on_device; m->inRows = nrows; m->inCols = ncols; m->inBatch = batch_size; m->inMode = mode;
   m->md.coordsReady = static_cast<cudaEvent_t>(coords_ready_event);
+  // (normal-priority streams for this job -- Metadata::use_low_priority_streams -- were measured slightly slower: 5.39 vs 5.27 ms)
   m->ops.clear();
   m->ops2.clear();
   PrefetchOp in;

@@ -50,7 +50,7 @@ constexpr size_t kChunkGrow = 16ull << 30; // below this total, a new chunk is a
 // blocking every other thread's launches.)
 static size_t chunk_round(size_t b) { size_t c = 32u << 20; while (c < b) c <<= 1; return c; }
 // build streams are recycled like the pinned blocks (stream creation is not free either)
-static std::vector<cudaStream_t> g_stream_free;
+static std::vector<cudaStream_t> g_stream_free, g_stream_free_lo;
 static std::vector<cudaEvent_t> g_event_free;
 thread_local bool tl_prefetch_worker = false;
 thread_local int tl_ctx = 0; // build context of this thread: 0 = caller and chain worker, 1 = second prefetch worker
@@ -131,10 +131,37 @@ Metadata::~Metadata() {
       g_chunk_bytes += k.cap;
     }
     if (c.h_scalars) g_pinned_free.push_back(c.h_scalars);
-    if (c.ownStream) g_stream_free.push_back(c.stream);
+    if (c.ownStream) (c.lowPrio ? g_stream_free_lo : g_stream_free).push_back(c.stream);
   }
   for (cudaEvent_t e : events) g_event_free.push_back(e);
   if (evCompute) cudaEventDestroy(evCompute);
+}
+// The build streams are high-priority so that the short build kernels of the grid pyramid get in front of the long
+// convolution kernels.  A Metadata whose grids are only needed at the END of a forward (the reference-numbered twin of an
+// internally numbered run) must not compete with that pyramid: its contexts move to normal-priority streams.
+int Metadata::use_low_priority_streams() {
+  for (int i = 0; i < nCtx; i++) {
+    BuildCtx &c = cx[i];
+    if (!c.ownStream || c.lowPrio) continue;
+    cudaStream_t lo = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(g_pool_mu);
+      if (!g_stream_free_lo.empty()) { lo = g_stream_free_lo.back(); g_stream_free_lo.pop_back(); }
+    }
+    if (!lo) {
+      int least = 0, greatest = 0;
+      SCN_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      SCN_CUDA(cudaStreamCreateWithPriority(&lo, cudaStreamNonBlocking, least));
+    }
+    if (evCompute) { // what init() queued on the old stream (pool memsets) comes first
+      SCN_CUDA(cudaEventRecord(evCompute, c.stream));
+      SCN_CUDA(cudaStreamWaitEvent(lo, evCompute, 0));
+    }
+    { std::lock_guard<std::mutex> lk(g_pool_mu); g_stream_free.push_back(c.stream); }
+    c.stream = lo;
+    c.lowPrio = true;
+  }
+  return 0;
 }
 int Metadata::from_compute() {
   if (cur().stream == cstream || !evCompute) return 0;

@@ -104,6 +104,7 @@ struct Chunk { void *p; size_t cap; cudaEvent_t freed; };
 struct BuildCtx {
   cudaStream_t stream = 0;
   bool ownStream = false;
+  bool lowPrio = false;     // stream taken from the normal-priority list (use_low_priority_streams)
   int *d_scalars = nullptr; // small device scratch (256 ints)
   int *h_scalars = nullptr; // pinned host mirror
   int *d_err = nullptr;
@@ -135,6 +136,7 @@ struct Metadata {
   BuildCtx &cur();           // build context of the calling thread
   cudaEvent_t evCompute = nullptr;
   cudaEvent_t coordsReady = nullptr; // optional (not owned): device coordinates are complete once this event has fired (input_layer, on_device == 1)
+  int use_low_priority_streams(); // builds of this Metadata are not urgent: move its build contexts to normal-priority streams
   int from_compute();        // the current build stream waits for everything the caller has queued so far
   // `mapMu` guards the structure of the caches and the ready / building flags; `cv` wakes threads
   // that wait for an entry another thread is building.
