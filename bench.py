@@ -160,6 +160,13 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference_arm(args, rank, world)
+    # stdout carries exactly ONE line (the JSON): libraries that chat on fd 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     import numpy as np
     import torch
@@ -310,7 +317,7 @@ def main():
         line["cpu_baseline"] = {"value": (nv / B470_VOXELS) / t, "unit": "buildings/s", "cores": threads, "kind": kind,
                                 "sample": f"one forward of a {nx}x{nx}x68 crop of B470 ({nv} voxels = {nv / B470_VOXELS:.3f} building, {macs / 1e9:.1f} GMAC) in {t:.1f} s, scaled by voxel count"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
