@@ -281,8 +281,10 @@ def main():
     e2e_ms, _ = timed(step_e2e, args.steps, 1)
     # streaming variant (FPN_Net.prefetch builds the Metadata two buildings ahead); reported beside the headline, which
     # stays the plain one-building-at-a-time number
-    stream_ms, _ = timed_stream(step_resident, coords_dev, args.steps, 6)  # (the Metadata pool needs a few streamed steps to reach its steady size)
-    net.__dict__.pop("_prefetched", None)
+    stream_ms = None
+    if world == 1:  # (single-process extra; the Metadata pool needs a few streamed steps to reach its steady size)
+        stream_ms, _ = timed_stream(step_resident, coords_dev, args.steps, 6)
+        net.__dict__.pop("_prefetched", None)
     ms_step = total_ms / args.steps
     value = world * 1e3 / ms_step
     d2h = 0
@@ -302,8 +304,9 @@ def main():
                      "bf16": "bf16 operands (tf32 where rows are < 64 channels), fp32 accumulate, fp32 feature tensors; end-to-end <= 6e-2 of max|ref| (tests), measured 2.3e-2"}[math],
         "config": {"workload": "sw_4c_fpn432 backbone forward incl. Metadata/rulebook build, one B470 synthetic building (1,155,656 active voxels) per GPU per step",
                    "l2": "256 MiB L2 flush between timed iterations", "parallelism": f"replicas x{world}, no collective"},
-        "streaming": {"ms_per_step": stream_ms / args.steps, "value": world * 1e3 / (stream_ms / args.steps), "unit": "buildings/s",
-                      "note": "same forwards back to back with FPN_Net.prefetch building the Metadata two buildings ahead; L2 flush inside the timed region"},
+        "streaming": None if stream_ms is None else {
+            "ms_per_step": stream_ms / args.steps, "value": world * 1e3 / (stream_ms / args.steps), "unit": "buildings/s",
+            "note": "same forwards back to back with FPN_Net.prefetch building the Metadata two buildings ahead; L2 flush inside the timed region"},
         "tflops": value * 2 * macs_per_step / 1e12, "gmac_per_step": macs_per_step / 1e9,
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": world * 1e3 / (e2e_ms / args.steps), "unit": "buildings/s", "h2d_bytes_per_step": coords_np.nbytes + feats_np.nbytes, "d2h_bytes_per_step": d2h},
