@@ -572,6 +572,39 @@ def test_fpn_forward_tensor_core_vs_reference_golden(name, cfgname, bld, math):
             assert err < TC_E2E[math], (tag, i, float(err))
 
 
+def test_replayed_program_with_internal_numbering_vs_reference_golden():
+    """Second forward of the sw4c backbone on the 300x280x40 building = program replay on an internally numbered Metadata
+    (rows in spatial order, no hash-order emulation on the critical path; general multi-launch build for the large levels,
+    one-launch build for the small ones) with the outputs gathered into the reference numbering: features and row
+    coordinates must equal the outputs of the reference's own scn.FPN_Net (golden fixture), like the first forward's."""
+    import detection_3d_b200.sparseconvnet as scn
+    cfg = scn.sw4c_fpn432_config()
+    bld = dict(nx=300, ny=280, nz=40, n_walls=5, seed=5)
+    g = np.load(os.path.join(GOLD, "fpn_sw4c_mid.npz"))
+    try:
+        scn.set_math_mode("fp32")
+        net = scn.FPN_Net(**cfg)
+        net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+        net = net.cuda().eval()
+        coords = synthetic.building_coords(**bld)
+        c, f = torch.from_numpy(coords), torch.from_numpy(fpn_util.features_for(coords)).cuda()
+        with torch.no_grad():
+            net([c, f])  # records
+            assert net.__dict__.get("_program") is not None, net.__dict__.get("_program_error")
+            for _ in range(2):
+                scn.forward_pass_multiplyAdd_count = 0
+                rpn, roi = net([c, f])  # replays
+                assert scn.forward_pass_multiplyAdd_count == float(g["macs"])
+                for tag, maps in (("rpn", rpn), ("roi", roi)):
+                    assert len(maps) == int(g[f"n_{tag}"])
+                    for i, m in enumerate(maps):
+                        assert np.array_equal(m.get_spatial_locations().numpy(), g[f"{tag}{i}_locations"]), (tag, i)
+                        _close(m.features.cpu().numpy(), g[f"{tag}{i}_features"], rtol=2e-3, atol=2e-4)
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+
+
 # ------------------------------------------------------------------ recorded program (one native call per forward)
 @pytest.mark.parametrize("math", ["fp32", "bf16"])
 def test_recorded_program_matches_layer_by_layer(math):
