@@ -131,6 +131,7 @@ class FPN_Net(nn.Module):
                 self.__dict__.setdefault("_prefetched", []).append((coords, coords._version, md))
             if dev is not None and isinstance(feats, torch.Tensor):
                 feats = feats.to(dev, non_blocking=True)
+                net0 = [coords, feats] + list(net0[2:])  # (the layer-by-layer path below must see the device tensor too)
             if prog is not None and isinstance(coords, torch.Tensor) and prog.usable(coords, feats, mode):
                 return self._run_program(prog, coords, feats)
             if prog is None and self.__dict__.get("_program_error") is None and isinstance(feats, torch.Tensor) and feats.is_cuda:
