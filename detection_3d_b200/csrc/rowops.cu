@@ -256,15 +256,26 @@ __global__ void __launch_bounds__(256) k_bn_apply_sums(const float *__restrict__
     sShift[c] = -mean * w + (F.bias ? F.bias[c] : 0.f);
   }
   __syncthreads();
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % cv);
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
-    const float4 a = reinterpret_cast<const float4 *>(sScale)[cg], b = reinterpret_cast<const float4 *>(sShift)[cg];
-    float4 o;
-    o.x = fmaf(v.x, a.x, b.x); o.y = fmaf(v.y, a.y, b.y); o.z = fmaf(v.z, a.z, b.z); o.w = fmaf(v.w, a.w, b.w);
-    o.x = o.x > 0 ? o.x : o.x * leak; o.y = o.y > 0 ? o.y : o.y * leak; o.z = o.z > 0 ? o.z : o.z * leak; o.w = o.w > 0 ? o.w : o.w * leak;
-    if (y) reinterpret_cast<float4 *>(y)[i] = o; // y == nullptr: only the bf16 copy is consumed downstream
-    if (y16) store_bf16x4(y16, i, o);
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < total4; i0 += 4 * stride) { // four independent 16-byte loads in flight per thread
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long i = i0 + u * stride;
+      if (i < total4) v[u] = __ldg(reinterpret_cast<const float4 *>(x) + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long i = i0 + u * stride;
+      if (i >= total4) break;
+      const int cg = (int)(i % cv);
+      const float4 a = reinterpret_cast<const float4 *>(sScale)[cg], b = reinterpret_cast<const float4 *>(sShift)[cg];
+      float4 o;
+      o.x = fmaf(v[u].x, a.x, b.x); o.y = fmaf(v[u].y, a.y, b.y); o.z = fmaf(v[u].z, a.z, b.z); o.w = fmaf(v[u].w, a.w, b.w);
+      o.x = o.x > 0 ? o.x : o.x * leak; o.y = o.y > 0 ? o.y : o.y * leak; o.z = o.z > 0 ? o.z : o.z * leak; o.w = o.w > 0 ? o.w : o.w * leak;
+      if (y) reinterpret_cast<float4 *>(y)[i] = o; // y == nullptr: only the bf16 copy is consumed downstream
+      if (y16) store_bf16x4(y16, i, o);
+    }
   }
 }
 int bn_forward_from_sums(const float *x, float *y, long n, int C, const double *sums, float *saveMean, float *saveInvStd, float *runningMean,
@@ -408,23 +419,42 @@ __global__ void __launch_bounds__(256) k_input_bwd(float *__restrict__ din, cons
 }
 // Same, plus a bf16 copy of the output rows zero-padded to Cp channels (the packed operand of the first convolution in
 // bf16 mode, which otherwise needs a separate padding pass over the rows).
+// One thread per output row: the rule-table entries are read once per row (not once per channel) and the bf16 row
+// (Cp <= 32 channels) leaves as 16-byte stores.
 __global__ void __launch_bounds__(256) k_input_fwd_pad16(const float *__restrict__ in, float *__restrict__ out, __nv_bfloat16 *__restrict__ out16, int nOut, int w,
                                                          int C, int Cp, const int *__restrict__ tab, int average) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < (long)nOut * Cp; i += (long)gridDim.x * blockDim.x) {
-    int row = (int)(i / Cp), c = (int)(i % Cp);
-    float acc = 0.f;
-    if (c < C) {
-      const int *r = tab + (long)row * w;
-      int na = r[0];
-      float mult = (average && na > 0) ? 1.f / na : 1.f;
-      for (int j = 1; j <= na; j++) acc += mult * __ldg(in + (long)r[j] * C + c);
-      out[(long)row * C + c] = acc;
+  for (long row = blockIdx.x * (long)blockDim.x + threadIdx.x; row < nOut; row += (long)gridDim.x * blockDim.x) {
+    const int *r = tab + row * w;
+    const int na = r[0];
+    const float mult = (average && na > 0) ? 1.f / na : 1.f;
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) acc[c] = 0.f;
+    for (int j = 1; j <= na; j++) {
+      const float *src = in + (long)r[j] * C;
+#pragma unroll
+      for (int c = 0; c < 32; c++)
+        if (c < C) acc[c] += mult * __ldg(src + c);
     }
-    out16[i] = __float2bfloat16_rn(acc);
+#pragma unroll
+    for (int c = 0; c < 32; c++)
+      if (c < C) out[row * C + c] = acc[c];
+    uint4 *dst = reinterpret_cast<uint4 *>(out16 + row * Cp);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (q * 8 >= Cp) break;
+      __nv_bfloat162 v0 = __floats2bfloat162_rn(acc[q * 8], acc[q * 8 + 1]), v1 = __floats2bfloat162_rn(acc[q * 8 + 2], acc[q * 8 + 3]);
+      __nv_bfloat162 v2 = __floats2bfloat162_rn(acc[q * 8 + 4], acc[q * 8 + 5]), v3 = __floats2bfloat162_rn(acc[q * 8 + 6], acc[q * 8 + 7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<unsigned int *>(&v0); pk.y = *reinterpret_cast<unsigned int *>(&v1);
+      pk.z = *reinterpret_cast<unsigned int *>(&v2); pk.w = *reinterpret_cast<unsigned int *>(&v3);
+      dst[q] = pk;
+    }
   }
 }
 int input_forward_pad16(const float *in, float *out, void *out16, int nOut, int maxActive, int C, int Cp, const int *tab, int average, cudaStream_t s) {
-  if (nOut) k_input_fwd_pad16<<<stream_grid((long)nOut * Cp, 256), 256, 0, LS(s)>>>(in, out, static_cast<__nv_bfloat16 *>(out16), nOut, 1 + maxActive, C, Cp, tab, average);
+  SCN_CHECK(C <= 32 && Cp <= 32 && Cp % 8 == 0 && Cp >= C, "input_forward_pad16: at most 32 channels");
+  if (nOut) k_input_fwd_pad16<<<stream_grid(nOut, 256, 16), 256, 0, LS(s)>>>(in, out, static_cast<__nv_bfloat16 *>(out16), nOut, 1 + maxActive, C, Cp, tab, average);
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
