@@ -180,8 +180,9 @@ def main():
         # GPU events dozens of times per forward; ranks migrating over each other's cores cost ~2 ms per step at N = 2)
         try:
             cores = sorted(os.sched_getaffinity(0))
-            per = max(1, len(cores) // world)
-            os.sched_setaffinity(0, cores[local * per:(local + 1) * per] or cores)
+            per = len(cores) // world
+            if per >= 4:  # main thread + three build workers; with fewer cores per rank the scheduler does better unpinned
+                os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
         except OSError:
             pass
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
