@@ -489,6 +489,7 @@ static int run_plan(Metadata &M, const scn::NbrPlan &plan, const float *in, floa
   if (tc_ok(Cin, Cout, plan.K))
     return scn::launch_conv_plan_tc(in, out, w, plan.nbr, plan.outRow, plan.tileMask, plan.nOut, plan.K, Cin, Cout, bias, scn::g_math_mode, M.cstream,
                                     nullptr, plan.K, nInRows, in16, wTag, addend, out16, plan.nOut);
+  SCN_CHECK(in && out, "CUDA-core path needs the fp32 rows");
   SCN_TRY(scn::launch_conv_plan_simt(in, out, w, plan.nbr, plan.outRow, plan.nOut, plan.K, Cin, Cout, bias, M.cstream));
   return plain_epilogue(out, addend, out16, plan.nOut, Cout, M.cstream);
 }
@@ -536,6 +537,7 @@ int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long out
     return scn::launch_conv_plan_tc(in, out, w, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, 1, Cin, Cout, nullptr, scn::g_math_mode, s, d.tileW,
                                     e->rb.nLists, m->md.find_grid(inS)->n, in_bf16, weight_tag, add_in, out_bf16, gf->n);
   }
+  SCN_CHECK(in && out, "CUDA-core deconvolution needs the fp32 rows");
   SCN_TRY(m->md.ensure_conv_rules(*e));
   SCN_TRY(m->md.wait_ready(e->rdy));
   SCN_TRY(m->md.wait_ready(e->rulesRdy));

@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 32
 #pragma unroll
             for (int i = 0; i < NI; i++)
               if (rows[i] >= 0) {
-                *reinterpret_cast<float4 *>(P.out + (size_t)rows[i] * P.Cout + c0 + cc) = o[i];
+                if (P.out) *reinterpret_cast<float4 *>(P.out + (size_t)rows[i] * P.Cout + c0 + cc) = o[i]; // null: only the bf16 copy is consumed
                 if (P.out16) {
                   __nv_bfloat162 lo = __floats2bfloat162_rn(o[i].x, o[i].y), hi = __floats2bfloat162_rn(o[i].z, o[i].w);
                   uint2 pk;
@@ -831,6 +831,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   P.lag = std::max(0, std::min(3, envLag >= 0 ? envLag : P.S - 2));
   if (P.lag > P.S - 2) P.lag = std::max(0, P.S - 2);
   const size_t smem = (size_t)P.S * stageBytes + fixed;
+  SCN_CHECK(out || (P.kSplit == 1 && out16), "tcgen05 path: fp32 output dropped on a launch that needs it");
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
   unsigned char *wimg = nullptr;
   bool wimgOwned = false;

@@ -24,6 +24,7 @@ int bn_forward_from_sums(const float *x, float *y, long n, int C, const double *
 
 namespace {
 
+constexpr long kHalfOnlyRows = 32768; // from here on a convolution never splits its filter offsets over CTAs (its epilogue stores final values)
 enum Kind { K_INPUT = 0, K_SUBM = 1, K_CONV = 2, K_DECONV = 3, K_BN = 4, K_ADD = 5 };
 struct Op {
   int kind;
@@ -121,6 +122,7 @@ int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, co
   for (int i = 0; i < 4; i++) op.f[i] = i < n_fargs ? fargs[i] : 0.0;
   op.a[18] = -1; // lateral 1x1x1 convolution folded into this convolution: its input register, weight parameter (a[19]), channels (a[20])
   op.a[21] = -1; // statistics slot shared by a convolution and the BatchNorm ops that read its output (scn_program_finish)
+  op.a[23] = 0;
   op.a[22] = -1; // register added in the epilogue of a convolution (set by the fusion pass of scn_program_finish)
   p->ops.push_back(op);
   return 0;
@@ -232,6 +234,13 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
       if (o.a[18] >= 0) bad[o.a[18]] = 1; // whether a lateral is folded in (bf16 copy) or run on its own is decided at run time: keep the fp32 rows
     }
     for (Op &bn : p->ops) if (bn.kind == K_BN) bn.a[19] = (good[bn.a[1]] && !bad[bn.a[1]] && bn.a[2] % 32 == 0) ? 1 : 0;
+    // the same for the OUTPUT of a convolution (a[23] = 1): the finest top-down sum deconv(x) + lateral is read only by the
+    // merged 3^3 convolution.  Applied at run time to large levels only (no offset splitting there, see launch_conv_plan_tc).
+    for (Op &c : p->ops)
+      if (c.kind == K_SUBM || c.kind == K_CONV || c.kind == K_DECONV) {
+        const long Cout = c.kind == K_SUBM ? c.a[11] : c.a[17];
+        c.a[23] = (good[c.a[1]] && !bad[c.a[1]] && Cout % 32 == 0) ? 1 : 0;
+      }
   }
   p->nRegs = n_regs;
   p->lastUse.assign(n_regs, -1);
@@ -415,6 +424,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     const Reg &Y = p->regs[op.a[18]];
     macs += (double)Y.rows * (double)op.a[20] * Cout;
     if (done || out.rows == 0) return 0;
+    if (!out.p) { scn::set_error("program: lateral not folded in although the fp32 output was dropped"); return -2; }
     float *tmp = static_cast<float *>(slot_get(p, (size_t)out.rows * Cout * 4));
     if (!tmp) return -1;
     const long one[3] = {1, 1, 1};
@@ -452,7 +462,8 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_SUBM: { // in, out, size[3], filter[3], w, bias, Cin, Cout
         long n = 0;
         rc = scn_get_nactive(M, a + 2, &n);
-        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], a[22] >= 0 || a[18] >= 0);
+        const bool half = a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], half || a[22] >= 0 || a[18] >= 0, half);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0 && I.pad16) scn::prepadded_arm(I.p16, I.pad16);
@@ -468,7 +479,8 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_CONV: { // in, out, inS[3], outS[3], f[3], s[3], w, bias, Cin, Cout
         long n = 0, nr = 0;
         rc = scn_convolution_prepare(M, a + 2, a + 5, a + 8, a + 11, &n, &nr);
-        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0 || a[18] >= 0);
+        const bool half = a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], half || a[22] >= 0 || a[18] >= 0, half);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0)
@@ -482,7 +494,8 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_DECONV: {
         long n = 0;
         rc = scn_get_nactive(M, a + 5, &n);
-        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], a[22] >= 0 || a[18] >= 0);
+        const bool half = a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
+        if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], half || a[22] >= 0 || a[18] >= 0, half);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
         if (rc == 0)
