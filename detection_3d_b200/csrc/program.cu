@@ -217,8 +217,8 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
     }
   }
   { // bf16 mode: a BatchNorm output that only feeds tensor-core convolutions gathering its bf16 copy is never read in fp32;
-    // such BatchNorm ops (a[19] = 1) write the bf16 copy only.  Deconvolutions are excluded (their CUDA-core fallback is a
-    // run-time decision), as are outputs, addends and anything whose channel counts take the TF32 / CUDA-core route.
+    // such BatchNorm ops (a[19] = 1) write the bf16 copy only.  Outputs, addends, laterals and anything whose channel counts
+    // or geometry may take the TF32 / CUDA-core route keep their fp32 rows.
     std::vector<int> good(n_regs, 0), bad(n_regs, 0);
     for (int i = 0; i < n_outputs; i++) bad[outputs[i]] = 1;
     for (const Op &o : p->ops) {
@@ -229,7 +229,9 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
       long K = 1;
       for (int d = 0; d < 3; d++) K *= o.kind == K_SUBM ? o.a[5 + d] : o.a[8 + d];
       const bool tc = Cout % 32 == 0 && Cout >= 32 && Cout <= 256 && K <= 63 && (Cin % 64 == 0 || (Cin == 32 && Cout <= 128));
-      if (o.kind != K_DECONV && tc) good[o.a[0]] = 1; else bad[o.a[0]] = 1;
+      // a deconvolution takes the tensor-core path when every fine site has exactly one parent: guaranteed by filter == stride
+      const bool deconvTc = o.kind == K_DECONV && Cin % 64 == 0 && o.a[8] == o.a[11] && o.a[9] == o.a[12] && o.a[10] == o.a[13];
+      if (tc && (o.kind != K_DECONV || deconvTc)) good[o.a[0]] = 1; else bad[o.a[0]] = 1;
       if (o.a[22] >= 0) bad[o.a[22]] = 1;
       if (o.a[18] >= 0) bad[o.a[18]] = 1; // whether a lateral is folded in (bf16 copy) or run on its own is decided at run time: keep the fp32 rows
     }
