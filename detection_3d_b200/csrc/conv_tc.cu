@@ -799,6 +799,12 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   int ctas = envCtas ? envCtas : 2;
   if (Cout > 128) ctas = 1;
   if (packG > 1) ctas = 2;
+  // Small levels (at most one tile per SM): nothing else runs beside them, so one CTA per SM with the whole shared memory as
+  // a deep ring (up to 6 stages) and 8 producer warps hides the gather latency of the serial offset loop far better than two
+  // half-sized CTAs that would mostly stay unused.
+  static int smallOne = -1;
+  if (smallOne < 0) smallOne = getenv("SCN_TC_SMALL_ONE") ? atoi(getenv("SCN_TC_SMALL_ONE")) : 1;
+  if (smallOne && !envCtas && packG == 1 && cdiv(nOut, kTileM) <= kSMs) ctas = 1;
   P.tmemCols = ctas == 2 ? 256 : 512;
   const size_t smemBudget = ctas == 2 ? ((233472 - kBuildRoom) / 2 - 1024) : (227 * 1024 - kBuildRoom);
   const int Tcap = std::min(packG == 4 ? 2 : kMaxT, P.tmemCols / Cout);
