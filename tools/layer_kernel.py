@@ -16,10 +16,12 @@ ap.add_argument("--cin", type=int, default=32)
 ap.add_argument("--cout", type=int, default=32)
 ap.add_argument("--f", type=int, default=3)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--nx", type=int, default=542)  # footprint of the synthetic building (smaller = a stand-in for the deep levels)
+ap.add_argument("--ny", type=int, default=542)
 a = ap.parse_args()
 scn.set_math_mode(a.math)
 L = torch.LongTensor
-coords = torch.from_numpy(synthetic.building_coords()).cuda()
+coords = torch.from_numpy(synthetic.building_coords(nx=a.nx, ny=a.ny)).cuda()
 md = scn.Metadata(3)
 x0 = torch.empty(0, device="cuda")
 scn.SCN.InputLayer_updateOutput(md, L([2048, 2048, 512]), coords, torch.zeros(coords.size(0), 1, device="cuda"), x0, 0, 4)
