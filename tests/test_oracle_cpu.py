@@ -210,3 +210,24 @@ class TestAgainstCompiledReference:
         np.testing.assert_allclose(din, din2.numpy(), rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(dw, dw2.numpy(), rtol=1e-4, atol=1e-4)
         np.testing.assert_allclose(db, db2.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_program_recorder_hoists_lateral_convolutions():
+    """Host logic of the recorded programs (sparseconvnet/program.py): a 1x1x1 SubmanifoldConvolution is moved right behind
+    the op that produces its input, everything else keeps its order (no GPU needed: pure list manipulation)."""
+    from detection_3d_b200.sparseconvnet import program
+    sz, f3, f1 = [64, 64, 32], [3, 3, 3], [1, 1, 1]
+    ops = [
+        (0, [0] + sz + [4, 0, 9], []),                       # input -> r0
+        (1, [0, 1] + sz + f3 + [0, -1, 9, 32], []),          # subm 3^3 r0 -> r1
+        (4, [1, 2, 32, 1, 2, -1, -1, 2], [1e-4, 0.9, 0.0]),  # bn r1 -> r2
+        (1, [2, 3] + sz + f3 + [3, -1, 32, 32], []),         # subm 3^3 r2 -> r3
+        (2, [3, 4] + sz + [32, 32, 16] + [2, 2, 2] + [2, 2, 2] + [4, -1, 32, 64], []),  # conv r3 -> r4
+        (1, [1, 5] + sz + f1 + [5, -1, 32, 128], []),        # lateral 1x1x1 on r1 -> r5 (recorded late)
+    ]
+    out = program._hoist_pointwise(ops)
+    assert len(out) == len(ops)
+    kinds = [(k, i[0], i[1]) for k, i, _ in out]
+    assert kinds[1] == (1, 0, 1) and kinds[2] == (1, 1, 5), kinds  # the lateral now follows its producer
+    rest = [o for o in out if o is not ops[5]]
+    assert rest == ops[:5]                                          # relative order of the others unchanged
