@@ -22,6 +22,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+WORKLOAD = ("sw_4c_fpn432 backbone forward incl. Metadata/rulebook build, one B470 synthetic building (1,155,656 active voxels) "
+            "per GPU per step")  # the same string in both arms (the reference arm's per-step sample is stated in cpu_baseline.sample)
+# end-to-end tolerance of each math mode against the reference's fp32 outputs (max |got - ref| / max(1, max|ref|) per returned
+# map; the same numbers tests/test_gpu_pins.py states): exact fp32 / tf32 operands / bf16 operands
+PARITY_TOL = {"fp32": 2e-3, "tf32": 3e-2, "bf16": 6e-2}
 B470_VOXELS = 1155656
 B470_GMAC = 334.126  # reference's own forward_pass_multiplyAdd_count for B470
 # dominant kernel: m_mergeds.7 = SubmanifoldConvolution 128->128, 3^3, on level 0 (10,715,792 rules)
@@ -77,19 +82,56 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_forward(coords, feats, cfg, state):
+def host_threads():
+    """All host cores this process may use; exported as OMP_NUM_THREADS unconditionally (torchrun sets it to 1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
+def cpu_reference_forward(coords, feats, cfg, state, keep=None):
     """One backbone forward on the host cores with the reference's own CPU code (oracle/_ref) when
-    it was built, else with our C port of it.  Returns (seconds, macs, kind, threads)."""
+    it was built, else with our C port of it.  Returns (seconds, macs, kind, threads); `keep`, a list,
+    receives the returned maps (dicts: features, locations, spatial_size) for the parity check."""
     import torch
     from oracle import fpn_oracle, ref_python
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    threads = host_threads()
+    torch.set_num_threads(threads)  # (torchrun exports OMP_NUM_THREADS=1; host_threads() has already overridden it)
     have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "SCN.so"))
     fn = fpn_oracle.run_fpn_ref if have_ref else fpn_oracle.run_fpn_port
     t0 = time.perf_counter()
-    _, _, macs = fn(cfg, state, coords, feats)
-    return time.perf_counter() - t0, macs, ("reference" if have_ref else "port"), threads
+    rpn, roi, macs = fn(cfg, state, coords, feats)
+    dt = time.perf_counter() - t0
+    if keep is not None:
+        keep[:] = rpn + roi
+    return dt, macs, ("reference" if have_ref else "port"), threads
+
+
+def config_of(n_gpus):
+    """`config` of the JSON line -- the same object in both arms."""
+    return {"workload": WORKLOAD, "l2": "256 MiB L2 flush between timed iterations (GPU arm)", "parallelism": f"replicas x{n_gpus}, no collective"}
+
+
+def parity_of(maps, ref_maps, tol):
+    """GPU step outputs (SparseConvNetTensors) against the reference's outputs of the same building (dicts from the
+    cpu_baseline leg): identical row coordinates, and per returned map max |got - ref| / max(1, max|ref|) and relative rms."""
+    import numpy as np
+    worst, worst_rms, same_rows, per_map = 0.0, 0.0, True, []
+    for m, r in zip(maps, ref_maps):
+        got = m.features.float().cpu().numpy()
+        ref = np.asarray(r["features"], dtype=np.float32)
+        loc_ok = bool(np.array_equal(m.get_spatial_locations().numpy(), np.asarray(r["locations"])))
+        same_rows = same_rows and loc_ok and got.shape == ref.shape
+        if got.shape != ref.shape:
+            per_map.append(None)
+            continue
+        err = float(np.abs(got - ref).max() / max(1.0, float(np.abs(ref).max()))) if ref.size else 0.0
+        rms = float(np.sqrt(((got - ref).astype(np.float64) ** 2).mean()) / max(1e-30, np.sqrt((ref.astype(np.float64) ** 2).mean()))) if ref.size else 0.0
+        worst, worst_rms = max(worst, err), max(worst_rms, rms)
+        per_map.append(round(err, 6))
+    return {"max_abs_over_max": worst, "rel_rms": worst_rms, "rows_identical": same_rows, "n_maps": len(ref_maps), "per_map": per_map,
+            "tolerance": tol, "ok": bool(same_rows and len(maps) == len(ref_maps) and worst <= tol),
+            "against": "reference CPU forward of the same full B470 building in this run (cpu_baseline leg)"}
 
 
 def make_model(cfg, device):
@@ -107,6 +149,7 @@ def run_reference_arm(args, rank, world):
     """--impl reference: the reference CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
+    host_threads()  # before torch / OpenMP start
     import numpy as np
     import fpn_util
     import detection_3d_b200.sparseconvnet.fpn as fpn
@@ -136,7 +179,7 @@ def run_reference_arm(args, rank, world):
     line = {
         "impl": "reference", "metric": "backbone_buildings_per_s", "value": value, "unit": "buildings/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": "sw_4c_fpn432 backbone forward incl. rulebook build, B470 synthetic building (bounded sample, see cpu_baseline.sample)"},
+        "data": "synthetic", "config": config_of(args.gpus),
         "cpu_baseline": {"value": value, "unit": "buildings/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "buildings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "tflops": 2 * macs / step / 1e12, "gpu_launches": 0,
@@ -147,12 +190,16 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 400 for our arm = a >= 2 s steady-state window, 3 for the reference arm)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default=os.environ.get("SCN_MATH", "auto"), choices=["auto", "fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained leg and the tf32 / fp32 sub-results")
+    ap.add_argument("--sustain-steps", type=int, default=400, help="steps of the steady-state leg (>= 2 s of back-to-back forwards)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 400 if args.impl == "ours" else 3
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -288,10 +335,27 @@ def main():
         net.__dict__.pop("_prefetched", None)
     ms_step = total_ms / args.steps
     value = world * 1e3 / ms_step
+    # steady state: >= 2 s of back-to-back forwards with the clocks sampled over that window (a burst of 20 forwards at the
+    # boost clock says little about a stream of buildings); when K itself is that long the headline IS the steady-state number
+    sustained = None
+    if not args.no_extras:
+        if args.steps >= args.sustain_steps:
+            sustained = {"steps": args.steps, "ms_per_step": ms_step, "value": value, "unit": "buildings/s", "seconds": total_ms / 1e3, "clocks": clocks,
+                         "note": "the headline window itself"}
+        else:
+            smp = ClockSampler(local)
+            smp.start()
+            sus_ms, _ = timed(step_resident, args.sustain_steps, 0)
+            sus_clocks = smp.stop()
+            sustained = {"steps": args.sustain_steps, "ms_per_step": sus_ms / args.sustain_steps, "value": world * 1e3 / (sus_ms / args.sustain_steps),
+                         "unit": "buildings/s", "seconds": sus_ms / 1e3, "clocks": sus_clocks,
+                         "note": "same step as the headline, timed over a longer window right after it"}
     d2h = 0
     with torch.no_grad():
         rpn, roi = net([coords_dev, feats_dev])
         d2h = sum(m.features.numel() * 4 for m in rpn + roi)
+        torch.cuda.synchronize()
+    headline_maps = rpn + roi  # outputs of the very code path that was timed (replayed program, this math mode)
 
     # roofline of the dominant kernel, timed alone on the launching stream
     pk = peaks()
@@ -302,9 +366,8 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[math], "data": "synthetic",
         "numerics": {"fp32": "exact fp32 CUDA cores", "tf32": "tf32 operands, fp32 accumulate; end-to-end <= 3e-2 of max|ref| (tests)",
-                     "bf16": "bf16 operands (tf32 where rows are < 64 channels), fp32 accumulate, fp32 feature tensors; end-to-end <= 6e-2 of max|ref| (tests), measured 2.3e-2"}[math],
-        "config": {"workload": "sw_4c_fpn432 backbone forward incl. Metadata/rulebook build, one B470 synthetic building (1,155,656 active voxels) per GPU per step",
-                   "l2": "256 MiB L2 flush between timed iterations", "parallelism": f"replicas x{world}, no collective"},
+                     "bf16": "bf16 operands, fp32 accumulate, fp32 feature tensors at the API; end-to-end <= 6e-2 of max|ref| (tests + `parity` of this run)"}[math],
+        "config": config_of(world), "sustained": sustained,
         "streaming": None if stream_ms is None else {
             "ms_per_step": stream_ms / args.steps, "value": world * 1e3 / (stream_ms / args.steps), "unit": "buildings/s",
             "note": "same forwards back to back with FPN_Net.prefetch building the Metadata two buildings ahead; L2 flush inside the timed region"},
@@ -313,17 +376,46 @@ def main():
         "e2e": {"value": world * 1e3 / (e2e_ms / args.steps), "unit": "buildings/s", "h2d_bytes_per_step": coords_np.nbytes + feats_np.nbytes, "d2h_bytes_per_step": d2h},
         "roofline": roof,
     }
+    parity_failed = False
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        nx = 271  # quarter-footprint crop keeps the CPU leg at ~10 s
-        cc = synthetic.building_coords(nx=nx, ny=nx, nz=68)
-        t, macs, kind, threads = cpu_reference_forward(cc, fpn_util.features_for(cc), cfg, state)
-        nv = np.unique(cc[:, :3], axis=0).shape[0]
-        line["cpu_baseline"] = {"value": (nv / B470_VOXELS) / t, "unit": "buildings/s", "cores": threads, "kind": kind,
-                                "sample": f"one forward of a {nx}x{nx}x68 crop of B470 ({nv} voxels = {nv / B470_VOXELS:.3f} building, {macs / 1e9:.1f} GMAC) in {t:.1f} s, scaled by voxel count"}
+        # the reference's CPU forward of the SAME full building (6-7 s on 16 cores): the CPU baseline number, and its outputs are
+        # what the GPU step's outputs are checked against, in every math mode measured
+        ref_maps = []
+        t, macs, kind, threads = cpu_reference_forward(coords_np, feats_np, cfg, state, keep=ref_maps)
+        line["cpu_baseline"] = {"value": 1.0 / t, "unit": "buildings/s", "cores": threads, "kind": kind,
+                                "sample": f"one forward of the full B470 building ({B470_VOXELS} voxels, {macs / 1e9:.1f} GMAC) in {t:.1f} s; outputs kept for `parity`"}
+        line["parity"] = parity_of(headline_maps, ref_maps, PARITY_TOL[math])
+        line["parity"]["macs_equal"] = bool(macs == macs_per_step)
+        parity_failed = not line["parity"]["ok"]
+        if not args.no_extras:  # the like-for-like precision modes, same building, same check
+            modes = {}
+            for other, k in (("tf32", 10), ("fp32", 3)):
+                if other == math or (other != "fp32" and not scn.SCN.lib().scn_tensor_core_path_available()):
+                    continue
+                try:
+                    scn.set_math_mode(other)
+                    net.reset_program()
+                    oms, _ = timed(step_resident, k, 3)
+                    with torch.no_grad():
+                        orpn, oroi = net([coords_dev, feats_dev])
+                        torch.cuda.synchronize()
+                    par = parity_of(orpn + oroi, ref_maps, PARITY_TOL[other])
+                    modes[other] = {"ms_per_step": oms / k, "value": 1e3 / (oms / k), "unit": "buildings/s", "steps": k,
+                                    "tflops": 1e3 / (oms / k) * 2 * macs_per_step / 1e12,
+                                    "parity": {q: par[q] for q in ("max_abs_over_max", "rel_rms", "rows_identical", "tolerance", "ok")}}
+                    parity_failed = parity_failed or not par["ok"]
+                except Exception as e:  # a sub-result must never cost the headline
+                    modes[other] = {"error": str(e)[:300]}
+            scn.set_math_mode(math)
+            net.reset_program()
+            line["modes"] = modes
     if rank == 0:
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if parity_failed:
+        sys.stderr.write("bench.py: PARITY FAILURE -- GPU outputs differ from the reference's beyond the stated tolerance: %s\n" % json.dumps(line.get("parity")))
+        sys.exit(3)
 
 
 def dominant_kernel_roofline(scn, torch, dev, coords_dev, flush, pk, math):

@@ -43,6 +43,8 @@ SYMBOLS = {
     "scn_input_layer_forward": (_i, [_vp, _vp, _vp, _i]),
     "scn_input_layer_forward_padded_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i]),
     "scn_input_layer_backward": (_i, [_vp, _vp, _vp, _i]),
+    "scn_output_layer_forward": (_i, [_vp, _vp, _vp, _i]),
+    "scn_output_layer_backward": (_i, [_vp, _vp, _vp, _i]),
     "scn_get_nactive": (_i, [_vp, L3, _pl]),
     "scn_get_spatial_locations": (_i, [_vp, L3, _vp, _i]),
     "scn_submanifold_prepare": (_i, [_vp, L3, L3, _pl]),
@@ -58,12 +60,18 @@ SYMBOLS = {
     "scn_deconvolution_backward": (_i, [_vp, L3, L3, L3, L3, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i]),
     "scn_batchnorm_forward": (_i, [_vp, _vp, _l, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _vp, _vp]),
     "scn_batchnorm_backward": (_i, [_vp, _vp, _vp, _vp, _l, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
+    "scn_network_in_network_forward": (_i, [_vp, _vp, _vp, _vp, _l, _i, _i, _pd, _vp, _vp, C.c_longlong]),
+    "scn_network_in_network_backward_input": (_i, [_vp, _vp, _vp, _l, _i, _i, _vp]),
+    "scn_network_in_network_backward_params": (_i, [_vp, _vp, _vp, _vp, _l, _i, _i, _vp]),
     "scn_add_features": (_i, [_vp, _vp, _vp, _l, _vp, _vp]),
     "scn_set_math_mode": (_i, [_i]),
     "scn_get_math_mode": (_i, []),
     "scn_tensor_core_path_available": (_i, []),
     "scn_kernel_launch_count": (_l, []),
     "scn_debug_counter": (_l, [_i]),
+    "scn_fuse_next_lateral": (_i, [_vp, _vp, _vp, C.c_longlong, _i, _l]),
+    "scn_fuse_next_stats": (_i, [_vp]),
+    "scn_fuse_result": (_i, [_pi, _pi]),
 }
 
 

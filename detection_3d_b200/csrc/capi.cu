@@ -13,6 +13,11 @@
 
 namespace scn {
 std::atomic<long> g_launches{0};
+std::atomic<long> g_counters[kCntCounters];
+void epilogue_stats_arm(double *sums);
+bool epilogue_stats_take();
+void lateral_arm(const float *in, const void *in16, const float *w, long long tag, int Cin, long rows);
+bool lateral_take();
 namespace {
 struct TlEv { const char *who; int kind; long a, b; double t; };
 std::vector<TlEv> g_tl;
@@ -60,6 +65,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
                         long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0);
 int to_bf16(const float *x, void *y, long n, cudaStream_t s);
+int dense_rows_dw(const float *in, const float *d_out, float *dW, float *d_bias, long n, int Cin, int Cout, cudaStream_t s);
 static int g_math_mode = 0;
 } // namespace scn
 
@@ -95,7 +101,26 @@ int scn_version(void) { return 1; }
 int scn_n_rulebook_bits(void) { return 32; }
 long scn_kernel_launch_count(void) { return scn::g_launches; }
 int scn_set_pool_growth(int on) { scn::set_pool_growth(on); return 0; }
-long scn_debug_counter(int which) { return which == 0 ? scn::debug_chunk_mallocs() : which == 1 ? scn::debug_chunk_waits() : scn::debug_chunk_total_mb(); }
+long scn_debug_counter(int which) {
+  if (which >= 3 && which < scn::kCntCounters) return scn::g_counters[which].load();
+  return which == 0 ? scn::debug_chunk_mallocs() : which == 1 ? scn::debug_chunk_waits() : scn::debug_chunk_total_mb();
+}
+int scn_fuse_next_lateral(const float *lat_in, const void *lat_in_bf16, const float *lat_weight, long long weight_tag, int n_in, long rows) {
+  SCN_CHECK(lat_in && lat_weight && n_in > 0 && rows >= 0, "lateral request");
+  scn::lateral_arm(lat_in, lat_in_bf16, lat_weight, weight_tag, n_in, rows);
+  return 0;
+}
+int scn_fuse_next_stats(double *sums) {
+  SCN_CHECK(sums, "statistics buffer");
+  scn::epilogue_stats_arm(sums);
+  return 0;
+}
+int scn_fuse_result(int *lateral_taken, int *stats_taken) {
+  const bool l = scn::lateral_take(), st = scn::epilogue_stats_take();
+  if (lateral_taken) *lateral_taken = l ? 1 : 0;
+  if (stats_taken) *stats_taken = st ? 1 : 0;
+  return 0;
+}
 int scn_set_math_mode(int mode) {
   if (mode < 0 || mode > 2) { scn::set_error("math mode must be 0 (fp32), 1 (tf32) or 2 (bf16)"); return -2; }
   scn::g_math_mode = mode;
@@ -319,6 +344,31 @@ int scn_input_layer_backward(scn_metadata *m, float *din, const float *dout, int
     return 0;
   }
   return scn::input_backward(din, dout, I.nIn, I.nOut, I.maxActive, C, I.tab, I.mode == 4, m->md.cstream);
+}
+
+// OutputLayer (CPU/IOLayers.cpp:97-140): the InputLayer's rule table run backwards WITHOUT averaging -- every input row receives
+// the feature row of its voxel; its gradient sums the rows of a voxel.
+int scn_output_layer_forward(scn_metadata *m, const float *in, float *out, int C) {
+  M_OR_FAIL(m);
+  auto &I = m->md.input;
+  SCN_CHECK(I.valid, "input layer not built");
+  SCN_TRY(m->md.wait_ready(I.rdy));
+  if (I.mode == 0) {
+    SCN_CUDA(cudaMemcpyAsync(out, in, (size_t)I.nOut * C * 4, cudaMemcpyDeviceToDevice, m->md.cstream));
+    return 0;
+  }
+  return scn::input_backward(out, in, I.nIn, I.nOut, I.maxActive, C, I.tab, /*average=*/0, m->md.cstream);
+}
+int scn_output_layer_backward(scn_metadata *m, float *d_in, const float *d_out, int C) {
+  M_OR_FAIL(m);
+  auto &I = m->md.input;
+  SCN_CHECK(I.valid, "input layer not built");
+  SCN_TRY(m->md.wait_ready(I.rdy));
+  if (I.mode == 0) {
+    SCN_CUDA(cudaMemcpyAsync(d_in, d_out, (size_t)I.nOut * C * 4, cudaMemcpyDeviceToDevice, m->md.cstream));
+    return 0;
+  }
+  return scn::input_forward(d_out, d_in, I.nOut, I.maxActive, C, I.tab, /*average=*/0, m->md.cstream);
 }
 
 // ---- internal row numbering (program replay): see Metadata::spatialIds
@@ -608,6 +658,36 @@ int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long ou
   return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, gc->n, gf->n, Cin, Cout, 1, m->md.cstream, tcIn, scn::g_math_mode);
 }
 
+// ---- NetworkInNetwork: a 1x1 "convolution" = dense GEMM over the feature rows, no Metadata involved
+static int dense_rows_gemm(const float *in, float *out, const float *w, const float *bias, long n, int Cin, int Cout, cudaStream_t s, const void *in16, long long tag) {
+  if (n == 0) return 0;
+  SCN_CHECK(n < (1l << 31) - 256, "too many rows");
+  if (tc_ok(Cin, Cout, 1)) // the tensor-core gather-GEMM with the identity plan (site p reads row p, writes row p)
+    return scn::launch_conv_plan_tc(in, out, w, nullptr, nullptr, nullptr, (int)n, 1, Cin, Cout, bias, scn::g_math_mode, s, nullptr, 1, n, in16, tag, nullptr, nullptr, n);
+  return scn::launch_conv_plan_simt(in, out, w, nullptr, nullptr, (int)n, 1, Cin, Cout, bias, s);
+}
+int scn_network_in_network_forward(const float *in, float *out, const float *weight, const float *bias, long n_rows, int n_in, int n_out, double *macs,
+                                   void *stream, const void *in_bf16, long long weight_tag) {
+  SCN_CHECK(n_rows >= 0 && n_in > 0 && n_out > 0 && (n_rows == 0 || (in && out && weight)), "NetworkInNetwork arguments");
+  if (macs) *macs = (double)n_rows * n_in * n_out; // CPU/NetworkInNetwork.cpp:23
+  return dense_rows_gemm(in, out, weight, bias, n_rows, n_in, n_out, static_cast<cudaStream_t>(stream), in_bf16, weight_tag);
+}
+int scn_network_in_network_backward_input(float *d_in, const float *d_out, const float *weight, long n_rows, int n_in, int n_out, void *stream) {
+  SCN_CHECK(n_rows >= 0 && n_in > 0 && n_out > 0, "NetworkInNetwork arguments");
+  if (n_rows == 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float *Wt = nullptr;
+  SCN_CUDA(cudaMallocAsync((void **)&Wt, (size_t)n_in * n_out * 4, s));
+  int r = scn::transpose_weights(weight, Wt, 1, n_in, n_out, 0, s);
+  if (r == 0) r = dense_rows_gemm(d_out, d_in, Wt, nullptr, n_rows, n_out, n_in, s, nullptr, 0);
+  cudaFreeAsync(Wt, s);
+  return r;
+}
+int scn_network_in_network_backward_params(const float *in, const float *d_out, float *d_weight, float *d_bias, long n_rows, int n_in, int n_out, void *stream) {
+  SCN_CHECK(n_rows >= 0 && n_in > 0 && n_out > 0 && d_weight, "NetworkInNetwork arguments");
+  return scn::dense_rows_dw(in, d_out, d_weight, d_bias, n_rows, n_in, n_out, static_cast<cudaStream_t>(stream));
+}
+
 int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *save_mean, float *save_invstd, float *running_mean,
                           float *running_var, const float *weight, const float *bias, float eps, float momentum, int mode, float leak,
                           void *stream, void *out_bf16) {
@@ -616,17 +696,19 @@ int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *sav
   // persistent, zero-initialised workspace per stream (calls on one stream are ordered; the
   // finalize kernel re-zeroes the statistics): no allocation, no memset per call
   static std::mutex mu;
-  static std::vector<std::pair<cudaStream_t, void *>> cache;
+  static std::vector<std::pair<std::pair<int, cudaStream_t>, void *>> cache; // keyed by (device, stream): stream handle 0 means "default" on every device
   constexpr int kMaxC = scn::kBnMaxC;
   SCN_CHECK(C <= kMaxC, "BatchNorm: too many channels");
   void *ws = nullptr;
   {
+    int dev = 0;
+    SCN_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(mu);
-    for (auto &e : cache) if (e.first == s) ws = e.second;
+    for (auto &e : cache) if (e.first.first == dev && e.first.second == s) ws = e.second;
     if (!ws) {
       SCN_CUDA(cudaMalloc(&ws, scn::kBnWorkspaceBytes));
       SCN_CUDA(cudaMemset(ws, 0, scn::kBnWorkspaceBytes));
-      cache.emplace_back(s, ws);
+      cache.emplace_back(std::make_pair(dev, s), ws);
     }
   }
   return scn::bn_forward(in, out, n, C, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, mode, leak, ws, s, out_bf16);

@@ -42,6 +42,20 @@ void timeline_dump();
 // every kernel launch of this library passes its stream through LS(): launch accounting
 extern std::atomic<long> g_launches;
 static inline cudaStream_t LS(cudaStream_t s) { ++g_launches; return s; }
+// which-fusion-was-taken counters (scn_debug_counter(3..)): the parity tests assert on them that the benchmarked code path
+// -- lateral stage, epilogue statistics, bf16-only outputs -- really ran, instead of a silent fallback
+enum DebugCounter {
+  kCntLateralFolded = 3,   // tensor-core launches that carried a lateral 1x1x1 stage (in2 / wimg2)
+  kCntEpilogueStats = 4,   // tensor-core launches whose epilogue accumulated BatchNorm statistics
+  kCntHalfOnlyOut = 5,     // program registers that were written as bf16 only (no fp32 rows)
+  kCntLateralFallback = 6, // laterals the program executor had to run as a separate 1x1x1 convolution + add
+  kCntTcLaunch = 7,        // conv_plan_tc launches
+  kCntBnFromSums = 8,      // BatchNorm ops that ran their apply pass from epilogue statistics
+  kCntSplitLaunch = 9,     // conv_plan_tc launches that split the filter offsets over CTAs (atomic epilogue)
+  kCntSimtLaunch = 10,     // CUDA-core convolution launches (plan or list)
+  kCntCounters = 16
+};
+extern std::atomic<long> g_counters[kCntCounters];
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

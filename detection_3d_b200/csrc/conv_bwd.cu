@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_dw(const float *__restrict__ in, const 
     __syncthreads();
     if (tid < BK) {
       int2 pr = make_int2(-1, -1);
-      if (ib + tid < i1) pr = __ldg(pairs + start + ib + tid);
+      if (ib + tid < i1) pr = pairs ? __ldg(pairs + start + ib + tid) : make_int2(start + ib + tid, start + ib + tid); // no list: dense rows
       s_src[tid] = srcIsY ? pr.y : pr.x;
       s_dst[tid] = srcIsY ? pr.x : pr.y;
     }
@@ -93,6 +93,23 @@ __global__ void k_colsum(const float *__restrict__ x, long n, int C, float *__re
   float s = 0.f;
   for (long r = blockIdx.x; r < n; r += gridDim.x) s += x[r * C + c];
   atomicAdd(out + c, s);
+}
+
+// NetworkInNetwork_accGradParameters (SCN/CPU/NetworkInNetwork.cpp:36-46): dW = in^T @ d_out over dense rows (row i pairs with row i),
+// d_bias = column sums of d_out.  Both overwritten.
+int dense_rows_dw(const float *in, const float *d_out, float *dW, float *d_bias, long n, int Cin, int Cout, cudaStream_t s) {
+  SCN_CUDA(cudaMemsetAsync(dW, 0, (size_t)Cin * Cout * 4, s));
+  if (d_bias) {
+    SCN_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)Cout * 4, s));
+    if (n) k_colsum<<<dim3(kSMs * 2, cdiv(Cout, 128)), 128, 0, LS(s)>>>(d_out, n, Cout, d_bias);
+  }
+  if (n == 0) return 0;
+  int chunk = std::max(256, cdiv(n, kSMs * 4));
+  chunk = (chunk + BK - 1) / BK * BK;
+  dim3 grid(cdiv(n, chunk), cdiv(Cin, BM), cdiv(Cout, BN));
+  k_dw<<<grid, 256, 0, LS(s)>>>(in, d_out, dW, nullptr, 0, (int)n, chunk, Cin, Cout, 0);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // skipDIn: the caller computes d_in itself (tensor-core forward kernel on (d_out, W^T)); only dW / d_bias here

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) conv_plan_simt(const float *__restrict__ 
     for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
   for (int k = 0; k < K; k++) {
     int id = -1;
-    if (tid < TM && p0 + tid < nOut) id = __ldg(nbr + nbr_index(p0 + tid, k, K));
+    if (tid < TM && p0 + tid < nOut) id = nbr ? __ldg(nbr + nbr_index(p0 + tid, k, K)) : p0 + tid; // no plan: dense rows (NetworkInNetwork)
     __syncthreads(); // previous offset's readers of s_ids / tiles are done
     if (tid < TM) s_ids[tid] = id;
     if (!__syncthreads_or(id >= 0)) continue;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) conv_plan_simt(const float *__restrict__ 
   for (int i = 0; i < 4; i++) {
     int p = p0 + ty * 4 + i;
     if (p >= nOut) continue;
-    float *dst = out + (long)__ldg(outRow + p) * Cout + n0 + tx * 4;
+    float *dst = out + (long)(outRow ? __ldg(outRow + p) : p) * Cout + n0 + tx * 4;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       int c = n0 + tx * 4 + j;
@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) conv_list_simt(const float *__restrict__ 
 int launch_conv_plan_simt(const float *in, float *out, const float *W, const int *nbr, const int *outRow, int nOut, int K, int Cin, int Cout,
                           const float *bias, cudaStream_t s) {
   if (nOut == 0) return 0;
+  ++g_counters[kCntSimtLaunch];
   dim3 grid(cdiv(nOut, TM), cdiv(Cout, TN));
   if (Cin % 4 == 0 && Cout % 4 == 0)
     conv_plan_simt<true><<<grid, 256, 0, LS(s)>>>(in, out, W, nbr, outRow, nOut, K, Cin, Cout, bias);
@@ -176,6 +177,7 @@ int launch_conv_plan_simt(const float *in, float *out, const float *W, const int
 int launch_conv_list_simt(const float *in, float *out, const float *W, const int2 *pairs, const int *d_off, const int *offHost, int K, int Cin,
                           int Cout, int srcIsY, int singlePass, cudaStream_t s) {
   const bool vec = Cin % 4 == 0 && Cout % 4 == 0;
+  ++g_counters[kCntSimtLaunch];
   if (singlePass) {
     long tiles = 0;
     for (int L = 0; L < K; L++) tiles += cdiv(offHost[L + 1] - offHost[L], TM);

@@ -201,7 +201,8 @@ __device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
 #pragma unroll
   for (int t = 0; t < kMaxT; t++) {
     const int tile = I.st * P.T + t;
-    I.m[t] = (t < P.T && tile < P.nTiles) ? (group_mask<G>(__ldg(P.tileMask + tile)) & kmask) : 0ull;
+    // (no plan = dense rows, NetworkInNetwork: the one "filter offset" is live everywhere)
+    I.m[t] = (t < P.T && tile < P.nTiles) ? (group_mask<G>(P.tileMask ? __ldg(P.tileMask + tile) : 1ull) & kmask) : 0ull;
     if (G == 1 && P.in2 && I.part == 0 && t < P.T && tile < P.nTiles) I.m[t] |= 1ull << kLateralBit;
     I.uni |= I.m[t];
   }
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 32
 #pragma unroll
       for (int t = 0; t < kMaxT; t++) {
         const long p = (long)(I.st * P.T + t) * kTileM + warp * 32 + lane;
-        myRow[t] = (t < P.T && p < P.nOut) ? __ldg(P.outRow + p) : -1;
+        myRow[t] = (t < P.T && p < P.nOut) ? (P.outRow ? __ldg(P.outRow + p) : (int)p) : -1;
       }
       mbar_wait_t(smem_u32(accFull + a), use & 1, pw0, prof);
       tc_fence_after();
@@ -394,7 +395,10 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 32
           for (int t = 0; t < TM; t++) {
             if (G == 1 && k == kLateralBit) { // lateral stage: the input row of an output site is its own output row
               const long p = (long)(I.st * P.T + t) * kTileM + pw * kRowsPerWarp + (lane & (kRowsPerWarp - 1));
-              dst[g][t] = (((I.m[t] >> k) & 1ull) && p < P.nOut) ? __ldg(P.outRow + p) : -1;
+              dst[g][t] = (((I.m[t] >> k) & 1ull) && p < P.nOut) ? (P.outRow ? __ldg(P.outRow + p) : (int)p) : -1;
+            } else if (!P.nbr) { // dense rows: site p reads row p
+              const long p = (long)(I.st * P.T + t) * kTileM + pw * kRowsPerWarp + (lane & (kRowsPerWarp - 1));
+              dst[g][t] = (((I.m[t] >> k) & 1ull) && g == 0 && p < P.nOut) ? (int)p : -1;
             } else {
               dst[g][t] = (((I.m[t] >> k) & 1ull) && k + g < P.K) ? __ldg(idBase + ((size_t)t * P.K + k + g) * 128) : -1;
             }
@@ -600,9 +604,9 @@ __global__ void k_prep_wimg_packed(const float *__restrict__ W, unsigned char *_
 // type) -> image.  The tag is how the caller says "same contents as last time" (the Python layer
 // passes a per-Parameter token combined with the tensor's in-place version counter); tag 0 = no caching.
 struct WimgKey {
-  const void *w; long long tag; int K, Cin, CinW, Cout, bf16;
+  const void *w; long long tag; int K, Cin, CinW, Cout, bf16, dev;
   bool operator<(const WimgKey &o) const {
-    return std::tie(w, tag, K, Cin, CinW, Cout, bf16) < std::tie(o.w, o.tag, o.K, o.Cin, o.CinW, o.Cout, o.bf16);
+    return std::tie(w, tag, K, Cin, CinW, Cout, bf16, dev) < std::tie(o.w, o.tag, o.K, o.Cin, o.CinW, o.Cout, o.bf16, o.dev);
   }
 };
 struct WimgVal { unsigned char *img; size_t bytes; cudaEvent_t ready; cudaStream_t stream; unsigned long long lastUse; };
@@ -623,8 +627,10 @@ static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int
   const size_t bytes = packG > 1 ? (size_t)((K + packG - 1) / packG) * Cout * 128 : (size_t)K * Cin * Cout * (bf16 ? 2 : 4);
   *owned = false;
   if (tag != 0) {
+    int dev = 0;
+    SCN_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_wimg_mu);
-    WimgKey key{W, tag, K, Cin, CinW, Cout, bf16};
+    WimgKey key{W, tag, K, Cin, CinW, Cout, bf16, dev};
     auto it = g_wimg.find(key);
     if (it != g_wimg.end()) {
       it->second.lastUse = ++g_wimg_clock;
@@ -634,7 +640,7 @@ static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int
     }
     // stale versions of the same weight tensor, then least-recently-used entries beyond the budget
     for (auto j = g_wimg.begin(); j != g_wimg.end();) {
-      if (j->first.w == W && j->first.tag != tag) { cudaFree(j->second.img); cudaEventDestroy(j->second.ready); g_wimg_bytes -= j->second.bytes; j = g_wimg.erase(j); }
+      if (j->first.w == W && j->first.dev == dev && j->first.tag != tag) { cudaFree(j->second.img); cudaEventDestroy(j->second.ready); g_wimg_bytes -= j->second.bytes; j = g_wimg.erase(j); }
       else ++j;
     }
     while (g_wimg_bytes + bytes > kWimgBudget && !g_wimg.empty()) {
@@ -699,14 +705,18 @@ int to_bf16(const float *x, void *y, long n, cudaStream_t s) {
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
-// Grow-only scratch per stream for the operand copies a call may need (zero-padded rows of a narrow
-// input, bf16 copy of an input that arrived without one).  Uses on one stream are ordered, so one
-// buffer per stream suffices; cudaMallocAsync took milliseconds for these 150-300 MB blocks.
-static int stream_scratch(cudaStream_t s, size_t bytes, void **out) {
+// Grow-only scratch per (device, stream, slot) for the operand copies a call may need (slot 0: zero-padded rows of a
+// narrow input; slot 1: bf16 copy of an input that arrived without one -- one launch can need both, the second derived
+// from the first, so they must not share a buffer; slot 2: the operand pair of the weight-gradient kernel).  Uses of a
+// slot on one stream are ordered; cudaMallocAsync took milliseconds for these 150-300 MB blocks.
+enum ScratchSlot { kScratchPad = 0, kScratchBf16 = 1, kScratchDw = 2 };
+static int stream_scratch(cudaStream_t s, int slot, size_t bytes, void **out) {
   static std::mutex mu;
-  static std::map<cudaStream_t, std::pair<void *, size_t>> cache;
+  static std::map<std::tuple<int, cudaStream_t, int>, std::pair<void *, size_t>> cache;
+  int dev = 0;
+  SCN_CUDA(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(mu);
-  auto &e = cache[s];
+  auto &e = cache[std::make_tuple(dev, s, slot)];
   if (e.second < bytes) {
     if (e.first) { SCN_CUDA(cudaStreamSynchronize(s)); SCN_CUDA(cudaFree(e.first)); }
     e.second = bytes + bytes / 8 + (1u << 20);
@@ -749,7 +759,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     if (tl_prepad && tl_prepad_c == Cp) {
       xp = const_cast<__nv_bfloat16 *>(static_cast<const __nv_bfloat16 *>(tl_prepad)); // the producer already wrote the padded copy
     } else {
-      SCN_TRY(stream_scratch(s, (size_t)nInRows * Cp * 2 + 16, (void **)&xp));
+      SCN_TRY(stream_scratch(s, kScratchBf16, (size_t)nInRows * Cp * 2 + 16, (void **)&xp));
       k_pad_rows_bf16<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
     }
     tl_prepad = nullptr;
@@ -758,7 +768,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (Cin % 32 != 0 && !(canPack && Cin == 16)) { // rows zero-padded to a multiple of 32 channels (the weight image pads itself)
     const int Cp = (Cin + 31) / 32 * 32;
     float *xp = nullptr;
-    SCN_TRY(stream_scratch(s, (size_t)nInRows * Cp * 4 + 16, (void **)&xp));
+    SCN_TRY(stream_scratch(s, kScratchPad, (size_t)nInRows * Cp * 4 + 16, (void **)&xp));
     k_pad_rows<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
     return launch_conv_plan_tc(xp, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr, wTag, addend, out16, nOutRows, Cin);
   }
@@ -781,7 +791,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   void *tmp16 = nullptr;
   if (P.bf16) {
     if (!in16) {
-      SCN_TRY(stream_scratch(s, (size_t)nInRows * Cin * 2 + 16, &tmp16));
+      SCN_TRY(stream_scratch(s, kScratchBf16, (size_t)nInRows * Cin * 2 + 16, &tmp16));
       if (nInRows) k_to_bf16<<<stream_grid(nInRows * Cin / 4, 256), 256, 0, LS(s)>>>(in, static_cast<uint2 *>(tmp16), nInRows * Cin / 4);
       in16 = tmp16;
     }
@@ -827,7 +837,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (kSplitMaxItems < 0) kSplitMaxItems = getenv("SCN_TC_SPLIT_MAX") ? atoi(getenv("SCN_TC_SPLIT_MAX")) : 24;
   if (P.nSuper <= kSplitMaxItems && !tileW) P.kSplit = std::max(1, std::min(packG > 1 ? P.KG : K, kSMs * ctas / P.nSuper));
   P.stats = nullptr;
-  if (tl_stats && P.kSplit == 1 && Cout <= kFusedStatsC && Cout % 32 == 0) { P.stats = tl_stats; tl_stats_done = true; }
+  if (tl_stats && P.kSplit == 1 && Cout <= kFusedStatsC && Cout % 32 == 0) { P.stats = tl_stats; tl_stats_done = true; ++g_counters[kCntEpilogueStats]; }
   tl_stats = nullptr;
   const size_t stageBytes = (size_t)P.T * kAtomBytes + (size_t)Cout * 128;
   P.S = (int)std::min<size_t>(envS > 0 ? envS : 6, (smemBudget - fixed) / stageBytes);
@@ -838,6 +848,8 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (P.lag > P.S - 2) P.lag = std::max(0, P.S - 2);
   const size_t smem = (size_t)P.S * stageBytes + fixed;
   SCN_CHECK(out || (P.kSplit == 1 && out16), "tcgen05 path: fp32 output dropped on a launch that needs it");
+  ++g_counters[kCntTcLaunch];
+  if (P.kSplit > 1) ++g_counters[kCntSplitLaunch];
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
   unsigned char *wimg = nullptr;
   bool wimgOwned = false;
@@ -856,6 +868,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
       P.nAtoms2 = C2p / per;
       P.wimg2 = wimg2;
       tl_lat_done = true;
+      ++g_counters[kCntLateralFolded];
     }
   }
   tl_lat.in = nullptr;
@@ -1079,7 +1092,7 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
   if (bf16) { // operand copies of both row matrices, side by side in the stream's scratch buffer
     unsigned char *scr = nullptr;
     const size_t na = ((size_t)nInRows * CinP * 2 + 255) & ~(size_t)255;
-    SCN_TRY(stream_scratch(s, na + (size_t)nOutRows * Cout * 2 + 16, (void **)&scr));
+    SCN_TRY(stream_scratch(s, kScratchDw, na + (size_t)nOutRows * Cout * 2 + 16, (void **)&scr));
     if (CinP == Cin) SCN_TRY(to_bf16(in, scr, nInRows * Cin, s));
     else if (nInRows) k_pad_rows_bf16<<<stream_grid(nInRows * CinP, 256), 256, 0, LS(s)>>>(in, reinterpret_cast<__nv_bfloat16 *>(scr), nInRows, Cin, CinP);
     SCN_TRY(to_bf16(d_out, scr + na, nOutRows * Cout, s));

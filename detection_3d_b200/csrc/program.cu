@@ -397,6 +397,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     R.cols = cols;
     R.pad16 = 0;
     R.p = halfOnly ? nullptr : static_cast<float *>(slot_get(p, (size_t)std::max(1l, rows * cols) * 4));
+    if (halfOnly) ++scn::g_counters[scn::kCntHalfOnlyOut];
     if (!R.p && !halfOnly) return -1;
     if (shadow && mode == 2 && cols % 32 == 0 && rows > 0) {
       R.p16 = slot_get(p, (size_t)rows * cols * 2);
@@ -426,6 +427,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     const Reg &Y = p->regs[op.a[18]];
     macs += (double)Y.rows * (double)op.a[20] * Cout;
     if (done || out.rows == 0) return 0;
+    ++scn::g_counters[scn::kCntLateralFallback];
     if (!out.p) { scn::set_error("program: lateral not folded in although the fp32 output was dropped"); return -2; }
     float *tmp = static_cast<float *>(slot_get(p, (size_t)out.rows * Cout * 4));
     if (!tmp) return -1;
@@ -514,6 +516,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
         const bool halfOnly = fromSums && a[19] == 1 && mode == 2 && scn_tensor_core_path_available();
         rc = alloc_reg(a[1], I.rows, (int)a[2], true, halfOnly);
         if (rc == 0 && fromSums) {
+          ++scn::g_counters[scn::kCntBnFromSums];
           rc = scn::bn_forward_from_sums(I.p, p->regs[a[1]].p, I.rows, (int)a[2], p->stats + a[21] * statsStride, p->bnScratch, p->bnScratch + scn::kBnMaxC,
                                          const_cast<float *>(P(a[5])), const_cast<float *>(P(a[6])), P(a[3]), P(a[4]), (float)op.f[0], (float)op.f[1], (int)a[7],
                                          (float)op.f[2], s, p->regs[a[1]].p16);
@@ -541,7 +544,13 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
         if (R.p16) { slot_put(p, R.p16); R.p16 = nullptr; }
       }
   }
-  if (rc) { release_regs(p, true); return rc; }
+  if (rc) { // no fusion request may stay armed for the next convolution this thread makes
+    scn::lateral_take();
+    scn::epilogue_stats_take();
+    scn::prepadded_disarm();
+    release_regs(p, true);
+    return rc;
+  }
   if (macs_out) *macs_out = macs;
   if (p->internal) SCN_TRY(scn_metadata_wait_jobs(m)); // the reference-numbered grids of the outputs
   cudaEvent_t &ev = p->evEnd[p->nRuns & 1];

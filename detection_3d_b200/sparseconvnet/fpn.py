@@ -20,16 +20,7 @@ from .tensor import SparseConvNetTensor
 _PROGRAMS = os.environ.get("SCN_PROGRAM", "1") != "0"  # developer switch: always run layer by layer
 
 
-class OutputLayer(nn.Module):
-    """Parameter-free inverse of InputLayer (reference: sparseconvnet/ioLayers.py:68-90).  FPN_Net holds
-    one in `layers_out` but never calls it; it exists so the module tree matches."""
-
-    def __init__(self, dimension):
-        nn.Module.__init__(self)
-        self.dimension = dimension
-
-    def forward(self, input):
-        raise NotImplementedError("OutputLayer is not on the Detection_3D backbone path")
+OutputLayer = L.OutputLayer  # (FPN_Net holds one in `layers_out`; the shipped forward never calls it)
 
 
 _ELEMENT_CHANNELS = {'xyz': 3, 'color': 3, 'normal': 3}
@@ -176,6 +167,34 @@ class FPN_Net(nn.Module):
         """Forget the recorded program (call after changing the module tree)."""
         self.__dict__.pop("_program", None)
         self.__dict__.pop("_program_error", None)
+        self.__dict__.pop("_prefetched", None)
+
+    # The recorded program and the Metadata objects built ahead are handles into the native library (ctypes pointers):
+    # a copy / pickle of the network (EMA copies, torch.save(model), as with the reference) drops them and records again.
+    _RUNTIME_STATE = ("_program", "_program_error", "_program_n_rpn", "_prefetched")
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in self._RUNTIME_STATE:
+            state.pop(k, None)
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k not in self._RUNTIME_STATE:
+                new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
+    def load_state_dict(self, *args, **kwargs):
+        # loaders write through `.data` / copy_ on detached views, which does not always bump Tensor._version: the packed
+        # weight images (keyed by token + version) are dropped explicitly
+        out = nn.Module.load_state_dict(self, *args, **kwargs)
+        native.invalidate_weight_cache(self)
+        return out
 
     def _run_program(self, prog, coords, feats):
         import detection_3d_b200.sparseconvnet as pkg

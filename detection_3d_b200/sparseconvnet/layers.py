@@ -111,6 +111,33 @@ class InputLayerFunction(Function):
         return None, None, None, None, grad_input, None, None
 
 
+class OutputLayer(Module):
+    """Parameter-free inverse of InputLayer: SparseConvNetTensor -> float [N input rows, planes], every input row receives
+    the feature row of its voxel.  reference: sparseconvnet/ioLayers.py:68-90,198-223."""
+
+    def __init__(self, dimension):
+        Module.__init__(self)
+        self.dimension = dimension
+
+    def forward(self, input):
+        return _run(OutputLayerFunction, self.dimension, input.metadata, input.features)
+
+
+class OutputLayerFunction(Function):
+    @staticmethod
+    def forward(ctx, dimension, metadata, input_features):
+        out = input_features.new()
+        ctx.metadata_ = metadata
+        native.OutputLayer_updateOutput(metadata, input_features.contiguous(), out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        grad_input = grad_output.new()
+        native.OutputLayer_updateGradInput(ctx.metadata_, grad_input, grad_output.contiguous())
+        return None, None, grad_input
+
+
 # ------------------------------------------------------------------------------- convolutions
 class SubmanifoldConvolution(Module):
     """reference: sparseconvnet/submanifoldConvolution.py:14-59"""
@@ -362,9 +389,34 @@ class BatchNormalizationFunction(Function):
         return grad_input, optionalTensorReturn(grad_weight), optionalTensorReturn(grad_bias), None, None, None, None, None, None, None
 
 
+class NetworkInNetworkFunction(Function):
+    """reference: sparseconvnet/networkInNetwork.py:14-56"""
+
+    @staticmethod
+    def forward(ctx, input_features, weight, bias):
+        out = input_features.new()
+        x = input_features.contiguous()
+        ctx.save_for_backward(x, weight, bias)
+        pkg = _counters()
+        pkg.forward_pass_multiplyAdd_count += native.NetworkInNetwork_updateOutput(x, out, weight, bias)
+        pkg.forward_pass_hidden_states += out.nelement()
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, weight, bias = ctx.saved_tensors
+        g = grad_output.contiguous()
+        grad_input = grad_output.new()
+        grad_weight = torch.zeros_like(weight)
+        grad_bias = torch.zeros_like(bias)
+        native.NetworkInNetwork_updateGradInput(grad_input, g, weight)
+        native.NetworkInNetwork_accGradParameters(x, g, grad_weight, grad_bias)
+        return grad_input, grad_weight, optionalTensorReturn(grad_bias)
+
+
 class NetworkInNetwork(Module):
-    """1x1 'convolution' on feature rows (reference: sparseconvnet/networkInNetwork.py); only built by
-    FPN_Net when a residual block changes width, which no shipped config does."""
+    """1x1 'convolution' on feature rows (reference: sparseconvnet/networkInNetwork.py:59-92; SCN/CPU/NetworkInNetwork.cpp:7-46);
+    built by FPN_Net when a residual block changes width (fpn_net.py:63)."""
 
     def __init__(self, nIn, nOut, bias):
         Module.__init__(self)
@@ -375,7 +427,13 @@ class NetworkInNetwork(Module):
             self.bias = Parameter(torch.Tensor(nOut).zero_())
 
     def forward(self, input):
-        raise NotImplementedError("NetworkInNetwork is outside the Detection_3D backbone hot path (never instantiated by shipped configs)")
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nIn, (self.nIn, input.features.shape)
+        out = SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size)
+        out.features = _run(NetworkInNetworkFunction, input.features, self.weight, optionalTensor(self, 'bias'))
+        return out
+
+    def __repr__(self):
+        return 'NetworkInNetwork' + str(self.nIn) + '->' + str(self.nOut)
 
     def input_spatial_size(self, out_size):
         return out_size

@@ -68,13 +68,35 @@ def _weight_tag(w):
     """Identifies the contents of a weight tensor for the native operand-image cache: a token that
     is unique per tensor OBJECT (ids and addresses get reused) combined with the in-place version."""
     tok = getattr(w, "_scn_token", None)
-    if tok is None:
-        tok = next(_TOKENS)
+    if tok is None or tok[1] != _EPOCH:
+        tok = (next(_TOKENS), _EPOCH)
         try:
             w._scn_token = tok
         except Exception:
             return 0
-    return (tok << 24) + (w._version & 0xFFFFFF) + 1
+    return (tok[0] << 24) + (w._version & 0xFFFFFF) + 1
+
+
+def invalidate_weight_cache(module_or_tensor=None):
+    """The packed weight images and bf16 copies are keyed by (per-tensor token, Tensor._version).  Writes through `.data`
+    (older optimizers, EMA / checkpoint code: `p.data.copy_(...)`) do NOT bump `_version`; call this after such a write --
+    with a module, a tensor, or nothing (= every tensor gets a new token on its next use) -- so the next convolution
+    rebuilds its operand image.  `load_state_dict` of FPN_Net calls it."""
+    global _EPOCH
+    if module_or_tensor is None:
+        _EPOCH += 1
+        return
+    ts = [module_or_tensor] if isinstance(module_or_tensor, torch.Tensor) else list(module_or_tensor.parameters()) + list(module_or_tensor.buffers())
+    for t in ts:
+        for attr in ("_scn_token", "_scn_bf16"):
+            if hasattr(t, attr):
+                try:
+                    delattr(t, attr)
+                except Exception:
+                    pass
+
+
+_EPOCH = 0
 
 
 def _shadow_ptr(t):
@@ -201,6 +223,24 @@ def InputLayer_updateGradInput(m, d_input_features, d_output_features):
         check(lib().scn_input_layer_backward(m._h, _dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"), planes))
 
 
+def OutputLayer_updateOutput(m, input_features, output_features):
+    """pybind.cpp:163-166"""
+    hdr = m.inputLayerRuleBook()[0]
+    mode, n_in, n_out, planes = int(hdr[0]), int(hdr[2]), int(hdr[3]), input_features.size(1)
+    output_features.resize_(n_out if mode == 0 else n_in, planes)
+    if output_features.numel():
+        check(lib().scn_output_layer_forward(m._h, _dev_f32(input_features, "in"), _dev_f32(output_features, "out"), planes))
+
+
+def OutputLayer_updateGradInput(m, d_input_features, d_output_features):
+    """pybind.cpp:167-170"""
+    hdr = m.inputLayerRuleBook()[0]
+    n_out, planes = int(hdr[3]), d_output_features.size(1)
+    d_input_features.resize_(n_out, planes)
+    if d_input_features.numel():
+        check(lib().scn_output_layer_backward(m._h, _dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"), planes))
+
+
 # ------------------------------------------------------------------ convolutions
 def _w3(weight):
     # (K, groups=1, Cin, Cout)
@@ -322,6 +362,37 @@ def BatchNormalization_backward(input_features, d_input_features, output_feature
     check(lib().scn_batchnorm_backward(_dev_f32(input_features, "in"), _dev_f32(d_input_features, "d_in"), _dev_f32(output_features, "out"),
                                        _dev_f32(d_output_features, "d_out"), n, c, _dev_f32(saveMean, "saveMean"), _dev_f32(saveInvStd, "saveInvStd"),
                                        _opt(weight, "weight"), _opt(d_weight, "d_weight"), _opt(d_bias, "d_bias"), float(leakiness), _stream()))
+
+
+# ------------------------------------------------------------------ NetworkInNetwork
+def NetworkInNetwork_updateOutput(input_features, output_features, weight, bias):
+    """pybind.cpp:224-225 -> returns nActive * nIn * nOut like the reference"""
+    n, cin, cout = input_features.size(0), weight.size(0), weight.size(1)
+    output_features.resize_(n, cout)
+    macs = C.c_double()
+    check(lib().scn_network_in_network_forward(_dev_f32(input_features, "in") if n else None, _dev_f32(output_features, "out") if n else None,
+                                               _dev_f32(weight, "weight"), _opt(bias, "bias"), n, cin, cout, C.byref(macs), _stream(),
+                                               _shadow_ptr(input_features), _weight_tag(weight)))
+    tr = _tr()
+    if tr is not None:
+        tr.fail("NetworkInNetwork is not recorded")
+    return macs.value
+
+
+def NetworkInNetwork_updateGradInput(d_input_features, d_output_features, weight):
+    """pybind.cpp:226"""
+    n, cin, cout = d_output_features.size(0), weight.size(0), weight.size(1)
+    d_input_features.resize_(n, cin)
+    if n:
+        check(lib().scn_network_in_network_backward_input(_dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"),
+                                                          _dev_f32(weight, "weight"), n, cin, cout, _stream()))
+
+
+def NetworkInNetwork_accGradParameters(input_features, d_output_features, d_weight, d_bias):
+    """pybind.cpp:227-228"""
+    n, cin, cout = input_features.size(0), d_weight.size(0), d_weight.size(1)
+    check(lib().scn_network_in_network_backward_params(_dev_f32(input_features, "in") if n else None, _dev_f32(d_output_features, "d_out") if n else None,
+                                                       _dev_f32(d_weight, "d_weight"), _opt(d_bias, "d_bias"), n, cin, cout, _stream()))
 
 
 def add_features(a, b):

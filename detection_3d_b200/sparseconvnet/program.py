@@ -116,6 +116,7 @@ class Program(object):
             self.out_regs.append(r)
             self.out_sizes.append(size.clone())
         ops = _hoist_pointwise(trace.ops)
+        self.planes = next((ints[6] for kind, ints, _ in ops if kind == 0), None)  # channels of the network input
         self._h = C.c_void_p()
         check(lib().scn_program_create(C.byref(self._h)))
         for kind, ints, floats in ops:
@@ -136,8 +137,10 @@ class Program(object):
             self._h = None
 
     def usable(self, coords, feats, math_mode):
+        # (a wrongly shaped input takes the layer-by-layer path, whose asserts then raise as the reference's would)
         return (math_mode == self.math_mode and isinstance(feats, torch.Tensor) and feats.is_cuda and feats.dtype == torch.float32
-                and feats.dim() == 2 and coords.dtype == torch.int64 and coords.dim() == 2)
+                and feats.dim() == 2 and coords.dtype == torch.int64 and coords.dim() == 2 and coords.size(1) in (3, 4)
+                and feats.size(0) == coords.size(0) and feats.size(1) == self.planes)
 
     def throttle(self):
         """Wait until at most one forward of this program is still running (scn_program_throttle)."""

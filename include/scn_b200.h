@@ -55,6 +55,11 @@ int scn_input_layer_forward_padded_bf16(scn_metadata *m, const float *in_feature
 /* InputLayer_updateGradInput (pybind.cpp:159-162; CPU/IOLayers.cpp:30-47) */
 int scn_input_layer_backward(scn_metadata *m, float *d_in_features, const float *d_out_features, int n_planes);
 
+/* OutputLayer_updateOutput / _updateGradInput (pybind.cpp:163-170; CPU/IOLayers.cpp:97-140): out [n input rows][n_planes] =
+ * the feature row of each input row's voxel (no averaging); d_in [nActive][n_planes] = sum over the rows of a voxel. */
+int scn_output_layer_forward(scn_metadata *m, const float *in_features, float *out_features, int n_planes);
+int scn_output_layer_backward(scn_metadata *m, float *d_in_features, const float *d_out_features, int n_planes);
+
 /* Metadata::getNActive (Metadata.cpp:67-69) */
 int scn_get_nactive(scn_metadata *m, const long spatial_size[3], long *n_active);
 /* Metadata::getSpatialLocations (pybind.cpp:17; Metadata.cpp:147-168): int64 [nActive][4] */
@@ -140,6 +145,16 @@ int scn_batchnorm_backward(const float *in, float *d_in, const float *out, float
                            const float *save_mean, const float *save_invstd, const float *weight, float *d_weight,
                            float *d_bias, float leakiness, void *stream);
 
+/* NetworkInNetwork_updateOutput / _updateGradInput / _accGradParameters (pybind.cpp:224-228; CPU/NetworkInNetwork.cpp:7-46):
+ * out[n][n_out] = bias + in[n][n_in] @ weight[n_in][n_out]; d_in = d_out @ weight^T; d_weight = in^T @ d_out and
+ * d_bias = column sums of d_out (both overwritten; d_bias may be NULL).  *macs = n_rows * n_in * n_out.  in_bf16 /
+ * weight_tag as for the convolutions. */
+int scn_network_in_network_forward(const float *in, float *out, const float *weight, const float *bias, long n_rows, int n_in, int n_out,
+                                   double *macs, void *stream, const void *in_bf16, long long weight_tag);
+int scn_network_in_network_backward_input(float *d_in, const float *d_out, const float *weight, long n_rows, int n_in, int n_out, void *stream);
+int scn_network_in_network_backward_params(const float *in, const float *d_out, float *d_weight, float *d_bias, long n_rows, int n_in, int n_out,
+                                           void *stream);
+
 /* AddTable / add_feature_planes (sparseconvnet/tables.py:28-41, utils.py:61-66): out = a + b */
 int scn_add_features(const float *a, const float *b, float *out, long n_elements, void *stream, void *out_bf16);
 
@@ -201,8 +216,27 @@ int scn_get_math_mode(void);
 int scn_tensor_core_path_available(void);
 /* number of kernels this library has launched since load (for bench.py's gpu_launches) */
 long scn_kernel_launch_count(void);
-/* developer counters of the Metadata memory pool: 0 = chunks taken from the driver, 1 = waits for a chunk still in use, 2 = pool size in MiB */
+/* developer counters.  Metadata memory pool: 0 = chunks taken from the driver, 1 = waits for a chunk still in use, 2 = pool
+ * size in MiB.  Which code path ran (monotonic since load; the parity tests assert on their deltas): 3 = tensor-core launches
+ * that carried a lateral 1x1x1 stage, 4 = launches whose epilogue accumulated BatchNorm statistics, 5 = program registers
+ * written as bf16 only, 6 = laterals run as a separate convolution + add (fallback), 7 = tcgen05 convolution launches,
+ * 8 = BatchNorm ops applied from epilogue statistics, 9 = launches that split the filter offsets over CTAs (atomic
+ * epilogue), 10 = CUDA-core convolution launches. */
 long scn_debug_counter(int which);
+
+/* Fusion requests for the NEXT convolution forward call made by this thread (what the program executor uses to fold the
+ * FPN's lateral 1x1x1 convolution and the statistics of a following BatchNorm into a convolution; no reference counterpart:
+ * the reference runs NetworkInNetwork / SubmanifoldConvolution(1), AddTable and BatchNormalization as separate passes,
+ * fpn_net.py:166-176, CPU/BatchNormalization.cpp:12-62).
+ *  lateral: out = conv(in) [+ add_in] + lat_in[row] @ lat_weight ([n_in][n_out], one filter offset), lat_in_bf16 = bf16
+ *           copy of lat_in (needed in math mode 2);
+ *  stats:   sums = [8 replicas][2][128] doubles, zeroed by the caller; the launch adds per-channel sum (first 128) and sum
+ *           of squares (second 128) of the rows it stores, spread over the replicas.
+ * A launch that cannot honour a request (CUDA-core path, packed rows, split offsets, > 128 channels) ignores it;
+ * scn_fuse_result reports what the last call did and disarms both requests. */
+int scn_fuse_next_lateral(const float *lat_in, const void *lat_in_bf16, const float *lat_weight, long long weight_tag, int n_in, long rows);
+int scn_fuse_next_stats(double *sums);
+int scn_fuse_result(int *lateral_taken, int *stats_taken);
 
 #ifdef __cplusplus
 }

@@ -325,3 +325,44 @@ def o_bn_backward(feats, out, d_out, save_mean, save_invstd, weight, leakiness=0
     olib().o_bn_backward(feats.ctypes.data, d_in.ctypes.data, out.ctypes.data, d_out.ctypes.data, c, n, _f32(save_mean).ctypes.data,
                          _f32(save_invstd).ctypes.data, _f32(weight).ctypes.data, dw.ctypes.data, db.ctypes.data, leakiness)
     return d_in, dw, db
+
+
+def o_output_layer_forward(feats, rules_hdr, rules_tab):
+    """cpu_OutputLayer_updateOutput (SCN/CPU/IOLayers.cpp:97-118): InputLayer_BackwardPass with average = false --
+    every input row receives its voxel's feature row; rows dropped by modes 1 / 2 stay zero.  mode 0: copy."""
+    feats = _f32(feats)
+    mode, max_active, n_in, n_out = [int(x) for x in rules_hdr]
+    if mode == 0:
+        return feats.copy()
+    out = np.zeros((n_in, feats.shape[1]), dtype=np.float32)
+    tab = np.ascontiguousarray(rules_tab, dtype=np.int32)
+    olib().o_input_layer_backward(out.ctypes.data, feats.ctypes.data, n_in, n_out, max_active, feats.shape[1], tab.ctypes.data, 0)
+    return out
+
+
+def o_output_layer_backward(d_out, rules_hdr, rules_tab):
+    """cpu_OutputLayer_updateGradInput (SCN/CPU/IOLayers.cpp:119-140): InputLayer_ForwardPass with average = false."""
+    d_out = _f32(d_out)
+    mode, max_active, _, n_out = [int(x) for x in rules_hdr]
+    if mode == 0:
+        return d_out.copy()
+    d_in = np.zeros((n_out, d_out.shape[1]), dtype=np.float32)
+    tab = np.ascontiguousarray(rules_tab, dtype=np.int32)
+    olib().o_input_layer_forward(d_out.ctypes.data, d_in.ctypes.data, n_out, max_active, d_out.shape[1], tab.ctypes.data, 0)
+    return d_in
+
+
+def o_nin_forward(feats, weight, bias=None):
+    """cpu_NetworkInNetwork_updateOutput (SCN/CPU/NetworkInNetwork.cpp:7-24): out = bias + feats @ weight; returns (out, macs)."""
+    feats, weight = _f32(feats), _f32(weight)
+    out = feats @ weight
+    if bias is not None:
+        out = out + _f32(bias)[None, :]
+    return out.astype(np.float32), float(feats.shape[0]) * weight.shape[0] * weight.shape[1]
+
+
+def o_nin_backward(feats, d_out, weight):
+    """cpu_NetworkInNetwork_updateGradInput / _accGradParameters (SCN/CPU/NetworkInNetwork.cpp:25-46):
+    d_in = d_out @ W^T, dW = feats^T @ d_out, d_bias = column sums of d_out."""
+    feats, d_out, weight = _f32(feats), _f32(d_out), _f32(weight)
+    return d_out @ weight.T, feats.T @ d_out, d_out.sum(0)

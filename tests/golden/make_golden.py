@@ -6,6 +6,8 @@
                        /root/reference on top of oracle/_ref/SCN.so) for a deterministic state_dict
                        and a seeded synthetic building: features + spatial locations of every
                        returned map, and the multiply-add counter.
+ * fpn_mini4_train.npz one training step of the reference's scn.FPN_Net (train-mode forward, loss, autograd backward):
+                       parameter gradients and BatchNorm buffers.
  * rulebooks.json      sha1 digests of every grid / iteration order / rulebook of the reference's
                        own Metadata<3> (oracle/_ref/libscn_ref_rules.so) for three buildings,
                        including the full-size B470 building of BASELINE.json.
@@ -57,6 +59,37 @@ def run_reference_fpn(name):
     print(name, "macs", float(out["macs"]), {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim == 2})
 
 
+def run_reference_fpn_train(name="mini4"):
+    """Whole-network TRAINING step of the reference's own scn.FPN_Net through its autograd Functions (CPU extension):
+    train-mode forward (batch statistics, running statistics updated), loss = sum over the returned maps of mean(f^2),
+    backward.  Stored: the loss, every parameter gradient (None for the dead top-down levels, recorded as absent) and
+    the BatchNorm buffers after the step."""
+    cfg, bld = CASES[name]
+    cfg = dict(cfg, track_running_stats=True)
+    scn = ref_python.load_reference_package()
+    args, kw = fpn_util.ref_ctor_args(cfg)
+    net = scn.FPN_Net(*args, **kw)
+    net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+    net.train()
+    coords = synthetic.building_coords(**bld)
+    feats = fpn_util.features_for(coords)
+    rpn, roi = net([torch.from_numpy(coords), torch.from_numpy(feats)])
+    maps = rpn + roi
+    loss = sum((m.features ** 2).mean() for m in maps)
+    loss.backward()
+    out = {"loss": np.float64(loss.item()), "n_maps": len(maps)}
+    out["map_mean_sq"] = np.array([float((m.features ** 2).mean()) for m in maps], np.float64)  # (the loss terms; eval-mode features are in fpn_<name>.npz)
+    n_grad = 0
+    for k, p_ in net.named_parameters():
+        if p_.grad is not None:
+            out["grad:" + k] = p_.grad.numpy().astype(np.float32)
+            n_grad += 1
+    for k, b in net.named_buffers():
+        out["buf:" + k] = b.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, f"fpn_{name}_train.npz"), **out)
+    print(name, "train: loss", float(out["loss"]), "params with grad", n_grad, "of", len(list(net.parameters())))
+
+
 def rulebook_digests():
     res = {}
     cases = {
@@ -105,3 +138,4 @@ if __name__ == "__main__":
     rulebook_digests()
     for name in CASES:
         run_reference_fpn(name)
+    run_reference_fpn_train("mini4")

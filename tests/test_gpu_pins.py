@@ -1,0 +1,418 @@
+"""GPU parity tests that pin the BENCHMARKED code path (bf16 / tf32 operands, replayed program on an internally numbered
+Metadata, lateral 1x1x1 stage folded into the convolution, BatchNorm statistics in the epilogue, bf16-only outputs, packed
+narrow rows) to the outputs of the reference itself, plus the pieces round 1 left untested: InputLayer backward, OutputLayer,
+NetworkInNetwork, a whole-network training step against the reference's autograd, odd channel counts on the scratch path.
+`scn_debug_counter` deltas prove that the fused paths really ran (no silent fallback)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import fpn_util
+from detection_3d_b200 import synthetic
+from oracle import scn_oracle as so
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+L = torch.LongTensor
+CNT = dict(lateral=3, stats=4, half_only=5, lateral_fallback=6, tc=7, bn_from_sums=8, split=9, simt=10)
+
+TF32_TOL, BF16_TOL = (4e-3, 2e-3), (1.6e-2, 8e-3)   # per layer: rtol, atol x max|ref|  (operand rounding 2^-10 / 2^-8 per product)
+TC_TOL = {"tf32": TF32_TOL, "bf16": BF16_TOL}
+TC_E2E = {"tf32": 3e-2, "bf16": 6e-2}               # end to end: max |got - ref| / max(1, max|ref|) per returned map
+
+
+def _scn():
+    import detection_3d_b200.sparseconvnet as scn
+    return scn
+
+
+def _counters():
+    from detection_3d_b200._lib import lib
+    return {k: lib().scn_debug_counter(i) for k, i in CNT.items()}
+
+
+def _delta(before):
+    now = _counters()
+    return {k: now[k] - before[k] for k in now}
+
+
+def _tc_or_skip(scn):
+    if not scn.SCN.lib().scn_tensor_core_path_available():
+        pytest.skip("tcgen05 path needs an sm_100 device")
+
+
+def _close(got, want, rtol, atol):
+    want = np.asarray(want)
+    scale = max(1.0, float(np.abs(want).max())) if want.size else 1.0
+    np.testing.assert_allclose(np.asarray(got), want, rtol=rtol, atol=atol * scale)
+
+
+def _gpu():
+    from gpu_adapter import GpuMetadata
+    return GpuMetadata()
+
+
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------ IO layers
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_input_layer_backward_and_output_layer(mode):
+    """scn_input_layer_backward vs InputLayer_BackwardPass (SCN/CPU/IOLayers.cpp:30-47,76-95) and the OutputLayer pair
+    (:97-140), all five input modes, duplicates present for modes 1-4."""
+    scn = _scn()
+    rs = np.random.RandomState(40 + mode)
+    c = rs.randint(0, 10, (2500, 3))
+    if mode == 0:
+        c = np.unique(c, axis=0)
+        c = c[rs.permutation(c.shape[0])]
+    f = rs.randn(c.shape[0], 9).astype(np.float32)
+    G, O = _gpu(), so.OracleMetadata()
+    n = G.input_layer([16, 16, 16], c, 0, mode, feats=f)
+    assert n == O.input_layer([16, 16, 16], c, 0, mode)
+    hdr, tab = (O.input_rules() + [np.zeros(0, np.int32)])[:2]
+    if mode == 0:
+        hdr = np.array([0, 1, c.shape[0], c.shape[0]])
+    dy = rs.randn(n, 9).astype(np.float32)
+    want = dy.copy() if mode == 0 else so.o_input_layer_backward(dy, hdr, tab)
+    din = torch.empty(0, device="cuda")
+    scn.SCN.InputLayer_updateGradInput(G.m, din, T(dy))
+    assert din.shape == want.shape
+    np.testing.assert_allclose(din.cpu().numpy(), want, rtol=1e-6, atol=1e-6)
+    # OutputLayer forward: voxel rows back to input rows; backward: sums per voxel
+    x = rs.randn(n, 5).astype(np.float32)
+    out = torch.empty(0, device="cuda")
+    scn.SCN.OutputLayer_updateOutput(G.m, T(x), out)
+    np.testing.assert_allclose(out.cpu().numpy(), so.o_output_layer_forward(x, hdr, tab), rtol=1e-6, atol=1e-6)
+    g = rs.randn(*out.shape).astype(np.float32)
+    gin = torch.empty(0, device="cuda")
+    scn.SCN.OutputLayer_updateGradInput(G.m, gin, T(g))
+    np.testing.assert_allclose(gin.cpu().numpy(), so.o_output_layer_backward(g, hdr, tab), rtol=1e-5, atol=1e-5)
+
+
+def test_output_layer_module_autograd():
+    """scn.OutputLayer through the module API, gradient through InputLayer -> OutputLayer (mode 4): d feats = mean over the voxel."""
+    scn = _scn()
+    rs = np.random.RandomState(3)
+    c = rs.randint(0, 6, (400, 3))
+    f = torch.from_numpy(rs.randn(400, 4).astype(np.float32)).cuda().requires_grad_(True)
+    inp = scn.InputLayer(3, [8, 8, 8], mode=4)
+    x = inp([torch.from_numpy(c), f])
+    y = scn.OutputLayer(3)(x)
+    assert y.shape == (400, 4)
+    w = torch.from_numpy(rs.randn(400, 4).astype(np.float32)).cuda()
+    (y * w).sum().backward()
+    O = so.OracleMetadata()
+    O.input_layer([8, 8, 8], c, 0, 4)
+    hdr, tab = O.input_rules()
+    want = so.o_input_layer_backward(so.o_output_layer_backward(w.cpu().numpy(), hdr, tab), hdr, tab)
+    np.testing.assert_allclose(f.grad.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), so.o_output_layer_forward(so.o_input_layer_forward(f.detach().cpu().numpy(), hdr, tab), hdr, tab), rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ NetworkInNetwork
+@pytest.mark.parametrize("math", ["fp32", "tf32", "bf16"])
+@pytest.mark.parametrize("n,cin,cout,bias", [(3000, 64, 128, False), (777, 32, 32, True), (20000, 128, 64, False), (5, 9, 16, True), (0, 32, 32, False)])
+def test_network_in_network(math, n, cin, cout, bias):
+    """scn.NetworkInNetwork forward + autograd backward vs cpu_NetworkInNetwork_* (SCN/CPU/NetworkInNetwork.cpp:7-46)."""
+    scn = _scn()
+    if math != "fp32":
+        _tc_or_skip(scn)
+    rs = np.random.RandomState(n + cin + cout)
+    x = rs.randn(n, cin).astype(np.float32)
+    dy = rs.randn(n, cout).astype(np.float32)
+    rtol, atol = (2e-4, 2e-5) if math == "fp32" else TC_TOL[math]
+    try:
+        scn.set_math_mode(math)
+        m = scn.NetworkInNetwork(cin, cout, bias).cuda()
+        if bias:
+            with torch.no_grad():
+                m.bias.copy_(torch.from_numpy(rs.randn(cout).astype(np.float32)))
+        w = m.weight.detach().cpu().numpy()
+        b = m.bias.detach().cpu().numpy() if bias else None
+        xt = T(x).requires_grad_(True)
+        t = scn.SparseConvNetTensor(features=xt, metadata=None, spatial_size=L([8, 8, 8]))
+        scn.forward_pass_multiplyAdd_count = 0
+        y = m(t).features
+        want, macs = so.o_nin_forward(x, w, b)
+        assert scn.forward_pass_multiplyAdd_count == macs and y.shape == (n, cout)
+        _close(y.detach().cpu().numpy(), want, rtol, atol)
+        if n:
+            y.backward(T(dy))
+            din, dw, db = so.o_nin_backward(x, dy, w)
+            _close(xt.grad.cpu().numpy(), din, rtol, atol)
+            _close(m.weight.grad.cpu().numpy(), dw, 1e-3, 1e-4)   # weight gradient always runs in fp32 on the CUDA cores
+            if bias:
+                _close(m.bias.grad.cpu().numpy(), db, 1e-3, 1e-4)
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+
+
+# ------------------------------------------------------------------ fused lateral stage and epilogue statistics (C-ABI)
+def _stats_buffer():
+    return torch.zeros(8 * 2 * 128, dtype=torch.float64, device="cuda")
+
+
+def _reduce_stats(buf, c):
+    s = buf.view(8, 2, 128).sum(0).cpu().numpy()
+    return s[0, :c], s[1, :c]
+
+
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+@pytest.mark.parametrize("kind,big,c_lat", [("subm", True, 64), ("subm", True, 32), ("deconv", False, 128), ("deconv", True, 64), ("conv", False, 256)])
+def test_fused_lateral_stage_and_epilogue_stats(math, kind, big, c_lat):
+    """out = conv(x) + y[row] @ W_lat with the per-channel sum / sum of squares of `out` accumulated by the epilogue, requested
+    through scn_fuse_next_lateral / scn_fuse_next_stats -- the in2 / wimg2 / stats arguments of conv_plan_tc that the replayed
+    program uses for the FPN's top-down step.  Checked against the oracle's conv (+ deconv) + NetworkInNetwork + add and
+    against out.sum(0), (out * out).sum(0); scn_fuse_result must report that both requests were honoured."""
+    scn = _scn()
+    from detection_3d_b200._lib import check, l3, lib
+    _tc_or_skip(scn)
+    if big:
+        c = synthetic.building_coords(nx=300, ny=280, nz=40, n_walls=5, seed=5)
+        full, coarse = [2048, 2048, 512], [1024, 1024, 256]
+    else:
+        c = synthetic.small_building(40, 36, 12, 3, seed=4)
+        full, coarse = [64, 64, 32], [32, 32, 16]
+    G, O = _gpu(), so.OracleMetadata()
+    n = G.input_layer(full, c, 0, 4)
+    assert n == O.input_layer(full, c, 0, 4)
+    rules2 = O.conv_rules(full, coarse, [2, 2, 2], [2, 2, 2])
+    G.conv_rules(full, coarse, [2, 2, 2], [2, 2, 2])
+    nc = O.nactive(coarse)
+    rs = np.random.RandomState(c_lat + n % 97)
+    C0 = 128
+    if kind == "subm":
+        x = rs.randn(n, C0).astype(np.float32)
+        w = (rs.randn(27, 1, C0, C0) * (2.0 / (C0 * 27)) ** 0.5).astype(np.float32)
+        conv_out, _ = so.o_conv_forward(x, w, O.submanifold_rules(full, [3, 3, 3]), n)
+        n_out = n
+    elif kind == "deconv":
+        x = rs.randn(nc, C0).astype(np.float32)
+        w = (rs.randn(8, 1, C0, C0) * (2.0 / (C0 * 8)) ** 0.5).astype(np.float32)
+        conv_out, _ = so.o_conv_forward(x, w, rules2, n, deconv=True)
+        n_out = n
+    else:
+        x = rs.randn(n, C0).astype(np.float32)
+        w = (rs.randn(8, 1, C0, C0) * (2.0 / (C0 * 8)) ** 0.5).astype(np.float32)
+        conv_out, _ = so.o_conv_forward(x, w, rules2, nc)
+        n_out = nc
+    y = rs.randn(n_out, c_lat).astype(np.float32)
+    wl = (rs.randn(c_lat, C0) * (2.0 / c_lat) ** 0.5).astype(np.float32)
+    lat, _ = so.o_nin_forward(y, wl)
+    want = conv_out + lat
+    p = lambda t: C.c_void_p(t.data_ptr())
+    try:
+        scn.set_math_mode(math)
+        xt, wt, yt, wlt = T(x), T(w), T(y), T(wl)
+        y16 = yt.to(torch.bfloat16)
+        out = torch.empty(n_out, C0, device="cuda")
+        stats = _stats_buffer()
+        macs = C.c_double()
+        before = _counters()
+        check(lib().scn_fuse_next_lateral(p(yt), p(y16), p(wlt), 0, c_lat, n_out))
+        check(lib().scn_fuse_next_stats(p(stats)))
+        if kind == "subm":
+            check(lib().scn_submanifold_convolution_forward(G.m._h, l3(full), l3([3, 3, 3]), p(xt), p(out), p(wt), None, C0, C0, C.byref(macs), None, 0, None, None))
+        elif kind == "deconv":
+            check(lib().scn_deconvolution_forward(G.m._h, l3(coarse), l3(full), l3([2, 2, 2]), l3([2, 2, 2]), p(xt), p(out), p(wt), None, C0, C0, C.byref(macs), None, 0, None, None))
+        else:
+            check(lib().scn_convolution_forward(G.m._h, l3(full), l3(coarse), l3([2, 2, 2]), l3([2, 2, 2]), p(xt), p(out), p(wt), None, C0, C0, C.byref(macs), None, 0, None, None))
+        took_l, took_s = C.c_int(), C.c_int()
+        check(lib().scn_fuse_result(C.byref(took_l), C.byref(took_s)))
+        torch.cuda.synchronize()
+        d = _delta(before)
+    finally:
+        scn.set_math_mode("fp32")
+    assert took_l.value == 1 and d["lateral"] == 1, (took_l.value, d)
+    rtol, atol = TC_TOL[math]
+    _close(out.cpu().numpy(), want, rtol, atol * 1.5)  # two operand-rounded products summed
+    if d["split"] == 0:  # (small levels split the filter offsets over CTAs: no statistics there, by design)
+        assert took_s.value == 1 and d["stats"] == 1, (took_s.value, d)
+        s1, s2 = _reduce_stats(stats, C0)
+        o64 = out.double()
+        np.testing.assert_allclose(s1, o64.sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3 * n_out ** 0.5)
+        np.testing.assert_allclose(s2, (o64 * o64).sum(0).cpu().numpy(), rtol=1e-4)
+    else:
+        assert took_s.value == 0
+
+
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+def test_epilogue_stats_alone_packed_and_plain(math):
+    """Statistics request without a lateral on a 32-channel layer (packed rows in bf16 mode) and a 64-channel one."""
+    scn = _scn()
+    from detection_3d_b200._lib import check, l3, lib
+    _tc_or_skip(scn)
+    c = synthetic.building_coords(nx=300, ny=280, nz=40, n_walls=5, seed=5)
+    full = [2048, 2048, 512]
+    G, O = _gpu(), so.OracleMetadata()
+    n = G.input_layer(full, c, 0, 4)
+    O.input_layer(full, c, 0, 4)
+    rules = O.submanifold_rules(full, [3, 3, 3])
+    p = lambda t: C.c_void_p(t.data_ptr())
+    try:
+        scn.set_math_mode(math)
+        for ch in (32, 64):
+            rs = np.random.RandomState(ch)
+            x = rs.randn(n, ch).astype(np.float32)
+            w = (rs.randn(27, 1, ch, ch) * (2.0 / (ch * 27)) ** 0.5).astype(np.float32)
+            want, _ = so.o_conv_forward(x, w, rules, n)
+            xt, wt = T(x), T(w)
+            out = torch.empty(n, ch, device="cuda")
+            stats = _stats_buffer()
+            macs = C.c_double()
+            check(lib().scn_fuse_next_stats(p(stats)))
+            check(lib().scn_submanifold_convolution_forward(G.m._h, l3(full), l3([3, 3, 3]), p(xt), p(out), p(wt), None, ch, ch, C.byref(macs), None, 0, None, None))
+            took_l, took_s = C.c_int(), C.c_int()
+            check(lib().scn_fuse_result(C.byref(took_l), C.byref(took_s)))
+            torch.cuda.synchronize()
+            assert took_s.value == 1 and took_l.value == 0
+            _close(out.cpu().numpy(), want, *TC_TOL[math])
+            s1, s2 = _reduce_stats(stats, ch)
+            o64 = out.double()
+            np.testing.assert_allclose(s1, o64.sum(0).cpu().numpy(), rtol=1e-4, atol=1e-3 * n ** 0.5)
+            np.testing.assert_allclose(s2, (o64 * o64).sum(0).cpu().numpy(), rtol=1e-4)
+    finally:
+        scn.set_math_mode("fp32")
+
+
+# ------------------------------------------------------------------ odd channel counts: padded copy + bf16 copy in one launch
+@pytest.mark.parametrize("math", ["tf32", "bf16"])
+def test_odd_channel_counts_use_separate_scratch(math):
+    """Cin = 48 with Cout = 256 (no packing) and a Deconvolution with Cin = 48: the rows are zero-padded to 64 channels into
+    one scratch buffer and, in bf16 mode, converted into a SECOND one (round 1 used the same buffer for both)."""
+    scn = _scn()
+    _tc_or_skip(scn)
+    c = synthetic.small_building(40, 36, 12, 3, seed=4)
+    full, coarse = [64, 64, 32], [32, 32, 16]
+    G, O = _gpu(), so.OracleMetadata()
+    n = G.input_layer(full, c, 0, 4)
+    O.input_layer(full, c, 0, 4)
+    rules2 = O.conv_rules(full, coarse, [2, 2, 2], [2, 2, 2])
+    nc = O.nactive(coarse)
+    rs = np.random.RandomState(48)
+    x = rs.randn(n, 48).astype(np.float32)
+    w = (rs.randn(27, 1, 48, 256) * (2.0 / (48 * 27)) ** 0.5).astype(np.float32)
+    want, _ = so.o_conv_forward(x, w, O.submanifold_rules(full, [3, 3, 3]), n)
+    xc = rs.randn(nc, 48).astype(np.float32)
+    wd = (rs.randn(8, 1, 48, 64) * (2.0 / (48 * 8)) ** 0.5).astype(np.float32)
+    wantd, _ = so.o_conv_forward(xc, wd, rules2, n, deconv=True)
+    dy = rs.randn(n, 256).astype(np.float32)
+    din_w, dw_w = so.o_conv_backward(x, dy, w, O.submanifold_rules(full, [3, 3, 3]))
+    try:
+        scn.set_math_mode(math)
+        out, outd = torch.empty(0, device="cuda"), torch.empty(0, device="cuda")
+        scn.SCN.SubmanifoldConvolution_updateOutput(L(full), L([3, 3, 3]), G.m, T(x), out, T(w), torch.Tensor())
+        scn.SCN.Convolution_updateOutput(L(full), L(coarse), L([2, 2, 2]), L([2, 2, 2]), G.m, T(rs.randn(n, 48).astype(np.float32)), torch.empty(0, device="cuda"),
+                                         T((rs.randn(8, 1, 48, 64) * 0.05).astype(np.float32)), torch.Tensor())
+        scn.SCN.Deconvolution_updateOutput(L(coarse), L(full), L([2, 2, 2]), L([2, 2, 2]), G.m, T(xc), outd, T(wd), torch.Tensor())
+        din, dw = torch.empty(0, device="cuda"), torch.zeros(w.shape, device="cuda")
+        scn.SCN.SubmanifoldConvolution_backward(L(full), L([3, 3, 3]), G.m, T(x), din, T(dy), T(w), dw, torch.Tensor())
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+    rtol, atol = TC_TOL[math]
+    _close(out.cpu().numpy(), want, rtol, atol)
+    _close(outd.cpu().numpy(), wantd, rtol, atol)
+    _close(din.cpu().numpy(), din_w, rtol, atol)
+    _close(dw.cpu().numpy(), dw_w, rtol, atol)
+
+
+# ------------------------------------------------------------------ the benchmarked path vs the reference's outputs
+@pytest.mark.parametrize("math", ["bf16", "tf32"])
+def test_replayed_program_tensor_core_vs_reference_golden(math):
+    """What bench.py times: tensor-core math mode + REPLAYED program on an internally numbered Metadata, on the sw4c backbone
+    (128-channel <1,4,1> kernel, level 0 with >= 32768 rows => bf16-only outputs in bf16 mode) against the outputs of the
+    reference's own scn.FPN_Net (tests/golden/fpn_sw4c_mid.npz).  Replayed twice.  Counters prove the lateral stage, the
+    epilogue statistics and the bf16-only outputs were taken and that no lateral fell back to a separate pass."""
+    scn = _scn()
+    _tc_or_skip(scn)
+    cfg = scn.sw4c_fpn432_config()
+    bld = dict(nx=300, ny=280, nz=40, n_walls=5, seed=5)
+    g = np.load(os.path.join(GOLD, "fpn_sw4c_mid.npz"))
+    try:
+        scn.set_math_mode(math)
+        net = scn.FPN_Net(**cfg)
+        net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+        net = net.cuda().eval()
+        coords = synthetic.building_coords(**bld)
+        c, f = torch.from_numpy(coords), torch.from_numpy(fpn_util.features_for(coords)).cuda()
+        with torch.no_grad():
+            net([c, f])  # records (layer by layer)
+            assert net.__dict__.get("_program") is not None, net.__dict__.get("_program_error")
+            for rep in range(2):
+                before = _counters()
+                scn.forward_pass_multiplyAdd_count = 0
+                rpn, roi = net([c, f])  # replays
+                torch.cuda.synchronize()
+                d = _delta(before)
+                assert scn.forward_pass_multiplyAdd_count == float(g["macs"])
+                # 8 top-down steps: deconvolution + lateral shortcut in one launch each; none may fall back
+                assert d["lateral"] == 8 and d["lateral_fallback"] == 0, d
+                assert d["stats"] >= 8 and d["bn_from_sums"] >= 8, d
+                assert d["simt"] == 0, d
+                if math == "bf16":
+                    assert d["half_only"] >= 3, d
+                worst = 0.0
+                for tag, maps in (("rpn", rpn), ("roi", roi)):
+                    assert len(maps) == int(g[f"n_{tag}"])
+                    for i, m in enumerate(maps):
+                        assert np.array_equal(m.get_spatial_locations().numpy(), g[f"{tag}{i}_locations"]), (tag, i)
+                        ref = g[f"{tag}{i}_features"]
+                        err = float(np.abs(m.features.cpu().numpy() - ref).max() / max(1.0, np.abs(ref).max()))
+                        worst = max(worst, err)
+                        assert err < TC_E2E[math], (tag, i, err, rep)
+                print(f"[pin] {math} replay {rep}: worst map error {worst:.3e} of max|ref| (tolerance {TC_E2E[math]})", d)
+    finally:
+        scn.set_math_mode("fp32")
+
+
+# ------------------------------------------------------------------ whole-network training step vs the reference's autograd
+@pytest.mark.parametrize("math", ["fp32", "bf16"])
+def test_whole_network_training_step_vs_reference_autograd(math):
+    """Train-mode forward (batch statistics, running statistics updated), loss = sum of mean(f^2) over the returned maps,
+    autograd backward through every layer kind, against the same step of the reference's scn.FPN_Net on its CPU extension
+    (tests/golden/fpn_mini4_train.npz, tests/golden/make_golden.py::run_reference_fpn_train).  Parameters of the dead
+    top-down levels get no gradient on either side.  Tolerances: fp32 5e-3, bf16 8e-2 of max|grad| per tensor."""
+    scn = _scn()
+    if math != "fp32":
+        _tc_or_skip(scn)
+    g = np.load(os.path.join(GOLD, "fpn_mini4_train.npz"))
+    cfg = dict(fpn_util.mini4_config(), track_running_stats=True)
+    bld = dict(nx=60, ny=56, nz=24, n_walls=3, seed=3)
+    tol = 5e-3 if math == "fp32" else 8e-2
+    try:
+        scn.set_math_mode(math)
+        net = scn.FPN_Net(**cfg)
+        net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+        net = net.cuda().train()
+        coords = synthetic.building_coords(**bld)
+        rpn, roi = net([torch.from_numpy(coords), torch.from_numpy(fpn_util.features_for(coords)).cuda()])
+        maps = rpn + roi
+        assert len(maps) == int(g["n_maps"])
+        terms = [(m.features ** 2).mean() for m in maps]
+        loss = sum(terms)
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+    np.testing.assert_allclose(np.array([float(t) for t in terms]), g["map_mean_sq"], rtol=tol)
+    assert abs(float(loss) - float(g["loss"])) <= tol * float(g["loss"])
+    want_keys = {k[5:] for k in g.files if k.startswith("grad:")}
+    got = {k: p.grad for k, p in net.named_parameters()}
+    assert {k for k, v in got.items() if v is not None} == want_keys
+    worst = ("", 0.0)
+    for k in sorted(want_keys):
+        ref = g["grad:" + k]
+        err = float(np.abs(got[k].cpu().numpy() - ref).max() / max(1e-6, np.abs(ref).max()))
+        if err > worst[1]:
+            worst = (k, err)
+        assert err < tol, (k, err)
+    for k, b in net.named_buffers():
+        ref = g["buf:" + k]
+        np.testing.assert_allclose(b.cpu().numpy(), ref, rtol=tol, atol=tol * max(1e-3, float(np.abs(ref).max())), err_msg=k)
+    print(f"[pin] training step {math}: worst gradient error {worst[1]:.3e} of max|grad| ({worst[0]})")
