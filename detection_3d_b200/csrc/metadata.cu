@@ -924,23 +924,97 @@ int Metadata::build_tile_masks(NbrPlan &plan) {
 // RectangularRegions.h:56-71; window [c - f/2, c + f - 1 - f/2], SubmanifoldConvolutionRules.h:11-22).
 // 128 threads per block = one plan tile per loop iteration: the tile's offset mask (bit k: some site of the tile has a
 // neighbour at offset k) is reduced on the spot instead of by a second pass over the plan.
+//
+// SORTED PLANS.  The plan may list the sites in any order (slot q of the plan <-> site perm[q]; outRow[q] names its output row).
+// The tensor-core kernel multiplies whole 128-row tiles per live filter offset, so a tile whose sites have DIFFERENT neighbour
+// patterns (a piece of floor next to a piece of wall) pays for the union of their offsets with half-empty operand rows: on the
+// B470 building 14.9 of 27 offsets are live per tile at a row fill of 62 %.  Inside windows of kSortWindow sites (in spatial
+// order, so the gathers stay local) the sites are therefore grouped by the AXES along which they have neighbours (x / y / z: 3
+// bits -- floor, the two wall orientations, junctions), stable within a group: 10.4 live offsets per tile, fill 89 %.
+constexpr int kSortWindow = 16384;   // sites per window = 128 tiles; one CTA sorts one window
+constexpr int kSortMinSites = 4096;  // smaller levels keep the spatial order
+__global__ void __launch_bounds__(256) k_site_class(GridView g, const int4 *__restrict__ coords, const int *__restrict__ p2id, int n, int f0, int f1, int f2,
+                                                    unsigned char *__restrict__ cls) {
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x) {
+    const int4 c = coords[p2id[p]];
+    int m = 0;
+    for (int a = 0; a < f0 && m != 7; a++)
+      for (int b = 0; b < f1 && m != 7; b++)
+        for (int d = 0; d < f2; d++) {
+          const int dx = a - f0 / 2, dy = b - f1 / 2, dz = d - f2 / 2;
+          const int bits = (dx ? 4 : 0) | (dy ? 2 : 0) | (dz ? 1 : 0);
+          if ((bits & ~m) == 0) continue; // nothing new to learn from this offset (includes the centre)
+          if (grid_has(g, c.x + dx, c.y + dy, c.z + dz, c.w)) m |= bits;
+        }
+    cls[p] = (unsigned char)m;
+  }
+}
+// stable counting sort of one window by class: perm[q] = p, slot[p] = q (both in [window start, window end))
+__global__ void __launch_bounds__(1024) k_window_sort(const unsigned char *__restrict__ cls, int n, int *__restrict__ perm, int *__restrict__ slot) {
+  constexpr int PER = kSortWindow / 1024;
+  __shared__ int s_warp[8][32];
+  __shared__ int s_base[8];
+  const int w0 = blockIdx.x * kSortWindow, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int p0 = w0 + tid * PER;
+  unsigned char mine[PER];
+  int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < PER; j++) {
+    mine[j] = p0 + j < n ? cls[p0 + j] : 255;
+#pragma unroll
+    for (int c = 0; c < 8; c++) cnt[c] += mine[j] == c;
+  }
+  int excl[8]; // exclusive prefix of this thread's count within its class, over the threads of the block
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int inc = warp_incl_scan(cnt[c], lane);
+    excl[c] = inc - cnt[c];
+    if (lane == 31) s_warp[c][wid] = inc;
+  }
+  __syncthreads();
+  if (wid < 8) { // warp c scans the 32 warp totals of class c
+    const int v = s_warp[wid][lane], inc = warp_incl_scan(v, lane);
+    s_warp[wid][lane] = inc - v;
+    if (lane == 31) s_base[wid] = inc; // class total
+  }
+  __syncthreads();
+  int base = 0;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    excl[c] += s_warp[c][wid] + base;
+    base += s_base[c];
+  }
+#pragma unroll
+  for (int j = 0; j < PER; j++) {
+    if (p0 + j >= n) break;
+    int q = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+      if (mine[j] == c) q = excl[c]++;
+    perm[w0 + q] = p0 + j;
+    slot[p0 + j] = w0 + q;
+  }
+}
+
 __global__ void __launch_bounds__(128) k_subm_nbr(GridView g, const int4 *coords, const int *p2id, int n, int f0, int f1, int f2, int *nbr, int *nValid,
-                                                  unsigned long long *tileMask) {
+                                                  unsigned long long *tileMask, const int *__restrict__ perm, int *__restrict__ outRow) {
   const int K = f0 * f1 * f2;
   __shared__ unsigned long long s_m[4];
   int cntv = 0;
   const long nPad = ((long)n + 127) / 128 * 128;
-  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < nPad; p += (long)gridDim.x * blockDim.x) {
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < nPad; p += (long)gridDim.x * blockDim.x) { // p = plan slot
     unsigned long long m = 0;
     if (p < n) {
-      const int id = p2id[p];
+      const int site = perm ? perm[p] : (int)p; // spatial index of the site in this slot
+      const int id = p2id[site];
+      if (outRow) outRow[p] = id;
       const int4 c = coords[id];
       int k = 0;
       for (int a = 0; a < f0; a++)
         for (int b = 0; b < f1; b++)
           for (int d = 0; d < f2; d++, k++) {
             int x = c.x - f0 / 2 + a, y = c.y - f1 / 2 + b, z = c.z - f2 / 2 + d;
-            int q = (x == c.x && y == c.y && z == c.z) ? (int)p : grid_lookup(g, x, y, z, c.w);
+            int q = (x == c.x && y == c.y && z == c.z) ? site : grid_lookup(g, x, y, z, c.w);
             int v = q >= 0 ? p2id[q] : -1;
             nbr[nbr_index(p, k, K)] = v;
             cntv += v >= 0;
@@ -957,19 +1031,22 @@ __global__ void __launch_bounds__(128) k_subm_nbr(GridView g, const int4 *coords
   if ((threadIdx.x & 31) == 0 && cntv) atomicAdd(nValid, cntv);
 }
 struct SubmMask {
-  const int *rank2id, *id2p, *nbr; int K;
+  const int *rank2id, *id2p, *nbr; int K; const int *slot;
   __device__ unsigned long long operator()(int r) const {
-    const long p = id2p[rank2id[r]];
+    long p = id2p[rank2id[r]];
+    if (slot) p = slot[p];
     unsigned long long m = 0;
     for (int k = 0; k < K; k++) m |= (unsigned long long)(nbr[nbr_index(p, k, K)] >= 0) << k;
     return m;
   }
 };
 struct SubmPair {
-  const int *rank2id, *id2p, *nbr; int K;
+  const int *rank2id, *id2p, *nbr; int K; const int *slot;
   __device__ int2 operator()(int r, int L) const {
     int id = rank2id[r];
-    return make_int2(nbr[nbr_index(id2p[id], L, K)], id); // (input row, output row)
+    long p = id2p[id];
+    if (slot) p = slot[p];
+    return make_int2(nbr[nbr_index(p, L, K)], id); // (input row, output row)
   }
 };
 
@@ -1008,7 +1085,21 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   SCN_CUDA(cudaMemsetAsync(cur().d_scalars, 0, 4, cur().stream));
   e.plan.tileMask = alloc_n<unsigned long long>(cdiv(std::max(g->n, 1), 128) + 8);
   SCN_CHECK(e.plan.tileMask, "alloc");
-  if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, cur().d_scalars, e.plan.tileMask);
+  static int sortOn = -1;
+  if (sortOn < 0) sortOn = getenv("SCN_PLAN_SORT") ? atoi(getenv("SCN_PLAN_SORT")) : 1;
+  int *perm = nullptr, *outRowSorted = nullptr;
+  if (sortOn && K > 1 && g->n >= kSortMinSites) { // sorted plan (see k_site_class)
+    unsigned char *cls = static_cast<unsigned char *>(alloc((size_t)g->n + 16));
+    perm = alloc_n<int>(g->n);
+    int *slot = alloc_n<int>(g->n);
+    outRowSorted = alloc_n<int>(g->n);
+    SCN_CHECK(cls && perm && slot && outRowSorted, "alloc");
+    k_site_class<<<stream_grid(g->n, 256, 8), 256, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], cls);
+    k_window_sort<<<cdiv(g->n, kSortWindow), 1024, 0, LS(cur().stream)>>>(cls, g->n, perm, slot);
+    e.plan.outRow = outRowSorted;
+    e.plan.slot = slot;
+  }
+  if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, cur().d_scalars, e.plan.tileMask, perm, outRowSorted);
   // The forward pass only needs the plan and the rule COUNT (the reference's multiply-add counter);
   // the per-offset (in,out) lists in the reference's hash-iteration order are materialised on demand
   // (ensure_subm_rules: backward pass, rulebook inspection).
@@ -1032,7 +1123,7 @@ int Metadata::ensure_subm_rules(SubmEntry &e) {
   SCN_TRY(need(e.rdy));
   SCN_TRY(ensure_rank(*g));
   const int K = e.plan.K;
-  SCN_TRY(build_rule_lists(*this, g->n, K, SubmMask{g->rank2id, g->id2p, e.plan.nbr, K}, SubmPair{g->rank2id, g->id2p, e.plan.nbr, K}, e.rb, 0));
+  SCN_TRY(build_rule_lists(*this, g->n, K, SubmMask{g->rank2id, g->id2p, e.plan.nbr, K, e.plan.slot}, SubmPair{g->rank2id, g->id2p, e.plan.nbr, K, e.plan.slot}, e.rb, 0));
   SCN_CHECK(e.plan.nValid == e.rb.total, "internal: rule count mismatch");
   return mark_ready(e.rulesRdy);
 }

@@ -64,6 +64,7 @@ struct NbrPlan {
   int nOut = 0;
   int *nbr = nullptr;         // [plan_padded(nOut)*K] input row ids at nbr_index(p, k, K), p = OUTPUT spatial index
   const int *outRow = nullptr; // p -> output row id (p2id of the output grid)
+  const int *slot = nullptr;  // optional: plan slot of spatial index p (sorted plans, get_submanifold); null = slot p
   long nValid = 0;            // number of non-negative entries (= rules)
   unsigned long long *tileMask = nullptr; // per 128-site tile: bit k set when some site of the tile has a neighbour at offset k
 };
@@ -204,6 +205,15 @@ struct GridView {
   long dirCells;
   int sz0, sz1, sz2;
 };
+// occupancy test only (no rank): is (x, y, z, b) an active site?
+__device__ __forceinline__ bool grid_has(const GridView &g, int x, int y, int z, int b) {
+  if ((unsigned)x >= (unsigned)g.sz0 || (unsigned)y >= (unsigned)g.sz1 || (unsigned)z >= (unsigned)g.sz2) return false;
+  long cell = (long)b * g.dirCells + ((long)(x >> 3) * g.dd1 + (y >> 3)) * g.dd2 + (z >> 3);
+  int blk = __ldg(g.dir + cell);
+  if (blk < 0) return false;
+  int bit = ((x & 7) << 6) | ((y & 7) << 3) | (z & 7);
+  return (__ldg(g.bmask + blk * 8 + (bit >> 6)) >> (bit & 63)) & 1ull;
+}
 // spatial index of an active site, or -1
 __device__ __forceinline__ int grid_lookup(const GridView &g, int x, int y, int z, int b) {
   if ((unsigned)x >= (unsigned)g.sz0 || (unsigned)y >= (unsigned)g.sz1 || (unsigned)z >= (unsigned)g.sz2) return -1;
