@@ -65,6 +65,7 @@ struct TcParams {
   int KG;     // packed layers (template G > 1): number of offset groups = ceil(K / G)
   int dbg;    // developer switches (SCN_TC_DBG): 1 = skip A gathers, 2 = skip B copies, 4 = skip MMAs
   int kSplit; // > 1: the filter offsets of a work item are split over kSplit CTAs, epilogue accumulates atomically
+  unsigned *sched; // dynamic work distribution: [0] next work item, [1] CTAs that have drawn their last item (self-resetting); null = static stride
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -209,6 +210,40 @@ __device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
   return I;
 }
 
+// ------------------------------------------------------------------ dynamic work distribution
+// Work items are handed out by a global counter instead of a static stride: a CTA that starts late (its SM was still running a
+// kernel of another stream -- the rulebook builds run beside the layers) or draws long items simply takes fewer of them, so the
+// launch ends when the work ends instead of when the unluckiest CTA ends.  One thread per CTA (the weight loader) draws the
+// items, one ahead of its own use, and publishes them to the other roles through a 4-slot ring in shared memory
+// (full / empty mbarriers): every role sees the same item sequence.
+constexpr int kSchedSlots = 4;
+struct Sched {
+  uint64_t *full, *empty; // [kSchedSlots]
+  volatile int *item;     // [kSchedSlots]
+};
+// consumer side: item number n of this CTA (or -1: no more work).  Called by whole warps or by a single thread.
+__device__ __forceinline__ int sched_take(const Sched &S, int n, bool arrive) {
+  const int slot = n & (kSchedSlots - 1);
+  mbar_wait(smem_u32(S.full + slot), (uint32_t)(n / kSchedSlots) & 1u);
+  const int wi = S.item[slot];
+  __syncwarp(__activemask());
+  if (arrive) mbar_arrive(smem_u32(S.empty + slot));
+  return wi;
+}
+// producer side (one thread)
+__device__ __forceinline__ int sched_draw(const TcParams &P, int nWork) {
+  const unsigned v = atomicAdd(P.sched, 1u);
+  if (v < (unsigned)nWork) return (int)v;
+  if (atomicAdd(P.sched + 1, 1u) == gridDim.x - 1) { P.sched[0] = 0u; P.sched[1] = 0u; } // every CTA draws exactly one item beyond the end: the last one resets the counters
+  return -1;
+}
+__device__ __forceinline__ void sched_publish(const Sched &S, int n, int wi) {
+  const int slot = n & (kSchedSlots - 1);
+  if (n >= kSchedSlots) mbar_wait(smem_u32(S.empty + slot), (uint32_t)(n / kSchedSlots - 1) & 1u);
+  S.item[slot] = wi;
+  mbar_arrive(smem_u32(S.full + slot)); // (mbarrier arrive has release semantics at CTA scope: the store above is visible to the waiters)
+}
+
 // ------------------------------------------------------------------ kernel
 // Launch bound 576 (> the 448 threads used) caps the kernel at 112 registers per thread: a resident
 // CTA then leaves ~15K registers and ~17 KB of shared memory per SM, enough for the short
@@ -216,8 +251,10 @@ __device__ __forceinline__ Item load_item(const TcParams &P, int wi) {
 // PW = producer warps: 8 with one CTA per SM (all 512 TMEM columns), 4 with two CTAs per SM (256
 // columns and half the shared memory each): two independent pipelines per SM hide each other's
 // barrier hand-offs.
-template <bool BF16, int PW, int G>
-__global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 320), PW == 8 ? 1 : 2) conv_plan_tc(const TcParams P) {
+// CTAS = CTAs per SM the variant is built for (register cap: 65536 / (CTAS x threads)): <PW 8, CTAS 2> caps the kernel at 72
+// registers (a few spilled words in the epilogue) and doubles the gather issue rate of the two-CTA configuration.
+template <bool BF16, int PW, int G, int CTAS>
+__global__ void __launch_bounds__(CTAS == 1 ? 576 : (PW == 8 ? 448 : (SCN_EPI_COLS == 16 ? 384 : 320)), CTAS) conv_plan_tc(const TcParams P) {
   constexpr int TM = G == 4 ? 2 : kMaxT; // tiles per item the producers keep neighbour ids for (G ids per row and tile)
   constexpr int kProdWarps = PW;
   constexpr int kRowsPerWarp = kTileM / PW; // rows of a tile one producer warp gathers
@@ -231,13 +268,16 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 32
   uint64_t *bars = reinterpret_cast<uint64_t *>(sEpi + kEpiBytes / 4);
   uint64_t *full = bars, *empty = bars + P.S, *accFull = bars + 2 * P.S, *accEmpty = accFull + 2;
   uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 2);
+  Sched SC{bars + 24, bars + 24 + kSchedSlots, reinterpret_cast<volatile int *>(bars + 24 + 2 * kSchedSlots)}; // (64 barrier words are reserved; 2 S + 5 <= 17 are used above)
+  const bool dyn = P.sched != nullptr;
 
   if (tid == 0) {
     for (int i = 0; i < P.S; i++) { mbar_init(smem_u32(full + i), kProdWarps * 32 + 1); mbar_init(smem_u32(empty + i), 1); }
     for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
+    for (int i = 0; i < kSchedSlots; i++) { mbar_init(smem_u32(SC.full + i), 1); mbar_init(smem_u32(SC.empty + i), 4 + kProdWarps + 1); } // takers: epilogue + producer warps + MMA warp (the loader keeps its own copy)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  constexpr int kMmaWarp = 4 + PW, kLoadWarp = 5 + PW;
+  constexpr int kMmaWarp = 4 + PW;
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"((uint32_t)P.tmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -260,8 +300,9 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 32
     float *stg = sEpi + warp * (32 * EC);
     const int cl = lane % LPR, cc = cl * 4, rsub = lane / LPR;
     float4 sAcc = make_float4(0.f, 0.f, 0.f, 0.f), qAcc = sAcc; // column sums of the EC-column block this lane group owns (block == rsub)
-    int it = 0;
-    for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
+    for (int it = 0;; it++) {
+      const int wi = dyn ? sched_take(SC, it, lane == 0) : (int)(blockIdx.x + (long)it * gridDim.x < nWork ? blockIdx.x + it * gridDim.x : -1);
+      if (wi < 0) break;
       const Item I = load_item<G>(P, wi);
       const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
       int myRow[kMaxT]; // output row of (tile t, TMEM lane), fetched before the accumulators are ready
@@ -383,7 +424,9 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 32
     const int pw = warp - 4;
     const int chunk = lane & 7, rsub = lane >> 3;
     uint32_t n = 0, slot = 0, round = 0; // stage counter, ring slot, ring round
-    for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
+    for (int itp = 0;; itp++) {
+      const int wi = dyn ? sched_take(SC, itp, lane == 0) : (int)(blockIdx.x + (long)itp * gridDim.x < nWork ? blockIdx.x + itp * gridDim.x : -1);
+      if (wi < 0) break;
       const Item I = load_item<G>(P, wi);
       if (!I.uni) continue;
       const int *idBase = P.nbr + ((size_t)I.st * P.T * P.K) * 128 + pw * kRowsPerWarp + (lane & (kRowsPerWarp - 1));
@@ -468,9 +511,10 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 32
       const uint32_t fmt = BF16 ? 1u : 2u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.Cout >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       uint32_t n = 0, slot = 0, round = 0;
-      int it = 0;
       const uint32_t sStage0 = smem_u32(sStage), full0 = smem_u32(full), empty0 = smem_u32(empty);
-      for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x, it++) {
+      for (int it = 0;; it++) {
+        const int wi = dyn ? sched_take(SC, it, lane == 0) : (int)(blockIdx.x + (long)it * gridDim.x < nWork ? blockIdx.x + it * gridDim.x : -1);
+        if (wi < 0) break;
         const Item I = load_item<G>(P, wi);
         const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
         mbar_wait_t(smem_u32(accEmpty + a), (use & 1) ^ 1, pw0, prof); // epilogue has drained this accumulator stage
@@ -523,7 +567,21 @@ __global__ void __launch_bounds__(PW == 8 ? 576 : (SCN_EPI_COLS == 16 ? 384 : 32
     // ============================ B loader ============================
     if (lane == 0) {
       uint32_t n = 0, slot = 0, round = 0;
-      for (int wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
+      // this thread also draws the work items (dynamic distribution): item itb is published before it is used here, item itb + 1
+      // is drawn while item itb is being loaded
+      int cur = 0, nxt = -1;
+      if (dyn) { cur = sched_draw(P, nWork); sched_publish(SC, 0, cur); nxt = cur >= 0 ? sched_draw(P, nWork) : -1; }
+      for (int itb = 0;; itb++) {
+        int wi;
+        if (dyn) {
+          if (cur < 0) break;
+          sched_publish(SC, itb + 1, nxt);
+          const int nn = nxt >= 0 ? sched_draw(P, nWork) : -1;
+          wi = cur; cur = nxt; nxt = nn;
+        } else {
+          if (blockIdx.x + (long)itb * gridDim.x >= nWork) break;
+          wi = blockIdx.x + itb * gridDim.x;
+        }
         const Item I = load_item<G>(P, wi);
         unsigned long long rest = I.uni;
         while (rest) {
@@ -725,6 +783,22 @@ static int stream_scratch(cudaStream_t s, int slot, size_t bytes, void **out) {
   *out = e.first;
   return 0;
 }
+// Work-item counters of the dynamic distribution: two zero-initialised words per (device, stream); launches on one stream are
+// ordered and every launch leaves them zeroed again (sched_draw).
+static int sched_counters(cudaStream_t s, unsigned **out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, unsigned *> cache;
+  int dev = 0;
+  SCN_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  unsigned *&e = cache[std::make_pair(dev, s)];
+  if (!e) {
+    SCN_CUDA(cudaMalloc((void **)&e, 64));
+    SCN_CUDA(cudaMemset(e, 0, 64));
+  }
+  *out = e;
+  return 0;
+}
 // Side channel used by the program executor (program.cu): the next tensor-core convolution launched by THIS thread
 // also accumulates the per-channel sum / sum of squares of its output into `sums` (zeroed by the caller) when its
 // configuration allows it; epilogue_stats_take() says whether it did and disarms the request.
@@ -834,7 +908,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   // atomic accumulation and a separate bf16 pass, and rules out the BatchNorm statistics in the epilogue; from a few dozen
   // items on, one CTA per item doing all offsets is as fast and needs one launch instead of three.
   static int kSplitMaxItems = -1;
-  if (kSplitMaxItems < 0) kSplitMaxItems = getenv("SCN_TC_SPLIT_MAX") ? atoi(getenv("SCN_TC_SPLIT_MAX")) : 24;
+  if (kSplitMaxItems < 0) kSplitMaxItems = getenv("SCN_TC_SPLIT_MAX") ? atoi(getenv("SCN_TC_SPLIT_MAX")) : 40;
   if (P.nSuper <= kSplitMaxItems && !tileW) P.kSplit = std::max(1, std::min(packG > 1 ? P.KG : K, kSMs * ctas / P.nSuper));
   P.stats = nullptr;
   if (tl_stats && P.kSplit == 1 && Cout <= kFusedStatsC && Cout % 32 == 0) { P.stats = tl_stats; tl_stats_done = true; ++g_counters[kCntEpilogueStats]; }
@@ -874,30 +948,44 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   tl_lat.in = nullptr;
   static bool attr = false;
   if (!attr) {
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (233472 - kBuildRoom) / 2 - 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (233472 - kBuildRoom) / 2 - 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (233472 - kBuildRoom) / 2 - 1024));
-    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (233472 - kBuildRoom) / 2 - 1024));
+    const int half = (233472 - kBuildRoom) / 2 - 1024;
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 8, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 8, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, half));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, half));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, half));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, half));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<false, 8, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, half));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 8, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, half));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 8, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, half));
+    SCN_CUDA(cudaFuncSetAttribute(conv_plan_tc<true, 8, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, half));
     attr = true;
   }
   static int envSms = -1;
   if (envSms < 0) envSms = getenv("SCN_TC_SMS") ? atoi(getenv("SCN_TC_SMS")) : kSMs;
   const int grid = std::min(P.nSuper * P.kSplit, std::min(kSMs, envSms) * ctas);
+  static int envDyn = -1;
+  if (envDyn < 0) envDyn = getenv("SCN_TC_DYNAMIC") ? atoi(getenv("SCN_TC_DYNAMIC")) : 0; // measured on B470: dominant layer 0.536 (dynamic) vs 0.545 ms (static), whole forward 5.0-5.1 vs 4.92 ms -> static stride stays the default
+  P.sched = nullptr;
+  if (envDyn && P.nSuper * P.kSplit > grid) SCN_TRY(sched_counters(s, &P.sched)); // (one item per CTA: nothing to balance)
   P.prof = nullptr;
   if (envProf) {
     SCN_CUDA(cudaMallocAsync((void **)&P.prof, 2 * kSMs * 32 * 8, s));
     SCN_CUDA(cudaMemsetAsync(P.prof, 0, 2 * kSMs * 32 * 8, s));
   }
-  if (packG == 2) conv_plan_tc<true, 4, 2><<<grid, 32 * 10, smem, LS(s)>>>(P);
-  else if (packG == 4) conv_plan_tc<true, 4, 4><<<grid, 32 * 10, smem, LS(s)>>>(P);
+  // producer warps of the two-CTA configuration: 4 (96 registers) or 8 (72 registers); bit 0 = packed layers, bit 1 = whole-atom layers
+  static int envPw8 = -1;
+  if (envPw8 < 0) envPw8 = getenv("SCN_TC_PW8") ? atoi(getenv("SCN_TC_PW8")) : 0;
+  const bool pw8 = ctas == 2 && ((packG > 1 && (envPw8 & 1)) || (packG == 1 && (envPw8 & 2)));
+  const int th2 = 32 * (pw8 ? 14 : 10);
+  if (packG == 2) { if (pw8) conv_plan_tc<true, 8, 2, 2><<<grid, th2, smem, LS(s)>>>(P); else conv_plan_tc<true, 4, 2, 2><<<grid, th2, smem, LS(s)>>>(P); }
+  else if (packG == 4) { if (pw8) conv_plan_tc<true, 8, 4, 2><<<grid, th2, smem, LS(s)>>>(P); else conv_plan_tc<true, 4, 4, 2><<<grid, th2, smem, LS(s)>>>(P); }
   else if (ctas == 2) {
-    if (P.bf16) conv_plan_tc<true, 4, 1><<<grid, 32 * 10, smem, LS(s)>>>(P);
-    else conv_plan_tc<false, 4, 1><<<grid, 32 * 10, smem, LS(s)>>>(P);
+    if (P.bf16) { if (pw8) conv_plan_tc<true, 8, 1, 2><<<grid, th2, smem, LS(s)>>>(P); else conv_plan_tc<true, 4, 1, 2><<<grid, th2, smem, LS(s)>>>(P); }
+    else { if (pw8) conv_plan_tc<false, 8, 1, 2><<<grid, th2, smem, LS(s)>>>(P); else conv_plan_tc<false, 4, 1, 2><<<grid, th2, smem, LS(s)>>>(P); }
   } else {
-    if (P.bf16) conv_plan_tc<true, 8, 1><<<grid, 32 * 14, smem, LS(s)>>>(P);
-    else conv_plan_tc<false, 8, 1><<<grid, 32 * 14, smem, LS(s)>>>(P);
+    if (P.bf16) conv_plan_tc<true, 8, 1, 1><<<grid, 32 * 14, smem, LS(s)>>>(P);
+    else conv_plan_tc<false, 8, 1, 1><<<grid, 32 * 14, smem, LS(s)>>>(P);
   }
   SCN_CUDA(cudaGetLastError());
   if (envProf) { // developer aid: mean stall cycles per role over the CTAs of this launch

@@ -949,18 +949,93 @@ __global__ void __launch_bounds__(256) k_site_class(GridView g, const int4 *__re
     cls[p] = (unsigned char)m;
   }
 }
+// 3x3x3 filters: the 27-bit neighbour mask of EVERY site of a 64-site occupancy word at once, by shifting occupancy words.
+// Bit i of a word = site (y, z) = (i >> 3, i & 7) of one x-slice of an 8x8x8 block; the neighbour at (dy, dz) of all 64 sites is
+// the word shifted by 8 dy + dz bits with the bits that cross the block border taken from the adjacent blocks' words.  One thread
+// per word: 27 directory / word loads for 64 sites instead of 26 probes (2 loads each) per site.  nmask[p] bit k = filter offset k.
+__device__ __forceinline__ unsigned long long shift_z(unsigned long long c, unsigned long long side, int dz) {
+  if (dz == 0) return c;
+  if (dz > 0) return ((c >> 1) & 0x7f7f7f7f7f7f7f7full) | ((side << 7) & 0x8080808080808080ull);
+  return ((c << 1) & 0xfefefefefefefefeull) | ((side >> 7) & 0x0101010101010101ull);
+}
+__global__ void __launch_bounds__(128) k_word_masks3(GridView g, const int4 *__restrict__ coords, const int *__restrict__ p2id, const int *__restrict__ nblocks,
+                                                     unsigned *__restrict__ nmask) {
+  const long nWords = (long)(*nblocks) * 8;
+  for (long w = blockIdx.x * (long)blockDim.x + threadIdx.x; w < nWords; w += (long)gridDim.x * blockDim.x) {
+    const unsigned long long W = g.bmask[w];
+    if (!W) continue;
+    const int p0 = g.wbase[w];
+    const int4 c0 = coords[p2id[p0]]; // any site of the word names its block
+    const int bx = c0.x >> 3, by = c0.y >> 3, bz = c0.z >> 3, xs = (int)(w & 7);
+    unsigned long long N[27];
+#pragma unroll
+    for (int a = -1; a <= 1; a++) {
+      const int xa = xs + a, bxa = bx + (xa < 0 ? -1 : (xa > 7 ? 1 : 0)), xsa = xa & 7;
+      unsigned long long B[3][3]; // occupancy words of x-slice xs + a in the 3 x 3 blocks around (by, bz)
+#pragma unroll
+      for (int jy = -1; jy <= 1; jy++)
+#pragma unroll
+        for (int jz = -1; jz <= 1; jz++) {
+          const int yy = by + jy, zz = bz + jz;
+          unsigned long long v = 0;
+          if ((unsigned)bxa < (unsigned)g.dd0 && (unsigned)yy < (unsigned)g.dd1 && (unsigned)zz < (unsigned)g.dd2) {
+            const int blk = __ldg(g.dir + (long)c0.w * g.dirCells + ((long)bxa * g.dd1 + yy) * g.dd2 + zz);
+            if (blk >= 0) v = __ldg(g.bmask + (long)blk * 8 + xsa);
+          }
+          B[jy + 1][jz + 1] = v;
+        }
+#pragma unroll
+      for (int dz = -1; dz <= 1; dz++) {
+        unsigned long long Z[3];
+#pragma unroll
+        for (int jy = 0; jy < 3; jy++) Z[jy] = shift_z(B[jy][1], B[jy][1 + (dz == 0 ? 0 : dz)], dz);
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++) {
+          unsigned long long S = dy == 0 ? Z[1] : (dy > 0 ? ((Z[1] >> 8) | (Z[2] << 56)) : ((Z[1] << 8) | (Z[0] >> 56)));
+          N[(a + 1) * 9 + (dy + 1) * 3 + (dz + 1)] = W & S;
+        }
+      }
+    }
+    int r = 0;
+    for (unsigned long long rest = W; rest; rest &= rest - 1, r++) {
+      const int i = __ffsll((long long)rest) - 1;
+      unsigned m = 0;
+#pragma unroll
+      for (int k = 0; k < 27; k++) m |= (unsigned)((N[k] >> i) & 1ull) << k;
+      nmask[p0 + r] = m;
+    }
+  }
+}
+constexpr unsigned kMaskX = 0x7fc01ffu;  // offsets with dx != 0: k < 9 or k >= 18
+constexpr unsigned kMaskY = 0x71f8fc7u;  // dy != 0: (k / 3) % 3 != 1
+constexpr unsigned kMaskZ = 0x5b6db6du;  // dz != 0: k % 3 != 1
+__global__ void __launch_bounds__(256) k_class_from_mask(const unsigned *__restrict__ nmask, int n, unsigned char *__restrict__ cls) {
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x) {
+    const unsigned m = nmask[p];
+    cls[p] = (unsigned char)(((m & kMaskX) ? 4 : 0) | ((m & kMaskY) ? 2 : 0) | ((m & kMaskZ) ? 1 : 0));
+  }
+}
 // stable counting sort of one window by class: perm[q] = p, slot[p] = q (both in [window start, window end))
 __global__ void __launch_bounds__(1024) k_window_sort(const unsigned char *__restrict__ cls, int n, int *__restrict__ perm, int *__restrict__ slot) {
   constexpr int PER = kSortWindow / 1024;
+  static_assert(PER == 16, "one 16-byte load per thread");
   __shared__ int s_warp[8][32];
   __shared__ int s_base[8];
   const int w0 = blockIdx.x * kSortWindow, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int p0 = w0 + tid * PER;
   unsigned char mine[PER];
   int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (p0 + PER <= n) { // (cls is 16-byte aligned and padded)
+    const uint4 v = *reinterpret_cast<const uint4 *>(cls + p0);
+    const unsigned q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < PER; j++) mine[j] = (unsigned char)(q[j >> 2] >> ((j & 3) * 8));
+  } else {
+#pragma unroll
+    for (int j = 0; j < PER; j++) mine[j] = p0 + j < n ? cls[p0 + j] : 255;
+  }
 #pragma unroll
   for (int j = 0; j < PER; j++) {
-    mine[j] = p0 + j < n ? cls[p0 + j] : 255;
 #pragma unroll
     for (int c = 0; c < 8; c++) cnt[c] += mine[j] == c;
   }
@@ -997,7 +1072,8 @@ __global__ void __launch_bounds__(1024) k_window_sort(const unsigned char *__res
 }
 
 __global__ void __launch_bounds__(128) k_subm_nbr(GridView g, const int4 *coords, const int *p2id, int n, int f0, int f1, int f2, int *nbr, int *nValid,
-                                                  unsigned long long *tileMask, const int *__restrict__ perm, int *__restrict__ outRow) {
+                                                  unsigned long long *tileMask, const int *__restrict__ perm, int *__restrict__ outRow,
+                                                  const unsigned *__restrict__ nmask) {
   const int K = f0 * f1 * f2;
   __shared__ unsigned long long s_m[4];
   int cntv = 0;
@@ -1009,12 +1085,13 @@ __global__ void __launch_bounds__(128) k_subm_nbr(GridView g, const int4 *coords
       const int id = p2id[site];
       if (outRow) outRow[p] = id;
       const int4 c = coords[id];
+      const unsigned long long have = nmask ? (unsigned long long)nmask[site] : ~0ull; // known-absent neighbours are not probed
       int k = 0;
       for (int a = 0; a < f0; a++)
         for (int b = 0; b < f1; b++)
           for (int d = 0; d < f2; d++, k++) {
             int x = c.x - f0 / 2 + a, y = c.y - f1 / 2 + b, z = c.z - f2 / 2 + d;
-            int q = (x == c.x && y == c.y && z == c.z) ? site : grid_lookup(g, x, y, z, c.w);
+            int q = (x == c.x && y == c.y && z == c.z) ? site : (((have >> k) & 1ull) ? grid_lookup(g, x, y, z, c.w) : -1);
             int v = q >= 0 ? p2id[q] : -1;
             nbr[nbr_index(p, k, K)] = v;
             cntv += v >= 0;
@@ -1088,18 +1165,25 @@ int Metadata::get_submanifold(const long *sz, const long *f, SubmEntry **out) {
   static int sortOn = -1;
   if (sortOn < 0) sortOn = getenv("SCN_PLAN_SORT") ? atoi(getenv("SCN_PLAN_SORT")) : 1;
   int *perm = nullptr, *outRowSorted = nullptr;
+  unsigned *nmask = nullptr;
   if (sortOn && K > 1 && g->n >= kSortMinSites) { // sorted plan (see k_site_class)
     unsigned char *cls = static_cast<unsigned char *>(alloc((size_t)g->n + 16));
     perm = alloc_n<int>(g->n);
     int *slot = alloc_n<int>(g->n);
     outRowSorted = alloc_n<int>(g->n);
     SCN_CHECK(cls && perm && slot && outRowSorted, "alloc");
-    k_site_class<<<stream_grid(g->n, 256, 8), 256, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], cls);
+    if (f[0] == 3 && f[1] == 3 && f[2] == 3) { // neighbour masks of all sites by word shifts; k_subm_nbr then probes present neighbours only
+      nmask = alloc_n<unsigned>(g->n);
+      SCN_CHECK(nmask, "alloc");
+      k_word_masks3<<<stream_grid(g->maxBlocks * 8, 128, 16), 128, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->d_nblocks, nmask);
+      k_class_from_mask<<<stream_grid(g->n, 256, 8), 256, 0, LS(cur().stream)>>>(nmask, g->n, cls);
+    } else
+      k_site_class<<<stream_grid(g->n, 256, 8), 256, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], cls);
     k_window_sort<<<cdiv(g->n, kSortWindow), 1024, 0, LS(cur().stream)>>>(cls, g->n, perm, slot);
     e.plan.outRow = outRowSorted;
     e.plan.slot = slot;
   }
-  if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, cur().d_scalars, e.plan.tileMask, perm, outRowSorted);
+  if (g->n) k_subm_nbr<<<stream_grid(g->n, 128, 16), 128, 0, LS(cur().stream)>>>(view(*g), g->coords, g->p2id, g->n, (int)f[0], (int)f[1], (int)f[2], e.plan.nbr, cur().d_scalars, e.plan.tileMask, perm, outRowSorted, nmask);
   // The forward pass only needs the plan and the rule COUNT (the reference's multiply-add counter);
   // the per-offset (in,out) lists in the reference's hash-iteration order are materialised on demand
   // (ensure_subm_rules: backward pass, rulebook inspection).

@@ -8,6 +8,7 @@
 #include "../../include/scn_b200.h"
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
 #include <array>
 #include <vector>
 
@@ -377,7 +378,8 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       for (int d = 0; d < 12; d++) h[1 + d] = o.a[2 + d];
       hints.insert(hints.end(), h, h + 13);
     }
-    if (batch == 1)
+    static const bool skipTwin = getenv("SCN_SKIP_TWIN") && atoi(getenv("SCN_SKIP_TWIN")); // developer timing experiment only: outputs stay in internal row order
+    if (batch == 1 && !skipTwin)
     SCN_TRY(scn_metadata_build_reference_grids(m, inOp->a + 1, coords, coords_on_device, nrows, ncols, (int)inOp->a[5], (int)inOp->a[4],
                                                (int)(hints.size() / 13), hints.data(), coords_on_device == 1 ? p->evCoords : nullptr));
     if (batch == 1) {
@@ -570,7 +572,8 @@ int scn_program_output_copy(scn_program *p, scn_metadata *m, int reg, const long
   SCN_CHECK(p && reg >= 0 && reg < p->nRegs && p->isOutput[reg], "not an output register");
   const Reg &R = p->regs[reg];
   if (R.rows == 0) return 0;
-  if (p->internal) return scn_rows_to_reference_order(m, p->ms, spatial_size, R.p, dst, R.cols);
+  static const bool skipTwin = getenv("SCN_SKIP_TWIN") && atoi(getenv("SCN_SKIP_TWIN"));
+  if (p->internal && !skipTwin) return scn_rows_to_reference_order(m, p->ms, spatial_size, R.p, dst, R.cols);
   return scn_copy_device(dst, R.p, R.rows * R.cols * 4, p->stream);
 }
 int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const float **ptr) {
