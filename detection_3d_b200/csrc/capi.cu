@@ -6,6 +6,7 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <map>
 #include <deque>
 #include <condition_variable>
 #include <chrono>
@@ -83,9 +84,11 @@ struct scn_metadata {
   // input-layer arguments of a job that starts with the input layer itself (kind 0, scn_metadata_build_reference_grids)
   long inSz[3] = {0, 0, 0}; const long *inCoords = nullptr; int inOnDevice = 0; long inRows = 0; int inCols = 0, inBatch = 0, inMode = 0;
   int device = 0;
+  std::map<scn::P3, scn::RuleBookDev> s2d; // SparseToDense rulebooks (parity / inspection only: the scatter kernel does not need them)
 };
 
 using scn::Metadata;
+namespace scn { Metadata *metadata_of(scn_metadata *m) { return &m->md; } } // for the translation units that only see the opaque handle
 
 #define M_OR_FAIL(m)                               \
   if (!(m)) {                                      \
@@ -451,7 +454,39 @@ int scn_convolution_prepare(scn_metadata *m, const long inS[3], const long outS[
   return 0;
 }
 
+// getSparseToDenseRuleBook (Metadata.cpp:469-483; ConvolutionRules.h:109-151): per batch item the pairs (row, spatial offset) of its
+// sites in hash-iteration order, offset = RectangularRegion::offset over the whole spatial size (last dimension fastest).
+__global__ void k_s2d_rules(const int *__restrict__ rank2id, const int4 *__restrict__ coords, int n, int sy, int sz, int2 *__restrict__ pairs) {
+  for (long r = blockIdx.x * (long)blockDim.x + threadIdx.x; r < n; r += (long)gridDim.x * blockDim.x) {
+    const int id = rank2id[r];
+    const int4 c = coords[id];
+    pairs[r] = make_int2(id, (c.x * sy + c.y) * sz + c.z);
+  }
+}
+static int s2d_rulebook(scn_metadata *m, const long a[3], scn::RuleBookDev **out) {
+  const scn::P3 key{a[0], a[1], a[2]};
+  auto it = m->s2d.find(key);
+  if (it != m->s2d.end()) { *out = &it->second; return 0; }
+  scn::Grid *g = m->md.find_grid(a);
+  SCN_CHECK(g, "no active sites recorded for this spatial size");
+  SCN_CHECK(a[0] * a[1] * a[2] < (1l << 31), "spatial volume exceeds the int32 rule format");
+  scn::Metadata::BuildLock bl(m->md);
+  SCN_TRY(m->md.ensure_rank(*g));
+  scn::RuleBookDev rb;
+  rb.nLists = g->batch;
+  rb.total = g->n;
+  rb.off.assign(1, 0);
+  for (int b = 0; b < g->batch; b++) rb.off.push_back(rb.off.back() + g->itemCount[b]);
+  rb.pairs = m->md.alloc_n<int2>(std::max(1, g->n));
+  SCN_CHECK(rb.pairs, "alloc");
+  cudaStream_t s = m->md.cur().stream;
+  if (g->n) k_s2d_rules<<<scn::stream_grid(g->n, 256), 256, 0, scn::LS(s)>>>(g->rank2id, g->coords, g->n, (int)a[1], (int)a[2], rb.pairs);
+  SCN_CUDA(cudaStreamSynchronize(s));
+  *out = &(m->s2d[key] = rb);
+  return 0;
+}
 static int find_rb(scn_metadata *m, int kind, const long a[3], const long b[3], const long c[3], scn::RuleBookDev **rb) {
+  if (kind == 3) return s2d_rulebook(m, a, rb);
   if (kind == 1) {
     scn::SubmEntry *e = nullptr;
     {

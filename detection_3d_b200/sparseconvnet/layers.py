@@ -138,6 +138,51 @@ class OutputLayerFunction(Function):
         return None, None, grad_input
 
 
+class SparseToDense(Module):
+    """SparseConvNetTensor -> dense [batch, nPlanes, X, Y, Z] (zeros at inactive sites).
+    reference: sparseconvnet/sparseToDense.py:25-78; used by layers/roi_align_rotated_3d.py:81 and tools_3d_2d.py."""
+
+    def __init__(self, dimension, nPlanes):
+        Module.__init__(self)
+        self.dimension = dimension
+        self.nPlanes = nPlanes
+
+    def forward(self, input):
+        return _run(SparseToDenseFunction, input.features, input.metadata, input.spatial_size, self.dimension, self.nPlanes)
+
+    def input_spatial_size(self, out_size):
+        return out_size
+
+    def __repr__(self):
+        return 'SparseToDense(' + str(self.dimension) + ',' + str(self.nPlanes) + ')'
+
+
+class SparseToDenseFunction(Function):
+    @staticmethod
+    def forward(ctx, input_features, input_metadata, spatial_size, dimension, nPlanes):
+        ctx.input_metadata = input_metadata
+        ctx.dimension = dimension
+        ctx.save_for_backward(input_features, spatial_size)
+        out = input_features.new()
+        native.SparseToDense_updateOutput(spatial_size, input_metadata, input_features.contiguous(), out, nPlanes)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input_features, spatial_size = ctx.saved_tensors
+        grad_input = grad_output.new()
+        native.SparseToDense_updateGradInput(spatial_size, ctx.input_metadata, input_features, grad_input, grad_output.contiguous())
+        return grad_input, None, None, None, None
+
+
+def sparse_3d_to_dense_2d(feat_s3d):
+    """reference: sparseconvnet/tools_3d_2d.py:7-48 -- densify and crop to the occupied extent [0:x_size, 0:y_size, 0:z_size]."""
+    loc = feat_s3d.get_spatial_locations()
+    x_size, y_size, z_size, _ = (loc.max(0)[0] + 1).tolist()
+    dense = SparseToDense(dimension=4, nPlanes=feat_s3d.features.shape[1])(feat_s3d)
+    return dense[:, :, 0:x_size, 0:y_size, 0:z_size]
+
+
 # ------------------------------------------------------------------------------- convolutions
 class SubmanifoldConvolution(Module):
     """reference: sparseconvnet/submanifoldConvolution.py:14-59"""

@@ -183,10 +183,39 @@ class Metadata_3(object):
         check(lib().scn_submanifold_prepare(self._h, l3(spatial_size), l3(filter_size), C.byref(n)))
         return [t.view(-1, 2) for t in self._rulebook(1, l3(spatial_size), l3(filter_size), l3([0, 0, 0]))]
 
+    def sparseToDenseRuleBook(self, spatial_size):
+        """one [n, 2] (row, spatial offset) list per batch item, hash-iteration order (Metadata.cpp:469-483)"""
+        z = l3([0, 0, 0])
+        return [t.view(-1, 2) for t in self._rulebook(3, l3(spatial_size), z, z)]
+
     def ruleBook(self, in_size, out_size, filter_size, filter_stride):
         n, r = C.c_long(), C.c_long()
         check(lib().scn_convolution_prepare(self._h, l3(in_size), l3(out_size), l3(filter_size), l3(filter_stride), C.byref(n), C.byref(r)))
         return [t.view(-1, 2) for t in self._rulebook(2, l3(in_size), l3(filter_size), l3(filter_stride))]
+
+
+# ------------------------------------------------------------------ SparseToDense
+def SparseToDense_updateOutput(spatial_size, m, input_features, output_features, nPlanes):
+    """pybind.cpp SparseToDense_updateOutput; CPU/SparseToDense.cpp:34-66 -> [batch, nPlanes, X, Y, Z], zero where inactive"""
+    sz = _ints(spatial_size)
+    b = C.c_int()
+    check(lib().scn_get_batch_size(m._h, l3(sz), C.byref(b)))
+    output_features.resize_(max(b.value, 1), int(nPlanes), *sz)
+    if input_features.dim() == 2:
+        check(lib().scn_sparse_to_dense_forward(m._h, l3(sz), _dev_f32(input_features, "in") if input_features.numel() else None,
+                                                _dev_f32(output_features, "out"), input_features.size(1)))
+    else:
+        output_features.zero_()
+
+
+def SparseToDense_updateGradInput(spatial_size, m, input_features, d_input_features, d_output_features):
+    """CPU/SparseToDense.cpp:67-101"""
+    d_input_features.resize_as_(input_features)
+    if input_features.dim() == 2 and input_features.numel():
+        check(lib().scn_sparse_to_dense_backward(m._h, l3(_ints(spatial_size)), _dev_f32(d_input_features, "d_in"), _dev_f32(d_output_features, "d_out"),
+                                                 input_features.size(1)))
+    else:
+        d_input_features.zero_()
 
 
 def n_rulebook_bits():

@@ -80,7 +80,8 @@ int scn_convolution_prepare(scn_metadata *m, const long in_size[3], const long o
                             const long filter_stride[3], long *n_active_out, long *n_rules);
 
 /* Rulebook access for parity checks (the reference keeps these as public members,
- * Metadata/Metadata.h:56-67).  kind 0 = input-layer table, 1 = submanifold, 2 = strided.
+ * Metadata/Metadata.h:56-67).  kind 0 = input-layer table, 1 = submanifold, 2 = strided, 3 = SparseToDense (a = spatial size;
+ * one list per batch item of (row, spatial offset) pairs in hash-iteration order, Metadata.cpp:469-483).
  * scn_rulebook_info fills n_lists and list_len[n_lists] (ints per list: 2*pairs; for kind 0:
  * list 0 = {mode,maxActive,nIn,nOut}, list 1 = nOut*(1+maxActive)).  scn_rulebook_copy copies
  * one list to HOST memory as the reference lays it out ((in,out) int32 pairs). */
@@ -206,6 +207,25 @@ int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const flo
 int scn_program_output_copy(scn_program *p, scn_metadata *m, int reg, const long spatial_size[3], float *dst);
 /* device-to-device copy on `stream` (hands an output register to a caller-owned tensor) */
 int scn_copy_device(void *dst, const void *src, long bytes, void *stream);
+
+/* SparseToDense_updateOutput / _updateGradInput (pybind.cpp: SparseToDense_*; CPU/SparseToDense.cpp:34-101): out = zero-filled
+ * [batch][n_planes][X][Y][Z] float32 with out[b][c][x][y][z] = in[row of the site][c]; d_in[row][c] = d_out[b][c][x][y][z]
+ * (every row of the grid is written).  Both run on the Metadata's compute stream. */
+int scn_sparse_to_dense_forward(scn_metadata *m, const long spatial_size[3], const float *in, float *out, int n_planes);
+int scn_sparse_to_dense_backward(scn_metadata *m, const long spatial_size[3], float *d_in, const float *d_out, int n_planes);
+
+/* ---- first consumers of the backbone's maps: the RPN head and its anchors.
+ * RPNHead.forward for ONE feature map (maskrcnn_benchmark/modeling/rpn/rpn_sparse3d.py:81-131): t = relu(conv(x)), logits =
+ * cls_logits(t), reg = bbox_pred(t); the three layers are 1x1 Conv2d on [1, C, n, 1] = GEMMs over the n feature rows.  Weights in
+ * Conv2d layout [out][in] (kernel 1x1), biases may be NULL.  logits [n][n_cls], reg [n][n_reg] -- the memory the reference's
+ * permute(0,2,1,3).reshape(1, n, A, sep) / (1, n, A, 7 sep) views.  One kernel, exact fp32. */
+int scn_rpn_head_forward(const float *feats, long n_rows, int n_planes, const float *w_conv, const float *b_conv, const float *w_cls, const float *b_cls,
+                         int n_cls, const float *w_reg, const float *b_reg, int n_reg, float *logits, float *reg, void *stream);
+/* AnchorGenerator.grid_anchors for one map (anchor_generator_sparse3d.py:88-104): anchors[(row * A + a)][7] =
+ * [loc_xyz / voxel_scale * stride, 0, 0, 0, 0] + base_anchors[a]; locations = DEVICE int64 [n][4] as scn_get_spatial_locations
+ * (out_on_device = 1) returns them, base_anchors = device float32 [A][7] (generate_anchors_3d, :213-250). */
+int scn_rpn_grid_anchors(const long *locations, long n_rows, float voxel_scale, const float stride[3], const float *base_anchors, int n_anchors, float *anchors,
+                         void *stream);
 
 /* Selects the arithmetic of the gather-GEMM kernels for this process: 0 = fp32 CUDA cores
  * (exact-fp32 anchor), 1 = tcgen05 tensor cores, TF32 inputs / fp32 accumulate (default where the

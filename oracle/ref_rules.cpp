@@ -65,7 +65,7 @@ long ref_md_batch_size(void *m_, const long *spatial) {
 }
 
 // kind 0: inputLayerRuleBook; 1: getSubmanifoldRuleBook(a=spatial, b=filter);
-// 2: getRuleBook(a=inSize, b=outSize, c=filter, d=stride).  Returns RuleBook*.
+// 2: getRuleBook(a=inSize, b=outSize, c=filter, d=stride); 3: getSparseToDenseRuleBook(a=spatial).  Returns RuleBook*.
 void *ref_md_rulebook(void *m_, int kind, const long *a, const long *b, const long *c,
                       const long *d, int openmp) {
   auto &m = *static_cast<Metadata<3> *>(m_);
@@ -73,6 +73,8 @@ void *ref_md_rulebook(void *m_, int kind, const long *a, const long *b, const lo
     return &m.inputLayerRuleBook;
   if (kind == 1)
     return &m.getSubmanifoldRuleBook(L3(a), L3(b), openmp != 0);
+  if (kind == 3) // getSparseToDenseRuleBook(a = spatial size), Metadata.cpp:469-483
+    return &m.getSparseToDenseRuleBook(L3(a), openmp != 0);
   return &m.getRuleBook(L3(a), L3(b), L3(c), L3(d), openmp != 0);
 }
 long ref_rb_nlists(void *rb) { return (long)static_cast<RuleBook *>(rb)->size(); }

@@ -154,6 +154,7 @@ typedef struct {
   RuleBook inputRules;            /* Metadata.h:56 */
   int nsub; long subkey[MAXRB][6]; RuleBook sub[MAXRB];   /* submanifoldRuleBooks */
   int nrb;  long rbkey[MAXRB][9];  RuleBook rb[MAXRB];    /* ruleBooks */
+  int ns2d; long s2dkey[MAXG][3]; RuleBook s2d[MAXG];      /* sparseToDenseRuleBooks */
 } OMeta;
 
 OMeta *omd_create(void) { return (OMeta *)calloc(1, sizeof(OMeta)); }
@@ -161,6 +162,7 @@ void omd_destroy(OMeta *m) {
   for (int i = 0; i < m->ngrids; i++) sgs_clear(&m->grids[i]);
   if (m->inputRules.nlists) rb_free(&m->inputRules);
   for (int i = 0; i < m->nsub; i++) rb_free(&m->sub[i]);
+  for (int i = 0; i < m->ns2d; i++) rb_free(&m->s2d[i]);
   for (int i = 0; i < m->nrb; i++) rb_free(&m->rb[i]);
   free(m);
 }
@@ -337,6 +339,45 @@ RuleBook *omd_conv_rules(OMeta *m, const long *inS, const long *outS, const long
   }
   m->nActive[gout] = out_n;
   return R;
+}
+
+/* getSparseToDenseRuleBook -> SparseToDense_InputSgsToRulesAndOutputSgs, Metadata/Metadata.cpp:469-483,
+ * ConvolutionRules.h:109-151: one list per batch item of (row = id + ctr, offset = RectangularRegion([0, size-1]).offset(point),
+ * last dimension fastest, RectangularRegions.h:30-38) in hash-iteration order. */
+RuleBook *omd_sparse_to_dense_rules(OMeta *m, const long *sz) {
+  for (int i = 0; i < m->ns2d; i++)
+    if (!memcmp(m->s2dkey[i], sz, 3 * sizeof(long))) return &m->s2d[i];
+  int ri = m->ns2d++;
+  memcpy(m->s2dkey[ri], sz, 3 * sizeof(long));
+  RuleBook *R = &m->s2d[ri];
+  SparseGrids *S = &m->grids[omd_grid(m, sz)];
+  rb_init(R, (int)S->size);
+  for (size_t gi = 0; gi < S->size; gi++) {
+    DHM *mp = &S->g[gi].mp; Int ctr = S->g[gi].ctr;
+    for (size_t b = 0; b < mp->nb; b++) {
+      if (dhm_is_empty(mp, b)) continue;
+      const Int *p = mp->k + 3 * b;
+      rb_push(R, (int)gi, mp->v[b] + ctr);
+      rb_push(R, (int)gi, (Int)(((long)p[0] * sz[1] + p[1]) * sz[2] + p[2]));
+    }
+  }
+  return R;
+}
+/* SparseToDense_ForwardPass / _BackwardPass, CPU/SparseToDense.cpp:7-31: rules = (row, offset) pairs of ONE batch item,
+ * out / d_out point at that item's [nPlanes][spatialVolume] block (caller zero-fills, :46). */
+void o_sparse_to_dense_forward(const float *in, float *out, long nPlanes, long spatialVolume, const Int *rules, long nHot) {
+  for (long s = 0; s < nHot; s++) {
+    const float *i = in + (long)rules[2 * s] * nPlanes;
+    float *o = out + rules[2 * s + 1];
+    for (long c = 0; c < nPlanes; c++) o[c * spatialVolume] = i[c];
+  }
+}
+void o_sparse_to_dense_backward(float *d_in, const float *d_out, long nPlanes, long spatialVolume, const Int *rules, long nHot) {
+  for (long s = 0; s < nHot; s++) {
+    float *di = d_in + (long)rules[2 * s] * nPlanes;
+    const float *o = d_out + rules[2 * s + 1];
+    for (long c = 0; c < nPlanes; c++) di[c] = o[c * spatialVolume];
+  }
 }
 
 RuleBook *omd_input_rules(OMeta *m) { return &m->inputRules; }

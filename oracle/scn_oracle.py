@@ -72,6 +72,10 @@ def olib():
         lib.omd_submanifold_rules.argtypes = [C.c_void_p, _L3, _L3]
         lib.omd_conv_rules.restype = C.c_void_p
         lib.omd_conv_rules.argtypes = [C.c_void_p, _L3, _L3, _L3, _L3]
+        lib.omd_sparse_to_dense_rules.restype = C.c_void_p
+        lib.omd_sparse_to_dense_rules.argtypes = [C.c_void_p, _L3]
+        lib.o_sparse_to_dense_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_long]
+        lib.o_sparse_to_dense_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_long]
         lib.omd_input_rules.restype = C.c_void_p
         lib.omd_input_rules.argtypes = [C.c_void_p]
         lib.orb_nlists.restype = C.c_long
@@ -188,6 +192,11 @@ class OracleMetadata:
         return _pairs(_lists(self.lib.orb_nlists, self.lib.orb_list_size, self.lib.orb_list_copy, rb))
 
 
+    def sparse_to_dense_rules(self, spatial):
+        rb = C.c_void_p(self.lib.omd_sparse_to_dense_rules(self.h, _l3(spatial)))
+        return _pairs(_lists(self.lib.orb_nlists, self.lib.orb_list_size, self.lib.orb_list_copy, rb))
+
+
 class RefMetadata:
     """The reference's own Metadata<3> (compiled from /root/reference, oracle/_ref)."""
 
@@ -240,6 +249,41 @@ class RefMetadata:
     def conv_rules(self, in_size, out_size, filt, stride):
         rb = self._rb(2, _l3(in_size), _l3(out_size), _l3(filt), _l3(stride))
         return _pairs(_lists(self.lib.ref_rb_nlists, self.lib.ref_rb_list_size, self.lib.ref_rb_list_copy, rb))
+
+
+def _ref_s2d(self, spatial):
+    rb = self._rb(3, _l3(spatial))
+    return _pairs(_lists(self.lib.ref_rb_nlists, self.lib.ref_rb_list_size, self.lib.ref_rb_list_copy, rb))
+
+
+RefMetadata.sparse_to_dense_rules = _ref_s2d
+
+
+def o_sparse_to_dense_forward(feats, rules, spatial, n_planes=None):
+    """cpu_SparseToDense_updateOutput (SCN/CPU/SparseToDense.cpp:34-66): [batch, nPlanes, X, Y, Z], zero-filled, one rule list
+    (row, offset) per batch item."""
+    feats = _f32(feats)
+    c = feats.shape[1] if n_planes is None else n_planes
+    vol = int(np.prod(spatial))
+    out = np.zeros((max(1, len(rules)), c) + tuple(int(v) for v in spatial), dtype=np.float32)
+    for b, r in enumerate(rules):
+        r = np.ascontiguousarray(r, dtype=np.int32)
+        if r.shape[0]:
+            olib().o_sparse_to_dense_forward(feats.ctypes.data, out[b].ctypes.data, feats.shape[1], vol, r.ctypes.data, r.shape[0])
+    return out
+
+
+def o_sparse_to_dense_backward(d_out, rules, n_rows):
+    """cpu_SparseToDense_updateGradInput (SCN/CPU/SparseToDense.cpp:67-101)."""
+    d_out = _f32(d_out)
+    c = d_out.shape[1]
+    vol = int(np.prod(d_out.shape[2:]))
+    d_in = np.zeros((n_rows, c), dtype=np.float32)
+    for b, r in enumerate(rules):
+        r = np.ascontiguousarray(r, dtype=np.int32)
+        if r.shape[0]:
+            olib().o_sparse_to_dense_backward(d_in.ctypes.data, d_out[b].ctypes.data, c, vol, r.ctypes.data, r.shape[0])
+    return d_in
 
 
 def point_hash(x, y, z):

@@ -8,6 +8,7 @@
                        returned map, and the multiply-add counter.
  * fpn_mini4_train.npz one training step of the reference's scn.FPN_Net (train-mode forward, loss, autograd backward):
                        parameter gradients and BatchNorm buffers.
+ * sparse_to_dense.npz scn.SparseToDense forward / backward and sparse_3d_to_dense_2d of the reference on a two-item batch.
  * rulebooks.json      sha1 digests of every grid / iteration order / rulebook of the reference's
                        own Metadata<3> (oracle/_ref/libscn_ref_rules.so) for three buildings,
                        including the full-size B470 building of BASELINE.json.
@@ -90,6 +91,28 @@ def run_reference_fpn_train(name="mini4"):
     print(name, "train: loss", float(out["loss"]), "params with grad", n_grad, "of", len(list(net.parameters())))
 
 
+def run_reference_sparse_to_dense():
+    """scn.SparseToDense forward + backward and tools_3d_2d.sparse_3d_to_dense_2d of the reference package on a two-item batch."""
+    scn = ref_python.load_reference_package()
+    rs = np.random.RandomState(21)
+    coords = np.concatenate([np.concatenate([rs.randint(0, [12, 14, 6], (300, 3)), np.zeros((300, 1), np.int64)], 1),
+                             np.concatenate([rs.randint(0, [9, 16, 8], (200, 3)), np.ones((200, 1), np.int64)], 1)]).astype(np.int64)
+    feats = rs.randn(coords.shape[0], 6).astype(np.float32)
+    inp = scn.InputLayer(3, torch.LongTensor([16, 16, 8]), mode=4)
+    f = torch.from_numpy(feats).requires_grad_(True)
+    x = inp([torch.from_numpy(coords), f])
+    dense = scn.SparseToDense(3, 6)(x)
+    w = torch.from_numpy(rs.randn(*dense.shape).astype(np.float32))
+    (dense * w).sum().backward()
+    sys.modules.setdefault("sparseconvnet", scn)
+    from sparseconvnet.tools_3d_2d import sparse_3d_to_dense_2d
+    crop = sparse_3d_to_dense_2d(x)
+    np.savez_compressed(os.path.join(HERE, "sparse_to_dense.npz"), coords=coords, feats=feats, dense=dense.detach().numpy(), w=w.numpy(),
+                        grad_feats=f.grad.numpy(), crop=crop.detach().numpy(), locations=x.get_spatial_locations().numpy(),
+                        rows=x.features.detach().numpy())
+    print("sparse_to_dense", tuple(dense.shape), tuple(crop.shape))
+
+
 def rulebook_digests():
     res = {}
     cases = {
@@ -139,3 +162,4 @@ if __name__ == "__main__":
     for name in CASES:
         run_reference_fpn(name)
     run_reference_fpn_train("mini4")
+    run_reference_sparse_to_dense()

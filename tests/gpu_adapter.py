@@ -42,3 +42,6 @@ class GpuMetadata:
 
     def conv_rules(self, in_sz, out_sz, f, s):
         return [t.numpy() for t in self.m.ruleBook(list(in_sz), list(out_sz), list(f), list(s))]
+
+    def sparse_to_dense_rules(self, sz):
+        return [t.numpy() for t in self.m.sparseToDenseRuleBook(list(sz))]

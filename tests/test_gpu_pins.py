@@ -437,3 +437,131 @@ def test_whole_network_training_step_vs_reference_autograd(math):
         ref = g["buf:" + k]
         np.testing.assert_allclose(b.cpu().numpy(), ref, rtol=tol, atol=tol * max(1e-3, float(np.abs(ref).max())), err_msg=k)
     print(f"[pin] training step {math}: worst gradient error {worst[1]:.3e} of max|grad| ({worst[0]})")
+
+
+# ------------------------------------------------------------------ next rows: RPN head + anchors, SparseToDense
+def test_rpn_head_and_anchors_vs_reference_golden():
+    """detection_3d_b200.rpn.RPNHead / AnchorGenerator (one CUDA kernel per map each) against the outputs of the reference's own
+    RPNHead.forward / AnchorGenerator.grid_anchors (tests/golden/rpn_sw4c_mid.npz) and against the CPU oracle on ragged sizes."""
+    from detection_3d_b200 import rpn
+    from oracle import rpn_oracle as ro
+    g = np.load(os.path.join(GOLD, "rpn_sw4c_mid.npz"))
+    f = np.load(os.path.join(GOLD, "fpn_sw4c_mid.npz"))
+    head = rpn.RPNHead(128, 4, 2)
+    head.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")})
+    head = head.cuda().eval()
+    gen = rpn.sw4c_anchor_generator()
+    n = int(g["n_maps"])
+    feats = [T(f[f"rpn{i}_features"]) for i in range(n)]
+    with torch.no_grad():
+        logits, regs = head([x.t().unsqueeze(0).unsqueeze(3) for x in feats])  # the reference's [1, C, n, 1] layout
+        logits2, _ = head(feats)                                               # plain rows
+        anchors = gen.grid_anchors([torch.from_numpy(f[f"rpn{i}_locations"].astype(np.int64)) for i in range(n)])
+    torch.cuda.synchronize()
+    for i in range(n):
+        assert tuple(logits[i].shape) == g[f"logits{i}"].shape and tuple(regs[i].shape) == g[f"reg{i}"].shape
+        np.testing.assert_allclose(logits[i].cpu().numpy(), g[f"logits{i}"], rtol=1e-4, atol=1e-6)  # fp32, summation order only
+        np.testing.assert_allclose(regs[i].cpu().numpy(), g[f"reg{i}"], rtol=1e-4, atol=1e-6)
+        assert torch.equal(logits[i], logits2[i])
+        assert np.array_equal(anchors[i].cpu().numpy(), g[f"anchors{i}"])  # bit exact
+    # ragged / edge shapes against the oracle: 1 row, a non-multiple of the row tile, 0 rows, other channel counts and group counts
+    rs = np.random.RandomState(5)
+    for rows, c, A, sep in [(1, 128, 4, 2), (13, 64, 2, 1), (0, 128, 4, 2), (777, 256, 3, 3)]:
+        h = rpn.RPNHead(c, A, sep).cuda()
+        with torch.no_grad():
+            for p_ in h.parameters():
+                p_.copy_(torch.from_numpy((rs.randn(*p_.shape) * 0.1).astype(np.float32)))
+        x = rs.randn(rows, c).astype(np.float32)
+        with torch.no_grad():
+            lg, rg = h([T(x)])
+        if rows == 0:  # (torch's conv2d -- what the reference runs -- rejects an empty map; ours returns empty outputs)
+            assert tuple(lg[0].shape) == (1, 0, A, sep) and tuple(rg[0].shape) == (1, 0, A, 7 * sep)
+            continue
+        sd = {k: v.detach().cpu().numpy() for k, v in h.state_dict().items()}
+        wl, wr = ro.rpn_head_forward(x, sd["conv.weight"], sd["conv.bias"], sd["cls_logits.weight"], sd["cls_logits.bias"], sd["bbox_pred.weight"],
+                                     sd["bbox_pred.bias"], A, sep)
+        assert tuple(lg[0].shape) == wl.shape and tuple(rg[0].shape) == wr.shape
+        if rows:
+            _close(lg[0].cpu().numpy(), wl, 1e-4, 1e-5)
+            _close(rg[0].cpu().numpy(), wr, 1e-4, 1e-5)
+
+
+def test_rpn_on_backbone_outputs_end_to_end():
+    """BASELINE.json config 3 up to the proposals' inputs: backbone (fp32 mode) -> RPN head + anchors on its four rpn maps with
+    device-resident locations, against the reference's outputs for the same building (golden): same rows, same order."""
+    scn = _scn()
+    from detection_3d_b200 import rpn
+    g = np.load(os.path.join(GOLD, "rpn_sw4c_mid.npz"))
+    cfg = scn.sw4c_fpn432_config()
+    try:
+        scn.set_math_mode("fp32")
+        net = scn.FPN_Net(**cfg)
+        net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+        net = net.cuda().eval()
+        head = rpn.RPNHead(128, 4, 2)
+        head.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")})
+        head = head.cuda().eval()
+        gen = rpn.sw4c_anchor_generator()
+        coords = synthetic.building_coords(nx=300, ny=280, nz=40, n_walls=5, seed=5)
+        with torch.no_grad():
+            rpn_maps, _ = net([torch.from_numpy(coords), torch.from_numpy(fpn_util.features_for(coords)).cuda()])
+            logits, regs = head([m.features for m in rpn_maps])
+            anchors, scopes = gen(None, rpn_maps)
+            obj, reg = rpn.cat_scales_obj_reg(logits, regs, scopes)
+        torch.cuda.synchronize()
+    finally:
+        scn.set_math_mode("fp32")
+    for i in range(4):
+        assert np.array_equal(anchors[i].cpu().numpy(), g[f"anchors{i}"])
+        _close(logits[i].cpu().numpy(), g[f"logits{i}"], 2e-3, 2e-4)  # backbone fp32 end-to-end tolerance carried through the head
+        _close(regs[i].cpu().numpy(), g[f"reg{i}"], 2e-3, 2e-4)
+    n_anchor = sum(a.shape[0] for a in anchors)
+    assert tuple(obj.shape) == (n_anchor, 2) and tuple(reg.shape) == (n_anchor, 14)
+    assert torch.equal(obj[:anchors[0].shape[0]], logits[0].reshape(-1, 2))
+
+
+@pytest.mark.parametrize("case", ["golden", "building", "big"])
+def test_sparse_to_dense_forward_backward(case):
+    """scn.SparseToDense (+ rulebook kind 3, bit exact) against the reference package's outputs (golden, two batch items) and the
+    CPU oracle; `big` = the level-4 roi map size of the B470 building ([128, 128, 32] x 128 planes)."""
+    scn = _scn()
+    g = np.load(os.path.join(GOLD, "sparse_to_dense.npz"))
+    rs = np.random.RandomState(3)
+    if case == "golden":
+        coords, feats, sz = g["coords"], g["feats"], [16, 16, 8]
+    elif case == "building":
+        coords = np.concatenate([synthetic.small_building(40, 36, 12, 3, seed=4), synthetic.small_building(30, 30, 10, 2, seed=5, batch_index=1)])
+        feats, sz = rs.randn(coords.shape[0], 20).astype(np.float32), [64, 64, 32]
+    else:
+        c0 = synthetic.building_coords()
+        coords = np.unique(np.concatenate([c0[:, :3] >> 4, c0[:, 3:]], 1), axis=0)
+        feats, sz = rs.randn(coords.shape[0], 128).astype(np.float32), [128, 128, 32]
+    inp = scn.InputLayer(3, sz, mode=4)
+    ft = T(feats).requires_grad_(True)
+    x = inp([torch.from_numpy(coords.astype(np.int64)), ft])
+    dense = scn.SparseToDense(3, feats.shape[1])(x)
+    O = so.OracleMetadata()
+    n = O.input_layer(sz, coords, 0, 4)
+    rules = O.sparse_to_dense_rules(sz)
+    got_rules = [t.numpy() for t in x.metadata.sparseToDenseRuleBook(sz)]
+    assert len(got_rules) == len(rules)
+    for a, b in zip(got_rules, rules):
+        assert np.array_equal(a, b)
+    want = so.o_sparse_to_dense_forward(x.features.detach().cpu().numpy(), rules, sz)
+    assert tuple(dense.shape) == want.shape
+    assert np.array_equal(dense.detach().cpu().numpy(), want)
+    w = rs.randn(*want.shape).astype(np.float32)
+    (dense * T(w)).sum().backward()
+    hdr, tab = O.input_rules()
+    want_g = so.o_input_layer_backward(so.o_sparse_to_dense_backward(w, rules, n), hdr, tab)
+    np.testing.assert_allclose(ft.grad.cpu().numpy(), want_g, rtol=1e-6, atol=1e-7)
+    crop = scn.sparse_3d_to_dense_2d(x)
+    ext = (coords[:, :3].max(0) + 1).tolist()
+    assert tuple(crop.shape[2:]) == tuple(ext)
+    if case == "golden":
+        # (the voxel means of the input layer differ from the CPU's in the last bit: fused multiply-add; the scatter itself is exact, above)
+        np.testing.assert_allclose(dense.detach().cpu().numpy(), g["dense"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(crop.detach().cpu().numpy(), g["crop"], rtol=1e-6, atol=1e-7)
+        dense2 = scn.SparseToDense(3, 6)(x)
+        (dense2 * T(g["w"])).sum().backward()  # (second backward accumulates: compare the increment)
+        np.testing.assert_allclose(ft.grad.cpu().numpy() - want_g, g["grad_feats"], rtol=1e-5, atol=1e-6)

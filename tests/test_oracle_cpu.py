@@ -231,3 +231,68 @@ def test_program_recorder_hoists_lateral_convolutions():
     assert kinds[1] == (1, 0, 1) and kinds[2] == (1, 1, 5), kinds  # the lateral now follows its producer
     rest = [o for o in out if o is not ops[5]]
     assert rest == ops[:5]                                          # relative order of the others unchanged
+
+
+# ------------------------------------------------------------------ next rows: RPN head / anchors, SparseToDense
+def test_rpn_oracle_vs_reference_golden():
+    """oracle/rpn_oracle.py against the outputs of the reference's own RPNHead / AnchorGenerator code
+    (tests/golden/rpn_sw4c_mid.npz, generated by tests/golden/make_golden_rpn.py from /root/reference)."""
+    from oracle import rpn_oracle as ro
+    g = np.load(os.path.join(GOLD, "rpn_sw4c_mid.npz"))
+    f = np.load(os.path.join(GOLD, "fpn_sw4c_mid.npz"))
+    sizes = [[0.4, 1.5, 1.5], [0.2, 0.5, 3], [0.4, 1.5, 3], [0.6, 2.5, 3]]
+    yaws = np.array((0, -1.57, -0.785, 0.785), np.float32).reshape(-1, 1)
+    ratios = np.array([[1, 1, 1], [1, 2, 1], [2, 1, 1], [1.7, 1.7, 1]], np.float32)
+    strides = [32, 16, 32, 64]
+    for i in range(int(g["n_maps"])):
+        lg, rg = ro.rpn_head_forward(f[f"rpn{i}_features"], g["w:conv.weight"], g["w:conv.bias"], g["w:cls_logits.weight"], g["w:cls_logits.bias"],
+                                     g["w:bbox_pred.weight"], g["w:bbox_pred.bias"], 4, 2)
+        assert lg.shape == g[f"logits{i}"].shape and rg.shape == g[f"reg{i}"].shape
+        np.testing.assert_allclose(lg, g[f"logits{i}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rg, g[f"reg{i}"], rtol=1e-5, atol=1e-6)
+        cell = ro.generate_anchors_3d(sizes[i], yaws, ratios, 1)
+        assert np.array_equal(cell, g[f"cell{i}"])
+        a = ro.grid_anchors(f[f"rpn{i}_locations"], cell, 50, [strides[i]] * 3)
+        assert np.array_equal(a, g[f"anchors{i}"])  # three separately rounded fp32 operations: bit exact
+    assert np.array_equal(ro.generate_anchors_3d([0.4, 1.5, 3], np.array([[0], [-1.57]], np.float32), np.array([[1, 1, 1], [1, 2, 1]], np.float32), 0), g["cell_ratio"])
+
+
+def test_rpn_module_mirrors_reference_parameters():
+    """detection_3d_b200.rpn.RPNHead keeps the reference's parameter names / shapes (checkpoint compatibility) and the anchor
+    generator its base anchors (host logic only: no GPU needed)."""
+    from detection_3d_b200 import rpn
+    g = np.load(os.path.join(GOLD, "rpn_sw4c_mid.npz"))
+    head = rpn.RPNHead(128, 4, 2)
+    want = {k[2:]: g[k].shape for k in g.files if k.startswith("w:")}
+    assert {k: tuple(v.shape) for k, v in head.state_dict().items()} == want
+    gen = rpn.sw4c_anchor_generator()
+    assert gen.num_anchors_per_location() == 4
+    for i in range(4):
+        assert np.array_equal(gen.cell_anchors[i].numpy(), g[f"cell{i}"])
+    import torch
+    assert rpn.examples_bidx_2_sizes(torch.tensor([0, 0, 0, 1, 1, 3])).tolist() == [[0, 3], [3, 5], [5, 5], [5, 6]]
+
+
+def test_sparse_to_dense_oracle_vs_reference_golden():
+    """C port of the SparseToDense rules + passes against the reference package's scn.SparseToDense (tests/golden/sparse_to_dense.npz)."""
+    g = np.load(os.path.join(GOLD, "sparse_to_dense.npz"))
+    O = so.OracleMetadata()
+    sz = [16, 16, 8]
+    n = O.input_layer(sz, g["coords"], 0, 4)
+    assert np.array_equal(O.spatial_locations(sz), g["locations"]) and n == g["rows"].shape[0]
+    hdr, tab = O.input_rules()
+    rows = so.o_input_layer_forward(g["feats"], hdr, tab)
+    np.testing.assert_allclose(rows, g["rows"], rtol=1e-6, atol=1e-7)
+    rules = O.sparse_to_dense_rules(sz)
+    assert len(rules) == 2 and sum(r.shape[0] for r in rules) == n
+    dense = so.o_sparse_to_dense_forward(g["rows"], rules, sz)
+    assert np.array_equal(dense, g["dense"])
+    d_rows = so.o_sparse_to_dense_backward(g["w"], rules, n)
+    np.testing.assert_allclose(so.o_input_layer_backward(d_rows, hdr, tab), g["grad_feats"], rtol=1e-6, atol=1e-7)
+    x_size, y_size, z_size = (g["locations"][:, :3].max(0) + 1).tolist()
+    assert np.array_equal(dense[:, :, :x_size, :y_size, :z_size], g["crop"])
+    if so.have_ref():
+        R = so.RefMetadata()
+        R.input_layer(sz, g["coords"], 0, 4)
+        for a, b in zip(rules, R.sparse_to_dense_rules(sz)):
+            assert np.array_equal(a, b)
