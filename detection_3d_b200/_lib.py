@@ -68,6 +68,8 @@ SYMBOLS = {
     "scn_sparse_to_dense_backward": (_i, [_vp, L3, _vp, _vp, _i]),
     "scn_rpn_head_forward": (_i, [_vp, _l, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "scn_rpn_grid_anchors": (_i, [_vp, _l, _f, C.POINTER(_f), _vp, _i, _vp, _vp]),
+    "scn_roi_align_rotated_3d_forward": (_i, [_vp, L3, _vp, _i, C.POINTER(_i), _vp, _l, _f, _i, _i, _i, _i, _vp]),
+    "scn_roi_align_rotated_3d_backward": (_i, [_vp, L3, _vp, _i, C.POINTER(_i), _vp, _l, _f, _i, _i, _i, _i, _vp]),
     "scn_set_math_mode": (_i, [_i]),
     "scn_get_math_mode": (_i, []),
     "scn_tensor_core_path_available": (_i, []),

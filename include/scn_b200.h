@@ -227,6 +227,17 @@ int scn_rpn_head_forward(const float *feats, long n_rows, int n_planes, const fl
 int scn_rpn_grid_anchors(const long *locations, long n_rows, float voxel_scale, const float stride[3], const float *base_anchors, int n_anchors, float *anchors,
                          void *stream);
 
+/* ROIAlignRotated3D on a SPARSE feature map: what maskrcnn_benchmark/layers/roi_align_rotated_3d.py:56-86
+ * computes by densifying the map (sparse_3d_to_dense_2d) and running csrc/cuda/ROIAlignRotated3D_cuda.cu:89-172 / :238-346 on it,
+ * evaluated straight from the sparse grid.  feats [nActive][n_planes]; extent = the occupied extent the reference crops the dense
+ * tensor to (max coordinate + 1 per dimension = its height, width, zsize); rois = device float32 [n_rois][8] (batch, center_w,
+ * center_h, center_z, w, h, z, theta in degrees); out [n_rois][n_planes][ph][pw][pz]; d_feats [nActive][n_planes] is overwritten
+ * (zero where no sample touches a site).  Both run on the Metadata's compute stream. */
+int scn_roi_align_rotated_3d_forward(scn_metadata *m, const long spatial_size[3], const float *feats, int n_planes, const int extent[3], const float *rois,
+                                     long n_rois, float spatial_scale, int pooled_h, int pooled_w, int pooled_z, int sampling_ratio, float *out);
+int scn_roi_align_rotated_3d_backward(scn_metadata *m, const long spatial_size[3], float *d_feats, int n_planes, const int extent[3], const float *rois,
+                                      long n_rois, float spatial_scale, int pooled_h, int pooled_w, int pooled_z, int sampling_ratio, const float *d_out);
+
 /* Selects the arithmetic of the gather-GEMM kernels for this process: 0 = fp32 CUDA cores
  * (exact-fp32 anchor), 1 = tcgen05 tensor cores, TF32 inputs / fp32 accumulate (default where the
  * channel counts allow), 2 = tcgen05 BF16 inputs / fp32 accumulate. */

@@ -20,6 +20,7 @@
  * sparsehash, not to a sparsehash binary.
  */
 #include <limits.h>
+
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -510,4 +511,72 @@ void o_bn_backward(const float *in, float *d_in, const float *out, float *d_out,
                               saveInvStd[c] * (weight ? weight[c] : 1);
   if (d_weight) for (long c = 0; c < nPlanes; c++) d_weight[c] = dp[c] * saveInvStd[c];
   free(gm); free(dp); free(k);
+}
+
+/* ----------------------------------------------------------- ROIAlignRotated3D (maskrcnn_benchmark/csrc/cuda/ROIAlignRotated3D_cuda.cu)
+ * Restatement of the reference's CUDA kernels as plain loops, T = float as in the only instantiation the reference uses:
+ * bilinear_interpolate :16-86, RoIAlignRotated3DForward :89-172, bilinear_interpolate_gradient :176-232,
+ * RoIAlignRotated3DBackwardFeature :235-346.  Checked against the reference's own kernels (compiled unmodified into
+ * oracle/_ref/libroialign3d_ref.so) by the GPU parity tests. */
+static float roi3d_interp(const float *d, int H, int W, int Z, float y, float x, float z) {
+  if (y < -1.0f || y > H || x < -1.0f || x > W || z < -1.0f) return 0.f; /* :27 (`zsize > zsize` never rejects) */
+  if (y <= 0) y = 0;
+  if (x <= 0) x = 0;
+  if (z <= 0) z = 0;
+  int yl = (int)y, xl = (int)x, zl = (int)z, yh, xh, zh;
+  if (yl >= H - 1) { yh = yl = H - 1; y = (float)yl; } else yh = yl + 1;
+  if (xl >= W - 1) { xh = xl = W - 1; x = (float)xl; } else xh = xl + 1;
+  if (zl >= Z - 1) { zh = zl = Z - 1; z = (float)zl; } else zh = zl + 1;
+  float ly = y - yl, lx = x - xl, lz = z - zl, hy = 1.f - ly, hx = 1.f - lx, hz = 1.f - lz;
+  float v1 = d[(yl * W + xl) * Z + zl], v2 = d[(yl * W + xh) * Z + zl], v3 = d[(yh * W + xl) * Z + zl], v4 = d[(yh * W + xh) * Z + zl];
+  float v5 = d[(yl * W + xl) * Z + zh], v6 = d[(yl * W + xh) * Z + zh], v7 = d[(yh * W + xl) * Z + zh], v8 = d[(yh * W + xh) * Z + zh];
+  float w1 = hy * hx * hz, w2 = hy * lx * hz, w3 = ly * hx * hz, w4 = ly * lx * hz, w5 = hy * hx * lz, w6 = hy * lx * lz, w7 = ly * hx * lz, w8 = ly * lx * lz;
+  return w1 * v1 + w2 * v2 + w3 * v3 + w4 * v4 + w5 * v5 + w6 * v6 + w7 * v7 + w8 * v8;
+}
+/* backward == 0: out[n][C][PH][PW][PZ] from input[B][C][H][W][Z];  backward != 0: d_input (zeroed by the caller) += from top_diff = out */
+void o_roi_align_rotated_3d(const float *input, float *d_input, long C, long H, long W, long Z, const float *rois, long n_rois, float scale, long PH, long PW,
+                            long PZ, long sampling, float *out, int backward) {
+  for (long n = 0; n < n_rois; n++) {
+    const float *r = rois + n * 8;
+    int bi = (int)r[0];
+    float cw = r[1] * scale, ch = r[2] * scale, cz = r[3] * scale, rw = r[4] * scale, rh = r[5] * scale, rz = r[6] * scale;
+    float theta = (float)(r[7] * 3.14159265358979323846 / 180.0);
+    rw = rw > 1.f ? rw : 1.f; rh = rh > 1.f ? rh : 1.f; rz = rz > 1.f ? rz : 1.f;
+    float bh = rh / (float)PH, bw = rw / (float)PW, bz = rz / (float)PZ;
+    int gh = sampling > 0 ? (int)sampling : (int)ceilf(rh / PH), gw = sampling > 0 ? (int)sampling : (int)ceilf(rw / PW), gz = sampling > 0 ? (int)sampling : (int)ceilf(rz / PZ);
+    float sh = -rh / 2.0f, sw = -rw / 2.0f, sz = -rz / 2.0f, cosT = cosf(theta), sinT = sinf(theta), count = (float)(gh * gw * gz);
+    for (long c = 0; c < C; c++) {
+      const float *d = input ? input + ((long)bi * C + c) * H * W * Z : NULL;
+      float *dd = d_input ? d_input + ((long)bi * C + c) * H * W * Z : NULL;
+      for (long ph = 0; ph < PH; ph++) for (long pw = 0; pw < PW; pw++) for (long pz = 0; pz < PZ; pz++) {
+        float *o = out + (((n * C + c) * PH + ph) * PW + pw) * PZ + pz;
+        float val = 0.f;
+        for (int iy = 0; iy < gh; iy++) {
+          float yy = sh + ph * bh + (iy + .5f) * bh / (float)gh;
+          for (int ix = 0; ix < gw; ix++) {
+            float xx = sw + pw * bw + (ix + .5f) * bw / (float)gw;
+            for (int iz = 0; iz < gz; iz++) {
+              float zz = sz + pz * bz + (iz + .5f) * bz / (float)gz;
+              float x = xx * cosT + yy * sinT + cw, y = yy * cosT - xx * sinT + ch, z = zz + cz;
+              if (!backward) { val += roi3d_interp(d, (int)H, (int)W, (int)Z, y, x, z); continue; }
+              if (y < -1.0f || y > H || x < -1.0f || x > W || z < -1.0f || z > Z) continue; /* :184 (the gradient variant does test z > zsize) */
+              if (y <= 0) y = 0;
+              if (x <= 0) x = 0;
+              if (z <= 0) z = 0;
+              int yl = (int)y, xl = (int)x, zl = (int)z, yh, xh, zh;
+              if (yl >= H - 1) { yh = yl = (int)H - 1; y = (float)yl; } else yh = yl + 1;
+              if (xl >= W - 1) { xh = xl = (int)W - 1; x = (float)xl; } else xh = xl + 1;
+              if (zl >= Z - 1) { zh = zl = (int)Z - 1; z = (float)zl; } else zh = zl + 1;
+              float ly = y - yl, lx = x - xl, lz = z - zl, hy = 1.f - ly, hx = 1.f - lx, hz = 1.f - lz, t = *o;
+              dd[(yl * W + xl) * Z + zl] += t * (hy * hx * hz) / count; dd[(yl * W + xh) * Z + zl] += t * (hy * lx * hz) / count;
+              dd[(yh * W + xl) * Z + zl] += t * (ly * hx * hz) / count; dd[(yh * W + xh) * Z + zl] += t * (ly * lx * hz) / count;
+              dd[(yl * W + xl) * Z + zh] += t * (hy * hx * lz) / count; dd[(yl * W + xh) * Z + zh] += t * (hy * lx * lz) / count;
+              dd[(yh * W + xl) * Z + zh] += t * (ly * hx * lz) / count; dd[(yh * W + xh) * Z + zh] += t * (ly * lx * lz) / count;
+            }
+          }
+        }
+        if (!backward) *o = val / count;
+      }
+    }
+  }
 }

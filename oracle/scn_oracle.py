@@ -76,6 +76,8 @@ def olib():
         lib.omd_sparse_to_dense_rules.argtypes = [C.c_void_p, _L3]
         lib.o_sparse_to_dense_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_long]
         lib.o_sparse_to_dense_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_void_p, C.c_long]
+        lib.o_roi_align_rotated_3d.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_long, C.c_float, C.c_long, C.c_long,
+                                               C.c_long, C.c_long, C.c_void_p, C.c_int]
         lib.omd_input_rules.restype = C.c_void_p
         lib.omd_input_rules.argtypes = [C.c_void_p]
         lib.orb_nlists.restype = C.c_long
@@ -284,6 +286,46 @@ def o_sparse_to_dense_backward(d_out, rules, n_rows):
         if r.shape[0]:
             olib().o_sparse_to_dense_backward(d_in.ctypes.data, d_out[b].ctypes.data, c, vol, r.ctypes.data, r.shape[0])
     return d_in
+
+
+def o_roi_align_rotated_3d_forward(dense, rois, scale, pooled, sampling):
+    """RoIAlignRotated3DForward (maskrcnn_benchmark/csrc/cuda/ROIAlignRotated3D_cuda.cu:89-172) on a dense [B, C, H, W, Z] input;
+    rois [n, 8] = (batch, center_w, center_h, center_z, w, h, z, theta in degrees).  -> [n, C, ph, pw, pz]."""
+    dense, rois = _f32(dense), _f32(rois)
+    _, c, h, w, z = dense.shape
+    out = np.zeros((rois.shape[0], c) + tuple(pooled), dtype=np.float32)
+    olib().o_roi_align_rotated_3d(dense.ctypes.data, None, c, h, w, z, rois.ctypes.data, rois.shape[0], scale, pooled[0], pooled[1], pooled[2], sampling,
+                                  out.ctypes.data, 0)
+    return out
+
+
+def o_roi_align_rotated_3d_backward(grad, rois, scale, pooled, sampling, dense_shape):
+    """RoIAlignRotated3DBackwardFeature (:235-346) -> d_input [B, C, H, W, Z]."""
+    grad, rois = _f32(grad), _f32(rois)
+    b, c, h, w, z = dense_shape
+    d = np.zeros(dense_shape, dtype=np.float32)
+    olib().o_roi_align_rotated_3d(None, d.ctypes.data, c, h, w, z, rois.ctypes.data, rois.shape[0], scale, pooled[0], pooled[1], pooled[2], sampling,
+                                  grad.ctypes.data, 1)
+    return d
+
+
+_roi_ref = None
+
+
+def roi_align_ref_lib():
+    """The reference's own ROIAlignRotated3D CUDA kernels (oracle/_ref/libroialign3d_ref.so, built by `make -C oracle ref`); GPU box only."""
+    global _roi_ref
+    if _roi_ref is None:
+        path = os.path.join(HERE, "_ref", "libroialign3d_ref.so")
+        if not os.path.exists(path):
+            return None
+        import torch  # noqa: F401  (libtorch must be loaded first)
+        lib = C.CDLL(path)
+        vp, l, f, i = C.c_void_p, C.c_long, C.c_float, C.c_int
+        lib.ref_roi_align_rotated_3d_forward.argtypes = [vp, l, l, l, l, l, vp, l, f, i, i, i, i, vp]
+        lib.ref_roi_align_rotated_3d_backward.argtypes = [vp, vp, l, f, i, i, i, l, l, l, l, l, i, vp]
+        _roi_ref = lib
+    return _roi_ref
 
 
 def point_hash(x, y, z):
