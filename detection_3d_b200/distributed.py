@@ -102,6 +102,92 @@ def allreduce_gradients(params, group=None, bucket_bytes=64 << 20, average=True)
     return len(buckets)
 
 
+class GradientReducer(object):
+    """Data-parallel gradient all-reduce overlapped with the backward pass ("bucketed to overlap with
+    backward"; the reference wraps the model in DistributedDataParallel, tools/train_net_sparse3d.py:52-58).
+
+    * ONE persistent flat fp32 buffer holds every gradient; each `p.grad` is a view into it (autograd accumulates in place), so
+      there is no packing or unpacking and no allocation per step -- `zero()` is one memset.
+    * The buffer is cut into buckets in REVERSE parameter order (the order in which the backward pass finishes them).  A bucket
+      is all-reduced asynchronously as soon as every LIVE parameter in it has received its gradient (post-accumulate hooks);
+      the collective runs on NCCL's own stream while the backward kernels of the earlier layers keep the SMs busy.
+    * Parameters that never receive a gradient (the dead top-down levels, App. D.2) are learnt in the first step (`calibrate`):
+      they stay zero in the buffer and never hold a bucket back; every rank reduces the same flat layout regardless.
+    `finish()` launches what is left, waits for all collectives and divides by the world size."""
+
+    def __init__(self, params, bucket_bytes=24 << 20, group=None, average=True):
+        self.params = [p for p in params if p.requires_grad]
+        self.group, self.average = group, average
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        order = list(reversed(self.params))
+        self.slices, self.bucket_of, self.buckets = {}, {}, []   # param -> (lo, hi); param -> bucket index; bucket -> (lo, hi)
+        off, cur_lo, cur_bytes = 0, 0, 0
+        for p in order:
+            n = p.numel()
+            if cur_bytes and cur_bytes + n * 4 > bucket_bytes:
+                self.buckets.append((cur_lo, off))
+                cur_lo, cur_bytes = off, 0
+            self.slices[p] = (off, off + n)
+            self.bucket_of[p] = len(self.buckets)
+            off += n
+            cur_bytes += n * 4
+        self.buckets.append((cur_lo, off))
+        self.live = None            # set of parameters that receive gradients (after the first step)
+        self.pending, self.seen, self.handles, self.launched = [], set(), [], set()
+        for p in self.params:
+            lo, hi = self.slices[p]
+            p.grad = self.flat[lo:hi].view_as(p)
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    def zero(self):
+        """Start of a step: gradients to zero (one memset), bucket bookkeeping reset."""
+        self.flat.zero_()
+        for p in self.params:  # (an optimizer / zero_grad(set_to_none=True) may have dropped the views)
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + self.slices[p][0] * 4:
+                lo, hi = self.slices[p]
+                p.grad = self.flat[lo:hi].view_as(p)
+        self.seen, self.handles, self.launched = set(), [], set()
+        if self.live is not None:
+            self.pending = [sum(1 for p in self.params if self.bucket_of[p] == b and p in self.live) for b in range(len(self.buckets))]
+
+    def _launch(self, b):
+        if b in self.launched or self.world == 1:
+            self.launched.add(b)
+            return
+        lo, hi = self.buckets[b]
+        self.handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.launched.add(b)
+
+    def _hook(self, p):
+        self.seen.add(p)
+        if self.live is None or p not in self.live:
+            return
+        b = self.bucket_of[p]
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            self._launch(b)
+
+    def finish(self):
+        """After backward: launch the buckets that did not complete on their own (first step, buckets without live
+        parameters), wait, average.  Returns the number of collectives of this step."""
+        if self.live is None:
+            self.live = set(self.seen)
+        for b in range(len(self.buckets)):
+            self._launch(b)
+        for h in self.handles:
+            h.wait()
+        n = len(self.handles)
+        if self.average and self.world > 1:
+            self.flat.div_(self.world)
+        return n
+
+    def nbytes(self):
+        return self.flat.numel() * 4
+
+
 def max_over_ranks_ms(ms, device, group=None):
     """Device-timed milliseconds -> max over ranks (how every multi-GPU number of bench.py is taken)."""
     t = torch.tensor([float(ms)], dtype=torch.float64, device=device)

@@ -69,6 +69,38 @@ def _worker(rank, world, port, ret):
         assert torch.allclose(ps[1].grad, torch.arange(5, dtype=torch.float32) / 2.0)  # zeros from rank 1
         assert ps[2].grad is not None and torch.count_nonzero(ps[2].grad) == 0
         assert torch.allclose(ps[3].grad, torch.full((1000,), 1.0))
+        # ---- overlapped reducer: gradients are views of one flat buffer, buckets fire from hooks, dead parameters stay zero
+        torch.manual_seed(1)
+        lin = [torch.nn.Linear(6, 6) for _ in range(4)]
+        dead = torch.nn.Parameter(torch.ones(50))  # never used: no gradient on any rank
+        params = [q for l in lin for q in l.parameters()] + [dead]
+        for q in params:
+            dist.broadcast(q.data, 0)
+        red = D.GradientReducer(params, bucket_bytes=200)
+        assert len(red.buckets) >= 3
+        for step in range(3):
+            red.zero()
+            x = torch.full((2, 6), float(rank + 1 + step))
+            y = x
+            for l in lin:
+                y = torch.tanh(l(y))
+            y.sum().backward()
+            n_coll = red.finish()
+            assert n_coll == len(red.buckets)
+            # reference: the same computation for both ranks' inputs, averaged
+            want = []
+            for r in range(world):
+                ps2 = [q.detach().clone().requires_grad_(True) for q in params[:-1]]
+                yy = torch.full((2, 6), float(r + 1 + step))
+                for k in range(4):
+                    yy = torch.tanh(torch.nn.functional.linear(yy, ps2[2 * k], ps2[2 * k + 1]))
+                want.append(torch.autograd.grad(yy.sum(), ps2))
+            for k, q in enumerate(params[:-1]):
+                assert q.grad.data_ptr() == red.flat.data_ptr() + red.slices[q][0] * 4  # still a view of the flat buffer
+                assert torch.allclose(q.grad, (want[0][k] + want[1][k]) / 2, atol=1e-6), (step, k)
+            assert torch.count_nonzero(dead.grad) == 0
+            if step > 0:
+                assert dead not in red.live and len(red.live) == 8
         # ---- timing helper: max over ranks
         assert D.max_over_ranks_ms(10.0 + rank, torch.device("cpu")) == 10.0 + world - 1
         ret[rank] = "ok"
