@@ -630,7 +630,9 @@ def dominant_kernel_roofline(scn, torch, dev, coords_dev, flush, pk, math):
     # bytes the gathers pull through L2 (every rule fetches one input row) -- what actually bounds the kernel
     gather_bytes = DOM_RULES * DOM_C * esz
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_dominant_kernel_dram_bytes.json")
+    tp = os.path.join(ROOT, "profiles", "r2_dominant_kernel_dram_bytes.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r1_dominant_kernel_dram_bytes.json")
     if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch
         traffic = json.load(open(tp)).get(math)
     return {"kernel": "conv_plan_tc (SubmanifoldConvolution 128->128 3^3, level 0: m_mergeds.7)", "bound": "tensor", "achieved": achieved,
