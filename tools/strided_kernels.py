@@ -54,14 +54,14 @@ elif a.what == "deconv":  # m_ups.7 + m_shortcuts.0 folded in: Deconvolution 2^3
     y16 = y.to(torch.bfloat16)
     wl = torch.randn(32, 128, device="cuda") * 0.05
     out = torch.empty(n0, 128, device="cuda")
-    macs = C.c_double()
+    macs_c = C.c_double()
 
     def run():
         check(lib().scn_fuse_next_lateral(p(y), p(y16), p(wl), 0, 32, n0))
-        check(lib().scn_deconvolution_forward(md._h, l3(half), l3(full), l3([2] * 3), l3([2] * 3), p(x), p(out), p(w), None, 128, 128, C.byref(macs),
+        check(lib().scn_deconvolution_forward(md._h, l3(half), l3(full), l3([2] * 3), l3([2] * 3), p(x), p(out), p(w), None, 128, 128, C.byref(macs_c),
                                               p(x._scn_bf16[0]) if a.math == "bf16" else None, 0, None, None))
         lib().scn_fuse_result(None, None)
-        return macs.value + n0 * 32 * 128
+        return macs_c.value + n0 * 32 * 128
     bytes_alg = lambda: n1 * 128 * 2 + n0 * 32 * 2 + n0 * 128 * 4 + n0 * 4 * 2
 else:                     # weight gradient of SubmanifoldConvolution 128 -> 128, 3^3, level 0 (conv_dw_tc in bf16 mode)
     x = torch.randn(n0, 128, device="cuda")
