@@ -36,6 +36,8 @@ SYMBOLS = {
     "scn_metadata_wait_jobs": (_i, [_vp]),
     "scn_rows_to_reference_order": (_i, [_vp, _vp, L3, _vp, _vp, _i]),
     "scn_program_output_copy": (_i, [_vp, _vp, _i, L3, _vp]),
+    "scn_program_outputs_copy": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "scn_rows_to_reference_order_multi": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "scn_set_pool_growth": (_i, [_i]),
     "scn_input_layer_built": (_i, [_vp, _pl, _pi]),
     "scn_copy_device": (_i, [_vp, _vp, _l, _vp]),
@@ -70,6 +72,12 @@ SYMBOLS = {
     "scn_rpn_grid_anchors": (_i, [_vp, _l, _f, C.POINTER(_f), _vp, _i, _vp, _vp]),
     "scn_roi_align_rotated_3d_forward": (_i, [_vp, L3, _vp, _i, C.POINTER(_i), _vp, _l, _f, _i, _i, _i, _i, _vp]),
     "scn_roi_align_rotated_3d_backward": (_i, [_vp, L3, _vp, _i, C.POINTER(_i), _vp, _l, _f, _i, _i, _i, _i, _vp]),
+    "scn_top_k_descending": (_i, [_vp, _l, _i, _l, _vp, _vp, _vp]),
+    "scn_box_decode_3d": (_i, [_vp, _vp, _vp, _l, C.POINTER(_f), _f, _i, _vp, _vp]),
+    "scn_boxes_iou_3d": (_i, [_vp, _l, _vp, _l, C.POINTER(_f), _i, _i, _vp, _vp]),
+    "scn_rotate_nms_3d": (_i, [_vp, _vp, _l, _l, _l, _f, _vp, _vp, _vp]),
+    "scn_voxelize_extent": (_i, [_vp, _l, _pd, _pd, _pd, _vp]),
+    "scn_voxelize": (_i, [_vp, _vp, _l, _i, _pd, _pd, _d, _pd, _i, _l, _i, _vp, _vp, _pl, _vp]),
     "scn_set_math_mode": (_i, [_i]),
     "scn_get_math_mode": (_i, []),
     "scn_tensor_core_path_available": (_i, []),

@@ -88,7 +88,11 @@ struct scn_metadata {
 };
 
 using scn::Metadata;
-namespace scn { Metadata *metadata_of(scn_metadata *m) { return &m->md; } } // for the translation units that only see the opaque handle
+namespace scn {
+Metadata *metadata_of(scn_metadata *m) { return &m->md; }
+int build_subm_on_caller(Metadata &md, const long *sz, const long *f);
+int build_subm_on_caller(scn_metadata *m, const long *sz, const long *f) { return m ? build_subm_on_caller(m->md, sz, f) : -3; }
+} // for the translation units that only see the opaque handle
 
 #define M_OR_FAIL(m)                               \
   if (!(m)) {                                      \
@@ -252,6 +256,21 @@ int scn_metadata_prefetch(scn_metadata *m, int n_ops, const long *ops) {
   // shallow ones -- buildable long before -- queue behind them.
   // Submanifold plans first (the bottom-up pass needs them level by level, as the chain worker descends), then what the
   // top-down pass and the z-collapsing convolutions need, deepest level first -- the order in which the network uses them.
+  static const bool interleave = !(getenv("SCN_DECONV_EARLY") && atoi(getenv("SCN_DECONV_EARLY")) == 0);
+  if (interleave) {
+    // A deconvolution plan (coarse -> fine) becomes buildable together with the submanifold plans of its COARSE grid (the chain
+    // worker has built the convolution fine -> coarse by then): it is built right behind them, while this worker would
+    // otherwise idle until the next level's grid exists.  Taken after ALL submanifold plans (deepest first), the plans of
+    // the large levels were finished last and the top-down pass waited for them (two ~50 us stalls on the caller's stream).
+    std::stable_sort(m->ops2.begin(), m->ops2.end(), [](const PrefetchOp &x, const PrefetchOp &y) {
+      auto cls = [](const PrefetchOp &o) { return o.v[0] == 2 ? 1 : 0; };               // leaf convolutions (z-collapse) last
+      auto level = [](const PrefetchOp &o) { return o.v[1]; };                             // subm: its grid; deconv: its coarse grid; conv: its input grid
+      if (cls(x) != cls(y)) return cls(x) < cls(y);
+      if (cls(x) == 1) return level(x) < level(y);
+      if (level(x) != level(y)) return level(x) > level(y);
+      return (x.v[0] == 1) && (y.v[0] != 1);
+    });
+  } else
   std::stable_sort(m->ops2.begin(), m->ops2.end(), [](const PrefetchOp &x, const PrefetchOp &y) {
     auto fine = [](const PrefetchOp &o) { return o.v[0] == 3 ? o.v[4] : o.v[1]; }; // spatial size[0] of the (fine) grid the entry hangs off
     const bool sx = x.v[0] == 1, sy = y.v[0] == 1;
@@ -418,6 +437,62 @@ int scn_rows_to_reference_order(scn_metadata *ref, scn_metadata *internal, const
                                                                                        gr->n, cols / 4);
   SCN_CUDA(cudaGetLastError());
   cudaFreeAsync(perm, s);
+  return 0;
+}
+// The same for SEVERAL feature matrices in ONE launch (the end of a replayed forward hands out 5 small maps: five pairs of
+// launches, five stream-ordered allocations and the host time between them were 0.2 ms of a 4.9 ms forward).  One warp per
+// destination row: lane 0 looks the row's site up in the internal grid, the warp copies the row.
+namespace {
+constexpr int kMaxOutMaps = 8;
+struct OutMap { const int4 *refCoords; const int *p2id; const float4 *src; float4 *dst; scn::GridView g; int n, c4, firstWarp; };
+struct OutMaps { OutMap m[kMaxOutMaps]; int count, totalWarps; };
+__global__ void __launch_bounds__(256) k_rows_to_reference_multi(OutMaps P) {
+  const int lane = threadIdx.x & 31;
+  for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < P.totalWarps; w += gridDim.x * (blockDim.x >> 5)) {
+    int k = 0;
+    while (k + 1 < P.count && w >= P.m[k + 1].firstWarp) k++;
+    const OutMap &M = P.m[k];
+    const int row = w - M.firstWarp;
+    int srcRow = -1;
+    if (lane == 0) {
+      const int4 c = M.refCoords[row];
+      const int p = scn::grid_lookup(M.g, c.x, c.y, c.z, c.w);
+      srcRow = p >= 0 ? M.p2id[p] : -1;
+    }
+    srcRow = __shfl_sync(0xffffffffu, srcRow, 0);
+    for (int j = lane; j < M.c4; j += 32) M.dst[(long)row * M.c4 + j] = srcRow >= 0 ? M.src[(long)srcRow * M.c4 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+} // namespace
+int scn_rows_to_reference_order_multi(scn_metadata *ref, scn_metadata *internal, int n_maps, const long *sizes, const float *const *src, float *const *dst,
+                                      const int *cols) {
+  M_OR_FAIL(ref);
+  M_OR_FAIL(internal);
+  SCN_CHECK(n_maps >= 0 && n_maps <= kMaxOutMaps, "rows_to_reference_order_multi: at most 8 maps per call");
+  OutMaps P;
+  P.count = 0;
+  P.totalWarps = 0;
+  cudaStream_t s = ref->md.cstream;
+  for (int i = 0; i < n_maps; i++) {
+    scn::Grid *gr = ref->md.find_grid(sizes + 3 * i), *gi = internal->md.find_grid(sizes + 3 * i);
+    SCN_CHECK(gr && gi && gr->n == gi->n && cols[i] % 4 == 0, "rows_to_reference_order: grids differ");
+    if (gr->n == 0) continue;
+    SCN_TRY(ref->md.wait_ready(gr->rdy));
+    if (gi->rdy.ev) SCN_CUDA(cudaStreamWaitEvent(s, gi->rdy.ev, 0));
+    OutMap &M = P.m[P.count++];
+    M.refCoords = gr->coords;
+    M.p2id = gi->p2id;
+    M.src = reinterpret_cast<const float4 *>(src[i]);
+    M.dst = reinterpret_cast<float4 *>(dst[i]);
+    M.g = scn::GridView{gi->dir, gi->bmask, gi->wbase, gi->dd[0], gi->dd[1], gi->dd[2], gi->dirCells, (int)gi->sz[0], (int)gi->sz[1], (int)gi->sz[2]};
+    M.n = gr->n;
+    M.c4 = cols[i] / 4;
+    M.firstWarp = P.totalWarps;
+    P.totalWarps += gr->n;
+  }
+  if (P.totalWarps == 0) return 0;
+  k_rows_to_reference_multi<<<std::min(scn::cdiv(P.totalWarps, 8), 148 * 8), 256, 0, scn::LS(s)>>>(P);
+  SCN_CUDA(cudaGetLastError());
   return 0;
 }
 int scn_get_batch_size(scn_metadata *m, const long sz[3], int *batch) {

@@ -19,6 +19,7 @@ void lateral_arm(const float *in, const void *in16, const float *w, long long ta
 bool lateral_take();
 void prepadded_arm(const void *rows16, int Cp);
 void prepadded_disarm();
+int build_subm_on_caller(scn_metadata *m, const long *sz, const long *f);
 int bn_forward_from_sums(const float *x, float *y, long n, int C, const double *sums, float *saveMean, float *saveInvStd, float *runningMean,
                          float *runningVar, const float *weight, const float *bias, float eps, float momentum, int mode, float leak, cudaStream_t s, void *y16);
 } // namespace scn
@@ -344,6 +345,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   if (internalOn < 0) internalOn = getenv("SCN_INTERNAL_IDS") ? atoi(getenv("SCN_INTERNAL_IDS")) : 1;
   if (p->ms) { scn_metadata_destroy(p->ms); p->ms = nullptr; }
   p->internal = false;
+  const bool preparedAhead = scn_input_layer_built(m, nullptr, nullptr) != 0; // scn_program_prepare ran for `m` (streaming): its workers build everything
   scn_metadata *M = m;
   const Op *inOp = nullptr;
   for (const Op &o : p->ops) if (o.kind == K_INPUT) { inOp = &o; break; }
@@ -440,6 +442,9 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     slot_put(p, tmp);
     return r;
   };
+  static const bool firstPlanOn = !(getenv("SCN_FIRST_PLAN_HERE") && atoi(getenv("SCN_FIRST_PLAN_HERE")) == 0);
+  const bool firstPlanHere = firstPlanOn && !preparedAhead;
+  bool firstPlanDone = false;
   for (int i = 0; i < (int)p->ops.size() && rc == 0; i++) {
     const Op &op = p->ops[i];
     const long *a = op.a;
@@ -467,6 +472,11 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       }
       case K_SUBM: { // in, out, size[3], filter[3], w, bias, Cin, Cout
         long n = 0;
+        if (firstPlanHere && !firstPlanDone) { // the first plan of an unprepared forward: built here, now (see build_subm_on_caller)
+          firstPlanDone = true;
+          rc = scn::build_subm_on_caller(M, a + 2, a + 5);
+          if (rc) break;
+        }
         rc = scn_get_nactive(M, a + 2, &n);
         const bool half = a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], half || a[22] >= 0 || a[18] >= 0, half);
@@ -575,6 +585,24 @@ int scn_program_output_copy(scn_program *p, scn_metadata *m, int reg, const long
   static const bool skipTwin = getenv("SCN_SKIP_TWIN") && atoi(getenv("SCN_SKIP_TWIN"));
   if (p->internal && !skipTwin) return scn_rows_to_reference_order(m, p->ms, spatial_size, R.p, dst, R.cols);
   return scn_copy_device(dst, R.p, R.rows * R.cols * 4, p->stream);
+}
+// All output registers at once (regs[i] -> dst[i], grids sizes[3 i .. 3 i + 2]): one gather launch instead of two per map.
+int scn_program_outputs_copy(scn_program *p, scn_metadata *m, int n, const int *regs, const long *sizes, float *const *dst) {
+  SCN_CHECK(p && n >= 0 && n <= 8, "at most 8 output registers per call");
+  static const bool skipTwin = getenv("SCN_SKIP_TWIN") && atoi(getenv("SCN_SKIP_TWIN"));
+  static const bool multi = !(getenv("SCN_OUT_MULTI") && atoi(getenv("SCN_OUT_MULTI")) == 0);
+  if (!(p->internal && !skipTwin && multi)) {
+    for (int i = 0; i < n; i++) SCN_TRY(scn_program_output_copy(p, m, regs[i], sizes + 3 * i, dst[i]));
+    return 0;
+  }
+  const float *src[8];
+  int cols[8];
+  for (int i = 0; i < n; i++) {
+    SCN_CHECK(regs[i] >= 0 && regs[i] < p->nRegs && p->isOutput[regs[i]], "not an output register");
+    src[i] = p->regs[regs[i]].p;
+    cols[i] = p->regs[regs[i]].cols;
+  }
+  return scn_rows_to_reference_order_multi(m, p->ms, n, sizes, src, dst, cols);
 }
 int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const float **ptr) {
   SCN_CHECK(p && reg >= 0 && reg < p->nRegs && p->isOutput[reg], "not an output register");

@@ -166,14 +166,20 @@ class Program(object):
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         check(lib().scn_program_run(self._h, metadata._h, C.c_void_p(coords.data_ptr()), int(coords.is_cuda), coords.size(0), coords.size(1),
                                     C.c_void_p(feats.data_ptr()), ptrs, tags, n, stream, C.byref(macs)))
-        outs, cache = [], {}
+        uniq, tens = [], {}
         for r, size in zip(self.out_regs, self.out_sizes):
-            if r not in cache:
+            if r not in tens:
                 rows, cols, ptr = C.c_long(), C.c_int(), C.c_void_p()
                 check(lib().scn_program_output(self._h, r, C.byref(rows), C.byref(cols), C.byref(ptr)))
-                t = torch.empty((rows.value, cols.value), dtype=torch.float32, device=feats.device)
-                if t.numel():  # rows in the numbering of `metadata` (the executor may have computed them in its internal order)
-                    check(lib().scn_program_output_copy(self._h, metadata._h, r, l3(size), C.c_void_p(t.data_ptr())))
-                cache[r] = t
-            outs.append(cache[r])
+                tens[r] = torch.empty((rows.value, cols.value), dtype=torch.float32, device=feats.device)
+                if tens[r].numel():
+                    uniq.append((r, size))
+        # rows in the numbering of `metadata` (the executor may have computed them in its internal order): one launch for all maps
+        for k in range(0, len(uniq), 8):
+            part = uniq[k:k + 8]
+            regs = (C.c_int * len(part))(*[r for r, _ in part])
+            sizes = (C.c_long * (3 * len(part)))(*[int(v) for _, size in part for v in size.tolist()])
+            dst = (C.c_void_p * len(part))(*[tens[r].data_ptr() for r, _ in part])
+            check(lib().scn_program_outputs_copy(self._h, metadata._h, len(part), regs, sizes, dst))
+        outs = [tens[r] for r in self.out_regs]
         return outs, macs.value

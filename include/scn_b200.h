@@ -191,6 +191,9 @@ int scn_metadata_wait_jobs(scn_metadata *m);
 /* batch items of the grid of this spatial size (0 when there is none) */
 int scn_get_batch_size(scn_metadata *m, const long spatial_size[3], int *batch);
 int scn_rows_to_reference_order(scn_metadata *ref, scn_metadata *internal, const long spatial_size[3], const float *src, float *dst, int cols);
+/* the same for up to 8 feature matrices in one launch (sizes: n_maps x 3) */
+int scn_rows_to_reference_order_multi(scn_metadata *ref, scn_metadata *internal, int n_maps, const long *sizes, const float *const *src, float *const *dst,
+                                      const int *cols);
 /* Build half of a run, callable ahead of scn_program_run for the NEXT input while the GPU still computes the current
  * one (streaming many buildings through one network): input layer + the worker threads that build every rulebook the
  * program requests.  coords_on_device: 0 host, 1 device (ordered after the caller's stream), 2 device and complete.
@@ -205,6 +208,8 @@ int scn_set_pool_growth(int on);
 int scn_program_output(scn_program *p, int reg, long *rows, int *cols, const float **ptr);
 /* output register -> caller's device buffer [rows][cols], in the row numbering of the caller's Metadata `m` */
 int scn_program_output_copy(scn_program *p, scn_metadata *m, int reg, const long spatial_size[3], float *dst);
+/* every output register of the last run at once (n <= 8; sizes: n x 3): one gather launch */
+int scn_program_outputs_copy(scn_program *p, scn_metadata *m, int n, const int *regs, const long *sizes, float *const *dst);
 /* device-to-device copy on `stream` (hands an output register to a caller-owned tensor) */
 int scn_copy_device(void *dst, const void *src, long bytes, void *stream);
 
@@ -237,6 +242,39 @@ int scn_roi_align_rotated_3d_forward(scn_metadata *m, const long spatial_size[3]
                                      long n_rois, float spatial_scale, int pooled_h, int pooled_w, int pooled_z, int sampling_ratio, float *out);
 int scn_roi_align_rotated_3d_backward(scn_metadata *m, const long spatial_size[3], float *d_feats, int n_planes, const int extent[3], const float *rois,
                                       long n_rois, float spatial_scale, int pooled_h, int pooled_w, int pooled_z, int sampling_ratio, const float *d_out);
+
+/* ---- the steps either side of the path: RPN post-processing and the input voxeliser.  All pointers
+ * are DEVICE pointers unless stated otherwise; everything runs on `stream`.
+ *
+ * torch.topk(values, k, sorted=True) (inference_3d.py:101-104, box_torch_ops.py:495-499): the k largest values in descending order and
+ * their indices; apply_sigmoid = 1 ranks sigmoid(values) (objectness.sigmoid().topk) and returns the sigmoid values.  Ties: lower
+ * index first (torch leaves the order of equal values unspecified). */
+int scn_top_k_descending(const float *values, long n, int apply_sigmoid, long k, float *out_values, long *out_indices, void *stream);
+/* BoxCoder3D.decode (maskrcnn_benchmark/modeling/box_coder_3d.py:38-65 -> second_box_decode, second/pytorch/core/box_torch_ops.py:51-88):
+ * boxes[i] = decode(encodings[j] / weights, anchors[j]), j = indices[i] (or i when indices is NULL); sizes clamped to `clip`, smooth_dim
+ * 1 = (t + 1) * a, 0 = exp(t) * a; yaw wrapped into [-pi/2, pi/2) by limit_period(., 0.5, pi).  weights = HOST float[7]. */
+int scn_box_decode_3d(const float *encodings, const float *anchors, const long *indices, long n, const float weights[7], float clip, int smooth_dim, float *boxes,
+                      void *stream);
+/* boxes_iou_3d (utils3d/rotate_nms_3d_torch.py:22-84): iou[t][a] = rotated BEV IoU (rotate_iou_gpu_eval, second/core/non_max_suppression/
+ * nms_gpu.py:548-667, criterion -1 / 0 / 1 / 2 / other = intersection area; identical rectangles forced to 1) times the IoU of the z
+ * extents (only_xy = 0).  Boxes are yx_zb rows [x, y, z_bottom, size_y, size_x, size_z, yaw]; aug_thickness = HOST float[4] = minimum
+ * size_y / size_z of the targets, then of the anchors (NULL = no augmentation). */
+int scn_boxes_iou_3d(const float *targets, long n_targets, const float *anchors, long n_anchors, const float aug_thickness[4], int criterion, int only_xy, float *iou,
+                     void *stream);
+/* rotate_nms_3d (second/pytorch/core/box_torch_ops.py:489-514 -> rotate_nms_3d_cc, second/core/non_max_suppression/nms_cpu.py:32-44):
+ * top pre_max_size boxes by score, greedy suppression in score order (a kept box removes every later box whose 3-D IoU with it is
+ * positive and whose BEV polygon IoU reaches iou_threshold), first post_max_size survivors.  keep = device long[>= min(n, post_max_size)]
+ * receives indices into `boxes`, n_keep = device long[1] their count.  At most 16384 candidates after pre_max_size. */
+int scn_rotate_nms_3d(const float *boxes, const float *scores, long n, long pre_max_size, long post_max_size, float iou_threshold, long *keep, long *n_keep,
+                      void *stream);
+/* Input voxeliser (data3d/suncg_utils/suncg_dataset.py:115-177): a = xyz @ matrix + offset (float64), rows with any coordinate outside
+ * [0, full_scale) dropped (order kept), locs = trunc(a) as int64 [kept][loc_cols] (loc_cols 4 appends batch_index), feats_out = feats with
+ * columns 0..2 replaced by a / scale when xyz_in_feats.  matrix (row-major 3x3, as numpy's a @ m), offset, full_scale = HOST doubles;
+ * n_kept = HOST long, written after a stream synchronisation.  scn_voxelize_extent returns min / max of xyz @ matrix per coordinate
+ * (the `offset = -a.min(0)` of :131-134) to HOST doubles. */
+int scn_voxelize_extent(const float *xyz, long n, const double matrix[9], double extent_min[3], double extent_max[3], void *stream);
+int scn_voxelize(const float *xyz, const float *feats, long n, int n_feat, const double matrix[9], const double offset[3], double scale, const double full_scale[3],
+                 int xyz_in_feats, long batch_index, int loc_cols, long *locs, float *feats_out, long *n_kept, void *stream);
 
 /* Selects the arithmetic of the gather-GEMM kernels for this process: 0 = fp32 CUDA cores
  * (exact-fp32 anchor), 1 = tcgen05 tensor cores, TF32 inputs / fp32 accumulate (default where the

@@ -634,3 +634,139 @@ def test_roi_align_rotated_3d_vs_reference_kernel(case, sampling):
     g_t = T(g)
     assert ref.ref_roi_align_rotated_3d_backward(p(g_t), p(r_t), n_rois, scale, pooled[0], pooled[1], pooled[2], batch, C_, ext[0], ext[1], ext[2], sampling, p(d_ref)) == 0
     _close(dd, d_ref.cpu().numpy(), 1e-4, 5e-5)
+
+
+# ------------------------------------------------------------------ RPN post-processing and voxeliser
+def _rpn_golden_inputs():
+    r = np.load(os.path.join(GOLD, "rpn_sw4c_mid.npz"))
+    nm = int(r["n_maps"])
+    anchors = np.concatenate([r[f"anchors{i}"] for i in range(nm)], 0)
+    logits = np.concatenate([r[f"logits{i}"].reshape(-1, r[f"logits{i}"].shape[-1]) for i in range(nm)], 0)
+    regs = np.concatenate([r[f"reg{i}"].reshape(-1, r[f"reg{i}"].shape[-1]) for i in range(nm)], 0)
+    return anchors, logits, regs
+
+
+def test_box_decode_and_top_k_vs_reference_golden():
+    """BoxCoder3D.decode (one class, two classes per anchor, weights) against the reference's own decode; top_k against torch.topk."""
+    from detection_3d_b200 import postproc as pp
+    g = np.load(os.path.join(GOLD, "postproc.npz"))
+    OS, RS = np.float32(g["obj_scale"]), np.float32(g["reg_scale"])
+    anchors, logits, regs = _rpn_golden_inputs()
+    coder = pp.BoxCoder3D()
+    _close(coder.decode(T(regs[:, :7] * RS), T(anchors)).cpu().numpy(), g["decode_1"], 2e-6, 2e-6)
+    _close(coder.decode(T(regs[:500] * RS), T(anchors[:500])).cpu().numpy(), g["decode_2"], 2e-6, 2e-6)
+    _close(pp.BoxCoder3D(weights=(10., 10., 5., 5., 5., 5., 2.)).decode(T(regs[:500, :7] * RS), T(anchors[:500])).cpu().numpy(), g["decode_w"], 2e-6, 2e-6)
+    idx = torch.randperm(anchors.shape[0], generator=torch.Generator().manual_seed(0))[:777].cuda()
+    assert torch.equal(coder.decode(T(regs[:, :7] * RS), T(anchors), indices=idx), coder.decode(T(regs[:, :7] * RS), T(anchors))[idx])
+    v = T(logits[:, 0] * OS)
+    for k, sig in ((1500, True), (v.numel(), False), (1, True), (0, False)):
+        got_v, got_i = pp.top_k(v, k, sigmoid=sig)
+        ref_v, ref_i = torch.topk(v.sigmoid() if sig else v, k, sorted=True)
+        assert torch.equal(got_v, ref_v)
+        assert torch.equal((v.sigmoid() if sig else v)[got_i], ref_v)  # (indices of equal values may legitimately differ)
+    ties = torch.tensor([0.5, 2.0, 0.5, 2.0, -1.0, 2.0], device="cuda")
+    tv, ti = pp.top_k(ties, 5)
+    assert ti.tolist() == [1, 3, 5, 0, 2] and tv.tolist() == [2.0, 2.0, 2.0, 0.5, 0.5]  # ties: lower index first
+    big = torch.randn(200000, generator=torch.Generator().manual_seed(1)).cuda()
+    bv, bi = pp.top_k(big, 3000)
+    assert torch.equal(bv, torch.topk(big, 3000)[0]) and torch.equal(big[bi], bv)
+
+
+def test_boxes_iou_3d_vs_reference_golden_and_oracle():
+    """Rotated BEV IoU (all criteria) and 3-D IoU against the reference's numba kernel outputs (golden) and the CPU restatement on
+    random + degenerate boxes.  Tolerance 3e-5 absolute: float32 polygon clipping vs the reference's vertex sort + triangle fan."""
+    from detection_3d_b200 import postproc as pp
+    from oracle import postproc_oracle as po
+    g = np.load(os.path.join(GOLD, "postproc.npz"))
+    b5, rows, qs = g["iou2d_boxes"], g["iou2d_rows"], g["iou2d_query_sel"]
+    to7 = lambda b: np.stack([b[:, 0], b[:, 1], np.zeros(len(b)), b[:, 2], b[:, 3], np.ones(len(b)), b[:, 4]], 1).astype(np.float32)
+    for crit in (-1, 0, 1, 2, 3):
+        got = pp.boxes_iou_3d(T(to7(b5[rows])), T(to7(b5[qs])), None, criterion=crit, only_xy=True, flag='rpn_post').cpu().numpy()
+        np.testing.assert_allclose(got, g[f"iou2d_c{crit}"], rtol=2e-4, atol=3e-5)
+    t7, a7 = g["iou3d_targets"], g["iou3d_anchors"]
+    np.testing.assert_allclose(pp.boxes_iou_3d(T(t7), T(a7), None, flag='rpn_post').cpu().numpy(), g["iou3d_plain"], rtol=2e-4, atol=3e-5)
+    aug = {'target_Y': 0.3, 'target_Z': 0.4, 'anchor_Y': 0.0, 'anchor_Z': 0.0}
+    np.testing.assert_allclose(pp.boxes_iou_3d(T(t7), T(a7), aug, criterion=1, flag='rpn_label_generation').cpu().numpy(), g["iou3d_aug"], rtol=2e-4, atol=3e-5)
+    np.testing.assert_allclose(pp.boxes_iou_3d(T(t7), T(a7), None, only_xy=True, flag='roi_post').cpu().numpy(), g["iou3d_xy"], rtol=2e-4, atol=3e-5)
+    with pytest.raises(AssertionError):
+        pp.boxes_iou_3d(T(t7), T(a7), aug, flag='rpn_post')  # the reference asserts aug_thickness is None here
+    rs = np.random.RandomState(5)
+    n = 40
+    b = np.stack([rs.uniform(0, 5, n), rs.uniform(0, 5, n), rs.uniform(0, 2, n), rs.uniform(0.1, 3, n), rs.uniform(0.1, 3, n), rs.uniform(0.1, 2, n), rs.uniform(-4, 4, n)], 1).astype(np.float32)
+    b[1] = b[0]                      # identical
+    b[2, [3, 4]] = 0                 # zero footprint: 0 / 0 = nan in the reference too
+    b[3] = [1, 1, 0, 2, 2, 1, 0]; b[4] = [1, 1, 0.5, 2, 2, 1, 0]; b[5] = [3, 1, 0, 2, 2, 1, 0]  # same square, shifted in z; touching square
+    got = pp.boxes_iou_3d(T(b), T(b), None, flag='rpn_post').cpu().numpy()
+    want = po.boxes_iou_3d(b, b)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    np.testing.assert_allclose(np.nan_to_num(got), np.nan_to_num(want), rtol=2e-4, atol=3e-5)
+    assert got[0, 1] == pytest.approx(1.0, abs=1e-6) and got[3, 5] == 0.0
+    assert pp.boxes_iou_3d(T(b[:0]), T(b), None, flag='rpn_post').shape == (0, n)
+
+
+def test_rotate_nms_3d_and_rpn_post_processor_vs_reference_golden():
+    """The whole chain of inference_3d.py:82-161 for one example against the reference's own RPNPostProcessor output (bit-exact
+    selection and order of the surviving boxes; box values to 2e-6), rotate_nms_3d on its own, and -- at the B470 size (9,248
+    anchors -> 1,500 candidates) -- against the CPU restatement."""
+    from detection_3d_b200 import postproc as pp
+    from oracle import postproc_oracle as po
+    g = np.load(os.path.join(GOLD, "postproc.npz"))
+    OS, RS = np.float32(g["obj_scale"]), np.float32(g["reg_scale"])
+    anchors, logits, regs = _rpn_golden_inputs()
+    sel = g["rpn_sel"]
+    anc, obj, reg = anchors[sel], logits[sel, 0] * OS, regs[sel, :7] * RS
+    post = pp.RPNPostProcessor(batch_size=1, fpn_pre_nms_top_n=130, fpn_post_nms_top_n=105, nms_thresh=0.1, nms_aug_thickness=[0.3, 0.3], min_size=0).eval()
+    res = post(pp.Boxes3D(T(anc)), T(obj), T(reg))
+    assert len(res) == 1 and tuple(res[0].bbox3d.shape) == g["rpn_boxes"].shape
+    _close(res[0].bbox3d.cpu().numpy(), g["rpn_boxes"], 2e-6, 2e-6)
+    np.testing.assert_allclose(res[0].get_field("objectness").cpu().numpy(), g["rpn_objectness"], rtol=2e-6, atol=1e-7)
+    dec = pp.BoxCoder3D().decode(T(reg), T(anc))
+    keep = pp.rotate_nms_3d(dec[:150], T(obj[:150]), pre_max_size=120, post_max_size=60, iou_threshold=0.3, flag='rpn_post')
+    assert np.array_equal(keep.cpu().numpy(), g["nms_keep_03"])
+    assert pp.rotate_nms_3d(dec[:0], T(obj[:0]), 100, 50, 0.3).numel() == 0
+    # two examples in one batch = the two halves processed independently
+    half = anc.shape[0] // 2
+    both = pp.Boxes3D(T(anc), examples_idxscope=torch.tensor([[0, half], [half, anc.shape[0]]]))
+    r2 = post(both, T(obj), T(reg))
+    one = post(pp.Boxes3D(T(anc[half:])), T(obj[half:]), T(reg[half:]))
+    assert len(r2) == 2 and torch.equal(r2[1].bbox3d, one[0].bbox3d)
+    # full size of the B470 building: every anchor of the four rpn maps, sw4c's top-n (tools/train_net_sparse3d.py:247-255)
+    big = pp.RPNPostProcessor(1, 1500, 750, 0.1, [0.3, 0.3], 0).eval()
+    full_obj, full_reg = logits[:, 0] * OS, regs[:, :7] * RS
+    got = big(pp.Boxes3D(T(anchors)), T(full_obj), T(full_reg))[0]
+    wb, wo = po.rpn_post_process(anchors, full_obj, full_reg, 1500, 750, 0.1, (0.3, 0.3))
+    assert tuple(got.bbox3d.shape) == wb.shape
+    _close(got.bbox3d.cpu().numpy(), wb, 2e-6, 2e-6)
+    np.testing.assert_allclose(got.get_field("objectness").cpu().numpy(), wo, rtol=2e-6, atol=1e-7)
+    assert (np.diff(got.get_field("objectness").cpu().numpy()) <= 0).all()  # survivors stay in descending score order
+
+
+def test_voxelize_vs_reference_golden():
+    """Input voxeliser against the statements of the reference's SUNCGDataset.__getitem__ executed on the same points (golden): integer
+    voxel coordinates bit-exact, features to float32 rounding, dropped rows identical; B470-sized cloud against the CPU restatement."""
+    from detection_3d_b200 import postproc as pp
+    from oracle import postproc_oracle as po
+    g = np.load(os.path.join(GOLD, "postproc.npz"))
+    pcl = g["vox_pcl"]
+    locs, feats, size3d = pp.voxelize(T(pcl[:, :3].copy()), T(pcl), 50, [2048, 2048, 512])
+    assert np.array_equal(locs.cpu().numpy(), g["vox_locs"])
+    np.testing.assert_allclose(feats.cpu().numpy(), g["vox_feats"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(size3d.numpy(), g["vox_size3d"], rtol=1e-6)
+    locs, feats, _ = pp.voxelize(T(pcl[:, :3].copy()), T(pcl[:, [0, 1, 2, 6, 7, 8]].copy()), 50, [1900, 2048, 512])
+    assert np.array_equal(locs.cpu().numpy(), g["vox2_locs"])
+    np.testing.assert_allclose(feats.cpu().numpy(), g["vox2_feats"], rtol=1e-6, atol=1e-6)
+    rs = np.random.RandomState(2)
+    pts = rs.uniform(0, 21.7, (1200000, 3)).astype(np.float32)
+    f = rs.randn(1200000, 9).astype(np.float32)
+    th = 0.3
+    m = np.array([[np.cos(th), np.sin(th), 0], [-np.sin(th), np.cos(th), 0], [0, 0, 1]]) * 25.0
+    locs, feats, size3d = pp.voxelize(T(pts), T(f), 25, [700, 700, 512], matrix=m, batch_index=3)
+    wl, wf, ws = po.voxelize(pts, f, 25, [700, 700, 512], matrix=m)
+    assert locs.shape[0] == wl.shape[0] < pts.shape[0] and (locs[:, 3] == 3).all()
+    same = (locs[:, :3].cpu().numpy() == wl).all(1)
+    assert same.mean() > 0.99999  # (a point within one float64 ulp of a voxel face may fall either way: fused multiply-add vs BLAS)
+    np.testing.assert_allclose(feats.cpu().numpy(), wf, rtol=1e-5, atol=1e-5)
+    # the voxelised cloud feeds the backbone's InputLayer directly
+    scn = _scn()
+    x = scn.InputLayer(3, [2048, 2048, 512], mode=4)([locs[:, :3].contiguous(), feats])
+    assert x.features.shape[0] == np.unique(wl, axis=0).shape[0]

@@ -296,3 +296,44 @@ def test_sparse_to_dense_oracle_vs_reference_golden():
         R.input_layer(sz, g["coords"], 0, 4)
         for a, b in zip(rules, R.sparse_to_dense_rules(sz)):
             assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------ RPN post-processing / voxeliser
+def test_postproc_oracle_vs_reference_golden():
+    """oracle/postproc_oracle.py against tests/golden/postproc.npz = outputs of the reference's own decode / rotated IoU / 3-D IoU /
+    rotate_nms_3d / RPNPostProcessor / voxeliser code (tests/golden/make_golden_postproc.py).  Float outputs: the reference's numba
+    kernel mixes float32 arrays with double scalars, the restatement is float32 throughout -> 2e-5 absolute on IoUs in [0, 1]."""
+    from oracle import postproc_oracle as po
+    g = np.load(os.path.join(GOLD, "postproc.npz"))
+    OS, RS = np.float32(g["obj_scale"]), np.float32(g["reg_scale"])
+    b5, rows, qs = g["iou2d_boxes"], g["iou2d_rows"], g["iou2d_query_sel"]
+    for crit in (-1, 0, 1, 2, 3):
+        np.testing.assert_allclose(po.rotated_iou_2d(b5[rows], b5[qs], crit), g[f"iou2d_c{crit}"], rtol=1e-4, atol=2e-5)
+    t7, a7 = g["iou3d_targets"], g["iou3d_anchors"]
+    np.testing.assert_allclose(po.boxes_iou_3d(t7, a7), g["iou3d_plain"], rtol=1e-4, atol=2e-5)
+    aug = {'target_Y': 0.3, 'target_Z': 0.4, 'anchor_Y': 0.0, 'anchor_Z': 0.0}
+    np.testing.assert_allclose(po.boxes_iou_3d(t7, a7, aug, criterion=1), g["iou3d_aug"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(po.boxes_iou_3d(t7, a7, only_xy=True), g["iou3d_xy"], rtol=1e-4, atol=2e-5)
+    r = np.load(os.path.join(GOLD, "rpn_sw4c_mid.npz"))
+    nm = int(r["n_maps"])
+    anchors = np.concatenate([r[f"anchors{i}"] for i in range(nm)], 0)
+    logits = np.concatenate([r[f"logits{i}"].reshape(-1, r[f"logits{i}"].shape[-1]) for i in range(nm)], 0)
+    regs = np.concatenate([r[f"reg{i}"].reshape(-1, r[f"reg{i}"].shape[-1]) for i in range(nm)], 0)
+    np.testing.assert_allclose(po.box_decode(regs[:, :7] * RS, anchors), g["decode_1"], rtol=1e-6, atol=1e-6)
+    two = np.concatenate([po.box_decode(regs[:500, 7 * c:7 * c + 7] * RS, anchors[:500]) for c in range(2)], 1)
+    np.testing.assert_allclose(two, g["decode_2"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(po.box_decode(regs[:500, :7] * RS, anchors[:500], (10., 10., 5., 5., 5., 5., 2.)), g["decode_w"], rtol=1e-6, atol=1e-6)
+    sel = g["rpn_sel"]
+    boxes, obj = po.rpn_post_process(anchors[sel], logits[sel, 0] * OS, regs[sel, :7] * RS, 130, 105, 0.1, (0.3, 0.3))
+    assert boxes.shape == g["rpn_boxes"].shape  # the same boxes survive, in the same order
+    np.testing.assert_allclose(boxes, g["rpn_boxes"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(obj, g["rpn_objectness"], rtol=1e-6, atol=1e-7)
+    dec = po.box_decode(regs[sel, :7] * RS, anchors[sel])
+    assert np.array_equal(po.rotate_nms_3d(dec[:150], (logits[sel, 0] * OS)[:150], 120, 60, 0.3), g["nms_keep_03"])
+    pcl = g["vox_pcl"]
+    locs, feats, size3d = po.voxelize(pcl[:, :3], pcl, 50, [2048, 2048, 512])
+    assert np.array_equal(locs, g["vox_locs"]) and np.array_equal(feats, g["vox_feats"])
+    np.testing.assert_allclose(size3d, g["vox_size3d"], rtol=1e-6)
+    locs, feats, size3d = po.voxelize(pcl[:, :3], pcl[:, [0, 1, 2, 6, 7, 8]], 50, [1900, 2048, 512])
+    assert np.array_equal(locs, g["vox2_locs"]) and np.array_equal(feats, g["vox2_feats"])
+    assert locs.shape[0] < pcl.shape[0]  # points outside the full scale were dropped

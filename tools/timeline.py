@@ -17,6 +17,9 @@ if os.environ.get("SCN_TIMELINE") != "1":
             cur = []
         else:
             print(line)
+    if "--raw" in sys.argv:  # every milestone of the last forward: time, thread role, kind, two arguments
+        for e in fw[-1][1]:
+            print("%9.1f us  %-7s kind %d  %d %d" % e)
     for line, evs in fw[-6:]:
         def first(pred):
             return next((e[0] for e in evs if pred(e)), float("nan"))
@@ -36,7 +39,7 @@ import fpn_util  # noqa: E402
 import detection_3d_b200.sparseconvnet as scn  # noqa: E402
 from detection_3d_b200 import synthetic  # noqa: E402
 
-scn.set_math_mode(sys.argv[1] if len(sys.argv) > 1 else "bf16")
+scn.set_math_mode(next((a for a in sys.argv[1:] if not a.startswith("--")), "bf16"))
 net = scn.FPN_Net(**scn.sw4c_fpn432_config())
 net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
 net = net.cuda().eval()
