@@ -281,6 +281,52 @@ def leg_batch64(args, rank, world, dev, net, n_build=64):
             "note": "64 distinct buildings (B470 +-15 %), host pinned inputs, sharded longest-first, Metadata built two buildings ahead, outputs copied to pinned host memory"}
 
 
+def leg_rpn(args, rank, world, dev, net, coords_pin, feats_pin, steps=20, warmup=3):
+    """BASELINE.json config 3: full sw_4c_fpn432 RPN inference per building -- backbone + FPN (the headline path), RPN head and anchors
+    on the four rpn maps, then per class group sigmoid / top-1500 / box decode / rotated 3-D NMS / top-750 (tools/train_net_sparse3d.py:
+    247-255) -- from pinned host inputs to the proposals on the host.  Random-init head (no checkpoint): the NMS work depends on the
+    boxes, so the proposal counts are reported beside the time."""
+    import torch
+    import torch.distributed as dist
+    from detection_3d_b200 import detector
+    torch.manual_seed(0)
+    det = detector.SparseRPNDetector(net, detector.RPNModule()).to(dev).eval()
+    with torch.no_grad():
+        # the default init (std 0.01) gives logits and box deltas of ~1e-3, i.e. all-equal scores and boxes = anchors: scale the layers so
+        # that the outputs have the spread of a trained head (logits of a few units, deltas of ~0.2)
+        det.rpn.head.conv.weight.mul_(10.0)
+        det.rpn.head.cls_logits.weight.mul_(20.0)
+        det.rpn.head.bbox_pred.weight.mul_(1.5)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        with torch.no_grad():
+            groups = det([coords_pin, feats_pin])
+            return [(b.bbox3d.to("cpu", non_blocking=True), b.get_field("objectness").to("cpu", non_blocking=True)) for gr in groups for b in gr]
+
+    for _ in range(warmup):
+        out = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        out = step()
+        b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    n_anchor = sum(int(x) for x in [786, 1156, 289, 81]) * 4
+    return {"metric": "rpn_inference_buildings_per_s", "value": world * 1e3 / ms, "unit": "buildings/s", "ms_per_step": ms, "steps": steps, "scaling": "weak",
+            "anchors": n_anchor, "proposals_per_group": [int(o[0].shape[0]) for o in out], "finite": all(bool(torch.isfinite(o[0]).all()) for o in out),
+            "note": "backbone + RPN head + anchors + per-group top-1500 / decode / rotated 3-D NMS (thresh 0.5) / top-750; pinned host inputs -> proposals on the host; "
+                    "L2 flush between steps; random-init head"}
+
+
 def leg_train(args, rank, world, dev, scn, steps=5, warmup=2):
     """BASELINE.json config 5: 6c_fpn4321 backbone training step (train-mode forward, loss = sum of squares of the returned maps,
     backward), batch 1 per GPU (one B470 building per rank, seed = rank), data-parallel gradient all-reduce over NCCL overlapped
@@ -351,7 +397,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default=os.environ.get("SCN_MATH", "auto"), choices=["auto", "fp32", "tf32", "bf16"])
-    ap.add_argument("--config", default="backbone", choices=["backbone", "batch64", "train"],
+    ap.add_argument("--config", default="backbone", choices=["backbone", "rpn", "batch64", "train"],
                     help="backbone = BASELINE.json configs[1] (the headline; its JSON line also carries batch64 / train sub-results unless --no-extras); "
                          "batch64 = config 4 alone; train = config 5 alone")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -406,11 +452,16 @@ def main():
     cfg = scn.sw4c_fpn432_config()
     net, state = make_model(cfg, dev)
     if args.config != "backbone":  # configs 4 / 5 on their own: one JSON line in the same format
-        sub = leg_batch64(args, rank, world, dev, net) if args.config == "batch64" else leg_train(args, rank, world, dev, scn)
+        if args.config == "rpn":
+            c_np = synthetic.building_coords()
+            sub = leg_rpn(args, rank, world, dev, net, torch.from_numpy(c_np).pin_memory(), torch.from_numpy(fpn_util.features_for(c_np)).pin_memory())
+        else:
+            sub = leg_batch64(args, rank, world, dev, net) if args.config == "batch64" else leg_train(args, rank, world, dev, scn)
         line = {"metric": sub.pop("metric"), "value": sub.pop("value"), "unit": sub.pop("unit"), "n_gpus": world, "steps": sub.get("steps", 1), "warmup": args.warmup,
                 "ms_per_step": sub.get("ms_per_step", sub.get("ms_total")), "higher_is_better": True, "scaling": sub.pop("scaling"), "vs_baseline": None,
                 "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[math], "data": "synthetic",
-                "config": {"workload": "BASELINE.json config 4 (batch64)" if args.config == "batch64" else "BASELINE.json config 5 (6c_fpn4321 training step)"},
+                "config": {"workload": {"batch64": "BASELINE.json config 4 (batch64)", "rpn": "BASELINE.json config 3 (backbone + FPN + RPN inference per building)",
+                                        "train": "BASELINE.json config 5 (6c_fpn4321 training step)"}[args.config]},
                 "detail": sub}
         if rank == 0:
             emit(line)
@@ -550,7 +601,8 @@ def main():
         "roofline": roof,
     }
     if not args.no_extras:  # BASELINE.json configs 4 and 5 ride along (same process group; a failing sub-leg never costs the headline)
-        for name, fn in (("batch64", lambda: leg_batch64(args, rank, world, dev, net)), ("train", lambda: leg_train(args, rank, world, dev, scn))):
+        for name, fn in (("rpn", lambda: leg_rpn(args, rank, world, dev, net, coords_pin, feats_pin)), ("batch64", lambda: leg_batch64(args, rank, world, dev, net)),
+                         ("train", lambda: leg_train(args, rank, world, dev, scn))):
             try:
                 line[name] = fn()
             except Exception as e:

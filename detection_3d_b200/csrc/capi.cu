@@ -26,6 +26,11 @@ std::mutex g_tl_mu;
 int g_tl_on = -1;
 double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 } // namespace
+int pdl_mode() {
+  static int on = -1;
+  if (on < 0) on = getenv("SCN_PDL") ? atoi(getenv("SCN_PDL")) : 0;
+  return on;
+}
 void timeline_mark(const char *who, int kind, long a, long b) {
   if (g_tl_on < 0) g_tl_on = getenv("SCN_TIMELINE") ? atoi(getenv("SCN_TIMELINE")) : 0;
   if (!g_tl_on) return;
@@ -447,6 +452,8 @@ constexpr int kMaxOutMaps = 8;
 struct OutMap { const int4 *refCoords; const int *p2id; const float4 *src; float4 *dst; scn::GridView g; int n, c4, firstWarp; };
 struct OutMaps { OutMap m[kMaxOutMaps]; int count, totalWarps; };
 __global__ void __launch_bounds__(256) k_rows_to_reference_multi(OutMaps P) {
+  scn::pdl_launch_dependents();
+  scn::pdl_wait();
   const int lane = threadIdx.x & 31;
   for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < P.totalWarps; w += gridDim.x * (blockDim.x >> 5)) {
     int k = 0;
@@ -491,7 +498,7 @@ int scn_rows_to_reference_order_multi(scn_metadata *ref, scn_metadata *internal,
     P.totalWarps += gr->n;
   }
   if (P.totalWarps == 0) return 0;
-  k_rows_to_reference_multi<<<std::min(scn::cdiv(P.totalWarps, 8), 148 * 8), 256, 0, scn::LS(s)>>>(P);
+  SCN_CUDA(scn::launch_pdl(k_rows_to_reference_multi, dim3(std::min(scn::cdiv(P.totalWarps, 8), 148 * 8)), dim3(256), 0, scn::LS(s), P));
   SCN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -59,6 +59,37 @@ extern std::atomic<long> g_counters[kCntCounters];
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// ---------------------------------------------------------------- programmatic dependent launch (sm_90+)
+// The layer kernels of a forward sit back to back on one stream, ~100 of them, half of them a few microseconds long.  Launched with
+// the programmatic-stream-serialization attribute a kernel's CTAs become resident while the previous kernel is still draining
+// and run their prologue (barrier initialisation, TMEM allocation, scale / shift tables); `pdl_wait()` then blocks until the
+// previous kernel has completed and its writes are visible.  Rules: (1) a kernel launched through launch_pdl() executes
+// pdl_wait() in every thread before its first global-memory access; (2) it calls pdl_launch_dependents() on entry, so that the
+// NEXT kernel may do the same (all grids here fit in one wave, so early residents never starve their predecessor's CTAs).
+// Any other operation between two kernels (event wait, memset, a kernel launched the ordinary way) keeps full serialisation.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// (the fence makes ptxas emit CCTL.IVALL: an early-resident CTA shares its SM's L1 with CTAs of older kernels that may have cached
+//  lines of a buffer the previous kernel has since rewritten -- register buffers are recycled -- and this kernel reads with ld.global.nc)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n\tfence.acq_rel.gpu;" ::: "memory"); }
+#endif
+int pdl_mode(); // SCN_PDL: 0 = attribute off (the two instructions are then no-ops), 1 = every launch_pdl() launch, 2 = only grids of at most 64 CTAs
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const int mode = pdl_mode();
+  cfg.numAttrs = (mode == 1 || (mode == 2 && (long)grid.x * grid.y * grid.z <= 64)) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // B200: 148 SMs.  Element-wise / streaming kernels use grid-stride loops over a grid that is
 // a multiple of the SM count.
 constexpr int kSMs = 148;

@@ -282,9 +282,11 @@ __global__ void __launch_bounds__(CTAS == 1 ? 576 : (PW == 8 ? 448 : (SCN_EPI_CO
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"((uint32_t)P.tmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait(); // barriers and TMEM are set up: from here on the kernel reads what the previous kernel on the stream wrote
   const uint32_t tmemBase = *tmemSlot;
   const int accCols = P.T * P.Cout; // columns of one accumulator stage
   const bool prof = P.prof != nullptr;
@@ -748,6 +750,8 @@ __global__ void k_pad_rows_bf16(const float *__restrict__ in, __nv_bfloat16 *__r
 }
 // fp32 -> bf16 (rn) copy of a feature matrix, for inputs that arrive without a bf16 shadow
 __global__ void __launch_bounds__(256) k_to_bf16(const float *__restrict__ x, uint2 *__restrict__ y, long n4) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
     __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
@@ -759,7 +763,7 @@ __global__ void __launch_bounds__(256) k_to_bf16(const float *__restrict__ x, ui
 }
 int to_bf16(const float *x, void *y, long n, cudaStream_t s) {
   SCN_CHECK(n % 4 == 0, "bf16 copy needs an element count that is a multiple of 4");
-  if (n) k_to_bf16<<<stream_grid(n / 4, 256), 256, 0, LS(s)>>>(x, static_cast<uint2 *>(y), n / 4);
+  if (n) SCN_CUDA(launch_pdl(k_to_bf16, dim3(stream_grid(n / 4, 256)), dim3(256), 0, LS(s), x, static_cast<uint2 *>(y), n / 4));
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -866,7 +870,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (P.bf16) {
     if (!in16) {
       SCN_TRY(stream_scratch(s, kScratchBf16, (size_t)nInRows * Cin * 2 + 16, &tmp16));
-      if (nInRows) k_to_bf16<<<stream_grid(nInRows * Cin / 4, 256), 256, 0, LS(s)>>>(in, static_cast<uint2 *>(tmp16), nInRows * Cin / 4);
+      if (nInRows) SCN_CUDA(launch_pdl(k_to_bf16, dim3(stream_grid(nInRows * Cin / 4, 256)), dim3(256), 0, LS(s), in, static_cast<uint2 *>(tmp16), nInRows * Cin / 4));
       in16 = tmp16;
     }
     P.in = static_cast<const unsigned char *>(in16);
@@ -978,14 +982,14 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (envPw8 < 0) envPw8 = getenv("SCN_TC_PW8") ? atoi(getenv("SCN_TC_PW8")) : 0;
   const bool pw8 = ctas == 2 && ((packG > 1 && (envPw8 & 1)) || (packG == 1 && (envPw8 & 2)));
   const int th2 = 32 * (pw8 ? 14 : 10);
-  if (packG == 2) { if (pw8) conv_plan_tc<true, 8, 2, 2><<<grid, th2, smem, LS(s)>>>(P); else conv_plan_tc<true, 4, 2, 2><<<grid, th2, smem, LS(s)>>>(P); }
-  else if (packG == 4) { if (pw8) conv_plan_tc<true, 8, 4, 2><<<grid, th2, smem, LS(s)>>>(P); else conv_plan_tc<true, 4, 4, 2><<<grid, th2, smem, LS(s)>>>(P); }
+  if (packG == 2) { if (pw8) SCN_CUDA(launch_pdl(conv_plan_tc<true, 8, 2, 2>, dim3(grid), dim3(th2), (size_t)smem, LS(s), P)); else SCN_CUDA(launch_pdl(conv_plan_tc<true, 4, 2, 2>, dim3(grid), dim3(th2), (size_t)smem, LS(s), P)); }
+  else if (packG == 4) { if (pw8) SCN_CUDA(launch_pdl(conv_plan_tc<true, 8, 4, 2>, dim3(grid), dim3(th2), (size_t)smem, LS(s), P)); else SCN_CUDA(launch_pdl(conv_plan_tc<true, 4, 4, 2>, dim3(grid), dim3(th2), (size_t)smem, LS(s), P)); }
   else if (ctas == 2) {
-    if (P.bf16) { if (pw8) conv_plan_tc<true, 8, 1, 2><<<grid, th2, smem, LS(s)>>>(P); else conv_plan_tc<true, 4, 1, 2><<<grid, th2, smem, LS(s)>>>(P); }
-    else { if (pw8) conv_plan_tc<false, 8, 1, 2><<<grid, th2, smem, LS(s)>>>(P); else conv_plan_tc<false, 4, 1, 2><<<grid, th2, smem, LS(s)>>>(P); }
+    if (P.bf16) { if (pw8) SCN_CUDA(launch_pdl(conv_plan_tc<true, 8, 1, 2>, dim3(grid), dim3(th2), (size_t)smem, LS(s), P)); else SCN_CUDA(launch_pdl(conv_plan_tc<true, 4, 1, 2>, dim3(grid), dim3(th2), (size_t)smem, LS(s), P)); }
+    else { if (pw8) SCN_CUDA(launch_pdl(conv_plan_tc<false, 8, 1, 2>, dim3(grid), dim3(th2), (size_t)smem, LS(s), P)); else SCN_CUDA(launch_pdl(conv_plan_tc<false, 4, 1, 2>, dim3(grid), dim3(th2), (size_t)smem, LS(s), P)); }
   } else {
-    if (P.bf16) conv_plan_tc<true, 8, 1, 1><<<grid, 32 * 14, smem, LS(s)>>>(P);
-    else conv_plan_tc<false, 8, 1, 1><<<grid, 32 * 14, smem, LS(s)>>>(P);
+    if (P.bf16) SCN_CUDA(launch_pdl(conv_plan_tc<true, 8, 1, 1>, dim3(grid), dim3(32 * 14), (size_t)smem, LS(s), P));
+    else SCN_CUDA(launch_pdl(conv_plan_tc<false, 8, 1, 1>, dim3(grid), dim3(32 * 14), (size_t)smem, LS(s), P));
   }
   SCN_CUDA(cudaGetLastError());
   if (envProf) { // developer aid: mean stall cycles per role over the CTAs of this launch
@@ -999,7 +1003,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
     cudaFreeAsync(P.prof, s);
   }
   if (out16 && P.kSplit > 1 && nOutRows > 0) // partial sums were accumulated atomically: the bf16 copy needs the finished rows
-    k_to_bf16<<<stream_grid(nOutRows * Cout / 4, 256), 256, 0, LS(s)>>>(out, static_cast<uint2 *>(out16), nOutRows * Cout / 4);
+    SCN_CUDA(launch_pdl(k_to_bf16, dim3(stream_grid(nOutRows * Cout / 4, 256)), dim3(256), 0, LS(s), out, static_cast<uint2 *>(out16), nOutRows * Cout / 4));
   if (wimgOwned) cudaFreeAsync(wimg, s);
   if (wimg2Owned) cudaFreeAsync(wimg2, s);
 

@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(256) k_bn_stats(const float *__restrict__ x, l
 __global__ void __launch_bounds__(256) k_bn_small(const float *__restrict__ x, float *__restrict__ y, int n, int C, BnFin F, float leak, void *__restrict__ y16) {
   __shared__ float4 S[256], Q[256];
   __shared__ float sScale[32], sShift[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x, cgl = tid & 7, rl = tid >> 3; // 8 float4 column groups x 32 row lanes
   const int cg = blockIdx.x * 8 + cgl, cv = C >> 2;
   const bool live = cg < cv;
@@ -235,6 +237,8 @@ __global__ void __launch_bounds__(256) k_bn_apply_scalar(const float *__restrict
 __global__ void __launch_bounds__(256) k_bn_apply_sums(const float *__restrict__ x, float *__restrict__ y, long total4, int cv, const double *__restrict__ sums,
                                                        BnFin F, float leak, void *__restrict__ y16) {
   __shared__ __align__(16) float sScale[kFusedStatsC], sShift[kFusedStatsC];
+  pdl_launch_dependents();
+  pdl_wait(); // (the sums come from the producing convolution's epilogue)
   for (int c = threadIdx.x; c < F.C; c += 256) {
     double a = 0, b = 0;
     for (int r = 0; r < kBnReplicas; r++) { a += sums[(size_t)r * 2 * kFusedStatsC + c]; b += sums[(size_t)r * 2 * kFusedStatsC + kFusedStatsC + c]; }
@@ -283,7 +287,7 @@ int bn_forward_from_sums(const float *x, float *y, long n, int C, const double *
   SCN_CHECK(C % 4 == 0 && C <= kFusedStatsC && (mode == 0 || mode == 2) && n > 0, "bn_forward_from_sums: unsupported configuration");
   BnFin F{n, C, mode, eps, momentum, saveMean, saveInvStd, runningMean, runningVar, weight, bias, nullptr, nullptr};
   const long total4 = n * C / 4;
-  k_bn_apply_sums<<<stream_grid(total4, 256), 256, 0, LS(s)>>>(x, y, total4, C / 4, sums, F, leak, y16);
+  SCN_CUDA(launch_pdl(k_bn_apply_sums, dim3(stream_grid(total4, 256)), dim3(256), 0, LS(s), x, y, total4, C / 4, sums, F, leak, y16));
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
@@ -297,7 +301,7 @@ int bn_forward(const float *x, float *y, long n, int C, float *saveMean, float *
   BnFin F{n, C, mode, eps, momentum, saveMean, saveInvStd, runningMean, runningVar, weight, bias, scale, shift};
   SCN_CHECK(!y16 || C % 4 == 0, "bf16 shadow needs a channel count that is a multiple of 4");
   if (C % 4 == 0 && n > 0 && n <= 2048) { // small levels: statistics, finalize and apply in ONE launch
-    k_bn_small<<<cdiv(C, 32), 256, 0, LS(s)>>>(x, y, (int)n, C, F, leak, y16);
+    SCN_CUDA(launch_pdl(k_bn_small, dim3(cdiv(C, 32)), dim3(256), 0, LS(s), x, y, (int)n, C, F, leak, y16));
     SCN_CUDA(cudaGetLastError());
     return 0;
   }
