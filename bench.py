@@ -339,7 +339,7 @@ def leg_train(args, rank, world, dev, scn, steps=5, warmup=2):
     net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
     net = net.to(dev).train()
     coords_np = synthetic.building_coords(seed=rank)
-    coords = torch.from_numpy(coords_np)
+    coords = torch.from_numpy(coords_np).pin_memory()  # host coordinates as in the reference (ioLayers.py:60), page-locked: a pageable 37 MB copy blocks the host for ~3 ms
     feats = torch.from_numpy(fpn_util.features_for(coords_np)).to(dev)
     params = [p for p in net.parameters() if p.requires_grad]
     red = distributed.GradientReducer(params)

@@ -211,26 +211,49 @@ __global__ void __launch_bounds__(64) k_nms_mask(const float *__restrict__ boxes
   }
   mask[(long)i * words + jw] = bits;
 }
-// one CTA: greedy sweep in score order; keep[] = positions (in the sorted list) that survive, at most postMax of them
+// One CTA: greedy sweep in score order, 64 candidates at a time.  Within a block of 64 one thread resolves who survives from the
+// block's diagonal mask words (register work); then every thread ORs the rows of the survivors into its word of the `removed`
+// bitmap.  keep[] = indices of the survivors (into the caller's boxes), at most postMax; stops as soon as postMax are found.
 __global__ void __launch_bounds__(256) k_nms_sweep(const unsigned long long *__restrict__ mask, int n, int words, const long *__restrict__ sortedIdx, long postMax,
                                                    long *__restrict__ keep, long *__restrict__ nKeep) {
   extern __shared__ unsigned long long removed[];
-  __shared__ int s_alive;
+  __shared__ unsigned long long s_diag[64];
+  __shared__ unsigned long long s_keptBits;
+  __shared__ long s_kept;
   for (int w = threadIdx.x; w < words; w += blockDim.x) removed[w] = 0;
+  if (threadIdx.x == 0) s_kept = 0;
   __syncthreads();
-  long kept = 0;
-  for (int i = 0; i < n; i++) {
-    if (threadIdx.x == 0) s_alive = !((removed[i >> 6] >> (i & 63)) & 1ull);
+  for (int b = 0; b < words; b++) {
+    if (threadIdx.x < 64) {
+      const int row = b * 64 + threadIdx.x;
+      s_diag[threadIdx.x] = row < n ? mask[(long)row * words + b] : 0ull;
+    }
     __syncthreads();
-    const bool alive = s_alive;
-    if (alive) {
-      if (threadIdx.x == 0 && kept < postMax) keep[kept] = sortedIdx ? sortedIdx[i] : i;
-      kept++;
-      for (int w = (i >> 6) + threadIdx.x; w < words; w += blockDim.x) removed[w] |= mask[(long)i * words + w];
+    if (threadIdx.x == 0) {
+      unsigned long long alive = ~removed[b], kb = 0;
+      const int left = n - b * 64;
+      if (left < 64) alive &= (1ull << left) - 1ull;
+      long k = s_kept;
+      for (int t = 0; t < 64 && k < postMax; t++)
+        if ((alive >> t) & 1ull) {
+          kb |= 1ull << t;
+          alive &= ~s_diag[t];
+          keep[k++] = sortedIdx ? sortedIdx[b * 64 + t] : (long)(b * 64 + t);
+        }
+      s_keptBits = kb;
+      s_kept = k;
+    }
+    __syncthreads();
+    if (s_kept >= postMax) break;
+    const unsigned long long kb = s_keptBits;
+    for (int w = b + 1 + threadIdx.x; w < words; w += blockDim.x) {
+      unsigned long long acc = removed[w];
+      for (unsigned long long rest = kb; rest; rest &= rest - 1) acc |= mask[(long)(b * 64 + __ffsll((long long)rest) - 1) * words + w];
+      removed[w] = acc;
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *nKeep = kept < postMax ? kept : postMax;
+  if (threadIdx.x == 0) *nKeep = s_kept;
 }
 __global__ void k_gather_boxes(const float *__restrict__ boxes, const long *__restrict__ idx, long n, float *__restrict__ out) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
