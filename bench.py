@@ -384,7 +384,8 @@ def leg_train(args, rank, world, dev, scn, steps=5, warmup=2):
            "forward_ms": t[0].item(), "backward_ms": t[1].item(), "allreduce_exposed_ms": t[2].item(), "collectives_per_step": n_coll,
            "gradient_bytes": red.nbytes(), "allreduce_alone": bus, "loss": float(loss), "params_with_grad": with_grad, "params": len(params),
            "scaling": "weak", "steps": steps, "math": {0: "fp32", 1: "tf32", 2: "bf16"}[scn.SCN.math_mode()],
-           "note": "6c_fpn4321 backbone, one B470 building per rank, autograd layer by layer; gradients are views of one flat buffer, buckets all-reduced from hooks while the backward runs"}
+           "replayed": bool(net.__dict__.get("_program_train") is not None), "program_backward_calls": int(scn.SCN.lib().scn_debug_counter(11)),
+           "note": "6c_fpn4321 backbone, one B470 building per rank; first step layer by layer under autograd while the calls are recorded, later steps = ONE autograd node (scn_program_run in training mode + scn_program_backward); gradients land in one flat buffer, buckets all-reduced from hooks"}
     del net, red
     torch.cuda.empty_cache()
     return out

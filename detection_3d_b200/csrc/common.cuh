@@ -53,6 +53,7 @@ enum DebugCounter {
   kCntBnFromSums = 8,      // BatchNorm ops that ran their apply pass from epilogue statistics
   kCntSplitLaunch = 9,     // conv_plan_tc launches that split the filter offsets over CTAs (atomic epilogue)
   kCntSimtLaunch = 10,     // CUDA-core convolution launches (plan or list)
+  kCntTrainReplay = 11,    // backward passes run by the program executor (scn_program_backward)
   kCntCounters = 16
 };
 extern std::atomic<long> g_counters[kCntCounters];

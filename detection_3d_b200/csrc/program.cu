@@ -66,6 +66,12 @@ struct scn_program {
   cudaEvent_t evEnd[2] = {nullptr, nullptr}; // end of the last two runs on `stream` (throttle of scn_program_prepare)
   long nRuns = 0;
   cudaStream_t stream = nullptr;
+  // Training replay (scn_program_set_training): every register stays alive until the next run, nothing is written as bf16 only,
+  // the layers run on the caller's Metadata (reference numbering), and every BatchNorm keeps its saveMean / saveInvStd for
+  // scn_program_backward.
+  bool train = false;
+  std::vector<float *> bnSave;  // per op: [2][C] floats (train mode), from the slot pool
+  scn_metadata *lastMd = nullptr; // Metadata of the last training run (the backward pass needs its rulebooks)
 };
 
 static void *slot_get(scn_program *p, size_t bytes) {
@@ -88,6 +94,9 @@ static void slot_put(scn_program *p, void *ptr) {
   for (Slot &s : p->slots) if (s.p == ptr) { s.busy = false; return; }
 }
 static void release_regs(scn_program *p, bool outputsToo) {
+  if (outputsToo) {
+    for (float *&b : p->bnSave) if (b) { slot_put(p, b); b = nullptr; }
+  }
   for (size_t i = 0; i < p->regs.size(); i++) {
     Reg &r = p->regs[i];
     if (!outputsToo && p->isOutput[i]) continue;
@@ -115,6 +124,11 @@ void scn_program_destroy(scn_program *p) {
   if (p->ms) scn_metadata_destroy(p->ms);
   if (p->evCoords) cudaEventDestroy(p->evCoords);
   delete p;
+}
+int scn_program_set_training(scn_program *p, int on) {
+  SCN_CHECK(p, "null program");
+  p->train = on != 0;
+  return 0;
 }
 int scn_program_add(scn_program *p, int kind, const long *iargs, int n_iargs, const double *fargs, int n_fargs) {
   SCN_CHECK(p && kind >= K_INPUT && kind <= K_ADD && n_iargs <= 24 && n_fargs <= 4, "bad program op");
@@ -349,7 +363,10 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   scn_metadata *M = m;
   const Op *inOp = nullptr;
   for (const Op &o : p->ops) if (o.kind == K_INPUT) { inOp = &o; break; }
-  if (internalOn && inOp && inOp->a[4] != 0 && !scn_input_layer_built(m, nullptr, nullptr)) {
+  const bool train = p->train;
+  p->lastMd = train ? m : nullptr;
+  if (train) p->bnSave.assign(p->ops.size(), nullptr);
+  if (!train && internalOn && inOp && inOp->a[4] != 0 && !scn_input_layer_built(m, nullptr, nullptr)) {
     if (coords_on_device == 1) {
       if (!p->evCoords) SCN_CUDA(cudaEventCreateWithFlags(&p->evCoords, cudaEventDisableTiming));
       SCN_CUDA(cudaEventRecord(p->evCoords, s));
@@ -478,7 +495,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
           if (rc) break;
         }
         rc = scn_get_nactive(M, a + 2, &n);
-        const bool half = a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
+        const bool half = !train && a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[11], half || a[22] >= 0 || a[18] >= 0, half);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
@@ -495,7 +512,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_CONV: { // in, out, inS[3], outS[3], f[3], s[3], w, bias, Cin, Cout
         long n = 0, nr = 0;
         rc = scn_convolution_prepare(M, a + 2, a + 5, a + 8, a + 11, &n, &nr);
-        const bool half = a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
+        const bool half = !train && a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], half || a[22] >= 0 || a[18] >= 0, half);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
@@ -510,7 +527,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_DECONV: {
         long n = 0;
         rc = scn_get_nactive(M, a + 5, &n);
-        const bool half = a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
+        const bool half = !train && a[23] == 1 && mode == 2 && n >= kHalfOnlyRows && scn_tensor_core_path_available();
         if (rc == 0) rc = alloc_reg(a[1], n, (int)a[17], half || a[22] >= 0 || a[18] >= 0, half);
         const Reg &I = p->regs[a[0]];
         if (rc == 0) { arm(op); arm_lateral(op); }
@@ -525,17 +542,24 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_BN: { // in, out, C, weight, bias, running mean, running var, mode; f: eps, momentum, leakiness
         const Reg &I = p->regs[a[0]];
         const bool fromSums = a[21] >= 0 && p->statsDone[a[21]] && I.rows > 0;
-        const bool halfOnly = fromSums && a[19] == 1 && mode == 2 && scn_tensor_core_path_available();
+        const bool halfOnly = !train && fromSums && a[19] == 1 && mode == 2 && scn_tensor_core_path_available();
         rc = alloc_reg(a[1], I.rows, (int)a[2], true, halfOnly);
+        float *saveM = p->bnScratch, *saveI = p->bnScratch + scn::kBnMaxC;
+        if (rc == 0 && train) { // kept for the backward pass
+          p->bnSave[i] = static_cast<float *>(slot_get(p, (size_t)2 * a[2] * 4));
+          if (!p->bnSave[i]) { rc = -1; break; }
+          saveM = p->bnSave[i];
+          saveI = saveM + a[2];
+        }
         if (rc == 0 && fromSums) {
           ++scn::g_counters[scn::kCntBnFromSums];
-          rc = scn::bn_forward_from_sums(I.p, p->regs[a[1]].p, I.rows, (int)a[2], p->stats + a[21] * statsStride, p->bnScratch, p->bnScratch + scn::kBnMaxC,
+          rc = scn::bn_forward_from_sums(I.p, p->regs[a[1]].p, I.rows, (int)a[2], p->stats + a[21] * statsStride, saveM, saveI,
                                          const_cast<float *>(P(a[5])), const_cast<float *>(P(a[6])), P(a[3]), P(a[4]), (float)op.f[0], (float)op.f[1], (int)a[7],
                                          (float)op.f[2], s, p->regs[a[1]].p16);
           break;
         }
         if (rc == 0)
-          rc = scn_batchnorm_forward(I.p, p->regs[a[1]].p, I.rows, (int)a[2], p->bnScratch, p->bnScratch + scn::kBnMaxC, const_cast<float *>(P(a[5])),
+          rc = scn_batchnorm_forward(I.p, p->regs[a[1]].p, I.rows, (int)a[2], saveM, saveI, const_cast<float *>(P(a[5])),
                                      const_cast<float *>(P(a[6])), P(a[3]), P(a[4]), (float)op.f[0], (float)op.f[1], (int)a[7], (float)op.f[2], s, p->regs[a[1]].p16);
         break;
       }
@@ -549,7 +573,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     }
     if (rc) break;
     scn::timeline_mark("main", op.kind, a[2], p->regs[a[op.kind == K_ADD ? 2 : (op.kind == K_INPUT ? 0 : 1)]].rows);
-    for (int r = 0; r < p->nRegs; r++) // free what this op used last (stream-ordered: safe right after the launch)
+    for (int r = 0; !train && r < p->nRegs; r++) // free what this op used last (stream-ordered: safe right after the launch)
       if (p->lastUse[r] == i && !p->isOutput[r]) {
         Reg &R = p->regs[r];
         if (R.p) { slot_put(p, R.p); R.p = nullptr; }
@@ -569,6 +593,129 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   if (!ev) SCN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   SCN_CUDA(cudaEventRecord(ev, s));
   p->nRuns++;
+  return 0;
+}
+
+// The backward pass of the last TRAINING run (scn_program_set_training), op by op in reverse: the same native backward entries
+// the layer-by-layer autograd Functions call (scn_*_convolution_backward, scn_batchnorm_backward, NetworkInNetwork backward for a
+// folded lateral), driven from C++ instead of ~100 Python autograd nodes.  d_out[i]: gradient of output register out_regs[i]
+// ([rows][cols] float32, device; not modified).  param_grads[j]: device buffer of parameter j's gradient (overwritten) or NULL
+// (not wanted).  param_live[j] = 1 when parameter j received a gradient: ops whose output reaches no program output (the dead
+// top-down levels of the FPN) are skipped, as autograd skips them.  d_features: NULL or the gradient of the
+// network input [nIn rows][planes].
+int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const float *const *d_out, const void *const *params, void *const *param_grads,
+                         int n_params, float *d_features, int *param_live) {
+  SCN_CHECK(p && p->train && p->lastMd && p->nRegs > 0, "scn_program_backward needs a preceding training run of this program");
+  scn_metadata *m = p->lastMd;
+  cudaStream_t s = p->stream;
+  auto P = [&](long i) -> const float * { return (i < 0 || i >= n_params) ? nullptr : static_cast<const float *>(params[i]); };
+  auto G = [&](long i) -> float * { return (i < 0 || i >= n_params) ? nullptr : static_cast<float *>(param_grads[i]); };
+  std::vector<char> live(std::max(1, n_params), 0);
+  int rc = 0;
+  auto mark = [&](long i) -> int {
+    if (i < 0 || i >= n_params || !param_grads[i]) return 0;
+    if (live[i]) { scn::set_error("program backward: a parameter is used by more than one op (not supported by the replayed training step)"); return -2; }
+    live[i] = 1;
+    return 0;
+  };
+  std::vector<float *> g(p->nRegs, nullptr);
+  auto elems = [&](long r) -> long { return p->regs[r].rows * (long)p->regs[r].cols; };
+  // adds `src` to the gradient of register r (first contribution: copy; `owned`: src is a slot buffer that may be adopted)
+  auto contribute = [&](long r, float *src, bool owned) -> int {
+    const long n = elems(r);
+    if (n == 0) { if (owned) slot_put(p, src); return 0; }
+    if (!g[r]) {
+      if (owned) { g[r] = src; return 0; }
+      g[r] = static_cast<float *>(slot_get(p, (size_t)n * 4));
+      if (!g[r]) return -1;
+      SCN_CUDA(cudaMemcpyAsync(g[r], src, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+      return 0;
+    }
+    int r2 = scn_add_features(g[r], src, g[r], n, s, nullptr);
+    if (owned) slot_put(p, src);
+    return r2;
+  };
+  for (int i = 0; i < n_out; i++) {
+    SCN_CHECK(out_regs[i] >= 0 && out_regs[i] < p->nRegs && p->isOutput[out_regs[i]], "not an output register");
+    if (d_out[i]) SCN_TRY(contribute(out_regs[i], const_cast<float *>(d_out[i]), false));
+  }
+  for (int i = (int)p->ops.size() - 1; i >= 0 && rc == 0; i--) {
+    const Op &op = p->ops[i];
+    const long *a = op.a;
+    const long outReg = op.kind == K_INPUT ? a[0] : (op.kind == K_ADD ? a[2] : a[1]);
+    float *dy = g[outReg];
+    if (!dy) continue; // nothing downstream of this op reaches an output
+    switch (op.kind) {
+      case K_INPUT:
+        if (d_features) rc = scn_input_layer_backward(m, d_features, dy, (int)a[6]);
+        break;
+      case K_ADD:
+        rc = contribute(a[0], dy, false);
+        if (rc == 0) rc = contribute(a[1], dy, false);
+        break;
+      case K_BN: {
+        const Reg &X = p->regs[a[0]], &Y = p->regs[a[1]];
+        if (X.rows == 0) break;
+        SCN_CHECK(X.p && Y.p && p->bnSave[i], "program backward: BatchNorm activations were not kept");
+        float *dx = static_cast<float *>(slot_get(p, (size_t)elems(a[0]) * 4));
+        if (!dx) { rc = -1; break; }
+        if ((rc = mark(a[3])) || (rc = mark(a[4]))) break;
+        rc = scn_batchnorm_backward(X.p, dx, Y.p, dy, X.rows, (int)a[2], p->bnSave[i], p->bnSave[i] + a[2], P(a[3]), G(a[3]), G(a[4]), (float)op.f[2], s);
+        if (rc == 0) rc = contribute(a[0], dx, true);
+        break;
+      }
+      default: { // the three convolution kinds
+        const Reg &I = p->regs[a[0]];
+        const int Cin = (int)(op.kind == K_SUBM ? a[10] : a[16]), Cout = (int)(op.kind == K_SUBM ? a[11] : a[17]);
+        const long wi = op.kind == K_SUBM ? a[8] : a[14], bi = op.kind == K_SUBM ? a[9] : a[15];
+        if (a[22] >= 0 && (rc = contribute(a[22], dy, false))) break;       // addend fused into the epilogue: out = conv + other
+        if (a[18] >= 0) {                                                   // folded lateral: out += Y @ W_lat
+          const Reg &Y = p->regs[a[18]];
+          const int Cl = (int)a[20];
+          if (Y.rows > 0) {
+            float *dl = static_cast<float *>(slot_get(p, (size_t)Y.rows * Cl * 4));
+            if (!dl) { rc = -1; break; }
+            if ((rc = mark(a[19]))) break;
+            rc = scn_network_in_network_backward_input(dl, dy, P(a[19]), Y.rows, Cl, Cout, s);
+            if (rc == 0 && G(a[19])) rc = scn_network_in_network_backward_params(Y.p, dy, G(a[19]), nullptr, Y.rows, Cl, Cout, s);
+            if (rc == 0) rc = contribute(a[18], dl, true);
+            if (rc) break;
+          }
+        }
+        if (I.rows == 0 || p->regs[outReg].rows == 0) break;
+        SCN_CHECK(I.p, "program backward: convolution input was not kept");
+        if ((rc = mark(wi)) || (rc = mark(bi))) break;
+        // the gradient of the network input is only computed on request (App. D.13)
+        bool inputIsNetworkInput = false;
+        for (const Op &o : p->ops) if (o.kind == K_INPUT && o.a[0] == a[0]) inputIsNetworkInput = true;
+        const bool wantDIn = !(inputIsNetworkInput && !d_features) || op.kind != K_SUBM;
+        float *din = wantDIn ? static_cast<float *>(slot_get(p, (size_t)elems(a[0]) * 4)) : nullptr;
+        if (wantDIn && !din) { rc = -1; break; }
+        float *dw = G(wi);
+        float *dwTmp = nullptr;
+        if (!dw) { // gradient not wanted: the entry still needs a buffer
+          long K = 1;
+          for (int d = 0; d < 3; d++) K *= op.kind == K_SUBM ? a[5 + d] : a[8 + d];
+          dwTmp = static_cast<float *>(slot_get(p, (size_t)K * Cin * Cout * 4));
+          if (!dwTmp) { rc = -1; break; }
+          dw = dwTmp;
+        }
+        if (op.kind == K_SUBM) rc = scn_submanifold_convolution_backward(m, a + 2, a + 5, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
+        else if (op.kind == K_CONV) rc = scn_convolution_backward(m, a + 2, a + 5, a + 8, a + 11, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
+        else rc = scn_deconvolution_backward(m, a + 2, a + 5, a + 8, a + 11, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
+        if (dwTmp) slot_put(p, dwTmp);
+        if (rc == 0 && din) rc = contribute(a[0], din, true);
+        break;
+      }
+    }
+    if (rc) break;
+    slot_put(p, dy); // consumed (stream-ordered: the kernels above were queued before any later user of the slot)
+    g[outReg] = nullptr;
+  }
+  for (float *&q : g) if (q) { slot_put(p, q); q = nullptr; }
+  if (rc) return rc;
+  if (param_live) for (int j = 0; j < n_params; j++) param_live[j] = live[j];
+  ++scn::g_counters[scn::kCntTrainReplay];
   return 0;
 }
 

@@ -21,7 +21,10 @@ def _sum_features(tensors):
     acc = feats[0]
     for f in feats[1:]:
         if torch.is_grad_enabled() and (acc.requires_grad or f.requires_grad):
-            acc = acc + f
+            a, acc = acc, acc + f
+            tr = native._tr()
+            if tr is not None:  # a training forward is being recorded (program.Trace(training=True))
+                tr.add(5, [tr.reg(a), tr.reg(f), tr.new_reg(acc)])
         elif acc.is_cuda and acc.dtype == torch.float32 and acc.is_contiguous() and f.is_contiguous():
             acc = native.add_features(acc, f)
         else:

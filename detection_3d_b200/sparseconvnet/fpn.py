@@ -18,6 +18,7 @@ from .containers import AddTable, ConcatTable, Identity, Sequential, add_feature
 from .tensor import SparseConvNetTensor
 
 _PROGRAMS = os.environ.get("SCN_PROGRAM", "1") != "0"  # developer switch: always run layer by layer
+_TRAIN_PROGRAMS = os.environ.get("SCN_TRAIN_PROGRAM", "1") != "0"  # training forwards: replay too (one autograd node per forward)
 
 
 OutputLayer = L.OutputLayer  # (FPN_Net holds one in `layers_out`; the shipped forward never calls it)
@@ -134,6 +135,35 @@ class FPN_Net(nn.Module):
                 except Exception as e:  # the layer-by-layer path stays in charge
                     self.__dict__["_program_error"] = str(e)
                 return rpn_maps, roi_maps
+        if (_PROGRAMS and _TRAIN_PROGRAMS and self.training and torch.is_grad_enabled() and len(net0) == 2 and isinstance(net0[1], torch.Tensor)
+                and isinstance(net0[0], torch.Tensor)):
+            # Training: the first step runs layer by layer under autograd while the calls are recorded; later steps are ONE autograd node
+            # whose forward replays the program in training mode and whose backward is scn_program_backward.
+            coords, feats = net0[0], net0[1]
+            dev = self.layers_in[0].device
+            if dev is not None:
+                feats = feats.to(dev, non_blocking=True)
+                net0 = [coords, feats]
+            mode = native.math_mode()
+            prog = self.__dict__.get("_program_train")
+            if prog is not None and prog.usable(coords, feats, mode):
+                md = L.Metadata(self.dimension)
+                import detection_3d_b200.sparseconvnet as pkg
+                uniq = program.TrainFunction.apply(prog, md, coords, feats, *prog.params)
+                pkg.forward_pass_multiplyAdd_count += prog.last_macs
+                by_reg = dict(zip(sorted(set(prog.out_regs)), uniq))
+                maps = [SparseConvNetTensor(features=by_reg[r], metadata=md, spatial_size=s.clone()) for r, s in zip(prog.out_regs, prog.out_sizes)]
+                n = self.__dict__["_program_train_n_rpn"]
+                return maps[:n], maps[n:]
+            if prog is None and self.__dict__.get("_program_train_error") is None and feats.is_cuda:
+                with program.Trace(training=True) as tr:
+                    rpn_maps, roi_maps = self.forward_fpn(self.layers_in(net0))
+                try:
+                    self.__dict__["_program_train"] = program.Program(tr, [(m.features, m.spatial_size) for m in rpn_maps + roi_maps], mode)
+                    self.__dict__["_program_train_n_rpn"] = len(rpn_maps)
+                except Exception as e:  # the layer-by-layer path stays in charge
+                    self.__dict__["_program_train_error"] = str(e)
+                return rpn_maps, roi_maps
         return self.forward_fpn(self.layers_in(net0))
 
     def _has_prefetched(self, coords):
@@ -168,10 +198,12 @@ class FPN_Net(nn.Module):
         self.__dict__.pop("_program", None)
         self.__dict__.pop("_program_error", None)
         self.__dict__.pop("_prefetched", None)
+        for k in ("_program_train", "_program_train_error", "_program_train_n_rpn"):
+            self.__dict__.pop(k, None)
 
     # The recorded program and the Metadata objects built ahead are handles into the native library (ctypes pointers):
     # a copy / pickle of the network (EMA copies, torch.save(model), as with the reference) drops them and records again.
-    _RUNTIME_STATE = ("_program", "_program_error", "_program_n_rpn", "_prefetched")
+    _RUNTIME_STATE = ("_program", "_program_error", "_program_n_rpn", "_prefetched", "_program_train", "_program_train_error", "_program_train_n_rpn")
 
     def __getstate__(self):
         state = self.__dict__.copy()

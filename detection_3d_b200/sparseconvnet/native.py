@@ -377,7 +377,7 @@ def BatchNormalization_updateOutput(input_features, output_features, saveMean, s
     _attach_shadow(output_features, sh)
     tr = _tr()
     if tr is not None:
-        if train:
+        if train and not tr.training:
             tr.fail("training-mode BatchNorm is not recorded")
         tr.add(4, [tr.reg(input_features), tr.new_reg(output_features), c, tr.param(weight), tr.param(bias), tr.param(runningMean),
                    tr.param(runningVar), mode], [eps, momentum, leakiness])

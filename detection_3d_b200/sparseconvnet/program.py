@@ -21,7 +21,8 @@ def active():
 
 
 class Trace(object):
-    def __init__(self):
+    def __init__(self, training=False):
+        self.training = training  # a training forward is being recorded (training-mode BatchNorm, torch adds under autograd)
         self.ops = []          # (kind, [ints], [floats])
         self.regs = {}         # id(tensor) -> register
         self.params = []       # parameter / buffer tensors, index = position
@@ -107,6 +108,7 @@ class Program(object):
         if trace.failed:
             raise RuntimeError(trace.failed)
         self.math_mode = math_mode
+        self.training = trace.training
         self.params = trace.params
         self.out_regs, self.out_sizes = [], []
         for feats, size in outputs:
@@ -126,6 +128,8 @@ class Program(object):
         uniq = sorted(set(self.out_regs))
         check(lib().scn_program_finish(self._h, len(trace.regs), (C.c_int * len(uniq))(*uniq), len(uniq)))
         self.n_ops = len(trace.ops)
+        if self.training:
+            check(lib().scn_program_set_training(self._h, 1))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -183,3 +187,44 @@ class Program(object):
             check(lib().scn_program_outputs_copy(self._h, metadata._h, len(part), regs, sizes, dst))
         outs = [tens[r] for r in self.out_regs]
         return outs, macs.value
+
+    def backward(self, regs, d_outs, want_d_features, n_in_rows):
+        """Backward pass of the last training run (scn_program_backward).  d_outs[i]: gradient (or None) of output register
+        regs[i].  -> (one gradient tensor or None per recorded parameter, gradient of the network input or None)."""
+        n = len(self.params)
+        pairs = [(r, g.contiguous()) for r, g in zip(regs, d_outs) if g is not None and g.numel()]
+        grads = [torch.empty_like(p) if (p.requires_grad and p.is_floating_point()) else None for p in self.params]
+        d_feats = torch.empty((n_in_rows, self.planes), dtype=torch.float32, device=self.params[0].device) if want_d_features else None
+        ptrs = (C.c_void_p * n)(*[p.data_ptr() for p in self.params])
+        gptrs = (C.c_void_p * n)(*[None if g is None else g.data_ptr() for g in grads])
+        live = (C.c_int * n)()
+        k = max(1, len(pairs))
+        check(lib().scn_program_backward(self._h, len(pairs), (C.c_int * k)(*[r for r, _ in pairs]), (C.c_void_p * k)(*[g.data_ptr() for _, g in pairs]),
+                                         ptrs, gptrs, n, None if d_feats is None else C.c_void_p(d_feats.data_ptr()), live))
+        return [g if (g is not None and live[i]) else None for i, g in enumerate(grads)], d_feats
+
+
+class TrainFunction(torch.autograd.Function):
+    """One autograd node for a whole replayed training forward: forward = scn_program_run in training mode, backward =
+    scn_program_backward (the reference: one node per layer, ~100 per forward).  Returns one tensor per DISTINCT output
+    register, in the order of sorted(set(prog.out_regs))."""
+
+    @staticmethod
+    def forward(ctx, prog, md, coords, feats, *params):
+        outs, macs = prog.run(md, coords, feats)
+        prog.last_macs = macs
+        prog.run_id = getattr(prog, "run_id", 0) + 1
+        ctx.prog, ctx.md, ctx.n_in, ctx.run_id = prog, md, feats.size(0), prog.run_id
+        by_reg = dict(zip(prog.out_regs, outs))
+        ctx.regs = sorted(by_reg)
+        return tuple(by_reg[r] for r in ctx.regs)
+
+    @staticmethod
+    def backward(ctx, *d_outs):
+        prog = ctx.prog
+        if ctx.run_id != prog.run_id:
+            raise RuntimeError("replayed training step: another forward of this network ran before backward(); the activations are gone "
+                               "(set SCN_TRAIN_PROGRAM=0 to train layer by layer)")
+        grads, d_feats = prog.backward(ctx.regs, d_outs, ctx.needs_input_grad[3], ctx.n_in)
+        grads = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[4:])]
+        return (None, None, None, d_feats) + tuple(grads)

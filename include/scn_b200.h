@@ -180,6 +180,17 @@ int scn_program_finish(scn_program *p, int n_regs, const int *outputs, int n_out
 int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coords_on_device, long nrows, int ncols,
                     const float *features, const void *const *params, const long long *weight_tags, int n_params,
                     void *stream, double *macs);
+/* Training replay.  scn_program_set_training(p, 1): scn_program_run keeps every register (and every BatchNorm's saved mean / inverse
+ * standard deviation) until the next run, writes nothing as bf16 only and runs the layers on the caller's Metadata in the
+ * reference's numbering.  scn_program_backward then runs the backward pass of that run, op by op in reverse, through the same
+ * scn_*_backward entries the per-layer autograd Functions use (the reference: one autograd node per layer,
+ * sparseconvnet/{submanifoldConvolution,convolution,deconvolution,batchNormalization}.py).  d_out[i] = gradient of output register
+ * out_regs[i] (device, not modified); param_grads[j] = device buffer for parameter j's gradient (overwritten) or NULL; param_live[j]
+ * (host, may be NULL) = 1 when parameter j received one -- ops that reach no output are skipped, as autograd skips them;
+ * d_features = NULL or the gradient of the network input.  The Metadata of the run must still be alive. */
+int scn_program_set_training(scn_program *p, int on);
+int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const float *const *d_out, const void *const *params, void *const *param_grads,
+                         int n_params, float *d_features, int *param_live);
 /* Internal row numbering (used by scn_program_run, never handed to callers): rows of every grid are numbered by spatial
  * index instead of the reference's first-touch order in dense_hash_map iteration order, which removes the hash-order
  * emulation from the critical path.  scn_rows_to_reference_order hands a feature matrix computed under such a Metadata
@@ -290,7 +301,7 @@ long scn_kernel_launch_count(void);
  * that carried a lateral 1x1x1 stage, 4 = launches whose epilogue accumulated BatchNorm statistics, 5 = program registers
  * written as bf16 only, 6 = laterals run as a separate convolution + add (fallback), 7 = tcgen05 convolution launches,
  * 8 = BatchNorm ops applied from epilogue statistics, 9 = launches that split the filter offsets over CTAs (atomic
- * epilogue), 10 = CUDA-core convolution launches. */
+ * epilogue), 10 = CUDA-core convolution launches, 11 = backward passes run by scn_program_backward. */
 long scn_debug_counter(int which);
 
 /* Fusion requests for the NEXT convolution forward call made by this thread (what the program executor uses to fold the

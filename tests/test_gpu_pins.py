@@ -373,8 +373,10 @@ def test_replayed_program_tensor_core_vs_reference_golden(math):
 
 # ------------------------------------------------------------------ whole-network training step vs the reference's autograd
 @pytest.mark.parametrize("math", ["fp32", "tf32", "bf16"])
-def test_whole_network_training_step_vs_reference_autograd(math):
-    """Train-mode forward (batch statistics, running statistics updated), loss = sum of mean(f^2) over the returned maps,
+@pytest.mark.parametrize("replay", [False, True])
+def test_whole_network_training_step_vs_reference_autograd(math, replay):
+    """replay=True: the SECOND training step of the network, i.e. the recorded program replayed in training mode (one autograd node,
+    scn_program_run + scn_program_backward) from the same initial state.  Train-mode forward (batch statistics, running statistics updated), loss = sum of mean(f^2) over the returned maps,
     autograd backward through every layer kind, against the same step of the reference's scn.FPN_Net on its CPU extension
     (tests/golden/fpn_mini4_train.npz, tests/golden/make_golden.py::run_reference_fpn_train).  Parameters of the dead
     top-down levels get no gradient on either side.  Tolerances per parameter tensor (worst element / max|grad|, relative
@@ -398,6 +400,13 @@ def test_whole_network_training_step_vs_reference_autograd(math):
         net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
         net = net.cuda().train()
         coords = synthetic.building_coords(**bld)
+        if replay:  # first step records; then back to the initial state (in place: the program keeps the parameter tensors)
+            rpn, roi = net([torch.from_numpy(coords), torch.from_numpy(fpn_util.features_for(coords)).cuda()])
+            sum((m.features ** 2).mean() for m in rpn + roi).backward()
+            assert net.__dict__.get("_program_train") is not None, net.__dict__.get("_program_train_error")
+            net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+            net.zero_grad(set_to_none=True)
+            n0 = scn.SCN.lib().scn_debug_counter(11)
         rpn, roi = net([torch.from_numpy(coords), torch.from_numpy(fpn_util.features_for(coords)).cuda()])
         maps = rpn + roi
         assert len(maps) == int(g["n_maps"])
@@ -405,6 +414,8 @@ def test_whole_network_training_step_vs_reference_autograd(math):
         loss = sum(terms)
         loss.backward()
         torch.cuda.synchronize()
+        if replay:
+            assert scn.SCN.lib().scn_debug_counter(11) == n0 + 1, "the backward pass did not run through scn_program_backward"
     finally:
         scn.set_math_mode("fp32")
     np.testing.assert_allclose(np.array([float(t) for t in terms]), g["map_mean_sq"], rtol=tol)
