@@ -40,6 +40,7 @@ SYMBOLS = {
     "scn_program_output_copy": (_i, [_vp, _vp, _i, L3, _vp]),
     "scn_program_outputs_copy": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "scn_rows_to_reference_order_multi": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "scn_rows_from_reference_order": (_i, [_vp, _vp, L3, _vp, _vp, _i]),
     "scn_set_pool_growth": (_i, [_i]),
     "scn_input_layer_built": (_i, [_vp, _pl, _pi]),
     "scn_copy_device": (_i, [_vp, _vp, _l, _vp]),

@@ -60,7 +60,13 @@ int input_forward_pad16(const float *in, float *out, void *out16, int nOut, int 
 int input_backward(float *din, const float *dout, long nIn, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
 int add_rows(const float *a, const float *b, float *o, long n, cudaStream_t s, void *o16);
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
-                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn = 0, int mathMode = 0);
+                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn = 0, int mathMode = 0,
+                       const void *in16 = nullptr, const void *dout16 = nullptr, const int *planNbr = nullptr, const int *planOutRow = nullptr,
+                       const unsigned long long *planMask = nullptr, int planPos = 0);
+int dout_bf16_copy(const float *d_out, long n, cudaStream_t s, const void **out);
+bool dw_plan_ok(int Cin, int Cout, int K, int mathMode);
+void bwd_in16_arm(const void *in16);
+const void *bwd_in16_take();
 int transpose_weights(const float *W, float *Wt, int K, int Cin, int Cout, int reverse, cudaStream_t s);
 int tc_available();
 void set_pool_growth(int on);
@@ -450,7 +456,7 @@ int scn_rows_to_reference_order(scn_metadata *ref, scn_metadata *internal, const
 namespace {
 constexpr int kMaxOutMaps = 8;
 struct OutMap { const int4 *refCoords; const int *p2id; const float4 *src; float4 *dst; scn::GridView g; int n, c4, firstWarp; };
-struct OutMaps { OutMap m[kMaxOutMaps]; int count, totalWarps; };
+struct OutMaps { OutMap m[kMaxOutMaps]; int count, totalWarps, scatter; }; // scatter: dst[internal row] = src[reference row] (gradients on their way in)
 __global__ void __launch_bounds__(256) k_rows_to_reference_multi(OutMaps P) {
   scn::pdl_launch_dependents();
   scn::pdl_wait();
@@ -467,12 +473,26 @@ __global__ void __launch_bounds__(256) k_rows_to_reference_multi(OutMaps P) {
       srcRow = p >= 0 ? M.p2id[p] : -1;
     }
     srcRow = __shfl_sync(0xffffffffu, srcRow, 0);
+    if (P.scatter) {
+      if (srcRow >= 0) for (int j = lane; j < M.c4; j += 32) M.dst[(long)srcRow * M.c4 + j] = M.src[(long)row * M.c4 + j];
+      continue;
+    }
     for (int j = lane; j < M.c4; j += 32) M.dst[(long)row * M.c4 + j] = srcRow >= 0 ? M.src[(long)srcRow * M.c4 + j] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
+static int rows_reorder_multi(scn_metadata *ref, scn_metadata *internal, int n_maps, const long *sizes, const float *const *src, float *const *dst,
+                              const int *cols, int scatter);
 } // namespace
 int scn_rows_to_reference_order_multi(scn_metadata *ref, scn_metadata *internal, int n_maps, const long *sizes, const float *const *src, float *const *dst,
                                       const int *cols) {
+  return rows_reorder_multi(ref, internal, n_maps, sizes, src, dst, cols, 0);
+}
+int scn_rows_from_reference_order(scn_metadata *ref, scn_metadata *internal, const long size[3], const float *src, float *dst, int cols) {
+  return rows_reorder_multi(ref, internal, 1, size, &src, &dst, &cols, 1);
+}
+namespace {
+static int rows_reorder_multi(scn_metadata *ref, scn_metadata *internal, int n_maps, const long *sizes, const float *const *src, float *const *dst,
+                              const int *cols, int scatter) {
   M_OR_FAIL(ref);
   M_OR_FAIL(internal);
   SCN_CHECK(n_maps >= 0 && n_maps <= kMaxOutMaps, "rows_to_reference_order_multi: at most 8 maps per call");
@@ -498,10 +518,12 @@ int scn_rows_to_reference_order_multi(scn_metadata *ref, scn_metadata *internal,
     P.totalWarps += gr->n;
   }
   if (P.totalWarps == 0) return 0;
+  P.scatter = scatter;
   SCN_CUDA(scn::launch_pdl(k_rows_to_reference_multi, dim3(std::min(scn::cdiv(P.totalWarps, 8), 148 * 8)), dim3(256), 0, scn::LS(s), P));
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
+} // namespace
 int scn_get_batch_size(scn_metadata *m, const long sz[3], int *batch) {
   M_OR_FAIL(m);
   scn::Grid *g = m->md.find_grid(sz);
@@ -717,63 +739,84 @@ int scn_deconvolution_forward(scn_metadata *m, const long inS[3], const long out
 // d_in = forward tensor-core convolution of d_out with transposed weights (conv_bwd.cu header).  W: [K][Cin][Cout] of the
 // FORWARD layer; d_out rows have Cout channels (nSrcRows of them), d_in rows Cin channels (nDstRows, all written by the plan).
 static int dIn_tensor_core(Metadata &M, const float *d_out, float *d_in, const float *W, int K, int Cin, int Cout, int reverse, const int *nbr,
-                           const int *outRow, const unsigned long long *tileMask, int nOutPlan, const int *tileW, long nSrcRows, long nDstRows) {
+                           const int *outRow, const unsigned long long *tileMask, int nOutPlan, const int *tileW, long nSrcRows, long nDstRows,
+                           const void *dout16 = nullptr) {
   cudaStream_t s = M.cstream;
   float *Wt = nullptr;
   SCN_CUDA(cudaMallocAsync((void **)&Wt, (size_t)K * Cin * Cout * 4, s));
   int r = scn::transpose_weights(W, Wt, K, Cin, Cout, reverse, s);
   if (r == 0)
     r = scn::launch_conv_plan_tc(d_out, d_in, Wt, nbr, outRow, tileMask, nOutPlan, tileW ? 1 : K, /*Cin=*/Cout, /*Cout=*/Cin, nullptr, scn::g_math_mode, s, tileW, K,
-                                 nSrcRows, nullptr, 0, nullptr, nullptr, nDstRows);
+                                 nSrcRows, dout16, 0, nullptr, nullptr, nDstRows);
   cudaFreeAsync(Wt, s);
   return r;
 }
+// bf16 mode: one bf16 copy of d_out serves both gradient kernels of a backward call (each used to make its own)
+static int shared_dout16(cudaStream_t s, const float *d_out, long rows, int Cin, int Cout, const void **out) {
+  *out = nullptr;
+  if (scn::g_math_mode != 2 || !scn::tc_available() || rows == 0 || Cout % 32 != 0 || !tc_ok(Cout, Cin, 1)) return 0;
+  return scn::dout_bf16_copy(d_out, rows * Cout, s, out);
+}
 int scn_submanifold_convolution_backward(scn_metadata *m, const long sz[3], const long f[3], const float *in, float *d_in, const float *d_out,
                                          const float *w, float *dw, float *d_bias, int Cin, int Cout) {
+  const void *in16 = scn::bwd_in16_take(), *dout16 = nullptr;
   M_OR_FAIL(m);
   scn::SubmEntry *e;
   SCN_TRY(m->md.get_submanifold(sz, f, &e));
-  SCN_TRY(m->md.ensure_subm_rules(*e));
   scn::Grid *g = m->md.find_grid(sz);
-  SCN_TRY(m->md.wait_ready(e->rdy));
-  SCN_TRY(m->md.wait_ready(e->rulesRdy));
   // d_in on the tensor cores: the plan of an odd filter is symmetric, d_in[q] = sum_j d_out[nbr[q][j]] @ W[K-1-j]^T
   const bool tcIn = d_in && tc_ok(Cout, Cin, e->plan.K) && f[0] % 2 == 1 && f[1] % 2 == 1 && f[2] % 2 == 1 && g->n > 0;
-  if (tcIn) SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->plan.K, Cin, Cout, /*reverse=*/1, e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut, nullptr, g->n, g->n));
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, g->n, g->n, Cin, Cout, 0, m->md.cstream, tcIn || !d_in, scn::g_math_mode); // d_in == NULL: input gradient not wanted
+  // the per-offset rule lists (reference order) are only materialised when a CUDA-core kernel needs them: both tensor-core
+  // gradient kernels read the execution plan
+  const bool lists = !((tcIn || !d_in) && scn::dw_plan_ok(Cin, Cout, e->plan.K, scn::g_math_mode));
+  if (lists) SCN_TRY(m->md.ensure_subm_rules(*e));
+  SCN_TRY(m->md.wait_ready(e->rdy));
+  if (lists) SCN_TRY(m->md.wait_ready(e->rulesRdy));
+  SCN_TRY(shared_dout16(m->md.cstream, d_out, g->n, Cin, Cout, &dout16));
+  if (tcIn) SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->plan.K, Cin, Cout, /*reverse=*/1, e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut, nullptr, g->n, g->n, dout16));
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, lists ? e->rb.pairs : nullptr, e->rb.d_off, lists ? e->rb.off.data() : nullptr, e->plan.K, g->n, g->n, Cin, Cout, 0, m->md.cstream, tcIn || !d_in, scn::g_math_mode, in16, dout16,
+                                 e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut); // d_in == NULL: input gradient not wanted
 }
 int scn_convolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                              float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
+  const void *in16 = scn::bwd_in16_take(), *dout16 = nullptr;
   M_OR_FAIL(m);
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(inS, outS, f, st, &e));
-  SCN_TRY(m->md.ensure_conv_rules(*e));
-  SCN_TRY(m->md.wait_ready(e->rdy));
-  SCN_TRY(m->md.wait_ready(e->rulesRdy));
   // d_in (fine rows) on the tensor cores: a deconvolution of d_out with W^T over the single-parent plan
   scn::Grid *gf = m->md.find_grid(inS), *gc = m->md.find_grid(outS);
   const bool tcIn = tc_ok(Cout, Cin, 1) && e->geom.M == 1 && e->rb.total == gf->n && gf->n > 0;
+  const bool lists = !(tcIn && scn::dw_plan_ok(Cin, Cout, e->plan.K, scn::g_math_mode));
+  if (lists) SCN_TRY(m->md.ensure_conv_rules(*e));
+  SCN_TRY(m->md.wait_ready(e->rdy));
+  if (lists) SCN_TRY(m->md.wait_ready(e->rulesRdy));
+  SCN_TRY(shared_dout16(m->md.cstream, d_out, gc->n, Cin, Cout, &dout16));
   if (tcIn) {
     SCN_TRY(m->md.get_deconv_plan(*e));
     SCN_TRY(m->md.wait_ready(e->deconvRdy));
     const scn::DeconvPlan &d = e->deconv;
-    SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->rb.nLists, Cin, Cout, /*reverse=*/0, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, d.tileW, gc->n, gf->n));
+    SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->rb.nLists, Cin, Cout, /*reverse=*/0, d.nbr, d.outRow, d.tileMask, d.nTiles * 128, d.tileW, gc->n, gf->n, dout16));
   }
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, gf->n, gc->n, Cin, Cout, 0, m->md.cstream, tcIn, scn::g_math_mode);
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, lists ? e->rb.pairs : nullptr, e->rb.d_off, lists ? e->rb.off.data() : nullptr, e->plan.K, gf->n, gc->n, Cin, Cout, 0, m->md.cstream, tcIn, scn::g_math_mode, in16, dout16,
+                                 e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut);
 }
 int scn_deconvolution_backward(scn_metadata *m, const long inS[3], const long outS[3], const long f[3], const long st[3], const float *in,
                                float *d_in, const float *d_out, const float *w, float *dw, float *d_bias, int Cin, int Cout) {
+  const void *in16 = scn::bwd_in16_take(), *dout16 = nullptr;
   M_OR_FAIL(m);
   scn::ConvEntry *e;
   SCN_TRY(m->md.get_conv(outS, inS, f, st, &e));
-  SCN_TRY(m->md.ensure_conv_rules(*e));
-  SCN_TRY(m->md.wait_ready(e->rdy));
-  SCN_TRY(m->md.wait_ready(e->rulesRdy));
   // d_in (coarse rows) on the tensor cores: the strided convolution fine -> coarse of d_out with W^T
   scn::Grid *gc = m->md.find_grid(inS), *gf = m->md.find_grid(outS);
   const bool tcIn = tc_ok(Cout, Cin, e->plan.K) && gc->n > 0;
-  if (tcIn) SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->plan.K, Cin, Cout, /*reverse=*/0, e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut, nullptr, gf->n, gc->n));
-  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, e->rb.pairs, e->rb.d_off, e->rb.off.data(), e->rb.nLists, gc->n, gf->n, Cin, Cout, 1, m->md.cstream, tcIn, scn::g_math_mode);
+  const bool lists = !(tcIn && scn::dw_plan_ok(Cin, Cout, e->plan.K, scn::g_math_mode));
+  if (lists) SCN_TRY(m->md.ensure_conv_rules(*e));
+  SCN_TRY(m->md.wait_ready(e->rdy));
+  if (lists) SCN_TRY(m->md.wait_ready(e->rulesRdy));
+  SCN_TRY(shared_dout16(m->md.cstream, d_out, gf->n, Cin, Cout, &dout16));
+  if (tcIn) SCN_TRY(dIn_tensor_core(m->md, d_out, d_in, w, e->plan.K, Cin, Cout, /*reverse=*/0, e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut, nullptr, gf->n, gc->n, dout16));
+  return scn::conv_backward_simt(in, d_in, d_out, w, dw, d_bias, lists ? e->rb.pairs : nullptr, e->rb.d_off, lists ? e->rb.off.data() : nullptr, e->plan.K, gc->n, gf->n, Cin, Cout, 1, m->md.cstream, tcIn, scn::g_math_mode, in16, dout16,
+                                 e->plan.nbr, e->plan.outRow, e->plan.tileMask, e->plan.nOut);
 }
 
 // ---- NetworkInNetwork: a 1x1 "convolution" = dense GEMM over the feature rows, no Metadata involved

@@ -54,6 +54,8 @@ enum DebugCounter {
   kCntSplitLaunch = 9,     // conv_plan_tc launches that split the filter offsets over CTAs (atomic epilogue)
   kCntSimtLaunch = 10,     // CUDA-core convolution launches (plan or list)
   kCntTrainReplay = 11,    // backward passes run by the program executor (scn_program_backward)
+  kCntDwPlanLaunch = 13,   // weight-gradient launches driven by the output-stationary plan (conv_dw_plan_tc)
+  kCntBwdOperandReused = 12, // bf16 operand copies the weight-gradient kernel took from its caller instead of converting again
   kCntCounters = 16
 };
 extern std::atomic<long> g_counters[kCntCounters];

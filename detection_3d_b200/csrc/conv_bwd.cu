@@ -13,7 +13,8 @@ namespace scn {
 int launch_conv_list_simt(const float *in, float *out, const float *W, const int2 *pairs, const int *d_off, const int *offHost, int K, int Cin,
                           int Cout, int srcIsY, int singlePass, cudaStream_t s);
 int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2 *pairs, const int *d_off, const int *offHost, int K, long nInRows,
-                      long nOutRows, int Cin, int Cout, int srcIsY, int mathMode, cudaStream_t s);
+                      long nOutRows, int Cin, int Cout, int srcIsY, int mathMode, cudaStream_t s, const void *in16, const void *dout16,
+                      const int *planNbr, const int *planOutRow, const unsigned long long *planMask, int planPos);
 
 // Wt[k'][co][ci] = W[k][ci][co], k' = k or (reverse) K - 1 - k
 __global__ void k_transpose_w(const float *__restrict__ W, float *__restrict__ Wt, int K, int Cin, int Cout, int reverse) {
@@ -114,14 +115,17 @@ int dense_rows_dw(const float *in, const float *d_out, float *dW, float *d_bias,
 
 // skipDIn: the caller computes d_in itself (tensor-core forward kernel on (d_out, W^T)); only dW / d_bias here
 int conv_backward_simt(const float *in, float *d_in, const float *d_out, const float *W, float *dW, float *d_bias, const int2 *pairs,
-                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn, int mathMode) {
+                       const int *d_off, const int *offHost, int K, long nInRows, long nOutRows, int Cin, int Cout, int srcIsY, cudaStream_t s, int skipDIn, int mathMode,
+                       const void *in16, const void *dout16, const int *planNbr, const int *planOutRow, const unsigned long long *planMask, int planPos) {
   if (!skipDIn) SCN_CUDA(cudaMemsetAsync(d_in, 0, (size_t)nInRows * Cin * 4, s));
   SCN_CUDA(cudaMemsetAsync(dW, 0, (size_t)K * Cin * Cout * 4, s));
   if (d_bias) {
     SCN_CUDA(cudaMemsetAsync(d_bias, 0, (size_t)Cout * 4, s));
     if (nOutRows) k_colsum<<<dim3(kSMs * 2, cdiv(Cout, 128)), 128, 0, LS(s)>>>(d_out, nOutRows, Cout, d_bias);
   }
-  if (offHost[K] == 0) return 0;
+  // pairs == nullptr: the caller did not build the rule lists (input gradient done / not wanted, weight gradient from the plan)
+  if (pairs && offHost[K] == 0) return 0;
+  if (!pairs && (!skipDIn || !planNbr || mathMode == 0)) { set_error("convolution backward: rule lists missing"); return -2; }
   if (!skipDIn) {
     float *Wt = nullptr;
     SCN_CUDA(cudaMallocAsync((void **)&Wt, (size_t)K * Cin * Cout * 4, s));
@@ -132,9 +136,10 @@ int conv_backward_simt(const float *in, float *d_in, const float *d_out, const f
     if (r) return r;
   }
   if (mathMode != 0) { // weight gradient on the tensor cores where the channel counts allow (conv_tc.cu, conv_dw_tc)
-    int r = launch_conv_dw_tc(in, d_out, dW, pairs, d_off, offHost, K, nInRows, nOutRows, Cin, Cout, srcIsY, mathMode, s);
+    int r = launch_conv_dw_tc(in, d_out, dW, pairs, d_off, offHost, K, nInRows, nOutRows, Cin, Cout, srcIsY, mathMode, s, in16, dout16, planNbr, planOutRow, planMask, planPos);
     if (r <= 0) return r;
   }
+  if (!pairs) { set_error("convolution backward: rule lists missing for the CUDA-core weight gradient"); return -2; }
   for (int L_ = 0; L_ < K; L_++) {
     int len = offHost[L_ + 1] - offHost[L_];
     if (!len) continue;

@@ -767,11 +767,25 @@ int to_bf16(const float *x, void *y, long n, cudaStream_t s) {
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
+static int stream_scratch(cudaStream_t s, int slot, size_t bytes, void **out);
+// bf16 copy of a backward call's d_out, made once and read by both the input-gradient and the weight-gradient kernel
+int dout_bf16_copy(const float *d_out, long n, cudaStream_t s, const void **out) {
+  void *p = nullptr;
+  SCN_TRY(stream_scratch(s, 3, (size_t)n * 2 + 16, &p));
+  SCN_TRY(to_bf16(d_out, p, n, s));
+  *out = p;
+  return 0;
+}
+// Side channel of the program executor's backward pass: a bf16 copy of the NEXT scn_*_convolution_backward call's `in` rows
+// (the forward pass wrote it: the bf16 shadow of the register) -- taken (and cleared) by that call.
+static thread_local const void *tl_bwd_in16 = nullptr;
+void bwd_in16_arm(const void *in16) { tl_bwd_in16 = in16; }
+const void *bwd_in16_take() { const void *p = tl_bwd_in16; tl_bwd_in16 = nullptr; return p; }
 // Grow-only scratch per (device, stream, slot) for the operand copies a call may need (slot 0: zero-padded rows of a
 // narrow input; slot 1: bf16 copy of an input that arrived without one -- one launch can need both, the second derived
 // from the first, so they must not share a buffer; slot 2: the operand pair of the weight-gradient kernel).  Uses of a
 // slot on one stream are ordered; cudaMallocAsync took milliseconds for these 150-300 MB blocks.
-enum ScratchSlot { kScratchPad = 0, kScratchBf16 = 1, kScratchDw = 2 };
+enum ScratchSlot { kScratchPad = 0, kScratchBf16 = 1, kScratchDw = 2, kScratchDout = 3 }; // 3: bf16 copy of d_out shared by the two gradient kernels of a backward call
 static int stream_scratch(cudaStream_t s, int slot, size_t bytes, void **out) {
   static std::mutex mu;
   static std::map<std::tuple<int, cudaStream_t, int>, std::pair<void *, size_t>> cache;
@@ -1017,6 +1031,79 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
 // operand (instruction descriptor bits 15 / 16, shared-memory descriptor LBO = distance between channel blocks, SBO =
 // 1024 B between groups of 8 rules) the very same bytes are the transposed matrices the product needs -- no transpose
 // pass, both operands are plain row gathers.  Replaces dConvolution_KMxKN_backward_dW_A/B (SCN/CUDA/Convolution.cu:249-410).
+// Producer side of both weight-gradient kernels: one warp requests its RW rows of a stage (4 rows per instruction, 8 lanes x 16 B per
+// 128-byte block of a row).  Straight-line code: the kernels are paced by how fast 8 producer warps can issue these requests
+// (measured with run-time block loops: ~1000 instructions per warp and stage, 3 us per stage, every memory pipe below 10 %).
+// maskA / maskB: bit b = this lane's 16-byte chunk of block b exists in a row (narrow rows end inside a block); blocks that lie
+// entirely beyond the row (the zero padding of M to 128) are zeroed once at kernel start and never written again.
+struct DwLane { uint32_t maskA, maskB, chunkOff; int nBaReal, nBb; };
+__device__ __forceinline__ DwLane dw_lane(int rowBytesA, int rowBytesB, int lane) {
+  DwLane L;
+  L.chunkOff = (uint32_t)(lane & 7) * 16u;
+  L.nBaReal = (rowBytesA + 127) / 128;
+  L.nBb = (rowBytesB + 127) / 128;
+  L.maskA = 0; L.maskB = 0;
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    if (b * 128 + (int)L.chunkOff < rowBytesA) L.maskA |= 1u << b;
+    if (b * 128 + (int)L.chunkOff < rowBytesB) L.maskB |= 1u << b;
+  }
+  return L;
+}
+template <int RW>
+__device__ __forceinline__ void dw_fill_stage(const DwLane &L, const unsigned char *A, const unsigned char *B, int rowBytesA, int rowBytesB, int srcId, int dstId,
+                                              uint32_t sbase, uint32_t blockBytes, int nBa, int pw, int lane) {
+  static_assert(RW >= 4 && RW % 4 == 0, "a producer warp requests 4 rows per instruction");
+  // Rolled loops with everything loop-invariant hoisted: ~10 instructions per copy.  (Fully unrolled with per-copy predicates the
+  // compiler produced ~40 instructions per copy, ~800 per warp and stage, and the eight producer warps' issue rate set the pace.)
+  const int chunk = lane & 7, rsub = lane >> 3;
+  const uint32_t bBase = (uint32_t)nBa * blockBytes;
+#pragma unroll 2
+  for (int i = 0; i < RW / 4; i++) {
+    const int rl = i * 4 + rsub;
+    const int ia = __shfl_sync(0xffffffffu, srcId, rl), ib = __shfl_sync(0xffffffffu, dstId, rl);
+    const int row = pw * RW + rl;
+    const uint32_t dst = sbase + (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4);
+    const unsigned char *pa = A + (size_t)max(ia, 0) * rowBytesA;
+    const unsigned char *pb = B + (size_t)max(ib, 0) * rowBytesB;
+    const uint32_t okA = ia >= 0 ? 16u : 0u, okB = ib >= 0 ? 16u : 0u;
+#pragma unroll 1
+    for (int b = 0; b < L.nBaReal; b++) {
+      const bool v = (L.maskA >> b) & 1u; // this lane's chunk of block b lies inside the row
+      cp_async16(dst + (uint32_t)b * blockBytes, pa + (v ? (uint32_t)b * 128u + L.chunkOff : 0u), v ? okA : 0u);
+    }
+#pragma unroll 1
+    for (int b = 0; b < L.nBb; b++) {
+      const bool v = (L.maskB >> b) & 1u;
+      cp_async16(dst + bBase + (uint32_t)b * blockBytes, pb + (v ? (uint32_t)b * 128u + L.chunkOff : 0u), v ? okB : 0u);
+    }
+  }
+}
+// zero the blocks of every stage that hold the channel padding of A (rows narrower than 256 bytes): written here once, read by the MMAs only
+__device__ __forceinline__ void dw_zero_padding(unsigned char *sStage, int S, uint32_t stageBytes, uint32_t blockBytes, int nBaReal, int nBa) {
+  if (nBaReal >= nBa) return;
+  const uint32_t padBytes = (uint32_t)(nBa - nBaReal) * blockBytes;
+  for (int st = 0; st < S; st++) {
+    uint4 *q = reinterpret_cast<uint4 *>(sStage + (size_t)st * stageBytes + (size_t)nBaReal * blockBytes);
+    for (uint32_t i = threadIdx.x; i < padBytes / 16; i += blockDim.x) q[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async(); // generic-proxy writes -> the tensor core's (async proxy) reads
+}
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lboBytes);
+// MMA issue of one weight-gradient stage: NJ x nMh instructions as straight-line code from precomputed descriptors.  The issuing
+// warp, not the memory system, paced these kernels: with run-time loop bounds and an integer division per instruction it spent
+// ~3000 cycles per stage on 8 instructions (SCN_DW_PROF: wait-full 7 % of the MMA warp's time, producers waiting 15 %).
+template <bool BF16, int NJ>
+__device__ __forceinline__ void dw_issue_stage(uint32_t sbase, uint32_t blockBytes, int nBa, int nMh, uint32_t aBlkStride16, uint32_t tmemD, int Cout, uint32_t idesc, bool first) {
+  constexpr uint32_t kStep16 = (uint32_t)(BF16 ? 16 : 8) * 128u >> 4; // descriptor address units (16 B) per instruction along the rule dimension
+  const uint64_t a0 = smem_desc_mn_sw128(sbase, blockBytes), b0 = smem_desc_mn_sw128(sbase + (uint32_t)nBa * blockBytes, blockBytes);
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    tc_mma<BF16>(tmemD, a0 + (uint64_t)(j * kStep16), b0 + (uint64_t)(j * kStep16), idesc, (!first || j > 0) ? 1u : 0u);
+    if (nMh > 1) tc_mma<BF16>(tmemD + (uint32_t)Cout, a0 + (uint64_t)(aBlkStride16 + j * kStep16), b0 + (uint64_t)(j * kStep16), idesc, (!first || j > 0) ? 1u : 0u);
+  }
+}
+constexpr int kDwProd = 16; // producer warps of the weight-gradient kernels (their request issue rate paces the kernels: 8 -> 16 measured below)
 // One CTA per SM: 4 epilogue warps (TMEM -> red.global.add), 8 producer warps, 1 MMA warp; a work item is a chunk of
 // one offset's rule list, its partial dW[k] is accumulated in TMEM and added to global memory once.
 struct DwParams {
@@ -1030,7 +1117,7 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t l
   return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lboBytes >> 4) & 0x3fffu) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 template <bool BF16>
-__global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
+__global__ void __launch_bounds__(32 * (5 + kDwProd), 1) conv_dw_tc(const DwParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ int s_first[66]; // first work item of every list (prefix of ceil(len / chunk))
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -1042,14 +1129,15 @@ __global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
   uint64_t *full = bars, *empty = bars + P.S, *accFull = bars + 2 * P.S, *accEmpty = accFull + 2;
   uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 2);
   if (tid == 0) {
-    for (int i = 0; i < P.S; i++) { mbar_init(smem_u32(full + i), 8 * 32); mbar_init(smem_u32(empty + i), 1); }
+    for (int i = 0; i < P.S; i++) { mbar_init(smem_u32(full + i), kDwProd * 32); mbar_init(smem_u32(empty + i), 1); }
     for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int a = 0;
     for (int k = 0; k < P.K; k++) { s_first[k] = a; a += (P.d_off[k + 1] - P.d_off[k] + P.chunk - 1) / P.chunk; }
     s_first[P.K] = a;
   }
-  constexpr int kMmaWarp = 12;
+  dw_zero_padding(sStage, P.S, stageBytes, blockBytes, (P.rowBytesA + 127) / 128, nBa);
+  constexpr int kMmaWarp = 4 + kDwProd;
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -1094,34 +1182,30 @@ __global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(accEmpty + a));
     }
-  } else if (warp < 12) {
+  } else if (warp < 4 + kDwProd) {
     // ---------------- producers: rows of `in` by the rules' source ids, rows of `d_out` by their destination ids
-    const int pw = warp - 4, RW = R / 8; // rules per warp and stage (16 or 8)
-    const int chunk = lane & 7, rsub = lane >> 3;
+    const int pw = warp - 4, RW = R / kDwProd; // rules per warp and stage
+    const DwLane DL = dw_lane(P.rowBytesA, P.rowBytesB, lane);
     uint32_t slot = 0, round = 0;
     for (int w = blockIdx.x; w < nItems; w += gridDim.x) {
       int k, r0, cnt;
       item(w, k, r0, cnt);
-      for (int base = 0; base < cnt; base += R) {
+      // the rule ids of a stage are fetched two stages ahead: the dependent chain (ids -> row addresses -> copies) otherwise
+      // costs one memory round trip per stage and sets the pace of the whole kernel on narrow layers
+      auto load_pair = [&](int base) {
         const int rr = base + pw * RW + (lane & (RW - 1));
-        int2 pr = make_int2(-1, -1);
-        if (rr < cnt) pr = __ldg(P.pairs + r0 + rr);
+        return (base < cnt && rr < cnt) ? __ldg(P.pairs + r0 + rr) : make_int2(-1, -1);
+      };
+      int2 pr1 = load_pair(0), pr2 = load_pair(R);
+      for (int base = 0; base < cnt; base += R) {
+        const int2 pr = pr1;
+        pr1 = pr2;
+        pr2 = load_pair(base + 2 * R);
         const int srcId = P.srcIsY ? pr.y : pr.x, dstId = P.srcIsY ? pr.x : pr.y;
         mbar_wait(smem_u32(empty + slot), (round & 1u) ^ 1u);
         const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
-        for (int i = 0; i < RW / 4; i++) {
-          const int row = pw * RW + i * 4 + rsub;
-          const int ia = __shfl_sync(0xffffffffu, srcId, i * 4 + rsub), ib = __shfl_sync(0xffffffffu, dstId, i * 4 + rsub);
-          const uint32_t off = (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4);
-          for (int b = 0; b < nBa; b++) {
-            const bool have = ia >= 0 && b * 128 + chunk * 16 < P.rowBytesA;
-            cp_async16(sbase + b * blockBytes + off, have ? P.a + (size_t)ia * P.rowBytesA + b * 128 + chunk * 16 : P.a, have ? 16u : 0u);
-          }
-          for (int b = 0; b < nBb; b++) {
-            const bool have = ib >= 0 && b * 128 + chunk * 16 < P.rowBytesB;
-            cp_async16(sbase + (nBa + b) * blockBytes + off, have ? P.b + (size_t)ib * P.rowBytesB + b * 128 + chunk * 16 : P.b, have ? 16u : 0u);
-          }
-        }
+        if (R == 128) dw_fill_stage<128 / kDwProd>(DL, P.a, P.b, P.rowBytesA, P.rowBytesB, srcId, dstId, sbase, blockBytes, nBa, pw, lane);
+        else dw_fill_stage<64 / kDwProd>(DL, P.a, P.b, P.rowBytesA, P.rowBytesB, srcId, dstId, sbase, blockBytes, nBa, pw, lane);
         cp_async_mbar_arrive_noinc(smem_u32(full + slot));
         if (++slot == (uint32_t)P.S) { slot = 0; round++; }
       }
@@ -1131,6 +1215,7 @@ __global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
     const uint32_t fmt = BF16 ? 1u : 2u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr int kRulesPerMma = BF16 ? 16 : 8;
+    const uint32_t aBlkStride16 = ((uint32_t)(nBa / nMh) * blockBytes) >> 4; // second half of M (channels 128..255): descriptor units
     uint32_t slot = 0, round = 0;
     int it = 0;
     for (int w = blockIdx.x; w < nItems; w += gridDim.x, it++) {
@@ -1144,13 +1229,8 @@ __global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
         tc_fence_after();
         const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
         if (elect_one()) {
-          for (int j = 0; j < R / kRulesPerMma; j++) {
-            const uint64_t bDesc = smem_desc_mn_sw128(sbase + nBa * blockBytes + (uint32_t)j * kRulesPerMma * 128u, blockBytes);
-            for (int mh = 0; mh < nMh; mh++) {
-              const uint64_t aDesc = smem_desc_mn_sw128(sbase + (uint32_t)mh * (nBa / nMh) * blockBytes + (uint32_t)j * kRulesPerMma * 128u, blockBytes);
-              tc_mma<BF16>(tmemBase + (uint32_t)(a * accCols + mh * P.Cout), aDesc, bDesc, idesc, (base > 0 || j > 0) ? 1u : 0u);
-            }
-          }
+          if (R == 128) dw_issue_stage<BF16, 128 / kRulesPerMma>(sbase, blockBytes, nBa, nMh, aBlkStride16, tmemBase + (uint32_t)(a * accCols), P.Cout, idesc, base == 0);
+          else dw_issue_stage<BF16, 64 / kRulesPerMma>(sbase, blockBytes, nBa, nMh, aBlkStride16, tmemBase + (uint32_t)(a * accCols), P.Cout, idesc, base == 0);
           tc_commit(smem_u32(empty + slot));
         }
         __syncwarp();
@@ -1167,15 +1247,258 @@ __global__ void __launch_bounds__(416, 1) conv_dw_tc(const DwParams P) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
   }
 }
+// The live tiles of a work item (tiles t0, t0 + step, ... whose mask has bit k), found 32 candidates at a time: every lane reads one
+// candidate's mask word, a ballot turns the words into a bit set, and the words of the NEXT 32 candidates are already on their way
+// while the current ones are consumed (probing tile by tile cost one dependent memory round trip per candidate).  Whole-warp calls.
+struct LiveTiles {
+  const unsigned long long *mask;
+  int k, t0, t1, step, lane, base;
+  unsigned bits;
+  unsigned long long ahead; // this lane's mask word of candidate base + 32 + lane
+  __device__ __forceinline__ unsigned long long word(int b) const {
+    const long t = t0 + (long)(b + lane) * step;
+    return t < t1 ? __ldg(mask + t) : 0ull;
+  }
+  __device__ __forceinline__ void init(const unsigned long long *m, int k_, int t0_, int t1_, int step_, int lane_) {
+    mask = m; k = k_; t0 = t0_; t1 = t1_; step = step_; lane = lane_; base = 0;
+    const unsigned long long w0 = word(0);
+    ahead = word(32);
+    bits = __ballot_sync(0xffffffffu, (w0 >> k) & 1ull);
+  }
+  __device__ __forceinline__ int next() { // the next live tile, or t1 when there is none left
+    for (;;) {
+      if (bits) { const int j = __ffs(bits) - 1; bits &= bits - 1; return t0 + (base + j) * step; }
+      if (t0 + (long)(base + 32) * step >= t1) return t1;
+      base += 32;
+      bits = __ballot_sync(0xffffffffu, (ahead >> k) & 1ull);
+      ahead = word(base + 32);
+    }
+  }
+};
+// The same product driven by the OUTPUT-STATIONARY PLAN instead of the per-offset rule lists.  The rule lists are in the
+// reference's hash-iteration order, i.e. random in memory: every rule cost two random 64..512-byte DRAM accesses (measured: 1.1 ms
+// for each of the three level-0 layers of B470 whatever their width).  The plan lists the same rules tile by tile in spatial block
+// order -- (nbr[p][k], outRow[p]) for every plan position p with a neighbour at offset k -- so consecutive rules touch
+// neighbouring rows and the gathers hit L2 like the forward pass's.  A work item is (offset k, a range of tiles); a stage is R
+// positions of one tile whose mask has bit k set; positions without a neighbour are zero-filled rows (no traffic, no contribution).
+struct DwPlanParams {
+  const unsigned char *a, *b; // operand-typed rows: `in` (rowBytesA per row) and `d_out` (rowBytesB)
+  const int *nbr, *outRow;
+  const unsigned long long *tileMask;
+  float *dW;
+  int K, Cin, Cout, swap, rowBytesA, rowBytesB, R, S, nAcc;
+  int nPos, nTiles, chunkTiles, itemsPerK; // plan positions, tiles of 128, tiles per work item, work items per offset
+  unsigned *sched; // [0] next work item, [1] CTAs that have drawn their last item (self-resetting, see sched_counters)
+  long long *prof; // developer (SCN_DW_PROF): per CTA [0] total, [1] producer wait-empty, [2] producer stages, [3] mma total, [4] mma wait-full, [5] mma wait-acc, [6] epilogue busy
+};
+template <bool BF16>
+__global__ void __launch_bounds__(32 * (6 + kDwProd), 1) conv_dw_plan_tc(const DwPlanParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int R = P.R, nBa = max(P.rowBytesA, 256) / 128, nBb = (P.rowBytesB + 127) / 128, nHalf = 128 / R;
+  const uint32_t blockBytes = (uint32_t)R * 128u, stageBytes = (uint32_t)(nBa + nBb) * blockBytes;
+  unsigned char *sStage = smem;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sStage + (size_t)P.S * stageBytes);
+  uint64_t *full = bars, *empty = bars + P.S, *accFull = bars + 2 * P.S, *accEmpty = accFull + 2;
+  uint32_t *tmemSlot = reinterpret_cast<uint32_t *>(accEmpty + 2);
+  // work items are drawn from a global counter by warp 13 and published to the other 13 warps through a ring in shared memory
+  // (the cost of an item -- the live tiles of its offset -- is only known on the device: a static stride left the average CTA idle
+  // for 45 % of the launch)
+  Sched SC{bars + 24, bars + 24 + kSchedSlots, reinterpret_cast<volatile int *>(bars + 24 + 2 * kSchedSlots)};
+  if (tid == 0) {
+    for (int i = 0; i < P.S; i++) { mbar_init(smem_u32(full + i), kDwProd * 32); mbar_init(smem_u32(empty + i), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
+    for (int i = 0; i < kSchedSlots; i++) { mbar_init(smem_u32(SC.full + i), 1); mbar_init(smem_u32(SC.empty + i), 5 + kDwProd); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  dw_zero_padding(sStage, P.S, stageBytes, blockBytes, (P.rowBytesA + 127) / 128, nBa);
+  constexpr int kMmaWarp = 4 + kDwProd;
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmemSlot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemBase = *tmemSlot;
+  const int nItems = P.K * P.itemsPerK;
+  const int nMh = (P.Cin + 127) / 128, accCols = nMh * P.Cout;
+  // item -> (offset k, tile range); every role walks the live tiles of the range in the same order
+  // Work item w = (offset k = w % K, tile class c = w / K): the tiles c, c + itemsPerK, c + 2 itemsPerK, ...  Every item of an offset
+  // samples the whole grid (equal cost within an offset: a contiguous range of a sparse offset may hold no live tile at all) and
+  // consecutive items -- the ones a CTA draws with its static stride -- belong to different offsets.
+  const int tStep = P.itemsPerK;
+  auto item = [&](int w, int &k, int &t0, int &t1) {
+    k = w % P.K;
+    t0 = w / P.K;
+    t1 = P.nTiles;
+  };
+
+  if (warp < 4) {
+    // ---------------- epilogue: partial dW[k] of the item -> global memory (fp32 reductions)
+    int it = 0;
+    for (;; it++) {
+      const int w = sched_take(SC, it, lane == 0);
+      if (w < 0) break;
+      int k, t0, t1;
+      item(w, k, t0, t1);
+      LiveTiles LT;
+      LT.init(P.tileMask, k, t0, t1, tStep, lane);
+      const bool any = LT.next() < t1;
+      const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
+      mbar_wait(smem_u32(accFull + a), use & 1);
+      tc_fence_after();
+      for (int mh = 0; any && mh < nMh; mh++) {
+        const int ci = mh * 128 + warp * 32 + lane;
+        float *dst = P.dW + ((size_t)k * P.Cin + ci) * P.Cout;
+        if (mh * 128 + warp * 32 >= P.Cin) continue; // rows of the channel padding (warp-uniform)
+        for (int c0 = 0; c0 < P.Cout; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld(tmemBase + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * accCols + mh * P.Cout + c0), v);
+          if (ci < P.Cin) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(accEmpty + a));
+    }
+  } else if (warp < 4 + kDwProd) {
+    // ---------------- producers: rows of `in` by the plan's neighbour ids, rows of `d_out` by its output rows (swapped for a deconvolution)
+    const int pw = warp - 4, RW = R / kDwProd; // positions per warp and stage
+    const DwLane DL = dw_lane(P.rowBytesA, P.rowBytesB, lane);
+    uint32_t slot = 0, round = 0;
+    long long pwait = 0, pstages = 0;
+    const long long pt0 = P.prof ? clock64() : 0;
+    for (int itp = 0;; itp++) {
+      const int w = sched_take(SC, itp, lane == 0);
+      if (w < 0) break;
+      int k, t0, t1;
+      item(w, k, t0, t1);
+      // (both loads are independent of each other's result: the ids of the next two stages are in flight while this stage's rows are requested)
+      auto load_ids = [&](int t, int h, int &idn, int &ido) { // lane l holds position h R + pw RW + l % RW of tile t
+        idn = -1; ido = -1;
+        if (t >= t1) return;
+        const int r = h * R + pw * RW + (lane & (RW - 1));
+        const long p = (long)t * 128 + r;
+        idn = __ldg(P.nbr + ((size_t)t * P.K + k) * 128 + r);
+        ido = p < P.nPos ? (P.outRow ? __ldg(P.outRow + p) : (int)p) : -1;
+      };
+      LiveTiles LT;
+      LT.init(P.tileMask, k, t0, t1, tStep, lane);
+      // three stages in flight: (t, h) is being filled, (tB, hB) and (tA, hA) are the next two, their ids already requested
+      auto advance = [&](int &t, int &h) { if (++h == nHalf) { h = 0; t = LT.next(); } };
+      int t = LT.next(), h = 0;
+      int tB = t, hB = h, tA, hA, idn1, ido1, idn2, ido2;
+      load_ids(t, h, idn1, ido1);
+      if (tB < t1) advance(tB, hB);
+      tA = tB; hA = hB;
+      load_ids(tB, hB, idn2, ido2);
+      while (t < t1) {
+        int idn = idn1, ido = ido1;
+        idn1 = idn2; ido1 = ido2;
+        if (tA < t1) advance(tA, hA);
+        load_ids(tA, hA, idn2, ido2);
+        if (idn < 0 || ido < 0) { idn = -1; ido = -1; } // no neighbour at this offset / beyond the last site: zero rows
+        const int srcId = P.swap ? ido : idn, dstId = P.swap ? idn : ido;
+        { const long long c0 = P.prof ? clock64() : 0; mbar_wait(smem_u32(empty + slot), (round & 1u) ^ 1u); if (P.prof) { pwait += clock64() - c0; pstages++; } }
+        const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
+        if (R == 128) dw_fill_stage<128 / kDwProd>(DL, P.a, P.b, P.rowBytesA, P.rowBytesB, srcId, dstId, sbase, blockBytes, nBa, pw, lane);
+        else dw_fill_stage<64 / kDwProd>(DL, P.a, P.b, P.rowBytesA, P.rowBytesB, srcId, dstId, sbase, blockBytes, nBa, pw, lane);
+        cp_async_mbar_arrive_noinc(smem_u32(full + slot));
+        if (++slot == (uint32_t)P.S) { slot = 0; round++; }
+        t = tB; h = hB;
+        tB = tA; hB = hA;
+      }
+    }
+    if (P.prof && pw == 0 && lane == 0) { long long *q = P.prof + blockIdx.x * 8; q[0] = clock64() - pt0; q[1] = pwait; q[2] = pstages; }
+  } else if (warp == kMmaWarp) {
+    // ---------------- MMA issuer: both operands MN-major (bits 15, 16), M = 128, N = Cout, 32 bytes of K (= 16 bf16 / 8 tf32 positions) per instruction
+    const uint32_t fmt = BF16 ? 1u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P.Cout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr int kRulesPerMma = BF16 ? 16 : 8;
+    const uint32_t aBlkStride16 = ((uint32_t)(nBa / nMh) * blockBytes) >> 4; // second half of M (channels 128..255): descriptor units
+    uint32_t slot = 0, round = 0;
+    int it = 0;
+    long long mfull = 0, macc = 0;
+    const long long mt0 = P.prof ? clock64() : 0;
+    for (;; it++) {
+      const int w = sched_take(SC, it, lane == 0);
+      if (w < 0) break;
+      int k, t0, t1;
+      item(w, k, t0, t1);
+      const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
+      { const long long c0 = P.prof ? clock64() : 0; mbar_wait(smem_u32(accEmpty + a), (use & 1) ^ 1); if (P.prof) macc += clock64() - c0; }
+      tc_fence_after();
+      bool first = true;
+      LiveTiles LT;
+      LT.init(P.tileMask, k, t0, t1, tStep, lane);
+      for (int t = LT.next(); t < t1; t = LT.next()) {
+        for (int h = 0; h < nHalf; h++) {
+          { const long long c0 = P.prof ? clock64() : 0; mbar_wait(smem_u32(full + slot), round & 1u); if (P.prof) mfull += clock64() - c0; }
+          tc_fence_after();
+          const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
+          if (elect_one()) {
+            if (R == 128) dw_issue_stage<BF16, 128 / kRulesPerMma>(sbase, blockBytes, nBa, nMh, aBlkStride16, tmemBase + (uint32_t)(a * accCols), P.Cout, idesc, first);
+            else dw_issue_stage<BF16, 64 / kRulesPerMma>(sbase, blockBytes, nBa, nMh, aBlkStride16, tmemBase + (uint32_t)(a * accCols), P.Cout, idesc, first);
+            tc_commit(smem_u32(empty + slot));
+          }
+          __syncwarp();
+          first = false;
+          if (++slot == (uint32_t)P.S) { slot = 0; round++; }
+        }
+      }
+      if (elect_one()) tc_commit(smem_u32(accFull + a));
+      __syncwarp();
+    }
+    if (P.prof && lane == 0) { long long *q = P.prof + blockIdx.x * 8; q[3] = clock64() - mt0; q[4] = mfull; q[5] = macc; }
+  } else if (lane == 0) {
+    // ---------------- scheduler: draws items (one beyond the end per CTA: the last CTA to do so re-zeroes the counters)
+    for (int n = 0;; n++) {
+      const unsigned v = atomicAdd(P.sched, 1u);
+      int wi = (int)v;
+      if (v >= (unsigned)nItems) {
+        wi = -1;
+        if (atomicAdd(P.sched + 1, 1u) == gridDim.x - 1) { P.sched[0] = 0u; P.sched[1] = 0u; }
+      }
+      sched_publish(SC, n, wi);
+      if (wi < 0) break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
+  }
+}
+// whether launch_conv_dw_tc would run the plan-driven kernel for this shape (the caller then does not need the rule lists)
+bool dw_plan_ok(int Cin, int Cout, int K, int mathMode) {
+  static int planOn = -1;
+  if (planOn < 0) planOn = getenv("SCN_DW_PLAN") ? atoi(getenv("SCN_DW_PLAN")) : 0;
+  if (!planOn || mathMode != 2 || !tc_available()) return false;
+  return !((Cin % 32 != 0 && Cin > 32) || Cin > 256 || (Cin > 128 && Cin % 128 != 0) || Cout % 32 != 0 || Cout > 256 || ((Cin + 127) / 128) * Cout > 512 || K > 64);
+}
 // dW must be zero on entry.  Returns 1 when the configuration is not supported (the caller then uses the CUDA-core kernel).
+// in16 / dout16: optional bf16 copies of `in` / `d_out` ([rows][Cin] / [rows][Cout], same layout) the caller already has.
 int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2 *pairs, const int *d_off, const int *offHost, int K, long nInRows,
-                      long nOutRows, int Cin, int Cout, int srcIsY, int mathMode, cudaStream_t s) {
+                      long nOutRows, int Cin, int Cout, int srcIsY, int mathMode, cudaStream_t s, const void *in16, const void *dout16,
+                      const int *planNbr, const int *planOutRow, const unsigned long long *planMask, int planPos) {
   // bf16 mode only: with TF32 operands the MN-major product came out as zeros on B200 (unresolved; tf32 mode keeps the CUDA-core kernel)
   if (mathMode != 2 || !tc_available()) return 1;
   const bool bf16 = true;
   if ((Cin % 32 != 0 && Cin > 32) || Cin > 256 || (Cin > 128 && Cin % 128 != 0) || Cout % 32 != 0 || Cout > 256 || ((Cin + 127) / 128) * Cout > 512 || K > 64) return 1;
   const int CinP = Cin % 32 == 0 ? Cin : (Cin <= 16 ? 16 : 32); // odd narrow inputs (the 9-channel network input): bf16 rows zero-padded to 16 / 32 channels
-  const long total = offHost[K];
+  static int planOn = -1;
+  // Measured on B470 / 6c_fpn4321 (internal numbering, 16 producer warps): level-0 32 -> 32 layers 0.45 ms with the rule lists
+  // (100 % row fill, equal work items) against 0.69 ms with the plan (row fill 89 %, items of unequal cost), all 39 launches of a
+  // step 2.6 against 4.2 ms -- the list kernel is the default, SCN_DW_PLAN=1 selects the plan-driven one.
+  if (planOn < 0) planOn = getenv("SCN_DW_PLAN") ? atoi(getenv("SCN_DW_PLAN")) : 0;
+  const bool usePlan = planOn && planNbr && planMask && planPos > 0;
+  SCN_CHECK(usePlan || offHost, "weight gradient: neither a plan nor rule lists");
+  const long total = usePlan ? 1 : offHost[K];
   if (total == 0) return 0;
   DwParams P;
   P.pairs = pairs; P.d_off = d_off; P.dW = dW; P.K = K; P.Cin = Cin; P.Cout = Cout; P.srcIsY = srcIsY;
@@ -1183,12 +1506,16 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
   P.rowBytesB = Cout * (bf16 ? 2 : 4);
   if (bf16) { // operand copies of both row matrices, side by side in the stream's scratch buffer
     unsigned char *scr = nullptr;
-    const size_t na = ((size_t)nInRows * CinP * 2 + 255) & ~(size_t)255;
-    SCN_TRY(stream_scratch(s, kScratchDw, na + (size_t)nOutRows * Cout * 2 + 16, (void **)&scr));
-    if (CinP == Cin) SCN_TRY(to_bf16(in, scr, nInRows * Cin, s));
+    const bool haveA = in16 && CinP == Cin, haveB = dout16 != nullptr;
+    const size_t na = haveA ? 0 : (((size_t)nInRows * CinP * 2 + 255) & ~(size_t)255);
+    if (!haveA || !haveB) SCN_TRY(stream_scratch(s, kScratchDw, na + (haveB ? 0 : (size_t)nOutRows * Cout * 2) + 16, (void **)&scr));
+    if (haveA) ++g_counters[kCntBwdOperandReused];
+    else if (CinP == Cin) SCN_TRY(to_bf16(in, scr, nInRows * Cin, s));
     else if (nInRows) k_pad_rows_bf16<<<stream_grid(nInRows * CinP, 256), 256, 0, LS(s)>>>(in, reinterpret_cast<__nv_bfloat16 *>(scr), nInRows, Cin, CinP);
-    SCN_TRY(to_bf16(d_out, scr + na, nOutRows * Cout, s));
-    P.a = scr; P.b = scr + na;
+    if (haveB) ++g_counters[kCntBwdOperandReused];
+    else SCN_TRY(to_bf16(d_out, scr + na, nOutRows * Cout, s));
+    P.a = haveA ? static_cast<const unsigned char *>(in16) : scr;
+    P.b = haveB ? static_cast<const unsigned char *>(dout16) : scr + na;
   } else {
     P.a = reinterpret_cast<const unsigned char *>(in); P.b = reinterpret_cast<const unsigned char *>(d_out);
   }
@@ -1200,6 +1527,44 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
   if (P.S < 2) return 1;
   const int accCols = ((Cin + 127) / 128) * Cout;
   P.nAcc = 2 * accCols <= 512 ? 2 : 1;
+  if (usePlan) { // plan order (spatially coherent gathers), see conv_dw_plan_tc
+    DwPlanParams Q;
+    Q.a = P.a; Q.b = P.b; Q.nbr = planNbr; Q.outRow = planOutRow; Q.tileMask = planMask; Q.dW = dW;
+    Q.K = K; Q.Cin = Cin; Q.Cout = Cout; Q.swap = srcIsY; Q.rowBytesA = P.rowBytesA; Q.rowBytesB = P.rowBytesB; Q.R = P.R; Q.S = P.S; Q.nAcc = P.nAcc;
+    Q.nPos = planPos;
+    Q.nTiles = cdiv(planPos, 128);
+    static int envIpc = -1;
+    if (envIpc < 0) envIpc = getenv("SCN_DW_ITEMS") ? atoi(getenv("SCN_DW_ITEMS")) : 12; // items per CTA: fine enough for the dynamic distribution to balance offsets of very different cost
+    Q.itemsPerK = std::max(1, std::min(Q.nTiles, cdiv(kSMs * envIpc, K)));
+    Q.chunkTiles = cdiv(Q.nTiles, Q.itemsPerK);
+    Q.itemsPerK = cdiv(Q.nTiles, Q.chunkTiles);
+    const size_t smemQ = (size_t)Q.S * stageBytes + 64 * 8 + 64;
+    static bool attrQ = false;
+    if (!attrQ) {
+      SCN_CUDA(cudaFuncSetAttribute(conv_dw_plan_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+      attrQ = true;
+    }
+    const int gridQ = std::min(K * Q.itemsPerK, kSMs);
+    static int envProf = -1;
+    if (envProf < 0) envProf = getenv("SCN_DW_PROF") ? atoi(getenv("SCN_DW_PROF")) : 0;
+    Q.prof = nullptr;
+    if (envProf) { SCN_CUDA(cudaMalloc((void **)&Q.prof, kSMs * 8 * 8)); SCN_CUDA(cudaMemsetAsync(Q.prof, 0, kSMs * 8 * 8, s)); }
+    SCN_TRY(sched_counters(s, &Q.sched));
+    conv_dw_plan_tc<true><<<gridQ, 32 * (6 + kDwProd), smemQ, LS(s)>>>(Q);
+    SCN_CUDA(cudaGetLastError());
+    if (envProf) { // developer aid: per-role cycle counters, mean and max over the CTAs
+      static long long h[kSMs * 8];
+      SCN_CUDA(cudaMemcpyAsync(h, Q.prof, sizeof h, cudaMemcpyDeviceToHost, s));
+      SCN_CUDA(cudaStreamSynchronize(s));
+      double mean[8] = {0}, mx[8] = {0};
+      for (int b = 0; b < gridQ; b++) for (int i = 0; i < 8; i++) { mean[i] += (double)h[b * 8 + i] / gridQ; mx[i] = std::max(mx[i], (double)h[b * 8 + i]); }
+      fprintf(stderr, "[dwprof] K=%d Cin=%d Cout=%d tiles=%d items/K=%d R=%d S=%d | producer total %.0f (max %.0f) wait-empty %.0f stages %.0f (max %.0f) | mma total %.0f wait-full %.0f wait-acc %.0f\n",
+              K, Cin, Cout, Q.nTiles, Q.itemsPerK, Q.R, Q.S, mean[0], mx[0], mean[1], mean[2], mx[2], mean[3], mean[4], mean[5]);
+      cudaFree(Q.prof);
+    }
+    ++g_counters[kCntDwPlanLaunch];
+    return 0;
+  }
   long chunk = (total + kSMs * 3 - 1) / (kSMs * 3);
   chunk = std::max<long>(4 * P.R, (chunk + P.R - 1) / P.R * P.R);
   P.chunk = (int)chunk;
@@ -1213,8 +1578,8 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
     attr = true;
   }
   const int grid = (int)std::min<long>(nItems, kSMs);
-  if (bf16) conv_dw_tc<true><<<grid, 416, smemBytes, LS(s)>>>(P);
-  else conv_dw_tc<false><<<grid, 416, smemBytes, LS(s)>>>(P);
+  if (bf16) conv_dw_tc<true><<<grid, 32 * (5 + kDwProd), smemBytes, LS(s)>>>(P);
+  else conv_dw_tc<false><<<grid, 32 * (5 + kDwProd), smemBytes, LS(s)>>>(P);
   SCN_CUDA(cudaGetLastError());
   return 0;
 }

@@ -18,6 +18,7 @@ bool epilogue_stats_take();
 void lateral_arm(const float *in, const void *in16, const float *w, long long tag, int Cin, long rows);
 bool lateral_take();
 void prepadded_arm(const void *rows16, int Cp);
+void bwd_in16_arm(const void *in16);
 void prepadded_disarm();
 int build_subm_on_caller(scn_metadata *m, const long *sz, const long *f);
 int bn_forward_from_sums(const float *x, float *y, long n, int C, const double *sums, float *saveMean, float *saveInvStd, float *runningMean,
@@ -71,7 +72,8 @@ struct scn_program {
   // scn_program_backward.
   bool train = false;
   std::vector<float *> bnSave;  // per op: [2][C] floats (train mode), from the slot pool
-  scn_metadata *lastMd = nullptr; // Metadata of the last training run (the backward pass needs its rulebooks)
+  scn_metadata *lastMd = nullptr; // Metadata the layers of the last training run ran on (the backward pass needs its rulebooks): the caller's, or `ms`
+  scn_metadata *lastRef = nullptr; // the caller's Metadata of that run (reference numbering: the order gradients arrive in)
 };
 
 static void *slot_get(scn_program *p, size_t bytes) {
@@ -365,8 +367,11 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
   for (const Op &o : p->ops) if (o.kind == K_INPUT) { inOp = &o; break; }
   const bool train = p->train;
   p->lastMd = train ? m : nullptr;
+  p->lastRef = train ? m : nullptr;
   if (train) p->bnSave.assign(p->ops.size(), nullptr);
-  if (!train && internalOn && inOp && inOp->a[4] != 0 && !scn_input_layer_built(m, nullptr, nullptr)) {
+  static int trainInternal = -1; // training runs on the internally numbered Metadata too (rows in spatial order: every gather of the
+  if (trainInternal < 0) trainInternal = getenv("SCN_TRAIN_INTERNAL") ? atoi(getenv("SCN_TRAIN_INTERNAL")) : 1; // forward AND backward pass stays local)
+  if ((!train || trainInternal) && internalOn && inOp && inOp->a[4] != 0 && !scn_input_layer_built(m, nullptr, nullptr)) {
     if (coords_on_device == 1) {
       if (!p->evCoords) SCN_CUDA(cudaEventCreateWithFlags(&p->evCoords, cudaEventDisableTiming));
       SCN_CUDA(cudaEventRecord(p->evCoords, s));
@@ -404,6 +409,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
     if (batch == 1) {
       M = p->ms;
       p->internal = true;
+      if (train) p->lastMd = p->ms;
     } else { // several batch items: the caller's Metadata does everything (reference numbering throughout)
       scn_metadata_destroy(p->ms);
       p->ms = nullptr;
@@ -637,7 +643,16 @@ int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const f
   };
   for (int i = 0; i < n_out; i++) {
     SCN_CHECK(out_regs[i] >= 0 && out_regs[i] < p->nRegs && p->isOutput[out_regs[i]], "not an output register");
-    if (d_out[i]) SCN_TRY(contribute(out_regs[i], const_cast<float *>(d_out[i]), false));
+    if (!d_out[i]) continue;
+    const long r = out_regs[i];
+    if (p->internal && elems(r) > 0) { // the run was numbered internally: bring the gradient rows from the caller's (reference) order into it
+      SCN_CHECK(p->ms == m && p->lastRef, "program backward: the internally numbered Metadata of the run is gone");
+      float *gi = static_cast<float *>(slot_get(p, (size_t)elems(r) * 4));
+      if (!gi) return -1;
+      SCN_TRY(scn_rows_from_reference_order(p->lastRef, p->ms, p->outSize[r].data(), d_out[i], gi, p->regs[r].cols));
+      SCN_TRY(contribute(r, gi, true));
+    } else
+      SCN_TRY(contribute(r, const_cast<float *>(d_out[i]), false));
   }
   for (int i = (int)p->ops.size() - 1; i >= 0 && rc == 0; i--) {
     const Op &op = p->ops[i];
@@ -700,6 +715,9 @@ int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const f
           if (!dwTmp) { rc = -1; break; }
           dw = dwTmp;
         }
+        // bf16 mode: the forward pass left a bf16 copy of the input rows (same layout: whole rows, no padding) -- the
+        // weight-gradient kernel gathers from it instead of converting the fp32 rows again
+        if (I.p16 && !I.pad16 && Cin % 32 == 0 && scn_get_math_mode() == 2) scn::bwd_in16_arm(I.p16);
         if (op.kind == K_SUBM) rc = scn_submanifold_convolution_backward(m, a + 2, a + 5, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
         else if (op.kind == K_CONV) rc = scn_convolution_backward(m, a + 2, a + 5, a + 8, a + 11, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
         else rc = scn_deconvolution_backward(m, a + 2, a + 5, a + 8, a + 11, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);

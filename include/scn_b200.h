@@ -205,6 +205,9 @@ int scn_rows_to_reference_order(scn_metadata *ref, scn_metadata *internal, const
 /* the same for up to 8 feature matrices in one launch (sizes: n_maps x 3) */
 int scn_rows_to_reference_order_multi(scn_metadata *ref, scn_metadata *internal, int n_maps, const long *sizes, const float *const *src, float *const *dst,
                                       const int *cols);
+/* The inverse for gradients (training replay): dst[internal row of site x] = src[reference row of site x] for every site of
+ * the grid `size`; dst [rows][cols] is written completely (the two numberings are bijections of the same site set). */
+int scn_rows_from_reference_order(scn_metadata *ref, scn_metadata *internal, const long size[3], const float *src, float *dst, int cols);
 /* Build half of a run, callable ahead of scn_program_run for the NEXT input while the GPU still computes the current
  * one (streaming many buildings through one network): input layer + the worker threads that build every rulebook the
  * program requests.  coords_on_device: 0 host, 1 device (ordered after the caller's stream), 2 device and complete.
@@ -301,7 +304,8 @@ long scn_kernel_launch_count(void);
  * that carried a lateral 1x1x1 stage, 4 = launches whose epilogue accumulated BatchNorm statistics, 5 = program registers
  * written as bf16 only, 6 = laterals run as a separate convolution + add (fallback), 7 = tcgen05 convolution launches,
  * 8 = BatchNorm ops applied from epilogue statistics, 9 = launches that split the filter offsets over CTAs (atomic
- * epilogue), 10 = CUDA-core convolution launches, 11 = backward passes run by scn_program_backward. */
+ * epilogue), 10 = CUDA-core convolution launches, 11 = backward passes run by scn_program_backward, 12 = bf16 operand copies the
+ * weight-gradient kernel took from its caller (forward shadow / shared d_out copy) instead of converting again. */
 long scn_debug_counter(int which);
 
 /* Fusion requests for the NEXT convolution forward call made by this thread (what the program executor uses to fold the

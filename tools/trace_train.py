@@ -34,3 +34,7 @@ tot = sum(v[1] for v in agg.values())
 print(f"kernel time {tot / 1e3:.2f} ms")
 for n, (cnt, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:24]:
     print(f"{t / 1e3:8.2f} ms {cnt:4d}x {n}")
+if os.environ.get("LIST"):
+    pat = os.environ["LIST"]
+    for e in sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and pat in e.name], key=lambda e: e.time_range.start):
+        print(f"{e.time_range.start - prof.events()[0].time_range.start:10.0f} {e.device_time:8.1f} us  {e.name[:60]}")
