@@ -1111,7 +1111,7 @@ struct DwParams {
   const int2 *pairs;
   const int *d_off;           // K + 1 list offsets
   float *dW;
-  int K, Cin, Cout, chunk, srcIsY, rowBytesA, rowBytesB, R, S, nAcc;
+  int K, Cin, Cout, nC, srcIsY, rowBytesA, rowBytesB, R, S, nAcc; // nC: parts per rule list
 };
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lboBytes) {
   return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lboBytes >> 4) & 0x3fffu) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -1119,7 +1119,6 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t l
 template <bool BF16>
 __global__ void __launch_bounds__(32 * (5 + kDwProd), 1) conv_dw_tc(const DwParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  __shared__ int s_first[66]; // first work item of every list (prefix of ceil(len / chunk))
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // `in` rows narrower than 128 channels are zero-padded to M = 128 in shared memory (zero-filled chunks, no traffic)
   const int R = P.R, nBa = max(P.rowBytesA, 256) / 128, nBb = (P.rowBytesB + 127) / 128;
@@ -1132,9 +1131,6 @@ __global__ void __launch_bounds__(32 * (5 + kDwProd), 1) conv_dw_tc(const DwPara
     for (int i = 0; i < P.S; i++) { mbar_init(smem_u32(full + i), kDwProd * 32); mbar_init(smem_u32(empty + i), 1); }
     for (int i = 0; i < 2; i++) { mbar_init(smem_u32(accFull + i), 1); mbar_init(smem_u32(accEmpty + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    int a = 0;
-    for (int k = 0; k < P.K; k++) { s_first[k] = a; a += (P.d_off[k + 1] - P.d_off[k] + P.chunk - 1) / P.chunk; }
-    s_first[P.K] = a;
   }
   dw_zero_padding(sStage, P.S, stageBytes, blockBytes, (P.rowBytesA + 127) / 128, nBa);
   constexpr int kMmaWarp = 4 + kDwProd;
@@ -1146,22 +1142,28 @@ __global__ void __launch_bounds__(32 * (5 + kDwProd), 1) conv_dw_tc(const DwPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmemBase = *tmemSlot;
-  const int nItems = s_first[P.K];
+  const int nItems = P.K * P.nC;
   const int nMh = (P.Cin + 127) / 128, accCols = nMh * P.Cout;
-  // item -> (list k, first rule, number of rules)
+  // item w -> (list k = w % K, part c = w / K of nC): the rules [len c / nC, len (c + 1) / nC) of list k.  The lists are in row
+  // order, so part c of every list covers about the same region of the grid, and the ~148 items in flight at any time are
+  // all 27 offsets of a few neighbouring parts: their rows stay in L2 across the offsets.  (List-major order swept the whole grid
+  // once per offset: 4.3 GB of DRAM reads for 5.6 GB of requests on the 128 -> 128 level-0 layer, 81 % of the HBM peak.)
   auto item = [&](int w, int &k, int &r0, int &cnt) {
-    k = 0;
-    while (s_first[k + 1] <= w) k++;
+    const int c = w / P.K;
+    k = w - c * P.K;
     const int lo = __ldg(P.d_off + k), hi = __ldg(P.d_off + k + 1);
-    r0 = lo + (w - s_first[k]) * P.chunk;
-    cnt = min(P.chunk, hi - r0);
+    const long len = hi - lo;
+    r0 = lo + (int)(len * c / P.nC);
+    cnt = lo + (int)(len * (c + 1) / P.nC) - r0; // may be 0 (a short list): every role skips such an item
   };
   if (warp < 4) {
     // ---------------- epilogue: partial dW[k] of the item -> global memory (fp32 reductions)
-    int it = 0;
-    for (int w = blockIdx.x; w < nItems; w += gridDim.x, it++) {
+    int itN = 0;
+    for (int w = blockIdx.x; w < nItems; w += gridDim.x) {
       int k, r0, cnt;
       item(w, k, r0, cnt);
+      if (cnt <= 0) continue;
+      const int it = itN++;
       const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
       mbar_wait(smem_u32(accFull + a), use & 1);
       tc_fence_after();
@@ -1190,6 +1192,7 @@ __global__ void __launch_bounds__(32 * (5 + kDwProd), 1) conv_dw_tc(const DwPara
     for (int w = blockIdx.x; w < nItems; w += gridDim.x) {
       int k, r0, cnt;
       item(w, k, r0, cnt);
+      if (cnt <= 0) continue;
       // the rule ids of a stage are fetched two stages ahead: the dependent chain (ids -> row addresses -> copies) otherwise
       // costs one memory round trip per stage and sets the pace of the whole kernel on narrow layers
       auto load_pair = [&](int base) {
@@ -1217,10 +1220,12 @@ __global__ void __launch_bounds__(32 * (5 + kDwProd), 1) conv_dw_tc(const DwPara
     constexpr int kRulesPerMma = BF16 ? 16 : 8;
     const uint32_t aBlkStride16 = ((uint32_t)(nBa / nMh) * blockBytes) >> 4; // second half of M (channels 128..255): descriptor units
     uint32_t slot = 0, round = 0;
-    int it = 0;
-    for (int w = blockIdx.x; w < nItems; w += gridDim.x, it++) {
+    int itN = 0;
+    for (int w = blockIdx.x; w < nItems; w += gridDim.x) {
       int k, r0, cnt;
       item(w, k, r0, cnt);
+      if (cnt <= 0) continue;
+      const int it = itN++;
       const int a = P.nAcc == 2 ? (it & 1) : 0, use = P.nAcc == 2 ? (it >> 1) : it;
       mbar_wait(smem_u32(accEmpty + a), (use & 1) ^ 1);
       tc_fence_after();
@@ -1565,11 +1570,15 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
     ++g_counters[kCntDwPlanLaunch];
     return 0;
   }
-  long chunk = (total + kSMs * 3 - 1) / (kSMs * 3);
-  chunk = std::max<long>(4 * P.R, (chunk + P.R - 1) / P.R * P.R);
-  P.chunk = (int)chunk;
-  long nItems = 0;
-  for (int k = 0; k < K; k++) nItems += (offHost[k + 1] - offHost[k] + chunk - 1) / chunk;
+  // parts per list: ~8K rules each on the large levels (the rows of all offsets of the parts in flight then fit in L2), at least
+  // ~3 items per SM where the lists are long enough, never parts of fewer than 4 stages
+  static int envPart = -1;
+  if (envPart < 0) envPart = getenv("SCN_DW_PART") ? atoi(getenv("SCN_DW_PART")) : 8192;
+  const long avgLen = std::max<long>(1, total / K);
+  long nC = std::max<long>(1, avgLen / envPart);
+  if (K * nC < 3 * kSMs) nC = std::max<long>(nC, std::min<long>(cdiv(3 * kSMs, K), std::max<long>(1, avgLen / (4 * P.R))));
+  P.nC = (int)std::min<long>(nC, 4096);
+  const long nItems = (long)K * P.nC;
   const size_t smemBytes = (size_t)P.S * stageBytes + 64 * 8 + 64;
   static bool attr = false;
   if (!attr) {

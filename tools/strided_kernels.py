@@ -20,11 +20,17 @@ ap = argparse.ArgumentParser()
 ap.add_argument("what", choices=["conv", "deconv", "dw"])
 ap.add_argument("--math", default="bf16")
 ap.add_argument("--reps", type=int, default=4)
+ap.add_argument("--sorted", action="store_true", help="input points in spatial order (rows then numbered like the internally numbered Metadata of a replayed step)")
 a = ap.parse_args()
 scn.set_math_mode(a.math)
 L = torch.LongTensor
 full, half = [2048, 2048, 512], [1024, 1024, 256]
-coords = torch.from_numpy(synthetic.building_coords()).cuda()
+c_np = synthetic.building_coords()
+if a.sorted:
+    import numpy as np
+    key = (c_np[:, 0] // 8 * 4096 + c_np[:, 1] // 8) * 4096 + c_np[:, 2] // 8  # 8^3 blocks, then row-major inside
+    c_np = c_np[np.lexsort((c_np[:, 2], c_np[:, 1], c_np[:, 0], key))]
+coords = torch.from_numpy(c_np).cuda()
 md = scn.Metadata(3)
 scn.SCN.InputLayer_updateOutput(md, L(full), coords, torch.zeros(coords.size(0), 1, device="cuda"), torch.empty(0, device="cuda"), 0, 4)
 n0 = md.getNActive(L(full))
