@@ -469,6 +469,17 @@ __global__ void __launch_bounds__(CTAS == 1 ? 576 : (PW == 8 ? 448 : (SCN_EPI_CO
           n++;
           mbar_wait_t(smem_u32(empty + slot), (round & 1u) ^ 1u, pw0, prof);
           const uint32_t sbase = smem_u32(sStage) + slot * stageBytes;
+          // Everything that does not depend on the row is computed once per stage: the producers are paced by their instruction issue
+          // rate (ncu: ~20 SASS instructions per copy, waiting for a free slot only a third of the time), so a copy is SHFL + clamp +
+          // compare + one IMAD.WIDE (row id x row bytes + per-lane base) + the request.  A missing neighbour (id < 0) or a chunk
+          // beyond a narrow row (a 32-channel lateral) requests 0 bytes = zero fill; its address stays inside row 0.
+          const bool inRow = G > 1 || c * 128 + chunk * 16 < srcRowBytes;
+          unsigned long long laneBase = reinterpret_cast<unsigned long long>(G == 1 ? srcBase + (inRow ? c * 128 + chunk * 16 : 0) : P.in + sub * 16);
+          asm volatile("" : "+l"(laneBase)); // one 64-bit value: the address of a row is then a single IMAD.WIDE
+          const int notInRow = inRow ? 0 : (int)0x80000000; // OR-ed into the id: such a lane always requests 0 bytes
+          const unsigned rowStep = G == 1 ? (unsigned)srcRowBytes : (unsigned)(128 / G);
+          const uint32_t dstLane = sbase + (uint32_t)(pw * kRowsPerWarp + rsub) * 128u;
+          const uint32_t swz0 = (uint32_t)(chunk ^ rsub) << 4, swz1 = (uint32_t)(chunk ^ (rsub + 4)) << 4; // row & 7 = rsub (i even) or rsub + 4 (i odd)
           if (!(P.dbg & 1)) {
 #pragma unroll
             for (int t = 0; t < TM; t++) {
@@ -481,12 +492,9 @@ __global__ void __launch_bounds__(CTAS == 1 ? 576 : (PW == 8 ? 448 : (SCN_EPI_CO
                   const int v = __shfl_sync(0xffffffffu, idc[g][t], i * 4 + rsub);
                   if (g == myG) id = v;
                 }
-                const int row = pw * kRowsPerWarp + i * 4 + rsub;
-                const unsigned char *src = G == 1 ? srcBase + (size_t)(id >= 0 ? id : 0) * srcRowBytes + c * 128 + chunk * 16
-                                                  : P.in + (size_t)(id >= 0 ? id : 0) * (128 / G) + sub * 16;
-                // rows narrower than the atom (a 32-channel bf16 lateral): the missing chunks are zero-filled
-                const bool have = id >= 0 && (G > 1 || c * 128 + chunk * 16 < srcRowBytes);
-                cp_async16(sbase + t * kAtomBytes + row * 128 + ((chunk ^ (row & 7)) << 4), have ? src : srcBase, have ? 16u : 0u);
+                id |= notInRow;
+                const void *src = reinterpret_cast<const void *>(laneBase + (unsigned long long)(unsigned)max(id, 0) * rowStep);
+                cp_async16(dstLane + (uint32_t)(t * kAtomBytes + i * 512) + ((i & 1) ? swz1 : swz0), src, id >= 0 ? 16u : 0u);
               }
             }
           }
@@ -1050,43 +1058,56 @@ __device__ __forceinline__ DwLane dw_lane(int rowBytesA, int rowBytesB, int lane
   }
   return L;
 }
+// one operand of a stage: the RW rows of this warp, ids in lanes 0..RW-1 (replicated every RW lanes)
+template <int RW>
+__device__ __forceinline__ void dw_fill_operand(const unsigned char *base, int rowBytes, int nB, uint32_t mask, uint32_t chunkOff, int ids, uint32_t sOp,
+                                                uint32_t blockBytes, int pw, int lane) {
+  if (rowBytes <= 64) {
+    // Narrow rows (64 / 32 bytes = 32 / 16 bf16 channels): 4 / 2 lanes per row, 8 / 16 rows per instruction instead of 4 -- only the
+    // chunks that exist are written, the rest of the 128-byte row stays zero from the start of the launch (dw_zero_padding).
+    const int cpr = rowBytes >> 4, sh = cpr == 4 ? 2 : 1; // chunks per row (power of two), log2
+    const int ch = lane & (cpr - 1), rs = lane >> sh, rpi = 32 >> sh;
+#pragma unroll 1
+    for (int i = 0; i < RW; i += rpi) {
+      const int rl = i + rs;
+      const bool mine = rl < RW;
+      const int id = __shfl_sync(0xffffffffu, ids, mine ? rl : 0);
+      const int row = pw * RW + rl;
+      if (mine) cp_async16(sOp + (uint32_t)row * 128u + ((uint32_t)(ch ^ (row & 7)) << 4), base + (size_t)max(id, 0) * rowBytes + ch * 16, id >= 0 ? 16u : 0u);
+    }
+    return;
+  }
+  const int chunk = lane & 7, rsub = lane >> 3;
+#pragma unroll 2
+  for (int i = 0; i < RW / 4; i++) {
+    const int rl = i * 4 + rsub;
+    const int id = __shfl_sync(0xffffffffu, ids, rl);
+    const int row = pw * RW + rl;
+    const uint32_t dst = sOp + (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4);
+    const unsigned char *pr = base + (size_t)max(id, 0) * rowBytes;
+    const uint32_t ok = id >= 0 ? 16u : 0u;
+#pragma unroll 1
+    for (int b = 0; b < nB; b++) {
+      const bool v = (mask >> b) & 1u; // this lane's chunk of block b lies inside the row
+      cp_async16(dst + (uint32_t)b * blockBytes, pr + (v ? (uint32_t)b * 128u + chunkOff : 0u), v ? ok : 0u);
+    }
+  }
+}
 template <int RW>
 __device__ __forceinline__ void dw_fill_stage(const DwLane &L, const unsigned char *A, const unsigned char *B, int rowBytesA, int rowBytesB, int srcId, int dstId,
                                               uint32_t sbase, uint32_t blockBytes, int nBa, int pw, int lane) {
   static_assert(RW >= 4 && RW % 4 == 0, "a producer warp requests 4 rows per instruction");
   // Rolled loops with everything loop-invariant hoisted: ~10 instructions per copy.  (Fully unrolled with per-copy predicates the
-  // compiler produced ~40 instructions per copy, ~800 per warp and stage, and the eight producer warps' issue rate set the pace.)
-  const int chunk = lane & 7, rsub = lane >> 3;
-  const uint32_t bBase = (uint32_t)nBa * blockBytes;
-#pragma unroll 2
-  for (int i = 0; i < RW / 4; i++) {
-    const int rl = i * 4 + rsub;
-    const int ia = __shfl_sync(0xffffffffu, srcId, rl), ib = __shfl_sync(0xffffffffu, dstId, rl);
-    const int row = pw * RW + rl;
-    const uint32_t dst = sbase + (uint32_t)row * 128u + ((uint32_t)(chunk ^ (row & 7)) << 4);
-    const unsigned char *pa = A + (size_t)max(ia, 0) * rowBytesA;
-    const unsigned char *pb = B + (size_t)max(ib, 0) * rowBytesB;
-    const uint32_t okA = ia >= 0 ? 16u : 0u, okB = ib >= 0 ? 16u : 0u;
-#pragma unroll 1
-    for (int b = 0; b < L.nBaReal; b++) {
-      const bool v = (L.maskA >> b) & 1u; // this lane's chunk of block b lies inside the row
-      cp_async16(dst + (uint32_t)b * blockBytes, pa + (v ? (uint32_t)b * 128u + L.chunkOff : 0u), v ? okA : 0u);
-    }
-#pragma unroll 1
-    for (int b = 0; b < L.nBb; b++) {
-      const bool v = (L.maskB >> b) & 1u;
-      cp_async16(dst + bBase + (uint32_t)b * blockBytes, pb + (v ? (uint32_t)b * 128u + L.chunkOff : 0u), v ? okB : 0u);
-    }
-  }
+  // compiler produced ~40 instructions per copy, ~800 per warp and stage, and the producer warps' issue rate set the pace.)
+  dw_fill_operand<RW>(A, rowBytesA, L.nBaReal, L.maskA, L.chunkOff, srcId, sbase, blockBytes, pw, lane);
+  dw_fill_operand<RW>(B, rowBytesB, L.nBb, L.maskB, L.chunkOff, dstId, sbase + (uint32_t)nBa * blockBytes, blockBytes, pw, lane);
 }
-// zero the blocks of every stage that hold the channel padding of A (rows narrower than 256 bytes): written here once, read by the MMAs only
+// Zero the whole stage ring once per launch: the blocks that hold the channel padding of A (rows narrower than 256 bytes) and the
+// chunks of a 128-byte row beyond a narrow row's end are never written by the producers and read (as zeros) by every MMA.
 __device__ __forceinline__ void dw_zero_padding(unsigned char *sStage, int S, uint32_t stageBytes, uint32_t blockBytes, int nBaReal, int nBa) {
-  if (nBaReal >= nBa) return;
-  const uint32_t padBytes = (uint32_t)(nBa - nBaReal) * blockBytes;
-  for (int st = 0; st < S; st++) {
-    uint4 *q = reinterpret_cast<uint4 *>(sStage + (size_t)st * stageBytes + (size_t)nBaReal * blockBytes);
-    for (uint32_t i = threadIdx.x; i < padBytes / 16; i += blockDim.x) q[i] = make_uint4(0u, 0u, 0u, 0u);
-  }
+  uint4 *q = reinterpret_cast<uint4 *>(sStage);
+  const uint32_t n = (uint32_t)S * stageBytes / 16u;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) q[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async(); // generic-proxy writes -> the tensor core's (async proxy) reads
 }
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t addr, uint32_t lboBytes);
@@ -1570,10 +1591,10 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
     ++g_counters[kCntDwPlanLaunch];
     return 0;
   }
-  // parts per list: ~8K rules each on the large levels (the rows of all offsets of the parts in flight then fit in L2), at least
+  // parts per list: ~4K rules each on the large levels (the rows of all offsets of the parts in flight then fit in L2), at least
   // ~3 items per SM where the lists are long enough, never parts of fewer than 4 stages
   static int envPart = -1;
-  if (envPart < 0) envPart = getenv("SCN_DW_PART") ? atoi(getenv("SCN_DW_PART")) : 8192;
+  if (envPart < 0) envPart = getenv("SCN_DW_PART") ? atoi(getenv("SCN_DW_PART")) : 4096;
   const long avgLen = std::max<long>(1, total / K);
   long nC = std::max<long>(1, avgLen / envPart);
   if (K * nC < 3 * kSMs) nC = std::max<long>(nC, std::min<long>(cdiv(3 * kSMs, K), std::max<long>(1, avgLen / (4 * P.R))));
