@@ -53,8 +53,31 @@ class RPNModule(nn.Module):
         self.box_selector_test.eval()
         if self.group_num == 1:
             return self.box_selector_test(anchors, objectness.squeeze(1), rpn_box_regression, targets), {}
-        boxes_g = [self.box_selector_test(anchors, objectness[:, gi].contiguous(), rpn_box_regression[:, gi * 7:gi * 7 + 7].contiguous(), targets)
-                   for gi in range(self.group_num)]                                         # seperate_classifier.py:68-71
+        # seperate_classifier.py:68-71.  The class groups are independent: each is queued on a stream of its own (the greedy NMS sweep
+        # is one CTA) and nothing is read back until all of them are queued -- one device round trip for the proposal counts instead
+        # of one per group in the middle of the work.
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_streams") or len(self._streams) != self.group_num:
+            self._streams = [torch.cuda.Stream() for _ in range(self.group_num)]
+        pending = []
+        for gi, st in enumerate(self._streams):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                obj_g, reg_g = objectness[:, gi].contiguous(), rpn_box_regression[:, gi * 7:gi * 7 + 7].contiguous()
+                for t in (objectness, rpn_box_regression, anchors.bbox3d):
+                    t.record_stream(st)
+                pending.append(self.box_selector_test(anchors, obj_g, reg_g, targets, lazy=True))
+        for st in self._streams:
+            cur.wait_stream(st)
+        for group in pending:  # allocated on the side streams, consumed on the caller's from here on
+            for b, n_keep in group:
+                for t in [b.bbox3d, n_keep] + list(b.extra_fields.values()):
+                    t.record_stream(cur)
+        flat = postproc.truncate_lazy([pb for group in pending for pb in group])
+        boxes_g, k = [], 0
+        for group in pending:
+            boxes_g.append(flat[k:k + len(group)])
+            k += len(group)
         return boxes_g, {}
 
 

@@ -101,17 +101,21 @@ def boxes_iou_3d(targets_bbox3d, anchors_bbox3d, aug_thickness=None, criterion=-
     return out
 
 
-def rotate_nms_3d(rbboxes, scores, pre_max_size=None, post_max_size=None, iou_threshold=0.5, flag=''):
-    """second/pytorch/core/box_torch_ops.py:489-514 -> int64 indices into rbboxes, in descending score order."""
+def rotate_nms_3d(rbboxes, scores, pre_max_size=None, post_max_size=None, iou_threshold=0.5, flag='', lazy=False):
+    """second/pytorch/core/box_torch_ops.py:489-514 -> int64 indices into rbboxes, in descending score order.
+    lazy=True: no device round trip -- returns (keep [post] padded with index 0, n_keep 1-element device tensor); the caller truncates."""
     b, s = _dev(rbboxes), _dev(scores).reshape(-1)
     n = b.shape[0]
     if n == 0:
-        return torch.zeros([0]).long().to(b.device)
+        empty = torch.zeros([0]).long().to(b.device)
+        return (empty, torch.zeros(1, dtype=torch.int64, device=b.device)) if lazy else empty
     pre = min(n, pre_max_size) if pre_max_size is not None else n
     post = pre if post_max_size is None else min(pre, int(post_max_size))
-    keep = torch.empty(max(post, 1), dtype=torch.int64, device=b.device)
+    keep = torch.zeros(max(post, 1), dtype=torch.int64, device=b.device)
     n_keep = torch.zeros(1, dtype=torch.int64, device=b.device)
     check(lib().scn_rotate_nms_3d(_p(b), _p(s), n, pre, post, float(iou_threshold), _p(keep), _p(n_keep), _stream()))
+    if lazy:
+        return keep, n_keep
     return keep[:int(n_keep.item())]
 
 
@@ -146,8 +150,9 @@ class Boxes3D(object):
         return out
 
 
-def boxlist_nms_3d(boxlist, nms_thresh, nms_aug_thickness=None, max_proposals=-1, score_field="score", flag=''):
-    """maskrcnn_benchmark/structures/boxlist_ops_3d.py:14-61."""
+def boxlist_nms_3d(boxlist, nms_thresh, nms_aug_thickness=None, max_proposals=-1, score_field="score", flag='', lazy=False):
+    """maskrcnn_benchmark/structures/boxlist_ops_3d.py:14-61.  lazy=True -> (boxlist of max_proposals rows, n_keep device tensor): the rows
+    beyond n_keep are padding, `truncate_lazy` cuts them off after ONE device round trip for all pending lists."""
     if nms_aug_thickness is None:
         nms_aug_thickness = [0, 0]
     if flag == 'rpn_post':
@@ -162,8 +167,18 @@ def boxlist_nms_3d(boxlist, nms_thresh, nms_aug_thickness=None, max_proposals=-1
     bbox3d = boxlist.bbox3d.clone().detach()
     bbox3d[:, 3:5] = torch.clamp(bbox3d[:, 3:5], min=nms_aug_thickness[0])
     bbox3d[:, 5] = torch.clamp(bbox3d[:, 5], min=nms_aug_thickness[1])
-    keep = rotate_nms_3d(bbox3d, objectness, pre_max_size=2000, post_max_size=max_proposals, iou_threshold=nms_thresh, flag=flag)
+    keep = rotate_nms_3d(bbox3d, objectness, pre_max_size=2000, post_max_size=max_proposals, iou_threshold=nms_thresh, flag=flag, lazy=lazy)
+    if lazy:
+        return boxlist[keep[0]], keep[1]
     return boxlist[keep]
+
+
+def truncate_lazy(pending):
+    """pending: list of (Boxes3D padded, n_keep device tensor) from boxlist_nms_3d(lazy=True) -> list of Boxes3D, one host read for all."""
+    if not pending:
+        return []
+    counts = torch.cat([n for _, n in pending]).tolist()
+    return [b[torch.arange(c, device=b.bbox3d.device)] if c < len(b) else b for (b, _), c in zip(pending, counts)]
 
 
 class RPNPostProcessor(torch.nn.Module):
@@ -179,7 +194,7 @@ class RPNPostProcessor(torch.nn.Module):
         self.min_size = min_size
         self.box_coder = box_coder if box_coder is not None else BoxCoder3D()
 
-    def forward_for_single_feature_map(self, anchors, objectness, box_regression, targets=None):
+    def forward_for_single_feature_map(self, anchors, objectness, box_regression, targets=None, lazy=False):
         """anchors: Boxes3D (all examples of the batch concatenated), objectness [N], box_regression [N, 7] (:82-161).
         -> list of Boxes3D, one per example, with the field "objectness"."""
         assert objectness.shape[0] == box_regression.shape[0] == len(anchors)
@@ -195,13 +210,13 @@ class RPNPostProcessor(torch.nn.Module):
             boxlist = Boxes3D(proposals_i, size3d, mode="yx_zb", examples_idxscope=torch.tensor([[0, proposals_i.shape[0]]]), constants={'prediction': True})
             boxlist.add_field("objectness", objectness_i)
             result.append(boxlist_nms_3d(boxlist, self.nms_thresh, nms_aug_thickness=self.nms_aug_thickness, max_proposals=self.fpn_post_nms_top_n,
-                                         score_field="objectness", flag='rpn_post'))                 # :140-147
+                                         score_field="objectness", flag='rpn_post', lazy=lazy))      # :140-147
         return result
 
-    def forward(self, anchors, objectness, box_regression, targets=None, add_gt_proposals=False):
+    def forward(self, anchors, objectness, box_regression, targets=None, add_gt_proposals=False, lazy=False):
         if self.training and add_gt_proposals:
             raise NotImplementedError("appending ground-truth boxes (training) is outside this path")
-        return self.forward_for_single_feature_map(anchors, objectness, box_regression, targets)
+        return self.forward_for_single_feature_map(anchors, objectness, box_regression, targets, lazy=lazy)
 
 
 def voxelize(xyz, feats, scale, full_scale, matrix=None, offset=None, xyz_in_feats=True, batch_index=None):

@@ -132,7 +132,12 @@ class AnchorGenerator(nn.Module):
         locations = [f.metadata.getSpatialLocations(f.spatial_size, device="cuda") if hasattr(f.metadata, "getSpatialLocations") else f.get_spatial_locations()
                      for f in feature_maps_sparse]
         anchors = self.grid_anchors(locations)
-        scopes = [examples_bidx_2_sizes(l[:, -1]) * self.anchor_num_per_loc for l in locations]
+        scopes = []
+        for f, l in zip(feature_maps_sparse, locations):
+            # one batch item (every shipped config): the scope is the whole map -- known on the host, where the reference reads the
+            # batch column back (two device round trips per map)
+            one = hasattr(f.metadata, "getBatchSize") and f.metadata.getBatchSize(f.spatial_size) == 1
+            scopes.append((torch.tensor([[0, l.shape[0]]]) if one else examples_bidx_2_sizes(l[:, -1])) * self.anchor_num_per_loc)
         return anchors, scopes
 
 

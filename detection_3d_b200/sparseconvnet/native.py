@@ -146,6 +146,12 @@ class Metadata_3(object):
         check(lib().scn_get_nactive(self._h, l3(spatial_size), C.byref(n)))
         return n.value
 
+    def getBatchSize(self, spatial_size):
+        """number of batch items on the grid of `spatial_size` (known on the host: no device round trip)"""
+        b = C.c_int()
+        check(lib().scn_get_batch_size(self._h, l3(spatial_size), C.byref(b)))
+        return b.value
+
     def getSpatialLocations(self, spatial_size, device="cpu"):
         """int64 [nActive, 4] (x, y, z, batch) in row order; the reference returns a CPU tensor."""
         n = self.getNActive(spatial_size)

@@ -37,3 +37,13 @@ with torch.no_grad():
         tail(maps)
     torch.cuda.synchronize(); pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+from torch.profiler import ProfilerActivity, profile
+import collections, re
+with torch.no_grad():
+    maps, _ = net(pts); torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        tail(maps); torch.cuda.synchronize()
+ev = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+t0 = ev[0].time_range.start
+for e in ev:
+    print(f"{e.time_range.start - t0:8.0f} {e.device_time:7.1f} us  {re.sub(r'\(.*', '', e.name)[:70]}")
