@@ -366,7 +366,8 @@ def _tc_or_skip(scn):
 
 
 @pytest.mark.parametrize("math", ["tf32", "bf16"])
-@pytest.mark.parametrize("cin,cout,f", [(9, 32, 3), (32, 32, 3), (64, 64, 3), (128, 128, 3), (256, 256, 3), (32, 128, 1), (64, 128, 3), (256, 128, 1), (20, 64, 3)])
+@pytest.mark.parametrize("cin,cout,f", [(9, 32, 3), (32, 32, 3), (64, 64, 3), (128, 128, 3), (256, 256, 3), (32, 128, 1), (64, 128, 3), (256, 128, 1), (20, 64, 3),
+                                       (48, 256, 3)])  # (48 -> 256: rows padded to 64 channels AND copied to bf16, two scratch buffers in one launch)
 def test_tc_submanifold_forward(cin, cout, f, math):
     scn, G, O = _setup_levels()
     _tc_or_skip(scn)
@@ -482,7 +483,7 @@ def test_bf16_shadow_from_batchnorm_and_add():
 
 
 @pytest.mark.parametrize("math", ["tf32", "bf16"])
-@pytest.mark.parametrize("cin,cout", [(32, 64), (128, 128)])
+@pytest.mark.parametrize("cin,cout", [(32, 64), (128, 128), (48, 64)])
 def test_tc_strided_conv_and_z_collapse(cin, cout, math):
     scn, G, O = _setup_levels()
     _tc_or_skip(scn)
