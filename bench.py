@@ -604,6 +604,8 @@ def main():
     if not args.no_extras:  # BASELINE.json configs 4 and 5 ride along (same process group; a failing sub-leg never costs the headline)
         for name, fn in (("rpn", lambda: leg_rpn(args, rank, world, dev, net, coords_pin, feats_pin)), ("batch64", lambda: leg_batch64(args, rank, world, dev, net)),
                          ("train", lambda: leg_train(args, rank, world, dev, scn))):
+            if name in os.environ.get("BENCH_SKIP", "").split(","):  # developer switch
+                continue
             try:
                 line[name] = fn()
             except Exception as e:
@@ -656,6 +658,10 @@ def dominant_kernel_roofline(scn, torch, dev, coords_dev, flush, pk, math):
     """m_mergeds.7: SubmanifoldConvolution 128->128 3^3 on level 0 -- 175.6 of the 334.1 GMAC."""
     L = torch.LongTensor
     md = scn.Metadata(3)
+    # rows numbered as in the timed forward: a replayed program runs on an internally numbered Metadata (row id = spatial rank,
+    # DESIGN.md section 5), not in the reference's first-touch order of the (shuffled) input points
+    from detection_3d_b200._lib import check, lib
+    check(lib().scn_metadata_set_internal_numbering(md._h, 1))
     x0 = torch.empty(0, device=dev)
     scn.SCN.InputLayer_updateOutput(md, L([2048, 2048, 512]), coords_dev, torch.zeros(coords_dev.size(0), 1, device=dev), x0, 0, 4)
     n = md.getNActive(L([2048, 2048, 512]))
@@ -688,7 +694,7 @@ def dominant_kernel_roofline(scn, torch, dev, coords_dev, flush, pk, math):
         tp = os.path.join(ROOT, "profiles", "r1_dominant_kernel_dram_bytes.json")
     if os.path.exists(tp):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch
         traffic = json.load(open(tp)).get(math)
-    return {"kernel": "conv_plan_tc (SubmanifoldConvolution 128->128 3^3, level 0: m_mergeds.7)", "bound": "tensor", "achieved": achieved,
+    return {"kernel": "conv_plan_tc (SubmanifoldConvolution 128->128 3^3, level 0: m_mergeds.7; rows in the internal numbering of the timed forward)", "bound": "tensor", "achieved": achieved,
             "peak": pk["tc_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tc_burst"], "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
             "ms_per_launch": ms, "algorithmic_flops": 2 * macs, "traffic": traffic, "algorithmic_hbm_bytes": alg_bytes,
             "hbm_gbs_if_compulsory_only": alg_bytes / (ms * 1e-3) / 1e9, "l2_gather_bytes": gather_bytes,

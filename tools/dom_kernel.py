@@ -15,11 +15,21 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--math", default="tf32")
 ap.add_argument("--c", type=int, default=128)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--internal", action="store_true", help="internally numbered Metadata (row id = spatial rank), as a replayed forward uses")
+ap.add_argument("--sorted", action="store_true", help="input points in spatial (8^3 block) order: rows numbered like the internally numbered Metadata of a replayed forward")
 a = ap.parse_args()
 scn.set_math_mode(a.math)
 L = torch.LongTensor
-coords = torch.from_numpy(synthetic.building_coords()).cuda()
+c_np = synthetic.building_coords()
+if a.sorted:
+    import numpy as np
+    key = (c_np[:, 0] // 8 * 4096 + c_np[:, 1] // 8) * 4096 + c_np[:, 2] // 8
+    c_np = c_np[np.lexsort((c_np[:, 2], c_np[:, 1], c_np[:, 0], key))]
+coords = torch.from_numpy(c_np).cuda()
 md = scn.Metadata(3)
+if a.internal:
+    from detection_3d_b200._lib import check, lib
+    check(lib().scn_metadata_set_internal_numbering(md._h, 1))
 x0 = torch.empty(0, device="cuda")
 scn.SCN.InputLayer_updateOutput(md, L([2048, 2048, 512]), coords, torch.zeros(coords.size(0), 1, device="cuda"), x0, 0, 4)
 n = md.getNActive(L([2048, 2048, 512]))
