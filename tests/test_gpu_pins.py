@@ -838,3 +838,56 @@ def test_detector_backbone_rpn_proposals_end_to_end():
         assert tuple(got.bbox3d.shape) == wb.shape
         _close(got.bbox3d.cpu().numpy(), wb, 3e-3, 3e-4)   # the backbone's fp32 end-to-end tolerance carried through head and decode
         np.testing.assert_allclose(got.get_field("objectness").cpu().numpy(), wo, rtol=3e-3, atol=3e-4)
+
+
+# ------------------------------------------------------------------ replayed training step: input gradient, misuse
+def test_replayed_training_step_input_gradient_and_misuse():
+    """The replayed training step (program.TrainFunction) against the layer-by-layer autograd path of the same network: gradient of
+    the network INPUT (InputLayer backward through scn_program_backward, gradients brought from the reference's row order into the
+    internal one on the way in) and parameter gradients, fp32 mode (summation order only); a second training forward before
+    backward() raises instead of using activations that are gone."""
+    scn = _scn()
+    cfg = dict(fpn_util.mini4_config(), track_running_stats=True)
+    coords = synthetic.building_coords(nx=52, ny=44, nz=20, n_walls=3, seed=4)
+    feats_np = fpn_util.features_for(coords)
+    rs = np.random.RandomState(0)
+
+    def step(net, w):
+        net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+        net.zero_grad(set_to_none=True)
+        f = torch.from_numpy(feats_np).cuda().requires_grad_(True)
+        rpn, roi = net([torch.from_numpy(coords), f])
+        loss = sum((m.features * wi).sum() for m, wi in zip(rpn + roi, w))
+        loss.backward()
+        return f.grad.clone(), {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}, [m.features.detach().clone() for m in rpn + roi]
+
+    try:
+        scn.set_math_mode("fp32")
+        net = scn.FPN_Net(**cfg)
+        net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+        net = net.cuda().train()
+        with torch.no_grad():
+            net.eval()
+            shapes = [m.features.shape for m in sum(net([torch.from_numpy(coords), torch.from_numpy(feats_np).cuda()]), [])]
+            net.train()
+        w = [torch.from_numpy(rs.randn(*s).astype(np.float32)).cuda() for s in shapes]
+        df0, g0, o0 = step(net, w)            # layer by layer (records)
+        assert net.__dict__.get("_program_train") is not None, net.__dict__.get("_program_train_error")
+        n0 = scn.SCN.lib().scn_debug_counter(11)
+        df1, g1, o1 = step(net, w)            # replayed
+        assert scn.SCN.lib().scn_debug_counter(11) == n0 + 1
+        torch.cuda.synchronize()
+        for a, b in zip(o0, o1):
+            _close(b.cpu().numpy(), a.cpu().numpy(), 2e-3, 2e-4)
+        assert set(g0) == set(g1)
+        for k in g0:
+            _close(g1[k].cpu().numpy(), g0[k].cpu().numpy(), 5e-3, 5e-4)
+        _close(df1.cpu().numpy(), df0.cpu().numpy(), 5e-3, 5e-4)
+        # misuse: two forwards, then backward of the first
+        f = torch.from_numpy(feats_np).cuda()
+        rpn_a, _ = net([torch.from_numpy(coords), f])
+        net([torch.from_numpy(coords), f])
+        with pytest.raises(RuntimeError, match="another forward"):
+            rpn_a[0].features.sum().backward()
+    finally:
+        scn.set_math_mode("fp32")
