@@ -86,6 +86,7 @@ SYMBOLS = {
     "scn_tensor_core_path_available": (_i, []),
     "scn_kernel_launch_count": (_l, []),
     "scn_debug_counter": (_l, [_i]),
+    "scn_release_cached_memory": (_l, []),
     "scn_fuse_next_lateral": (_i, [_vp, _vp, _vp, C.c_longlong, _i, _l]),
     "scn_fuse_next_stats": (_i, [_vp]),
     "scn_fuse_result": (_i, [_pi, _pi]),

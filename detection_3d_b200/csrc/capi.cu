@@ -73,6 +73,8 @@ void set_pool_growth(int on);
 long debug_chunk_mallocs();
 long debug_chunk_waits();
 long debug_chunk_total_mb();
+long release_idle_chunks();
+long release_conv_caches();
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
                         long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0);
@@ -122,6 +124,10 @@ int scn_set_pool_growth(int on) { scn::set_pool_growth(on); return 0; }
 long scn_debug_counter(int which) {
   if (which >= 3 && which < scn::kCntCounters) return scn::g_counters[which].load();
   return which == 0 ? scn::debug_chunk_mallocs() : which == 1 ? scn::debug_chunk_waits() : scn::debug_chunk_total_mb();
+}
+long scn_release_cached_memory(void) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  return scn::release_idle_chunks() + scn::release_conv_caches();
 }
 int scn_fuse_next_lateral(const float *lat_in, const void *lat_in_bf16, const float *lat_weight, long long weight_tag, int n_in, long rows) {
   SCN_CHECK(lat_in && lat_weight && n_in > 0 && rows >= 0, "lateral request");

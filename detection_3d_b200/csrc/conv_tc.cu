@@ -794,13 +794,13 @@ const void *bwd_in16_take() { const void *p = tl_bwd_in16; tl_bwd_in16 = nullptr
 // from the first, so they must not share a buffer; slot 2: the operand pair of the weight-gradient kernel).  Uses of a
 // slot on one stream are ordered; cudaMallocAsync took milliseconds for these 150-300 MB blocks.
 enum ScratchSlot { kScratchPad = 0, kScratchBf16 = 1, kScratchDw = 2, kScratchDout = 3 }; // 3: bf16 copy of d_out shared by the two gradient kernels of a backward call
+static std::mutex g_scratch_mu;
+static std::map<std::tuple<int, cudaStream_t, int>, std::pair<void *, size_t>> g_scratch;
 static int stream_scratch(cudaStream_t s, int slot, size_t bytes, void **out) {
-  static std::mutex mu;
-  static std::map<std::tuple<int, cudaStream_t, int>, std::pair<void *, size_t>> cache;
   int dev = 0;
   SCN_CUDA(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lk(mu);
-  auto &e = cache[std::make_tuple(dev, s, slot)];
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  auto &e = g_scratch[std::make_tuple(dev, s, slot)];
   if (e.second < bytes) {
     if (e.first) { SCN_CUDA(cudaStreamSynchronize(s)); SCN_CUDA(cudaFree(e.first)); }
     e.second = bytes + bytes / 8 + (1u << 20);
@@ -1612,6 +1612,23 @@ int launch_conv_dw_tc(const float *in, const float *d_out, float *dW, const int2
   else conv_dw_tc<false><<<grid, 32 * (5 + kDwProd), smemBytes, LS(s)>>>(P);
   SCN_CUDA(cudaGetLastError());
   return 0;
+}
+
+// frees the cached weight operand images and the per-stream scratch buffers (the caller has synchronised the device) -> bytes released
+long release_conv_caches() {
+  long freed = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_wimg_mu);
+    for (auto &kv : g_wimg) { cudaFree(kv.second.img); cudaEventDestroy(kv.second.ready); freed += (long)kv.second.bytes; }
+    g_wimg.clear();
+    g_wimg_bytes = 0;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    for (auto &kv : g_scratch) if (kv.second.first) { cudaFree(kv.second.first); freed += (long)kv.second.second; }
+    g_scratch.clear();
+  }
+  return freed;
 }
 
 } // namespace scn

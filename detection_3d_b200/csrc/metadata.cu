@@ -42,6 +42,20 @@ long debug_chunk_total_mb() ;
 static size_t g_chunk_bytes_total = 0; // every chunk ever taken from the driver and not returned
 constexpr size_t kChunkKeep = 32ull << 30; // beyond this much idle memory, chunks go back to the driver
 long debug_chunk_total_mb() { return (long)(g_chunk_bytes_total >> 20); }
+// hands every idle chunk back to the driver (the caller has synchronised the device) -> bytes released
+long release_idle_chunks() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  long freed = 0;
+  for (Chunk &k : g_chunks) {
+    if (k.freed) { cudaEventSynchronize(k.freed); cudaEventDestroy(k.freed); }
+    cudaFree(k.p);
+    freed += (long)k.cap;
+    g_chunk_bytes_total -= k.cap;
+  }
+  g_chunks.clear();
+  g_chunk_bytes = 0;
+  return freed;
+}
 constexpr size_t kChunkGrow = 16ull << 30; // below this total, a new chunk is allocated rather than waiting for one that is still in use
 // Size classes are powers of two (>= 32 MiB) and a request is only served by a chunk of exactly its class: every
 // Metadata of a given network then draws the same multiset of classes, and the pool stops growing after the first few

@@ -19,5 +19,5 @@ from .layers import (BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, Conv
                      Metadata, NetworkInNetwork, SparseToDense, SubmanifoldConvolution, ValidConvolution, optionalTensor,
                      optionalTensorReturn, sparse_3d_to_dense_2d, toLongTensor)
 from . import layers as sparseToDense  # noqa: E402  (the reference reaches the class as scn.sparseToDense.SparseToDense, tools_3d_2d.py:26)
-from .native import kernel_launch_count, set_math_mode  # noqa: E402
+from .native import empty_cache, kernel_launch_count, set_math_mode  # noqa: E402
 from .tensor import SparseConvNetTensor  # noqa: E402

@@ -47,6 +47,7 @@ def _opt(t, what):
 # fp32 values; the next convolution gathers from that copy (half the bytes).  The attribute dies
 # with the tensor object and is ignored once the tensor has been modified in place (_version).
 _MATH = {"mode": 0}
+_WEIGHT_IMAGES_DROPPED = [0]  # (statistics only)
 
 
 def _new_shadow(t):
@@ -459,3 +460,14 @@ def math_mode():
 
 def kernel_launch_count():
     return lib().scn_kernel_launch_count()
+
+
+def empty_cache():
+    """Hand the library's idle device memory back to the driver (scn_release_cached_memory): Metadata chunks of finished forwards,
+    cached weight operand images, scratch buffers -- memory torch.cuda.empty_cache() cannot see.  Synchronises the device; live
+    Metadata objects and recorded programs (FPN_Net.reset_program drops a network's) keep theirs.  -> bytes released."""
+    _WEIGHT_IMAGES_DROPPED[0] += 1
+    n = lib().scn_release_cached_memory()
+    if n < 0:
+        raise RuntimeError("scn_release_cached_memory failed")
+    return n

@@ -307,6 +307,11 @@ long scn_kernel_launch_count(void);
  * epilogue), 10 = CUDA-core convolution launches, 11 = backward passes run by scn_program_backward, 12 = bf16 operand copies the
  * weight-gradient kernel took from its caller (forward shadow / shared d_out copy) instead of converting again. */
 long scn_debug_counter(int which);
+/* Hands the library's idle device memory back to the driver: Metadata chunks not owned by a live Metadata, cached weight operand
+ * images, per-stream scratch buffers (the library recycles these itself instead of returning them; torch.cuda.empty_cache() cannot
+ * see them).  Synchronises the device first.  Returns the number of bytes released, -1 on a CUDA error.  Live Metadata objects and
+ * recorded programs keep their memory (destroy them first). */
+long scn_release_cached_memory(void);
 
 /* Fusion requests for the NEXT convolution forward call made by this thread (what the program executor uses to fold the
  * FPN's lateral 1x1x1 convolution and the statistics of a following BatchNorm into a convolution; no reference counterpart:

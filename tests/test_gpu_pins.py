@@ -891,3 +891,29 @@ def test_replayed_training_step_input_gradient_and_misuse():
             rpn_a[0].features.sum().backward()
     finally:
         scn.set_math_mode("fp32")
+
+
+def test_empty_cache_releases_library_memory_and_forward_still_works():
+    """scn.empty_cache() (scn_release_cached_memory): the idle Metadata chunks, weight images and scratch buffers go back to the
+    driver; the next forward allocates them again and gives the same result."""
+    scn = _scn()
+    cfg = fpn_util.mini4_config()
+    net = scn.FPN_Net(**cfg)
+    net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+    net = net.cuda().eval()
+    coords = synthetic.building_coords(nx=44, ny=40, nz=20, n_walls=3, seed=9)
+    x = [torch.from_numpy(coords), torch.from_numpy(fpn_util.features_for(coords)).cuda()]
+    with torch.no_grad():
+        a = [m.features.clone() for m in sum(net(x), [])]
+        a2 = [m.features.clone() for m in sum(net(x), [])]   # replayed
+        del a2
+        net.reset_program()
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info()[0]
+        released = scn.empty_cache()
+        free1 = torch.cuda.mem_get_info()[0]
+        assert released > 0 and free1 > free0, (released, free0, free1)
+        b = [m.features.clone() for m in sum(net(x), [])]
+    torch.cuda.synchronize()
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
