@@ -343,8 +343,10 @@ def leg_train(args, rank, world, dev, scn, steps=5, warmup=2):
     feats = torch.from_numpy(fpn_util.features_for(coords_np)).to(dev)
     params = [p for p in net.parameters() if p.requires_grad]
     red = distributed.GradientReducer(params)
-    times, loss = [], None
+    times, loss, attached = [], None, False
     for it in range(warmup + steps):
+        if not attached:  # from the second step on the backward pass writes into the reducer's buffer and signals per-parameter events
+            attached = red.attach(net)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         if world > 1 and it == warmup:
             dist.barrier()
@@ -385,7 +387,7 @@ def leg_train(args, rank, world, dev, scn, steps=5, warmup=2):
            "gradient_bytes": red.nbytes(), "allreduce_alone": bus, "loss": float(loss), "params_with_grad": with_grad, "params": len(params),
            "scaling": "weak", "steps": steps, "math": {0: "fp32", 1: "tf32", 2: "bf16"}[scn.SCN.math_mode()],
            "replayed": bool(net.__dict__.get("_program_train") is not None), "program_backward_calls": int(scn.SCN.lib().scn_debug_counter(11)),
-           "note": "6c_fpn4321 backbone, one B470 building per rank; first step layer by layer under autograd while the calls are recorded, later steps = ONE autograd node (scn_program_run in training mode + scn_program_backward); gradients land in one flat buffer, buckets all-reduced from hooks"}
+           "note": "6c_fpn4321 backbone, one B470 building per rank; first step layer by layer under autograd while the calls are recorded, later steps = ONE autograd node (scn_program_run in training mode + scn_program_backward) that writes the gradients straight into the reducer's flat buffer; every bucket's all-reduce waits for the events of its own parameters only (overlaps the rest of the backward pass)"}
     del net, red
     torch.cuda.empty_cache()
     return out

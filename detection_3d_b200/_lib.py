@@ -31,7 +31,7 @@ SYMBOLS = {
     "scn_program_prepare": (_i, [_vp, _vp, _vp, _i, _l, _i]),
     "scn_program_throttle": (_i, [_vp]),
     "scn_program_set_training": (_i, [_vp, _i]),
-    "scn_program_backward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _pi]),
+    "scn_program_backward": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _pi, _vp]),
     "scn_metadata_set_internal_numbering": (_i, [_vp, _i]),
     "scn_get_batch_size": (_i, [_vp, L3, _pi]),
     "scn_metadata_build_reference_grids": (_i, [_vp, L3, _vp, _i, _l, _i, _i, _i, _i, _vp, _vp]),

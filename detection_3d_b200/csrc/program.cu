@@ -610,7 +610,7 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
 // top-down levels of the FPN) are skipped, as autograd skips them.  d_features: NULL or the gradient of the
 // network input [nIn rows][planes].
 int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const float *const *d_out, const void *const *params, void *const *param_grads,
-                         int n_params, float *d_features, int *param_live) {
+                         int n_params, float *d_features, int *param_live, void *const *param_events) {
   SCN_CHECK(p && p->train && p->lastMd && p->nRegs > 0, "scn_program_backward needs a preceding training run of this program");
   scn_metadata *m = p->lastMd;
   cudaStream_t s = p->stream;
@@ -623,6 +623,12 @@ int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const f
     if (live[i]) { scn::set_error("program backward: a parameter is used by more than one op (not supported by the replayed training step)"); return -2; }
     live[i] = 1;
     return 0;
+  };
+  // param_events[j] (optional, cudaEvent_t): recorded on the stream right after the kernels that write parameter j's gradient are
+  // queued -- a data-parallel caller starts the all-reduce of a gradient bucket behind the event of its last parameter while the
+  // backward pass of the earlier layers is still running
+  auto done = [&](long i) {
+    if (param_events && i >= 0 && i < n_params && param_events[i]) cudaEventRecord(static_cast<cudaEvent_t>(param_events[i]), s);
   };
   std::vector<float *> g(p->nRegs, nullptr);
   auto elems = [&](long r) -> long { return p->regs[r].rows * (long)p->regs[r].cols; };
@@ -676,6 +682,7 @@ int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const f
         if (!dx) { rc = -1; break; }
         if ((rc = mark(a[3])) || (rc = mark(a[4]))) break;
         rc = scn_batchnorm_backward(X.p, dx, Y.p, dy, X.rows, (int)a[2], p->bnSave[i], p->bnSave[i] + a[2], P(a[3]), G(a[3]), G(a[4]), (float)op.f[2], s);
+        done(a[3]); done(a[4]);
         if (rc == 0) rc = contribute(a[0], dx, true);
         break;
       }
@@ -693,6 +700,7 @@ int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const f
             if ((rc = mark(a[19]))) break;
             rc = scn_network_in_network_backward_input(dl, dy, P(a[19]), Y.rows, Cl, Cout, s);
             if (rc == 0 && G(a[19])) rc = scn_network_in_network_backward_params(Y.p, dy, G(a[19]), nullptr, Y.rows, Cl, Cout, s);
+            done(a[19]);
             if (rc == 0) rc = contribute(a[18], dl, true);
             if (rc) break;
           }
@@ -722,6 +730,7 @@ int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const f
         else if (op.kind == K_CONV) rc = scn_convolution_backward(m, a + 2, a + 5, a + 8, a + 11, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
         else rc = scn_deconvolution_backward(m, a + 2, a + 5, a + 8, a + 11, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
         if (dwTmp) slot_put(p, dwTmp);
+        done(wi); done(bi);
         if (rc == 0 && din) rc = contribute(a[0], din, true);
         break;
       }

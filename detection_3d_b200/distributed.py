@@ -142,9 +142,45 @@ class GradientReducer(object):
             p.grad = self.flat[lo:hi].view_as(p)
             p.register_post_accumulate_grad_hook(self._hook)
 
+    def attach(self, net):
+        """Replayed training steps (FPN_Net's recorded training program, one autograd node per step): the native backward pass writes
+        every parameter gradient straight into this reducer's flat buffer and records an event behind each; when the pass has been
+        QUEUED, every bucket's all-reduce is launched on a side stream that waits for the events of that bucket's parameters only, so
+        the collectives overlap the rest of the backward pass as they do with per-layer hooks.  Call once the program exists (after
+        the first training step); returns False while it does not."""
+        prog = net.__dict__.get("_program_train")
+        if prog is None or not self.flat.is_cuda:
+            return False
+        sink, events, self._prog_bucket = {}, {}, [[] for _ in self.buckets]
+        for i, p in enumerate(prog.params):
+            if p in self.slices:
+                lo, hi = self.slices[p]
+                sink[i] = self.flat[lo:hi].view_as(p)
+                ev = torch.cuda.Event()
+                ev.record()  # (creates the native event; re-recorded by scn_program_backward every step)
+                events[i] = ev
+                self._prog_bucket[self.bucket_of[p]].append(i)
+        prog.grad_sink, prog.grad_events, prog.after_backward = sink, events, self._after_replayed_backward
+        self._side = torch.cuda.Stream()
+        self._zero_ev = torch.cuda.Event()
+        return True
+
+    def _after_replayed_backward(self, prog):
+        if self.world == 1:
+            return
+        for b in range(len(self.buckets)):  # (reverse parameter order = the order in which the backward pass completes them)
+            with torch.cuda.stream(self._side):
+                self._side.wait_event(self._zero_ev)  # buckets without a live parameter are all zeros: only the memset must be done
+                for i in self._prog_bucket[b]:
+                    if prog.last_live[i]:
+                        self._side.wait_event(prog.grad_events[i])
+                self._launch(b)
+
     def zero(self):
         """Start of a step: gradients to zero (one memset), bucket bookkeeping reset."""
         self.flat.zero_()
+        if getattr(self, "_zero_ev", None) is not None:
+            self._zero_ev.record()
         for p in self.params:  # (an optimizer / zero_grad(set_to_none=True) may have dropped the views)
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + self.slices[p][0] * 4:
                 lo, hi = self.slices[p]

@@ -193,15 +193,26 @@ class Program(object):
         regs[i].  -> (one gradient tensor or None per recorded parameter, gradient of the network input or None)."""
         n = len(self.params)
         pairs = [(r, g.contiguous()) for r, g in zip(regs, d_outs) if g is not None and g.numel()]
-        grads = [torch.empty_like(p) if (p.requires_grad and p.is_floating_point()) else None for p in self.params]
+        # grad_sink (set by distributed.GradientReducer.attach): parameter index -> tensor the gradient is WRITTEN into (a view of the
+        # reducer's flat buffer, zeroed by the reducer every step); such parameters return no gradient to autograd.  grad_events:
+        # parameter index -> torch.cuda.Event recorded behind the kernels that write that gradient.
+        sink = getattr(self, "grad_sink", None) or {}
+        events = getattr(self, "grad_events", None) or {}
+        grads = [sink[i] if i in sink else (torch.empty_like(p) if (p.requires_grad and p.is_floating_point()) else None) for i, p in enumerate(self.params)]
         d_feats = torch.empty((n_in_rows, self.planes), dtype=torch.float32, device=self.params[0].device) if want_d_features else None
         ptrs = (C.c_void_p * n)(*[p.data_ptr() for p in self.params])
         gptrs = (C.c_void_p * n)(*[None if g is None else g.data_ptr() for g in grads])
         live = (C.c_int * n)()
         k = max(1, len(pairs))
+        evs = (C.c_void_p * n)(*[events[i].cuda_event if i in events else None for i in range(n)]) if events else None
         check(lib().scn_program_backward(self._h, len(pairs), (C.c_int * k)(*[r for r, _ in pairs]), (C.c_void_p * k)(*[g.data_ptr() for _, g in pairs]),
-                                         ptrs, gptrs, n, None if d_feats is None else C.c_void_p(d_feats.data_ptr()), live))
-        return [g if (g is not None and live[i]) else None for i, g in enumerate(grads)], d_feats
+                                         ptrs, gptrs, n, None if d_feats is None else C.c_void_p(d_feats.data_ptr()), live, evs))
+        self.last_live = [bool(live[i]) for i in range(n)]
+        out = [g if (g is not None and live[i] and i not in sink) else None for i, g in enumerate(grads)]
+        cb = getattr(self, "after_backward", None)
+        if cb is not None:  # (the kernels of the whole backward pass are queued; the reducer launches its buckets behind their events)
+            cb(self)
+        return out, d_feats
 
 
 class TrainFunction(torch.autograd.Function):

@@ -190,7 +190,11 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
  * d_features = NULL or the gradient of the network input.  The Metadata of the run must still be alive. */
 int scn_program_set_training(scn_program *p, int on);
 int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const float *const *d_out, const void *const *params, void *const *param_grads,
-                         int n_params, float *d_features, int *param_live);
+                         int n_params, float *d_features, int *param_live, void *const *param_events);
+/* param_events: NULL, or one cudaEvent_t (or NULL) per parameter, recorded on the program's stream right behind the kernels that
+ * write that parameter's gradient: a data-parallel caller lets the all-reduce of a gradient bucket wait for the event of the bucket's
+ * last parameter only, so that the collective overlaps the rest of the backward pass (the reference: DistributedDataParallel's
+ * bucketed all-reduce, tools/train_net_sparse3d.py:52-58). */
 /* Internal row numbering (used by scn_program_run, never handed to callers): rows of every grid are numbered by spatial
  * index instead of the reference's first-touch order in dense_hash_map iteration order, which removes the hash-order
  * emulation from the critical path.  scn_rows_to_reference_order hands a feature matrix computed under such a Metadata

@@ -917,3 +917,41 @@ def test_empty_cache_releases_library_memory_and_forward_still_works():
     torch.cuda.synchronize()
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+
+
+def test_gradient_reducer_attach_writes_replayed_gradients_into_flat_buffer():
+    """distributed.GradientReducer.attach: the replayed backward pass writes the parameter gradients straight into the reducer's flat
+    buffer (p.grad are views of it) and returns none to autograd; same values as the layer-by-layer step of the same state (fp32)."""
+    scn = _scn()
+    from detection_3d_b200 import distributed
+    cfg = fpn_util.mini4_config()
+    coords = synthetic.building_coords(nx=48, ny=44, nz=20, n_walls=3, seed=6)
+    feats = torch.from_numpy(fpn_util.features_for(coords)).cuda()
+    try:
+        scn.set_math_mode("fp32")
+        net = scn.FPN_Net(**cfg)
+        net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+        net = net.cuda().train()
+        red = distributed.GradientReducer([p for p in net.parameters() if p.requires_grad])
+        assert not red.attach(net)  # no program yet
+        got = []
+        for step in range(3):
+            if step == 1:
+                assert red.attach(net)
+            net.load_state_dict(fpn_util.deterministic_state(net, seed=1))
+            red.zero()
+            rpn, roi = net([torch.from_numpy(coords), feats])
+            sum((m.features ** 2).mean() for m in rpn + roi).backward()
+            red.finish()
+            torch.cuda.synchronize()
+            for p in red.params:  # still views of the flat buffer
+                lo, hi = red.slices[p]
+                assert p.grad.data_ptr() == red.flat.data_ptr() + lo * 4
+            got.append(red.flat.clone())
+        assert scn.SCN.lib().scn_debug_counter(11) >= 2
+    finally:
+        scn.set_math_mode("fp32")
+    assert float(got[0].abs().max()) > 0
+    scale = float(got[0].abs().max())
+    for g in got[1:]:
+        np.testing.assert_allclose(g.cpu().numpy(), got[0].cpu().numpy(), rtol=5e-3, atol=5e-4 * scale)
