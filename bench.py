@@ -327,7 +327,7 @@ def leg_rpn(args, rank, world, dev, net, coords_pin, feats_pin, steps=20, warmup
                     "L2 flush between steps; random-init head"}
 
 
-def leg_train(args, rank, world, dev, scn, steps=5, warmup=2):
+def leg_train(args, rank, world, dev, scn, steps=8, warmup=4):
     """BASELINE.json config 5: 6c_fpn4321 backbone training step (train-mode forward, loss = sum of squares of the returned maps,
     backward), batch 1 per GPU (one B470 building per rank, seed = rank), data-parallel gradient all-reduce over NCCL overlapped
     with the backward pass (distributed.GradientReducer).  CUDA-event times, max over ranks."""

@@ -77,7 +77,7 @@ long release_idle_chunks();
 long release_conv_caches();
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
-                        long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0);
+                        long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0, int wT = 0);
 int to_bf16(const float *x, void *y, long n, cudaStream_t s);
 int dense_rows_dw(const float *in, const float *d_out, float *dW, float *d_bias, long n, int Cin, int Cout, cudaStream_t s);
 static int g_math_mode = 0;
@@ -748,14 +748,9 @@ static int dIn_tensor_core(Metadata &M, const float *d_out, float *d_in, const f
                            const int *outRow, const unsigned long long *tileMask, int nOutPlan, const int *tileW, long nSrcRows, long nDstRows,
                            const void *dout16 = nullptr) {
   cudaStream_t s = M.cstream;
-  float *Wt = nullptr;
-  SCN_CUDA(cudaMallocAsync((void **)&Wt, (size_t)K * Cin * Cout * 4, s));
-  int r = scn::transpose_weights(W, Wt, K, Cin, Cout, reverse, s);
-  if (r == 0)
-    r = scn::launch_conv_plan_tc(d_out, d_in, Wt, nbr, outRow, tileMask, nOutPlan, tileW ? 1 : K, /*Cin=*/Cout, /*Cout=*/Cin, nullptr, scn::g_math_mode, s, tileW, K,
-                                 nSrcRows, dout16, 0, nullptr, nullptr, nDstRows);
-  cudaFreeAsync(Wt, s);
-  return r;
+  // the transposed (and, for the symmetric submanifold plan, offset-reversed) weights are read in place by the operand-image kernel
+  return scn::launch_conv_plan_tc(d_out, d_in, W, nbr, outRow, tileMask, nOutPlan, tileW ? 1 : K, /*Cin=*/Cout, /*Cout=*/Cin, nullptr, scn::g_math_mode, s, tileW, K,
+                                  nSrcRows, dout16, 0, nullptr, nullptr, nDstRows, 0, reverse ? 2 : 1);
 }
 // bf16 mode: one bf16 copy of d_out serves both gradient kernels of a backward call (each used to make its own)
 static int shared_dout16(cudaStream_t s, const float *d_out, long rows, int Cin, int Cout, const void **out) {

@@ -629,7 +629,9 @@ __global__ void __launch_bounds__(CTAS == 1 ? 576 : (PW == 8 ? 448 : (SCN_EPI_CO
 // Cout rows x 128 bytes (32 tf32 / 64 bf16 input channels of one output channel), 16-byte chunks
 // XOR-swizzled by (row & 7); values rounded to nearest (TF32: cvt.rna, BF16: rn).
 // Cin = padded channel count of the image (multiple of the atom width), CinW = channels W really has.
-__global__ void k_prep_wimg(const float *__restrict__ W, unsigned char *__restrict__ img, int K, int Cin, int CinW, int Cout, int bf16) {
+// wT: 0 = W is [K][CinW][Cout]; 1 / 2 = the operand is the TRANSPOSE of a forward weight tensor stored as [K][Cout][CinW] (the input-gradient
+// convolutions: Wt[k'][co][ci] = W[k][ci][co]), 2 = with the filter offsets reversed as well (k' = K - 1 - k) -- read in place, no transposed copy.
+__global__ void k_prep_wimg(const float *__restrict__ W, unsigned char *__restrict__ img, int K, int Cin, int CinW, int Cout, int bf16, int wT) {
   const long n = (long)K * Cin * Cout;
   const int per = bf16 ? 64 : 32, nAtoms = Cin / per;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -639,7 +641,8 @@ __global__ void k_prep_wimg(const float *__restrict__ W, unsigned char *__restri
     const int c = ci / per, j = ci % per;
     const int byte = j * (bf16 ? 2 : 4), chunk = byte >> 4, within = byte & 15;
     unsigned char *dst = img + ((long)k * nAtoms + c) * Cout * 128 + (long)co * 128 + ((chunk ^ (co & 7)) << 4) + within;
-    const float w = ci < CinW ? W[((long)k * CinW + ci) * Cout + co] : 0.f;
+    const int ks = wT == 2 ? K - 1 - k : k;
+    const float w = ci < CinW ? (wT ? W[((long)ks * Cout + co) * CinW + ci] : W[((long)k * CinW + ci) * Cout + co]) : 0.f;
     if (bf16) {
       *reinterpret_cast<unsigned short *>(dst) = __bfloat16_as_ushort(__float2bfloat16_rn(w));
     } else {
@@ -653,7 +656,7 @@ __global__ void k_prep_wimg(const float *__restrict__ W, unsigned char *__restri
 // Packed layers (bf16 rows of 128 / G bytes, G = 2 or 4): the K atom of offset group kg holds, for output channel co,
 // [offset kg G | offset kg G + 1 | ...] x Cin input channels -- the same order in which the producers lay the G
 // gathered neighbour rows side by side.  Offsets beyond K and channels beyond CinW are zero.
-__global__ void k_prep_wimg_packed(const float *__restrict__ W, unsigned char *__restrict__ img, int K, int G, int Cin, int CinW, int Cout) {
+__global__ void k_prep_wimg_packed(const float *__restrict__ W, unsigned char *__restrict__ img, int K, int G, int Cin, int CinW, int Cout, int wT) {
   const int KG = (K + G - 1) / G;
   const long n = (long)KG * G * Cin * Cout;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -663,7 +666,8 @@ __global__ void k_prep_wimg_packed(const float *__restrict__ W, unsigned char *_
     const int kg = k / G, g = k % G;
     const int byte = (g * Cin + ci) * 2, chunk = byte >> 4, within = byte & 15;
     unsigned char *dst = img + (long)kg * Cout * 128 + (long)co * 128 + ((chunk ^ (co & 7)) << 4) + within;
-    const float w = (k < K && ci < CinW) ? W[((long)k * CinW + ci) * Cout + co] : 0.f;
+    const int ks = wT == 2 ? K - 1 - k : k;
+    const float w = (k < K && ci < CinW) ? (wT ? W[((long)ks * Cout + co) * CinW + ci] : W[((long)k * CinW + ci) * Cout + co]) : 0.f;
     *reinterpret_cast<unsigned short *>(dst) = __bfloat16_as_ushort(__float2bfloat16_rn(w));
   }
 }
@@ -685,12 +689,13 @@ static unsigned long long g_wimg_clock = 0;
 constexpr size_t kWimgBudget = 768u << 20;
 // Returns the image; *owned = true when the caller must cudaFreeAsync it (uncached).
 // fmt: 0 = tf32, 1 = bf16, 1 + 16 G = packed bf16 (G offsets per atom)
-static void launch_prep_wimg(const float *W, unsigned char *img, int K, int Cin, int CinW, int Cout, int fmt, cudaStream_t s) {
+static void launch_prep_wimg(const float *W, unsigned char *img, int K, int Cin, int CinW, int Cout, int fmt, cudaStream_t s, int wT) {
   const int G = fmt >> 4;
-  if (G > 1) k_prep_wimg_packed<<<stream_grid((long)((K + G - 1) / G) * G * Cin * Cout, 256), 256, 0, LS(s)>>>(W, img, K, G, Cin, CinW, Cout);
-  else k_prep_wimg<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, img, K, Cin, CinW, Cout, fmt & 1);
+  if (G > 1) k_prep_wimg_packed<<<stream_grid((long)((K + G - 1) / G) * G * Cin * Cout, 256), 256, 0, LS(s)>>>(W, img, K, G, Cin, CinW, Cout, wT);
+  else k_prep_wimg<<<stream_grid((long)K * Cin * Cout, 256), 256, 0, LS(s)>>>(W, img, K, Cin, CinW, Cout, fmt & 1, wT);
 }
-static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int Cout, int bf16, cudaStream_t s, unsigned char **img, bool *owned) {
+static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int Cout, int bf16, cudaStream_t s, unsigned char **img, bool *owned, int wT = 0) {
+  if (wT) tag = 0; // (transposed operands belong to the backward pass of a training step: the weights change every step, nothing to cache)
   const int packG = bf16 >> 4;
   const size_t bytes = packG > 1 ? (size_t)((K + packG - 1) / packG) * Cout * 128 : (size_t)K * Cin * Cout * (bf16 ? 2 : 4);
   *owned = false;
@@ -719,7 +724,7 @@ static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int
     WimgVal v;
     SCN_CUDA(cudaMalloc((void **)&v.img, bytes));
     SCN_CUDA(cudaEventCreateWithFlags(&v.ready, cudaEventDisableTiming));
-    launch_prep_wimg(W, v.img, K, Cin, CinW, Cout, bf16, s);
+    launch_prep_wimg(W, v.img, K, Cin, CinW, Cout, bf16, s, 0);
     SCN_CUDA(cudaEventRecord(v.ready, s));
     v.bytes = bytes; v.stream = s; v.lastUse = ++g_wimg_clock;
     g_wimg[key] = v;
@@ -728,7 +733,7 @@ static int get_wimg(const float *W, long long tag, int K, int Cin, int CinW, int
     return 0;
   }
   SCN_CUDA(cudaMallocAsync((void **)img, bytes, s));
-  launch_prep_wimg(W, *img, K, Cin, CinW, Cout, bf16, s);
+  launch_prep_wimg(W, *img, K, Cin, CinW, Cout, bf16, s, wT);
   *owned = true;
   return 0;
 }
@@ -847,7 +852,7 @@ bool epilogue_stats_take() { bool d = tl_stats_done; tl_stats = nullptr; tl_stat
 // in16: optional bf16 copy of `in` (same layout); used in math mode 2 when Cin is a multiple of 64
 int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *nbr, const int *outRow, const unsigned long long *tileMask,
                         int nOut, int K, int Cin, int Cout, const float *bias, int mathMode, cudaStream_t s, const int *tileW, int nWeights,
-                        long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0) {
+                        long nInRows, const void *in16, long long wTag, const float *addend, void *out16, long nOutRows, int CinW = 0, int wT = 0) {
   if (nOut == 0) return 0;
   if (CinW == 0) CinW = Cin;
   const bool canPack = mathMode == 2 && !tileW && Cout <= 128; // packed narrow rows: two-CTA configuration only
@@ -863,14 +868,14 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
       k_pad_rows_bf16<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
     }
     tl_prepad = nullptr;
-    return launch_conv_plan_tc(in, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, xp, wTag, addend, out16, nOutRows, Cin);
+    return launch_conv_plan_tc(in, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, xp, wTag, addend, out16, nOutRows, Cin, wT);
   }
   if (Cin % 32 != 0 && !(canPack && Cin == 16)) { // rows zero-padded to a multiple of 32 channels (the weight image pads itself)
     const int Cp = (Cin + 31) / 32 * 32;
     float *xp = nullptr;
     SCN_TRY(stream_scratch(s, kScratchPad, (size_t)nInRows * Cp * 4 + 16, (void **)&xp));
     k_pad_rows<<<stream_grid(nInRows * Cp, 256), 256, 0, LS(s)>>>(in, xp, nInRows, Cin, Cp);
-    return launch_conv_plan_tc(xp, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr, wTag, addend, out16, nOutRows, Cin);
+    return launch_conv_plan_tc(xp, out, W, nbr, outRow, tileMask, nOut, K, Cp, Cout, bias, mathMode, s, tileW, nWeights, nInRows, nullptr, wTag, addend, out16, nOutRows, Cin, wT);
   }
   SCN_CHECK(Cout % 16 == 0 && Cout >= 16 && Cout <= 256 && K <= 64, "tcgen05 path: unsupported channel counts");
   static int envT = -1, envS = -1, envDbg = 0, envProf = 0, envCtas = 0;
@@ -953,7 +958,7 @@ int launch_conv_plan_tc(const float *in, float *out, const float *W, const int *
   if (P.kSplit > 1) SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)nOut * Cout * 4, s));
   unsigned char *wimg = nullptr;
   bool wimgOwned = false;
-  SCN_TRY(get_wimg(W, wTag, nWeights, Cin, CinW, Cout, packG > 1 ? 1 + 16 * packG : P.bf16, s, &wimg, &wimgOwned));
+  SCN_TRY(get_wimg(W, wTag, nWeights, Cin, CinW, Cout, packG > 1 ? 1 + 16 * packG : P.bf16, s, &wimg, &wimgOwned, wT));
   P.wimg = wimg;
   P.in2 = nullptr; P.wimg2 = nullptr; P.rowBytes2 = 0; P.nAtoms2 = 0;
   unsigned char *wimg2 = nullptr;
