@@ -382,17 +382,84 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ 
     dx[i] = (d[i] - gradMean[c] - (x[i] - saveMean[c]) * kk[c]) * saveInvStd[c] * (weight ? weight[c] : 1.f);
   }
 }
+// float4 versions (C % 4 == 0): four channels per thread, two rows in flight -- the scalar kernels above ran at well under half of
+// the HBM rate (one 4-byte access in flight per thread, an integer modulo per element in the apply pass).
+__global__ void __launch_bounds__(256) k_bn_bwd_stats4(const float4 *__restrict__ x, const float4 *__restrict__ y, float4 *__restrict__ dy, long n, int C4,
+                                                       int rowsPerCta, const float *__restrict__ saveMean, float leak, double *__restrict__ stats) {
+  __shared__ float4 S[256], Q[256];
+  const int tid = threadIdx.x;
+  const int cols = min(C4, 256), rowLanes = 256 / cols;
+  const long r0 = (long)blockIdx.x * rowsPerCta, r1 = min(n, r0 + rowsPerCta);
+  for (int cb = 0; cb < C4; cb += cols) {
+    const int c = cb + tid % cols, rl = tid / cols;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (rl < rowLanes && c < C4) {
+      const float4 m = __ldg(reinterpret_cast<const float4 *>(saveMean) + c);
+      auto one = [&](const float4 &xv, const float4 &yv, float4 d) {
+        d.x *= yv.x > 0 ? 1.f : leak; d.y *= yv.y > 0 ? 1.f : leak; d.z *= yv.z > 0 ? 1.f : leak; d.w *= yv.w > 0 ? 1.f : leak;
+        s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+        q.x = fmaf(xv.x - m.x, d.x, q.x); q.y = fmaf(xv.y - m.y, d.y, q.y); q.z = fmaf(xv.z - m.z, d.z, q.z); q.w = fmaf(xv.w - m.w, d.w, q.w);
+        return d;
+      };
+      long r = r0 + rl;
+      for (; r + rowLanes < r1; r += 2 * rowLanes) { // two rows in flight
+        const long i0 = r * C4 + c, i1 = (r + rowLanes) * C4 + c;
+        const float4 x0 = x[i0], y0 = y[i0], d0 = dy[i0], x1 = x[i1], y1 = y[i1], d1 = dy[i1];
+        dy[i0] = one(x0, y0, d0);
+        dy[i1] = one(x1, y1, d1);
+      }
+      if (r < r1) { const long i0 = r * C4 + c; dy[i0] = one(x[i0], y[i0], dy[i0]); }
+    }
+    S[tid] = s; Q[tid] = q;
+    __syncthreads();
+    if (tid < cols && cb + tid < C4) {
+      double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+      for (int l = 0; l < rowLanes; l++) {
+        const float4 sv = S[l * cols + tid], qv = Q[l * cols + tid];
+        a[0] += sv.x; a[1] += sv.y; a[2] += sv.z; a[3] += sv.w;
+        b[0] += qv.x; b[1] += qv.y; b[2] += qv.z; b[3] += qv.w;
+      }
+      const int ch = (cb + tid) * 4, C = C4 * 4;
+#pragma unroll
+      for (int j = 0; j < 4; j++) { atomicAdd(stats + ch + j, a[j]); atomicAdd(stats + C + ch + j, b[j]); }
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) k_bn_bwd_apply4(const float4 *__restrict__ x, const float4 *__restrict__ d, float4 *__restrict__ dx, long total4, int C4,
+                                                       const float *__restrict__ saveMean, const float *__restrict__ saveInvStd,
+                                                       const float *__restrict__ weight, const float *__restrict__ gradMean, const float *__restrict__ kk) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    const float4 m = __ldg(reinterpret_cast<const float4 *>(saveMean) + c), is = __ldg(reinterpret_cast<const float4 *>(saveInvStd) + c);
+    const float4 gm = __ldg(reinterpret_cast<const float4 *>(gradMean) + c), k4 = __ldg(reinterpret_cast<const float4 *>(kk) + c);
+    const float4 w = weight ? __ldg(reinterpret_cast<const float4 *>(weight) + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 xv = x[i], dv = d[i];
+    float4 o;
+    o.x = (dv.x - gm.x - (xv.x - m.x) * k4.x) * is.x * w.x;
+    o.y = (dv.y - gm.y - (xv.y - m.y) * k4.y) * is.y * w.y;
+    o.z = (dv.z - gm.z - (xv.z - m.z) * k4.z) * is.z * w.z;
+    o.w = (dv.w - gm.w - (xv.w - m.w) * k4.w) * is.w * w.w;
+    dx[i] = o;
+  }
+}
 int bn_backward(const float *x, float *dx, const float *y, float *dy, long n, int C, const float *saveMean, const float *saveInvStd,
                 const float *weight, float *dWeight, float *dBias, float leak, void *workspace, cudaStream_t s) {
   double *stats = static_cast<double *>(workspace);
   float *gradMean = reinterpret_cast<float *>(stats + 2 * C), *kk = gradMean + C;
   SCN_CUDA(cudaMemsetAsync(stats, 0, 2 * C * sizeof(double), s));
+  const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+                                  reinterpret_cast<uintptr_t>(saveMean) | reinterpret_cast<uintptr_t>(saveInvStd) | reinterpret_cast<uintptr_t>(weight)) & 15) == 0;
   if (n) {
     int rowsPerCta = (int)std::max<long>(64, (n + kSMs * 16 - 1) / (kSMs * 16));
-    k_bn_bwd_stats<<<cdiv(n, rowsPerCta), 256, 0, LS(s)>>>(x, y, dy, n, C, rowsPerCta, saveMean, leak, stats);
+    if (vec) k_bn_bwd_stats4<<<cdiv(n, rowsPerCta), 256, 0, LS(s)>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(y), reinterpret_cast<float4 *>(dy),
+                                                                     n, C / 4, rowsPerCta, saveMean, leak, stats);
+    else k_bn_bwd_stats<<<cdiv(n, rowsPerCta), 256, 0, LS(s)>>>(x, y, dy, n, C, rowsPerCta, saveMean, leak, stats);
   }
   k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, LS(s)>>>(stats, n, C, saveInvStd, dWeight, dBias, gradMean, kk);
-  if (n) k_bn_bwd_apply<<<stream_grid(n * C, 256), 256, 0, LS(s)>>>(x, dy, dx, n * C, C, saveMean, saveInvStd, weight, gradMean, kk);
+  if (n && vec) k_bn_bwd_apply4<<<stream_grid(n * C / 4, 256), 256, 0, LS(s)>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(dy), reinterpret_cast<float4 *>(dx),
+                                                                                n * C / 4, C / 4, saveMean, saveInvStd, weight, gradMean, kk);
+  else if (n) k_bn_bwd_apply<<<stream_grid(n * C, 256), 256, 0, LS(s)>>>(x, dy, dx, n * C, C, saveMean, saveInvStd, weight, gradMean, kk);
   SCN_CUDA(cudaGetLastError());
   return 0;
 }
