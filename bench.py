@@ -26,7 +26,7 @@ WORKLOAD = ("sw_4c_fpn432 backbone forward incl. Metadata/rulebook build, one B4
             "per GPU per step")  # the same string in both arms (the reference arm's per-step sample is stated in cpu_baseline.sample)
 # end-to-end tolerance of each math mode against the reference's fp32 outputs (max |got - ref| / max(1, max|ref|) per returned
 # map; the same numbers tests/test_gpu_pins.py states): exact fp32 / tf32 operands / bf16 operands
-PARITY_TOL = {"fp32": 2e-3, "tf32": 3e-2, "bf16": 6e-2}
+PARITY_TOL = {"fp32": 2e-4, "tf32": 1e-2, "bf16": 4.5e-2}  # measured on B470: 3.8e-6 / 4.0e-3 / 2.5-2.8e-2
 B470_VOXELS = 1155656
 B470_GMAC = 334.126  # reference's own forward_pass_multiplyAdd_count for B470
 # dominant kernel: m_mergeds.7 = SubmanifoldConvolution 128->128, 3^3, on level 0 (10,715,792 rules)
@@ -593,8 +593,8 @@ def main():
         "metric": "backbone_buildings_per_s", "value": value, "unit": "buildings/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[math], "data": "synthetic",
-        "numerics": {"fp32": "exact fp32 CUDA cores", "tf32": "tf32 operands, fp32 accumulate; end-to-end <= 3e-2 of max|ref| (tests)",
-                     "bf16": "bf16 operands, fp32 accumulate, fp32 feature tensors at the API; end-to-end <= 6e-2 of max|ref| (tests + `parity` of this run)"}[math],
+        "numerics": {"fp32": "exact fp32 CUDA cores", "tf32": "tf32 operands, fp32 accumulate; end-to-end <= 1e-2 of max|ref| (tests)",
+                     "bf16": "bf16 operands, fp32 accumulate, fp32 feature tensors at the API; end-to-end <= 4.5e-2 of max|ref| (tests + `parity` of this run)"}[math],
         "config": config_of(world), "sustained": sustained,
         "streaming": None if stream_ms is None else {
             "ms_per_step": stream_ms / args.steps, "value": world * 1e3 / (stream_ms / args.steps), "unit": "buildings/s",

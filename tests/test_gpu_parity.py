@@ -357,7 +357,7 @@ TF32_RTOL, TF32_ATOL = 4e-3, 2e-3
 # narrower than 64 channels keep TF32 operands.  Per-layer bound = 4x the TF32 one.
 BF16_RTOL, BF16_ATOL = 1.6e-2, 8e-3
 TC_TOL = {"tf32": (TF32_RTOL, TF32_ATOL), "bf16": (BF16_RTOL, BF16_ATOL)}
-TC_E2E = {"tf32": 3e-2, "bf16": 6e-2}
+TC_E2E = {"tf32": 1e-2, "bf16": 4.5e-2}
 
 
 def _tc_or_skip(scn):
@@ -551,8 +551,8 @@ def test_tc_large_level_many_supertiles(math):
 ])
 @pytest.mark.parametrize("math", ["tf32", "bf16"])
 def test_fpn_forward_tensor_core_vs_reference_golden(name, cfgname, bld, math):
-    """End-to-end tensor-core backbone vs the reference's fp32 outputs.  Stated tolerance: 3e-2 (TF32)
-    / 6e-2 (BF16) of the largest magnitude of each returned map (operand rounding through ~40 layers;
+    """End-to-end tensor-core backbone vs the reference's fp32 outputs.  Stated tolerance: 1e-2 (TF32)
+    / 4.5e-2 (BF16) of the largest magnitude of each returned map (operand rounding through ~40 layers;
     instance norm on as few as 4 rows at the top levels amplifies relative differences).  Measured on
     B200: TF32 <= 5.2e-3, BF16 <= 2.3e-2 (tools/mode_error.py)."""
     import detection_3d_b200.sparseconvnet as scn
