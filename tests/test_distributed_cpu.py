@@ -127,3 +127,37 @@ def test_single_process_paths_need_no_process_group():
     p = torch.nn.Parameter(torch.zeros(3))
     p.grad = torch.ones(3)
     assert D.allreduce_gradients([p]) == 0 and torch.equal(p.grad, torch.ones(3))
+
+
+def test_gradient_reducer_attach_is_a_no_op_without_a_recorded_program():
+    """GradientReducer.attach(net) before the first training step (no recorded program) or on CPU tensors returns False and leaves the
+    hook-driven path in charge."""
+    import torch
+    from detection_3d_b200 import distributed
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(4, 3))
+
+    net = Net()
+    red = distributed.GradientReducer(list(net.parameters()))
+    assert red.attach(net) is False
+    red.zero()
+    (net.w * 2).sum().backward()
+    assert red.finish() == 0
+    assert torch.equal(net.w.grad, torch.full((4, 3), 2.0)) and net.w.grad.data_ptr() == red.flat.data_ptr()
+
+
+def test_truncate_lazy_cuts_padded_proposal_lists_with_one_read():
+    """postproc.truncate_lazy: the padded keep lists of several class groups are cut to their device-side counts (host logic, CPU tensors)."""
+    import torch
+    from detection_3d_b200 import postproc
+    a = postproc.Boxes3D(torch.arange(35, dtype=torch.float32).view(5, 7))
+    a.add_field("objectness", torch.arange(5, dtype=torch.float32))
+    b = postproc.Boxes3D(torch.arange(21, dtype=torch.float32).view(3, 7))
+    b.add_field("objectness", torch.arange(3, dtype=torch.float32))
+    out = postproc.truncate_lazy([(a, torch.tensor([2])), (b, torch.tensor([3]))])
+    assert len(out[0]) == 2 and torch.equal(out[0].bbox3d, a.bbox3d[:2]) and torch.equal(out[0].get_field("objectness"), torch.tensor([0.0, 1.0]))
+    assert len(out[1]) == 3 and out[1] is b
+    assert postproc.truncate_lazy([]) == []
