@@ -54,7 +54,7 @@ int launch_conv_list_simt(const float *in, float *out, const float *W, const int
 int bn_forward(const float *x, float *y, long n, int C, float *saveMean, float *saveInvStd, float *runningMean, float *runningVar,
                const float *weight, const float *bias, float eps, float momentum, int mode, float leak, void *workspace, cudaStream_t s, void *y16);
 int bn_backward(const float *x, float *dx, const float *y, float *dy, long n, int C, const float *saveMean, const float *saveInvStd,
-                const float *weight, float *dWeight, float *dBias, float leak, void *workspace, cudaStream_t s);
+                const float *weight, float *dWeight, float *dBias, float leak, void *workspace, cudaStream_t s, const void *y16 = nullptr);
 int input_forward(const float *in, float *out, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
 int input_forward_pad16(const float *in, float *out, void *out16, int nOut, int maxActive, int C, int Cp, const int *tab, int average, cudaStream_t s);
 int input_backward(float *din, const float *dout, long nIn, int nOut, int maxActive, int C, const int *tab, int average, cudaStream_t s);
@@ -875,14 +875,22 @@ int scn_batchnorm_forward(const float *in, float *out, long n, int C, float *sav
   }
   return scn::bn_forward(in, out, n, C, save_mean, save_invstd, running_mean, running_var, weight, bias, eps, momentum, mode, leak, ws, s, out_bf16);
 }
-int scn_batchnorm_backward(const float *in, float *d_in, const float *out, float *d_out, long n, int C, const float *save_mean,
-                           const float *save_invstd, const float *weight, float *d_weight, float *d_bias, float leak, void *stream) {
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+extern "C++" {
+namespace scn {
+// (out may be NULL when out_bf16 is given: only the sign of the output is read)
+int batchnorm_backward_y16(const float *in, float *d_in, const float *out, const void *out_bf16, float *d_out, long n, int C, const float *save_mean,
+                           const float *save_invstd, const float *weight, float *d_weight, float *d_bias, float leak, cudaStream_t s) {
   void *ws = nullptr;
   SCN_CUDA(cudaMallocAsync(&ws, (size_t)C * 24 + 64, s));
-  int r = scn::bn_backward(in, d_in, out, d_out, n, C, save_mean, save_invstd, weight, d_weight, d_bias, leak, ws, s);
+  int r = bn_backward(in, d_in, out, d_out, n, C, save_mean, save_invstd, weight, d_weight, d_bias, leak, ws, s, out_bf16);
   cudaFreeAsync(ws, s);
   return r;
+}
+} // namespace scn
+} // extern "C++"
+int scn_batchnorm_backward(const float *in, float *d_in, const float *out, float *d_out, long n, int C, const float *save_mean,
+                           const float *save_invstd, const float *weight, float *d_weight, float *d_bias, float leak, void *stream) {
+  return scn::batchnorm_backward_y16(in, d_in, out, nullptr, d_out, n, C, save_mean, save_invstd, weight, d_weight, d_bias, leak, static_cast<cudaStream_t>(stream));
 }
 int scn_add_features(const float *a, const float *b, float *out, long n, void *stream, void *out_bf16) {
   return scn::add_rows(a, b, out, n, static_cast<cudaStream_t>(stream), out_bf16);

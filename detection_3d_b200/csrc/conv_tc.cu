@@ -1505,6 +1505,24 @@ __global__ void __launch_bounds__(32 * (6 + kDwProd), 1) conv_dw_plan_tc(const D
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"(512u) : "memory");
   }
 }
+// whether launch_conv_dw_tc takes this shape at all (else the caller falls back to the CUDA-core kernel, which needs the fp32 rows)
+bool dw_tc_ok(int Cin, int Cout, int K, int mathMode) {
+  if (mathMode != 2 || !tc_available()) return false;
+  return !((Cin % 32 != 0 && Cin > 32) || Cin > 256 || (Cin > 128 && Cin % 128 != 0) || Cout % 32 != 0 || Cout > 256 || ((Cin + 127) / 128) * Cout > 512 || K > 64);
+}
+__global__ void __launch_bounds__(256) k_from_bf16(const uint2 *__restrict__ x, float4 *__restrict__ y, long n4) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const uint2 v = x[i];
+    y[i] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+  }
+}
+// bf16 rows -> fp32 rows (exact); n a multiple of 4
+int from_bf16(const void *x, float *y, long n, cudaStream_t s) {
+  SCN_CHECK(n % 4 == 0, "bf16 -> fp32 copy needs an element count that is a multiple of 4");
+  if (n) k_from_bf16<<<stream_grid(n / 4, 256), 256, 0, LS(s)>>>(static_cast<const uint2 *>(x), reinterpret_cast<float4 *>(y), n / 4);
+  SCN_CUDA(cudaGetLastError());
+  return 0;
+}
 // whether launch_conv_dw_tc would run the plan-driven kernel for this shape (the caller then does not need the rule lists)
 bool dw_plan_ok(int Cin, int Cout, int K, int mathMode) {
   static int planOn = -1;

@@ -19,6 +19,10 @@ void lateral_arm(const float *in, const void *in16, const float *w, long long ta
 bool lateral_take();
 void prepadded_arm(const void *rows16, int Cp);
 void bwd_in16_arm(const void *in16);
+bool dw_tc_ok(int Cin, int Cout, int K, int mathMode);
+int from_bf16(const void *x, float *y, long n, cudaStream_t s);
+int batchnorm_backward_y16(const float *in, float *d_in, const float *out, const void *out_bf16, float *d_out, long n, int C, const float *save_mean,
+                           const float *save_invstd, const float *weight, float *d_weight, float *d_bias, float leak, cudaStream_t s);
 void prepadded_disarm();
 int build_subm_on_caller(scn_metadata *m, const long *sz, const long *f);
 int bn_forward_from_sums(const float *x, float *y, long n, int C, const double *sums, float *saveMean, float *saveInvStd, float *runningMean,
@@ -548,7 +552,11 @@ int scn_program_run(scn_program *p, scn_metadata *m, const long *coords, int coo
       case K_BN: { // in, out, C, weight, bias, running mean, running var, mode; f: eps, momentum, leakiness
         const Reg &I = p->regs[a[0]];
         const bool fromSums = a[21] >= 0 && p->statsDone[a[21]] && I.rows > 0;
-        const bool halfOnly = !train && fromSums && a[19] == 1 && mode == 2 && scn_tensor_core_path_available();
+        // (training too: the backward pass reads the leaky-ReLU mask from the bf16 copy, and the consuming convolutions' weight-gradient
+        // kernels gather from it)
+        static int trainHalf = -1;
+        if (trainHalf < 0) trainHalf = getenv("SCN_TRAIN_HALF_BN") ? atoi(getenv("SCN_TRAIN_HALF_BN")) : 1;
+        const bool halfOnly = (!train || trainHalf) && fromSums && a[19] == 1 && mode == 2 && scn_tensor_core_path_available();
         rc = alloc_reg(a[1], I.rows, (int)a[2], true, halfOnly);
         float *saveM = p->bnScratch, *saveI = p->bnScratch + scn::kBnMaxC;
         if (rc == 0 && train) { // kept for the backward pass
@@ -677,11 +685,11 @@ int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const f
       case K_BN: {
         const Reg &X = p->regs[a[0]], &Y = p->regs[a[1]];
         if (X.rows == 0) break;
-        SCN_CHECK(X.p && Y.p && p->bnSave[i], "program backward: BatchNorm activations were not kept");
+        SCN_CHECK(X.p && (Y.p || Y.p16) && p->bnSave[i], "program backward: BatchNorm activations were not kept");
         float *dx = static_cast<float *>(slot_get(p, (size_t)elems(a[0]) * 4));
         if (!dx) { rc = -1; break; }
         if ((rc = mark(a[3])) || (rc = mark(a[4]))) break;
-        rc = scn_batchnorm_backward(X.p, dx, Y.p, dy, X.rows, (int)a[2], p->bnSave[i], p->bnSave[i] + a[2], P(a[3]), G(a[3]), G(a[4]), (float)op.f[2], s);
+        rc = scn::batchnorm_backward_y16(X.p, dx, Y.p, Y.p ? nullptr : Y.p16, dy, X.rows, (int)a[2], p->bnSave[i], p->bnSave[i] + a[2], P(a[3]), G(a[3]), G(a[4]), (float)op.f[2], s);
         done(a[3]); done(a[4]);
         if (rc == 0) rc = contribute(a[0], dx, true);
         break;
@@ -706,7 +714,7 @@ int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const f
           }
         }
         if (I.rows == 0 || p->regs[outReg].rows == 0) break;
-        SCN_CHECK(I.p, "program backward: convolution input was not kept");
+        SCN_CHECK(I.p || (I.p16 && !I.pad16 && Cin % 32 == 0 && scn_get_math_mode() == 2), "program backward: convolution input was not kept");
         if ((rc = mark(wi)) || (rc = mark(bi))) break;
         // the gradient of the network input is only computed on request (App. D.13)
         bool inputIsNetworkInput = false;
@@ -726,10 +734,23 @@ int scn_program_backward(scn_program *p, int n_out, const int *out_regs, const f
         // bf16 mode: the forward pass left a bf16 copy of the input rows (same layout: whole rows, no padding) -- the
         // weight-gradient kernel gathers from it instead of converting the fp32 rows again
         if (I.p16 && !I.pad16 && Cin % 32 == 0 && scn_get_math_mode() == 2) scn::bwd_in16_arm(I.p16);
-        if (op.kind == K_SUBM) rc = scn_submanifold_convolution_backward(m, a + 2, a + 5, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
-        else if (op.kind == K_CONV) rc = scn_convolution_backward(m, a + 2, a + 5, a + 8, a + 11, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
-        else rc = scn_deconvolution_backward(m, a + 2, a + 5, a + 8, a + 11, I.p, din, dy, P(wi), dw, G(bi), Cin, Cout);
+        const float *inRows = I.p;
+        float *inTmp = nullptr;
+        if (!inRows) { // the forward pass kept only the bf16 copy of these rows (a BatchNorm output read by tensor-core convolutions alone)
+          long Kv = 1;
+          for (int d = 0; d < 3; d++) Kv *= op.kind == K_SUBM ? a[5 + d] : a[8 + d];
+          if (!scn::dw_tc_ok(Cin, Cout, (int)Kv, scn_get_math_mode())) { // the CUDA-core weight-gradient kernel reads fp32 rows: widen the copy (exact)
+            inTmp = static_cast<float *>(slot_get(p, (size_t)elems(a[0]) * 4));
+            if (!inTmp) { rc = -1; break; }
+            if ((rc = scn::from_bf16(I.p16, inTmp, elems(a[0]), s))) break;
+            inRows = inTmp;
+          }
+        }
+        if (op.kind == K_SUBM) rc = scn_submanifold_convolution_backward(m, a + 2, a + 5, inRows, din, dy, P(wi), dw, G(bi), Cin, Cout);
+        else if (op.kind == K_CONV) rc = scn_convolution_backward(m, a + 2, a + 5, a + 8, a + 11, inRows, din, dy, P(wi), dw, G(bi), Cin, Cout);
+        else rc = scn_deconvolution_backward(m, a + 2, a + 5, a + 8, a + 11, inRows, din, dy, P(wi), dw, G(bi), Cin, Cout);
         if (dwTmp) slot_put(p, dwTmp);
+        if (inTmp) slot_put(p, inTmp);
         done(wi); done(bi);
         if (rc == 0 && din) rc = contribute(a[0], din, true);
         break;

@@ -384,7 +384,14 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float *__restrict__ 
 }
 // float4 versions (C % 4 == 0): four channels per thread, two rows in flight -- the scalar kernels above ran at well under half of
 // the HBM rate (one 4-byte access in flight per thread, an integer modulo per element in the apply pass).
-__global__ void __launch_bounds__(256) k_bn_bwd_stats4(const float4 *__restrict__ x, const float4 *__restrict__ y, float4 *__restrict__ dy, long n, int C4,
+// y16 (optional): the BatchNorm output as bf16 rows -- only its sign is needed (the leaky-ReLU mask), and a replayed training step in
+// bf16 mode never writes the fp32 output rows of a BatchNorm whose only readers are tensor-core convolutions.
+__device__ __forceinline__ float4 bn_y4(const float4 *y, const uint2 *y16, long i) {
+  if (!y16) return y[i];
+  const uint2 v = y16[i]; // bf16 = the upper half of the fp32 pattern: the sign survives a plain shift
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+}
+__global__ void __launch_bounds__(256) k_bn_bwd_stats4(const float4 *__restrict__ x, const float4 *__restrict__ y, const uint2 *__restrict__ y16, float4 *__restrict__ dy, long n, int C4,
                                                        int rowsPerCta, const float *__restrict__ saveMean, float leak, double *__restrict__ stats) {
   __shared__ float4 S[256], Q[256];
   const int tid = threadIdx.x;
@@ -404,11 +411,11 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats4(const float4 *__restrict_
       long r = r0 + rl;
       for (; r + rowLanes < r1; r += 2 * rowLanes) { // two rows in flight
         const long i0 = r * C4 + c, i1 = (r + rowLanes) * C4 + c;
-        const float4 x0 = x[i0], y0 = y[i0], d0 = dy[i0], x1 = x[i1], y1 = y[i1], d1 = dy[i1];
+        const float4 x0 = x[i0], y0 = bn_y4(y, y16, i0), d0 = dy[i0], x1 = x[i1], y1 = bn_y4(y, y16, i1), d1 = dy[i1];
         dy[i0] = one(x0, y0, d0);
         dy[i1] = one(x1, y1, d1);
       }
-      if (r < r1) { const long i0 = r * C4 + c; dy[i0] = one(x[i0], y[i0], dy[i0]); }
+      if (r < r1) { const long i0 = r * C4 + c; dy[i0] = one(x[i0], bn_y4(y, y16, i0), dy[i0]); }
     }
     S[tid] = s; Q[tid] = q;
     __syncthreads();
@@ -444,16 +451,18 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply4(const float4 *__restrict_
   }
 }
 int bn_backward(const float *x, float *dx, const float *y, float *dy, long n, int C, const float *saveMean, const float *saveInvStd,
-                const float *weight, float *dWeight, float *dBias, float leak, void *workspace, cudaStream_t s) {
+                const float *weight, float *dWeight, float *dBias, float leak, void *workspace, cudaStream_t s, const void *y16) {
   double *stats = static_cast<double *>(workspace);
   float *gradMean = reinterpret_cast<float *>(stats + 2 * C), *kk = gradMean + C;
   SCN_CUDA(cudaMemsetAsync(stats, 0, 2 * C * sizeof(double), s));
-  const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
+  SCN_CHECK(y || y16, "BatchNorm backward needs the output rows (fp32 or bf16)");
+  const bool vec = C % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(y16) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) |
                                   reinterpret_cast<uintptr_t>(saveMean) | reinterpret_cast<uintptr_t>(saveInvStd) | reinterpret_cast<uintptr_t>(weight)) & 15) == 0;
   if (n) {
     int rowsPerCta = (int)std::max<long>(64, (n + kSMs * 16 - 1) / (kSMs * 16));
-    if (vec) k_bn_bwd_stats4<<<cdiv(n, rowsPerCta), 256, 0, LS(s)>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(y), reinterpret_cast<float4 *>(dy),
-                                                                     n, C / 4, rowsPerCta, saveMean, leak, stats);
+    SCN_CHECK(vec || y, "BatchNorm backward: the bf16-only output path needs 16-byte aligned rows of a multiple of 4 channels");
+    if (vec) k_bn_bwd_stats4<<<cdiv(n, rowsPerCta), 256, 0, LS(s)>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<const float4 *>(y), y ? nullptr : static_cast<const uint2 *>(y16),
+                                                                     reinterpret_cast<float4 *>(dy), n, C / 4, rowsPerCta, saveMean, leak, stats);
     else k_bn_bwd_stats<<<cdiv(n, rowsPerCta), 256, 0, LS(s)>>>(x, y, dy, n, C, rowsPerCta, saveMean, leak, stats);
   }
   k_bn_bwd_finalize<<<cdiv(C, 128), 128, 0, LS(s)>>>(stats, n, C, saveInvStd, dWeight, dBias, gradMean, kk);
